@@ -1,0 +1,241 @@
+// psx_types.h — device command format shared by the host encoder and the CUDA kernels.
+//
+// PackedCmd is what the GP0 command encoder (encoder.cpp) writes into the pinned host
+// command buffer and what travels over PCIe: one fixed 64-byte record per primitive
+// (a quad becomes two triangle records, a polyline one record per segment), with every
+// piece of state the reference keeps in globals (drawing area, CLUT cache, mask bits)
+// resolved into the record so that records can be set up independently and in parallel.
+//
+// PrimSetup is the device-only result of the setup pre-pass (setup_kernel in kernels.cu):
+// everything the raster kernel needs, with all divisions done.  The closed forms it encodes
+// are derived in DESIGN.md §4 from the reference's DrawTriangle / DrawLine
+// (src/core/gpu_sw_rasterizer.inl:1417-1566, :814-892).
+#pragma once
+
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define PSX_HD __host__ __device__ __forceinline__
+#else
+#define PSX_HD inline
+#endif
+
+namespace psx {
+
+constexpr uint32_t VRAM_W = 1024, VRAM_H = 512, VRAM_PIXELS = VRAM_W * VRAM_H;
+constexpr uint32_t TILE_W = 64, TILE_H = 32;         // one CTA owns one tile (4 KiB of u16)
+constexpr uint32_t TILES_X = VRAM_W / TILE_W;        // 16
+constexpr uint32_t TILES_Y = VRAM_H / TILE_H;        // 16
+constexpr uint32_t NUM_TILES = TILES_X * TILES_Y;    // 256
+constexpr uint32_t STRIP_H = 4;                      // one warp owns a 64x4 strip of the tile
+constexpr uint32_t CLUT_ENTRIES = 256;
+
+enum PackedOp : uint8_t
+{
+  OP_TRIANGLE = 0,
+  OP_RECT = 1,
+  OP_LINE = 2,
+  OP_FILL = 3,
+  OP_COPY = 4,
+  OP_UPLOAD = 5,
+  OP_NOP = 6, // rejected by setup (degenerate triangle, culled sprite, over-long line)
+};
+
+// flags0 = the wire flag byte (include/psxgpu_wire.h PSX_DF_*), verbatim.
+enum : uint8_t
+{
+  F_INTERLACED = 0x01,
+  F_ACTIVE_LSB = 0x02,
+  F_SET_MASK = 0x04,
+  F_CHECK_MASK = 0x08,
+  F_TEXTURE = 0x10,
+  F_RAW = 0x20,
+  F_TRANSP = 0x40,
+  F_SHADED = 0x80,
+};
+enum : uint8_t
+{
+  F1_DITHER = 0x01,
+  F1_MOD5 = 0x02, // gpu_modulation_crop: Modulate5Bit instead of Modulate8Bit
+};
+
+// PrimSetup::tri.tflags
+enum : uint8_t
+{
+  TRI_SHORT_IS_RIGHT = 0x01, // the short edges are the right-hand boundary (reference: right_facing)
+  TRI_UPPER_UP = 0x02,       // rows [y0, y1) are walked upwards from v1 (reference: vo)
+  TRI_LOWER_UP = 0x04,       // rows [y1, y2) are walked upwards from v2 (reference: vp != 0)
+};
+
+struct PackedVertex
+{
+  int16_t x, y;
+  uint8_t r, g, b, u;
+  uint8_t v, pad;
+};
+static_assert(sizeof(PackedVertex) == 10, "PackedVertex");
+
+struct alignas(16) PackedCmd
+{
+  uint8_t op;
+  uint8_t flags0;
+  uint8_t flags1;
+  uint8_t reserved;
+  uint16_t draw_mode; // GPUDrawModeReg bits
+  uint8_t clut_lo;    // CLUT snapshot slot supplying palette entries 0..15
+  uint8_t clut_hi;    // slot supplying entries 16..255 (differs from clut_lo after a 4-bit load)
+  uint8_t win_and_x, win_and_y, win_or_x, win_or_y;
+  uint16_t clip_l, clip_t, clip_r, clip_b; // drawing area, inclusive, 0..1023
+  union
+  {
+    PackedVertex v[3]; // triangle; line uses v[0], v[1]
+    struct
+    {
+      int16_t x, y;
+      uint16_t w, h;
+      uint8_t r, g, b, u0;
+      uint8_t v0;
+    } rect;
+    struct
+    {
+      uint16_t x, y, w, h;
+      uint16_t color16;
+      uint8_t interlaced, active_lsb;
+    } fill;
+    struct
+    {
+      uint16_t sx, sy, dx, dy, w, h;
+    } copy;
+    struct
+    {
+      uint16_t x, y, w, h;
+      uint32_t payload; // offset into the payload buffer, in u16 units (global over the flush)
+    } upload;
+    uint8_t raw[44];
+  };
+};
+static_assert(sizeof(PackedCmd) == 64, "PackedCmd must be 64 bytes");
+
+// Epoch kinds (hazard/epoch splitter, encoder.cpp).
+enum EpochKind : uint32_t
+{
+  EPOCH_TILED = 0,        // binned per tile, tiles run in parallel
+  EPOCH_SELF_SAMPLING = 1, // one textured primitive whose texture footprint overlaps its own pixels
+  EPOCH_COPY_OVERLAP = 2,  // one CopyVRAM whose source and destination alias
+  EPOCH_UPLOAD_MASKED = 3, // one mask-checked CPU->VRAM upload
+};
+
+struct WaveItem
+{
+  uint32_t instance;
+  uint32_t cmd_begin, cmd_end; // global indices into the flush's command arrays
+  uint32_t kind;
+  uint32_t clut_begin, clut_end; // global indices into the flush's CLUT-op array
+  uint32_t pad[2];
+};
+static_assert(sizeof(WaveItem) == 32, "WaveItem");
+
+// CLUT snapshot: copy 16 (4-bit) or 256 (8-bit, x wraps at 1024) pixels of VRAM row y into a slot.
+struct ClutOp
+{
+  uint16_t dst_slot;
+  uint16_t x, y; // VRAM source
+  uint16_t is8bit;
+};
+static_assert(sizeof(ClutOp) == 8, "ClutOp");
+
+// ---- device-side setup record: 160 bytes, read by the raster kernel ----
+struct alignas(16) PrimSetup
+{
+  // 32-byte common header
+  uint8_t op, flags0, flags1, texmode; // texmode: 0 4-bit, 1 8-bit, 2 direct
+  uint16_t draw_mode;
+  uint8_t clut_lo, clut_hi;
+  uint8_t win_and_x, win_and_y, win_or_x, win_or_y;
+  int16_t clip_l, clip_t, clip_r, clip_b;
+  int16_t bx0, bx1;      // VRAM column range touched (inclusive), already clipped
+  uint16_t by0, bycount; // VRAM rows touched: (by0 + i) & 511, i < bycount
+  uint16_t tex_bx, tex_by; // texture page base
+
+  union
+  {
+    struct
+    {
+      // edges: x(cy) = start + (cy - anchor) * step   (mod 2^64), then >> 32
+      uint64_t long_start, long_step; // anchored at y0
+      uint64_t up_start, up_step;     // rows cy < y1
+      uint64_t lo_start, lo_step;     // rows cy >= y1
+      int16_t y0, y1;
+      int16_t up_anchor, lo_anchor;
+      int16_t up_lo, up_hi, lo_lo, lo_hi; // effective row ranges [lo, hi) after break emulation
+      uint32_t base[5], ddx[5], ddy[5];   // r g b u v : value(x,cy) = base + ddx*x + ddy*cy, top byte
+      uint8_t tflags;                     // TRI_SHORT_IS_RIGHT | TRI_UPPER_UP | TRI_LOWER_UP
+      uint8_t flat_r, flat_g, flat_b;
+    } tri; // 48 + 16 + 60 + 4 = 128
+    struct
+    {
+      int16_t x, y;
+      uint16_t w, h;
+      uint8_t r, g, b, u0, v0;
+    } rect;
+    struct
+    {
+      uint64_t curx0, cury0, dxdk, dydk;
+      uint32_t r0, g0, b0;
+      int32_t dr, dg, db;
+      int32_t k;
+      int16_t x0, y0; // p0 after the leftmost swap
+      uint8_t x_major, flat_r, flat_g, flat_b;
+    } line;
+    struct
+    {
+      uint16_t x, y, w, h;
+      uint16_t color16;
+      uint8_t interlaced, active_lsb;
+    } fill;
+    struct
+    {
+      uint16_t sx, sy, dx, dy, w, h;
+    } copy;
+    struct
+    {
+      uint16_t x, y, w, h;
+      uint32_t payload;
+    } upload;
+    uint32_t words[32];
+  };
+};
+static_assert(sizeof(PrimSetup) == 160, "PrimSetup must be 160 bytes");
+
+// Binning words produced by setup, read by every tile CTA of the epoch.
+struct BinInfo
+{
+  uint32_t tilemask; // bits 0-15: tile columns touched, bits 16-31: tile rows touched
+  uint32_t rows;     // by0 | bycount << 16
+};
+
+PSX_HD int32_t sext11(int32_t v)
+{
+  return static_cast<int32_t>(static_cast<uint32_t>(v) << 21) >> 21;
+}
+
+PSX_HD int32_t imin(int32_t a, int32_t b)
+{
+  return a < b ? a : b;
+}
+PSX_HD int32_t imax(int32_t a, int32_t b)
+{
+  return a > b ? a : b;
+}
+
+PSX_HD uint64_t mix64(uint64_t z)
+{
+  z ^= z >> 30;
+  z *= 0xBF58476D1CE4E5B9ull;
+  z ^= z >> 27;
+  z *= 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  return z;
+}
+
+} // namespace psx
