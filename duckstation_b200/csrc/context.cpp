@@ -1,0 +1,918 @@
+// context.cpp — the C ABI (include/psxgpu.h): device memory, the batched-instance scheduler and flush logic.
+//
+// One context = one CUDA device, one stream, N independent 1024x512 VRAM instances resident in HBM
+// (1 MiB each) plus a ring of CLUT snapshot slots per instance.  Commands are encoded per instance on the
+// host (encoder.cpp), packed into pinned staging buffers, copied once per flush and executed as "waves":
+// wave k runs epoch k of every instance that has one, as a single grid of (instance, tile) CTAs.
+#include "../../include/psxgpu.h"
+
+#include "encoder.h"
+#include "kernels.h"
+
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <unordered_map>
+#include <vector>
+
+using namespace psx;
+
+namespace {
+
+struct PinnedBuf
+{
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes)
+  {
+    if (bytes <= cap)
+      return cudaSuccess;
+    if (p)
+      cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+    const size_t want = bytes + bytes / 4 + 4096;
+    cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
+    if (e == cudaSuccess)
+      cap = want;
+    return e;
+  }
+  void release()
+  {
+    if (p)
+      cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+struct DevBuf
+{
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes)
+  {
+    if (bytes <= cap)
+      return cudaSuccess;
+    if (p)
+      cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    const size_t want = bytes + bytes / 4 + 4096;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess)
+      cap = want;
+    return e;
+  }
+  void release()
+  {
+    if (p)
+      cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+template<typename F>
+void parallel_for(uint32_t n, uint32_t threads, F&& fn)
+{
+  if (n == 0)
+    return;
+  threads = std::max(1u, std::min(threads, n));
+  if (threads == 1)
+  {
+    for (uint32_t i = 0; i < n; i++)
+      fn(i);
+    return;
+  }
+  std::vector<std::thread> pool;
+  pool.reserve(threads);
+  for (uint32_t t = 0; t < threads; t++)
+  {
+    pool.emplace_back([=, &fn]() {
+      const uint32_t lo = static_cast<uint32_t>((static_cast<uint64_t>(n) * t) / threads);
+      const uint32_t hi = static_cast<uint32_t>((static_cast<uint64_t>(n) * (t + 1)) / threads);
+      for (uint32_t i = lo; i < hi; i++)
+        fn(i);
+    });
+  }
+  for (auto& th : pool)
+    th.join();
+}
+
+double now_ms()
+{
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+} // namespace
+
+struct psxgpu_ctx
+{
+  int device = 0;
+  uint32_t n = 0;
+  psxgpu_opts opts{};
+  uint32_t clut_slots = 256;
+  uint32_t threads = 1;
+  cudaStream_t stream = nullptr;
+
+  uint16_t* d_vram = nullptr;
+  uint16_t* d_clut = nullptr;
+  unsigned long long* d_hash = nullptr;
+
+  std::vector<Encoder> enc;
+  std::vector<uint8_t> dirty;
+
+  PinnedBuf h_cmds, h_payload, h_clutops, h_items, h_misc;
+  DevBuf d_cmds, d_setups, d_bins, d_payload, d_clutops, d_items, d_scan;
+
+  struct Staged
+  {
+    bool valid = false;
+    uint32_t n_cmds = 0;
+    std::vector<uint32_t> wave_off; // wave k = items [wave_off[k], wave_off[k+1])
+    std::vector<uint8_t> wave_has_clut;
+  } staged;
+
+  std::unordered_map<uint32_t, std::vector<uint16_t>> shadow;
+  std::vector<uint8_t> display;
+  uint32_t disp_w = 0, disp_h = 0, disp_stride = 0, disp_rgba8 = 1;
+
+  cudaEvent_t ev_start = nullptr, ev_h2d = nullptr, ev_end = nullptr, ev_hash0 = nullptr, ev_hash1 = nullptr;
+  std::vector<cudaEvent_t> ev_raster; // pairs
+  uint32_t ev_raster_used = 0;
+  bool timing_pending = false;
+
+  psxgpu_stats counters{};
+  psxgpu_timing timing{};
+  std::vector<float> raster_ms;
+  double encode_ms_acc = 0;
+  std::string error;
+
+  int fail(cudaError_t e, const char* what)
+  {
+    char buf[256];
+    std::snprintf(buf, sizeof(buf), "%s: %s", what, cudaGetErrorString(e));
+    error = buf;
+    return PSXGPU_E_CUDA;
+  }
+  int invalid(const char* what)
+  {
+    error = what;
+    return PSXGPU_E_INVALID;
+  }
+};
+
+#define CK(expr, what)                                                                                                 \
+  do                                                                                                                   \
+  {                                                                                                                    \
+    cudaError_t e__ = (expr);                                                                                          \
+    if (e__ != cudaSuccess)                                                                                            \
+      return ctx->fail(e__, what);                                                                                     \
+  } while (0)
+
+namespace {
+
+uint16_t* inst_vram(psxgpu_ctx* ctx, uint32_t i)
+{
+  return ctx->d_vram + static_cast<size_t>(i) * VRAM_PIXELS;
+}
+uint16_t* inst_clut(psxgpu_ctx* ctx, uint32_t i, uint32_t slot)
+{
+  return ctx->d_clut + (static_cast<size_t>(i) * ctx->clut_slots + slot) * CLUT_ENTRIES;
+}
+
+int collect_timing(psxgpu_ctx* ctx)
+{
+  if (!ctx->timing_pending)
+    return PSXGPU_OK;
+  CK(cudaEventSynchronize(ctx->ev_end), "event sync");
+  float a = 0, b = 0;
+  cudaEventElapsedTime(&a, ctx->ev_start, ctx->ev_end);
+  cudaEventElapsedTime(&b, ctx->ev_h2d, ctx->ev_end);
+  ctx->timing.last_flush_device_ms = a;
+  ctx->timing.last_kernels_ms = b;
+  ctx->raster_ms.clear();
+  float sum = 0, mx = 0;
+  for (uint32_t i = 0; i < ctx->ev_raster_used; i += 2)
+  {
+    float t = 0;
+    cudaEventElapsedTime(&t, ctx->ev_raster[i], ctx->ev_raster[i + 1]);
+    ctx->raster_ms.push_back(t);
+    sum += t;
+    mx = std::max(mx, t);
+  }
+  ctx->timing.last_raster_ms = sum;
+  ctx->timing.last_raster_max_ms = mx;
+  ctx->timing.last_raster_launches = ctx->ev_raster_used / 2;
+  ctx->timing_pending = false;
+  return PSXGPU_OK;
+}
+
+// setup + all waves of the staged flush, on ctx->stream
+int run_device(psxgpu_ctx* ctx)
+{
+  auto& S = ctx->staged;
+  CK(cudaEventRecord(ctx->ev_h2d, ctx->stream), "event record");
+  CK(launch_setup(static_cast<const PackedCmd*>(ctx->d_cmds.p), static_cast<PrimSetup*>(ctx->d_setups.p),
+                  static_cast<BinInfo*>(ctx->d_bins.p), S.n_cmds, ctx->stream),
+     "setup_kernel");
+  if (S.n_cmds)
+    ctx->counters.kernel_launches++;
+  const uint32_t waves = static_cast<uint32_t>(S.wave_off.size()) - 1;
+  const bool prof = ctx->opts.profile != 0;
+  ctx->ev_raster_used = 0;
+  if (prof)
+  {
+    while (ctx->ev_raster.size() < static_cast<size_t>(waves) * 2)
+    {
+      cudaEvent_t e;
+      CK(cudaEventCreate(&e), "event create");
+      ctx->ev_raster.push_back(e);
+    }
+  }
+  const WaveItem* items = static_cast<const WaveItem*>(ctx->d_items.p);
+  for (uint32_t k = 0; k < waves; k++)
+  {
+    const uint32_t off = S.wave_off[k], cnt = S.wave_off[k + 1] - off;
+    if (cnt == 0)
+      continue;
+    if (S.wave_has_clut[k])
+    {
+      CK(launch_clut(items + off, cnt, static_cast<const ClutOp*>(ctx->d_clutops.p), ctx->d_vram, ctx->d_clut, ctx->clut_slots,
+                     ctx->stream),
+         "clut_kernel");
+      ctx->counters.kernel_launches++;
+    }
+    if (prof)
+      CK(cudaEventRecord(ctx->ev_raster[ctx->ev_raster_used++], ctx->stream), "event record");
+    CK(launch_raster(items + off, cnt, static_cast<const PrimSetup*>(ctx->d_setups.p), static_cast<const BinInfo*>(ctx->d_bins.p),
+                     ctx->d_vram, ctx->d_clut, static_cast<const uint16_t*>(ctx->d_payload.p), ctx->clut_slots, ctx->stream),
+       "raster_kernel");
+    ctx->counters.kernel_launches += (cnt + 32767) / 32768;
+    if (prof)
+      CK(cudaEventRecord(ctx->ev_raster[ctx->ev_raster_used++], ctx->stream), "event record");
+  }
+  CK(cudaEventRecord(ctx->ev_end, ctx->stream), "event record");
+  ctx->timing.last_waves = waves;
+  ctx->counters.waves += waves;
+  ctx->timing_pending = true;
+  return PSXGPU_OK;
+}
+
+int do_flush(psxgpu_ctx* ctx)
+{
+  std::vector<uint32_t> work;
+  for (uint32_t i = 0; i < ctx->n; i++)
+    if (ctx->dirty[i])
+      work.push_back(i);
+  if (work.empty())
+    return PSXGPU_OK;
+  int rc = collect_timing(ctx); // events are about to be reused
+  if (rc != PSXGPU_OK)
+    return rc;
+
+  const double t0 = now_ms();
+  const uint32_t nw = static_cast<uint32_t>(work.size());
+  parallel_for(nw, ctx->threads, [&](uint32_t w) { ctx->enc[work[w]].finish_flush(); });
+
+  std::vector<uint64_t> cmd_base(nw + 1, 0), pay_base(nw + 1, 0), clut_base(nw + 1, 0);
+  size_t max_epochs = 0, total_epochs = 0;
+  for (uint32_t w = 0; w < nw; w++)
+  {
+    const Encoder& e = ctx->enc[work[w]];
+    cmd_base[w + 1] = cmd_base[w] + e.cmds.size();
+    pay_base[w + 1] = pay_base[w] + e.payload.size();
+    clut_base[w + 1] = clut_base[w] + e.clut_ops.size();
+    max_epochs = std::max(max_epochs, e.epochs.size());
+    total_epochs += e.epochs.size();
+  }
+  const uint64_t n_cmds = cmd_base[nw], n_pay = pay_base[nw], n_clut = clut_base[nw];
+  if (n_cmds > 0xFFFFFFF0ull || n_pay > 0xFFFFFFF0ull)
+    return ctx->invalid("flush too large: more than 2^32 commands or payload pixels");
+
+  CK(ctx->h_cmds.ensure(n_cmds * sizeof(PackedCmd)), "pinned alloc (commands)");
+  CK(ctx->h_payload.ensure(n_pay * 2), "pinned alloc (payload)");
+  CK(ctx->h_clutops.ensure(n_clut * sizeof(ClutOp)), "pinned alloc (clut ops)");
+  CK(ctx->h_items.ensure(total_epochs * sizeof(WaveItem)), "pinned alloc (wave items)");
+  CK(ctx->d_cmds.ensure(n_cmds * sizeof(PackedCmd)), "device alloc (commands)");
+  CK(ctx->d_setups.ensure(n_cmds * sizeof(PrimSetup)), "device alloc (setup records)");
+  CK(ctx->d_bins.ensure(n_cmds * sizeof(BinInfo)), "device alloc (bins)");
+  CK(ctx->d_payload.ensure(n_pay * 2 + 16), "device alloc (payload)");
+  CK(ctx->d_clutops.ensure(n_clut * sizeof(ClutOp) + 16), "device alloc (clut ops)");
+  CK(ctx->d_items.ensure(total_epochs * sizeof(WaveItem) + 16), "device alloc (wave items)");
+
+  PackedCmd* hc = static_cast<PackedCmd*>(ctx->h_cmds.p);
+  uint16_t* hp = static_cast<uint16_t*>(ctx->h_payload.p);
+  ClutOp* ho = static_cast<ClutOp*>(ctx->h_clutops.p);
+  parallel_for(nw, ctx->threads, [&](uint32_t w) {
+    const Encoder& e = ctx->enc[work[w]];
+    if (!e.cmds.empty())
+      std::memcpy(hc + cmd_base[w], e.cmds.data(), e.cmds.size() * sizeof(PackedCmd));
+    for (uint32_t ui : e.upload_cmds)
+      hc[cmd_base[w] + ui].upload.payload += static_cast<uint32_t>(pay_base[w]);
+    if (!e.payload.empty())
+      std::memcpy(hp + pay_base[w], e.payload.data(), e.payload.size() * 2);
+    if (!e.clut_ops.empty())
+      std::memcpy(ho + clut_base[w], e.clut_ops.data(), e.clut_ops.size() * sizeof(ClutOp));
+  });
+
+  // waves: wave k = epoch k of every instance that has one
+  WaveItem* hi = static_cast<WaveItem*>(ctx->h_items.p);
+  auto& S = ctx->staged;
+  S.wave_off.assign(1, 0);
+  S.wave_has_clut.clear();
+  uint32_t n_items = 0;
+  for (size_t k = 0; k < max_epochs; k++)
+  {
+    uint8_t has_clut = 0;
+    for (uint32_t w = 0; w < nw; w++)
+    {
+      const Encoder& e = ctx->enc[work[w]];
+      if (e.epochs.size() <= k)
+        continue;
+      const Epoch& ep = e.epochs[k];
+      WaveItem it{};
+      it.instance = work[w];
+      it.cmd_begin = static_cast<uint32_t>(cmd_base[w] + ep.cmd_begin);
+      it.cmd_end = static_cast<uint32_t>(cmd_base[w] + ep.cmd_end);
+      it.kind = ep.kind;
+      it.clut_begin = static_cast<uint32_t>(clut_base[w] + ep.clut_begin);
+      it.clut_end = static_cast<uint32_t>(clut_base[w] + ep.clut_end);
+      has_clut |= (it.clut_end > it.clut_begin) ? 1 : 0;
+      hi[n_items++] = it;
+    }
+    S.wave_off.push_back(n_items);
+    S.wave_has_clut.push_back(has_clut);
+  }
+  S.n_cmds = static_cast<uint32_t>(n_cmds);
+  S.valid = true;
+  ctx->timing.last_stage_ms = static_cast<float>(now_ms() - t0);
+  ctx->timing.last_encode_ms = static_cast<float>(ctx->encode_ms_acc);
+  ctx->encode_ms_acc = 0;
+
+  CK(cudaEventRecord(ctx->ev_start, ctx->stream), "event record");
+  if (n_cmds)
+    CK(cudaMemcpyAsync(ctx->d_cmds.p, hc, n_cmds * sizeof(PackedCmd), cudaMemcpyHostToDevice, ctx->stream), "H2D commands");
+  if (n_pay)
+    CK(cudaMemcpyAsync(ctx->d_payload.p, hp, n_pay * 2, cudaMemcpyHostToDevice, ctx->stream), "H2D payload");
+  if (n_clut)
+    CK(cudaMemcpyAsync(ctx->d_clutops.p, ho, n_clut * sizeof(ClutOp), cudaMemcpyHostToDevice, ctx->stream), "H2D clut ops");
+  if (n_items)
+    CK(cudaMemcpyAsync(ctx->d_items.p, hi, n_items * sizeof(WaveItem), cudaMemcpyHostToDevice, ctx->stream), "H2D wave items");
+  ctx->counters.h2d_bytes += n_cmds * sizeof(PackedCmd) + n_pay * 2 + n_clut * sizeof(ClutOp) + n_items * sizeof(WaveItem);
+  ctx->counters.flushes++;
+
+  rc = run_device(ctx);
+  if (rc != PSXGPU_OK)
+    return rc;
+
+  // the pinned buffers are reused by the next flush: they must not be rewritten before the copies are done
+  CK(cudaEventSynchronize(ctx->ev_h2d), "H2D sync");
+  for (uint32_t w = 0; w < nw; w++)
+  {
+    ctx->enc[work[w]].begin_flush();
+    ctx->dirty[work[w]] = 0;
+  }
+  return PSXGPU_OK;
+}
+
+void scanout_params(const psxgpu_ctx* ctx, const psx_update_display* cmd, ScanoutParams& p, bool& disabled)
+{
+  // GPU_SW::UpdateDisplay, gpu_sw.cpp:391-448
+  std::memset(&p, 0, sizeof(p));
+  disabled = false;
+  if (ctx->opts.show_vram)
+  {
+    p.width = VRAM_W;
+    p.height = VRAM_H;
+    p.is24 = 0;
+  }
+  else
+  {
+    if (cmd->flags & PSX_UD_DISPLAY_DISABLED)
+    {
+      disabled = true;
+      return;
+    }
+    p.is24 = (cmd->flags & PSX_UD_DISPLAY_24BIT) ? 1 : 0;
+    const uint32_t inter = (cmd->flags & PSX_UD_INTERLACED_INTERLEAVED) ? 1u : 0u;
+    const uint32_t field = (cmd->flags & PSX_UD_INTERLACED_FIELD) ? 1u : 0u;
+    p.src_x = p.is24 ? cmd->X : cmd->display_vram_left;
+    p.skip_x = p.is24 ? static_cast<uint32_t>(cmd->display_vram_left - cmd->X) : 0;
+    p.src_y = cmd->display_vram_top + (field & inter);
+    p.width = cmd->display_vram_width;
+    p.height = cmd->display_vram_height;
+    p.line_skip = (cmd->flags & PSX_UD_INTERLACED_ENABLED) ? inter : 0;
+  }
+  if (p.is24)
+    p.fast = ((p.src_x + p.width) <= VRAM_W && (p.src_y + (p.height << p.line_skip)) <= VRAM_H) ? 1 : 0; // gpu_sw.cpp:305
+  else
+    p.fast = ((p.src_x + p.width) <= VRAM_W && (p.src_y + p.height) <= VRAM_H) ? 1 : 0; // gpu_sw.cpp:241
+  p.format = p.is24 ? 0 : ctx->opts.display_format;
+  const uint32_t bpp = (p.is24 || p.format == PSXGPU_FMT_RGBA8) ? 4 : 2;
+  p.out_stride = (p.width * bpp + 3u) & ~3u; // gpu_sw.cpp:236 / :301
+}
+
+int do_scanout(psxgpu_ctx* ctx, uint32_t instance, const psx_update_display* cmd, void* dst, uint32_t dst_stride, uint32_t* ow,
+               uint32_t* oh, uint32_t* obpp)
+{
+  ScanoutParams p;
+  bool disabled;
+  scanout_params(ctx, cmd, p, disabled);
+  if (disabled)
+    return 1;
+  if (p.width > 4096 || p.height > 4096)
+    return ctx->invalid("scan-out size out of range");
+  const uint32_t bpp = (p.is24 || p.format == PSXGPU_FMT_RGBA8) ? 4 : 2;
+  if (ow)
+    *ow = p.width;
+  if (oh)
+    *oh = p.height;
+  if (obpp)
+    *obpp = bpp;
+  if (p.width == 0 || p.height == 0)
+    return PSXGPU_OK;
+  if (dst_stride < p.width * bpp)
+    return ctx->invalid("scan-out destination stride too small");
+  int rc = do_flush(ctx);
+  if (rc != PSXGPU_OK)
+    return rc;
+  CK(ctx->d_scan.ensure(static_cast<size_t>(p.out_stride) * p.height), "device alloc (scan-out)");
+  CK(launch_scanout(inst_vram(ctx, instance), p, static_cast<uint8_t*>(ctx->d_scan.p), ctx->stream), "scanout_kernel");
+  ctx->counters.kernel_launches++;
+  CK(cudaMemcpy2DAsync(dst, dst_stride, ctx->d_scan.p, p.out_stride, static_cast<size_t>(p.width) * bpp, p.height,
+                       cudaMemcpyDeviceToHost, ctx->stream),
+     "D2H scan-out");
+  CK(cudaStreamSynchronize(ctx->stream), "stream sync");
+  ctx->counters.d2h_bytes += static_cast<uint64_t>(p.width) * bpp * p.height;
+  return PSXGPU_OK;
+}
+
+int do_read_vram(psxgpu_ctx* ctx, uint32_t instance, uint32_t x, uint32_t y, uint32_t w, uint32_t h, uint16_t* dst, uint32_t pitch)
+{
+  if (w == 0 || h == 0)
+    return PSXGPU_OK;
+  if (w > VRAM_W || h > VRAM_H || pitch < w)
+    return ctx->invalid("read_vram: rectangle larger than VRAM or pitch too small");
+  int rc = do_flush(ctx);
+  if (rc != PSXGPU_OK)
+    return rc;
+  x &= VRAM_W - 1;
+  y &= VRAM_H - 1;
+  // up to 2x2 pieces when the rectangle wraps (GPUREAD wraps, gpu.cpp:1896-1929)
+  const uint32_t w0 = std::min(w, VRAM_W - x), h0 = std::min(h, VRAM_H - y);
+  const uint32_t xs[2] = {x, 0}, ws[2] = {w0, w - w0}, ys[2] = {y, 0}, hs[2] = {h0, h - h0};
+  for (int j = 0; j < 2; j++)
+    for (int i = 0; i < 2; i++)
+    {
+      if (ws[i] == 0 || hs[j] == 0)
+        continue;
+      uint16_t* d = dst + static_cast<size_t>(j ? h0 : 0) * pitch + (i ? w0 : 0);
+      CK(cudaMemcpy2DAsync(d, static_cast<size_t>(pitch) * 2, inst_vram(ctx, instance) + ys[j] * VRAM_W + xs[i], VRAM_W * 2,
+                           static_cast<size_t>(ws[i]) * 2, hs[j], cudaMemcpyDeviceToHost, ctx->stream),
+         "D2H read_vram");
+    }
+  CK(cudaStreamSynchronize(ctx->stream), "stream sync");
+  ctx->counters.d2h_bytes += static_cast<uint64_t>(w) * h * 2;
+  return PSXGPU_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int psxgpu_abi_version(void)
+{
+  return PSXGPU_ABI_VERSION;
+}
+
+int psxgpu_create(int device, uint32_t n_instances, const psxgpu_opts* opts, psxgpu_ctx** out)
+{
+  if (!out || n_instances == 0)
+    return PSXGPU_E_INVALID;
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0 || device < 0 || device >= count)
+    return PSXGPU_E_CUDA; // no CPU fallback: the product path needs a CUDA device
+  psxgpu_ctx* ctx = new (std::nothrow) psxgpu_ctx();
+  if (!ctx)
+    return PSXGPU_E_NOMEM;
+  ctx->device = device;
+  ctx->n = n_instances;
+  if (opts)
+    std::memcpy(&ctx->opts, opts, std::min<size_t>(opts->struct_size ? opts->struct_size : sizeof(psxgpu_opts), sizeof(psxgpu_opts)));
+  ctx->clut_slots = ctx->opts.clut_slots ? std::min(256u, std::max(4u, ctx->opts.clut_slots)) : 256u;
+  ctx->threads = ctx->opts.encode_threads ? ctx->opts.encode_threads : std::max(1u, std::thread::hardware_concurrency());
+  if (ctx->opts.display_format > PSXGPU_FMT_RGB565)
+    ctx->opts.display_format = PSXGPU_FMT_RGBA8;
+
+  auto bail = [&](cudaError_t e, const char* what) {
+    std::fprintf(stderr, "psxgpu_create: %s: %s\n", what, cudaGetErrorString(e));
+    psxgpu_destroy(ctx);
+    return PSXGPU_E_CUDA;
+  };
+  cudaError_t e;
+  if ((e = cudaSetDevice(device)) != cudaSuccess)
+    return bail(e, "cudaSetDevice");
+  if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess)
+    return bail(e, "stream");
+  if ((e = cudaMalloc(&ctx->d_vram, static_cast<size_t>(n_instances) * VRAM_PIXELS * 2)) != cudaSuccess)
+    return bail(e, "VRAM pool");
+  if ((e = cudaMalloc(&ctx->d_clut, static_cast<size_t>(n_instances) * ctx->clut_slots * CLUT_ENTRIES * 2)) != cudaSuccess)
+    return bail(e, "CLUT pool");
+  if ((e = cudaMalloc(&ctx->d_hash, static_cast<size_t>(n_instances) * 8)) != cudaSuccess)
+    return bail(e, "hash buffer");
+  if ((e = cudaMemsetAsync(ctx->d_vram, 0, static_cast<size_t>(n_instances) * VRAM_PIXELS * 2, ctx->stream)) != cudaSuccess)
+    return bail(e, "VRAM clear");
+  if ((e = cudaMemsetAsync(ctx->d_clut, 0, static_cast<size_t>(n_instances) * ctx->clut_slots * CLUT_ENTRIES * 2, ctx->stream)) !=
+      cudaSuccess)
+    return bail(e, "CLUT clear");
+  for (cudaEvent_t* ev : {&ctx->ev_start, &ctx->ev_h2d, &ctx->ev_end, &ctx->ev_hash0, &ctx->ev_hash1})
+    if ((e = cudaEventCreate(ev)) != cudaSuccess)
+      return bail(e, "event");
+  if ((e = ctx->h_misc.ensure(std::max<size_t>(static_cast<size_t>(n_instances) * 8, 4096))) != cudaSuccess)
+    return bail(e, "pinned hash buffer");
+  if ((e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess)
+    return bail(e, "sync");
+
+  ctx->enc.reserve(n_instances);
+  for (uint32_t i = 0; i < n_instances; i++)
+  {
+    ctx->enc.emplace_back(ctx->clut_slots, ctx->opts.modulation_crop != 0);
+    ctx->enc.back().begin_flush();
+  }
+  ctx->dirty.assign(n_instances, 0);
+  ctx->staged.wave_off.assign(1, 0);
+  *out = ctx;
+  return PSXGPU_OK;
+}
+
+void psxgpu_destroy(psxgpu_ctx* ctx)
+{
+  if (!ctx)
+    return;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream)
+    cudaStreamSynchronize(ctx->stream);
+  for (PinnedBuf* b : {&ctx->h_cmds, &ctx->h_payload, &ctx->h_clutops, &ctx->h_items, &ctx->h_misc})
+    b->release();
+  for (DevBuf* b : {&ctx->d_cmds, &ctx->d_setups, &ctx->d_bins, &ctx->d_payload, &ctx->d_clutops, &ctx->d_items, &ctx->d_scan})
+    b->release();
+  if (ctx->d_vram)
+    cudaFree(ctx->d_vram);
+  if (ctx->d_clut)
+    cudaFree(ctx->d_clut);
+  if (ctx->d_hash)
+    cudaFree(ctx->d_hash);
+  for (cudaEvent_t ev : {ctx->ev_start, ctx->ev_h2d, ctx->ev_end, ctx->ev_hash0, ctx->ev_hash1})
+    if (ev)
+      cudaEventDestroy(ev);
+  for (cudaEvent_t ev : ctx->ev_raster)
+    cudaEventDestroy(ev);
+  if (ctx->stream)
+    cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char* psxgpu_last_error(const psxgpu_ctx* ctx)
+{
+  return ctx ? ctx->error.c_str() : "null context";
+}
+
+int psxgpu_flush(psxgpu_ctx* ctx)
+{
+  if (!ctx)
+    return PSXGPU_E_INVALID;
+  cudaSetDevice(ctx->device);
+  return do_flush(ctx);
+}
+
+int psxgpu_sync(psxgpu_ctx* ctx)
+{
+  if (!ctx)
+    return PSXGPU_E_INVALID;
+  cudaSetDevice(ctx->device);
+  CK(cudaStreamSynchronize(ctx->stream), "stream sync");
+  return collect_timing(ctx);
+}
+
+int psxgpu_run_staged(psxgpu_ctx* ctx)
+{
+  if (!ctx)
+    return PSXGPU_E_INVALID;
+  if (!ctx->staged.valid)
+    return ctx->invalid("run_staged: no flush is resident");
+  cudaSetDevice(ctx->device);
+  int rc = collect_timing(ctx);
+  if (rc != PSXGPU_OK)
+    return rc;
+  CK(cudaEventRecord(ctx->ev_start, ctx->stream), "event record");
+  return run_device(ctx);
+}
+
+int psxgpu_submit_wire(psxgpu_ctx* ctx, uint32_t instance, const void* wire, size_t bytes)
+{
+  if (!ctx || instance >= ctx->n || (!wire && bytes))
+    return ctx ? ctx->invalid("submit_wire: bad instance or buffer") : PSXGPU_E_INVALID;
+  cudaSetDevice(ctx->device);
+  const uint8_t* p = static_cast<const uint8_t*>(wire);
+  size_t off = 0;
+  while (off < bytes)
+  {
+    size_t used = 0;
+    const double t0 = now_ms();
+    const EncodeResult res = ctx->enc[instance].add_wire(p + off, bytes - off, &used);
+    ctx->encode_ms_acc += now_ms() - t0;
+    if (used)
+      ctx->dirty[instance] = 1;
+    off += used;
+    if (res == EncodeResult::Malformed)
+    {
+      ctx->error = "submit_wire: malformed record stream";
+      return PSXGPU_E_MALFORMED;
+    }
+    if (res != EncodeResult::Barrier)
+      continue;
+    const psx_cmd_header* h = reinterpret_cast<const psx_cmd_header*>(p + off);
+    int rc = PSXGPU_OK;
+    switch (h->type)
+    {
+      case PSX_CMD_CLEAR_VRAM: rc = psxgpu_clear_vram(ctx, instance); break;
+      case PSX_CMD_LOAD_STATE:
+      {
+        if (h->size < sizeof(psx_load_state))
+          return ctx->invalid("LoadState record too small");
+        const psx_load_state* ls = reinterpret_cast<const psx_load_state*>(h);
+        rc = psxgpu_load_state(ctx, instance, ls->vram_data, ls->clut_data);
+      }
+      break;
+      case PSX_CMD_READ_VRAM:
+      {
+        const psx_read_vram* rv = reinterpret_cast<const psx_read_vram*>(h);
+        uint16_t* sh = psxgpu_shadow_vram(ctx, instance);
+        // refresh the shadow rectangle in place (wrapping): row by row pieces handled by do_read_vram into a temp
+        std::vector<uint16_t> tmp(static_cast<size_t>(rv->width) * rv->height);
+        rc = do_read_vram(ctx, instance, rv->x, rv->y, rv->width, rv->height, tmp.data(), rv->width);
+        if (rc == PSXGPU_OK)
+          for (uint32_t r = 0; r < rv->height; r++)
+            for (uint32_t c = 0; c < rv->width; c++)
+              sh[((rv->y + r) & (VRAM_H - 1)) * VRAM_W + ((rv->x + c) & (VRAM_W - 1))] = tmp[static_cast<size_t>(r) * rv->width + c];
+      }
+      break;
+      case PSX_CMD_UPDATE_DISPLAY:
+      {
+        const psx_update_display* ud = reinterpret_cast<const psx_update_display*>(h);
+        ScanoutParams sp;
+        bool disabled;
+        scanout_params(ctx, ud, sp, disabled);
+        if (disabled)
+        {
+          ctx->disp_w = ctx->disp_h = 0;
+          rc = do_flush(ctx);
+          break;
+        }
+        const uint32_t bpp = (sp.is24 || sp.format == PSXGPU_FMT_RGBA8) ? 4 : 2;
+        ctx->display.resize(static_cast<size_t>(sp.out_stride) * sp.height);
+        uint32_t w = 0, hh = 0;
+        rc = do_scanout(ctx, instance, ud, ctx->display.data(), sp.out_stride, &w, &hh, nullptr);
+        ctx->disp_w = w;
+        ctx->disp_h = hh;
+        ctx->disp_stride = sp.out_stride;
+        ctx->disp_rgba8 = (bpp == 4);
+      }
+      break;
+      default: break;
+    }
+    if (rc < 0)
+      return rc;
+    off += h->size;
+  }
+  return PSXGPU_OK;
+}
+
+int psxgpu_submit_batch(psxgpu_ctx* ctx, uint32_t first, uint32_t count, const void* const* streams, const size_t* bytes)
+{
+  if (!ctx || !streams || !bytes || first + count > ctx->n || first + count < first)
+    return ctx ? ctx->invalid("submit_batch: bad arguments") : PSXGPU_E_INVALID;
+  const double t0 = now_ms();
+  std::vector<int> status(count, 0);
+  parallel_for(count, ctx->threads, [&](uint32_t i) {
+    size_t used = 0;
+    const EncodeResult res = ctx->enc[first + i].add_wire(streams[i], bytes[i], &used);
+    if (used)
+      ctx->dirty[first + i] = 1;
+    status[i] = (res == EncodeResult::Ok) ? 0 : (res == EncodeResult::Malformed ? PSXGPU_E_MALFORMED : PSXGPU_E_UNSUPPORTED);
+  });
+  ctx->encode_ms_acc += now_ms() - t0;
+  for (uint32_t i = 0; i < count; i++)
+    if (status[i] != 0)
+    {
+      ctx->error = (status[i] == PSXGPU_E_MALFORMED) ? "submit_batch: malformed record stream"
+                                                     : "submit_batch: read-back / state records are not allowed in a batch";
+      return status[i];
+    }
+  return PSXGPU_OK;
+}
+
+int psxgpu_read_vram(psxgpu_ctx* ctx, uint32_t instance, uint32_t x, uint32_t y, uint32_t w, uint32_t h, uint16_t* dst,
+                     uint32_t dst_pitch_px)
+{
+  if (!ctx || instance >= ctx->n || !dst)
+    return ctx ? ctx->invalid("read_vram: bad arguments") : PSXGPU_E_INVALID;
+  cudaSetDevice(ctx->device);
+  return do_read_vram(ctx, instance, x, y, w, h, dst, dst_pitch_px);
+}
+
+uint16_t* psxgpu_shadow_vram(psxgpu_ctx* ctx, uint32_t instance)
+{
+  if (!ctx || instance >= ctx->n)
+    return nullptr;
+  auto& v = ctx->shadow[instance];
+  if (v.empty())
+    v.assign(VRAM_PIXELS, 0);
+  return v.data();
+}
+
+int psxgpu_clear_vram(psxgpu_ctx* ctx, uint32_t instance)
+{
+  if (!ctx || instance >= ctx->n)
+    return ctx ? ctx->invalid("clear_vram: bad instance") : PSXGPU_E_INVALID;
+  cudaSetDevice(ctx->device);
+  int rc = do_flush(ctx);
+  if (rc != PSXGPU_OK)
+    return rc;
+  CK(cudaMemsetAsync(inst_vram(ctx, instance), 0, VRAM_PIXELS * 2, ctx->stream), "VRAM clear");
+  CK(cudaMemsetAsync(inst_clut(ctx, instance, 0), 0, CLUT_ENTRIES * 2, ctx->stream), "CLUT clear");
+  ctx->enc[instance].reset_clut_state();
+  return PSXGPU_OK;
+}
+
+int psxgpu_load_state(psxgpu_ctx* ctx, uint32_t instance, const uint16_t* vram, const uint16_t* clut)
+{
+  if (!ctx || instance >= ctx->n || !vram)
+    return ctx ? ctx->invalid("load_state: bad arguments") : PSXGPU_E_INVALID;
+  cudaSetDevice(ctx->device);
+  int rc = do_flush(ctx);
+  if (rc != PSXGPU_OK)
+    return rc;
+  CK(cudaMemcpyAsync(inst_vram(ctx, instance), vram, VRAM_PIXELS * 2, cudaMemcpyHostToDevice, ctx->stream), "H2D VRAM");
+  if (clut)
+    CK(cudaMemcpyAsync(inst_clut(ctx, instance, 0), clut, CLUT_ENTRIES * 2, cudaMemcpyHostToDevice, ctx->stream), "H2D CLUT");
+  else
+    CK(cudaMemsetAsync(inst_clut(ctx, instance, 0), 0, CLUT_ENTRIES * 2, ctx->stream), "CLUT clear");
+  CK(cudaStreamSynchronize(ctx->stream), "stream sync"); // caller's buffers may be reused on return
+  ctx->counters.h2d_bytes += VRAM_PIXELS * 2 + CLUT_ENTRIES * 2;
+  ctx->enc[instance].reset_clut_state();
+  return PSXGPU_OK;
+}
+
+int psxgpu_save_state(psxgpu_ctx* ctx, uint32_t instance, uint16_t* vram, uint16_t* clut)
+{
+  if (!ctx || instance >= ctx->n || !vram)
+    return ctx ? ctx->invalid("save_state: bad arguments") : PSXGPU_E_INVALID;
+  cudaSetDevice(ctx->device);
+  int rc = do_flush(ctx);
+  if (rc != PSXGPU_OK)
+    return rc;
+  CK(cudaMemcpyAsync(vram, inst_vram(ctx, instance), VRAM_PIXELS * 2, cudaMemcpyDeviceToHost, ctx->stream), "D2H VRAM");
+  if (clut)
+  {
+    const Encoder& e = ctx->enc[instance];
+    CK(cudaMemcpyAsync(clut, inst_clut(ctx, instance, e.clut_lo_slot()), 16 * 2, cudaMemcpyDeviceToHost, ctx->stream), "D2H CLUT");
+    CK(cudaMemcpyAsync(clut + 16, inst_clut(ctx, instance, e.clut_hi_slot()) + 16, 240 * 2, cudaMemcpyDeviceToHost, ctx->stream),
+       "D2H CLUT");
+  }
+  CK(cudaStreamSynchronize(ctx->stream), "stream sync");
+  ctx->counters.d2h_bytes += VRAM_PIXELS * 2 + CLUT_ENTRIES * 2;
+  return PSXGPU_OK;
+}
+
+int psxgpu_scanout(psxgpu_ctx* ctx, uint32_t instance, const psx_update_display* cmd, void* dst, uint32_t dst_stride,
+                   uint32_t* out_width, uint32_t* out_height)
+{
+  if (!ctx || instance >= ctx->n || !cmd || !dst)
+    return ctx ? ctx->invalid("scanout: bad arguments") : PSXGPU_E_INVALID;
+  cudaSetDevice(ctx->device);
+  return do_scanout(ctx, instance, cmd, dst, dst_stride, out_width, out_height, nullptr);
+}
+
+const void* psxgpu_display(psxgpu_ctx* ctx, uint32_t* width, uint32_t* height, uint32_t* stride, uint32_t* is_rgba8)
+{
+  if (!ctx)
+    return nullptr;
+  if (width)
+    *width = ctx->disp_w;
+  if (height)
+    *height = ctx->disp_h;
+  if (stride)
+    *stride = ctx->disp_stride;
+  if (is_rgba8)
+    *is_rgba8 = ctx->disp_rgba8;
+  return ctx->display.data();
+}
+
+static int hash_common(psxgpu_ctx* ctx, uint32_t first, uint32_t count)
+{
+  if (first + count > ctx->n || first + count < first)
+    return ctx->invalid("hash: bad instance range");
+  cudaSetDevice(ctx->device);
+  int rc = do_flush(ctx);
+  if (rc != PSXGPU_OK)
+    return rc;
+  CK(cudaEventRecord(ctx->ev_hash0, ctx->stream), "event record");
+  CK(launch_hash(ctx->d_vram, first, count, ctx->d_hash, ctx->stream), "hash_kernel");
+  CK(cudaEventRecord(ctx->ev_hash1, ctx->stream), "event record");
+  ctx->counters.kernel_launches += (count + 32767) / 32768;
+  return PSXGPU_OK;
+}
+
+int psxgpu_hash(psxgpu_ctx* ctx, uint32_t first, uint32_t count, uint64_t* out_host)
+{
+  if (!ctx || !out_host)
+    return ctx ? ctx->invalid("hash: bad arguments") : PSXGPU_E_INVALID;
+  int rc = hash_common(ctx, first, count);
+  if (rc != PSXGPU_OK)
+    return rc;
+  CK(cudaMemcpyAsync(ctx->h_misc.p, ctx->d_hash + first, static_cast<size_t>(count) * 8, cudaMemcpyDeviceToHost, ctx->stream),
+     "D2H hashes");
+  CK(cudaStreamSynchronize(ctx->stream), "stream sync");
+  std::memcpy(out_host, ctx->h_misc.p, static_cast<size_t>(count) * 8);
+  ctx->counters.d2h_bytes += static_cast<uint64_t>(count) * 8;
+  cudaEventElapsedTime(&ctx->timing.last_hash_ms, ctx->ev_hash0, ctx->ev_hash1);
+  return collect_timing(ctx);
+}
+
+int psxgpu_hash_device(psxgpu_ctx* ctx, uint32_t first, uint32_t count, void* out_device)
+{
+  if (!ctx || !out_device)
+    return ctx ? ctx->invalid("hash_device: bad arguments") : PSXGPU_E_INVALID;
+  int rc = hash_common(ctx, first, count);
+  if (rc != PSXGPU_OK)
+    return rc;
+  CK(cudaMemcpyAsync(out_device, ctx->d_hash + first, static_cast<size_t>(count) * 8, cudaMemcpyDeviceToDevice, ctx->stream),
+     "D2D hashes");
+  CK(cudaStreamSynchronize(ctx->stream), "stream sync");
+  cudaEventElapsedTime(&ctx->timing.last_hash_ms, ctx->ev_hash0, ctx->ev_hash1);
+  return collect_timing(ctx);
+}
+
+int psxgpu_get_stats(psxgpu_ctx* ctx, psxgpu_stats* out)
+{
+  if (!ctx || !out)
+    return PSXGPU_E_INVALID;
+  psxgpu_stats s = ctx->counters;
+  for (const Encoder& e : ctx->enc)
+  {
+    s.wire_commands += e.stats.wire_commands;
+    s.packed_prims += e.stats.packed_prims;
+    s.epochs += e.stats.epochs;
+    s.cuts_raw += e.stats.cuts_raw;
+    s.cuts_war += e.stats.cuts_war;
+    s.cuts_clut += e.stats.cuts_clut;
+    s.serial_self_sampling += e.stats.serial_self_sampling;
+    s.serial_copy += e.stats.serial_copy;
+    s.serial_upload += e.stats.serial_upload;
+    s.clut_ops += e.stats.clut_ops;
+    s.clut_cache_hits += e.stats.clut_cache_hits;
+    s.rejected += e.stats.rejected;
+  }
+  *out = s;
+  return PSXGPU_OK;
+}
+
+int psxgpu_reset_stats(psxgpu_ctx* ctx)
+{
+  if (!ctx)
+    return PSXGPU_E_INVALID;
+  ctx->counters = psxgpu_stats{};
+  for (Encoder& e : ctx->enc)
+    e.stats = EncoderStats{};
+  return PSXGPU_OK;
+}
+
+int psxgpu_get_timing(psxgpu_ctx* ctx, psxgpu_timing* out)
+{
+  if (!ctx || !out)
+    return PSXGPU_E_INVALID;
+  cudaSetDevice(ctx->device);
+  int rc = collect_timing(ctx);
+  *out = ctx->timing;
+  return rc;
+}
+
+int psxgpu_get_raster_launch_ms(psxgpu_ctx* ctx, float* out, uint32_t max_count)
+{
+  if (!ctx || !out)
+    return PSXGPU_E_INVALID;
+  collect_timing(ctx);
+  const uint32_t n = std::min<uint32_t>(max_count, static_cast<uint32_t>(ctx->raster_ms.size()));
+  for (uint32_t i = 0; i < n; i++)
+    out[i] = ctx->raster_ms[i];
+  return static_cast<int>(ctx->raster_ms.size());
+}
+
+} // extern "C"

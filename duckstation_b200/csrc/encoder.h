@@ -103,6 +103,8 @@ public:
   EncoderStats stats;
 
   void set_modulation_crop(bool on) { m_modulation_crop = on; }
+  uint32_t clut_lo_slot() const { return m_cur_lo; }
+  uint32_t clut_hi_slot() const { return m_cur_hi; }
 
 private:
   void handle_record(const uint8_t* rec);

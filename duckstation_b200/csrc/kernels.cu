@@ -1,0 +1,736 @@
+// kernels.cu — sm_100a kernels of the PSX rasteriser.
+//
+//   setup_kernel    one thread per primitive: PackedCmd -> PrimSetup + BinInfo (all divisions happen here)
+//   clut_kernel     CLUT snapshot pass of an epoch wave (reference: UpdateCLUT, gpu_sw_rasterizer.cpp:43-66)
+//   raster_kernel   one CTA per (instance, 64x32 VRAM tile): bins the epoch's primitives for its tile in
+//                   submission order (warp ballots), stages the tile in shared memory and lets each of its 8
+//                   warps walk the bin in order over its own 64x4 strip — one 32-bit word (2 pixels) per lane
+//                   per row — then writes the tile back with 128-bit stores.  Texels and CLUT entries come
+//                   from global memory through the read-only path (L1/L2 resident).
+//                   Epochs of a serial kind (self-sampling primitive, aliasing copy, mask-checked upload tail)
+//                   are executed by one CTA in the reference's own order.
+//   hash_kernel     vramhash64 per instance
+//   scanout_kernel  15-bit / 24-bit display read-out (reference: CopyOut15Bit / CopyOut24Bit, gpu_sw.cpp:230-356)
+//
+// Integer work only; bound by memory traffic and issue rate, so no tensor-core path.
+#include "kernels.h"
+#include "psx_pixel.h"
+#include "psx_setup.h"
+
+#include <cuda_runtime.h>
+
+namespace psx {
+
+// ------------------------------------------------------------------------------------------------ setup
+__global__ void __launch_bounds__(128) setup_kernel(const PackedCmd* __restrict__ cmds, PrimSetup* __restrict__ setups,
+                                                    BinInfo* __restrict__ bins, uint32_t n)
+{
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n)
+    return;
+  // 64-byte record as four 128-bit loads
+  PackedCmd c;
+  const uint4* src = reinterpret_cast<const uint4*>(cmds + i);
+  uint4* cdst = reinterpret_cast<uint4*>(&c);
+#pragma unroll
+  for (int k = 0; k < 4; k++)
+    cdst[k] = __ldg(src + k);
+  PrimSetup s;
+  uint4* sw = reinterpret_cast<uint4*>(&s);
+#pragma unroll
+  for (int k = 0; k < 10; k++)
+    sw[k] = make_uint4(0, 0, 0, 0);
+  BinInfo b;
+  setup_prim(c, s, b);
+  uint4* dst = reinterpret_cast<uint4*>(setups + i);
+#pragma unroll
+  for (int k = 0; k < 10; k++)
+    dst[k] = sw[k];
+  reinterpret_cast<uint2*>(bins)[i] = make_uint2(b.tilemask, b.rows);
+}
+
+// ------------------------------------------------------------------------------------------------ CLUT snapshots
+__global__ void __launch_bounds__(256) clut_kernel(const WaveItem* __restrict__ items, const ClutOp* __restrict__ ops,
+                                                   const uint16_t* __restrict__ vram_pool, uint16_t* __restrict__ clut_pool,
+                                                   uint32_t clut_slots)
+{
+  const WaveItem it = items[blockIdx.x];
+  const uint16_t* vram = vram_pool + static_cast<size_t>(it.instance) * VRAM_PIXELS;
+  uint16_t* cluts = clut_pool + static_cast<size_t>(it.instance) * clut_slots * CLUT_ENTRIES;
+  const uint32_t t = threadIdx.x;
+  for (uint32_t o = it.clut_begin; o < it.clut_end; o++)
+  {
+    const ClutOp op = ops[o];
+    if (op.is8bit || t < 16)
+      cluts[op.dst_slot * CLUT_ENTRIES + t] = vram[op.y * VRAM_W + ((op.x + t) & (VRAM_W - 1))];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ raster
+constexpr int RASTER_THREADS = 256;
+constexpr int RASTER_WARPS = RASTER_THREADS / 32;
+constexpr uint32_t LIST_CAP = 1024;
+constexpr uint32_t SETUP_WORDS = sizeof(PrimSetup) / 4; // 40
+
+struct alignas(16) RasterShared
+{
+  uint32_t tile[TILE_H][TILE_W / 2];           // 4 KiB: the VRAM tile, 2 pixels per word
+  uint32_t list[LIST_CAP];                     // bin: primitive index | strip mask << 16, submission order
+  uint32_t stage[RASTER_WARPS][SETUP_WORDS];   // per-warp copy of the primitive being rasterised
+  uint32_t warp_count[RASTER_WARPS];
+};
+
+__device__ __forceinline__ uint32_t strip_mask_for(uint32_t rows, uint32_t tile_y0)
+{
+  const uint32_t by0 = rows & 0xFFFFu, cnt = rows >> 16;
+  uint32_t m = 0;
+#pragma unroll
+  for (uint32_t s = 0; s < RASTER_WARPS; s++)
+  {
+    const uint32_t y = tile_y0 + STRIP_H * s;
+    const bool hit = (((y - by0) & (VRAM_H - 1)) < cnt) || (((by0 - y) & (VRAM_H - 1)) < STRIP_H);
+    m |= hit ? (1u << s) : 0u;
+  }
+  return m;
+}
+
+struct PixelCtx
+{
+  const uint16_t* vram; // this instance's VRAM in global memory (texture / copy source reads)
+  const uint16_t* clut_lo;
+  const uint16_t* clut_hi;
+};
+
+// One pixel through the pipeline.  bg = current value; returns the new value.
+__device__ __forceinline__ uint32_t shade_pixel(const PrimSetup& s, const PixelCtx& ctx, uint32_t px, uint32_t Y, uint32_t r,
+                                                uint32_t g, uint32_t b, uint32_t u, uint32_t v, uint32_t bg)
+{
+  uint16_t texel = 0;
+  if (s.flags0 & F_TEXTURE)
+    texel = fetch_texel<false>(s, ctx.vram, ctx.clut_lo, ctx.clut_hi, u, v);
+  uint16_t colour;
+  if (!shade_colour(s, px, Y, r, g, b, texel, colour))
+    return bg;
+  return blend_mask(s, static_cast<uint16_t>(bg), colour);
+}
+
+__device__ __forceinline__ uint32_t set_half(uint32_t word, uint32_t half, uint32_t value)
+{
+  return half ? ((word & 0x0000FFFFu) | (value << 16)) : ((word & 0xFFFF0000u) | (value & 0xFFFFu));
+}
+
+// A warp applies one primitive to its strip (rows strip_y0 .. strip_y0+3, columns tile_x0 .. tile_x0+63).
+__device__ __forceinline__ void raster_prim_on_strip(const PrimSetup& s, uint32_t* __restrict__ strip, uint32_t tile_x0,
+                                                     uint32_t strip_y0, const uint16_t* vram, const uint16_t* clut_pool_inst,
+                                                     const uint16_t* __restrict__ payload, uint32_t lane)
+{
+  PixelCtx ctx;
+  ctx.vram = vram;
+  ctx.clut_lo = clut_pool_inst + s.clut_lo * CLUT_ENTRIES;
+  ctx.clut_hi = clut_pool_inst + s.clut_hi * CLUT_ENTRIES;
+  const int32_t px0 = static_cast<int32_t>(tile_x0 + 2 * lane);
+
+  switch (s.op)
+  {
+    case OP_TRIANGLE:
+    {
+#pragma unroll 1
+      for (uint32_t r = 0; r < STRIP_H; r++)
+      {
+        const uint32_t Y = strip_y0 + r;
+        TriRow row;
+        if (!tri_row(s, Y, row))
+          continue;
+        const bool c0 = px0 >= row.x_lo && px0 < row.x_hi;
+        const bool c1 = (px0 + 1) >= row.x_lo && (px0 + 1) < row.x_hi;
+        if (!(c0 || c1))
+          continue;
+        uint32_t word = strip[r * 32 + lane];
+        uint32_t r0, g0, b0, u0, v0, r1, g1, b1, u1, v1;
+        tri_attrs(s, row, px0, r0, g0, b0, u0, v0);
+        tri_attrs(s, row, px0 + 1, r1, g1, b1, u1, v1);
+        uint32_t lo = word & 0xFFFFu, hi = word >> 16;
+        if (c0)
+          lo = shade_pixel(s, ctx, static_cast<uint32_t>(px0), Y, r0, g0, b0, u0, v0, lo);
+        if (c1)
+          hi = shade_pixel(s, ctx, static_cast<uint32_t>(px0 + 1), Y, r1, g1, b1, u1, v1, hi);
+        strip[r * 32 + lane] = lo | (hi << 16);
+      }
+    }
+    break;
+
+    case OP_RECT:
+    {
+#pragma unroll 1
+      for (uint32_t r = 0; r < STRIP_H; r++)
+      {
+        const uint32_t Y = strip_y0 + r;
+        RectRow row;
+        if (!rect_row(s, Y, row))
+          continue;
+        const bool c0 = px0 >= row.x_lo && px0 < row.x_hi;
+        const bool c1 = (px0 + 1) >= row.x_lo && (px0 + 1) < row.x_hi;
+        if (!(c0 || c1))
+          continue;
+        const uint32_t word = strip[r * 32 + lane];
+        uint32_t lo = word & 0xFFFFu, hi = word >> 16;
+        const uint32_t ub = s.rect.u0 + static_cast<uint32_t>(px0 - s.rect.x);
+        if (c0)
+          lo = shade_pixel(s, ctx, static_cast<uint32_t>(px0), Y, s.rect.r, s.rect.g, s.rect.b, ub & 0xFFu, row.v, lo);
+        if (c1)
+          hi = shade_pixel(s, ctx, static_cast<uint32_t>(px0 + 1), Y, s.rect.r, s.rect.g, s.rect.b, (ub + 1) & 0xFFu, row.v, hi);
+        strip[r * 32 + lane] = lo | (hi << 16);
+      }
+    }
+    break;
+
+    case OP_LINE:
+    {
+      if (s.line.x_major)
+      {
+        // at most one pixel per column; this lane owns columns px0 and px0+1
+#pragma unroll
+        for (int h = 0; h < 2; h++)
+        {
+          const int32_t px = px0 + h;
+          LinePixel p;
+          if (line_step(s, line_step_for_column(s, px), p) && p.x == px)
+          {
+            const uint32_t Y = static_cast<uint32_t>(p.y) & (VRAM_H - 1);
+            const uint32_t r = Y - strip_y0;
+            if (r < STRIP_H)
+            {
+              const uint32_t word = strip[r * 32 + lane];
+              const uint32_t bg = h ? (word >> 16) : (word & 0xFFFFu);
+              strip[r * 32 + lane] = set_half(word, h, shade_pixel(s, ctx, static_cast<uint32_t>(px), Y, p.r, p.g, p.b, 0, 0, bg));
+            }
+          }
+        }
+      }
+      else if (lane < STRIP_H)
+      {
+        // at most one pixel per row; lane r owns row r of the strip
+        const uint32_t Y = strip_y0 + lane;
+        LinePixel p;
+        if (line_step(s, line_step_for_row(s, Y), p) && (static_cast<uint32_t>(p.y) & (VRAM_H - 1)) == Y)
+        {
+          const uint32_t col = static_cast<uint32_t>(p.x) - tile_x0;
+          if (col < TILE_W)
+          {
+            const uint32_t word = strip[lane * 32 + (col >> 1)];
+            const uint32_t h = col & 1u;
+            const uint32_t bg = h ? (word >> 16) : (word & 0xFFFFu);
+            strip[lane * 32 + (col >> 1)] = set_half(word, h, shade_pixel(s, ctx, static_cast<uint32_t>(p.x), Y, p.r, p.g, p.b, 0, 0, bg));
+          }
+        }
+      }
+      __syncwarp();
+    }
+    break;
+
+    case OP_FILL:
+    {
+#pragma unroll 1
+      for (uint32_t r = 0; r < STRIP_H; r++)
+      {
+        const uint32_t Y = strip_y0 + r;
+        const bool c0 = fill_covers(s, static_cast<uint32_t>(px0), Y), c1 = fill_covers(s, static_cast<uint32_t>(px0 + 1), Y);
+        if (!(c0 || c1))
+          continue;
+        uint32_t word = strip[r * 32 + lane];
+        if (c0)
+          word = set_half(word, 0, s.fill.color16);
+        if (c1)
+          word = set_half(word, 1, s.fill.color16);
+        strip[r * 32 + lane] = word;
+      }
+    }
+    break;
+
+    case OP_COPY:
+    {
+#pragma unroll 1
+      for (uint32_t r = 0; r < STRIP_H; r++)
+      {
+        const uint32_t Y = strip_y0 + r;
+        uint32_t s0, s1;
+        const bool c0 = copy_covers(s, static_cast<uint32_t>(px0), Y, s0), c1 = copy_covers(s, static_cast<uint32_t>(px0 + 1), Y, s1);
+        if (!(c0 || c1))
+          continue;
+        uint32_t word = strip[r * 32 + lane];
+        if (c0)
+          word = set_half(word, 0, transfer_write(s, static_cast<uint16_t>(word), __ldg(vram + s0)));
+        if (c1)
+          word = set_half(word, 1, transfer_write(s, static_cast<uint16_t>(word >> 16), __ldg(vram + s1)));
+        strip[r * 32 + lane] = word;
+      }
+    }
+    break;
+
+    case OP_UPLOAD:
+    {
+#pragma unroll 1
+      for (uint32_t r = 0; r < STRIP_H; r++)
+      {
+        const uint32_t Y = strip_y0 + r;
+        uint32_t p0, p1;
+        const bool c0 = upload_covers(s, static_cast<uint32_t>(px0), Y, p0), c1 = upload_covers(s, static_cast<uint32_t>(px0 + 1), Y, p1);
+        if (!(c0 || c1))
+          continue;
+        uint32_t word = strip[r * 32 + lane];
+        if (c0)
+          word = set_half(word, 0, transfer_write(s, static_cast<uint16_t>(word), __ldg(payload + p0)));
+        if (c1)
+          word = set_half(word, 1, transfer_write(s, static_cast<uint16_t>(word >> 16), __ldg(payload + p1)));
+        strip[r * 32 + lane] = word;
+      }
+    }
+    break;
+
+    default: break;
+  }
+}
+
+// ---- serial epoch kinds: one CTA, the reference's own order ----
+
+// a textured primitive that samples pixels it writes.  The reference (4-wide vector build) gathers the
+// texels of 4 pixels, then stores those 4 pixels; rows and groups are visited in walk order.  One warp, lanes 0..3.
+__device__ void serial_self_sampling(const PrimSetup& s, uint16_t* vram, const uint16_t* clut_pool_inst)
+{
+  if (threadIdx.x >= 32)
+    return;
+  const uint32_t lane = threadIdx.x;
+  const uint16_t* clut_lo = clut_pool_inst + s.clut_lo * CLUT_ENTRIES;
+  const uint16_t* clut_hi = clut_pool_inst + s.clut_hi * CLUT_ENTRIES;
+  volatile uint16_t* vv = vram;
+
+  auto group = [&](int32_t x0, uint32_t Y, bool active, uint32_t r, uint32_t g, uint32_t b, uint32_t u, uint32_t v) {
+    uint16_t texel = 0;
+    if (active)
+      texel = fetch_texel<true>(s, vram, clut_lo, clut_hi, u, v);
+    __syncwarp();
+    if (active)
+    {
+      uint16_t colour;
+      const uint32_t px = static_cast<uint32_t>(x0) + lane;
+      if (shade_colour(s, px, Y, r, g, b, texel, colour))
+      {
+        const uint16_t bg = vv[Y * VRAM_W + px];
+        vv[Y * VRAM_W + px] = blend_mask(s, bg, colour);
+      }
+    }
+    __syncwarp();
+  };
+
+  if (s.op == OP_RECT)
+  {
+    for (uint32_t oy = 0; oy < s.rect.h; oy++)
+    {
+      const int32_t y = s.rect.y + static_cast<int32_t>(oy);
+      const uint32_t Y = static_cast<uint32_t>(y) & (VRAM_H - 1);
+      RectRow row;
+      if (!rect_row(s, Y, row) || row.y != y)
+        continue;
+      for (uint32_t ox = 0; ox < s.rect.w; ox += 4)
+      {
+        const int32_t x = s.rect.x + static_cast<int32_t>(ox + lane);
+        const bool active = lane < 4 && (ox + lane) < s.rect.w && x >= row.x_lo && x < row.x_hi;
+        group(s.rect.x + static_cast<int32_t>(ox), Y, active, s.rect.r, s.rect.g, s.rect.b, (s.rect.u0 + ox + lane) & 0xFFu, row.v);
+      }
+    }
+    return;
+  }
+  if (s.op != OP_TRIANGLE)
+    return;
+  const auto& T = s.tri;
+  const bool upper_up = (T.tflags & TRI_UPPER_UP) != 0, lower_up = (T.tflags & TRI_LOWER_UP) != 0;
+  // part order = triparts[0], triparts[1] (inl:1557-1560); the upper part is triparts[vo]
+  for (int part = 0; part < 2; part++)
+  {
+    const bool is_upper = (part == 0) != upper_up;
+    const int32_t lo = is_upper ? T.up_lo : T.lo_lo, hi = is_upper ? T.up_hi : T.lo_hi;
+    const bool up = is_upper ? upper_up : lower_up;
+    for (int32_t k = 0; k < hi - lo; k++)
+    {
+      const int32_t cy = up ? (hi - 1 - k) : (lo + k);
+      const uint32_t Y = static_cast<uint32_t>(sext11(cy)) & (VRAM_H - 1);
+      TriRow row;
+      if (!tri_row(s, Y, row) || row.cy != cy)
+        continue;
+      for (int32_t gx = row.x_lo; gx < row.x_hi; gx += 4)
+      {
+        const int32_t px = gx + static_cast<int32_t>(lane);
+        const bool active = lane < 4 && px < row.x_hi;
+        uint32_t r, g, b, u, v;
+        tri_attrs(s, row, px, r, g, b, u, v);
+        group(gx, Y, active, r, g, b, u, v);
+      }
+    }
+  }
+}
+
+// CopyVRAM whose source and destination alias: wrap split in the reference's order, rows sequential, each row
+// read completely before it is written (CopyVRAMImpl, inl:1833-1939).
+__device__ void serial_copy_rows(uint16_t* vram, uint32_t sx, uint32_t sy, uint32_t dx, uint32_t dy, uint32_t w, uint32_t h,
+                                 uint16_t mand, uint16_t mor)
+{
+  volatile uint16_t* vv = vram;
+  for (uint32_t r = 0; r < h; r++)
+  {
+    const uint32_t srow = ((sy + r) & (VRAM_H - 1)) * VRAM_W, drow = ((dy + r) & (VRAM_H - 1)) * VRAM_W;
+    uint16_t px[VRAM_W / RASTER_THREADS];
+#pragma unroll
+    for (uint32_t k = 0; k < VRAM_W / RASTER_THREADS; k++)
+    {
+      const uint32_t c = k * RASTER_THREADS + threadIdx.x;
+      px[k] = (c < w) ? vv[srow + ((sx + c) & (VRAM_W - 1))] : uint16_t(0);
+    }
+    __syncthreads();
+#pragma unroll
+    for (uint32_t k = 0; k < VRAM_W / RASTER_THREADS; k++)
+    {
+      const uint32_t c = k * RASTER_THREADS + threadIdx.x;
+      if (c < w)
+      {
+        const uint32_t a = drow + ((dx + c) & (VRAM_W - 1));
+        if ((vv[a] & mand) == 0)
+          vv[a] = static_cast<uint16_t>(px[k] | mor);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+__device__ void serial_copy(const PrimSetup& s, uint16_t* vram)
+{
+  const uint16_t mand = (s.flags0 & F_CHECK_MASK) ? 0x8000u : 0, mor = (s.flags0 & F_SET_MASK) ? 0x8000u : 0;
+  const uint32_t sx = s.copy.sx, sy = s.copy.sy, dx = s.copy.dx, dy = s.copy.dy, w = s.copy.w, h = s.copy.h;
+  if ((sx + w) <= VRAM_W && (dx + w) <= VRAM_W)
+  {
+    serial_copy_rows(vram, sx, sy, dx, dy, w, h, mand, mor);
+    return;
+  }
+  uint32_t rem_rows = h, csy = sy, cdy = dy;
+  while (rem_rows > 0)
+  {
+    const uint32_t rows = min(rem_rows, min(VRAM_H - csy, VRAM_H - cdy));
+    uint32_t rem_cols = w, csx = sx, cdx = dx;
+    while (rem_cols > 0)
+    {
+      const uint32_t cols = min(rem_cols, min(VRAM_W - csx, VRAM_W - cdx));
+      serial_copy_rows(vram, csx, csy, cdx, cdy, cols, rows, mand, mor);
+      csx = (csx + cols) & (VRAM_W - 1);
+      cdx = (cdx + cols) & (VRAM_W - 1);
+      rem_cols -= cols;
+    }
+    csy = (csy + rows) & (VRAM_H - 1);
+    cdy = (cdy + rows) & (VRAM_H - 1);
+    rem_rows -= rows;
+  }
+}
+
+// mask-checked upload.  Source index of a pixel = its linear index minus the number of masked pixels
+// before it (in scan order) that sit in the scalar tail of their row (columns >= aw).
+__device__ void serial_upload_masked(const PrimSetup& s, uint16_t* vram, const uint16_t* __restrict__ payload,
+                                     uint32_t* warp_count)
+{
+  const auto& U = s.upload;
+  const uint32_t aw = min(static_cast<uint32_t>(U.w), VRAM_W - U.x) & ~7u;
+  const uint16_t mor = (s.flags0 & F_SET_MASK) ? 0x8000u : 0;
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  uint32_t deficit = 0; // uniform across the CTA
+  for (uint32_t r = 0; r < U.h; r++)
+  {
+    const uint32_t drow = ((U.y + r) & (VRAM_H - 1)) * VRAM_W;
+    for (uint32_t base = 0; base < U.w; base += RASTER_THREADS)
+    {
+      const uint32_t c = base + threadIdx.x;
+      const bool in = c < U.w;
+      const uint32_t a = drow + ((U.x + c) & (VRAM_W - 1));
+      const uint16_t d = in ? vram[a] : uint16_t(0);
+      const bool masked = in && (d & 0x8000u);
+      const bool counts = masked && c >= aw;
+      const uint32_t bal = __ballot_sync(0xFFFFFFFFu, counts);
+      if (lane == 0)
+        warp_count[warp] = __popc(bal);
+      __syncthreads();
+      uint32_t before = __popc(bal & ((1u << lane) - 1u));
+      uint32_t total = 0;
+#pragma unroll
+      for (uint32_t k = 0; k < RASTER_WARPS; k++)
+      {
+        const uint32_t n = warp_count[k];
+        before += (k < warp) ? n : 0u;
+        total += n;
+      }
+      if (in && !masked)
+        vram[a] = static_cast<uint16_t>(__ldg(payload + U.payload + r * U.w + c - (deficit + before)) | mor);
+      deficit += total;
+      __syncthreads();
+    }
+  }
+}
+
+__global__ void __launch_bounds__(RASTER_THREADS) raster_kernel(const WaveItem* __restrict__ items,
+                                                                const PrimSetup* __restrict__ setups,
+                                                                const BinInfo* __restrict__ bins, uint16_t* __restrict__ vram_pool,
+                                                                const uint16_t* __restrict__ clut_pool,
+                                                                const uint16_t* __restrict__ payload, uint32_t clut_slots)
+{
+  __shared__ RasterShared sh;
+  const WaveItem it = items[blockIdx.y];
+  if (it.cmd_begin == it.cmd_end)
+    return;
+  uint16_t* vram = vram_pool + static_cast<size_t>(it.instance) * VRAM_PIXELS;
+  const uint16_t* cluts = clut_pool + static_cast<size_t>(it.instance) * clut_slots * CLUT_ENTRIES;
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+
+  if (it.kind != EPOCH_TILED)
+  {
+    if (blockIdx.x != 0)
+      return;
+    // stage the single primitive in shared memory for all threads
+    if (threadIdx.x < SETUP_WORDS)
+      sh.stage[0][threadIdx.x] = reinterpret_cast<const uint32_t*>(setups + it.cmd_begin)[threadIdx.x];
+    __syncthreads();
+    const PrimSetup& s = *reinterpret_cast<const PrimSetup*>(sh.stage[0]);
+    if (s.op == OP_NOP)
+      return;
+    if (it.kind == EPOCH_SELF_SAMPLING)
+      serial_self_sampling(s, vram, cluts);
+    else if (it.kind == EPOCH_COPY_OVERLAP)
+      serial_copy(s, vram);
+    else
+      serial_upload_masked(s, vram, payload, sh.warp_count);
+    return;
+  }
+
+  const uint32_t tx = blockIdx.x & (TILES_X - 1), ty = blockIdx.x / TILES_X;
+  const uint32_t tile_x0 = tx * TILE_W, tile_y0 = ty * TILE_H;
+  const uint32_t tile_bit = (1u << tx) | (1u << (16 + ty));
+  const uint32_t n_cmds = it.cmd_end - it.cmd_begin;
+
+  // 128-bit tile load/store mapping: thread t moves 8 pixels: row t/8, columns (t%8)*8 .. +7
+  const uint32_t ld_row = threadIdx.x >> 3, ld_col = (threadIdx.x & 7u) * 8u;
+  uint4* gtile = reinterpret_cast<uint4*>(vram + (tile_y0 + ld_row) * VRAM_W + tile_x0 + ld_col);
+  uint4* stile = reinterpret_cast<uint4*>(&sh.tile[ld_row][ld_col / 2]);
+
+  bool loaded = false;
+  uint32_t list_n = 0;
+  uint32_t* strip = &sh.tile[warp * STRIP_H][0];
+  const PrimSetup& staged = *reinterpret_cast<const PrimSetup*>(sh.stage[warp]);
+
+  for (uint32_t base = 0; base < n_cmds; base += RASTER_THREADS)
+  {
+    // ---- bin: one primitive per thread, order kept by ballot + prefix ----
+    const uint32_t i = base + threadIdx.x;
+    uint32_t entry = 0;
+    bool hit = false;
+    if (i < n_cmds)
+    {
+      const uint2 b = __ldg(reinterpret_cast<const uint2*>(bins) + it.cmd_begin + i);
+      hit = (b.x & tile_bit) == tile_bit;
+      if (hit)
+      {
+        const uint32_t sm = strip_mask_for(b.y, tile_y0);
+        entry = i | (sm << 16);
+        hit = sm != 0;
+      }
+    }
+    const uint32_t bal = __ballot_sync(0xFFFFFFFFu, hit);
+    if (lane == 0)
+      sh.warp_count[warp] = __popc(bal);
+    __syncthreads();
+    uint32_t pos = list_n + __popc(bal & ((1u << lane) - 1u));
+    uint32_t total = 0;
+#pragma unroll
+    for (uint32_t k = 0; k < RASTER_WARPS; k++)
+    {
+      const uint32_t n = sh.warp_count[k];
+      pos += (k < warp) ? n : 0u;
+      total += n;
+    }
+    if (hit)
+      sh.list[pos] = entry;
+    list_n += total;
+    const bool last = (base + RASTER_THREADS) >= n_cmds;
+    const bool run = list_n > 0 && (last || (list_n + RASTER_THREADS) > LIST_CAP);
+    if (run && !loaded)
+    {
+      *stile = *gtile;
+      loaded = true;
+    }
+    __syncthreads();
+    if (!run)
+      continue;
+
+    // ---- raster: every warp walks the bin in order over its own strip ----
+    for (uint32_t e = 0; e < list_n; e++)
+    {
+      const uint32_t ent = sh.list[e];
+      if (!((ent >> (16 + warp)) & 1u))
+        continue;
+      const uint32_t* src = reinterpret_cast<const uint32_t*>(setups + it.cmd_begin + (ent & 0xFFFFu));
+      sh.stage[warp][lane] = __ldg(src + lane);
+      if (lane < SETUP_WORDS - 32)
+        sh.stage[warp][32 + lane] = __ldg(src + 32 + lane);
+      __syncwarp();
+      raster_prim_on_strip(staged, strip, tile_x0, tile_y0 + warp * STRIP_H, vram, cluts, payload, lane);
+      __syncwarp();
+    }
+    list_n = 0;
+    __syncthreads();
+  }
+  if (loaded)
+    *gtile = *stile;
+}
+
+// ------------------------------------------------------------------------------------------------ hash
+constexpr uint32_t HASH_BLOCKS_PER_INSTANCE = 32;
+
+__global__ void __launch_bounds__(256) hash_kernel(const uint16_t* __restrict__ vram_pool, uint32_t first_instance,
+                                                   unsigned long long* __restrict__ out)
+{
+  const uint32_t inst = first_instance + blockIdx.y;
+  const uint4* v = reinterpret_cast<const uint4*>(vram_pool + static_cast<size_t>(inst) * VRAM_PIXELS);
+  constexpr uint32_t VEC_PER_INSTANCE = VRAM_PIXELS * 2 / 16; // 65536
+  constexpr uint32_t VEC_PER_BLOCK = VEC_PER_INSTANCE / HASH_BLOCKS_PER_INSTANCE;
+  uint64_t h = 0;
+  for (uint32_t k = threadIdx.x; k < VEC_PER_BLOCK; k += 256)
+  {
+    const uint32_t vi = blockIdx.x * VEC_PER_BLOCK + k;
+    const uint4 q = __ldg(v + vi);
+    const uint64_t wi = static_cast<uint64_t>(vi) * 4;
+    h += mix64(((wi + 0) << 32) | q.x);
+    h += mix64(((wi + 1) << 32) | q.y);
+    h += mix64(((wi + 2) << 32) | q.z);
+    h += mix64(((wi + 3) << 32) | q.w);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+    h += __shfl_xor_sync(0xFFFFFFFFu, h, o);
+  __shared__ uint64_t part[8];
+  if ((threadIdx.x & 31) == 0)
+    part[threadIdx.x >> 5] = h;
+  __syncthreads();
+  if (threadIdx.x == 0)
+  {
+    uint64_t t = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+      t += part[k];
+    atomicAdd(out + inst, static_cast<unsigned long long>(t));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ scan-out
+__device__ __forceinline__ uint32_t e5to8(uint32_t c)
+{
+  return (c * 527u + 23u) >> 6; // gpu_helpers.h:18-31
+}
+
+__global__ void scanout_kernel(const uint16_t* __restrict__ vram, ScanoutParams p, uint8_t* __restrict__ out)
+{
+  const uint32_t col = blockIdx.x * blockDim.x + threadIdx.x, row = blockIdx.y;
+  if (col >= p.width)
+    return;
+  if (!p.is24)
+  {
+    uint32_t idx;
+    if (p.fast)
+      idx = (p.src_y * VRAM_W + p.src_x + row * (VRAM_W << p.line_skip) + col) & (VRAM_PIXELS - 1); // gpu_sw.cpp:246-266
+    else
+      idx = ((p.src_y + (row << p.line_skip)) & (VRAM_H - 1)) * VRAM_W + ((p.src_x + col) & (VRAM_W - 1)); // :272-284
+    const uint32_t c = vram[idx];
+    if (p.format == 0)
+    {
+      const uint32_t v = e5to8(c & 31u) | (e5to8((c >> 5) & 31u) << 8) | (e5to8((c >> 10) & 31u) << 16) | ((c >> 15) ? 0xFF000000u : 0u);
+      reinterpret_cast<uint32_t*>(out + static_cast<size_t>(row) * p.out_stride)[col] = v;
+    }
+    else
+    {
+      uint32_t o;
+      if (p.format == 1)
+        o = (c & 0x83E0u) | ((c >> 10) & 0x1Fu) | ((c & 0x1Fu) << 10);
+      else if (p.format == 2)
+        o = ((c & 0x3E0u) << 1) | ((c >> 9) & 0x3Eu) | ((c & 0x1Fu) << 11) | (c >> 15);
+      else
+        o = ((c & 0x3E0u) << 1) | ((c & 0x20u) << 1) | ((c >> 10) & 0x1Fu) | ((c & 0x1Fu) << 11);
+      reinterpret_cast<uint16_t*>(out + static_cast<size_t>(row) * p.out_stride)[col] = static_cast<uint16_t>(o);
+    }
+    return;
+  }
+  uint32_t rgb;
+  if (p.fast)
+  {
+    // linear byte addressing, 3 bytes per pixel (gpu_sw.cpp:307-323); wraps at the end of VRAM instead of reading past it
+    const uint8_t* bytes = reinterpret_cast<const uint8_t*>(vram);
+    const uint32_t a = (p.src_y * VRAM_W + p.src_x) * 2u + p.skip_x * 3u + row * ((VRAM_W << p.line_skip) * 2u) + col * 3u;
+    constexpr uint32_t M = VRAM_PIXELS * 2u - 1u;
+    rgb = bytes[a & M] | (bytes[(a + 1) & M] << 8) | (bytes[(a + 2) & M] << 16);
+  }
+  else
+  {
+    const uint16_t* srow = vram + ((p.src_y + (row << p.line_skip)) & (VRAM_H - 1)) * VRAM_W; // gpu_sw.cpp:331-342
+    const uint32_t off = p.src_x + (((p.skip_x + col) * 3u) / 2u);
+    const uint32_t s0 = srow[off & (VRAM_W - 1)], s1 = srow[(off + 1) & (VRAM_W - 1)];
+    rgb = ((s1 << 16) | s0) >> ((col & 1u) * 8u);
+  }
+  reinterpret_cast<uint32_t*>(out + static_cast<size_t>(row) * p.out_stride)[col] = (rgb & 0x00FFFFFFu) | 0xFF000000u;
+}
+
+// ------------------------------------------------------------------------------------------------ launchers
+cudaError_t launch_setup(const PackedCmd* cmds, PrimSetup* setups, BinInfo* bins, uint32_t n, cudaStream_t st)
+{
+  if (n == 0)
+    return cudaSuccess;
+  setup_kernel<<<(n + 127) / 128, 128, 0, st>>>(cmds, setups, bins, n);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_clut(const WaveItem* items, uint32_t n_items, const ClutOp* ops, const uint16_t* vram_pool,
+                        uint16_t* clut_pool, uint32_t clut_slots, cudaStream_t st)
+{
+  if (n_items == 0)
+    return cudaSuccess;
+  clut_kernel<<<n_items, 256, 0, st>>>(items, ops, vram_pool, clut_pool, clut_slots);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_raster(const WaveItem* items, uint32_t n_items, const PrimSetup* setups, const BinInfo* bins,
+                          uint16_t* vram_pool, const uint16_t* clut_pool, const uint16_t* payload, uint32_t clut_slots,
+                          cudaStream_t st)
+{
+  // gridDim.y is limited to 65535: chunk the wave
+  for (uint32_t off = 0; off < n_items; off += 32768)
+  {
+    const uint32_t n = (n_items - off) < 32768u ? (n_items - off) : 32768u;
+    raster_kernel<<<dim3(NUM_TILES, n), RASTER_THREADS, 0, st>>>(items + off, setups, bins, vram_pool, clut_pool, payload, clut_slots);
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_hash(const uint16_t* vram_pool, uint32_t first, uint32_t count, unsigned long long* out, cudaStream_t st)
+{
+  if (count == 0)
+    return cudaSuccess;
+  cudaError_t e = cudaMemsetAsync(out + first, 0, sizeof(unsigned long long) * count, st);
+  if (e != cudaSuccess)
+    return e;
+  for (uint32_t off = 0; off < count; off += 32768)
+  {
+    const uint32_t n = (count - off) < 32768u ? (count - off) : 32768u;
+    hash_kernel<<<dim3(HASH_BLOCKS_PER_INSTANCE, n), 256, 0, st>>>(vram_pool, first + off, out);
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_scanout(const uint16_t* vram, const ScanoutParams& p, uint8_t* out, cudaStream_t st)
+{
+  if (p.width == 0 || p.height == 0)
+    return cudaSuccess;
+  scanout_kernel<<<dim3((p.width + 127) / 128, p.height), 128, 0, st>>>(vram, p, out);
+  return cudaGetLastError();
+}
+
+} // namespace psx

@@ -1,0 +1,30 @@
+// kernels.h — host-callable launchers for kernels.cu.
+#pragma once
+
+#include "psx_types.h"
+
+#include <cuda_runtime.h>
+
+namespace psx {
+
+struct ScanoutParams
+{
+  uint32_t src_x, src_y, skip_x;
+  uint32_t width, height;
+  uint32_t line_skip;
+  uint32_t is24;
+  uint32_t fast;       // the reference's non-wrapping fast path applies (gpu_sw.cpp:241 / :305)
+  uint32_t format;     // 0 RGBA8, 1 RGB5A1, 2 A1BGR5, 3 RGB565 (15-bit source only)
+  uint32_t out_stride; // bytes
+};
+
+cudaError_t launch_setup(const PackedCmd* cmds, PrimSetup* setups, BinInfo* bins, uint32_t n, cudaStream_t st);
+cudaError_t launch_clut(const WaveItem* items, uint32_t n_items, const ClutOp* ops, const uint16_t* vram_pool,
+                        uint16_t* clut_pool, uint32_t clut_slots, cudaStream_t st);
+cudaError_t launch_raster(const WaveItem* items, uint32_t n_items, const PrimSetup* setups, const BinInfo* bins,
+                          uint16_t* vram_pool, const uint16_t* clut_pool, const uint16_t* payload, uint32_t clut_slots,
+                          cudaStream_t st);
+cudaError_t launch_hash(const uint16_t* vram_pool, uint32_t first, uint32_t count, unsigned long long* out, cudaStream_t st);
+cudaError_t launch_scanout(const uint16_t* vram, const ScanoutParams& p, uint8_t* out, cudaStream_t st);
+
+} // namespace psx

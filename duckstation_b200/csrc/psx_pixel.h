@@ -65,12 +65,19 @@ PSX_HD uint32_t texel_addr(const PrimSetup& s, uint32_t u, uint32_t v, uint32_t&
 
 // Full texel fetch through the CLUT snapshots.  `clut_lo` holds palette entries 0..15 and `clut_hi` entries 16..255:
 // a 4-bit UpdateCLUT only replaces the first 16 entries of the reference's cache (gpu_sw_rasterizer.cpp:47-51).
-PSX_HD uint16_t fetch_texel(const PrimSetup& s, const uint16_t* __restrict__ vram, const uint16_t* __restrict__ clut_lo,
+// kLive = the texel word is read from VRAM that this very primitive is writing (self-sampling): the
+// read must then be a coherent (volatile) load instead of going through the read-only path.
+template<bool kLive>
+PSX_HD uint16_t fetch_texel(const PrimSetup& s, const uint16_t* vram, const uint16_t* __restrict__ clut_lo,
                             const uint16_t* __restrict__ clut_hi, uint32_t u, uint32_t v)
 {
   uint32_t shift, idxmask;
   const uint32_t a = texel_addr(s, u, v, shift, idxmask);
-  const uint16_t w = PSX_LD_TEX(vram + a);
+  uint16_t w;
+  if (kLive)
+    w = *reinterpret_cast<const volatile uint16_t*>(vram + a);
+  else
+    w = PSX_LD_TEX(vram + a);
   if (idxmask == 0)
     return w;
   const uint32_t idx = (w >> shift) & idxmask;

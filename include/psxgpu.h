@@ -1,0 +1,146 @@
+/* psxgpu.h — C ABI of the B200-native PSX GPU rasteriser (libpsxgpu.so).
+ *
+ * Drop-in boundary for DuckStation's software renderer: everything a `GPUBackend`
+ * subclass needs in order to replace `GPU_SW` (reference: src/core/gpu_backend.h:30-183,
+ * src/core/gpu_sw.h:17-69).  The C++ mirror of that class, `psx::CudaGpuBackend`
+ * (duckstation_b200/csrc/backend.h), is a thin layer over these calls; INTEGRATION.md
+ * shows the subclass a DuckStation maintainer would add.
+ *
+ * Conventions: plain pointers and sizes only; every call returns 0 on success or a
+ * negative PSXGPU_E_* code and never throws; a context is used by one thread at a time
+ * (the reference calls its backend from the video thread only, gpu_backend.h:27-28).
+ * There is no CPU fallback: without a CUDA device `psxgpu_create` fails.
+ *
+ * Command input is the reference's own wire format (include/psxgpu_wire.h ==
+ * src/core/video_thread_commands.h): a byte stream of size-prefixed records, exactly what
+ * GPUBackend::HandleCommand receives one at a time (src/core/gpu_backend.cpp:383-544).
+ */
+#ifndef PSXGPU_H
+#define PSXGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#include "psxgpu_wire.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PSXGPU_ABI_VERSION 1
+
+enum {
+  PSXGPU_OK = 0,
+  PSXGPU_E_INVALID = -1,   /* bad argument */
+  PSXGPU_E_CUDA = -2,      /* CUDA runtime error; see psxgpu_last_error */
+  PSXGPU_E_MALFORMED = -3, /* wire stream record sizes do not add up */
+  PSXGPU_E_NOMEM = -4,
+  PSXGPU_E_UNSUPPORTED = -5 /* record not allowed on this entry point (e.g. a read-back inside a batch submit) */
+};
+
+/* 15-bit scan-out formats (reference picks one from host-device support, gpu_sw.cpp:39-48). */
+enum { PSXGPU_FMT_RGBA8 = 0, PSXGPU_FMT_RGB5A1 = 1, PSXGPU_FMT_A1BGR5 = 2, PSXGPU_FMT_RGB565 = 3 };
+
+typedef struct psxgpu_ctx psxgpu_ctx;
+
+/* Replaces the three GPUSettings fields that change GPU_SW output (settings.h:83-85). */
+typedef struct psxgpu_opts {
+  uint32_t struct_size;      /* sizeof(psxgpu_opts) */
+  uint32_t modulation_crop;  /* gpu_modulation_crop */
+  uint32_t show_vram;        /* gpu_show_vram: scan-out shows the whole VRAM */
+  uint32_t display_format;   /* PSXGPU_FMT_* used for 15-bit scan-out */
+  uint32_t clut_slots;       /* CLUT snapshot slots per instance (4..256, 0 = 256) */
+  uint32_t encode_threads;   /* host threads for psxgpu_submit_batch (0 = hardware concurrency) */
+  uint32_t profile;          /* 1: time every raster wave with CUDA events (psxgpu_get_timing) */
+  uint32_t reserved[9];
+} psxgpu_opts;
+
+typedef struct psxgpu_stats {
+  uint64_t wire_commands, packed_prims, epochs, waves;
+  uint64_t cuts_raw, cuts_war, cuts_clut;
+  uint64_t serial_self_sampling, serial_copy, serial_upload;
+  uint64_t clut_ops, clut_cache_hits, rejected;
+  uint64_t kernel_launches;     /* our kernels launched since create/reset_stats */
+  uint64_t h2d_bytes, d2h_bytes;
+  uint64_t flushes;
+  uint64_t reserved[7];
+} psxgpu_stats;
+
+typedef struct psxgpu_timing {
+  float last_flush_device_ms;   /* H2D + setup + all waves of the last flush / run_staged (CUDA events on our stream) */
+  float last_kernels_ms;        /* setup + waves only */
+  float last_raster_ms;         /* sum over raster waves (profile=1) */
+  float last_raster_max_ms;     /* longest single raster launch (profile=1) */
+  uint32_t last_raster_launches;
+  uint32_t last_waves;
+  float last_hash_ms;           /* last psxgpu_hash* call */
+  float last_encode_ms;         /* host time spent in the encoder during the last submit(s) since the previous flush */
+  float last_stage_ms;          /* host time spent packing pinned staging buffers in the last flush */
+  float reserved[7];
+} psxgpu_timing;
+
+/* GPUBackend::CreateSoftwareBackend + Initialize(upload_vram=false) (gpu_sw.cpp:34-59, :450-453):
+ * n_instances independent 1024x512 VRAMs, cleared, on CUDA device `device`. */
+int psxgpu_create(int device, uint32_t n_instances, const psxgpu_opts* opts, psxgpu_ctx** out);
+void psxgpu_destroy(psxgpu_ctx* ctx);
+const char* psxgpu_last_error(const psxgpu_ctx* ctx);
+int psxgpu_abi_version(void);
+
+/* GPUBackend::HandleCommand for a run of records (gpu_backend.cpp:383-544).  Draw / fill / copy /
+ * upload / CLUT / drawing-area records are encoded and queued; ClearVRAM, LoadState and ReadVRAM are
+ * executed in order (they flush first).  ReadVRAM makes the host shadow current (see psxgpu_shadow_vram);
+ * UpdateDisplay scans out into the context's display buffer (psxgpu_display). */
+int psxgpu_submit_wire(psxgpu_ctx* ctx, uint32_t instance, const void* wire, size_t bytes);
+
+/* Batched form: streams[i] goes to instance first_instance + i.  Encoded in parallel on host threads.
+ * Barrier records (ReadVRAM, LoadState, ClearVRAM, UpdateDisplay) are not allowed here. */
+int psxgpu_submit_batch(psxgpu_ctx* ctx, uint32_t first_instance, uint32_t count, const void* const* streams,
+                        const size_t* bytes);
+
+/* GPUBackend::FlushRender (gpu_backend.h:150): upload queued commands and launch them (asynchronous). */
+int psxgpu_flush(psxgpu_ctx* ctx);
+/* Wait for everything launched so far. */
+int psxgpu_sync(psxgpu_ctx* ctx);
+
+/* Re-run the device part of the most recent flush (setup + all waves) from the command buffers that are still
+ * resident in HBM.  For steady-state measurement; the caller is responsible for the VRAM state it starts from. */
+int psxgpu_run_staged(psxgpu_ctx* ctx);
+
+/* GPUBackend::ReadVRAM contract (gpu_backend.h:152, gpu_hw.cpp:3472-3515): after the call the pixels of the
+ * rectangle (wrapping like GPUREAD, gpu.cpp:1896-1929) are in dst, row pitch dst_pitch_px pixels. */
+int psxgpu_read_vram(psxgpu_ctx* ctx, uint32_t instance, uint32_t x, uint32_t y, uint32_t w, uint32_t h, uint16_t* dst,
+                     uint32_t dst_pitch_px);
+/* The reference exposes VRAM as the global g_vram; this is its stand-in: a 1024x512 host copy refreshed by
+ * ReadVRAM records / psxgpu_read_vram(…, shadow) for `instance`. */
+uint16_t* psxgpu_shadow_vram(psxgpu_ctx* ctx, uint32_t instance);
+
+/* GPUBackend::ClearVRAM (gpu_sw.cpp:61-65) and LoadState (gpu_sw.cpp:67-71). */
+int psxgpu_clear_vram(psxgpu_ctx* ctx, uint32_t instance);
+int psxgpu_load_state(psxgpu_ctx* ctx, uint32_t instance, const uint16_t* vram_1024x512, const uint16_t* clut_256);
+/* DoMemoryState (gpu_sw.cpp:73-84): VRAM + the current 256-entry CLUT cache. */
+int psxgpu_save_state(psxgpu_ctx* ctx, uint32_t instance, uint16_t* vram_1024x512, uint16_t* clut_256);
+
+/* GPU_SW::UpdateDisplay minus presentation (gpu_sw.cpp:391-448).  Writes width*height pixels (RGBA8 for 24-bit
+ * sources, opts.display_format otherwise) to dst with row pitch dst_stride bytes.  Returns 1 if the display is
+ * disabled (nothing written). */
+int psxgpu_scanout(psxgpu_ctx* ctx, uint32_t instance, const psx_update_display* cmd, void* dst, uint32_t dst_stride,
+                   uint32_t* out_width, uint32_t* out_height);
+/* Result of the last UpdateDisplay record seen by psxgpu_submit_wire. */
+const void* psxgpu_display(psxgpu_ctx* ctx, uint32_t* width, uint32_t* height, uint32_t* stride, uint32_t* is_rgba8);
+
+/* vramhash64 of instances [first, first+count): sum over 32-bit words i of mix64((i<<32)|word) (include
+ * psxgpu_hash.h semantics in DESIGN.md §7).  Flushes and waits. */
+int psxgpu_hash(psxgpu_ctx* ctx, uint32_t first_instance, uint32_t count, uint64_t* out_host);
+/* Same, result left in device memory (e.g. a torch tensor) for a following NCCL gather; waits for completion. */
+int psxgpu_hash_device(psxgpu_ctx* ctx, uint32_t first_instance, uint32_t count, void* out_device);
+
+int psxgpu_get_stats(psxgpu_ctx* ctx, psxgpu_stats* out);
+int psxgpu_reset_stats(psxgpu_ctx* ctx);
+int psxgpu_get_timing(psxgpu_ctx* ctx, psxgpu_timing* out);
+/* Durations (ms) of the raster launches of the last profiled flush / run_staged; returns the count. */
+int psxgpu_get_raster_launch_ms(psxgpu_ctx* ctx, float* out, uint32_t max_count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PSXGPU_H */

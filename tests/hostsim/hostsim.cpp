@@ -29,7 +29,7 @@ void shade_and_store(const PrimSetup& s, const uint16_t*, uint32_t px, uint32_t 
 {
   uint16_t texel = 0;
   if (s.flags0 & F_TEXTURE)
-    texel = fetch_texel(s, g_snap.data(), &g_clut[s.clut_lo * 256], &g_clut[s.clut_hi * 256], u, v);
+    texel = fetch_texel<false>(s, g_snap.data(), &g_clut[s.clut_lo * 256], &g_clut[s.clut_hi * 256], u, v);
   uint16_t colour;
   if (!shade_colour(s, px, Y, r, g, b, texel, colour))
     return;
@@ -122,7 +122,7 @@ void shade_group(const PrimSetup& s, const uint16_t*, int32_t x0, uint32_t Y, ui
   uint16_t tex[4] = {0, 0, 0, 0};
   for (int l = 0; l < 4; l++)
     if ((active >> l) & 1u)
-      tex[l] = fetch_texel(s, g_vram.data(), &g_clut[s.clut_lo * 256], &g_clut[s.clut_hi * 256], u[l], v[l]); // LIVE vram
+      tex[l] = fetch_texel<true>(s, g_vram.data(), &g_clut[s.clut_lo * 256], &g_clut[s.clut_hi * 256], u[l], v[l]); // LIVE vram
   for (int l = 0; l < 4; l++)
   {
     if (!((active >> l) & 1u))
