@@ -1,0 +1,394 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200-native PSX rasteriser.
+
+Workload (BASELINE.json configs[3], the one the metric "at 1/2/4/8 B200" is quoted on): a batch of independent
+1024x512 VRAM instances, instance i generated from seed i: FillVRAM clear + 256x256 texture-atlas upload + 2000
+primitives of the config-2 state mix (70% triangles / 30% sprites, 4/8/15-bit CLUT textures, texture window, raw
+and modulated, dither, all four blend modes, mask set/check) at ~256 px mean area.  4096 instances PER GPU
+(weak scaling: rank r owns seeds [r*4096, (r+1)*4096)); no data-path collective, one NCCL all-gather of the
+per-instance 64-bit VRAM hashes per step.
+
+A "step" = every instance's full command list executed to completion + hash.
+  value : whole-job Gpixels/s (covered pixels = ShadePixel invocations + fill + upload destination pixels, counted by
+          the CPU oracle) with the packed command buffers already resident in HBM (psxgpu_run_staged + hash + gather).
+  e2e   : same metric through the reference-facing C ABI from HOST wire-format buffers: per step
+          psxgpu_submit_batch (host encode) + psxgpu_flush (pinned staging, H2D, kernels) + psxgpu_hash (D2H).
+Parity gate: every per-instance hash is compared with the CPU oracle's (all instances at N=1, a 64-instance
+sample per rank otherwise); a mismatch makes the run fail.
+
+--impl reference : the reference's own rasteriser TU (oracle/_ref, compiled in place) on all host cores, one
+instance per worker process, same workload, same metric.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "Gpixels/s (bit-exact vs GPU_SW; batched independent VRAM instances x 2k primitives)"
+UNIT = "Gpixels/s"
+CONFIG = 4
+PRIMS = 2000
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--instances", type=int, default=4096, help="instances per GPU")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--verify", default="auto", choices=["auto", "all", "sample", "none"])
+    return ap.parse_args()
+
+
+def bytes_model(stats: dict) -> dict:
+    """Algorithmic bytes (SURVEY §8d / BASELINE.md §5)."""
+    draw = 2 * stats["draw_px"] + 2 * stats["draw_px_rmw"] + 2 * stats["draw_px_tex"]
+    fill = 2 * stats["fill_px"]
+    copy = 4 * stats["copy_px"] + 2 * stats["copy_px_masked"]
+    upload = 4 * stats["upload_px"] + 2 * stats["upload_px_masked"]
+    return {"draw": draw, "fill": fill, "copy": copy, "upload": upload, "total": draw + fill + copy + upload}
+
+
+def unit_pixels(stats: dict) -> int:
+    return stats["draw_px"] + stats["fill_px"] + stats["copy_px"] + stats["upload_px"]
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+
+    def __init__(self, gpu_index: int):
+        self.rows = []
+        self.proc = None
+        self.gpu = gpu_index
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+                for n, v in zip(names, r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak() -> tuple[float, str]:
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def recorded_traffic():
+    """dram bytes per launch of the dominant kernel from the committed ncu capture, if any."""
+    p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    try:
+        with open(p) as f:
+            return json.load(f).get("raster_kernel_dram_bytes_per_launch")
+    except Exception:
+        return None
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def run_reference(args, rank: int, world: int):
+    if rank != 0:
+        return
+    from oracle.cpu_farm import CpuFarm, have_reference
+
+    kind = "reference" if have_reference() else "port"
+    cores = os.cpu_count() or 1
+    n_inst = args.instances
+    with CpuFarm(cores) as farm:
+        farm.prepare(CONFIG, list(range(n_inst)), PRIMS, 0)
+        _, _, stats = farm.run("port", True)  # pixel counts come from the instrumented port
+        px = unit_pixels(stats)
+        for _ in range(max(1, args.warmup)):
+            farm.run(kind, False)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            farm.run(kind, False)
+        dt = (time.perf_counter() - t0) / args.steps
+    value = px / dt / 1e9
+    sample = f"{n_inst} instances (seeds 0..{n_inst - 1}) x {PRIMS} primitives per step, one instance per worker process"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u16", "data": "synthetic",
+        "config": {"workload": f"BASELINE configs[3]: batched {n_inst} VRAM instances x {PRIMS} primitives (CPU sample)",
+                   "instances_per_step": n_inst, "frames_per_s": n_inst / dt},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def generate_streams(first_seed: int, count: int):
+    from concurrent.futures import ThreadPoolExecutor
+
+    from duckstation_b200 import streams
+
+    with ThreadPoolExecutor(max_workers=min(32, os.cpu_count() or 1)) as ex:
+        return list(ex.map(lambda s: streams.generate(CONFIG, s, PRIMS, 0), range(first_seed, first_seed + count)))
+
+
+def run_ours(args, rank: int, world: int, local_rank: int):
+    import ctypes as C
+
+    import numpy as np
+    import torch
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the rasteriser has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    from duckstation_b200 import Context
+    from duckstation_b200.sharding import gather_hashes, instance_range
+
+    n_inst = args.instances
+    first_seed, _ = instance_range(rank, world, n_inst * world)
+    wire = generate_streams(first_seed, n_inst)
+    wire_bytes = sum(len(s) for s in wire)
+
+    # CPU side: pixel counts + oracle hashes (parity gate) + baseline timing.  Rank 0 only at N>1 does the baseline.
+    verify = args.verify
+    if verify == "auto":
+        verify = "all" if world == 1 else "sample"
+    from oracle.cpu_farm import CpuFarm, have_reference
+
+    cores = max(1, (os.cpu_count() or 1) // max(1, world))
+    cpu_baseline = None
+    with CpuFarm(cores) as farm:
+        farm.prepare(CONFIG, list(range(first_seed, first_seed + n_inst)), PRIMS, 0)
+        _, oracle_hashes, stats = farm.run("port", True)
+        if rank == 0 and world == 1 and not args.no_cpu_baseline:
+            kind = "reference" if have_reference() else "port"
+            farm.run(kind, False)
+            best = min(farm.run(kind, False)[0] for _ in range(3))
+            cpu_baseline = {
+                "value": unit_pixels(stats) / best / 1e9, "unit": UNIT, "cores": cores, "kind": kind,
+                "sample": f"all {n_inst} instances x {PRIMS} primitives, best of 3 passes, one instance per worker process "
+                          f"({best * 1e3:.0f} ms per pass)",
+                "frames_per_s": n_inst / best,
+            }
+    px_rank = unit_pixels(stats)
+    bm = bytes_model(stats)
+
+    ctx = Context(n_inst, device=local_rank, profile=True)
+    ptrs = (C.c_void_p * n_inst)()
+    sizes = (C.c_size_t * n_inst)()
+    keep = [C.c_char_p(s) for s in wire]
+    for i, k in enumerate(keep):
+        ptrs[i] = C.cast(k, C.c_void_p)
+        sizes[i] = len(wire[i])
+    hash_dev = torch.zeros(n_inst, dtype=torch.int64, device="cuda")
+    gathered = [torch.zeros_like(hash_dev) for _ in range(world)] if world > 1 else None
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        ctx.sync()
+        torch.cuda.synchronize()
+
+    def gather():
+        if dist is not None:
+            dist.all_gather(gathered, hash_dev)
+
+    # ---- stage once: encode + H2D, commands stay resident in HBM ----
+    ctx.submit_batch_raw(ptrs, sizes, n_inst)
+    ctx.flush()
+    ctx.hash_into_device(hash_dev.data_ptr())
+    ctx.sync()
+    first_hashes = hash_dev.cpu().numpy().astype(np.uint64)
+    staged_stats = ctx.stats()
+
+    def resident_step():
+        ctx.run_staged()
+        ctx.hash_into_device(hash_dev.data_ptr())
+        gather()
+
+    for _ in range(args.warmup):
+        resident_step()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    launches0 = ctx.stats()["kernel_launches"]
+    dev_ms, raster_ms = 0.0, []
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        resident_step()
+        t = ctx.timing()
+        dev_ms += t["last_flush_device_ms"] + t["last_hash_ms"]
+        raster_ms.append(ctx.raster_launch_ms())
+    barrier()
+    dt = time.perf_counter() - t0
+    launches = ctx.stats()["kernel_launches"] - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    resident_hashes = hash_dev.cpu().numpy().astype(np.uint64)
+
+    # ---- e2e: host wire buffers -> C ABI -> hashes on the host, every step ----
+    host_hashes = None
+    ctx.reset_stats()
+    for _ in range(max(1, args.warmup // 2)):
+        ctx.submit_batch_raw(ptrs, sizes, n_inst)
+        ctx.flush()
+        host_hashes = ctx.hash()
+    barrier()
+    s0 = ctx.stats()
+    e2e_parts = {"encode_ms": 0.0, "stage_ms": 0.0, "device_ms": 0.0, "hash_ms": 0.0}
+    t1 = time.perf_counter()
+    for _ in range(args.steps):
+        ctx.submit_batch_raw(ptrs, sizes, n_inst)
+        ctx.flush()
+        host_hashes = ctx.hash()
+        t = ctx.timing()
+        e2e_parts["encode_ms"] += t["last_encode_ms"]
+        e2e_parts["stage_ms"] += t["last_stage_ms"]
+        e2e_parts["device_ms"] += t["last_flush_device_ms"]
+        e2e_parts["hash_ms"] += t["last_hash_ms"]
+    barrier()
+    dt_e2e = time.perf_counter() - t1
+    s1 = ctx.stats()
+
+    # ---- parity gate ----
+    def check(hashes, label):
+        idx = range(n_inst) if verify == "all" else (range(0, n_inst, max(1, n_inst // 64)) if verify == "sample" else [])
+        bad = [i for i in idx if int(hashes[i]) != oracle_hashes[first_seed + i]]
+        if bad:
+            raise SystemExit(f"bench.py: PARITY FAILURE ({label}) on rank {rank}: {len(bad)} instance hashes differ from the "
+                             f"oracle, first instance {first_seed + bad[0]}")
+        return len(list(idx))
+
+    checked = check(first_hashes, "first flush")
+    check(resident_hashes, "resident replay")
+    check(host_hashes, "e2e")
+
+    # ---- reduce over ranks: max time, sum pixels ----
+    red = torch.tensor([dt, dt_e2e, dev_ms], dtype=torch.float64, device="cuda")
+    tot = torch.tensor([float(px_rank), float(bm["total"])], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(red, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    dt_max, dt_e2e_max, dev_ms_max = [float(x) for x in red.cpu()]
+    px_total, bytes_total = [float(x) for x in tot.cpu()]
+
+    if rank == 0:
+        ms_step = dt_max / args.steps * 1e3
+        value = px_total * args.steps / dt_max / 1e9
+        e2e_value = px_total * args.steps / dt_e2e_max / 1e9
+        # dominant kernel: the raster launch of the wave that draws (the longest one of a step)
+        per_launch = list(zip(*raster_ms)) if raster_ms and raster_ms[0] else []
+        avg = [sum(x) / len(x) for x in per_launch]
+        dom = max(range(len(avg)), key=lambda i: avg[i]) if avg else None
+        peak, peak_src = measured_peak()
+        roofline = None
+        if dom is not None:
+            # wave 0 = fill + upload, the draw wave carries the primitive pixels
+            algo = bm["draw"] if dom > 0 or len(avg) == 1 else bm["fill"] + bm["upload"]
+            if len(avg) == 1:
+                algo = bm["total"]
+            achieved = algo / (avg[dom] * 1e-3) / 1e9
+            roofline = {"bound": "hbm", "kernel": "raster_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                        "frac": achieved / peak, "traffic": recorded_traffic(), "peak_source": peak_src,
+                        "algorithmic_bytes_per_launch": algo, "launch_ms": avg[dom], "raster_launch_ms": avg,
+                        "whole_step_algorithmic_frac": (bm["total"] / (ms_step * 1e-3) / 1e9) / peak,
+                        "compulsory_hbm_frac": ((2 * (1 << 20) * n_inst + staged_stats["h2d_bytes"]) / (ms_step * 1e-3) / 1e9) / peak}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u16",
+            "data": "synthetic",
+            "config": {"workload": f"BASELINE configs[3]: batched {n_inst} VRAM instances per GPU x {PRIMS} primitives "
+                                   "(config-2 state mix, ~256 px mean area), seeds = global instance index",
+                       "instances_per_gpu": n_inst, "instances_total": n_inst * world, "l2": "inputs (4 GiB VRAM pool + command "
+                       "buffers per GPU) exceed the 126 MB L2; no explicit flush",
+                       "pixels_per_instance": px_rank / n_inst, "prims_per_instance": staged_stats["packed_prims"] / n_inst,
+                       "epochs_per_instance": staged_stats["epochs"] / n_inst, "parity_checked_instances_per_rank": checked,
+                       "frames_per_s": n_inst * world * args.steps / dt_max},
+            "device_ms_per_step": dev_ms_max / args.steps,
+            "gpu_launches": launches,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": (s1["h2d_bytes"] - s0["h2d_bytes"]) // args.steps,
+                    "d2h_bytes_per_step": (s1["d2h_bytes"] - s0["d2h_bytes"]) // args.steps,
+                    "ms_per_step": dt_e2e_max / args.steps * 1e3, "wire_bytes_per_step": wire_bytes,
+                    "breakdown_ms_per_step": {k: v / args.steps for k, v in e2e_parts.items()},
+                    "frames_per_s": n_inst * world * args.steps / dt_e2e_max},
+            "roofline": roofline,
+            "cpu_baseline": cpu_baseline,
+            "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    from duckstation_b200 import build
+
+    if args.impl == "reference":
+        if rank == 0:
+            build.build_generator()
+            build.build_oracle()
+            build.build_reference()
+        run_reference(args, rank, world)
+        return
+    try:
+        build.build_all()  # no-op when the in-tree libraries are current; serialised across ranks by a file lock
+    except RuntimeError as e:  # no nvcc on the box: use the libraries that travelled with the snapshot
+        sys.stderr.write(f"bench.py: build skipped ({e})\n")
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

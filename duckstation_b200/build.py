@@ -94,13 +94,21 @@ def build_hostsim(force: bool = False) -> str:
 
 
 def build_all(force: bool = False) -> dict[str, str | None]:
-    return {
-        "product": build_product(force),
-        "generator": build_generator(force),
-        "oracle": build_oracle(force),
-        "reference": build_reference(force),
-        "hostsim": build_hostsim(force),
-    }
+    """Builds whatever is out of date.  Serialised across processes (torchrun ranks) with a file lock."""
+    import fcntl
+
+    with open(os.path.join(ROOT, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            return {
+                "product": build_product(force),
+                "generator": build_generator(force),
+                "oracle": build_oracle(force),
+                "reference": build_reference(force),
+                "hostsim": build_hostsim(force),
+            }
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
 
 
 if __name__ == "__main__":

@@ -2,11 +2,13 @@
 //
 //   setup_kernel    one thread per primitive: PackedCmd -> PrimSetup + BinInfo (all divisions happen here)
 //   clut_kernel     CLUT snapshot pass of an epoch wave (reference: UpdateCLUT, gpu_sw_rasterizer.cpp:43-66)
-//   raster_kernel   one CTA per (instance, 64x32 VRAM tile): bins the epoch's primitives for its tile in
-//                   submission order (warp ballots), stages the tile in shared memory and lets each of its 8
-//                   warps walk the bin in order over its own 64x4 strip — one 32-bit word (2 pixels) per lane
-//                   per row — then writes the tile back with 128-bit stores.  Texels and CLUT entries come
-//                   from global memory through the read-only path (L1/L2 resident).
+//   raster_kernel   one CTA per (instance, 256x64 block of VRAM = 4x2 tiles of 64x32): bins the epoch's primitives
+//                   for its block in submission order (warp ballots); each of its 8 warps owns one tile, staged
+//                   in shared memory, and walks the bin in order with no CTA-wide barrier.  Per primitive the
+//                   32 lanes compute the 32 row spans in one pass, a warp prefix sum compacts the covered
+//                   pixels and they are shaded 32 at a time (one pixel per lane), so small primitives keep the
+//                   lanes busy.  Tiles are read/written as coalesced 128-byte rows.  Texels and CLUT entries
+//                   come from global memory through the read-only path (L1/L2 resident).
 //                   Epochs of a serial kind (self-sampling primitive, aliasing copy, mask-checked upload tail)
 //                   are executed by one CTA in the reference's own order.
 //   hash_kernel     vramhash64 per instance
@@ -46,7 +48,7 @@ __global__ void __launch_bounds__(128) setup_kernel(const PackedCmd* __restrict_
 #pragma unroll
   for (int k = 0; k < 10; k++)
     dst[k] = sw[k];
-  reinterpret_cast<uint2*>(bins)[i] = make_uint2(b.tilemask, b.rows);
+  bins[i].tilemask = b.tilemask;
 }
 
 // ------------------------------------------------------------------------------------------------ CLUT snapshots
@@ -69,30 +71,19 @@ __global__ void __launch_bounds__(256) clut_kernel(const WaveItem* __restrict__ 
 // ------------------------------------------------------------------------------------------------ raster
 constexpr int RASTER_THREADS = 256;
 constexpr int RASTER_WARPS = RASTER_THREADS / 32;
+static_assert(RASTER_WARPS == CTA_TILES_X * CTA_TILES_Y, "one warp per tile of the CTA block");
 constexpr uint32_t LIST_CAP = 1024;
 constexpr uint32_t SETUP_WORDS = sizeof(PrimSetup) / 4; // 40
+constexpr uint32_t REGION_PITCH = 33;                   // words per tile row in shared memory (+1: bank skew)
+constexpr uint32_t REGION_PITCH16 = REGION_PITCH * 2;   // same, in pixels
 
 struct alignas(16) RasterShared
 {
-  uint32_t tile[TILE_H][TILE_W / 2];           // 4 KiB: the VRAM tile, 2 pixels per word
-  uint32_t list[LIST_CAP];                     // bin: primitive index | strip mask << 16, submission order
-  uint32_t stage[RASTER_WARPS][SETUP_WORDS];   // per-warp copy of the primitive being rasterised
+  uint32_t region[RASTER_WARPS][TILE_H * REGION_PITCH]; // 8 x 4224 B: one 64x32 tile per warp, 2 pixels per word
+  uint32_t list[LIST_CAP];                              // bin: primitive index | region mask << 16, submission order
+  uint32_t stage[RASTER_WARPS][SETUP_WORDS];            // per-warp copy of the primitive being rasterised
   uint32_t warp_count[RASTER_WARPS];
 };
-
-__device__ __forceinline__ uint32_t strip_mask_for(uint32_t rows, uint32_t tile_y0)
-{
-  const uint32_t by0 = rows & 0xFFFFu, cnt = rows >> 16;
-  uint32_t m = 0;
-#pragma unroll
-  for (uint32_t s = 0; s < RASTER_WARPS; s++)
-  {
-    const uint32_t y = tile_y0 + STRIP_H * s;
-    const bool hit = (((y - by0) & (VRAM_H - 1)) < cnt) || (((by0 - y) & (VRAM_H - 1)) < STRIP_H);
-    m |= hit ? (1u << s) : 0u;
-  }
-  return m;
-}
 
 struct PixelCtx
 {
@@ -119,67 +110,109 @@ __device__ __forceinline__ uint32_t set_half(uint32_t word, uint32_t half, uint3
   return half ? ((word & 0x0000FFFFu) | (value << 16)) : ((word & 0xFFFF0000u) | (value & 0xFFFFu));
 }
 
-// A warp applies one primitive to its strip (rows strip_y0 .. strip_y0+3, columns tile_x0 .. tile_x0+63).
-__device__ __forceinline__ void raster_prim_on_strip(const PrimSetup& s, uint32_t* __restrict__ strip, uint32_t tile_x0,
-                                                     uint32_t strip_y0, const uint16_t* vram, const uint16_t* clut_pool_inst,
-                                                     const uint16_t* __restrict__ payload, uint32_t lane)
+__device__ __forceinline__ uint32_t warp_inclusive_scan(uint32_t v, uint32_t lane)
+{
+#pragma unroll
+  for (uint32_t o = 1; o < 32; o <<= 1)
+  {
+    const uint32_t n = __shfl_up_sync(0xFFFFFFFFu, v, o);
+    if (lane >= o)
+      v += n;
+  }
+  return v;
+}
+
+// Given the inclusive prefix sums of per-row pixel counts (one row per lane), the row that owns compacted pixel j:
+// the first lane whose inclusive sum exceeds j.  Warp-wide binary search with shuffles; j < total required.
+__device__ __forceinline__ uint32_t row_of_pixel(uint32_t incl, uint32_t j)
+{
+  uint32_t r = 0;
+#pragma unroll
+  for (uint32_t step = 16; step >= 1; step >>= 1)
+  {
+    const uint32_t v = __shfl_sync(0xFFFFFFFFu, incl, r + step - 1);
+    if (v <= j)
+      r += step;
+  }
+  return r & 31u;
+}
+
+// A warp applies one primitive to its tile (rows ry0 .. ry0+31, columns rx0 .. rx0+63), held in shared memory.
+// Triangles and rectangles: lane r works out the span of tile row r (one pass for all 32 rows), the covered pixels of
+// all rows are then compacted (prefix sum) and handed out one per lane, 32 at a time, so small primitives do not
+// leave the warp mostly idle.
+__device__ __forceinline__ void raster_prim_on_region(const PrimSetup& s, uint32_t* __restrict__ region, uint32_t rx0, uint32_t ry0,
+                                                      const uint16_t* vram, const uint16_t* clut_pool_inst,
+                                                      const uint16_t* __restrict__ payload, uint32_t lane)
 {
   PixelCtx ctx;
   ctx.vram = vram;
   ctx.clut_lo = clut_pool_inst + s.clut_lo * CLUT_ENTRIES;
   ctx.clut_hi = clut_pool_inst + s.clut_hi * CLUT_ENTRIES;
-  const int32_t px0 = static_cast<int32_t>(tile_x0 + 2 * lane);
+  uint16_t* region16 = reinterpret_cast<uint16_t*>(region);
+  const int32_t x_min = static_cast<int32_t>(rx0), x_max = static_cast<int32_t>(rx0 + TILE_W);
 
   switch (s.op)
   {
     case OP_TRIANGLE:
     {
-#pragma unroll 1
-      for (uint32_t r = 0; r < STRIP_H; r++)
+      TriRow row;
+      const bool valid = tri_row(s, ry0 + lane, row);
+      const int32_t xs = valid ? imax(row.x_lo, x_min) : 0, xe = valid ? imin(row.x_hi, x_max) : 0;
+      const uint32_t cnt = (xe > xs) ? static_cast<uint32_t>(xe - xs) : 0u;
+      const uint32_t incl = warp_inclusive_scan(cnt, lane);
+      const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+      for (uint32_t base = 0; base < total; base += 32)
       {
-        const uint32_t Y = strip_y0 + r;
-        TriRow row;
-        if (!tri_row(s, Y, row))
-          continue;
-        const bool c0 = px0 >= row.x_lo && px0 < row.x_hi;
-        const bool c1 = (px0 + 1) >= row.x_lo && (px0 + 1) < row.x_hi;
-        if (!(c0 || c1))
-          continue;
-        uint32_t word = strip[r * 32 + lane];
-        uint32_t r0, g0, b0, u0, v0, r1, g1, b1, u1, v1;
-        tri_attrs(s, row, px0, r0, g0, b0, u0, v0);
-        tri_attrs(s, row, px0 + 1, r1, g1, b1, u1, v1);
-        uint32_t lo = word & 0xFFFFu, hi = word >> 16;
-        if (c0)
-          lo = shade_pixel(s, ctx, static_cast<uint32_t>(px0), Y, r0, g0, b0, u0, v0, lo);
-        if (c1)
-          hi = shade_pixel(s, ctx, static_cast<uint32_t>(px0 + 1), Y, r1, g1, b1, u1, v1, hi);
-        strip[r * 32 + lane] = lo | (hi << 16);
+        const uint32_t j = base + lane;
+        const bool active = j < total;
+        const uint32_t r = row_of_pixel(incl, active ? j : 0u);
+        const uint32_t r_incl = __shfl_sync(0xFFFFFFFFu, incl, r), r_cnt = __shfl_sync(0xFFFFFFFFu, cnt, r);
+        TriRow mine;
+        mine.cy = __shfl_sync(0xFFFFFFFFu, row.cy, r);
+        mine.xdelta = __shfl_sync(0xFFFFFFFFu, row.xdelta, r);
+        const int32_t r_xs = __shfl_sync(0xFFFFFFFFu, xs, r);
+        if (active)
+        {
+          const int32_t px = r_xs + static_cast<int32_t>(j - (r_incl - r_cnt));
+          uint32_t cr, cg, cb, cu, cv;
+          tri_attrs(s, mine, px, cr, cg, cb, cu, cv);
+          uint16_t* p = region16 + r * REGION_PITCH16 + (px - x_min);
+          const uint32_t bg = *p;
+          const uint32_t out = shade_pixel(s, ctx, static_cast<uint32_t>(px), ry0 + r, cr, cg, cb, cu, cv, bg);
+          if (out != bg)
+            *p = static_cast<uint16_t>(out);
+        }
       }
     }
     break;
 
     case OP_RECT:
     {
-#pragma unroll 1
-      for (uint32_t r = 0; r < STRIP_H; r++)
+      RectRow row;
+      const bool valid = rect_row(s, ry0 + lane, row);
+      const int32_t xs = valid ? imax(row.x_lo, x_min) : 0, xe = valid ? imin(row.x_hi, x_max) : 0;
+      const uint32_t cnt = (xe > xs) ? static_cast<uint32_t>(xe - xs) : 0u;
+      const uint32_t incl = warp_inclusive_scan(cnt, lane);
+      const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+      for (uint32_t base = 0; base < total; base += 32)
       {
-        const uint32_t Y = strip_y0 + r;
-        RectRow row;
-        if (!rect_row(s, Y, row))
-          continue;
-        const bool c0 = px0 >= row.x_lo && px0 < row.x_hi;
-        const bool c1 = (px0 + 1) >= row.x_lo && (px0 + 1) < row.x_hi;
-        if (!(c0 || c1))
-          continue;
-        const uint32_t word = strip[r * 32 + lane];
-        uint32_t lo = word & 0xFFFFu, hi = word >> 16;
-        const uint32_t ub = s.rect.u0 + static_cast<uint32_t>(px0 - s.rect.x);
-        if (c0)
-          lo = shade_pixel(s, ctx, static_cast<uint32_t>(px0), Y, s.rect.r, s.rect.g, s.rect.b, ub & 0xFFu, row.v, lo);
-        if (c1)
-          hi = shade_pixel(s, ctx, static_cast<uint32_t>(px0 + 1), Y, s.rect.r, s.rect.g, s.rect.b, (ub + 1) & 0xFFu, row.v, hi);
-        strip[r * 32 + lane] = lo | (hi << 16);
+        const uint32_t j = base + lane;
+        const bool active = j < total;
+        const uint32_t r = row_of_pixel(incl, active ? j : 0u);
+        const uint32_t r_incl = __shfl_sync(0xFFFFFFFFu, incl, r), r_cnt = __shfl_sync(0xFFFFFFFFu, cnt, r);
+        const uint32_t r_v = __shfl_sync(0xFFFFFFFFu, row.v, r);
+        const int32_t r_xs = __shfl_sync(0xFFFFFFFFu, xs, r);
+        if (active)
+        {
+          const int32_t px = r_xs + static_cast<int32_t>(j - (r_incl - r_cnt));
+          uint16_t* p = region16 + r * REGION_PITCH16 + (px - x_min);
+          const uint32_t bg = *p;
+          const uint32_t out = shade_pixel(s, ctx, static_cast<uint32_t>(px), ry0 + r, s.rect.r, s.rect.g, s.rect.b,
+                                           (s.rect.u0 + static_cast<uint32_t>(px - s.rect.x)) & 0xFFu, r_v, bg);
+          if (out != bg)
+            *p = static_cast<uint16_t>(out);
+        }
       }
     }
     break;
@@ -188,101 +221,101 @@ __device__ __forceinline__ void raster_prim_on_strip(const PrimSetup& s, uint32_
     {
       if (s.line.x_major)
       {
-        // at most one pixel per column; this lane owns columns px0 and px0+1
+        // at most one pixel per column: lanes take columns lane and lane+32
 #pragma unroll
         for (int h = 0; h < 2; h++)
         {
-          const int32_t px = px0 + h;
+          const int32_t px = x_min + static_cast<int32_t>(lane) + 32 * h;
           LinePixel p;
           if (line_step(s, line_step_for_column(s, px), p) && p.x == px)
           {
             const uint32_t Y = static_cast<uint32_t>(p.y) & (VRAM_H - 1);
-            const uint32_t r = Y - strip_y0;
-            if (r < STRIP_H)
+            const uint32_t r = Y - ry0;
+            if (r < TILE_H)
             {
-              const uint32_t word = strip[r * 32 + lane];
-              const uint32_t bg = h ? (word >> 16) : (word & 0xFFFFu);
-              strip[r * 32 + lane] = set_half(word, h, shade_pixel(s, ctx, static_cast<uint32_t>(px), Y, p.r, p.g, p.b, 0, 0, bg));
+              uint16_t* q = region16 + r * REGION_PITCH16 + (px - x_min);
+              *q = static_cast<uint16_t>(shade_pixel(s, ctx, static_cast<uint32_t>(px), Y, p.r, p.g, p.b, 0, 0, *q));
             }
           }
         }
       }
-      else if (lane < STRIP_H)
+      else
       {
-        // at most one pixel per row; lane r owns row r of the strip
-        const uint32_t Y = strip_y0 + lane;
+        // at most one pixel per row: lane r takes tile row r
+        const uint32_t Y = ry0 + lane;
         LinePixel p;
         if (line_step(s, line_step_for_row(s, Y), p) && (static_cast<uint32_t>(p.y) & (VRAM_H - 1)) == Y)
         {
-          const uint32_t col = static_cast<uint32_t>(p.x) - tile_x0;
+          const uint32_t col = static_cast<uint32_t>(p.x) - rx0;
           if (col < TILE_W)
           {
-            const uint32_t word = strip[lane * 32 + (col >> 1)];
-            const uint32_t h = col & 1u;
-            const uint32_t bg = h ? (word >> 16) : (word & 0xFFFFu);
-            strip[lane * 32 + (col >> 1)] = set_half(word, h, shade_pixel(s, ctx, static_cast<uint32_t>(p.x), Y, p.r, p.g, p.b, 0, 0, bg));
+            uint16_t* q = region16 + lane * REGION_PITCH16 + col;
+            *q = static_cast<uint16_t>(shade_pixel(s, ctx, static_cast<uint32_t>(p.x), Y, p.r, p.g, p.b, 0, 0, *q));
           }
         }
       }
-      __syncwarp();
     }
     break;
 
+    // transfers: lane = one word (2 pixels) of the row, rows in a loop
     case OP_FILL:
     {
-#pragma unroll 1
-      for (uint32_t r = 0; r < STRIP_H; r++)
+      const uint32_t px0 = rx0 + 2 * lane;
+#pragma unroll 4
+      for (uint32_t r = 0; r < TILE_H; r++)
       {
-        const uint32_t Y = strip_y0 + r;
-        const bool c0 = fill_covers(s, static_cast<uint32_t>(px0), Y), c1 = fill_covers(s, static_cast<uint32_t>(px0 + 1), Y);
+        const uint32_t Y = ry0 + r;
+        const bool c0 = fill_covers(s, px0, Y), c1 = fill_covers(s, px0 + 1, Y);
         if (!(c0 || c1))
           continue;
-        uint32_t word = strip[r * 32 + lane];
+        uint32_t word = region[r * REGION_PITCH + lane];
         if (c0)
           word = set_half(word, 0, s.fill.color16);
         if (c1)
           word = set_half(word, 1, s.fill.color16);
-        strip[r * 32 + lane] = word;
+        region[r * REGION_PITCH + lane] = word;
       }
     }
     break;
 
     case OP_COPY:
     {
-#pragma unroll 1
-      for (uint32_t r = 0; r < STRIP_H; r++)
+      const uint32_t px0 = rx0 + 2 * lane;
+#pragma unroll 2
+      for (uint32_t r = 0; r < TILE_H; r++)
       {
-        const uint32_t Y = strip_y0 + r;
+        const uint32_t Y = ry0 + r;
         uint32_t s0, s1;
-        const bool c0 = copy_covers(s, static_cast<uint32_t>(px0), Y, s0), c1 = copy_covers(s, static_cast<uint32_t>(px0 + 1), Y, s1);
+        const bool c0 = copy_covers(s, px0, Y, s0), c1 = copy_covers(s, px0 + 1, Y, s1);
         if (!(c0 || c1))
           continue;
-        uint32_t word = strip[r * 32 + lane];
+        uint32_t word = region[r * REGION_PITCH + lane];
         if (c0)
           word = set_half(word, 0, transfer_write(s, static_cast<uint16_t>(word), __ldg(vram + s0)));
         if (c1)
           word = set_half(word, 1, transfer_write(s, static_cast<uint16_t>(word >> 16), __ldg(vram + s1)));
-        strip[r * 32 + lane] = word;
+        region[r * REGION_PITCH + lane] = word;
       }
     }
     break;
 
     case OP_UPLOAD:
     {
-#pragma unroll 1
-      for (uint32_t r = 0; r < STRIP_H; r++)
+      const uint32_t px0 = rx0 + 2 * lane;
+#pragma unroll 2
+      for (uint32_t r = 0; r < TILE_H; r++)
       {
-        const uint32_t Y = strip_y0 + r;
+        const uint32_t Y = ry0 + r;
         uint32_t p0, p1;
-        const bool c0 = upload_covers(s, static_cast<uint32_t>(px0), Y, p0), c1 = upload_covers(s, static_cast<uint32_t>(px0 + 1), Y, p1);
+        const bool c0 = upload_covers(s, px0, Y, p0), c1 = upload_covers(s, px0 + 1, Y, p1);
         if (!(c0 || c1))
           continue;
-        uint32_t word = strip[r * 32 + lane];
+        uint32_t word = region[r * REGION_PITCH + lane];
         if (c0)
           word = set_half(word, 0, transfer_write(s, static_cast<uint16_t>(word), __ldg(payload + p0)));
         if (c1)
           word = set_half(word, 1, transfer_write(s, static_cast<uint16_t>(word >> 16), __ldg(payload + p1)));
-        strip[r * 32 + lane] = word;
+        region[r * REGION_PITCH + lane] = word;
       }
     }
     break;
@@ -505,20 +538,16 @@ __global__ void __launch_bounds__(RASTER_THREADS) raster_kernel(const WaveItem* 
     return;
   }
 
-  const uint32_t tx = blockIdx.x & (TILES_X - 1), ty = blockIdx.x / TILES_X;
-  const uint32_t tile_x0 = tx * TILE_W, tile_y0 = ty * TILE_H;
-  const uint32_t tile_bit = (1u << tx) | (1u << (16 + ty));
+  // CTA block (bx, by) of 4x2 tiles; warp w owns tile (4*bx + (w & 3), 2*by + (w >> 2))
+  const uint32_t bx = blockIdx.x % CTAS_X, by = blockIdx.x / CTAS_X;
   const uint32_t n_cmds = it.cmd_end - it.cmd_begin;
-
-  // 128-bit tile load/store mapping: thread t moves 8 pixels: row t/8, columns (t%8)*8 .. +7
-  const uint32_t ld_row = threadIdx.x >> 3, ld_col = (threadIdx.x & 7u) * 8u;
-  uint4* gtile = reinterpret_cast<uint4*>(vram + (tile_y0 + ld_row) * VRAM_W + tile_x0 + ld_col);
-  uint4* stile = reinterpret_cast<uint4*>(&sh.tile[ld_row][ld_col / 2]);
-
-  bool loaded = false;
-  uint32_t list_n = 0;
-  uint32_t* strip = &sh.tile[warp * STRIP_H][0];
+  const uint32_t rx0 = (bx * CTA_TILES_X + (warp & 3u)) * TILE_W, ry0 = (by * CTA_TILES_Y + (warp >> 2)) * TILE_H;
+  uint32_t* region = sh.region[warp];
+  uint32_t* gword = reinterpret_cast<uint32_t*>(vram + ry0 * VRAM_W + rx0) + lane; // this lane's word of tile row 0
   const PrimSetup& staged = *reinterpret_cast<const PrimSetup*>(sh.stage[warp]);
+
+  bool loaded = false; // warp-uniform: this warp's tile is in shared memory
+  uint32_t list_n = 0;
 
   for (uint32_t base = 0; base < n_cmds; base += RASTER_THREADS)
   {
@@ -528,14 +557,11 @@ __global__ void __launch_bounds__(RASTER_THREADS) raster_kernel(const WaveItem* 
     bool hit = false;
     if (i < n_cmds)
     {
-      const uint2 b = __ldg(reinterpret_cast<const uint2*>(bins) + it.cmd_begin + i);
-      hit = (b.x & tile_bit) == tile_bit;
-      if (hit)
-      {
-        const uint32_t sm = strip_mask_for(b.y, tile_y0);
-        entry = i | (sm << 16);
-        hit = sm != 0;
-      }
+      const uint32_t m = __ldg(reinterpret_cast<const uint32_t*>(bins) + it.cmd_begin + i);
+      const uint32_t cols = (m >> (bx * CTA_TILES_X)) & 0xFu, rows = (m >> (16 + by * CTA_TILES_Y)) & 0x3u;
+      const uint32_t regmask = ((rows & 1u) ? cols : 0u) | ((rows & 2u) ? (cols << 4) : 0u);
+      hit = regmask != 0;
+      entry = i | (regmask << 16);
     }
     const uint32_t bal = __ballot_sync(0xFFFFFFFFu, hit);
     if (lane == 0)
@@ -555,34 +581,60 @@ __global__ void __launch_bounds__(RASTER_THREADS) raster_kernel(const WaveItem* 
     list_n += total;
     const bool last = (base + RASTER_THREADS) >= n_cmds;
     const bool run = list_n > 0 && (last || (list_n + RASTER_THREADS) > LIST_CAP);
-    if (run && !loaded)
-    {
-      *stile = *gtile;
-      loaded = true;
-    }
     __syncthreads();
     if (!run)
       continue;
 
-    // ---- raster: every warp walks the bin in order over its own strip ----
-    for (uint32_t e = 0; e < list_n; e++)
+    // ---- raster: every warp walks the bin in order over its own tile; no CTA-wide sync inside ----
+    uint32_t e = 0;
+    // find this warp's first entry and prefetch its setup record
+    while (e < list_n && !((sh.list[e] >> (16 + warp)) & 1u))
+      e++;
+    uint32_t w0 = 0, w1 = 0;
+    if (e < list_n)
     {
-      const uint32_t ent = sh.list[e];
-      if (!((ent >> (16 + warp)) & 1u))
-        continue;
-      const uint32_t* src = reinterpret_cast<const uint32_t*>(setups + it.cmd_begin + (ent & 0xFFFFu));
-      sh.stage[warp][lane] = __ldg(src + lane);
+      const uint32_t* src = reinterpret_cast<const uint32_t*>(setups + it.cmd_begin + (sh.list[e] & 0xFFFFu));
+      w0 = __ldg(src + lane);
       if (lane < SETUP_WORDS - 32)
-        sh.stage[warp][32 + lane] = __ldg(src + 32 + lane);
+        w1 = __ldg(src + 32 + lane);
+    }
+    while (e < list_n)
+    {
+      sh.stage[warp][lane] = w0;
+      if (lane < SETUP_WORDS - 32)
+        sh.stage[warp][32 + lane] = w1;
+      // next entry of this warp: issue its loads now, they complete while this primitive is rasterised
+      uint32_t en = e + 1;
+      while (en < list_n && !((sh.list[en] >> (16 + warp)) & 1u))
+        en++;
+      if (en < list_n)
+      {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(setups + it.cmd_begin + (sh.list[en] & 0xFFFFu));
+        w0 = __ldg(src + lane);
+        if (lane < SETUP_WORDS - 32)
+          w1 = __ldg(src + 32 + lane);
+      }
+      if (!loaded)
+      {
+#pragma unroll 8
+        for (uint32_t r = 0; r < TILE_H; r++)
+          region[r * REGION_PITCH + lane] = gword[r * (VRAM_W / 2)];
+        loaded = true;
+      }
       __syncwarp();
-      raster_prim_on_strip(staged, strip, tile_x0, tile_y0 + warp * STRIP_H, vram, cluts, payload, lane);
+      raster_prim_on_region(staged, region, rx0, ry0, vram, cluts, payload, lane);
       __syncwarp();
+      e = en;
     }
     list_n = 0;
     __syncthreads();
   }
   if (loaded)
-    *gtile = *stile;
+  {
+#pragma unroll 8
+    for (uint32_t r = 0; r < TILE_H; r++)
+      gword[r * (VRAM_W / 2)] = region[r * REGION_PITCH + lane];
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ hash
@@ -705,7 +757,7 @@ cudaError_t launch_raster(const WaveItem* items, uint32_t n_items, const PrimSet
   for (uint32_t off = 0; off < n_items; off += 32768)
   {
     const uint32_t n = (n_items - off) < 32768u ? (n_items - off) : 32768u;
-    raster_kernel<<<dim3(NUM_TILES, n), RASTER_THREADS, 0, st>>>(items + off, setups, bins, vram_pool, clut_pool, payload, clut_slots);
+    raster_kernel<<<dim3(CTAS_PER_INSTANCE, n), RASTER_THREADS, 0, st>>>(items + off, setups, bins, vram_pool, clut_pool, payload, clut_slots);
   }
   return cudaGetLastError();
 }

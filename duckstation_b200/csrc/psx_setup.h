@@ -60,7 +60,6 @@ PSX_HD void set_bins(PrimSetup& s, BinInfo& b, int32_t x0, int32_t x1, uint32_t 
   }
   const uint32_t rowmask = tile_rowmask(s.by0, s.bycount);
   b.tilemask = (colmask && rowmask) ? (colmask | (rowmask << 16)) : 0u;
-  b.rows = static_cast<uint32_t>(s.by0) | (static_cast<uint32_t>(s.bycount) << 16);
 }
 
 PSX_HD void set_nop(PrimSetup& s, BinInfo& b)
@@ -71,7 +70,6 @@ PSX_HD void set_nop(PrimSetup& s, BinInfo& b)
   s.by0 = 0;
   s.bycount = 0;
   b.tilemask = 0;
-  b.rows = 0;
 }
 
 PSX_HD int64_t makefp_xy(int32_t x) // inl:1463

@@ -27,7 +27,11 @@ constexpr uint32_t TILE_W = 64, TILE_H = 32;         // one CTA owns one tile (4
 constexpr uint32_t TILES_X = VRAM_W / TILE_W;        // 16
 constexpr uint32_t TILES_Y = VRAM_H / TILE_H;        // 16
 constexpr uint32_t NUM_TILES = TILES_X * TILES_Y;    // 256
-constexpr uint32_t STRIP_H = 4;                      // one warp owns a 64x4 strip of the tile
+// Raster kernel geometry: one warp owns one 64x32 tile ("region"); a CTA of 8 warps owns a 256x64 block of 4x2 tiles.
+constexpr uint32_t CTA_TILES_X = 4, CTA_TILES_Y = 2;
+constexpr uint32_t CTAS_X = TILES_X / CTA_TILES_X;   // 4
+constexpr uint32_t CTAS_Y = TILES_Y / CTA_TILES_Y;   // 8
+constexpr uint32_t CTAS_PER_INSTANCE = CTAS_X * CTAS_Y; // 32
 constexpr uint32_t CLUT_ENTRIES = 256;
 
 enum PackedOp : uint8_t
@@ -210,8 +214,7 @@ static_assert(sizeof(PrimSetup) == 160, "PrimSetup must be 160 bytes");
 // Binning words produced by setup, read by every tile CTA of the epoch.
 struct BinInfo
 {
-  uint32_t tilemask; // bits 0-15: tile columns touched, bits 16-31: tile rows touched
-  uint32_t rows;     // by0 | bycount << 16
+  uint32_t tilemask; // bits 0-15: 64-px tile columns touched, bits 16-31: 32-row tile rows touched
 };
 
 PSX_HD int32_t sext11(int32_t v)

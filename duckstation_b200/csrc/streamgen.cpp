@@ -600,8 +600,8 @@ void gen_config4(Builder& b, Rng& r, uint32_t n)
   const TexLayout L{512, 0, 256, 256};
   b.fill(0, 0, 512, 511, r.next());
   noise_upload(b, r, 512, 0, 256, 256);
-  b.set_area(0, 0, 511, 511);
-  const MixParams P{0, 0, 512, 512, 20, 8, 24, 70, 20, true};
+  b.set_area(0, 0, 511, 510); // rows 0..510 == the cleared rows, so a re-run starts from the same pixels
+  const MixParams P{0, 0, 512, 511, 29, 8, 24, 70, 20, true};
   for (uint32_t i = 0; i < n; i++)
     emit_mix_prim(b, r, L, P, false);
 }
