@@ -80,3 +80,16 @@ FULL_SIZE = {
     5: (5, 1, 60, 1500),
 }
 BATCH_INSTANCES = 4096
+
+
+def make_update_display(left: int, top: int, width: int, height: int, *, is24: bool = False, X: int | None = None,
+                        interlaced: bool = False, field: bool = False, interleaved: bool = False,
+                        disabled: bool = False) -> bytes:
+    """One GPUBackendUpdateDisplayCommand record (64 bytes; layout include/psxgpu_wire.h psx_update_display)."""
+    flags = ((1 if interlaced else 0) | (2 if field else 0) | (4 if interleaved else 0) | (0x10 if is24 else 0) |
+             (0x20 if disabled else 0) | 0x40)
+    x = left if X is None else X
+    rec = struct.pack("<IB3x8HfHBB32x", 64, CMD_UPDATE_DISPLAY, width, height, 0, 0, left, top, width, height, 1.0, x, 0,
+                      flags)
+    assert len(rec) == 64
+    return rec

@@ -1,0 +1,87 @@
+"""The C-ABI shared library loads without a GPU and exports every symbol include/psxgpu.h declares; the wire-format
+mirror has the reference's layout; creating a context without a CUDA device fails loudly (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+import struct
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "psxgpu.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(psxgpu_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = C.CDLL(os.path.join(ROOT, "duckstation_b200", "libpsxgpu.so"))
+    names = _declared_symbols()
+    assert len(names) >= 20
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+    from duckstation_b200 import _lib
+
+    assert set(_lib.EXPORTS) == set(names)
+    assert lib.psxgpu_abi_version() == 1
+
+
+def test_product_library_does_not_link_the_oracle():
+    """The product path must not route through oracle/: no psxo_/psxref_ symbols, no dependency on those libraries."""
+    import subprocess
+
+    lib = os.path.join(ROOT, "duckstation_b200", "libpsxgpu.so")
+    syms = subprocess.run(["nm", "-D", lib], capture_output=True, text=True, check=True).stdout
+    assert "psxo_" not in syms and "psxref_" not in syms and "hostsim_" not in syms
+    deps = subprocess.run(["ldd", lib], capture_output=True, text=True, check=True).stdout
+    assert "psxoracle" not in deps and "psxref" not in deps
+    for f in os.listdir(os.path.join(ROOT, "duckstation_b200")):
+        if f.endswith(".py"):
+            src = open(os.path.join(ROOT, "duckstation_b200", f)).read()
+            assert "oracle" not in src.replace("parity oracle", "").replace("(gcc; test infrastructure)", "") or f == "build.py", f
+
+
+def test_create_without_gpu_fails_loudly():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from duckstation_b200 import Context, PsxGpuError
+
+    with pytest.raises(PsxGpuError):
+        Context(1)
+
+
+def test_null_arguments_are_rejected():
+    lib = C.CDLL(os.path.join(ROOT, "duckstation_b200", "libpsxgpu.so"))
+    lib.psxgpu_flush.argtypes = [C.c_void_p]
+    lib.psxgpu_create.argtypes = [C.c_int, C.c_uint32, C.c_void_p, C.c_void_p]
+    assert lib.psxgpu_flush(None) == -1
+    assert lib.psxgpu_create(0, 1, None, None) == -1
+    assert lib.psxgpu_create(0, 0, None, C.byref(C.c_void_p())) == -1
+
+
+def test_generator_records_have_the_reference_layout():
+    """Sizes probed from the reference headers (pinned by static_asserts in oracle/ref_build/ref_harness.cpp)."""
+    from duckstation_b200 import streams
+
+    s = streams.generate(3, 1, 400, 0)
+    seen = {}
+    for typ, off, size in streams.iter_records(s):
+        assert size % 16 == 0
+        seen.setdefault(typ, []).append((off, size))
+    # polygon: 20-byte header + 16 bytes per vertex
+    for off, size in seen[22]:
+        nv = struct.unpack_from("<H", s, off + 10)[0]
+        assert nv in (3, 4) and size == ((20 + 16 * nv + 15) & ~15)
+    for off, size in seen[24]:  # rectangle
+        assert size == 48
+    for off, size in seen[25]:  # line: 12 bytes per vertex, vertex pairs
+        nv = struct.unpack_from("<H", s, off + 10)[0]
+        assert nv % 2 == 0 and size == ((20 + 12 * nv + 15) & ~15)
+    for off, size in seen[17]:  # upload: 18-byte head + w*h pixels
+        w, h = struct.unpack_from("<HH", s, off + 12)
+        assert size == ((18 + 2 * w * h + 15) & ~15)
+    assert {16, 18, 19, 20} <= set(seen)  # fill, copy, drawing area, CLUT

@@ -1,0 +1,112 @@
+"""Host logic without a GPU: the encoder, the hazard/epoch splitter, the CLUT snapshot cache and the closed-form
+setup / coverage maths (the same headers the CUDA kernels compile), executed by tests/hostsim with the kernels'
+execution model and compared with the oracle."""
+import struct
+
+import numpy as np
+import pytest
+
+from duckstation_b200 import streams
+from tests.helpers import HostSim, Oracle, describe_diff
+
+
+@pytest.fixture(scope="module")
+def oracle():
+    return Oracle()
+
+
+@pytest.fixture(scope="module")
+def sim():
+    return HostSim()
+
+
+CASES = [(1, 3, 4000, 0), (2, 2, 5000, 0), (3, 2, 4000, 0), (4, 17, 2000, 0), (5, 4, 8, 300)] + \
+        [(0, s, 2000, f) for s in (31, 32) for f in (0, 1, 2, 3)]
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: "cfg{}-seed{}-n{}-f{}".format(*c))
+def test_hostsim_matches_oracle(oracle, sim, case):
+    s = streams.generate(*case)
+    got, want = sim.render(s), oracle.render(s)
+    assert np.array_equal(got, want), describe_diff(got, want)
+
+
+def test_modulation_crop(oracle, sim):
+    s = streams.generate(2, 3, 2000, 0)
+    assert np.array_equal(sim.render(s, True), oracle.render(s, True))
+    assert not np.array_equal(oracle.render(s, True), oracle.render(s, False))
+
+
+def test_empty_stream(oracle, sim):
+    assert not sim.render(b"").any()
+    assert sim.stats()["epochs"] == 0
+
+
+def test_malformed_stream_rejected(sim):
+    bad = struct.pack("<IB3x", 12, 22) + b"\0" * 4  # size not a multiple of 4 past the header rule / truncated payload
+    with pytest.raises(ValueError):
+        sim.render(bad[:10])
+
+
+# ---- epoch splitter behaviour (stats come from the encoder) ----
+def _rec(fmt, typ, *vals):
+    body = struct.pack(fmt, *vals)
+    size = (8 + len(body) + 15) & ~15
+    return struct.pack("<IB3x", size, typ) + body + b"\0" * (size - 8 - len(body))
+
+
+def _area(l, t, r, b):
+    return _rec("<4I", 19, l, t, r, b)
+
+
+def _rect(x, y, w, h, color=0x808080, textured=False, page_x=0, u=0, v=0, mode=2):
+    flags0 = 0x10 if textured else 0
+    draw_mode = (page_x & 15) | (mode << 7)
+    return _rec("<BBHHH4BHHH2xiiI", 24, flags0, 0, 1, draw_mode, 0, 0xFF, 0xFF, 0, 0, w, h, u | (v << 8), x, y, color)
+
+
+def _fill(x, y, w, h, color):
+    return _rec("<4HIBB", 16, x, y, w, h, color, 0, 0)
+
+
+def _copy(sx, sy, dx, dy, w, h):
+    return _rec("<6HBB", 18, sx, sy, dx, dy, w, h, 0, 0)
+
+
+def test_disjoint_draws_share_one_epoch(sim):
+    s = _area(0, 0, 1023, 511) + b"".join(_rect(16 * i, 8 * i, 40, 40) for i in range(20))
+    sim.render(s)
+    assert sim.stats()["epochs"] == 1
+
+
+def test_render_to_texture_forces_a_cut(oracle, sim):
+    # draw into page 8 (x = 512..), then sample page 8: RAW; then draw over page 8 again while it was sampled: WAR
+    s = (_area(0, 0, 1023, 511) + _fill(512, 0, 64, 64, 0x123456) + _rect(520, 8, 30, 30, 0xFFFFFF) +
+         _rect(10, 10, 40, 40, textured=True, page_x=8) + _rect(530, 4, 20, 20, 0x0000FF) + _rect(100, 100, 16, 16))
+    got = sim.render(s)
+    st = sim.stats()
+    assert st["cuts_raw"] == 1 and st["cuts_war"] == 1 and st["epochs"] == 3
+    assert np.array_equal(got, oracle.render(s))
+
+
+def test_self_sampling_goes_serial(oracle, sim):
+    s = _area(0, 0, 1023, 511) + _fill(0, 0, 256, 256, 0x336699) + _rect(3, 0, 200, 100, textured=True, page_x=0)
+    got = sim.render(s)
+    assert sim.stats()["serial_self_sampling"] == 1
+    assert np.array_equal(got, oracle.render(s))
+
+
+def test_overlapping_copy_goes_serial(oracle, sim):
+    noise = streams.generate(0, 5, 0, 0)  # just the noise upload of the fuzz generator
+    s = noise + _copy(100, 100, 104, 110, 200, 150) + _copy(1000, 500, 300, 200, 60, 40) + _copy(0, 0, 600, 300, 64, 64)
+    got = sim.render(s)
+    assert sim.stats()["serial_copy"] == 1
+    assert np.array_equal(got, oracle.render(s))
+
+
+def test_clut_cache_reuses_snapshots(sim):
+    s = streams.generate(4, 3, 2000, 0)
+    sim.render(s)
+    st = sim.stats()
+    assert st["epochs"] == 2  # clear + atlas upload | all primitives
+    assert st["clut_cache_hits"] > 10 * st["clut_ops"]
