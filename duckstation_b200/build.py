@@ -53,7 +53,7 @@ def build_product(force: bool = False) -> str:
     deps = srcs + [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [
         os.path.join(ROOT, "include", "psxgpu.h"), os.path.join(ROOT, "include", "psxgpu_wire.h")]
     if force or _newer(out, deps):
-        _run([_nvcc(), *NVCC_FLAGS, "-o", out, *srcs])
+        _run([_nvcc(), *NVCC_FLAGS, *os.environ.get("PSX_NVCC_EXTRA", "").split(), "-o", out, *srcs])
     return out
 
 

@@ -134,7 +134,7 @@ struct psxgpu_ctx
     bool valid = false;
     uint32_t n_cmds = 0;
     std::vector<uint32_t> wave_off; // wave k = items [wave_off[k], wave_off[k+1])
-    std::vector<uint8_t> wave_has_clut;
+    std::vector<uint8_t> wave_has_clut, wave_has_tiled, wave_has_serial;
   } staged;
 
   std::unordered_map<uint32_t, std::vector<uint16_t>> shadow;
@@ -249,10 +249,20 @@ int run_device(psxgpu_ctx* ctx)
     }
     if (prof)
       CK(cudaEventRecord(ctx->ev_raster[ctx->ev_raster_used++], ctx->stream), "event record");
-    CK(launch_raster(items + off, cnt, static_cast<const PrimSetup*>(ctx->d_setups.p), static_cast<const BinInfo*>(ctx->d_bins.p),
-                     ctx->d_vram, ctx->d_clut, static_cast<const uint16_t*>(ctx->d_payload.p), ctx->clut_slots, ctx->stream),
-       "raster_kernel");
-    ctx->counters.kernel_launches += (cnt + 32767) / 32768;
+    if (S.wave_has_tiled[k])
+    {
+      CK(launch_raster(items + off, cnt, static_cast<const PrimSetup*>(ctx->d_setups.p), static_cast<const BinInfo*>(ctx->d_bins.p),
+                       ctx->d_vram, ctx->d_clut, static_cast<const uint16_t*>(ctx->d_payload.p), ctx->clut_slots, ctx->stream),
+         "raster_kernel");
+      ctx->counters.kernel_launches += (cnt + 32767) / 32768;
+    }
+    if (S.wave_has_serial[k])
+    {
+      CK(launch_serial(items + off, cnt, static_cast<const PrimSetup*>(ctx->d_setups.p), ctx->d_vram, ctx->d_clut,
+                       static_cast<const uint16_t*>(ctx->d_payload.p), ctx->clut_slots, ctx->stream),
+         "serial_kernel");
+      ctx->counters.kernel_launches++;
+    }
     if (prof)
       CK(cudaEventRecord(ctx->ev_raster[ctx->ev_raster_used++], ctx->stream), "event record");
   }
@@ -325,10 +335,12 @@ int do_flush(psxgpu_ctx* ctx)
   auto& S = ctx->staged;
   S.wave_off.assign(1, 0);
   S.wave_has_clut.clear();
+  S.wave_has_tiled.clear();
+  S.wave_has_serial.clear();
   uint32_t n_items = 0;
   for (size_t k = 0; k < max_epochs; k++)
   {
-    uint8_t has_clut = 0;
+    uint8_t has_clut = 0, has_tiled = 0, has_serial = 0;
     for (uint32_t w = 0; w < nw; w++)
     {
       const Encoder& e = ctx->enc[work[w]];
@@ -343,10 +355,19 @@ int do_flush(psxgpu_ctx* ctx)
       it.clut_begin = static_cast<uint32_t>(clut_base[w] + ep.clut_begin);
       it.clut_end = static_cast<uint32_t>(clut_base[w] + ep.clut_end);
       has_clut |= (it.clut_end > it.clut_begin) ? 1 : 0;
+      if (it.cmd_end > it.cmd_begin)
+      {
+        if (ep.kind == EPOCH_TILED)
+          has_tiled = 1;
+        else
+          has_serial = 1;
+      }
       hi[n_items++] = it;
     }
     S.wave_off.push_back(n_items);
     S.wave_has_clut.push_back(has_clut);
+    S.wave_has_tiled.push_back(has_tiled);
+    S.wave_has_serial.push_back(has_serial);
   }
   S.n_cmds = static_cast<uint32_t>(n_cmds);
   S.valid = true;

@@ -2,15 +2,16 @@
 //
 //   setup_kernel    one thread per primitive: PackedCmd -> PrimSetup + BinInfo (all divisions happen here)
 //   clut_kernel     CLUT snapshot pass of an epoch wave (reference: UpdateCLUT, gpu_sw_rasterizer.cpp:43-66)
-//   raster_kernel   one CTA per (instance, 256x64 block of VRAM = 4x2 tiles of 64x32): bins the epoch's primitives
-//                   for its block in submission order (warp ballots); each of its 8 warps owns one tile, staged
-//                   in shared memory, and walks the bin in order with no CTA-wide barrier.  Per primitive the
-//                   32 lanes compute the 32 row spans in one pass, a warp prefix sum compacts the covered
-//                   pixels and they are shaded 32 at a time (one pixel per lane), so small primitives keep the
-//                   lanes busy.  Tiles are read/written as coalesced 128-byte rows.  Texels and CLUT entries
-//                   come from global memory through the read-only path (L1/L2 resident).
-//                   Epochs of a serial kind (self-sampling primitive, aliasing copy, mask-checked upload tail)
-//                   are executed by one CTA in the reference's own order.
+//   raster_kernel   one warp (= one CTA of 32 threads) per (instance, 64x32 VRAM tile): bins the epoch's
+//                   primitives for its tile in submission order (ballot + popc), stages the tile in shared
+//                   memory and walks the bin in order; no block-level barrier exists, so the hardware CTA
+//                   scheduler balances tiles and 32 CTAs stay resident per SM.  Per primitive the 32 lanes
+//                   compute the 32 row spans in one pass, a warp prefix sum compacts the covered pixels and
+//                   they are shaded 32 at a time (one pixel per lane), so small primitives keep the lanes
+//                   busy.  Tiles are read/written as coalesced 128-byte rows.  Texels and CLUT entries come
+//                   from global memory through the read-only path (L1/L2 resident).
+//   serial_kernel   epochs of a serial kind (self-sampling primitive, aliasing copy, mask-checked upload tail):
+//                   one CTA each, in the reference's own order.
 //   hash_kernel     vramhash64 per instance
 //   scanout_kernel  15-bit / 24-bit display read-out (reference: CopyOut15Bit / CopyOut24Bit, gpu_sw.cpp:230-356)
 //
@@ -69,20 +70,19 @@ __global__ void __launch_bounds__(256) clut_kernel(const WaveItem* __restrict__ 
 }
 
 // ------------------------------------------------------------------------------------------------ raster
-constexpr int RASTER_THREADS = 256;
-constexpr int RASTER_WARPS = RASTER_THREADS / 32;
-static_assert(RASTER_WARPS == CTA_TILES_X * CTA_TILES_Y, "one warp per tile of the CTA block");
-constexpr uint32_t LIST_CAP = 1024;
+constexpr int SERIAL_THREADS = 256;                     // serial_kernel: one CTA per serial epoch
+constexpr int SERIAL_WARPS = SERIAL_THREADS / 32;
+constexpr uint32_t LIST_CAP = 512;                      // per-tile bin capacity between raster phases
 constexpr uint32_t SETUP_WORDS = sizeof(PrimSetup) / 4; // 40
 constexpr uint32_t REGION_PITCH = 33;                   // words per tile row in shared memory (+1: bank skew)
 constexpr uint32_t REGION_PITCH16 = REGION_PITCH * 2;   // same, in pixels
 
+// raster_kernel: one warp == one CTA == one 64x32 tile.  5.4 KiB of shared memory, so 32 CTAs fit an SM.
 struct alignas(16) RasterShared
 {
-  uint32_t region[RASTER_WARPS][TILE_H * REGION_PITCH]; // 8 x 4224 B: one 64x32 tile per warp, 2 pixels per word
-  uint32_t list[LIST_CAP];                              // bin: primitive index | region mask << 16, submission order
-  uint32_t stage[RASTER_WARPS][SETUP_WORDS];            // per-warp copy of the primitive being rasterised
-  uint32_t warp_count[RASTER_WARPS];
+  uint32_t region[TILE_H * REGION_PITCH]; // 4224 B: the tile, 2 pixels per word
+  uint32_t stage[SETUP_WORDS];            // the primitive being rasterised
+  uint16_t list[LIST_CAP];                // bin: primitive indices (relative to the epoch), submission order
 };
 
 struct PixelCtx
@@ -92,17 +92,29 @@ struct PixelCtx
   const uint16_t* clut_hi;
 };
 
+// ShadeState straight from the first words of a staged PrimSetup (see the field order in psx_types.h).
+__device__ __forceinline__ ShadeState shade_state_from_words(const uint32_t* w)
+{
+  const uint32_t w0 = w[0], w1 = w[1];
+  ShadeState st;
+  st.flags = (w0 >> 8) & 0xFFFFu;                     // flags0 | flags1 << 8
+  st.modes = (w0 >> 24) | (((w1 >> 5) & 3u) << 8);    // texmode | transparency mode << 8
+  st.window = w[2];
+  st.texbase = w[7];
+  return st;
+}
+
 // One pixel through the pipeline.  bg = current value; returns the new value.
-__device__ __forceinline__ uint32_t shade_pixel(const PrimSetup& s, const PixelCtx& ctx, uint32_t px, uint32_t Y, uint32_t r,
+__device__ __forceinline__ uint32_t shade_pixel(const ShadeState& st, const PixelCtx& ctx, uint32_t px, uint32_t Y, uint32_t r,
                                                 uint32_t g, uint32_t b, uint32_t u, uint32_t v, uint32_t bg)
 {
   uint16_t texel = 0;
-  if (s.flags0 & F_TEXTURE)
-    texel = fetch_texel<false>(s, ctx.vram, ctx.clut_lo, ctx.clut_hi, u, v);
+  if (st.flags & F_TEXTURE)
+    texel = fetch_texel<false>(st, ctx.vram, ctx.clut_lo, ctx.clut_hi, u, v);
   uint16_t colour;
-  if (!shade_colour(s, px, Y, r, g, b, texel, colour))
+  if (!shade_colour(st, px, Y, r, g, b, texel, colour))
     return bg;
-  return blend_mask(s, static_cast<uint16_t>(bg), colour);
+  return blend_mask(st, static_cast<uint16_t>(bg), colour);
 }
 
 __device__ __forceinline__ uint32_t set_half(uint32_t word, uint32_t half, uint32_t value)
@@ -137,85 +149,156 @@ __device__ __forceinline__ uint32_t row_of_pixel(uint32_t incl, uint32_t j)
   return r & 31u;
 }
 
+// Triangle on one tile.  Lane r works out the span of tile row r (one pass for all 32 rows); the covered pixels of all
+// rows are compacted with a prefix sum and shaded 32 at a time, one per lane.  What a pixel lane needs from its row
+// lane travels by shuffle: the column offset (+ raw-x delta) in one word and the per-row interpolant bases.
+template<bool kShaded, bool kTextured>
+__device__ __forceinline__ void raster_triangle(const PrimSetup& s, const ShadeState st, const PixelCtx& ctx,
+                                                uint16_t* __restrict__ region16, int32_t x_min, uint32_t ry0, uint32_t lane)
+{
+  TriRow row;
+  const bool valid = tri_row(s, ry0 + lane, row);
+  const int32_t xs = valid ? imax(row.x_lo, x_min) : 0, xe = valid ? imin(row.x_hi, x_min + static_cast<int32_t>(TILE_W)) : 0;
+  const uint32_t cnt = (xe > xs) ? static_cast<uint32_t>(xe - xs) : 0u;
+  const uint32_t incl = warp_inclusive_scan(cnt, lane);
+  const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+  if (total == 0)
+    return;
+  const auto& T = s.tri;
+  // px = xoff + j ; x_raw = px + xdelta (xdelta is a multiple of 2048 that fits 16 bits, xoff is within +-2048)
+  const uint32_t packed = (static_cast<uint32_t>(xs - static_cast<int32_t>(incl - cnt)) & 0xFFFFu) | (static_cast<uint32_t>(row.xdelta) << 16);
+  const uint32_t cy = static_cast<uint32_t>(row.cy);
+  uint32_t rb_r = 0, rb_g = 0, rb_b = 0, rb_u = 0, rb_v = 0, dx_r = 0, dx_g = 0, dx_b = 0, dx_u = 0, dx_v = 0;
+  uint32_t flat = 0;
+  if (kShaded)
+  {
+    rb_r = T.base[0] + T.ddy[0] * cy;
+    rb_g = T.base[1] + T.ddy[1] * cy;
+    rb_b = T.base[2] + T.ddy[2] * cy;
+    dx_r = T.ddx[0];
+    dx_g = T.ddx[1];
+    dx_b = T.ddx[2];
+  }
+  else
+  {
+    flat = static_cast<uint32_t>(T.flat_r) | (static_cast<uint32_t>(T.flat_g) << 8) | (static_cast<uint32_t>(T.flat_b) << 16);
+  }
+  if (kTextured)
+  {
+    rb_u = T.base[3] + T.ddy[3] * cy;
+    rb_v = T.base[4] + T.ddy[4] * cy;
+    dx_u = T.ddx[3];
+    dx_v = T.ddx[4];
+  }
+  for (uint32_t base = 0; base < total; base += 32)
+  {
+    const uint32_t j = base + lane;
+    const bool active = j < total;
+    const uint32_t r = row_of_pixel(incl, active ? j : 0u);
+    const uint32_t pk = __shfl_sync(0xFFFFFFFFu, packed, r);
+    const int32_t px = static_cast<int32_t>(static_cast<int16_t>(pk & 0xFFFFu)) + static_cast<int32_t>(j);
+    const uint32_t xr = static_cast<uint32_t>(px + (static_cast<int32_t>(pk) >> 16));
+    uint32_t cr, cg, cb, cu = 0, cv = 0;
+    if (kShaded)
+    {
+      cr = (__shfl_sync(0xFFFFFFFFu, rb_r, r) + dx_r * xr) >> 24;
+      cg = (__shfl_sync(0xFFFFFFFFu, rb_g, r) + dx_g * xr) >> 24;
+      cb = (__shfl_sync(0xFFFFFFFFu, rb_b, r) + dx_b * xr) >> 24;
+    }
+    else
+    {
+      cr = flat & 0xFFu;
+      cg = (flat >> 8) & 0xFFu;
+      cb = flat >> 16;
+    }
+    if (kTextured)
+    {
+      cu = (__shfl_sync(0xFFFFFFFFu, rb_u, r) + dx_u * xr) >> 24;
+      cv = (__shfl_sync(0xFFFFFFFFu, rb_v, r) + dx_v * xr) >> 24;
+    }
+    if (active)
+    {
+      uint16_t* p = region16 + r * REGION_PITCH16 + (px - x_min);
+      const uint32_t bg = *p;
+      const uint32_t out = shade_pixel(st, ctx, static_cast<uint32_t>(px), ry0 + r, cr, cg, cb, cu, cv, bg);
+      if (out != bg)
+        *p = static_cast<uint16_t>(out);
+    }
+  }
+}
+
+__device__ __forceinline__ void raster_rect(const PrimSetup& s, const ShadeState st, const PixelCtx& ctx,
+                                            uint16_t* __restrict__ region16, int32_t x_min, uint32_t ry0, uint32_t lane)
+{
+  RectRow row;
+  const bool valid = rect_row(s, ry0 + lane, row);
+  const int32_t xs = valid ? imax(row.x_lo, x_min) : 0, xe = valid ? imin(row.x_hi, x_min + static_cast<int32_t>(TILE_W)) : 0;
+  const uint32_t cnt = (xe > xs) ? static_cast<uint32_t>(xe - xs) : 0u;
+  const uint32_t incl = warp_inclusive_scan(cnt, lane);
+  const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+  if (total == 0)
+    return;
+  const uint32_t packed = (static_cast<uint32_t>(xs - static_cast<int32_t>(incl - cnt)) & 0xFFFFu) | (row.v << 16);
+  const uint32_t cr = s.rect.r, cg = s.rect.g, cb = s.rect.b;
+  const uint32_t ubias = static_cast<uint32_t>(s.rect.u0) - static_cast<uint32_t>(static_cast<int32_t>(s.rect.x));
+  for (uint32_t base = 0; base < total; base += 32)
+  {
+    const uint32_t j = base + lane;
+    const bool active = j < total;
+    const uint32_t r = row_of_pixel(incl, active ? j : 0u);
+    const uint32_t pk = __shfl_sync(0xFFFFFFFFu, packed, r);
+    const int32_t px = static_cast<int32_t>(static_cast<int16_t>(pk & 0xFFFFu)) + static_cast<int32_t>(j);
+    if (active)
+    {
+      uint16_t* p = region16 + r * REGION_PITCH16 + (px - x_min);
+      const uint32_t bg = *p;
+      const uint32_t out = shade_pixel(st, ctx, static_cast<uint32_t>(px), ry0 + r, cr, cg, cb,
+                                       (ubias + static_cast<uint32_t>(px)) & 0xFFu, pk >> 16, bg);
+      if (out != bg)
+        *p = static_cast<uint16_t>(out);
+    }
+  }
+}
+
 // A warp applies one primitive to its tile (rows ry0 .. ry0+31, columns rx0 .. rx0+63), held in shared memory.
-// Triangles and rectangles: lane r works out the span of tile row r (one pass for all 32 rows), the covered pixels of
-// all rows are then compacted (prefix sum) and handed out one per lane, 32 at a time, so small primitives do not
-// leave the warp mostly idle.
 __device__ __forceinline__ void raster_prim_on_region(const PrimSetup& s, uint32_t* __restrict__ region, uint32_t rx0, uint32_t ry0,
                                                       const uint16_t* vram, const uint16_t* clut_pool_inst,
                                                       const uint16_t* __restrict__ payload, uint32_t lane)
 {
+  const uint32_t* words = reinterpret_cast<const uint32_t*>(&s);
+  const uint32_t w0 = words[0], w1 = words[1];
+  const uint32_t op = w0 & 0xFFu;
+  const ShadeState st = shade_state_from_words(words);
   PixelCtx ctx;
   ctx.vram = vram;
-  ctx.clut_lo = clut_pool_inst + s.clut_lo * CLUT_ENTRIES;
-  ctx.clut_hi = clut_pool_inst + s.clut_hi * CLUT_ENTRIES;
+  ctx.clut_lo = clut_pool_inst + ((w1 >> 16) & 0xFFu) * CLUT_ENTRIES;
+  ctx.clut_hi = clut_pool_inst + (w1 >> 24) * CLUT_ENTRIES;
   uint16_t* region16 = reinterpret_cast<uint16_t*>(region);
-  const int32_t x_min = static_cast<int32_t>(rx0), x_max = static_cast<int32_t>(rx0 + TILE_W);
+  const int32_t x_min = static_cast<int32_t>(rx0);
 
-  switch (s.op)
+  switch (op)
   {
     case OP_TRIANGLE:
     {
-      TriRow row;
-      const bool valid = tri_row(s, ry0 + lane, row);
-      const int32_t xs = valid ? imax(row.x_lo, x_min) : 0, xe = valid ? imin(row.x_hi, x_max) : 0;
-      const uint32_t cnt = (xe > xs) ? static_cast<uint32_t>(xe - xs) : 0u;
-      const uint32_t incl = warp_inclusive_scan(cnt, lane);
-      const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
-      for (uint32_t base = 0; base < total; base += 32)
+      const bool shaded = (st.flags & F_SHADED) != 0, textured = (st.flags & F_TEXTURE) != 0;
+      if (textured)
       {
-        const uint32_t j = base + lane;
-        const bool active = j < total;
-        const uint32_t r = row_of_pixel(incl, active ? j : 0u);
-        const uint32_t r_incl = __shfl_sync(0xFFFFFFFFu, incl, r), r_cnt = __shfl_sync(0xFFFFFFFFu, cnt, r);
-        TriRow mine;
-        mine.cy = __shfl_sync(0xFFFFFFFFu, row.cy, r);
-        mine.xdelta = __shfl_sync(0xFFFFFFFFu, row.xdelta, r);
-        const int32_t r_xs = __shfl_sync(0xFFFFFFFFu, xs, r);
-        if (active)
-        {
-          const int32_t px = r_xs + static_cast<int32_t>(j - (r_incl - r_cnt));
-          uint32_t cr, cg, cb, cu, cv;
-          tri_attrs(s, mine, px, cr, cg, cb, cu, cv);
-          uint16_t* p = region16 + r * REGION_PITCH16 + (px - x_min);
-          const uint32_t bg = *p;
-          const uint32_t out = shade_pixel(s, ctx, static_cast<uint32_t>(px), ry0 + r, cr, cg, cb, cu, cv, bg);
-          if (out != bg)
-            *p = static_cast<uint16_t>(out);
-        }
+        if (shaded)
+          raster_triangle<true, true>(s, st, ctx, region16, x_min, ry0, lane);
+        else
+          raster_triangle<false, true>(s, st, ctx, region16, x_min, ry0, lane);
+      }
+      else
+      {
+        if (shaded)
+          raster_triangle<true, false>(s, st, ctx, region16, x_min, ry0, lane);
+        else
+          raster_triangle<false, false>(s, st, ctx, region16, x_min, ry0, lane);
       }
     }
     break;
 
-    case OP_RECT:
-    {
-      RectRow row;
-      const bool valid = rect_row(s, ry0 + lane, row);
-      const int32_t xs = valid ? imax(row.x_lo, x_min) : 0, xe = valid ? imin(row.x_hi, x_max) : 0;
-      const uint32_t cnt = (xe > xs) ? static_cast<uint32_t>(xe - xs) : 0u;
-      const uint32_t incl = warp_inclusive_scan(cnt, lane);
-      const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
-      for (uint32_t base = 0; base < total; base += 32)
-      {
-        const uint32_t j = base + lane;
-        const bool active = j < total;
-        const uint32_t r = row_of_pixel(incl, active ? j : 0u);
-        const uint32_t r_incl = __shfl_sync(0xFFFFFFFFu, incl, r), r_cnt = __shfl_sync(0xFFFFFFFFu, cnt, r);
-        const uint32_t r_v = __shfl_sync(0xFFFFFFFFu, row.v, r);
-        const int32_t r_xs = __shfl_sync(0xFFFFFFFFu, xs, r);
-        if (active)
-        {
-          const int32_t px = r_xs + static_cast<int32_t>(j - (r_incl - r_cnt));
-          uint16_t* p = region16 + r * REGION_PITCH16 + (px - x_min);
-          const uint32_t bg = *p;
-          const uint32_t out = shade_pixel(s, ctx, static_cast<uint32_t>(px), ry0 + r, s.rect.r, s.rect.g, s.rect.b,
-                                           (s.rect.u0 + static_cast<uint32_t>(px - s.rect.x)) & 0xFFu, r_v, bg);
-          if (out != bg)
-            *p = static_cast<uint16_t>(out);
-        }
-      }
-    }
-    break;
+    case OP_RECT: raster_rect(s, st, ctx, region16, x_min, ry0, lane); break;
 
     case OP_LINE:
     {
@@ -234,7 +317,7 @@ __device__ __forceinline__ void raster_prim_on_region(const PrimSetup& s, uint32
             if (r < TILE_H)
             {
               uint16_t* q = region16 + r * REGION_PITCH16 + (px - x_min);
-              *q = static_cast<uint16_t>(shade_pixel(s, ctx, static_cast<uint32_t>(px), Y, p.r, p.g, p.b, 0, 0, *q));
+              *q = static_cast<uint16_t>(shade_pixel(st, ctx, static_cast<uint32_t>(px), Y, p.r, p.g, p.b, 0, 0, *q));
             }
           }
         }
@@ -250,7 +333,7 @@ __device__ __forceinline__ void raster_prim_on_region(const PrimSetup& s, uint32
           if (col < TILE_W)
           {
             uint16_t* q = region16 + lane * REGION_PITCH16 + col;
-            *q = static_cast<uint16_t>(shade_pixel(s, ctx, static_cast<uint32_t>(p.x), Y, p.r, p.g, p.b, 0, 0, *q));
+            *q = static_cast<uint16_t>(shade_pixel(st, ctx, static_cast<uint32_t>(p.x), Y, p.r, p.g, p.b, 0, 0, *q));
           }
         }
       }
@@ -336,20 +419,21 @@ __device__ void serial_self_sampling(const PrimSetup& s, uint16_t* vram, const u
   const uint16_t* clut_lo = clut_pool_inst + s.clut_lo * CLUT_ENTRIES;
   const uint16_t* clut_hi = clut_pool_inst + s.clut_hi * CLUT_ENTRIES;
   volatile uint16_t* vv = vram;
+  const ShadeState st = make_shade_state(s);
 
   auto group = [&](int32_t x0, uint32_t Y, bool active, uint32_t r, uint32_t g, uint32_t b, uint32_t u, uint32_t v) {
     uint16_t texel = 0;
     if (active)
-      texel = fetch_texel<true>(s, vram, clut_lo, clut_hi, u, v);
+      texel = fetch_texel<true>(st, vram, clut_lo, clut_hi, u, v);
     __syncwarp();
     if (active)
     {
       uint16_t colour;
       const uint32_t px = static_cast<uint32_t>(x0) + lane;
-      if (shade_colour(s, px, Y, r, g, b, texel, colour))
+      if (shade_colour(st, px, Y, r, g, b, texel, colour))
       {
         const uint16_t bg = vv[Y * VRAM_W + px];
-        vv[Y * VRAM_W + px] = blend_mask(s, bg, colour);
+        vv[Y * VRAM_W + px] = blend_mask(st, bg, colour);
       }
     }
     __syncwarp();
@@ -411,18 +495,18 @@ __device__ void serial_copy_rows(uint16_t* vram, uint32_t sx, uint32_t sy, uint3
   for (uint32_t r = 0; r < h; r++)
   {
     const uint32_t srow = ((sy + r) & (VRAM_H - 1)) * VRAM_W, drow = ((dy + r) & (VRAM_H - 1)) * VRAM_W;
-    uint16_t px[VRAM_W / RASTER_THREADS];
+    uint16_t px[VRAM_W / SERIAL_THREADS];
 #pragma unroll
-    for (uint32_t k = 0; k < VRAM_W / RASTER_THREADS; k++)
+    for (uint32_t k = 0; k < VRAM_W / SERIAL_THREADS; k++)
     {
-      const uint32_t c = k * RASTER_THREADS + threadIdx.x;
+      const uint32_t c = k * SERIAL_THREADS + threadIdx.x;
       px[k] = (c < w) ? vv[srow + ((sx + c) & (VRAM_W - 1))] : uint16_t(0);
     }
     __syncthreads();
 #pragma unroll
-    for (uint32_t k = 0; k < VRAM_W / RASTER_THREADS; k++)
+    for (uint32_t k = 0; k < VRAM_W / SERIAL_THREADS; k++)
     {
-      const uint32_t c = k * RASTER_THREADS + threadIdx.x;
+      const uint32_t c = k * SERIAL_THREADS + threadIdx.x;
       if (c < w)
       {
         const uint32_t a = drow + ((dx + c) & (VRAM_W - 1));
@@ -475,7 +559,7 @@ __device__ void serial_upload_masked(const PrimSetup& s, uint16_t* vram, const u
   for (uint32_t r = 0; r < U.h; r++)
   {
     const uint32_t drow = ((U.y + r) & (VRAM_H - 1)) * VRAM_W;
-    for (uint32_t base = 0; base < U.w; base += RASTER_THREADS)
+    for (uint32_t base = 0; base < U.w; base += SERIAL_THREADS)
     {
       const uint32_t c = base + threadIdx.x;
       const bool in = c < U.w;
@@ -490,7 +574,7 @@ __device__ void serial_upload_masked(const PrimSetup& s, uint16_t* vram, const u
       uint32_t before = __popc(bal & ((1u << lane) - 1u));
       uint32_t total = 0;
 #pragma unroll
-      for (uint32_t k = 0; k < RASTER_WARPS; k++)
+      for (uint32_t k = 0; k < SERIAL_WARPS; k++)
       {
         const uint32_t n = warp_count[k];
         before += (k < warp) ? n : 0u;
@@ -504,136 +588,103 @@ __device__ void serial_upload_masked(const PrimSetup& s, uint16_t* vram, const u
   }
 }
 
-__global__ void __launch_bounds__(RASTER_THREADS) raster_kernel(const WaveItem* __restrict__ items,
-                                                                const PrimSetup* __restrict__ setups,
-                                                                const BinInfo* __restrict__ bins, uint16_t* __restrict__ vram_pool,
-                                                                const uint16_t* __restrict__ clut_pool,
+// Epochs of a serial kind: one CTA per item, everything else returns at once.
+__global__ void __launch_bounds__(SERIAL_THREADS) serial_kernel(const WaveItem* __restrict__ items, const PrimSetup* __restrict__ setups,
+                                                                uint16_t* vram_pool, const uint16_t* __restrict__ clut_pool,
                                                                 const uint16_t* __restrict__ payload, uint32_t clut_slots)
 {
-  __shared__ RasterShared sh;
-  const WaveItem it = items[blockIdx.y];
-  if (it.cmd_begin == it.cmd_end)
+  __shared__ alignas(16) uint32_t stage[SETUP_WORDS];
+  __shared__ uint32_t warp_count[SERIAL_WARPS];
+  const WaveItem it = items[blockIdx.x];
+  if (it.kind == EPOCH_TILED || it.cmd_begin == it.cmd_end)
     return;
   uint16_t* vram = vram_pool + static_cast<size_t>(it.instance) * VRAM_PIXELS;
   const uint16_t* cluts = clut_pool + static_cast<size_t>(it.instance) * clut_slots * CLUT_ENTRIES;
-  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-
-  if (it.kind != EPOCH_TILED)
-  {
-    if (blockIdx.x != 0)
-      return;
-    // stage the single primitive in shared memory for all threads
-    if (threadIdx.x < SETUP_WORDS)
-      sh.stage[0][threadIdx.x] = reinterpret_cast<const uint32_t*>(setups + it.cmd_begin)[threadIdx.x];
-    __syncthreads();
-    const PrimSetup& s = *reinterpret_cast<const PrimSetup*>(sh.stage[0]);
-    if (s.op == OP_NOP)
-      return;
-    if (it.kind == EPOCH_SELF_SAMPLING)
-      serial_self_sampling(s, vram, cluts);
-    else if (it.kind == EPOCH_COPY_OVERLAP)
-      serial_copy(s, vram);
-    else
-      serial_upload_masked(s, vram, payload, sh.warp_count);
+  if (threadIdx.x < SETUP_WORDS)
+    stage[threadIdx.x] = reinterpret_cast<const uint32_t*>(setups + it.cmd_begin)[threadIdx.x];
+  __syncthreads();
+  const PrimSetup& s = *reinterpret_cast<const PrimSetup*>(stage);
+  if (s.op == OP_NOP)
     return;
-  }
+  if (it.kind == EPOCH_SELF_SAMPLING)
+    serial_self_sampling(s, vram, cluts);
+  else if (it.kind == EPOCH_COPY_OVERLAP)
+    serial_copy(s, vram);
+  else
+    serial_upload_masked(s, vram, payload, warp_count);
+}
 
-  // CTA block (bx, by) of 4x2 tiles; warp w owns tile (4*bx + (w & 3), 2*by + (w >> 2))
-  const uint32_t bx = blockIdx.x % CTAS_X, by = blockIdx.x / CTAS_X;
+// One warp per (instance, tile).  No block-level barrier anywhere: the hardware CTA scheduler balances tiles.
+__global__ void __launch_bounds__(32, 32) raster_kernel(const WaveItem* __restrict__ items, const PrimSetup* __restrict__ setups,
+                                                        const BinInfo* __restrict__ bins, uint16_t* __restrict__ vram_pool,
+                                                        const uint16_t* __restrict__ clut_pool,
+                                                        const uint16_t* __restrict__ payload, uint32_t clut_slots)
+{
+  __shared__ RasterShared sh;
+  const WaveItem it = items[blockIdx.y];
+  if (it.kind != EPOCH_TILED || it.cmd_begin == it.cmd_end)
+    return;
+  uint16_t* vram = vram_pool + static_cast<size_t>(it.instance) * VRAM_PIXELS;
+  const uint16_t* cluts = clut_pool + static_cast<size_t>(it.instance) * clut_slots * CLUT_ENTRIES;
+  const uint32_t lane = threadIdx.x;
+  const uint32_t tx = blockIdx.x % TILES_X, ty = blockIdx.x / TILES_X;
+  const uint32_t rx0 = tx * TILE_W, ry0 = ty * TILE_H;
+  const uint32_t tile_bits = (1u << tx) | (1u << (16 + ty));
   const uint32_t n_cmds = it.cmd_end - it.cmd_begin;
-  const uint32_t rx0 = (bx * CTA_TILES_X + (warp & 3u)) * TILE_W, ry0 = (by * CTA_TILES_Y + (warp >> 2)) * TILE_H;
-  uint32_t* region = sh.region[warp];
+  const uint32_t* bin_words = reinterpret_cast<const uint32_t*>(bins) + it.cmd_begin;
   uint32_t* gword = reinterpret_cast<uint32_t*>(vram + ry0 * VRAM_W + rx0) + lane; // this lane's word of tile row 0
-  const PrimSetup& staged = *reinterpret_cast<const PrimSetup*>(sh.stage[warp]);
+  const PrimSetup& staged = *reinterpret_cast<const PrimSetup*>(sh.stage);
 
-  bool loaded = false; // warp-uniform: this warp's tile is in shared memory
+  bool loaded = false;
   uint32_t list_n = 0;
-
-  for (uint32_t base = 0; base < n_cmds; base += RASTER_THREADS)
+  for (uint32_t base = 0; base < n_cmds; base += 32)
   {
-    // ---- bin: one primitive per thread, order kept by ballot + prefix ----
-    const uint32_t i = base + threadIdx.x;
-    uint32_t entry = 0;
-    bool hit = false;
-    if (i < n_cmds)
-    {
-      const uint32_t m = __ldg(reinterpret_cast<const uint32_t*>(bins) + it.cmd_begin + i);
-      const uint32_t cols = (m >> (bx * CTA_TILES_X)) & 0xFu, rows = (m >> (16 + by * CTA_TILES_Y)) & 0x3u;
-      const uint32_t regmask = ((rows & 1u) ? cols : 0u) | ((rows & 2u) ? (cols << 4) : 0u);
-      hit = regmask != 0;
-      entry = i | (regmask << 16);
-    }
+    // ---- bin: 32 primitives per step, order kept by ballot + popc ----
+    const uint32_t i = base + lane;
+    const bool hit = (i < n_cmds) && ((__ldg(bin_words + i) & tile_bits) == tile_bits);
     const uint32_t bal = __ballot_sync(0xFFFFFFFFu, hit);
-    if (lane == 0)
-      sh.warp_count[warp] = __popc(bal);
-    __syncthreads();
-    uint32_t pos = list_n + __popc(bal & ((1u << lane) - 1u));
-    uint32_t total = 0;
-#pragma unroll
-    for (uint32_t k = 0; k < RASTER_WARPS; k++)
-    {
-      const uint32_t n = sh.warp_count[k];
-      pos += (k < warp) ? n : 0u;
-      total += n;
-    }
     if (hit)
-      sh.list[pos] = entry;
-    list_n += total;
-    const bool last = (base + RASTER_THREADS) >= n_cmds;
-    const bool run = list_n > 0 && (last || (list_n + RASTER_THREADS) > LIST_CAP);
-    __syncthreads();
-    if (!run)
+      sh.list[list_n + __popc(bal & ((1u << lane) - 1u))] = static_cast<uint16_t>(i);
+    list_n += __popc(bal);
+    const bool last = (base + 32) >= n_cmds;
+    if (!(list_n > 0 && (last || (list_n + 32) > LIST_CAP)))
       continue;
+    __syncwarp();
 
-    // ---- raster: every warp walks the bin in order over its own tile; no CTA-wide sync inside ----
-    uint32_t e = 0;
-    // find this warp's first entry and prefetch its setup record
-    while (e < list_n && !((sh.list[e] >> (16 + warp)) & 1u))
-      e++;
-    uint32_t w0 = 0, w1 = 0;
-    if (e < list_n)
+    // ---- raster: walk the bin in order ----
+    if (!loaded)
     {
-      const uint32_t* src = reinterpret_cast<const uint32_t*>(setups + it.cmd_begin + (sh.list[e] & 0xFFFFu));
-      w0 = __ldg(src + lane);
-      if (lane < SETUP_WORDS - 32)
-        w1 = __ldg(src + 32 + lane);
+#pragma unroll 8
+      for (uint32_t r = 0; r < TILE_H; r++)
+        sh.region[r * REGION_PITCH + lane] = gword[r * (VRAM_W / 2)];
+      loaded = true;
     }
-    while (e < list_n)
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(setups + it.cmd_begin + sh.list[0]);
+    uint32_t w0 = __ldg(src + lane), w1 = (lane < SETUP_WORDS - 32) ? __ldg(src + 32 + lane) : 0u;
+    for (uint32_t e = 0; e < list_n; e++)
     {
-      sh.stage[warp][lane] = w0;
+      sh.stage[lane] = w0;
       if (lane < SETUP_WORDS - 32)
-        sh.stage[warp][32 + lane] = w1;
-      // next entry of this warp: issue its loads now, they complete while this primitive is rasterised
-      uint32_t en = e + 1;
-      while (en < list_n && !((sh.list[en] >> (16 + warp)) & 1u))
-        en++;
-      if (en < list_n)
+        sh.stage[32 + lane] = w1;
+      if (e + 1 < list_n)
       {
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(setups + it.cmd_begin + (sh.list[en] & 0xFFFFu));
+        // next primitive: issue its loads now, they complete while this one is rasterised
+        src = reinterpret_cast<const uint32_t*>(setups + it.cmd_begin + sh.list[e + 1]);
         w0 = __ldg(src + lane);
         if (lane < SETUP_WORDS - 32)
           w1 = __ldg(src + 32 + lane);
       }
-      if (!loaded)
-      {
-#pragma unroll 8
-        for (uint32_t r = 0; r < TILE_H; r++)
-          region[r * REGION_PITCH + lane] = gword[r * (VRAM_W / 2)];
-        loaded = true;
-      }
       __syncwarp();
-      raster_prim_on_region(staged, region, rx0, ry0, vram, cluts, payload, lane);
+      raster_prim_on_region(staged, sh.region, rx0, ry0, vram, cluts, payload, lane);
       __syncwarp();
-      e = en;
     }
     list_n = 0;
-    __syncthreads();
   }
   if (loaded)
   {
 #pragma unroll 8
     for (uint32_t r = 0; r < TILE_H; r++)
-      gword[r * (VRAM_W / 2)] = region[r * REGION_PITCH + lane];
+      gword[r * (VRAM_W / 2)] = sh.region[r * REGION_PITCH + lane];
   }
 }
 
@@ -757,8 +808,17 @@ cudaError_t launch_raster(const WaveItem* items, uint32_t n_items, const PrimSet
   for (uint32_t off = 0; off < n_items; off += 32768)
   {
     const uint32_t n = (n_items - off) < 32768u ? (n_items - off) : 32768u;
-    raster_kernel<<<dim3(CTAS_PER_INSTANCE, n), RASTER_THREADS, 0, st>>>(items + off, setups, bins, vram_pool, clut_pool, payload, clut_slots);
+    raster_kernel<<<dim3(NUM_TILES, n), 32, 0, st>>>(items + off, setups, bins, vram_pool, clut_pool, payload, clut_slots);
   }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_serial(const WaveItem* items, uint32_t n_items, const PrimSetup* setups, uint16_t* vram_pool,
+                          const uint16_t* clut_pool, const uint16_t* payload, uint32_t clut_slots, cudaStream_t st)
+{
+  if (n_items == 0)
+    return cudaSuccess;
+  serial_kernel<<<n_items, SERIAL_THREADS, 0, st>>>(items, setups, vram_pool, clut_pool, payload, clut_slots);
   return cudaGetLastError();
 }
 

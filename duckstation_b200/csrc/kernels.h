@@ -24,6 +24,8 @@ cudaError_t launch_clut(const WaveItem* items, uint32_t n_items, const ClutOp* o
 cudaError_t launch_raster(const WaveItem* items, uint32_t n_items, const PrimSetup* setups, const BinInfo* bins,
                           uint16_t* vram_pool, const uint16_t* clut_pool, const uint16_t* payload, uint32_t clut_slots,
                           cudaStream_t st);
+cudaError_t launch_serial(const WaveItem* items, uint32_t n_items, const PrimSetup* setups, uint16_t* vram_pool,
+                          const uint16_t* clut_pool, const uint16_t* payload, uint32_t clut_slots, cudaStream_t st);
 cudaError_t launch_hash(const uint16_t* vram_pool, uint32_t first, uint32_t count, unsigned long long* out, cudaStream_t st);
 cudaError_t launch_scanout(const uint16_t* vram, const ScanoutParams& p, uint8_t* out, cudaStream_t st);
 

@@ -35,31 +35,40 @@ PSX_HD uint32_t clamp5(int32_t v)
   return static_cast<uint32_t>(v < 0 ? 0 : (v > 31 ? 31 : v));
 }
 
-// Texture window + page addressing; returns the VRAM pixel index of the texel word and the sub-word shift.
-PSX_HD uint32_t texel_addr(const PrimSetup& s, uint32_t u, uint32_t v, uint32_t& shift, uint32_t& idxmask)
+// Everything the pixel pipeline needs from a primitive, packed into five registers so that the raster kernel can keep
+// it live across its pixel loop (reading it back from the staged record after every shared-memory store is what the
+// compiler would otherwise have to do).
+struct ShadeState
 {
-  u = (u & s.win_and_x) | s.win_or_x;
-  v = (v & s.win_and_y) | s.win_or_y;
-  const uint32_t ty = (s.tex_by + v) & (VRAM_H - 1);
-  uint32_t tx;
-  if (s.texmode == 0)
-  {
-    tx = (s.tex_bx + (u >> 2)) & (VRAM_W - 1);
-    shift = (u & 3u) * 4u;
-    idxmask = 0xFu;
-  }
-  else if (s.texmode == 1)
-  {
-    tx = (s.tex_bx + (u >> 1)) & (VRAM_W - 1);
-    shift = (u & 1u) * 8u;
-    idxmask = 0xFFu;
-  }
-  else
-  {
-    tx = (s.tex_bx + u) & (VRAM_W - 1);
-    shift = 0;
-    idxmask = 0; // direct
-  }
+  uint32_t flags;   // flags0 | flags1 << 8
+  uint32_t modes;   // texmode (0 4-bit, 1 8-bit, 2 direct) | transparency mode << 8
+  uint32_t window;  // and_x | and_y << 8 | or_x << 16 | or_y << 24
+  uint32_t texbase; // page base x | page base y << 16
+};
+
+PSX_HD ShadeState make_shade_state(const PrimSetup& s)
+{
+  ShadeState st;
+  st.flags = static_cast<uint32_t>(s.flags0) | (static_cast<uint32_t>(s.flags1) << 8);
+  st.modes = static_cast<uint32_t>(s.texmode) | (((static_cast<uint32_t>(s.draw_mode) >> 5) & 3u) << 8);
+  st.window = static_cast<uint32_t>(s.win_and_x) | (static_cast<uint32_t>(s.win_and_y) << 8) |
+              (static_cast<uint32_t>(s.win_or_x) << 16) | (static_cast<uint32_t>(s.win_or_y) << 24);
+  st.texbase = static_cast<uint32_t>(s.tex_bx) | (static_cast<uint32_t>(s.tex_by) << 16);
+  return st;
+}
+
+// Texture window + page addressing; returns the VRAM pixel index of the texel word, the sub-word shift and the palette
+// index mask (0 = direct colour).  Branch-free in the texture mode: 4-bit packs 4 indices per word, 8-bit 2, direct 1.
+PSX_HD uint32_t texel_addr(const ShadeState& st, uint32_t u, uint32_t v, uint32_t& shift, uint32_t& idxmask)
+{
+  u = (u & (st.window & 0xFFu)) | ((st.window >> 16) & 0xFFu);
+  v = (v & ((st.window >> 8) & 0xFFu)) | (st.window >> 24);
+  const uint32_t mode = st.modes & 0xFFu;
+  const uint32_t sh = 2u - mode; // log2(texels per VRAM word)
+  const uint32_t ty = ((st.texbase >> 16) + v) & (VRAM_H - 1);
+  const uint32_t tx = ((st.texbase & 0xFFFFu) + (u >> sh)) & (VRAM_W - 1);
+  shift = (u & ((1u << sh) - 1u)) << (2u + mode);
+  idxmask = (mode == 2u) ? 0u : ((1u << (4u << mode)) - 1u);
   return ty * VRAM_W + tx;
 }
 
@@ -68,11 +77,11 @@ PSX_HD uint32_t texel_addr(const PrimSetup& s, uint32_t u, uint32_t v, uint32_t&
 // kLive = the texel word is read from VRAM that this very primitive is writing (self-sampling): the
 // read must then be a coherent (volatile) load instead of going through the read-only path.
 template<bool kLive>
-PSX_HD uint16_t fetch_texel(const PrimSetup& s, const uint16_t* vram, const uint16_t* __restrict__ clut_lo,
+PSX_HD uint16_t fetch_texel(const ShadeState& st, const uint16_t* vram, const uint16_t* __restrict__ clut_lo,
                             const uint16_t* __restrict__ clut_hi, uint32_t u, uint32_t v)
 {
   uint32_t shift, idxmask;
-  const uint32_t a = texel_addr(s, u, v, shift, idxmask);
+  const uint32_t a = texel_addr(st, u, v, shift, idxmask);
   uint16_t w;
   if (kLive)
     w = *reinterpret_cast<const volatile uint16_t*>(vram + a);
@@ -85,26 +94,26 @@ PSX_HD uint16_t fetch_texel(const PrimSetup& s, const uint16_t* vram, const uint
 }
 
 // Colour before blending.  Returns false if the pixel is dropped (texel == 0).
-PSX_HD bool shade_colour(const PrimSetup& s, uint32_t px, uint32_t Y, uint32_t r, uint32_t g, uint32_t b, uint16_t texel,
+PSX_HD bool shade_colour(const ShadeState& st, uint32_t px, uint32_t Y, uint32_t r, uint32_t g, uint32_t b, uint16_t texel,
                          uint16_t& out)
 {
-  const int32_t dv = (s.flags1 & F1_DITHER) ? dither_offset(px, Y) : 0;
-  if (!(s.flags0 & F_TEXTURE))
+  const int32_t dv = (st.flags & (F1_DITHER << 8)) ? dither_offset(px, Y) : 0;
+  if (!(st.flags & F_TEXTURE))
   {
     out = static_cast<uint16_t>(clamp5(static_cast<int32_t>(r) + dv) | (clamp5(static_cast<int32_t>(g) + dv) << 5) |
-                                (clamp5(static_cast<int32_t>(b) + dv) << 10) | ((s.flags0 & F_TRANSP) ? 0x8000u : 0u));
+                                (clamp5(static_cast<int32_t>(b) + dv) << 10) | ((st.flags & F_TRANSP) ? 0x8000u : 0u));
     return true;
   }
   if (texel == 0)
     return false;
-  if (s.flags0 & F_RAW)
+  if (st.flags & F_RAW)
   {
     out = texel;
     return true;
   }
   const uint32_t tr = texel & 31u, tg = (texel >> 5) & 31u, tb = (texel >> 10) & 31u;
   uint32_t cr, cg, cb;
-  if (!(s.flags1 & F1_MOD5))
+  if (!(st.flags & (F1_MOD5 << 8)))
   {
     cr = clamp5(static_cast<int32_t>((tr * r) >> 4) + dv);
     cg = clamp5(static_cast<int32_t>((tg * g) >> 4) + dv);
@@ -121,15 +130,15 @@ PSX_HD bool shade_colour(const PrimSetup& s, uint32_t px, uint32_t Y, uint32_t r
 }
 
 // Blend (if enabled and applicable), mask test, mask set.  Returns the new pixel value (bg if masked).
-PSX_HD uint16_t blend_mask(const PrimSetup& s, uint16_t bg, uint16_t color)
+PSX_HD uint16_t blend_mask(const ShadeState& st, uint16_t bg, uint16_t color)
 {
-  if ((s.flags0 & F_CHECK_MASK) && (bg & 0x8000u))
+  if ((st.flags & F_CHECK_MASK) && (bg & 0x8000u))
     return bg;
-  const bool textured = (s.flags0 & F_TEXTURE) != 0;
-  if ((s.flags0 & F_TRANSP) && ((color & 0x8000u) || !textured))
+  const bool textured = (st.flags & F_TEXTURE) != 0;
+  if ((st.flags & F_TRANSP) && ((color & 0x8000u) || !textured))
   {
     uint32_t bgb = bg, fgb = color;
-    switch ((s.draw_mode >> 5) & 3u)
+    switch ((st.modes >> 8) & 3u)
     {
       case 0:
         bgb |= 0x8000u;
@@ -165,7 +174,7 @@ PSX_HD uint16_t blend_mask(const PrimSetup& s, uint16_t bg, uint16_t color)
     if (!textured)
       color &= 0x7FFFu;
   }
-  return static_cast<uint16_t>(color | ((s.flags0 & F_SET_MASK) ? 0x8000u : 0u));
+  return static_cast<uint16_t>(color | ((st.flags & F_SET_MASK) ? 0x8000u : 0u));
 }
 
 PSX_HD bool interlace_skip(const PrimSetup& s, uint32_t line)

@@ -27,11 +27,7 @@ constexpr uint32_t TILE_W = 64, TILE_H = 32;         // one CTA owns one tile (4
 constexpr uint32_t TILES_X = VRAM_W / TILE_W;        // 16
 constexpr uint32_t TILES_Y = VRAM_H / TILE_H;        // 16
 constexpr uint32_t NUM_TILES = TILES_X * TILES_Y;    // 256
-// Raster kernel geometry: one warp owns one 64x32 tile ("region"); a CTA of 8 warps owns a 256x64 block of 4x2 tiles.
-constexpr uint32_t CTA_TILES_X = 4, CTA_TILES_Y = 2;
-constexpr uint32_t CTAS_X = TILES_X / CTA_TILES_X;   // 4
-constexpr uint32_t CTAS_Y = TILES_Y / CTA_TILES_Y;   // 8
-constexpr uint32_t CTAS_PER_INSTANCE = CTAS_X * CTAS_Y; // 32
+// Raster kernel geometry: one warp (= one CTA) owns one 64x32 tile for the duration of an epoch.
 constexpr uint32_t CLUT_ENTRIES = 256;
 
 enum PackedOp : uint8_t
