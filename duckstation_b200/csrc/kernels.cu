@@ -77,19 +77,19 @@ constexpr uint32_t SETUP_WORDS = sizeof(PrimSetup) / 4; // 40
 constexpr uint32_t REGION_PITCH = 33;                   // words per tile row in shared memory (+1: bank skew)
 constexpr uint32_t REGION_PITCH16 = REGION_PITCH * 2;   // same, in pixels
 
-// raster_kernel: one warp == one CTA == one 64x32 tile.  5.4 KiB of shared memory, so 32 CTAs fit an SM.
+// raster_kernel: one warp == one CTA == one 64x32 tile.  5.9 KiB of shared memory, so 32 CTAs fit an SM.
 struct alignas(16) RasterShared
 {
   uint32_t region[TILE_H * REGION_PITCH]; // 4224 B: the tile, 2 pixels per word
   uint32_t stage[SETUP_WORDS];            // the primitive being rasterised
+  uint16_t clut[CLUT_ENTRIES];            // merged palette of the current primitive (entries 0-15 lo slot, 16-255 hi slot)
   uint16_t list[LIST_CAP];                // bin: primitive indices (relative to the epoch), submission order
 };
 
 struct PixelCtx
 {
   const uint16_t* vram; // this instance's VRAM in global memory (texture / copy source reads)
-  const uint16_t* clut_lo;
-  const uint16_t* clut_hi;
+  const uint16_t* clut; // the primitive's merged 256-entry palette, staged in shared memory
 };
 
 // ShadeState straight from the first words of a staged PrimSetup (see the field order in psx_types.h).
@@ -108,13 +108,13 @@ __device__ __forceinline__ ShadeState shade_state_from_words(const uint32_t* w)
 __device__ __forceinline__ uint32_t shade_pixel(const ShadeState& st, const PixelCtx& ctx, uint32_t px, uint32_t Y, uint32_t r,
                                                 uint32_t g, uint32_t b, uint32_t u, uint32_t v, uint32_t bg)
 {
-  uint16_t texel = 0;
+  uint32_t texel = 0;
   if (st.flags & F_TEXTURE)
-    texel = fetch_texel<false>(st, ctx.vram, ctx.clut_lo, ctx.clut_hi, u, v);
-  uint16_t colour;
+    texel = fetch_texel<false, true>(st, ctx.vram, ctx.clut, ctx.clut, u, v);
+  uint32_t colour;
   if (!shade_colour(st, px, Y, r, g, b, texel, colour))
     return bg;
-  return blend_mask(st, static_cast<uint16_t>(bg), colour);
+  return blend_mask(st, bg, colour);
 }
 
 __device__ __forceinline__ uint32_t set_half(uint32_t word, uint32_t half, uint32_t value)
@@ -261,9 +261,11 @@ __device__ __forceinline__ void raster_rect(const PrimSetup& s, const ShadeState
 }
 
 // A warp applies one primitive to its tile (rows ry0 .. ry0+31, columns rx0 .. rx0+63), held in shared memory.
+// clut_key: which palette (lo slot | hi slot << 8 | depth << 16) currently sits in clut_smem; reloaded on change.
 __device__ __forceinline__ void raster_prim_on_region(const PrimSetup& s, uint32_t* __restrict__ region, uint32_t rx0, uint32_t ry0,
                                                       const uint16_t* vram, const uint16_t* clut_pool_inst,
-                                                      const uint16_t* __restrict__ payload, uint32_t lane)
+                                                      const uint16_t* __restrict__ payload, uint16_t* clut_smem, uint32_t& clut_key,
+                                                      uint32_t lane)
 {
   const uint32_t* words = reinterpret_cast<const uint32_t*>(&s);
   const uint32_t w0 = words[0], w1 = words[1];
@@ -271,8 +273,26 @@ __device__ __forceinline__ void raster_prim_on_region(const PrimSetup& s, uint32
   const ShadeState st = shade_state_from_words(words);
   PixelCtx ctx;
   ctx.vram = vram;
-  ctx.clut_lo = clut_pool_inst + ((w1 >> 16) & 0xFFu) * CLUT_ENTRIES;
-  ctx.clut_hi = clut_pool_inst + (w1 >> 24) * CLUT_ENTRIES;
+  ctx.clut = clut_smem;
+  if ((st.flags & F_TEXTURE) && (st.modes & 0xFFu) < 2u)
+  {
+    // paletted: make sure the merged palette is in shared memory (one coalesced 512-byte read when it changes)
+    const uint32_t lo = (w1 >> 16) & 0xFFu, hi = w1 >> 24, is8 = st.modes & 1u;
+    const uint32_t key = lo | ((is8 ? hi : lo) << 8) | (is8 << 16) | 0x80000000u;
+    if (key != clut_key)
+    {
+      clut_key = key;
+      uint4* dst = reinterpret_cast<uint4*>(clut_smem);
+      if (is8)
+      {
+        dst[lane] = __ldg(reinterpret_cast<const uint4*>(clut_pool_inst + hi * CLUT_ENTRIES) + lane);
+        __syncwarp();
+      }
+      if (lane < 2 && (!is8 || lo != hi))
+        dst[lane] = __ldg(reinterpret_cast<const uint4*>(clut_pool_inst + lo * CLUT_ENTRIES) + lane);
+      __syncwarp();
+    }
+  }
   uint16_t* region16 = reinterpret_cast<uint16_t*>(region);
   const int32_t x_min = static_cast<int32_t>(rx0);
 
@@ -422,18 +442,18 @@ __device__ void serial_self_sampling(const PrimSetup& s, uint16_t* vram, const u
   const ShadeState st = make_shade_state(s);
 
   auto group = [&](int32_t x0, uint32_t Y, bool active, uint32_t r, uint32_t g, uint32_t b, uint32_t u, uint32_t v) {
-    uint16_t texel = 0;
+    uint32_t texel = 0;
     if (active)
       texel = fetch_texel<true>(st, vram, clut_lo, clut_hi, u, v);
     __syncwarp();
     if (active)
     {
-      uint16_t colour;
+      uint32_t colour;
       const uint32_t px = static_cast<uint32_t>(x0) + lane;
       if (shade_colour(st, px, Y, r, g, b, texel, colour))
       {
         const uint16_t bg = vv[Y * VRAM_W + px];
-        vv[Y * VRAM_W + px] = blend_mask(st, bg, colour);
+        vv[Y * VRAM_W + px] = static_cast<uint16_t>(blend_mask(st, bg, colour));
       }
     }
     __syncwarp();
@@ -630,24 +650,50 @@ __global__ void __launch_bounds__(32, 32) raster_kernel(const WaveItem* __restri
   const uint32_t tx = blockIdx.x % TILES_X, ty = blockIdx.x / TILES_X;
   const uint32_t rx0 = tx * TILE_W, ry0 = ty * TILE_H;
   const uint32_t tile_bits = (1u << tx) | (1u << (16 + ty));
-  const uint32_t n_cmds = it.cmd_end - it.cmd_begin;
-  const uint32_t* bin_words = reinterpret_cast<const uint32_t*>(bins) + it.cmd_begin;
   uint32_t* gword = reinterpret_cast<uint32_t*>(vram + ry0 * VRAM_W + rx0) + lane; // this lane's word of tile row 0
   const PrimSetup& staged = *reinterpret_cast<const PrimSetup*>(sh.stage);
 
+  // Binning reads the epoch's BinInfo words 128 at a time: one 128-bit load per lane, the next one in flight.
+  const uint32_t first = it.cmd_begin & ~3u; // 16-byte aligned start; indices below cmd_begin are masked out
+  const uint4* bin4 = reinterpret_cast<const uint4*>(bins) + (first >> 2);
+  const uint32_t n4 = (it.cmd_end - first + 3u) >> 2;
+  uint4 cur = (lane < n4) ? __ldg(bin4 + lane) : make_uint4(0, 0, 0, 0);
+
   bool loaded = false;
+  uint32_t clut_key = 0;
   uint32_t list_n = 0;
-  for (uint32_t base = 0; base < n_cmds; base += 32)
+  for (uint32_t q = 0; q < n4; q += 32)
   {
-    // ---- bin: 32 primitives per step, order kept by ballot + popc ----
-    const uint32_t i = base + lane;
-    const bool hit = (i < n_cmds) && ((__ldg(bin_words + i) & tile_bits) == tile_bits);
-    const uint32_t bal = __ballot_sync(0xFFFFFFFFu, hit);
-    if (hit)
-      sh.list[list_n + __popc(bal & ((1u << lane) - 1u))] = static_cast<uint16_t>(i);
-    list_n += __popc(bal);
-    const bool last = (base + 32) >= n_cmds;
-    if (!(list_n > 0 && (last || (list_n + 32) > LIST_CAP)))
+    const uint32_t qn = q + 32 + lane;
+    const uint4 nxt = (qn < n4) ? __ldg(bin4 + qn) : make_uint4(0, 0, 0, 0);
+    // ---- bin: 4 consecutive primitives per lane, order = (lane, k) ----
+    const uint32_t gi = first + ((q + lane) << 2); // global index of cur.x
+    uint32_t h = 0;
+    h |= ((cur.x & tile_bits) == tile_bits && gi + 0 >= it.cmd_begin && gi + 0 < it.cmd_end) ? 1u : 0u;
+    h |= ((cur.y & tile_bits) == tile_bits && gi + 1 >= it.cmd_begin && gi + 1 < it.cmd_end) ? 2u : 0u;
+    h |= ((cur.z & tile_bits) == tile_bits && gi + 2 >= it.cmd_begin && gi + 2 < it.cmd_end) ? 4u : 0u;
+    h |= ((cur.w & tile_bits) == tile_bits && gi + 3 >= it.cmd_begin && gi + 3 < it.cmd_end) ? 8u : 0u;
+    if (__any_sync(0xFFFFFFFFu, h != 0))
+    {
+      // exclusive prefix of per-lane hit counts via four ballots
+      const uint32_t lt = (1u << lane) - 1u;
+      const uint32_t b0 = __ballot_sync(0xFFFFFFFFu, h & 1u), b1 = __ballot_sync(0xFFFFFFFFu, h & 2u);
+      const uint32_t b2 = __ballot_sync(0xFFFFFFFFu, h & 4u), b3 = __ballot_sync(0xFFFFFFFFu, h & 8u);
+      uint32_t pos = list_n + __popc(b0 & lt) + __popc(b1 & lt) + __popc(b2 & lt) + __popc(b3 & lt);
+      const uint32_t rel = gi - it.cmd_begin;
+      if (h & 1u)
+        sh.list[pos++] = static_cast<uint16_t>(rel);
+      if (h & 2u)
+        sh.list[pos++] = static_cast<uint16_t>(rel + 1);
+      if (h & 4u)
+        sh.list[pos++] = static_cast<uint16_t>(rel + 2);
+      if (h & 8u)
+        sh.list[pos++] = static_cast<uint16_t>(rel + 3);
+      list_n += __popc(b0) + __popc(b1) + __popc(b2) + __popc(b3);
+    }
+    cur = nxt;
+    const bool last = (q + 32) >= n4;
+    if (!(list_n > 0 && (last || (list_n + 128) > LIST_CAP)))
       continue;
     __syncwarp();
 
@@ -675,7 +721,7 @@ __global__ void __launch_bounds__(32, 32) raster_kernel(const WaveItem* __restri
           w1 = __ldg(src + 32 + lane);
       }
       __syncwarp();
-      raster_prim_on_region(staged, sh.region, rx0, ry0, vram, cluts, payload, lane);
+      raster_prim_on_region(staged, sh.region, rx0, ry0, vram, cluts, payload, sh.clut, clut_key, lane);
       __syncwarp();
     }
     list_n = 0;

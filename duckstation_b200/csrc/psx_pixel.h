@@ -76,13 +76,13 @@ PSX_HD uint32_t texel_addr(const ShadeState& st, uint32_t u, uint32_t v, uint32_
 // a 4-bit UpdateCLUT only replaces the first 16 entries of the reference's cache (gpu_sw_rasterizer.cpp:47-51).
 // kLive = the texel word is read from VRAM that this very primitive is writing (self-sampling): the
 // read must then be a coherent (volatile) load instead of going through the read-only path.
-template<bool kLive>
-PSX_HD uint16_t fetch_texel(const ShadeState& st, const uint16_t* vram, const uint16_t* __restrict__ clut_lo,
+template<bool kLive, bool kClutInShared = false>
+PSX_HD uint32_t fetch_texel(const ShadeState& st, const uint16_t* vram, const uint16_t* __restrict__ clut_lo,
                             const uint16_t* __restrict__ clut_hi, uint32_t u, uint32_t v)
 {
   uint32_t shift, idxmask;
   const uint32_t a = texel_addr(st, u, v, shift, idxmask);
-  uint16_t w;
+  uint32_t w;
   if (kLive)
     w = *reinterpret_cast<const volatile uint16_t*>(vram + a);
   else
@@ -90,18 +90,20 @@ PSX_HD uint16_t fetch_texel(const ShadeState& st, const uint16_t* vram, const ui
   if (idxmask == 0)
     return w;
   const uint32_t idx = (w >> shift) & idxmask;
+  if (kClutInShared)
+    return clut_lo[idx]; // the raster kernel stages the merged 256-entry palette in shared memory
   return PSX_LD_TEX((idx < 16u ? clut_lo : clut_hi) + idx);
 }
 
 // Colour before blending.  Returns false if the pixel is dropped (texel == 0).
-PSX_HD bool shade_colour(const ShadeState& st, uint32_t px, uint32_t Y, uint32_t r, uint32_t g, uint32_t b, uint16_t texel,
-                         uint16_t& out)
+PSX_HD bool shade_colour(const ShadeState& st, uint32_t px, uint32_t Y, uint32_t r, uint32_t g, uint32_t b, uint32_t texel,
+                         uint32_t& out)
 {
   const int32_t dv = (st.flags & (F1_DITHER << 8)) ? dither_offset(px, Y) : 0;
   if (!(st.flags & F_TEXTURE))
   {
-    out = static_cast<uint16_t>(clamp5(static_cast<int32_t>(r) + dv) | (clamp5(static_cast<int32_t>(g) + dv) << 5) |
-                                (clamp5(static_cast<int32_t>(b) + dv) << 10) | ((st.flags & F_TRANSP) ? 0x8000u : 0u));
+    out = clamp5(static_cast<int32_t>(r) + dv) | (clamp5(static_cast<int32_t>(g) + dv) << 5) |
+          (clamp5(static_cast<int32_t>(b) + dv) << 10) | ((st.flags & F_TRANSP) ? 0x8000u : 0u);
     return true;
   }
   if (texel == 0)
@@ -125,12 +127,12 @@ PSX_HD bool shade_colour(const ShadeState& st, uint32_t px, uint32_t Y, uint32_t
     cg = clamp5(static_cast<int32_t>((tg * (g >> 3)) >> 1) + dv);
     cb = clamp5(static_cast<int32_t>((tb * (b >> 3)) >> 1) + dv);
   }
-  out = static_cast<uint16_t>(cr | (cg << 5) | (cb << 10) | (texel & 0x8000u));
+  out = cr | (cg << 5) | (cb << 10) | (texel & 0x8000u);
   return true;
 }
 
 // Blend (if enabled and applicable), mask test, mask set.  Returns the new pixel value (bg if masked).
-PSX_HD uint16_t blend_mask(const ShadeState& st, uint16_t bg, uint16_t color)
+PSX_HD uint32_t blend_mask(const ShadeState& st, uint32_t bg, uint32_t color)
 {
   if ((st.flags & F_CHECK_MASK) && (bg & 0x8000u))
     return bg;
@@ -142,14 +144,14 @@ PSX_HD uint16_t blend_mask(const ShadeState& st, uint16_t bg, uint16_t color)
     {
       case 0:
         bgb |= 0x8000u;
-        color = static_cast<uint16_t>(((fgb + bgb) - ((fgb ^ bgb) & 0x0421u)) >> 1);
+        color = (((fgb + bgb) - ((fgb ^ bgb) & 0x0421u)) >> 1) & 0xFFFFu;
         break;
       case 1:
       {
         bgb &= ~0x8000u;
         const uint32_t sum = fgb + bgb;
         const uint32_t carry = (sum - ((fgb ^ bgb) & 0x8421u)) & 0x8420u;
-        color = static_cast<uint16_t>((sum - carry) | (carry - (carry >> 5)));
+        color = ((sum - carry) | (carry - (carry >> 5))) & 0xFFFFu;
       }
       break;
       case 2:
@@ -158,7 +160,7 @@ PSX_HD uint16_t blend_mask(const ShadeState& st, uint16_t bg, uint16_t color)
         fgb &= ~0x8000u;
         const uint32_t diff = bgb - fgb + 0x108420u;
         const uint32_t borrow = (diff - ((bgb ^ fgb) & 0x108420u)) & 0x108420u;
-        color = static_cast<uint16_t>((diff - borrow) & (borrow - (borrow >> 5)));
+        color = ((diff - borrow) & (borrow - (borrow >> 5))) & 0xFFFFu;
       }
       break;
       default:
@@ -167,14 +169,14 @@ PSX_HD uint16_t blend_mask(const ShadeState& st, uint16_t bg, uint16_t color)
         fgb = ((fgb >> 2) & 0x1CE7u) | 0x8000u;
         const uint32_t sum = fgb + bgb;
         const uint32_t carry = (sum - ((fgb ^ bgb) & 0x8421u)) & 0x8420u;
-        color = static_cast<uint16_t>((sum - carry) | (carry - (carry >> 5)));
+        color = ((sum - carry) | (carry - (carry >> 5))) & 0xFFFFu;
       }
       break;
     }
     if (!textured)
       color &= 0x7FFFu;
   }
-  return static_cast<uint16_t>(color | ((st.flags & F_SET_MASK) ? 0x8000u : 0u));
+  return color | ((st.flags & F_SET_MASK) ? 0x8000u : 0u);
 }
 
 PSX_HD bool interlace_skip(const PrimSetup& s, uint32_t line)

@@ -28,14 +28,14 @@ void shade_and_store(const PrimSetup& s, const uint16_t*, uint32_t px, uint32_t 
                      uint32_t u, uint32_t v)
 {
   const ShadeState st = make_shade_state(s);
-  uint16_t texel = 0;
+  uint32_t texel = 0;
   if (s.flags0 & F_TEXTURE)
     texel = fetch_texel<false>(st, g_snap.data(), &g_clut[s.clut_lo * 256], &g_clut[s.clut_hi * 256], u, v);
-  uint16_t colour;
+  uint32_t colour;
   if (!shade_colour(st, px, Y, r, g, b, texel, colour))
     return;
   uint16_t& dst = g_vram[Y * VRAM_W + px];
-  dst = blend_mask(st, dst, colour);
+  dst = static_cast<uint16_t>(blend_mask(st, dst, colour));
 }
 
 void run_tiled_prim(const PrimSetup& s, const uint16_t* payload)
@@ -121,7 +121,7 @@ void shade_group(const PrimSetup& s, const uint16_t*, int32_t x0, uint32_t Y, ui
                  const uint32_t* g, const uint32_t* b, const uint32_t* u, const uint32_t* v)
 {
   const ShadeState st = make_shade_state(s);
-  uint16_t tex[4] = {0, 0, 0, 0};
+  uint32_t tex[4] = {0, 0, 0, 0};
   for (int l = 0; l < 4; l++)
     if ((active >> l) & 1u)
       tex[l] = fetch_texel<true>(st, g_vram.data(), &g_clut[s.clut_lo * 256], &g_clut[s.clut_hi * 256], u[l], v[l]); // LIVE vram
@@ -129,11 +129,11 @@ void shade_group(const PrimSetup& s, const uint16_t*, int32_t x0, uint32_t Y, ui
   {
     if (!((active >> l) & 1u))
       continue;
-    uint16_t colour;
+    uint32_t colour;
     if (!shade_colour(st, static_cast<uint32_t>(x0 + l), Y, r[l], g[l], b[l], tex[l], colour))
       continue;
     uint16_t& dst = g_vram[Y * VRAM_W + static_cast<uint32_t>(x0 + l)];
-    dst = blend_mask(st, dst, colour);
+    dst = static_cast<uint16_t>(blend_mask(st, dst, colour));
   }
 }
 
