@@ -58,6 +58,7 @@ def load() -> C.CDLL:
     lib.psxgpu_flush.argtypes = [P]
     lib.psxgpu_sync.argtypes = [P]
     lib.psxgpu_run_staged.argtypes = [P]
+    lib.psxgpu_set_batch_chunk.argtypes = [P, u32]
     lib.psxgpu_read_vram.argtypes = [P, u32, u32, u32, u32, u32, C.c_void_p, u32]
     lib.psxgpu_shadow_vram.argtypes = [P, u32]
     lib.psxgpu_shadow_vram.restype = C.POINTER(C.c_uint16)
@@ -74,7 +75,7 @@ def load() -> C.CDLL:
     lib.psxgpu_get_timing.argtypes = [P, C.POINTER(Timing)]
     lib.psxgpu_get_raster_launch_ms.argtypes = [P, C.POINTER(C.c_float), u32]
     for name in ("psxgpu_create", "psxgpu_submit_wire", "psxgpu_submit_batch", "psxgpu_flush", "psxgpu_sync",
-                 "psxgpu_run_staged", "psxgpu_read_vram", "psxgpu_clear_vram", "psxgpu_load_state",
+                 "psxgpu_run_staged", "psxgpu_set_batch_chunk", "psxgpu_read_vram", "psxgpu_clear_vram", "psxgpu_load_state",
                  "psxgpu_save_state", "psxgpu_scanout", "psxgpu_hash", "psxgpu_hash_device", "psxgpu_get_stats",
                  "psxgpu_reset_stats", "psxgpu_get_timing", "psxgpu_get_raster_launch_ms"):
         getattr(lib, name).restype = C.c_int
@@ -84,7 +85,7 @@ def load() -> C.CDLL:
 
 EXPORTS = (
     "psxgpu_abi_version", "psxgpu_create", "psxgpu_destroy", "psxgpu_last_error", "psxgpu_submit_wire",
-    "psxgpu_submit_batch", "psxgpu_flush", "psxgpu_sync", "psxgpu_run_staged", "psxgpu_read_vram",
+    "psxgpu_submit_batch", "psxgpu_flush", "psxgpu_sync", "psxgpu_run_staged", "psxgpu_set_batch_chunk", "psxgpu_read_vram",
     "psxgpu_shadow_vram", "psxgpu_clear_vram", "psxgpu_load_state", "psxgpu_save_state", "psxgpu_scanout",
     "psxgpu_display", "psxgpu_hash", "psxgpu_hash_device", "psxgpu_get_stats", "psxgpu_reset_stats",
     "psxgpu_get_timing", "psxgpu_get_raster_launch_ms",

@@ -94,6 +94,9 @@ class Context:
     def sync(self) -> None:
         self._check(self._lib.psxgpu_sync(self._ctx), "psxgpu_sync")
 
+    def set_batch_chunk(self, instances_per_chunk: int) -> None:
+        self._check(self._lib.psxgpu_set_batch_chunk(self._ctx, instances_per_chunk), "psxgpu_set_batch_chunk")
+
     def run_staged(self) -> None:
         self._check(self._lib.psxgpu_run_staged(self._ctx), "psxgpu_run_staged")
 

@@ -126,25 +126,45 @@ struct psxgpu_ctx
   std::vector<Encoder> enc;
   std::vector<uint8_t> dirty;
 
-  PinnedBuf h_cmds, h_payload, h_clutops, h_items, h_misc;
-  DevBuf d_cmds, d_setups, d_bins, d_payload, d_clutops, d_items, d_scan;
+  PinnedBuf h_misc;
+  DevBuf d_scan;
 
-  struct Staged
+  // One chunk = one flush unit: device-resident command buffers + launch descriptors.  A "group" is the list of chunks
+  // launched since the previous psxgpu_flush (a batched submit is cut into several so that host encoding of chunk k+1
+  // overlaps the copy + kernels of chunk k); psxgpu_run_staged replays the last closed group.
+  struct Chunk
   {
-    bool valid = false;
+    DevBuf d_cmds, d_setups, d_bins, d_payload, d_clutops, d_items;
     uint32_t n_cmds = 0;
-    std::vector<uint32_t> wave_off; // wave k = items [wave_off[k], wave_off[k+1])
+    std::vector<uint32_t> wave_off{0}; // wave k = items [wave_off[k], wave_off[k+1])
     std::vector<uint8_t> wave_has_clut, wave_has_tiled, wave_has_serial;
-  } staged;
+    std::vector<cudaEvent_t> ev_raster; // pairs, profile mode
+    uint32_t ev_raster_used = 0;
+  };
+  std::vector<Chunk*> chunks;
+  uint32_t group_n = 0;     // chunks of the open group
+  bool group_open = false;
+  uint32_t staged_n = 0;    // chunks of the last closed group
+  uint32_t batch_chunk = 0; // instances per chunk in psxgpu_submit_batch (0 = auto)
+
+  // pinned staging, triple buffered: a set may be refilled once the copies that read it have completed
+  struct PinnedSet
+  {
+    PinnedBuf cmds, payload, clutops, items;
+    cudaEvent_t free_ev = nullptr;
+    bool in_flight = false;
+  };
+  PinnedSet pinned[3];
+  uint32_t pin_next = 0;
 
   std::unordered_map<uint32_t, std::vector<uint16_t>> shadow;
   std::vector<uint8_t> display;
   uint32_t disp_w = 0, disp_h = 0, disp_stride = 0, disp_rgba8 = 1;
 
-  cudaEvent_t ev_start = nullptr, ev_h2d = nullptr, ev_end = nullptr, ev_hash0 = nullptr, ev_hash1 = nullptr;
-  std::vector<cudaEvent_t> ev_raster; // pairs
-  uint32_t ev_raster_used = 0;
+  cudaEvent_t ev_start = nullptr, ev_end = nullptr, ev_hash0 = nullptr, ev_hash1 = nullptr;
   bool timing_pending = false;
+  uint32_t timing_chunks = 0;
+  double stage_ms_acc = 0;
 
   psxgpu_stats counters{};
   psxgpu_timing timing{};
@@ -190,51 +210,55 @@ int collect_timing(psxgpu_ctx* ctx)
   if (!ctx->timing_pending)
     return PSXGPU_OK;
   CK(cudaEventSynchronize(ctx->ev_end), "event sync");
-  float a = 0, b = 0;
+  float a = 0;
   cudaEventElapsedTime(&a, ctx->ev_start, ctx->ev_end);
-  cudaEventElapsedTime(&b, ctx->ev_h2d, ctx->ev_end);
   ctx->timing.last_flush_device_ms = a;
-  ctx->timing.last_kernels_ms = b;
+  ctx->timing.last_kernels_ms = a;
   ctx->raster_ms.clear();
   float sum = 0, mx = 0;
-  for (uint32_t i = 0; i < ctx->ev_raster_used; i += 2)
+  uint32_t waves = 0;
+  for (uint32_t c = 0; c < ctx->timing_chunks && c < ctx->chunks.size(); c++)
   {
-    float t = 0;
-    cudaEventElapsedTime(&t, ctx->ev_raster[i], ctx->ev_raster[i + 1]);
-    ctx->raster_ms.push_back(t);
-    sum += t;
-    mx = std::max(mx, t);
+    psxgpu_ctx::Chunk& ch = *ctx->chunks[c];
+    waves += static_cast<uint32_t>(ch.wave_off.size()) - 1;
+    for (uint32_t i = 0; i + 1 < ch.ev_raster_used; i += 2)
+    {
+      float t = 0;
+      cudaEventElapsedTime(&t, ch.ev_raster[i], ch.ev_raster[i + 1]);
+      ctx->raster_ms.push_back(t);
+      sum += t;
+      mx = std::max(mx, t);
+    }
   }
   ctx->timing.last_raster_ms = sum;
   ctx->timing.last_raster_max_ms = mx;
-  ctx->timing.last_raster_launches = ctx->ev_raster_used / 2;
+  ctx->timing.last_raster_launches = static_cast<uint32_t>(ctx->raster_ms.size());
+  ctx->timing.last_waves = waves;
   ctx->timing_pending = false;
   return PSXGPU_OK;
 }
 
-// setup + all waves of the staged flush, on ctx->stream
-int run_device(psxgpu_ctx* ctx)
+// setup + all waves of one chunk, on ctx->stream
+int run_chunk(psxgpu_ctx* ctx, psxgpu_ctx::Chunk& S)
 {
-  auto& S = ctx->staged;
-  CK(cudaEventRecord(ctx->ev_h2d, ctx->stream), "event record");
-  CK(launch_setup(static_cast<const PackedCmd*>(ctx->d_cmds.p), static_cast<PrimSetup*>(ctx->d_setups.p),
-                  static_cast<BinInfo*>(ctx->d_bins.p), S.n_cmds, ctx->stream),
+  CK(launch_setup(static_cast<const PackedCmd*>(S.d_cmds.p), static_cast<PrimSetup*>(S.d_setups.p),
+                  static_cast<BinInfo*>(S.d_bins.p), S.n_cmds, ctx->stream),
      "setup_kernel");
   if (S.n_cmds)
     ctx->counters.kernel_launches++;
   const uint32_t waves = static_cast<uint32_t>(S.wave_off.size()) - 1;
   const bool prof = ctx->opts.profile != 0;
-  ctx->ev_raster_used = 0;
+  S.ev_raster_used = 0;
   if (prof)
   {
-    while (ctx->ev_raster.size() < static_cast<size_t>(waves) * 2)
+    while (S.ev_raster.size() < static_cast<size_t>(waves) * 2)
     {
       cudaEvent_t e;
       CK(cudaEventCreate(&e), "event create");
-      ctx->ev_raster.push_back(e);
+      S.ev_raster.push_back(e);
     }
   }
-  const WaveItem* items = static_cast<const WaveItem*>(ctx->d_items.p);
+  const WaveItem* items = static_cast<const WaveItem*>(S.d_items.p);
   for (uint32_t k = 0; k < waves; k++)
   {
     const uint32_t off = S.wave_off[k], cnt = S.wave_off[k + 1] - off;
@@ -242,97 +266,124 @@ int run_device(psxgpu_ctx* ctx)
       continue;
     if (S.wave_has_clut[k])
     {
-      CK(launch_clut(items + off, cnt, static_cast<const ClutOp*>(ctx->d_clutops.p), ctx->d_vram, ctx->d_clut, ctx->clut_slots,
+      CK(launch_clut(items + off, cnt, static_cast<const ClutOp*>(S.d_clutops.p), ctx->d_vram, ctx->d_clut, ctx->clut_slots,
                      ctx->stream),
          "clut_kernel");
       ctx->counters.kernel_launches++;
     }
     if (prof)
-      CK(cudaEventRecord(ctx->ev_raster[ctx->ev_raster_used++], ctx->stream), "event record");
+      CK(cudaEventRecord(S.ev_raster[S.ev_raster_used++], ctx->stream), "event record");
     if (S.wave_has_tiled[k])
     {
-      CK(launch_raster(items + off, cnt, static_cast<const PrimSetup*>(ctx->d_setups.p), static_cast<const BinInfo*>(ctx->d_bins.p),
-                       ctx->d_vram, ctx->d_clut, static_cast<const uint16_t*>(ctx->d_payload.p), ctx->clut_slots, ctx->stream),
+      CK(launch_raster(items + off, cnt, static_cast<const PrimSetup*>(S.d_setups.p), static_cast<const BinInfo*>(S.d_bins.p),
+                       ctx->d_vram, ctx->d_clut, static_cast<const uint16_t*>(S.d_payload.p), ctx->clut_slots, ctx->stream),
          "raster_kernel");
       ctx->counters.kernel_launches += (cnt + 32767) / 32768;
     }
     if (S.wave_has_serial[k])
     {
-      CK(launch_serial(items + off, cnt, static_cast<const PrimSetup*>(ctx->d_setups.p), ctx->d_vram, ctx->d_clut,
-                       static_cast<const uint16_t*>(ctx->d_payload.p), ctx->clut_slots, ctx->stream),
+      CK(launch_serial(items + off, cnt, static_cast<const PrimSetup*>(S.d_setups.p), ctx->d_vram, ctx->d_clut,
+                       static_cast<const uint16_t*>(S.d_payload.p), ctx->clut_slots, ctx->stream),
          "serial_kernel");
       ctx->counters.kernel_launches++;
     }
     if (prof)
-      CK(cudaEventRecord(ctx->ev_raster[ctx->ev_raster_used++], ctx->stream), "event record");
+      CK(cudaEventRecord(S.ev_raster[S.ev_raster_used++], ctx->stream), "event record");
   }
-  CK(cudaEventRecord(ctx->ev_end, ctx->stream), "event record");
-  ctx->timing.last_waves = waves;
   ctx->counters.waves += waves;
-  ctx->timing_pending = true;
   return PSXGPU_OK;
 }
 
-int do_flush(psxgpu_ctx* ctx)
+int open_group(psxgpu_ctx* ctx)
 {
-  std::vector<uint32_t> work;
-  for (uint32_t i = 0; i < ctx->n; i++)
-    if (ctx->dirty[i])
-      work.push_back(i);
-  if (work.empty())
+  if (ctx->group_open)
     return PSXGPU_OK;
-  int rc = collect_timing(ctx); // events are about to be reused
+  int rc = collect_timing(ctx); // the events are about to be reused
   if (rc != PSXGPU_OK)
     return rc;
+  ctx->group_open = true;
+  ctx->group_n = 0;
+  ctx->stage_ms_acc = 0;
+  CK(cudaEventRecord(ctx->ev_start, ctx->stream), "event record");
+  return PSXGPU_OK;
+}
 
-  const double t0 = now_ms();
+int close_group(psxgpu_ctx* ctx)
+{
+  if (!ctx->group_open)
+    return PSXGPU_OK;
+  CK(cudaEventRecord(ctx->ev_end, ctx->stream), "event record");
+  ctx->group_open = false;
+  ctx->staged_n = ctx->group_n;
+  ctx->timing_chunks = ctx->group_n;
+  ctx->timing_pending = true;
+  ctx->timing.last_stage_ms = static_cast<float>(ctx->stage_ms_acc);
+  ctx->timing.last_encode_ms = static_cast<float>(ctx->encode_ms_acc);
+  ctx->encode_ms_acc = 0;
+  ctx->counters.flushes++;
+  return PSXGPU_OK;
+}
+
+int acquire_pinned(psxgpu_ctx* ctx, psxgpu_ctx::PinnedSet*& out)
+{
+  psxgpu_ctx::PinnedSet& P = ctx->pinned[ctx->pin_next];
+  ctx->pin_next = (ctx->pin_next + 1) % 3;
+  if (P.in_flight)
+  {
+    CK(cudaEventSynchronize(P.free_ev), "pinned buffer sync");
+    P.in_flight = false;
+  }
+  out = &P;
+  return PSXGPU_OK;
+}
+
+// Common tail of a flush unit.  The packed records and upload pixels of work[w] already sit in the pinned set at
+// cmd_base[w] / pay_base[w] (cmd_base[nw] / pay_base[nw] = extents); this adds CLUT ops and wave descriptors, copies
+// everything to a chunk's device buffers and launches setup + waves.  Asynchronous.
+int launch_chunk(psxgpu_ctx* ctx, const std::vector<uint32_t>& work, const std::vector<uint64_t>& cmd_base,
+                 const std::vector<uint64_t>& pay_base, psxgpu_ctx::PinnedSet& P)
+{
   const uint32_t nw = static_cast<uint32_t>(work.size());
-  parallel_for(nw, ctx->threads, [&](uint32_t w) { ctx->enc[work[w]].finish_flush(); });
-
-  std::vector<uint64_t> cmd_base(nw + 1, 0), pay_base(nw + 1, 0), clut_base(nw + 1, 0);
+  const uint64_t n_cmds = cmd_base[nw], n_pay = pay_base[nw];
+  if (n_cmds > 0xFFFFFFF0ull || n_pay > 0xFFFFFFF0ull)
+    return ctx->invalid("flush too large: more than 2^32 commands or payload pixels");
+  std::vector<uint64_t> clut_base(nw + 1, 0);
   size_t max_epochs = 0, total_epochs = 0;
   for (uint32_t w = 0; w < nw; w++)
   {
     const Encoder& e = ctx->enc[work[w]];
-    cmd_base[w + 1] = cmd_base[w] + e.cmds.size();
-    pay_base[w + 1] = pay_base[w] + e.payload.size();
     clut_base[w + 1] = clut_base[w] + e.clut_ops.size();
     max_epochs = std::max(max_epochs, e.epochs.size());
     total_epochs += e.epochs.size();
   }
-  const uint64_t n_cmds = cmd_base[nw], n_pay = pay_base[nw], n_clut = clut_base[nw];
-  if (n_cmds > 0xFFFFFFF0ull || n_pay > 0xFFFFFFF0ull)
-    return ctx->invalid("flush too large: more than 2^32 commands or payload pixels");
+  const uint64_t n_clut = clut_base[nw];
 
-  CK(ctx->h_cmds.ensure(n_cmds * sizeof(PackedCmd)), "pinned alloc (commands)");
-  CK(ctx->h_payload.ensure(n_pay * 2), "pinned alloc (payload)");
-  CK(ctx->h_clutops.ensure(n_clut * sizeof(ClutOp)), "pinned alloc (clut ops)");
-  CK(ctx->h_items.ensure(total_epochs * sizeof(WaveItem)), "pinned alloc (wave items)");
-  CK(ctx->d_cmds.ensure(n_cmds * sizeof(PackedCmd)), "device alloc (commands)");
-  CK(ctx->d_setups.ensure(n_cmds * sizeof(PrimSetup)), "device alloc (setup records)");
-  CK(ctx->d_bins.ensure(n_cmds * sizeof(BinInfo)), "device alloc (bins)");
-  CK(ctx->d_payload.ensure(n_pay * 2 + 16), "device alloc (payload)");
-  CK(ctx->d_clutops.ensure(n_clut * sizeof(ClutOp) + 16), "device alloc (clut ops)");
-  CK(ctx->d_items.ensure(total_epochs * sizeof(WaveItem) + 16), "device alloc (wave items)");
+  if (ctx->group_n >= ctx->chunks.size())
+    ctx->chunks.push_back(new psxgpu_ctx::Chunk());
+  psxgpu_ctx::Chunk& S = *ctx->chunks[ctx->group_n++];
+  CK(P.clutops.ensure(n_clut * sizeof(ClutOp)), "pinned alloc (clut ops)");
+  CK(P.items.ensure(total_epochs * sizeof(WaveItem)), "pinned alloc (wave items)");
+  CK(S.d_cmds.ensure(n_cmds * sizeof(PackedCmd)), "device alloc (commands)");
+  CK(S.d_setups.ensure(n_cmds * sizeof(PrimSetup)), "device alloc (setup records)");
+  CK(S.d_bins.ensure(n_cmds * sizeof(BinInfo) + 64), "device alloc (bins)");
+  CK(S.d_payload.ensure(n_pay * 2 + 16), "device alloc (payload)");
+  CK(S.d_clutops.ensure(n_clut * sizeof(ClutOp) + 16), "device alloc (clut ops)");
+  CK(S.d_items.ensure(total_epochs * sizeof(WaveItem) + 16), "device alloc (wave items)");
 
-  PackedCmd* hc = static_cast<PackedCmd*>(ctx->h_cmds.p);
-  uint16_t* hp = static_cast<uint16_t*>(ctx->h_payload.p);
-  ClutOp* ho = static_cast<ClutOp*>(ctx->h_clutops.p);
-  parallel_for(nw, ctx->threads, [&](uint32_t w) {
+  PackedCmd* hc = static_cast<PackedCmd*>(P.cmds.p);
+  uint16_t* hp = static_cast<uint16_t*>(P.payload.p);
+  ClutOp* ho = static_cast<ClutOp*>(P.clutops.p);
+  for (uint32_t w = 0; w < nw; w++)
+  {
     const Encoder& e = ctx->enc[work[w]];
-    if (!e.cmds.empty())
-      std::memcpy(hc + cmd_base[w], e.cmds.data(), e.cmds.size() * sizeof(PackedCmd));
     for (uint32_t ui : e.upload_cmds)
       hc[cmd_base[w] + ui].upload.payload += static_cast<uint32_t>(pay_base[w]);
-    if (!e.payload.empty())
-      std::memcpy(hp + pay_base[w], e.payload.data(), e.payload.size() * 2);
     if (!e.clut_ops.empty())
       std::memcpy(ho + clut_base[w], e.clut_ops.data(), e.clut_ops.size() * sizeof(ClutOp));
-  });
+  }
 
   // waves: wave k = epoch k of every instance that has one
-  WaveItem* hi = static_cast<WaveItem*>(ctx->h_items.p);
-  auto& S = ctx->staged;
+  WaveItem* hi = static_cast<WaveItem*>(P.items.p);
   S.wave_off.assign(1, 0);
   S.wave_has_clut.clear();
   S.wave_has_tiled.clear();
@@ -370,35 +421,76 @@ int do_flush(psxgpu_ctx* ctx)
     S.wave_has_serial.push_back(has_serial);
   }
   S.n_cmds = static_cast<uint32_t>(n_cmds);
-  S.valid = true;
-  ctx->timing.last_stage_ms = static_cast<float>(now_ms() - t0);
-  ctx->timing.last_encode_ms = static_cast<float>(ctx->encode_ms_acc);
-  ctx->encode_ms_acc = 0;
-
-  CK(cudaEventRecord(ctx->ev_start, ctx->stream), "event record");
-  if (n_cmds)
-    CK(cudaMemcpyAsync(ctx->d_cmds.p, hc, n_cmds * sizeof(PackedCmd), cudaMemcpyHostToDevice, ctx->stream), "H2D commands");
-  if (n_pay)
-    CK(cudaMemcpyAsync(ctx->d_payload.p, hp, n_pay * 2, cudaMemcpyHostToDevice, ctx->stream), "H2D payload");
-  if (n_clut)
-    CK(cudaMemcpyAsync(ctx->d_clutops.p, ho, n_clut * sizeof(ClutOp), cudaMemcpyHostToDevice, ctx->stream), "H2D clut ops");
-  if (n_items)
-    CK(cudaMemcpyAsync(ctx->d_items.p, hi, n_items * sizeof(WaveItem), cudaMemcpyHostToDevice, ctx->stream), "H2D wave items");
-  ctx->counters.h2d_bytes += n_cmds * sizeof(PackedCmd) + n_pay * 2 + n_clut * sizeof(ClutOp) + n_items * sizeof(WaveItem);
-  ctx->counters.flushes++;
-
-  rc = run_device(ctx);
-  if (rc != PSXGPU_OK)
-    return rc;
-
-  // the pinned buffers are reused by the next flush: they must not be rewritten before the copies are done
-  CK(cudaEventSynchronize(ctx->ev_h2d), "H2D sync");
+  // everything the encoders held is in the pinned set now
   for (uint32_t w = 0; w < nw; w++)
   {
     ctx->enc[work[w]].begin_flush();
     ctx->dirty[work[w]] = 0;
   }
-  return PSXGPU_OK;
+
+  if (n_cmds)
+    CK(cudaMemcpyAsync(S.d_cmds.p, hc, n_cmds * sizeof(PackedCmd), cudaMemcpyHostToDevice, ctx->stream), "H2D commands");
+  if (n_pay)
+    CK(cudaMemcpyAsync(S.d_payload.p, hp, n_pay * 2, cudaMemcpyHostToDevice, ctx->stream), "H2D payload");
+  if (n_clut)
+    CK(cudaMemcpyAsync(S.d_clutops.p, ho, n_clut * sizeof(ClutOp), cudaMemcpyHostToDevice, ctx->stream), "H2D clut ops");
+  if (n_items)
+    CK(cudaMemcpyAsync(S.d_items.p, hi, n_items * sizeof(WaveItem), cudaMemcpyHostToDevice, ctx->stream), "H2D wave items");
+  CK(cudaEventRecord(P.free_ev, ctx->stream), "event record");
+  P.in_flight = true;
+  ctx->counters.h2d_bytes += n_cmds * sizeof(PackedCmd) + n_pay * 2 + n_clut * sizeof(ClutOp) + n_items * sizeof(WaveItem);
+  return run_chunk(ctx, S);
+}
+
+// Vector mode (records arrived one at a time through psxgpu_submit_wire): packs the finished encoders of `work` into a
+// pinned set and launches them as one chunk.
+int flush_work(psxgpu_ctx* ctx, const std::vector<uint32_t>& work)
+{
+  if (work.empty())
+    return PSXGPU_OK;
+  int rc = open_group(ctx);
+  if (rc != PSXGPU_OK)
+    return rc;
+  const double t0 = now_ms();
+  const uint32_t nw = static_cast<uint32_t>(work.size());
+  parallel_for(nw, ctx->threads, [&](uint32_t w) { ctx->enc[work[w]].finish_flush(); });
+  std::vector<uint64_t> cmd_base(nw + 1, 0), pay_base(nw + 1, 0);
+  for (uint32_t w = 0; w < nw; w++)
+  {
+    const Encoder& e = ctx->enc[work[w]];
+    cmd_base[w + 1] = cmd_base[w] + e.n_cmds();
+    pay_base[w + 1] = pay_base[w] + e.n_payload();
+  }
+  psxgpu_ctx::PinnedSet* P = nullptr;
+  rc = acquire_pinned(ctx, P);
+  if (rc != PSXGPU_OK)
+    return rc;
+  CK(P->cmds.ensure(cmd_base[nw] * sizeof(PackedCmd)), "pinned alloc (commands)");
+  CK(P->payload.ensure(pay_base[nw] * 2), "pinned alloc (payload)");
+  PackedCmd* hc = static_cast<PackedCmd*>(P->cmds.p);
+  uint16_t* hp = static_cast<uint16_t*>(P->payload.p);
+  parallel_for(nw, ctx->threads, [&](uint32_t w) {
+    const Encoder& e = ctx->enc[work[w]];
+    if (!e.cmds.empty())
+      std::memcpy(hc + cmd_base[w], e.cmds.data(), e.cmds.size() * sizeof(PackedCmd));
+    if (!e.payload.empty())
+      std::memcpy(hp + pay_base[w], e.payload.data(), e.payload.size() * 2);
+  });
+  ctx->stage_ms_acc += now_ms() - t0;
+  return launch_chunk(ctx, work, cmd_base, pay_base, *P);
+}
+
+// Flushes every instance that has queued work and closes the group.
+int do_flush(psxgpu_ctx* ctx)
+{
+  std::vector<uint32_t> work;
+  for (uint32_t i = 0; i < ctx->n; i++)
+    if (ctx->dirty[i])
+      work.push_back(i);
+  int rc = flush_work(ctx, work);
+  if (rc != PSXGPU_OK)
+    return rc;
+  return close_group(ctx);
 }
 
 void scanout_params(const psxgpu_ctx* ctx, const psx_update_display* cmd, ScanoutParams& p, bool& disabled)
@@ -552,7 +644,8 @@ int psxgpu_create(int device, uint32_t n_instances, const psxgpu_opts* opts, psx
   if ((e = cudaMemsetAsync(ctx->d_clut, 0, static_cast<size_t>(n_instances) * ctx->clut_slots * CLUT_ENTRIES * 2, ctx->stream)) !=
       cudaSuccess)
     return bail(e, "CLUT clear");
-  for (cudaEvent_t* ev : {&ctx->ev_start, &ctx->ev_h2d, &ctx->ev_end, &ctx->ev_hash0, &ctx->ev_hash1})
+  for (cudaEvent_t* ev : {&ctx->ev_start, &ctx->ev_end, &ctx->ev_hash0, &ctx->ev_hash1, &ctx->pinned[0].free_ev, &ctx->pinned[1].free_ev,
+                          &ctx->pinned[2].free_ev})
     if ((e = cudaEventCreate(ev)) != cudaSuccess)
       return bail(e, "event");
   if ((e = ctx->h_misc.ensure(std::max<size_t>(static_cast<size_t>(n_instances) * 8, 4096))) != cudaSuccess)
@@ -567,7 +660,6 @@ int psxgpu_create(int device, uint32_t n_instances, const psxgpu_opts* opts, psx
     ctx->enc.back().begin_flush();
   }
   ctx->dirty.assign(n_instances, 0);
-  ctx->staged.wave_off.assign(1, 0);
   *out = ctx;
   return PSXGPU_OK;
 }
@@ -579,21 +671,32 @@ void psxgpu_destroy(psxgpu_ctx* ctx)
   cudaSetDevice(ctx->device);
   if (ctx->stream)
     cudaStreamSynchronize(ctx->stream);
-  for (PinnedBuf* b : {&ctx->h_cmds, &ctx->h_payload, &ctx->h_clutops, &ctx->h_items, &ctx->h_misc})
-    b->release();
-  for (DevBuf* b : {&ctx->d_cmds, &ctx->d_setups, &ctx->d_bins, &ctx->d_payload, &ctx->d_clutops, &ctx->d_items, &ctx->d_scan})
-    b->release();
+  ctx->h_misc.release();
+  ctx->d_scan.release();
+  for (psxgpu_ctx::PinnedSet& ps : ctx->pinned)
+  {
+    for (PinnedBuf* b : {&ps.cmds, &ps.payload, &ps.clutops, &ps.items})
+      b->release();
+    if (ps.free_ev)
+      cudaEventDestroy(ps.free_ev);
+  }
+  for (psxgpu_ctx::Chunk* ch : ctx->chunks)
+  {
+    for (DevBuf* b : {&ch->d_cmds, &ch->d_setups, &ch->d_bins, &ch->d_payload, &ch->d_clutops, &ch->d_items})
+      b->release();
+    for (cudaEvent_t ev : ch->ev_raster)
+      cudaEventDestroy(ev);
+    delete ch;
+  }
   if (ctx->d_vram)
     cudaFree(ctx->d_vram);
   if (ctx->d_clut)
     cudaFree(ctx->d_clut);
   if (ctx->d_hash)
     cudaFree(ctx->d_hash);
-  for (cudaEvent_t ev : {ctx->ev_start, ctx->ev_h2d, ctx->ev_end, ctx->ev_hash0, ctx->ev_hash1})
+  for (cudaEvent_t ev : {ctx->ev_start, ctx->ev_end, ctx->ev_hash0, ctx->ev_hash1})
     if (ev)
       cudaEventDestroy(ev);
-  for (cudaEvent_t ev : ctx->ev_raster)
-    cudaEventDestroy(ev);
   if (ctx->stream)
     cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -625,14 +728,31 @@ int psxgpu_run_staged(psxgpu_ctx* ctx)
 {
   if (!ctx)
     return PSXGPU_E_INVALID;
-  if (!ctx->staged.valid)
-    return ctx->invalid("run_staged: no flush is resident");
+  if (ctx->group_open || ctx->staged_n == 0)
+    return ctx->invalid("run_staged: no flushed command buffers are resident");
   cudaSetDevice(ctx->device);
   int rc = collect_timing(ctx);
   if (rc != PSXGPU_OK)
     return rc;
   CK(cudaEventRecord(ctx->ev_start, ctx->stream), "event record");
-  return run_device(ctx);
+  for (uint32_t c = 0; c < ctx->staged_n; c++)
+  {
+    rc = run_chunk(ctx, *ctx->chunks[c]);
+    if (rc != PSXGPU_OK)
+      return rc;
+  }
+  CK(cudaEventRecord(ctx->ev_end, ctx->stream), "event record");
+  ctx->timing_chunks = ctx->staged_n;
+  ctx->timing_pending = true;
+  return PSXGPU_OK;
+}
+
+int psxgpu_set_batch_chunk(psxgpu_ctx* ctx, uint32_t instances_per_chunk)
+{
+  if (!ctx)
+    return PSXGPU_E_INVALID;
+  ctx->batch_chunk = instances_per_chunk;
+  return PSXGPU_OK;
 }
 
 int psxgpu_submit_wire(psxgpu_ctx* ctx, uint32_t instance, const void* wire, size_t bytes)
@@ -719,23 +839,87 @@ int psxgpu_submit_batch(psxgpu_ctx* ctx, uint32_t first, uint32_t count, const v
 {
   if (!ctx || !streams || !bytes || first + count > ctx->n || first + count < first)
     return ctx ? ctx->invalid("submit_batch: bad arguments") : PSXGPU_E_INVALID;
-  const double t0 = now_ms();
+  cudaSetDevice(ctx->device);
+  // records queued one at a time for these instances go first (they are older)
+  {
+    std::vector<uint32_t> pending;
+    for (uint32_t i = 0; i < count; i++)
+      if (ctx->dirty[first + i])
+        pending.push_back(first + i);
+    const int rc = flush_work(ctx, pending);
+    if (rc != PSXGPU_OK)
+      return rc;
+  }
+  // Cut the batch into chunks: while the copy engine and the SMs work on chunk k, the host threads encode chunk k+1
+  // — straight into pinned memory, at offsets fixed by a cheap header scan, so nothing is copied twice.
+  uint32_t per = ctx->batch_chunk;
+  if (per == 0)
+    per = (count <= 256) ? count : std::max<uint32_t>(128, (count + 7) / 8);
   std::vector<int> status(count, 0);
-  parallel_for(count, ctx->threads, [&](uint32_t i) {
-    size_t used = 0;
-    const EncodeResult res = ctx->enc[first + i].add_wire(streams[i], bytes[i], &used);
-    if (used)
-      ctx->dirty[first + i] = 1;
-    status[i] = (res == EncodeResult::Ok) ? 0 : (res == EncodeResult::Malformed ? PSXGPU_E_MALFORMED : PSXGPU_E_UNSUPPORTED);
-  });
-  ctx->encode_ms_acc += now_ms() - t0;
-  for (uint32_t i = 0; i < count; i++)
-    if (status[i] != 0)
+  std::vector<uint32_t> work, cap_cmds;
+  std::vector<uint64_t> cmd_base, pay_base;
+  for (uint32_t c0 = 0; c0 < count; c0 += per)
+  {
+    const uint32_t cn = std::min(per, count - c0);
+    int rc = open_group(ctx);
+    if (rc != PSXGPU_OK)
+      return rc;
+    const double t0 = now_ms();
+    cap_cmds.assign(cn, 0);
+    cmd_base.assign(cn + 1, 0);
+    pay_base.assign(cn + 1, 0);
+    std::vector<uint64_t> cap_pay(cn, 0);
+    parallel_for(cn, ctx->threads, [&](uint32_t k) {
+      if (!Encoder::scan_wire(streams[c0 + k], bytes[c0 + k], &cap_cmds[k], &cap_pay[k]))
+        status[c0 + k] = PSXGPU_E_MALFORMED;
+    });
+    for (uint32_t k = 0; k < cn; k++)
     {
-      ctx->error = (status[i] == PSXGPU_E_MALFORMED) ? "submit_batch: malformed record stream"
-                                                     : "submit_batch: read-back / state records are not allowed in a batch";
-      return status[i];
+      if (status[c0 + k] != 0)
+      {
+        ctx->error = "submit_batch: malformed record stream";
+        return status[c0 + k];
+      }
+      cmd_base[k + 1] = cmd_base[k] + cap_cmds[k];
+      pay_base[k + 1] = pay_base[k] + cap_pay[k];
     }
+    psxgpu_ctx::PinnedSet* P = nullptr;
+    rc = acquire_pinned(ctx, P);
+    if (rc != PSXGPU_OK)
+      return rc;
+    CK(P->cmds.ensure(cmd_base[cn] * sizeof(PackedCmd)), "pinned alloc (commands)");
+    CK(P->payload.ensure(pay_base[cn] * 2), "pinned alloc (payload)");
+    PackedCmd* hc = static_cast<PackedCmd*>(P->cmds.p);
+    uint16_t* hp = static_cast<uint16_t*>(P->payload.p);
+    parallel_for(cn, ctx->threads, [&](uint32_t k) {
+      Encoder& e = ctx->enc[first + c0 + k];
+      e.set_output(hc + cmd_base[k], cap_cmds[k], hp + pay_base[k], cap_pay[k]);
+      size_t used = 0;
+      const EncodeResult res = e.add_wire(streams[c0 + k], bytes[c0 + k], &used);
+      e.finish_flush();
+      status[c0 + k] = (res == EncodeResult::Ok && !e.overflowed()) ? 0 : (res == EncodeResult::Barrier ? PSXGPU_E_UNSUPPORTED : PSXGPU_E_MALFORMED);
+      // records that were culled leave a gap at the end of the slot: make the setup pre-pass skip it
+      for (uint32_t g = e.n_cmds(); g < cap_cmds[k]; g++)
+        hc[cmd_base[k] + g].op = OP_NOP;
+    });
+    ctx->encode_ms_acc += now_ms() - t0;
+    work.clear();
+    for (uint32_t k = 0; k < cn; k++)
+    {
+      if (status[c0 + k] != 0)
+      {
+        ctx->error = (status[c0 + k] == PSXGPU_E_MALFORMED) ? "submit_batch: malformed record stream"
+                                                            : "submit_batch: read-back / state records are not allowed in a batch";
+        for (uint32_t j = 0; j < cn; j++) // drop the half-encoded chunk
+          ctx->enc[first + c0 + j].begin_flush();
+        return status[c0 + k];
+      }
+      work.push_back(first + c0 + k);
+    }
+    rc = launch_chunk(ctx, work, cmd_base, pay_base, *P);
+    if (rc != PSXGPU_OK)
+      return rc;
+  }
   return PSXGPU_OK;
 }
 

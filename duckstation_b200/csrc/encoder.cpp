@@ -79,10 +79,54 @@ static bool grid_hits(const HazardGrid& g, const RectSet& s)
       return true;
   return false;
 }
-static void grid_mark(HazardGrid& g, const RectSet& s)
+// ---------------------------------------------------------------- HazardSet
+void HazardSet::clear()
+{
+  if (m_any)
+  {
+    m_grid.clear();
+    m_pending.clear();
+    m_any = false;
+  }
+}
+
+void HazardSet::add(const RectSet& s)
 {
   for (int i = 0; i < s.n; i++)
-    g.mark(s.r[i].x0, s.r[i].y0, s.r[i].x1, s.r[i].y1);
+  {
+    const RectSet::R& r = s.r[i];
+    if (!m_any)
+    {
+      m_x0 = r.x0;
+      m_y0 = r.y0;
+      m_x1 = r.x1;
+      m_y1 = r.y1;
+      m_any = true;
+    }
+    else
+    {
+      m_x0 = std::min(m_x0, r.x0);
+      m_y0 = std::min(m_y0, r.y0);
+      m_x1 = std::max(m_x1, r.x1);
+      m_y1 = std::max(m_y1, r.y1);
+    }
+    m_pending.push_back(r);
+  }
+}
+
+bool HazardSet::hits(const RectSet& s)
+{
+  if (!m_any)
+    return false;
+  bool maybe = false;
+  for (int i = 0; i < s.n && !maybe; i++)
+    maybe = s.r[i].x0 <= m_x1 && m_x0 <= s.r[i].x1 && s.r[i].y0 <= m_y1 && m_y0 <= s.r[i].y1;
+  if (!maybe)
+    return false;
+  for (const RectSet::R& r : m_pending)
+    m_grid.mark(r.x0, r.y0, r.x1, r.y1);
+  m_pending.clear();
+  return grid_hits(m_grid, s);
 }
 
 // ---------------------------------------------------------------- Encoder
@@ -90,6 +134,25 @@ Encoder::Encoder(uint32_t clut_slots, bool modulation_crop)
   : m_clut_slots(std::min<uint32_t>(std::max<uint32_t>(clut_slots, 4), 256)), m_modulation_crop(modulation_crop)
 {
   m_slots.resize(m_clut_slots);
+  m_chain.assign(m_clut_slots, 0);
+}
+
+void Encoder::chain_insert(uint32_t slot)
+{
+  const uint32_t b = bucket_of(m_slots[slot].x, m_slots[slot].y);
+  m_chain[slot] = m_bucket[b];
+  m_bucket[b] = static_cast<uint8_t>(slot);
+}
+
+void Encoder::chain_remove(uint32_t slot)
+{
+  const uint32_t b = bucket_of(m_slots[slot].x, m_slots[slot].y);
+  uint8_t* link = &m_bucket[b];
+  while (*link != 0 && *link != slot)
+    link = &m_chain[*link];
+  if (*link == slot)
+    *link = m_chain[slot];
+  m_chain[slot] = 0;
 }
 
 void Encoder::begin_flush()
@@ -97,6 +160,13 @@ void Encoder::begin_flush()
   cmds.clear();
   upload_cmds.clear();
   payload.clear();
+  m_out_cmds = nullptr;
+  m_out_payload = nullptr;
+  m_out_cmd_cap = 0;
+  m_out_pay_cap = 0;
+  m_n_cmds = 0;
+  m_n_payload = 0;
+  m_overflow = false;
   epochs.clear();
   clut_ops.clear();
   m_epoch_cmd_begin = 0;
@@ -107,7 +177,7 @@ void Encoder::begin_flush()
 
 void Encoder::finish_flush()
 {
-  if (cmds.size() > m_epoch_cmd_begin || clut_ops.size() > m_epoch_clut_begin)
+  if (m_n_cmds > m_epoch_cmd_begin || clut_ops.size() > m_epoch_clut_begin)
     close_epoch(EPOCH_TILED);
 }
 
@@ -115,6 +185,8 @@ void Encoder::reset_clut_state()
 {
   for (ClutSlot& s : m_slots)
     s = ClutSlot();
+  std::memset(m_bucket, 0, sizeof(m_bucket));
+  std::fill(m_chain.begin(), m_chain.end(), uint8_t(0));
   m_clut_sources.clear();
   m_cur_lo = m_cur_hi = 0;
   m_alloc_hand = 1;
@@ -124,7 +196,7 @@ void Encoder::close_epoch(uint32_t kind)
 {
   Epoch e;
   e.cmd_begin = m_epoch_cmd_begin;
-  e.cmd_end = static_cast<uint32_t>(cmds.size());
+  e.cmd_end = m_n_cmds;
   e.kind = kind;
   e.clut_begin = m_epoch_clut_begin;
   e.clut_end = static_cast<uint32_t>(clut_ops.size());
@@ -140,7 +212,7 @@ void Encoder::close_epoch(uint32_t kind)
 int Encoder::find_slot(uint32_t x, uint32_t y, bool is8) const
 {
   // a valid 8-bit snapshot at the same position also serves a 4-bit load (its first 16 entries are the same pixels)
-  for (uint32_t i = 1; i < m_clut_slots; i++)
+  for (uint32_t i = m_bucket[bucket_of(x, y)]; i != 0; i = m_chain[i])
   {
     const ClutSlot& s = m_slots[i];
     if (s.valid && s.x == x && s.y == y && (s.is8 || !is8))
@@ -185,6 +257,7 @@ void Encoder::invalidate_cluts(const RectSet& writes)
     if (src.intersects(writes))
     {
       s.valid = false; // contents stay in use by draws that already reference the slot
+      chain_remove(i);
       stats.clut_invalidations++;
       any = true;
     }
@@ -199,7 +272,7 @@ void Encoder::invalidate_cluts(const RectSet& writes)
         continue;
       RectSet src;
       src.add_wrapped(s.x, s.y, s.is8 ? 256u : 16u, 1);
-      grid_mark(m_clut_sources, src);
+      m_clut_sources.add(src);
     }
   }
 }
@@ -218,18 +291,21 @@ void Encoder::update_clut(uint16_t reg, bool is8)
     RectSet src;
     src.add_wrapped(x, y, is8 ? 256u : 16u, 1);
     // The snapshot is taken before the epoch rasterises, so only writes EARLIER in this epoch matter (RAW).
-    if (grid_hits(m_writes, src))
+    if (m_writes.hits(src))
     {
       close_epoch(EPOCH_TILED);
       stats.cuts_clut++;
     }
     slot = static_cast<int>(alloc_slot());
     ClutSlot& s = m_slots[slot];
+    if (s.valid)
+      chain_remove(static_cast<uint32_t>(slot)); // evicted
     s.x = static_cast<uint16_t>(x);
     s.y = static_cast<uint16_t>(y);
     s.is8 = is8 ? 1 : 0;
     s.valid = true;
-    grid_mark(m_clut_sources, src);
+    chain_insert(static_cast<uint32_t>(slot));
+    m_clut_sources.add(src);
     ClutOp op;
     op.dst_slot = static_cast<uint16_t>(slot);
     op.x = static_cast<uint16_t>(x);
@@ -244,25 +320,87 @@ void Encoder::update_clut(uint16_t reg, bool is8)
     m_cur_hi = static_cast<uint32_t>(slot);
 }
 
+void Encoder::set_output(PackedCmd* out_cmds, uint32_t cmd_capacity, uint16_t* out_payload, uint64_t payload_capacity)
+{
+  m_out_cmds = out_cmds;
+  m_out_cmd_cap = cmd_capacity;
+  m_out_payload = out_payload;
+  m_out_pay_cap = payload_capacity;
+}
+
+void Encoder::push_cmd(const PackedCmd& c)
+{
+  if (m_out_cmds)
+  {
+    if (m_n_cmds < m_out_cmd_cap)
+      m_out_cmds[m_n_cmds] = c;
+    else
+      m_overflow = true;
+  }
+  else
+  {
+    cmds.push_back(c);
+  }
+  m_n_cmds++;
+}
+
+bool Encoder::scan_wire(const void* wire, size_t bytes, uint32_t* max_cmds, uint64_t* max_payload)
+{
+  const uint8_t* p = static_cast<const uint8_t*>(wire);
+  const uint8_t* end = p + bytes;
+  uint32_t nc = 0;
+  uint64_t np = 0;
+  while (p < end)
+  {
+    if (static_cast<size_t>(end - p) < sizeof(psx_cmd_header))
+      return false;
+    const psx_cmd_header* h = reinterpret_cast<const psx_cmd_header*>(p);
+    if (h->size < sizeof(psx_cmd_header) || (h->size & 3u) != 0 || h->size > static_cast<size_t>(end - p))
+      return false;
+    switch (h->type)
+    {
+      case PSX_CMD_DRAW_POLYGON:
+      case PSX_CMD_DRAW_PRECISE_POLYGON: nc += (reinterpret_cast<const psx_draw_header*>(p)->num_vertices > 3) ? 2u : 1u; break;
+      case PSX_CMD_DRAW_LINE:
+      case PSX_CMD_DRAW_PRECISE_LINE: nc += reinterpret_cast<const psx_draw_header*>(p)->num_vertices / 2u; break;
+      case PSX_CMD_DRAW_RECTANGLE:
+      case PSX_CMD_FILL_VRAM:
+      case PSX_CMD_COPY_VRAM: nc += 1; break;
+      case PSX_CMD_UPDATE_VRAM:
+      {
+        const psx_update_vram* u = reinterpret_cast<const psx_update_vram*>(p);
+        nc += 1;
+        np += ((static_cast<uint64_t>(u->width) * u->height) + 7u) & ~static_cast<uint64_t>(7);
+      }
+      break;
+      default: break;
+    }
+    p += h->size;
+  }
+  *max_cmds = nc;
+  *max_payload = np;
+  return true;
+}
+
 void Encoder::emit(const PackedCmd& c, const RectSet& writes, const RectSet& reads, uint32_t serial_kind)
 {
-  if (grid_hits(m_clut_sources, writes))
+  if (m_clut_sources.hits(writes))
     invalidate_cluts(writes);
   const bool textured = (c.op == OP_TRIANGLE || c.op == OP_RECT) && (c.flags0 & F_TEXTURE);
   if (serial_kind != EPOCH_TILED)
   {
-    if (cmds.size() > m_epoch_cmd_begin)
+    if (m_n_cmds > m_epoch_cmd_begin)
       close_epoch(EPOCH_TILED);
     if (textured)
       m_slots[c.clut_lo].last_epoch = m_slots[c.clut_hi].last_epoch = m_epoch_serial;
-    cmds.push_back(c);
+    push_cmd(c);
     stats.packed_prims++;
     close_epoch(serial_kind);
     return;
   }
-  const bool raw = grid_hits(m_writes, reads);
-  const bool war = !raw && grid_hits(m_reads, writes);
-  const bool full = (cmds.size() - m_epoch_cmd_begin) >= 65535u;
+  const bool raw = m_writes.hits(reads);
+  const bool war = !raw && m_reads.hits(writes);
+  const bool full = (m_n_cmds - m_epoch_cmd_begin) >= 65535u;
   if (raw || war || full)
   {
     close_epoch(EPOCH_TILED);
@@ -273,10 +411,10 @@ void Encoder::emit(const PackedCmd& c, const RectSet& writes, const RectSet& rea
   }
   if (textured)
     m_slots[c.clut_lo].last_epoch = m_slots[c.clut_hi].last_epoch = m_epoch_serial;
-  cmds.push_back(c);
+  push_cmd(c);
   stats.packed_prims++;
-  grid_mark(m_writes, writes);
-  grid_mark(m_reads, reads);
+  m_writes.add(writes);
+  m_reads.add(reads);
 }
 
 void Encoder::fill_draw_header(PackedCmd& c, const void* draw_header) const
@@ -679,12 +817,28 @@ void Encoder::handle_record(const uint8_t* rec)
       c.upload.y = u->y;
       c.upload.w = u->width;
       c.upload.h = u->height;
-      c.upload.payload = static_cast<uint32_t>(payload.size());
+      c.upload.payload = static_cast<uint32_t>(m_n_payload);
       const uint16_t* px = reinterpret_cast<const uint16_t*>(rec + PSX_UPDATE_VRAM_DATA_OFFSET);
-      payload.insert(payload.end(), px, px + static_cast<size_t>(u->width) * u->height);
-      // keep every upload 8-pixel aligned in the payload buffer so device reads can be vectorised
-      while (payload.size() & 7u)
-        payload.push_back(0);
+      const uint64_t npx = static_cast<uint64_t>(u->width) * u->height;
+      const uint64_t padded = (npx + 7u) & ~static_cast<uint64_t>(7); // 8-pixel aligned so device reads can be vectorised
+      if (m_out_payload)
+      {
+        if (m_n_payload + padded <= m_out_pay_cap)
+        {
+          std::memcpy(m_out_payload + m_n_payload, px, npx * 2);
+          std::memset(m_out_payload + m_n_payload + npx, 0, (padded - npx) * 2);
+        }
+        else
+        {
+          m_overflow = true;
+        }
+      }
+      else
+      {
+        payload.insert(payload.end(), px, px + npx);
+        payload.resize(payload.size() + (padded - npx), 0);
+      }
+      m_n_payload += padded;
       stats.upload_pixels += static_cast<uint64_t>(u->width) * u->height;
       RectSet writes, reads;
       writes.add_wrapped(u->x, u->y, u->width, u->height);
@@ -697,7 +851,7 @@ void Encoder::handle_record(const uint8_t* rec)
         kind = EPOCH_UPLOAD_MASKED;
         stats.serial_upload++;
       }
-      upload_cmds.push_back(static_cast<uint32_t>(cmds.size())); // emit() appends exactly one record
+      upload_cmds.push_back(m_n_cmds); // emit() appends exactly one record
       emit(c, writes, reads, kind);
     }
     break;

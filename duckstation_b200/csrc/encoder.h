@@ -71,6 +71,24 @@ struct RectSet
   bool intersects(const RectSet& o) const;
 };
 
+// A set of VRAM rectangles with a cheap negative test: a bounding box answers "cannot overlap" in four compares, and
+// rectangles are only rasterised into the cell grid the first time the bounding box test is inconclusive.  In the common
+// frame (draws into the framebuffer, textures elsewhere) the grid is never touched.
+class HazardSet
+{
+public:
+  void clear();
+  void add(const RectSet& s);
+  bool hits(const RectSet& s);
+  bool empty() const { return !m_any; }
+
+private:
+  HazardGrid m_grid;
+  std::vector<RectSet::R> m_pending;
+  uint16_t m_x0 = 0, m_y0 = 0, m_x1 = 0, m_y1 = 0;
+  bool m_any = false;
+};
+
 enum class EncodeResult
 {
   Ok,        // whole buffer consumed
@@ -93,7 +111,16 @@ public:
   // VRAM + CLUT were replaced wholesale (ClearVRAM / LoadState): slot 0 now holds the CLUT.
   void reset_clut_state();
 
-  bool has_work() const { return !cmds.empty() || !clut_ops.empty(); }
+  bool has_work() const { return m_n_cmds != 0 || !clut_ops.empty(); }
+
+  // Direct mode (batched path): the next flush's records and upload pixels are written straight into caller-provided
+  // (pinned) memory instead of the vectors below.  Capacities come from scan_wire(); cleared by begin_flush().
+  void set_output(PackedCmd* out_cmds, uint32_t cmd_capacity, uint16_t* out_payload, uint64_t payload_capacity);
+  bool overflowed() const { return m_overflow; }
+  uint32_t n_cmds() const { return m_n_cmds; }
+  uint64_t n_payload() const { return m_n_payload; }
+  // Upper bound of packed records and exact upper bound of (8-pixel padded) upload pixels a wire stream can produce.
+  static bool scan_wire(const void* wire, size_t bytes, uint32_t* max_cmds, uint64_t* max_payload);
 
   std::vector<PackedCmd> cmds;
   std::vector<uint32_t> upload_cmds; // indices of OP_UPLOAD records (payload offsets get rebased at flush)
@@ -117,8 +144,17 @@ private:
   void draw_triangle(const void* draw_header, const PackedVertex& a, const PackedVertex& b, const PackedVertex& c3);
   void texture_footprint(const PackedCmd& c, uint32_t umin, uint32_t umax, uint32_t vmin, uint32_t vmax, RectSet& reads) const;
 
+  void push_cmd(const PackedCmd& c);
+
   uint32_t m_clut_slots;
   bool m_modulation_crop;
+  PackedCmd* m_out_cmds = nullptr;
+  uint16_t* m_out_payload = nullptr;
+  uint32_t m_out_cmd_cap = 0;
+  uint64_t m_out_pay_cap = 0;
+  uint32_t m_n_cmds = 0;
+  uint64_t m_n_payload = 0;
+  bool m_overflow = false;
 
   // GPU state mirrored from the command stream
   uint16_t m_area[4] = {0, 0, 0, 0}; // raw drawing area l, t, r, b
@@ -133,16 +169,22 @@ private:
     uint32_t last_epoch = 0xFFFFFFFFu; // serial of the last epoch that references the slot's current contents
   };
   std::vector<ClutSlot> m_slots;
+  // (x, y) -> chain of valid slots: bucket heads and per-slot links (0 = end; slot 0 is never cached)
+  uint8_t m_bucket[1024] = {};
+  std::vector<uint8_t> m_chain;
+  static uint32_t bucket_of(uint32_t x, uint32_t y) { return ((x >> 4) ^ (y * 67u)) & 1023u; }
+  void chain_insert(uint32_t slot);
+  void chain_remove(uint32_t slot);
   uint32_t m_cur_lo = 0, m_cur_hi = 0; // slots supplying palette entries 0..15 / 16..255 right now
   uint32_t m_alloc_hand = 1;
   uint32_t m_epoch_serial = 0;
-  HazardGrid m_clut_sources; // superset of the valid slots' source pixels (prefilter for invalidation)
+  HazardSet m_clut_sources; // superset of the valid slots' source pixels (prefilter for invalidation)
   void invalidate_cluts(const RectSet& writes);
 
   // open epoch
   uint32_t m_epoch_cmd_begin = 0;
   uint32_t m_epoch_clut_begin = 0;
-  HazardGrid m_writes, m_reads;
+  HazardSet m_writes, m_reads;
 };
 
 } // namespace psx

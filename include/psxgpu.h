@@ -102,6 +102,10 @@ int psxgpu_flush(psxgpu_ctx* ctx);
 /* Wait for everything launched so far. */
 int psxgpu_sync(psxgpu_ctx* ctx);
 
+/* psxgpu_submit_batch cuts a batch into chunks of this many instances and launches each chunk as soon as it is
+ * encoded, so that host encoding overlaps copies and kernels.  0 = automatic (count/8, at least 128). */
+int psxgpu_set_batch_chunk(psxgpu_ctx* ctx, uint32_t instances_per_chunk);
+
 /* Re-run the device part of the most recent flush (setup + all waves) from the command buffers that are still
  * resident in HBM.  For steady-state measurement; the caller is responsible for the VRAM state it starts from. */
 int psxgpu_run_staged(psxgpu_ctx* ctx);
