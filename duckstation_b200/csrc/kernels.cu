@@ -364,6 +364,16 @@ __device__ __forceinline__ void raster_prim_on_region(const PrimSetup& s, uint32
     case OP_FILL:
     {
       const uint32_t px0 = rx0 + 2 * lane;
+      // whole tile inside the rectangle and no interlace skip: 32 stores, nothing to test
+      if (!s.fill.interlaced && ((rx0 - s.fill.x) & (VRAM_W - 1)) + TILE_W <= s.fill.w &&
+          ((ry0 - s.fill.y) & (VRAM_H - 1)) + TILE_H <= s.fill.h)
+      {
+        const uint32_t c2 = static_cast<uint32_t>(s.fill.color16) * 0x10001u;
+#pragma unroll 8
+        for (uint32_t r = 0; r < TILE_H; r++)
+          region[r * REGION_PITCH + lane] = c2;
+        break;
+      }
 #pragma unroll 4
       for (uint32_t r = 0; r < TILE_H; r++)
       {
@@ -635,19 +645,27 @@ __global__ void __launch_bounds__(SERIAL_THREADS) serial_kernel(const WaveItem* 
 }
 
 // One warp per (instance, tile).  No block-level barrier anywhere: the hardware CTA scheduler balances tiles.
-__global__ void __launch_bounds__(32, 32) raster_kernel(const WaveItem* __restrict__ items, const PrimSetup* __restrict__ setups,
+#ifndef PSX_RASTER_WARPS
+#define PSX_RASTER_WARPS 1 // independent tiles (warps) per CTA; no barrier between them
+#endif
+#ifndef PSX_RASTER_MIN_CTAS
+#define PSX_RASTER_MIN_CTAS 32
+#endif
+__global__ void __launch_bounds__(32 * PSX_RASTER_WARPS, PSX_RASTER_MIN_CTAS) raster_kernel(const WaveItem* __restrict__ items, const PrimSetup* __restrict__ setups,
                                                         const BinInfo* __restrict__ bins, uint16_t* __restrict__ vram_pool,
                                                         const uint16_t* __restrict__ clut_pool,
                                                         const uint16_t* __restrict__ payload, uint32_t clut_slots)
 {
-  __shared__ RasterShared sh;
+  __shared__ RasterShared sh_all[PSX_RASTER_WARPS];
+  RasterShared& sh = sh_all[threadIdx.x >> 5];
   const WaveItem it = items[blockIdx.y];
   if (it.kind != EPOCH_TILED || it.cmd_begin == it.cmd_end)
     return;
   uint16_t* vram = vram_pool + static_cast<size_t>(it.instance) * VRAM_PIXELS;
   const uint16_t* cluts = clut_pool + static_cast<size_t>(it.instance) * clut_slots * CLUT_ENTRIES;
-  const uint32_t lane = threadIdx.x;
-  const uint32_t tx = blockIdx.x % TILES_X, ty = blockIdx.x / TILES_X;
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t tile = blockIdx.x * PSX_RASTER_WARPS + (threadIdx.x >> 5);
+  const uint32_t tx = tile % TILES_X, ty = tile / TILES_X;
   const uint32_t rx0 = tx * TILE_W, ry0 = ty * TILE_H;
   const uint32_t tile_bits = (1u << tx) | (1u << (16 + ty));
   uint32_t* gword = reinterpret_cast<uint32_t*>(vram + ry0 * VRAM_W + rx0) + lane; // this lane's word of tile row 0
@@ -854,7 +872,7 @@ cudaError_t launch_raster(const WaveItem* items, uint32_t n_items, const PrimSet
   for (uint32_t off = 0; off < n_items; off += 32768)
   {
     const uint32_t n = (n_items - off) < 32768u ? (n_items - off) : 32768u;
-    raster_kernel<<<dim3(NUM_TILES, n), 32, 0, st>>>(items + off, setups, bins, vram_pool, clut_pool, payload, clut_slots);
+    raster_kernel<<<dim3(NUM_TILES / PSX_RASTER_WARPS, n), 32 * PSX_RASTER_WARPS, 0, st>>>(items + off, setups, bins, vram_pool, clut_pool, payload, clut_slots);
   }
   return cudaGetLastError();
 }

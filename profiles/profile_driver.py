@@ -12,6 +12,7 @@ config = int(sys.argv[3]) if len(sys.argv) > 3 else 4
 prims = int(sys.argv[4]) if len(sys.argv) > 4 else 2000
 wire = [streams.generate(config, i, prims, 0) for i in range(n)]
 with Context(n, profile=True) as ctx:
+    ctx.set_batch_chunk(n)  # one chunk: one setup + one raster launch per wave
     ctx.submit_batch(wire)
     ctx.flush()
     ctx.sync()
