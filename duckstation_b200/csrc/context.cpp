@@ -122,6 +122,7 @@ struct psxgpu_ctx
   uint16_t* d_vram = nullptr;
   uint16_t* d_clut = nullptr;
   unsigned long long* d_hash = nullptr;
+  unsigned int* d_barrier = nullptr;
 
   std::vector<Encoder> enc;
   std::vector<uint8_t> dirty;
@@ -134,8 +135,10 @@ struct psxgpu_ctx
   // overlaps the copy + kernels of chunk k); psxgpu_run_staged replays the last closed group.
   struct Chunk
   {
-    DevBuf d_cmds, d_setups, d_bins, d_payload, d_clutops, d_items;
+    DevBuf d_cmds, d_setups, d_bins, d_payload, d_clutops, d_items, d_misc;
     uint32_t n_cmds = 0;
+    bool persistent = false; // few instances: one cooperative launch for all waves (raster_persistent_kernel)
+    uint32_t n_instances = 0;
     std::vector<uint32_t> wave_off{0}; // wave k = items [wave_off[k], wave_off[k+1])
     std::vector<uint8_t> wave_has_clut, wave_has_tiled, wave_has_serial;
     std::vector<cudaEvent_t> ev_raster; // pairs, profile mode
@@ -146,11 +149,12 @@ struct psxgpu_ctx
   bool group_open = false;
   uint32_t staged_n = 0;    // chunks of the last closed group
   uint32_t batch_chunk = 0; // instances per chunk in psxgpu_submit_batch (0 = auto)
+  uint32_t persist_max = 0; // largest instance count the persistent kernel can hold co-resident (0 = unavailable)
 
   // pinned staging, triple buffered: a set may be refilled once the copies that read it have completed
   struct PinnedSet
   {
-    PinnedBuf cmds, payload, clutops, items;
+    PinnedBuf cmds, payload, clutops, items, misc;
     cudaEvent_t free_ev = nullptr;
     bool in_flight = false;
   };
@@ -247,8 +251,21 @@ int run_chunk(psxgpu_ctx* ctx, psxgpu_ctx::Chunk& S)
   if (S.n_cmds)
     ctx->counters.kernel_launches++;
   const uint32_t waves = static_cast<uint32_t>(S.wave_off.size()) - 1;
-  const bool prof = ctx->opts.profile != 0;
   S.ev_raster_used = 0;
+  if (S.persistent)
+  {
+    const uint8_t* misc = static_cast<const uint8_t*>(S.d_misc.p);
+    CK(launch_persistent(static_cast<const WaveItem*>(S.d_items.p), misc, waves,
+                         reinterpret_cast<const uint32_t*>(misc + static_cast<size_t>(waves) * 16), S.n_instances,
+                         static_cast<const PrimSetup*>(S.d_setups.p), static_cast<const BinInfo*>(S.d_bins.p),
+                         static_cast<const ClutOp*>(S.d_clutops.p), ctx->d_vram, ctx->d_clut,
+                         static_cast<const uint16_t*>(S.d_payload.p), ctx->clut_slots, ctx->d_barrier, ctx->stream),
+       "raster_persistent_kernel");
+    ctx->counters.kernel_launches++;
+    ctx->counters.waves += waves;
+    return PSXGPU_OK;
+  }
+  const bool prof = ctx->opts.profile != 0;
   if (prof)
   {
     while (S.ev_raster.size() < static_cast<size_t>(waves) * 2)
@@ -421,6 +438,26 @@ int launch_chunk(psxgpu_ctx* ctx, const std::vector<uint32_t>& work, const std::
     S.wave_has_serial.push_back(has_serial);
   }
   S.n_cmds = static_cast<uint32_t>(n_cmds);
+  S.n_instances = nw;
+  const uint32_t n_waves = static_cast<uint32_t>(S.wave_off.size()) - 1;
+  S.persistent = ctx->persist_max != 0 && nw <= ctx->persist_max && n_waves > 0 && !ctx->opts.profile;
+  size_t misc_bytes = 0;
+  if (S.persistent)
+  {
+    misc_bytes = static_cast<size_t>(n_waves) * 16 + static_cast<size_t>(nw) * 4;
+    CK(P.misc.ensure(misc_bytes), "pinned alloc (wave table)");
+    CK(S.d_misc.ensure(misc_bytes + 16), "device alloc (wave table)");
+    uint32_t* wv = static_cast<uint32_t*>(P.misc.p);
+    for (uint32_t k = 0; k < n_waves; k++)
+    {
+      wv[k * 4 + 0] = S.wave_off[k];
+      wv[k * 4 + 1] = S.wave_off[k + 1] - S.wave_off[k];
+      wv[k * 4 + 2] = S.wave_has_clut[k];
+      wv[k * 4 + 3] = 0;
+    }
+    for (uint32_t w = 0; w < nw; w++)
+      wv[n_waves * 4 + w] = work[w];
+  }
   // everything the encoders held is in the pinned set now
   for (uint32_t w = 0; w < nw; w++)
   {
@@ -436,6 +473,8 @@ int launch_chunk(psxgpu_ctx* ctx, const std::vector<uint32_t>& work, const std::
     CK(cudaMemcpyAsync(S.d_clutops.p, ho, n_clut * sizeof(ClutOp), cudaMemcpyHostToDevice, ctx->stream), "H2D clut ops");
   if (n_items)
     CK(cudaMemcpyAsync(S.d_items.p, hi, n_items * sizeof(WaveItem), cudaMemcpyHostToDevice, ctx->stream), "H2D wave items");
+  if (misc_bytes)
+    CK(cudaMemcpyAsync(S.d_misc.p, P.misc.p, misc_bytes, cudaMemcpyHostToDevice, ctx->stream), "H2D wave table");
   CK(cudaEventRecord(P.free_ev, ctx->stream), "event record");
   P.in_flight = true;
   ctx->counters.h2d_bytes += n_cmds * sizeof(PackedCmd) + n_pay * 2 + n_clut * sizeof(ClutOp) + n_items * sizeof(WaveItem);
@@ -639,6 +678,8 @@ int psxgpu_create(int device, uint32_t n_instances, const psxgpu_opts* opts, psx
     return bail(e, "CLUT pool");
   if ((e = cudaMalloc(&ctx->d_hash, static_cast<size_t>(n_instances) * 8)) != cudaSuccess)
     return bail(e, "hash buffer");
+  if ((e = cudaMalloc(&ctx->d_barrier, 64)) != cudaSuccess)
+    return bail(e, "barrier counter");
   if ((e = cudaMemsetAsync(ctx->d_vram, 0, static_cast<size_t>(n_instances) * VRAM_PIXELS * 2, ctx->stream)) != cudaSuccess)
     return bail(e, "VRAM clear");
   if ((e = cudaMemsetAsync(ctx->d_clut, 0, static_cast<size_t>(n_instances) * ctx->clut_slots * CLUT_ENTRIES * 2, ctx->stream)) !=
@@ -653,6 +694,9 @@ int psxgpu_create(int device, uint32_t n_instances, const psxgpu_opts* opts, psx
   if ((e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess)
     return bail(e, "sync");
 
+  ctx->persist_max = static_cast<uint32_t>(std::max(0, persistent_max_instances(device)));
+  if (ctx->opts.reserved[0] == 1) // latency mode disabled (opts.reserved[0] = no_persistent)
+    ctx->persist_max = 0;
   ctx->enc.reserve(n_instances);
   for (uint32_t i = 0; i < n_instances; i++)
   {
@@ -675,14 +719,14 @@ void psxgpu_destroy(psxgpu_ctx* ctx)
   ctx->d_scan.release();
   for (psxgpu_ctx::PinnedSet& ps : ctx->pinned)
   {
-    for (PinnedBuf* b : {&ps.cmds, &ps.payload, &ps.clutops, &ps.items})
+    for (PinnedBuf* b : {&ps.cmds, &ps.payload, &ps.clutops, &ps.items, &ps.misc})
       b->release();
     if (ps.free_ev)
       cudaEventDestroy(ps.free_ev);
   }
   for (psxgpu_ctx::Chunk* ch : ctx->chunks)
   {
-    for (DevBuf* b : {&ch->d_cmds, &ch->d_setups, &ch->d_bins, &ch->d_payload, &ch->d_clutops, &ch->d_items})
+    for (DevBuf* b : {&ch->d_cmds, &ch->d_setups, &ch->d_bins, &ch->d_payload, &ch->d_clutops, &ch->d_items, &ch->d_misc})
       b->release();
     for (cudaEvent_t ev : ch->ev_raster)
       cudaEventDestroy(ev);
@@ -694,6 +738,8 @@ void psxgpu_destroy(psxgpu_ctx* ctx)
     cudaFree(ctx->d_clut);
   if (ctx->d_hash)
     cudaFree(ctx->d_hash);
+  if (ctx->d_barrier)
+    cudaFree(ctx->d_barrier);
   for (cudaEvent_t ev : {ctx->ev_start, ctx->ev_end, ctx->ev_hash0, ctx->ev_hash1})
     if (ev)
       cudaEventDestroy(ev);

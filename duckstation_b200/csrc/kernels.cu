@@ -77,10 +77,12 @@ constexpr uint32_t SETUP_WORDS = sizeof(PrimSetup) / 4; // 40
 constexpr uint32_t REGION_PITCH = 33;                   // words per tile row in shared memory (+1: bank skew)
 constexpr uint32_t REGION_PITCH16 = REGION_PITCH * 2;   // same, in pixels
 
-// raster_kernel: one warp == one CTA == one 64x32 tile.  5.9 KiB of shared memory, so 32 CTAs fit an SM.
+// Per-warp shared memory.  raster_kernel: one warp == one CTA == one 64x32 tile (RH = 32), 5.9 KiB, so 32 CTAs fit an SM.
+// raster_persistent_kernel: four warps per CTA, each owning a 64x8 strip of the tile (RH = 8).
+template<uint32_t RH>
 struct alignas(16) RasterShared
 {
-  uint32_t region[TILE_H * REGION_PITCH]; // 4224 B: the tile, 2 pixels per word
+  uint32_t region[RH * REGION_PITCH];     // the region, 2 pixels per word (4224 B at RH = 32)
   uint32_t stage[SETUP_WORDS];            // the primitive being rasterised
   uint16_t clut[CLUT_ENTRIES];            // merged palette of the current primitive (entries 0-15 lo slot, 16-255 hi slot)
   uint16_t list[LIST_CAP];                // bin: primitive indices (relative to the epoch), submission order
@@ -104,13 +106,21 @@ __device__ __forceinline__ ShadeState shade_state_from_words(const uint32_t* w)
   return st;
 }
 
+// kCoh: the kernel outlives an epoch (persistent kernel), so VRAM / CLUT-slot reads must not come from a stale L1 line.
+template<bool kCoh, typename T>
+__device__ __forceinline__ T ld_ro(const T* p)
+{
+  return kCoh ? __ldcg(p) : __ldg(p);
+}
+
 // One pixel through the pipeline.  bg = current value; returns the new value.
+template<bool kCoh>
 __device__ __forceinline__ uint32_t shade_pixel(const ShadeState& st, const PixelCtx& ctx, uint32_t px, uint32_t Y, uint32_t r,
                                                 uint32_t g, uint32_t b, uint32_t u, uint32_t v, uint32_t bg)
 {
   uint32_t texel = 0;
   if (st.flags & F_TEXTURE)
-    texel = fetch_texel<false, true>(st, ctx.vram, ctx.clut, ctx.clut, u, v);
+    texel = fetch_texel<kCoh, true>(st, ctx.vram, ctx.clut, ctx.clut, u, v);
   uint32_t colour;
   if (!shade_colour(st, px, Y, r, g, b, texel, colour))
     return bg;
@@ -152,12 +162,12 @@ __device__ __forceinline__ uint32_t row_of_pixel(uint32_t incl, uint32_t j)
 // Triangle on one tile.  Lane r works out the span of tile row r (one pass for all 32 rows); the covered pixels of all
 // rows are compacted with a prefix sum and shaded 32 at a time, one per lane.  What a pixel lane needs from its row
 // lane travels by shuffle: the column offset (+ raw-x delta) in one word and the per-row interpolant bases.
-template<bool kShaded, bool kTextured>
+template<uint32_t RH, bool kCoh, bool kShaded, bool kTextured>
 __device__ __forceinline__ void raster_triangle(const PrimSetup& s, const ShadeState st, const PixelCtx& ctx,
                                                 uint16_t* __restrict__ region16, int32_t x_min, uint32_t ry0, uint32_t lane)
 {
   TriRow row;
-  const bool valid = tri_row(s, ry0 + lane, row);
+  const bool valid = (RH == 32 || lane < RH) && tri_row(s, ry0 + lane, row);
   const int32_t xs = valid ? imax(row.x_lo, x_min) : 0, xe = valid ? imin(row.x_hi, x_min + static_cast<int32_t>(TILE_W)) : 0;
   const uint32_t cnt = (xe > xs) ? static_cast<uint32_t>(xe - xs) : 0u;
   const uint32_t incl = warp_inclusive_scan(cnt, lane);
@@ -220,18 +230,19 @@ __device__ __forceinline__ void raster_triangle(const PrimSetup& s, const ShadeS
     {
       uint16_t* p = region16 + r * REGION_PITCH16 + (px - x_min);
       const uint32_t bg = *p;
-      const uint32_t out = shade_pixel(st, ctx, static_cast<uint32_t>(px), ry0 + r, cr, cg, cb, cu, cv, bg);
+      const uint32_t out = shade_pixel<kCoh>(st, ctx, static_cast<uint32_t>(px), ry0 + r, cr, cg, cb, cu, cv, bg);
       if (out != bg)
         *p = static_cast<uint16_t>(out);
     }
   }
 }
 
+template<uint32_t RH, bool kCoh>
 __device__ __forceinline__ void raster_rect(const PrimSetup& s, const ShadeState st, const PixelCtx& ctx,
                                             uint16_t* __restrict__ region16, int32_t x_min, uint32_t ry0, uint32_t lane)
 {
   RectRow row;
-  const bool valid = rect_row(s, ry0 + lane, row);
+  const bool valid = (RH == 32 || lane < RH) && rect_row(s, ry0 + lane, row);
   const int32_t xs = valid ? imax(row.x_lo, x_min) : 0, xe = valid ? imin(row.x_hi, x_min + static_cast<int32_t>(TILE_W)) : 0;
   const uint32_t cnt = (xe > xs) ? static_cast<uint32_t>(xe - xs) : 0u;
   const uint32_t incl = warp_inclusive_scan(cnt, lane);
@@ -252,16 +263,17 @@ __device__ __forceinline__ void raster_rect(const PrimSetup& s, const ShadeState
     {
       uint16_t* p = region16 + r * REGION_PITCH16 + (px - x_min);
       const uint32_t bg = *p;
-      const uint32_t out = shade_pixel(st, ctx, static_cast<uint32_t>(px), ry0 + r, cr, cg, cb,
-                                       (ubias + static_cast<uint32_t>(px)) & 0xFFu, pk >> 16, bg);
+      const uint32_t out = shade_pixel<kCoh>(st, ctx, static_cast<uint32_t>(px), ry0 + r, cr, cg, cb,
+                                             (ubias + static_cast<uint32_t>(px)) & 0xFFu, pk >> 16, bg);
       if (out != bg)
         *p = static_cast<uint16_t>(out);
     }
   }
 }
 
-// A warp applies one primitive to its tile (rows ry0 .. ry0+31, columns rx0 .. rx0+63), held in shared memory.
+// A warp applies one primitive to its region (rows ry0 .. ry0+RH-1, columns rx0 .. rx0+63), held in shared memory.
 // clut_key: which palette (lo slot | hi slot << 8 | depth << 16) currently sits in clut_smem; reloaded on change.
+template<uint32_t RH, bool kCoh>
 __device__ __forceinline__ void raster_prim_on_region(const PrimSetup& s, uint32_t* __restrict__ region, uint32_t rx0, uint32_t ry0,
                                                       const uint16_t* vram, const uint16_t* clut_pool_inst,
                                                       const uint16_t* __restrict__ payload, uint16_t* clut_smem, uint32_t& clut_key,
@@ -285,11 +297,11 @@ __device__ __forceinline__ void raster_prim_on_region(const PrimSetup& s, uint32
       uint4* dst = reinterpret_cast<uint4*>(clut_smem);
       if (is8)
       {
-        dst[lane] = __ldg(reinterpret_cast<const uint4*>(clut_pool_inst + hi * CLUT_ENTRIES) + lane);
+        dst[lane] = ld_ro<kCoh>(reinterpret_cast<const uint4*>(clut_pool_inst + hi * CLUT_ENTRIES) + lane);
         __syncwarp();
       }
       if (lane < 2 && (!is8 || lo != hi))
-        dst[lane] = __ldg(reinterpret_cast<const uint4*>(clut_pool_inst + lo * CLUT_ENTRIES) + lane);
+        dst[lane] = ld_ro<kCoh>(reinterpret_cast<const uint4*>(clut_pool_inst + lo * CLUT_ENTRIES) + lane);
       __syncwarp();
     }
   }
@@ -304,21 +316,21 @@ __device__ __forceinline__ void raster_prim_on_region(const PrimSetup& s, uint32
       if (textured)
       {
         if (shaded)
-          raster_triangle<true, true>(s, st, ctx, region16, x_min, ry0, lane);
+          raster_triangle<RH, kCoh, true, true>(s, st, ctx, region16, x_min, ry0, lane);
         else
-          raster_triangle<false, true>(s, st, ctx, region16, x_min, ry0, lane);
+          raster_triangle<RH, kCoh, false, true>(s, st, ctx, region16, x_min, ry0, lane);
       }
       else
       {
         if (shaded)
-          raster_triangle<true, false>(s, st, ctx, region16, x_min, ry0, lane);
+          raster_triangle<RH, kCoh, true, false>(s, st, ctx, region16, x_min, ry0, lane);
         else
-          raster_triangle<false, false>(s, st, ctx, region16, x_min, ry0, lane);
+          raster_triangle<RH, kCoh, false, false>(s, st, ctx, region16, x_min, ry0, lane);
       }
     }
     break;
 
-    case OP_RECT: raster_rect(s, st, ctx, region16, x_min, ry0, lane); break;
+    case OP_RECT: raster_rect<RH, kCoh>(s, st, ctx, region16, x_min, ry0, lane); break;
 
     case OP_LINE:
     {
@@ -334,10 +346,10 @@ __device__ __forceinline__ void raster_prim_on_region(const PrimSetup& s, uint32
           {
             const uint32_t Y = static_cast<uint32_t>(p.y) & (VRAM_H - 1);
             const uint32_t r = Y - ry0;
-            if (r < TILE_H)
+            if (r < RH)
             {
               uint16_t* q = region16 + r * REGION_PITCH16 + (px - x_min);
-              *q = static_cast<uint16_t>(shade_pixel(st, ctx, static_cast<uint32_t>(px), Y, p.r, p.g, p.b, 0, 0, *q));
+              *q = static_cast<uint16_t>(shade_pixel<kCoh>(st, ctx, static_cast<uint32_t>(px), Y, p.r, p.g, p.b, 0, 0, *q));
             }
           }
         }
@@ -347,13 +359,13 @@ __device__ __forceinline__ void raster_prim_on_region(const PrimSetup& s, uint32
         // at most one pixel per row: lane r takes tile row r
         const uint32_t Y = ry0 + lane;
         LinePixel p;
-        if (line_step(s, line_step_for_row(s, Y), p) && (static_cast<uint32_t>(p.y) & (VRAM_H - 1)) == Y)
+        if ((RH == 32 || lane < RH) && line_step(s, line_step_for_row(s, Y), p) && (static_cast<uint32_t>(p.y) & (VRAM_H - 1)) == Y)
         {
           const uint32_t col = static_cast<uint32_t>(p.x) - rx0;
           if (col < TILE_W)
           {
             uint16_t* q = region16 + lane * REGION_PITCH16 + col;
-            *q = static_cast<uint16_t>(shade_pixel(st, ctx, static_cast<uint32_t>(p.x), Y, p.r, p.g, p.b, 0, 0, *q));
+            *q = static_cast<uint16_t>(shade_pixel<kCoh>(st, ctx, static_cast<uint32_t>(p.x), Y, p.r, p.g, p.b, 0, 0, *q));
           }
         }
       }
@@ -366,16 +378,16 @@ __device__ __forceinline__ void raster_prim_on_region(const PrimSetup& s, uint32
       const uint32_t px0 = rx0 + 2 * lane;
       // whole tile inside the rectangle and no interlace skip: 32 stores, nothing to test
       if (!s.fill.interlaced && ((rx0 - s.fill.x) & (VRAM_W - 1)) + TILE_W <= s.fill.w &&
-          ((ry0 - s.fill.y) & (VRAM_H - 1)) + TILE_H <= s.fill.h)
+          ((ry0 - s.fill.y) & (VRAM_H - 1)) + RH <= s.fill.h)
       {
         const uint32_t c2 = static_cast<uint32_t>(s.fill.color16) * 0x10001u;
 #pragma unroll 8
-        for (uint32_t r = 0; r < TILE_H; r++)
+        for (uint32_t r = 0; r < RH; r++)
           region[r * REGION_PITCH + lane] = c2;
         break;
       }
 #pragma unroll 4
-      for (uint32_t r = 0; r < TILE_H; r++)
+      for (uint32_t r = 0; r < RH; r++)
       {
         const uint32_t Y = ry0 + r;
         const bool c0 = fill_covers(s, px0, Y), c1 = fill_covers(s, px0 + 1, Y);
@@ -395,7 +407,7 @@ __device__ __forceinline__ void raster_prim_on_region(const PrimSetup& s, uint32
     {
       const uint32_t px0 = rx0 + 2 * lane;
 #pragma unroll 2
-      for (uint32_t r = 0; r < TILE_H; r++)
+      for (uint32_t r = 0; r < RH; r++)
       {
         const uint32_t Y = ry0 + r;
         uint32_t s0, s1;
@@ -404,9 +416,9 @@ __device__ __forceinline__ void raster_prim_on_region(const PrimSetup& s, uint32
           continue;
         uint32_t word = region[r * REGION_PITCH + lane];
         if (c0)
-          word = set_half(word, 0, transfer_write(s, static_cast<uint16_t>(word), __ldg(vram + s0)));
+          word = set_half(word, 0, transfer_write(s, static_cast<uint16_t>(word), ld_ro<kCoh>(vram + s0)));
         if (c1)
-          word = set_half(word, 1, transfer_write(s, static_cast<uint16_t>(word >> 16), __ldg(vram + s1)));
+          word = set_half(word, 1, transfer_write(s, static_cast<uint16_t>(word >> 16), ld_ro<kCoh>(vram + s1)));
         region[r * REGION_PITCH + lane] = word;
       }
     }
@@ -416,7 +428,7 @@ __device__ __forceinline__ void raster_prim_on_region(const PrimSetup& s, uint32
     {
       const uint32_t px0 = rx0 + 2 * lane;
 #pragma unroll 2
-      for (uint32_t r = 0; r < TILE_H; r++)
+      for (uint32_t r = 0; r < RH; r++)
       {
         const uint32_t Y = ry0 + r;
         uint32_t p0, p1;
@@ -451,22 +463,42 @@ __device__ void serial_self_sampling(const PrimSetup& s, uint16_t* vram, const u
   volatile uint16_t* vv = vram;
   const ShadeState st = make_shade_state(s);
 
-  auto group = [&](int32_t x0, uint32_t Y, bool active, uint32_t r, uint32_t g, uint32_t b, uint32_t u, uint32_t v) {
-    uint32_t texel = 0;
-    if (active)
-      texel = fetch_texel<true>(st, vram, clut_lo, clut_hi, u, v);
-    __syncwarp();
-    if (active)
+  // Eight consecutive 4-pixel groups of one row (pixels x0 .. x0+31, lane = pixel).  The reference runs them one after
+  // the other; running them together is the same thing unless a texel of group k is one of the pixels that groups
+  // 0..k-1 of this batch store.  That is checked on the addresses; only then the batch is replayed group by group.
+  auto batch = [&](int32_t x0, uint32_t Y, bool active, uint32_t r, uint32_t g, uint32_t b, uint32_t u, uint32_t v) {
+    uint32_t shift, idxmask;
+    const uint32_t addr = texel_addr(st, u, v, shift, idxmask);
+    const uint32_t first_px = Y * VRAM_W + static_cast<uint32_t>(x0);
+    const bool conflict = active && (addr - first_px) < (lane & ~3u); // texel in [first_px, first_px + 4k), k = lane / 4
+    const bool serial = __any_sync(0xFFFFFFFFu, conflict);
+    for (uint32_t k = 0; k < (serial ? 8u : 1u); k++)
     {
-      uint32_t colour;
-      const uint32_t px = static_cast<uint32_t>(x0) + lane;
-      if (shade_colour(st, px, Y, r, g, b, texel, colour))
+      const bool mine = active && (!serial || (lane >> 2) == k);
+      uint32_t texel = 0;
+      if (mine)
       {
-        const uint16_t bg = vv[Y * VRAM_W + px];
-        vv[Y * VRAM_W + px] = static_cast<uint16_t>(blend_mask(st, bg, colour));
+        const uint32_t w = vv[addr];
+        texel = w;
+        if (idxmask != 0)
+        {
+          const uint32_t idx = (w >> shift) & idxmask;
+          texel = __ldg((idx < 16u ? clut_lo : clut_hi) + idx);
+        }
       }
+      __syncwarp();
+      if (mine)
+      {
+        uint32_t colour;
+        const uint32_t px = static_cast<uint32_t>(x0) + lane;
+        if (shade_colour(st, px, Y, r, g, b, texel, colour))
+        {
+          const uint16_t bg = vv[Y * VRAM_W + px];
+          vv[Y * VRAM_W + px] = static_cast<uint16_t>(blend_mask(st, bg, colour));
+        }
+      }
+      __syncwarp();
     }
-    __syncwarp();
   };
 
   if (s.op == OP_RECT)
@@ -478,11 +510,12 @@ __device__ void serial_self_sampling(const PrimSetup& s, uint16_t* vram, const u
       RectRow row;
       if (!rect_row(s, Y, row) || row.y != y)
         continue;
-      for (uint32_t ox = 0; ox < s.rect.w; ox += 4)
+      // groups are counted from the unclipped origin (inl:777-779); 32 is a multiple of 4, so batches keep that phase
+      for (uint32_t ox = 0; ox < s.rect.w; ox += 32)
       {
         const int32_t x = s.rect.x + static_cast<int32_t>(ox + lane);
-        const bool active = lane < 4 && (ox + lane) < s.rect.w && x >= row.x_lo && x < row.x_hi;
-        group(s.rect.x + static_cast<int32_t>(ox), Y, active, s.rect.r, s.rect.g, s.rect.b, (s.rect.u0 + ox + lane) & 0xFFu, row.v);
+        const bool active = (ox + lane) < s.rect.w && x >= row.x_lo && x < row.x_hi;
+        batch(s.rect.x + static_cast<int32_t>(ox), Y, active, s.rect.r, s.rect.g, s.rect.b, (s.rect.u0 + ox + lane) & 0xFFu, row.v);
       }
     }
     return;
@@ -504,13 +537,14 @@ __device__ void serial_self_sampling(const PrimSetup& s, uint16_t* vram, const u
       TriRow row;
       if (!tri_row(s, Y, row) || row.cy != cy)
         continue;
-      for (int32_t gx = row.x_lo; gx < row.x_hi; gx += 4)
+      // groups are counted from the clipped span start (inl:1262-1268)
+      for (int32_t gx = row.x_lo; gx < row.x_hi; gx += 32)
       {
         const int32_t px = gx + static_cast<int32_t>(lane);
-        const bool active = lane < 4 && px < row.x_hi;
+        const bool active = px < row.x_hi;
         uint32_t r, g, b, u, v;
         tri_attrs(s, row, px, r, g, b, u, v);
-        group(gx, Y, active, r, g, b, u, v);
+        batch(gx, Y, active, r, g, b, u, v);
       }
     }
   }
@@ -518,6 +552,7 @@ __device__ void serial_self_sampling(const PrimSetup& s, uint16_t* vram, const u
 
 // CopyVRAM whose source and destination alias: wrap split in the reference's order, rows sequential, each row
 // read completely before it is written (CopyVRAMImpl, inl:1833-1939).
+template<int NT>
 __device__ void serial_copy_rows(uint16_t* vram, uint32_t sx, uint32_t sy, uint32_t dx, uint32_t dy, uint32_t w, uint32_t h,
                                  uint16_t mand, uint16_t mor)
 {
@@ -525,18 +560,18 @@ __device__ void serial_copy_rows(uint16_t* vram, uint32_t sx, uint32_t sy, uint3
   for (uint32_t r = 0; r < h; r++)
   {
     const uint32_t srow = ((sy + r) & (VRAM_H - 1)) * VRAM_W, drow = ((dy + r) & (VRAM_H - 1)) * VRAM_W;
-    uint16_t px[VRAM_W / SERIAL_THREADS];
+    uint16_t px[VRAM_W / NT];
 #pragma unroll
-    for (uint32_t k = 0; k < VRAM_W / SERIAL_THREADS; k++)
+    for (uint32_t k = 0; k < VRAM_W / NT; k++)
     {
-      const uint32_t c = k * SERIAL_THREADS + threadIdx.x;
+      const uint32_t c = k * NT + threadIdx.x;
       px[k] = (c < w) ? vv[srow + ((sx + c) & (VRAM_W - 1))] : uint16_t(0);
     }
     __syncthreads();
 #pragma unroll
-    for (uint32_t k = 0; k < VRAM_W / SERIAL_THREADS; k++)
+    for (uint32_t k = 0; k < VRAM_W / NT; k++)
     {
-      const uint32_t c = k * SERIAL_THREADS + threadIdx.x;
+      const uint32_t c = k * NT + threadIdx.x;
       if (c < w)
       {
         const uint32_t a = drow + ((dx + c) & (VRAM_W - 1));
@@ -548,13 +583,14 @@ __device__ void serial_copy_rows(uint16_t* vram, uint32_t sx, uint32_t sy, uint3
   }
 }
 
+template<int NT>
 __device__ void serial_copy(const PrimSetup& s, uint16_t* vram)
 {
   const uint16_t mand = (s.flags0 & F_CHECK_MASK) ? 0x8000u : 0, mor = (s.flags0 & F_SET_MASK) ? 0x8000u : 0;
   const uint32_t sx = s.copy.sx, sy = s.copy.sy, dx = s.copy.dx, dy = s.copy.dy, w = s.copy.w, h = s.copy.h;
   if ((sx + w) <= VRAM_W && (dx + w) <= VRAM_W)
   {
-    serial_copy_rows(vram, sx, sy, dx, dy, w, h, mand, mor);
+    serial_copy_rows<NT>(vram, sx, sy, dx, dy, w, h, mand, mor);
     return;
   }
   uint32_t rem_rows = h, csy = sy, cdy = dy;
@@ -565,7 +601,7 @@ __device__ void serial_copy(const PrimSetup& s, uint16_t* vram)
     while (rem_cols > 0)
     {
       const uint32_t cols = min(rem_cols, min(VRAM_W - csx, VRAM_W - cdx));
-      serial_copy_rows(vram, csx, csy, cdx, cdy, cols, rows, mand, mor);
+      serial_copy_rows<NT>(vram, csx, csy, cdx, cdy, cols, rows, mand, mor);
       csx = (csx + cols) & (VRAM_W - 1);
       cdx = (cdx + cols) & (VRAM_W - 1);
       rem_cols -= cols;
@@ -578,6 +614,7 @@ __device__ void serial_copy(const PrimSetup& s, uint16_t* vram)
 
 // mask-checked upload.  Source index of a pixel = its linear index minus the number of masked pixels
 // before it (in scan order) that sit in the scalar tail of their row (columns >= aw).
+template<int NT>
 __device__ void serial_upload_masked(const PrimSetup& s, uint16_t* vram, const uint16_t* __restrict__ payload,
                                      uint32_t* warp_count)
 {
@@ -589,7 +626,7 @@ __device__ void serial_upload_masked(const PrimSetup& s, uint16_t* vram, const u
   for (uint32_t r = 0; r < U.h; r++)
   {
     const uint32_t drow = ((U.y + r) & (VRAM_H - 1)) * VRAM_W;
-    for (uint32_t base = 0; base < U.w; base += SERIAL_THREADS)
+    for (uint32_t base = 0; base < U.w; base += NT)
     {
       const uint32_t c = base + threadIdx.x;
       const bool in = c < U.w;
@@ -604,7 +641,7 @@ __device__ void serial_upload_masked(const PrimSetup& s, uint16_t* vram, const u
       uint32_t before = __popc(bal & ((1u << lane) - 1u));
       uint32_t total = 0;
 #pragma unroll
-      for (uint32_t k = 0; k < SERIAL_WARPS; k++)
+      for (uint32_t k = 0; k < NT / 32; k++)
       {
         const uint32_t n = warp_count[k];
         before += (k < warp) ? n : 0u;
@@ -639,36 +676,22 @@ __global__ void __launch_bounds__(SERIAL_THREADS) serial_kernel(const WaveItem* 
   if (it.kind == EPOCH_SELF_SAMPLING)
     serial_self_sampling(s, vram, cluts);
   else if (it.kind == EPOCH_COPY_OVERLAP)
-    serial_copy(s, vram);
+    serial_copy<SERIAL_THREADS>(s, vram);
   else
-    serial_upload_masked(s, vram, payload, warp_count);
+    serial_upload_masked<SERIAL_THREADS>(s, vram, payload, warp_count);
 }
 
-// One warp per (instance, tile).  No block-level barrier anywhere: the hardware CTA scheduler balances tiles.
-#ifndef PSX_RASTER_WARPS
-#define PSX_RASTER_WARPS 1 // independent tiles (warps) per CTA; no barrier between them
-#endif
-#ifndef PSX_RASTER_MIN_CTAS
-#define PSX_RASTER_MIN_CTAS 32
-#endif
-__global__ void __launch_bounds__(32 * PSX_RASTER_WARPS, PSX_RASTER_MIN_CTAS) raster_kernel(const WaveItem* __restrict__ items, const PrimSetup* __restrict__ setups,
-                                                        const BinInfo* __restrict__ bins, uint16_t* __restrict__ vram_pool,
-                                                        const uint16_t* __restrict__ clut_pool,
-                                                        const uint16_t* __restrict__ payload, uint32_t clut_slots)
+// One warp runs one epoch of one instance on its region: bins the epoch's primitives (submission order), stages the
+// region in shared memory on the first hit, rasterises, writes it back.
+template<uint32_t RH, bool kCoh>
+__device__ __forceinline__ void process_epoch_region(const WaveItem& it, RasterShared<RH>& sh, uint32_t tx, uint32_t ty, uint32_t ry0,
+                                                     const PrimSetup* __restrict__ setups, const BinInfo* __restrict__ bins,
+                                                     uint16_t* vram, const uint16_t* cluts, const uint16_t* __restrict__ payload,
+                                                     uint32_t lane)
 {
-  __shared__ RasterShared sh_all[PSX_RASTER_WARPS];
-  RasterShared& sh = sh_all[threadIdx.x >> 5];
-  const WaveItem it = items[blockIdx.y];
-  if (it.kind != EPOCH_TILED || it.cmd_begin == it.cmd_end)
-    return;
-  uint16_t* vram = vram_pool + static_cast<size_t>(it.instance) * VRAM_PIXELS;
-  const uint16_t* cluts = clut_pool + static_cast<size_t>(it.instance) * clut_slots * CLUT_ENTRIES;
-  const uint32_t lane = threadIdx.x & 31u;
-  const uint32_t tile = blockIdx.x * PSX_RASTER_WARPS + (threadIdx.x >> 5);
-  const uint32_t tx = tile % TILES_X, ty = tile / TILES_X;
-  const uint32_t rx0 = tx * TILE_W, ry0 = ty * TILE_H;
+  const uint32_t rx0 = tx * TILE_W;
   const uint32_t tile_bits = (1u << tx) | (1u << (16 + ty));
-  uint32_t* gword = reinterpret_cast<uint32_t*>(vram + ry0 * VRAM_W + rx0) + lane; // this lane's word of tile row 0
+  uint32_t* gword = reinterpret_cast<uint32_t*>(vram + ry0 * VRAM_W + rx0) + lane; // this lane's word of region row 0
   const PrimSetup& staged = *reinterpret_cast<const PrimSetup*>(sh.stage);
 
   // Binning reads the epoch's BinInfo words 128 at a time: one 128-bit load per lane, the next one in flight.
@@ -719,8 +742,8 @@ __global__ void __launch_bounds__(32 * PSX_RASTER_WARPS, PSX_RASTER_MIN_CTAS) ra
     if (!loaded)
     {
 #pragma unroll 8
-      for (uint32_t r = 0; r < TILE_H; r++)
-        sh.region[r * REGION_PITCH + lane] = gword[r * (VRAM_W / 2)];
+      for (uint32_t r = 0; r < RH; r++)
+        sh.region[r * REGION_PITCH + lane] = kCoh ? __ldcg(gword + r * (VRAM_W / 2)) : gword[r * (VRAM_W / 2)];
       loaded = true;
     }
     const uint32_t* src = reinterpret_cast<const uint32_t*>(setups + it.cmd_begin + sh.list[0]);
@@ -739,7 +762,7 @@ __global__ void __launch_bounds__(32 * PSX_RASTER_WARPS, PSX_RASTER_MIN_CTAS) ra
           w1 = __ldg(src + 32 + lane);
       }
       __syncwarp();
-      raster_prim_on_region(staged, sh.region, rx0, ry0, vram, cluts, payload, sh.clut, clut_key, lane);
+      raster_prim_on_region<RH, kCoh>(staged, sh.region, rx0, ry0, vram, cluts, payload, sh.clut, clut_key, lane);
       __syncwarp();
     }
     list_n = 0;
@@ -747,8 +770,137 @@ __global__ void __launch_bounds__(32 * PSX_RASTER_WARPS, PSX_RASTER_MIN_CTAS) ra
   if (loaded)
   {
 #pragma unroll 8
-    for (uint32_t r = 0; r < TILE_H; r++)
+    for (uint32_t r = 0; r < RH; r++)
       gword[r * (VRAM_W / 2)] = sh.region[r * REGION_PITCH + lane];
+  }
+}
+
+// One warp per (instance, tile).  No block-level barrier anywhere: the hardware CTA scheduler balances tiles.
+#ifndef PSX_RASTER_WARPS
+#define PSX_RASTER_WARPS 1 // independent tiles (warps) per CTA; no barrier between them
+#endif
+#ifndef PSX_RASTER_MIN_CTAS
+#define PSX_RASTER_MIN_CTAS 32
+#endif
+__global__ void __launch_bounds__(32 * PSX_RASTER_WARPS, PSX_RASTER_MIN_CTAS) raster_kernel(
+  const WaveItem* __restrict__ items, const PrimSetup* __restrict__ setups, const BinInfo* __restrict__ bins,
+  uint16_t* __restrict__ vram_pool, const uint16_t* __restrict__ clut_pool, const uint16_t* __restrict__ payload, uint32_t clut_slots)
+{
+  __shared__ RasterShared<TILE_H> sh_all[PSX_RASTER_WARPS];
+  const WaveItem it = items[blockIdx.y];
+  if (it.kind != EPOCH_TILED || it.cmd_begin == it.cmd_end)
+    return;
+  uint16_t* vram = vram_pool + static_cast<size_t>(it.instance) * VRAM_PIXELS;
+  const uint16_t* cluts = clut_pool + static_cast<size_t>(it.instance) * clut_slots * CLUT_ENTRIES;
+  const uint32_t tile = blockIdx.x * PSX_RASTER_WARPS + (threadIdx.x >> 5);
+  const uint32_t tx = tile % TILES_X, ty = tile / TILES_X;
+  process_epoch_region<TILE_H, false>(it, sh_all[threadIdx.x >> 5], tx, ty, ty * TILE_H, setups, bins, vram, cluts, payload,
+                                      threadIdx.x & 31u);
+}
+
+// ------------------------------------------------------------------------------------------------ persistent (latency) mode
+// A handful of instances cannot fill the GPU and pays a kernel launch per epoch (a render-to-texture heavy frame has
+// thousands of epochs).  This cooperative kernel stays resident for a whole flush: 256 CTAs per instance, each of 4
+// warps owning the four 64x8 strips of one tile (4x the parallelism of raster_kernel for a single VRAM), with a
+// grid-wide barrier instead of a launch between epochs.  VRAM and CLUT-slot reads bypass L1 (kCoh) because other CTAs
+// rewrite them between epochs.
+constexpr uint32_t PERSIST_RH = 8;
+constexpr uint32_t PERSIST_WARPS = TILE_H / PERSIST_RH; // 4
+constexpr uint32_t PERSIST_THREADS = PERSIST_WARPS * 32;
+
+struct PersistWave
+{
+  uint32_t item_begin, item_count;
+  uint32_t has_clut;
+  uint32_t pad;
+};
+
+// Grid-wide barrier for the (cooperatively launched, hence co-resident) persistent kernel: one monotonic counter, one
+// atomic per CTA per barrier, thread 0 spins.  The fences make this CTA's VRAM stores visible before it arrives and
+// order the next epoch's (L1-bypassing) loads after the release.
+__device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int n_ctas, unsigned int& generation)
+{
+  __syncthreads();
+  if (threadIdx.x == 0)
+  {
+    generation++;
+    __threadfence();
+    atomicAdd(counter, 1u);
+    const unsigned int target = generation * n_ctas;
+    while (*reinterpret_cast<volatile unsigned int*>(counter) < target)
+    {
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(PERSIST_THREADS, 7) raster_persistent_kernel(
+  const WaveItem* __restrict__ items, const PersistWave* __restrict__ waves, uint32_t n_waves, const uint32_t* __restrict__ instances,
+  const PrimSetup* __restrict__ setups, const BinInfo* __restrict__ bins, const ClutOp* __restrict__ clut_ops, uint16_t* vram_pool,
+  uint16_t* clut_pool, const uint16_t* __restrict__ payload, uint32_t clut_slots, unsigned int* barrier_counter)
+{
+  __shared__ RasterShared<PERSIST_RH> sh_all[PERSIST_WARPS];
+  __shared__ uint32_t warp_count[PERSIST_WARPS];
+  const unsigned int n_ctas = gridDim.x * gridDim.y;
+  unsigned int generation = 0;
+  const uint32_t instance = instances[blockIdx.y];
+  uint16_t* vram = vram_pool + static_cast<size_t>(instance) * VRAM_PIXELS;
+  uint16_t* cluts = clut_pool + static_cast<size_t>(instance) * clut_slots * CLUT_ENTRIES;
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+  const uint32_t tx = blockIdx.x % TILES_X, ty = blockIdx.x / TILES_X;
+
+  for (uint32_t k = 0; k < n_waves; k++)
+  {
+    const PersistWave wv = waves[k];
+    // this instance's item of the wave, if it has an epoch k (a wave holds at most a few items in this mode)
+    WaveItem it;
+    bool mine = false;
+    for (uint32_t i = 0; i < wv.item_count && !mine; i++)
+    {
+      it = items[wv.item_begin + i];
+      mine = it.instance == instance;
+    }
+    if (wv.has_clut) // uniform over the grid
+    {
+      if (mine && blockIdx.x == 0)
+      {
+        for (uint32_t o = it.clut_begin; o < it.clut_end; o++)
+        {
+          const ClutOp op = clut_ops[o];
+          for (uint32_t t = threadIdx.x; t < (op.is8bit ? 256u : 16u); t += PERSIST_THREADS)
+            cluts[op.dst_slot * CLUT_ENTRIES + t] = __ldcg(vram + op.y * VRAM_W + ((op.x + t) & (VRAM_W - 1)));
+        }
+      }
+      grid_barrier(barrier_counter, n_ctas, generation);
+    }
+    if (mine && it.cmd_end > it.cmd_begin)
+    {
+      if (it.kind == EPOCH_TILED)
+      {
+        process_epoch_region<PERSIST_RH, true>(it, sh_all[warp], tx, ty, ty * TILE_H + warp * PERSIST_RH, setups, bins, vram, cluts,
+                                               payload, lane);
+      }
+      else if (blockIdx.x == 0)
+      {
+        __shared__ alignas(16) uint32_t stage[SETUP_WORDS];
+        if (threadIdx.x < SETUP_WORDS)
+          stage[threadIdx.x] = reinterpret_cast<const uint32_t*>(setups + it.cmd_begin)[threadIdx.x];
+        __syncthreads();
+        const PrimSetup& s = *reinterpret_cast<const PrimSetup*>(stage);
+        if (s.op != OP_NOP)
+        {
+          if (it.kind == EPOCH_SELF_SAMPLING)
+            serial_self_sampling(s, vram, cluts);
+          else if (it.kind == EPOCH_COPY_OVERLAP)
+            serial_copy<PERSIST_THREADS>(s, vram);
+          else
+            serial_upload_masked<PERSIST_THREADS>(s, vram, payload, warp_count);
+        }
+        __syncthreads();
+      }
+    }
+    grid_barrier(barrier_counter, n_ctas, generation);
   }
 }
 
@@ -884,6 +1036,35 @@ cudaError_t launch_serial(const WaveItem* items, uint32_t n_items, const PrimSet
     return cudaSuccess;
   serial_kernel<<<n_items, SERIAL_THREADS, 0, st>>>(items, setups, vram_pool, clut_pool, payload, clut_slots);
   return cudaGetLastError();
+}
+
+int persistent_max_instances(int device)
+{
+  int per_sm = 0, sms = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, raster_persistent_kernel, PERSIST_THREADS, 0) != cudaSuccess)
+    return 0;
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess)
+    return 0;
+  int coop = 0;
+  cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
+  return coop ? (per_sm * sms) / static_cast<int>(NUM_TILES) : 0;
+}
+
+cudaError_t launch_persistent(const WaveItem* items, const void* waves, uint32_t n_waves, const uint32_t* instances, uint32_t n_instances,
+                              const PrimSetup* setups, const BinInfo* bins, const ClutOp* clut_ops, uint16_t* vram_pool,
+                              uint16_t* clut_pool, const uint16_t* payload, uint32_t clut_slots, unsigned int* barrier_counter,
+                              cudaStream_t st)
+{
+  if (n_waves == 0 || n_instances == 0)
+    return cudaSuccess;
+  cudaError_t e = cudaMemsetAsync(barrier_counter, 0, sizeof(unsigned int), st);
+  if (e != cudaSuccess)
+    return e;
+  const PersistWave* wv = static_cast<const PersistWave*>(waves);
+  void* args[] = {&items, &wv, &n_waves, &instances, &setups, &bins, &clut_ops, &vram_pool, &clut_pool, &payload, &clut_slots,
+                  &barrier_counter};
+  return cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(raster_persistent_kernel), dim3(NUM_TILES, n_instances),
+                                     dim3(PERSIST_THREADS), args, 0, st);
 }
 
 cudaError_t launch_hash(const uint16_t* vram_pool, uint32_t first, uint32_t count, unsigned long long* out, cudaStream_t st)

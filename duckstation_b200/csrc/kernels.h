@@ -26,6 +26,13 @@ cudaError_t launch_raster(const WaveItem* items, uint32_t n_items, const PrimSet
                           cudaStream_t st);
 cudaError_t launch_serial(const WaveItem* items, uint32_t n_items, const PrimSetup* setups, uint16_t* vram_pool,
                           const uint16_t* clut_pool, const uint16_t* payload, uint32_t clut_slots, cudaStream_t st);
+// Persistent (latency) mode: whole flush of up to persistent_max_instances() instances in one cooperative launch.
+// `waves`: n_waves records of {item_begin, item_count, has_clut, pad} (uint32 each) in device memory.
+int persistent_max_instances(int device);
+cudaError_t launch_persistent(const WaveItem* items, const void* waves, uint32_t n_waves, const uint32_t* instances, uint32_t n_instances,
+                              const PrimSetup* setups, const BinInfo* bins, const ClutOp* clut_ops, uint16_t* vram_pool,
+                              uint16_t* clut_pool, const uint16_t* payload, uint32_t clut_slots, unsigned int* barrier_counter,
+                              cudaStream_t st);
 cudaError_t launch_hash(const uint16_t* vram_pool, uint32_t first, uint32_t count, unsigned long long* out, cudaStream_t st);
 cudaError_t launch_scanout(const uint16_t* vram, const ScanoutParams& p, uint8_t* out, cudaStream_t st);
 

@@ -17,7 +17,7 @@ for name, case in (("config1", (1, 1, 20000, 0)), ("config2", (2, 1, 20000, 0)),
     cpu_ms = (time.perf_counter() - t0) * 1e3
     orc.render(s)
     px = orc.stats()
-    with Context(1, profile=True) as ctx:
+    with Context(1) as ctx:
         best = 1e9
         for rep in range(4):
             ctx.clear_vram(0)
