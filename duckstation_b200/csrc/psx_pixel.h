@@ -29,10 +29,16 @@ PSX_HD int32_t dither_offset(uint32_t x, uint32_t y)
   const uint64_t m = 0x2637405137265140ull;
   return static_cast<int32_t>((m >> (((y & 3u) * 16u) + ((x & 3u) * 4u))) & 0xFu) - 4;
 }
-PSX_HD uint32_t clamp5(int32_t v)
+// clamp((v + d) >> 3, 0, 31) == clamp(v + d, 0, 255) >> 3 (the shift is monotone), which is one fused
+// add-min-relu instruction on sm_90+.
+PSX_HD uint32_t dither5(int32_t v, int32_t d)
 {
-  v >>= 3;
-  return static_cast<uint32_t>(v < 0 ? 0 : (v > 31 ? 31 : v));
+#if defined(__CUDA_ARCH__)
+  return static_cast<uint32_t>(__viaddmin_s32_relu(v, d, 255)) >> 3;
+#else
+  const int32_t t = v + d;
+  return static_cast<uint32_t>(t < 0 ? 0 : (t > 255 ? 255 : t)) >> 3;
+#endif
 }
 
 // Everything the pixel pipeline needs from a primitive, packed into five registers so that the raster kernel can keep
@@ -102,8 +108,8 @@ PSX_HD bool shade_colour(const ShadeState& st, uint32_t px, uint32_t Y, uint32_t
   const int32_t dv = (st.flags & (F1_DITHER << 8)) ? dither_offset(px, Y) : 0;
   if (!(st.flags & F_TEXTURE))
   {
-    out = clamp5(static_cast<int32_t>(r) + dv) | (clamp5(static_cast<int32_t>(g) + dv) << 5) |
-          (clamp5(static_cast<int32_t>(b) + dv) << 10) | ((st.flags & F_TRANSP) ? 0x8000u : 0u);
+    out = dither5(static_cast<int32_t>(r), dv) | (dither5(static_cast<int32_t>(g), dv) << 5) |
+          (dither5(static_cast<int32_t>(b), dv) << 10) | ((st.flags & F_TRANSP) ? 0x8000u : 0u);
     return true;
   }
   if (texel == 0)
@@ -117,15 +123,15 @@ PSX_HD bool shade_colour(const ShadeState& st, uint32_t px, uint32_t Y, uint32_t
   uint32_t cr, cg, cb;
   if (!(st.flags & (F1_MOD5 << 8)))
   {
-    cr = clamp5(static_cast<int32_t>((tr * r) >> 4) + dv);
-    cg = clamp5(static_cast<int32_t>((tg * g) >> 4) + dv);
-    cb = clamp5(static_cast<int32_t>((tb * b) >> 4) + dv);
+    cr = dither5(static_cast<int32_t>((tr * r) >> 4), dv);
+    cg = dither5(static_cast<int32_t>((tg * g) >> 4), dv);
+    cb = dither5(static_cast<int32_t>((tb * b) >> 4), dv);
   }
   else
   {
-    cr = clamp5(static_cast<int32_t>((tr * (r >> 3)) >> 1) + dv);
-    cg = clamp5(static_cast<int32_t>((tg * (g >> 3)) >> 1) + dv);
-    cb = clamp5(static_cast<int32_t>((tb * (b >> 3)) >> 1) + dv);
+    cr = dither5(static_cast<int32_t>((tr * (r >> 3)) >> 1), dv);
+    cg = dither5(static_cast<int32_t>((tg * (g >> 3)) >> 1), dv);
+    cb = dither5(static_cast<int32_t>((tb * (b >> 3)) >> 1), dv);
   }
   out = cr | (cg << 5) | (cb << 10) | (texel & 0x8000u);
   return true;
