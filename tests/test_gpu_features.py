@@ -229,3 +229,44 @@ def test_full_size_properties(oracle):
         ctx.clear_vram(1)
         ctx.submit(b"".join(recs[:8] + recs[8:][::-1]), 1)  # same primitives, reversed order
         assert ctx.hash(1, 1)[0] != h[0]  # the path is order dependent: a shuffled bin order must change the result
+
+
+@pytest.mark.parametrize("case", [(3, 8, 2500, 0), (2, 8, 3000, 0), (0, 51, 2500, 3)], ids=["mixed", "textured", "fuzz"])
+def test_latency_mode_equals_launch_per_epoch(oracle, case):
+    """The persistent cooperative kernel (flushes of <= 4 instances) and the launch-per-epoch path (forced here by
+    profile=True, or by more instances) must produce the same VRAM as the oracle."""
+    s = streams.generate(*case)
+    want = oracle.render(s)
+    with _ctx(1) as ctx:  # latency mode
+        ctx.submit(s)
+        a = ctx.read_vram()
+        launches_persistent = ctx.stats()["kernel_launches"]
+    with _ctx(1, profile=True) as ctx:  # one launch per epoch
+        ctx.submit(s)
+        b = ctx.read_vram()
+        launches_per_epoch = ctx.stats()["kernel_launches"]
+    assert np.array_equal(a, want), describe_diff(a, want)
+    assert np.array_equal(b, want), describe_diff(b, want)
+    assert launches_persistent < launches_per_epoch
+    with _ctx(6) as ctx:  # six instances: throughput kernels
+        ctx.submit_batch([s] * 6)
+        ctx.flush()
+        hs = ctx.hash()
+        assert all(int(h) == oracle.hash64(want) for h in hs)
+
+
+def test_batch_chunking_is_transparent(oracle):
+    n = 40
+    batch = [streams.generate(4, 2000 + i, 300, 0) for i in range(n)]
+    want = []
+    for s in batch:
+        oracle.render(s)
+        want.append(oracle.hash64())
+    for chunk in (0, 7, 16, n):
+        with _ctx(n) as ctx:
+            ctx.set_batch_chunk(chunk)
+            ctx.submit_batch(batch)
+            ctx.flush()
+            assert [int(x) for x in ctx.hash()] == want, f"chunk={chunk}"
+            ctx.run_staged()  # replays every chunk of the group
+            assert [int(x) for x in ctx.hash()] == want, f"chunk={chunk} replay"
