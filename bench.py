@@ -285,7 +285,8 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         host_hashes = ctx.hash()
     barrier()
     s0 = ctx.stats()
-    e2e_parts = {"encode_ms": 0.0, "stage_ms": 0.0, "device_ms": 0.0, "hash_ms": 0.0}
+    e2e_parts = {"encode_ms": 0.0, "scan_ms": 0.0, "pinned_wait_ms": 0.0, "launch_ms": 0.0, "stage_ms": 0.0, "device_ms": 0.0,
+                 "hash_ms": 0.0}
     t1 = time.perf_counter()
     for _ in range(args.steps):
         ctx.submit_batch_raw(ptrs, sizes, n_inst)
@@ -293,6 +294,9 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         host_hashes = ctx.hash()
         t = ctx.timing()
         e2e_parts["encode_ms"] += t["last_encode_ms"]
+        e2e_parts["scan_ms"] += t["last_scan_ms"]
+        e2e_parts["pinned_wait_ms"] += t["last_pinned_wait_ms"]
+        e2e_parts["launch_ms"] += t["last_launch_ms"]
         e2e_parts["stage_ms"] += t["last_stage_ms"]
         e2e_parts["device_ms"] += t["last_flush_device_ms"]
         e2e_parts["hash_ms"] += t["last_hash_ms"]

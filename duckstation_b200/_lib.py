@@ -28,7 +28,8 @@ class Timing(C.Structure):
         ("last_flush_device_ms", C.c_float), ("last_kernels_ms", C.c_float), ("last_raster_ms", C.c_float),
         ("last_raster_max_ms", C.c_float), ("last_raster_launches", C.c_uint32), ("last_waves", C.c_uint32),
         ("last_hash_ms", C.c_float), ("last_encode_ms", C.c_float), ("last_stage_ms", C.c_float),
-        ("reserved", C.c_float * 7),
+        ("last_scan_ms", C.c_float), ("last_pinned_wait_ms", C.c_float), ("last_launch_ms", C.c_float),
+        ("reserved", C.c_float * 4),
     ]
 
 

@@ -168,7 +168,7 @@ struct psxgpu_ctx
   cudaEvent_t ev_start = nullptr, ev_end = nullptr, ev_hash0 = nullptr, ev_hash1 = nullptr;
   bool timing_pending = false;
   uint32_t timing_chunks = 0;
-  double stage_ms_acc = 0;
+  double stage_ms_acc = 0, scan_ms_acc = 0, wait_ms_acc = 0, launch_ms_acc = 0;
 
   psxgpu_stats counters{};
   psxgpu_timing timing{};
@@ -336,7 +336,10 @@ int close_group(psxgpu_ctx* ctx)
   ctx->timing_pending = true;
   ctx->timing.last_stage_ms = static_cast<float>(ctx->stage_ms_acc);
   ctx->timing.last_encode_ms = static_cast<float>(ctx->encode_ms_acc);
-  ctx->encode_ms_acc = 0;
+  ctx->timing.last_scan_ms = static_cast<float>(ctx->scan_ms_acc);
+  ctx->timing.last_pinned_wait_ms = static_cast<float>(ctx->wait_ms_acc);
+  ctx->timing.last_launch_ms = static_cast<float>(ctx->launch_ms_acc);
+  ctx->encode_ms_acc = ctx->scan_ms_acc = ctx->wait_ms_acc = ctx->launch_ms_acc = 0;
   ctx->counters.flushes++;
   return PSXGPU_OK;
 }
@@ -347,7 +350,9 @@ int acquire_pinned(psxgpu_ctx* ctx, psxgpu_ctx::PinnedSet*& out)
   ctx->pin_next = (ctx->pin_next + 1) % 3;
   if (P.in_flight)
   {
+    const double t0 = now_ms();
     CK(cudaEventSynchronize(P.free_ev), "pinned buffer sync");
+    ctx->wait_ms_acc += now_ms() - t0;
     P.in_flight = false;
   }
   out = &P;
@@ -357,8 +362,18 @@ int acquire_pinned(psxgpu_ctx* ctx, psxgpu_ctx::PinnedSet*& out)
 // Common tail of a flush unit.  The packed records and upload pixels of work[w] already sit in the pinned set at
 // cmd_base[w] / pay_base[w] (cmd_base[nw] / pay_base[nw] = extents); this adds CLUT ops and wave descriptors, copies
 // everything to a chunk's device buffers and launches setup + waves.  Asynchronous.
+int launch_chunk_impl(psxgpu_ctx* ctx, const std::vector<uint32_t>& work, const std::vector<uint64_t>& cmd_base,
+                      const std::vector<uint64_t>& pay_base, psxgpu_ctx::PinnedSet& P);
 int launch_chunk(psxgpu_ctx* ctx, const std::vector<uint32_t>& work, const std::vector<uint64_t>& cmd_base,
                  const std::vector<uint64_t>& pay_base, psxgpu_ctx::PinnedSet& P)
+{
+  const double t0 = now_ms();
+  const int rc = launch_chunk_impl(ctx, work, cmd_base, pay_base, P);
+  ctx->launch_ms_acc += now_ms() - t0;
+  return rc;
+}
+int launch_chunk_impl(psxgpu_ctx* ctx, const std::vector<uint32_t>& work, const std::vector<uint64_t>& cmd_base,
+                      const std::vector<uint64_t>& pay_base, psxgpu_ctx::PinnedSet& P)
 {
   const uint32_t nw = static_cast<uint32_t>(work.size());
   const uint64_t n_cmds = cmd_base[nw], n_pay = pay_base[nw];
@@ -910,7 +925,7 @@ int psxgpu_submit_batch(psxgpu_ctx* ctx, uint32_t first, uint32_t count, const v
     int rc = open_group(ctx);
     if (rc != PSXGPU_OK)
       return rc;
-    const double t0 = now_ms();
+    double t0 = now_ms();
     cap_cmds.assign(cn, 0);
     cmd_base.assign(cn + 1, 0);
     pay_base.assign(cn + 1, 0);
@@ -929,10 +944,12 @@ int psxgpu_submit_batch(psxgpu_ctx* ctx, uint32_t first, uint32_t count, const v
       cmd_base[k + 1] = cmd_base[k] + cap_cmds[k];
       pay_base[k + 1] = pay_base[k] + cap_pay[k];
     }
+    ctx->scan_ms_acc += now_ms() - t0;
     psxgpu_ctx::PinnedSet* P = nullptr;
     rc = acquire_pinned(ctx, P);
     if (rc != PSXGPU_OK)
       return rc;
+    t0 = now_ms();
     CK(P->cmds.ensure(cmd_base[cn] * sizeof(PackedCmd)), "pinned alloc (commands)");
     CK(P->payload.ensure(pay_base[cn] * 2), "pinned alloc (payload)");
     PackedCmd* hc = static_cast<PackedCmd*>(P->cmds.p);

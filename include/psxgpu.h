@@ -76,7 +76,10 @@ typedef struct psxgpu_timing {
   float last_hash_ms;           /* last psxgpu_hash* call */
   float last_encode_ms;         /* host time spent in the encoder during the last submit(s) since the previous flush */
   float last_stage_ms;          /* host time spent packing pinned staging buffers in the last flush */
-  float reserved[7];
+  float last_scan_ms;           /* batched submit: header scan that sizes the pinned slots */
+  float last_pinned_wait_ms;    /* batched submit: host waiting for a pinned staging set to be consumed by its H2D copy */
+  float last_launch_ms;         /* host time building wave descriptors + enqueueing copies and kernels */
+  float reserved[4];
 } psxgpu_timing;
 
 /* GPUBackend::CreateSoftwareBackend + Initialize(upload_vram=false) (gpu_sw.cpp:34-59, :450-453):
