@@ -103,6 +103,27 @@ void parallel_for(uint32_t n, uint32_t threads, F&& fn)
     th.join();
 }
 
+// Like parallel_for, but hands every worker its contiguous range once: fn(worker, lo, hi).
+template<typename F>
+uint32_t parallel_ranges(uint32_t n, uint32_t threads, F&& fn)
+{
+  threads = std::max(1u, std::min(threads, std::max(1u, n)));
+  std::vector<std::thread> pool;
+  pool.reserve(threads);
+  for (uint32_t t = 0; t < threads; t++)
+  {
+    const uint32_t lo = static_cast<uint32_t>((static_cast<uint64_t>(n) * t) / threads);
+    const uint32_t hi = static_cast<uint32_t>((static_cast<uint64_t>(n) * (t + 1)) / threads);
+    if (threads == 1)
+      fn(t, lo, hi);
+    else
+      pool.emplace_back([=, &fn]() { fn(t, lo, hi); });
+  }
+  for (auto& th : pool)
+    th.join();
+  return threads;
+}
+
 double now_ms()
 {
   return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
@@ -362,18 +383,31 @@ int acquire_pinned(psxgpu_ctx* ctx, psxgpu_ctx::PinnedSet*& out)
 // Common tail of a flush unit.  The packed records and upload pixels of work[w] already sit in the pinned set at
 // cmd_base[w] / pay_base[w] (cmd_base[nw] / pay_base[nw] = extents); this adds CLUT ops and wave descriptors, copies
 // everything to a chunk's device buffers and launches setup + waves.  Asynchronous.
+// A run of records / upload pixels that is contiguous both in the pinned set and on the device.
+struct CopySeg
+{
+  uint64_t host_off, dev_off, count;
+};
+// Where the pinned copy differs from the device layout (per-thread arenas): host position of each instance's first
+// record and the copy segments.  Null = the pinned set is already laid out like the device buffers.
+struct HostLayout
+{
+  std::vector<uint64_t> host_cmd_base;
+  std::vector<CopySeg> cmd_segs, pay_segs;
+};
+
 int launch_chunk_impl(psxgpu_ctx* ctx, const std::vector<uint32_t>& work, const std::vector<uint64_t>& cmd_base,
-                      const std::vector<uint64_t>& pay_base, psxgpu_ctx::PinnedSet& P);
+                      const std::vector<uint64_t>& pay_base, psxgpu_ctx::PinnedSet& P, const HostLayout* layout);
 int launch_chunk(psxgpu_ctx* ctx, const std::vector<uint32_t>& work, const std::vector<uint64_t>& cmd_base,
-                 const std::vector<uint64_t>& pay_base, psxgpu_ctx::PinnedSet& P)
+                 const std::vector<uint64_t>& pay_base, psxgpu_ctx::PinnedSet& P, const HostLayout* layout = nullptr)
 {
   const double t0 = now_ms();
-  const int rc = launch_chunk_impl(ctx, work, cmd_base, pay_base, P);
+  const int rc = launch_chunk_impl(ctx, work, cmd_base, pay_base, P, layout);
   ctx->launch_ms_acc += now_ms() - t0;
   return rc;
 }
 int launch_chunk_impl(psxgpu_ctx* ctx, const std::vector<uint32_t>& work, const std::vector<uint64_t>& cmd_base,
-                      const std::vector<uint64_t>& pay_base, psxgpu_ctx::PinnedSet& P)
+                      const std::vector<uint64_t>& pay_base, psxgpu_ctx::PinnedSet& P, const HostLayout* layout)
 {
   const uint32_t nw = static_cast<uint32_t>(work.size());
   const uint64_t n_cmds = cmd_base[nw], n_pay = pay_base[nw];
@@ -408,8 +442,9 @@ int launch_chunk_impl(psxgpu_ctx* ctx, const std::vector<uint32_t>& work, const 
   for (uint32_t w = 0; w < nw; w++)
   {
     const Encoder& e = ctx->enc[work[w]];
+    const uint64_t host_first = layout ? layout->host_cmd_base[w] : cmd_base[w];
     for (uint32_t ui : e.upload_cmds)
-      hc[cmd_base[w] + ui].upload.payload += static_cast<uint32_t>(pay_base[w]);
+      hc[host_first + ui].upload.payload += static_cast<uint32_t>(pay_base[w]);
     if (!e.clut_ops.empty())
       std::memcpy(ho + clut_base[w], e.clut_ops.data(), e.clut_ops.size() * sizeof(ClutOp));
   }
@@ -480,10 +515,26 @@ int launch_chunk_impl(psxgpu_ctx* ctx, const std::vector<uint32_t>& work, const 
     ctx->dirty[work[w]] = 0;
   }
 
-  if (n_cmds)
-    CK(cudaMemcpyAsync(S.d_cmds.p, hc, n_cmds * sizeof(PackedCmd), cudaMemcpyHostToDevice, ctx->stream), "H2D commands");
-  if (n_pay)
-    CK(cudaMemcpyAsync(S.d_payload.p, hp, n_pay * 2, cudaMemcpyHostToDevice, ctx->stream), "H2D payload");
+  if (layout)
+  {
+    for (const CopySeg& g : layout->cmd_segs)
+      if (g.count)
+        CK(cudaMemcpyAsync(static_cast<PackedCmd*>(S.d_cmds.p) + g.dev_off, hc + g.host_off, g.count * sizeof(PackedCmd),
+                           cudaMemcpyHostToDevice, ctx->stream),
+           "H2D commands");
+    for (const CopySeg& g : layout->pay_segs)
+      if (g.count)
+        CK(cudaMemcpyAsync(static_cast<uint16_t*>(S.d_payload.p) + g.dev_off, hp + g.host_off, g.count * 2, cudaMemcpyHostToDevice,
+                           ctx->stream),
+           "H2D payload");
+  }
+  else
+  {
+    if (n_cmds)
+      CK(cudaMemcpyAsync(S.d_cmds.p, hc, n_cmds * sizeof(PackedCmd), cudaMemcpyHostToDevice, ctx->stream), "H2D commands");
+    if (n_pay)
+      CK(cudaMemcpyAsync(S.d_payload.p, hp, n_pay * 2, cudaMemcpyHostToDevice, ctx->stream), "H2D payload");
+  }
   if (n_clut)
     CK(cudaMemcpyAsync(S.d_clutops.p, ho, n_clut * sizeof(ClutOp), cudaMemcpyHostToDevice, ctx->stream), "H2D clut ops");
   if (n_items)
@@ -912,12 +963,12 @@ int psxgpu_submit_batch(psxgpu_ctx* ctx, uint32_t first, uint32_t count, const v
       return rc;
   }
   // Cut the batch into chunks: while the copy engine and the SMs work on chunk k, the host threads encode chunk k+1
-  // — straight into pinned memory, at offsets fixed by a cheap header scan, so nothing is copied twice.
+  // — straight into pinned memory, so nothing is copied twice.
   uint32_t per = ctx->batch_chunk;
   if (per == 0)
     per = (count <= 256) ? count : std::max<uint32_t>(128, (count + 7) / 8);
   std::vector<int> status(count, 0);
-  std::vector<uint32_t> work, cap_cmds;
+  std::vector<uint32_t> work;
   std::vector<uint64_t> cmd_base, pay_base;
   for (uint32_t c0 = 0; c0 < count; c0 += per)
   {
@@ -925,45 +976,53 @@ int psxgpu_submit_batch(psxgpu_ctx* ctx, uint32_t first, uint32_t count, const v
     int rc = open_group(ctx);
     if (rc != PSXGPU_OK)
       return rc;
-    double t0 = now_ms();
-    cap_cmds.assign(cn, 0);
-    cmd_base.assign(cn + 1, 0);
-    pay_base.assign(cn + 1, 0);
-    std::vector<uint64_t> cap_pay(cn, 0);
-    parallel_for(cn, ctx->threads, [&](uint32_t k) {
-      if (!Encoder::scan_wire(streams[c0 + k], bytes[c0 + k], &cap_cmds[k], &cap_pay[k]))
-        status[c0 + k] = PSXGPU_E_MALFORMED;
-    });
-    for (uint32_t k = 0; k < cn; k++)
-    {
-      if (status[c0 + k] != 0)
-      {
-        ctx->error = "submit_batch: malformed record stream";
-        return status[c0 + k];
-      }
-      cmd_base[k + 1] = cmd_base[k] + cap_cmds[k];
-      pay_base[k + 1] = pay_base[k] + cap_pay[k];
-    }
-    ctx->scan_ms_acc += now_ms() - t0;
+    // Every worker thread appends its instances back to back into its own arena of the pinned set, so there are no
+    // gaps to fill and no sizing pass over the streams: an arena is sized from the stream bytes alone (a record that
+    // yields a primitive is at least 24 bytes long; an upload pixel is 2 bytes).
     psxgpu_ctx::PinnedSet* P = nullptr;
     rc = acquire_pinned(ctx, P);
     if (rc != PSXGPU_OK)
       return rc;
-    t0 = now_ms();
-    CK(P->cmds.ensure(cmd_base[cn] * sizeof(PackedCmd)), "pinned alloc (commands)");
-    CK(P->payload.ensure(pay_base[cn] * 2), "pinned alloc (payload)");
+    const double t0 = now_ms();
+    const uint32_t T = std::max(1u, std::min(ctx->threads, cn));
+    std::vector<uint64_t> arena_c(T + 1, 0), arena_p(T + 1, 0);
+    for (uint32_t t = 0; t < T; t++)
+    {
+      const uint32_t lo = static_cast<uint32_t>((static_cast<uint64_t>(cn) * t) / T);
+      const uint32_t hi = static_cast<uint32_t>((static_cast<uint64_t>(cn) * (t + 1)) / T);
+      uint64_t c = 0, p = 0;
+      for (uint32_t k = lo; k < hi; k++)
+      {
+        c += bytes[c0 + k] / 24 + 2;
+        p += ((bytes[c0 + k] / 2 + 8) + 7) & ~static_cast<uint64_t>(7);
+      }
+      arena_c[t + 1] = arena_c[t] + c;
+      arena_p[t + 1] = arena_p[t] + p;
+    }
+    CK(P->cmds.ensure(arena_c[T] * sizeof(PackedCmd)), "pinned alloc (commands)");
+    CK(P->payload.ensure(arena_p[T] * 2), "pinned alloc (payload)");
     PackedCmd* hc = static_cast<PackedCmd*>(P->cmds.p);
     uint16_t* hp = static_cast<uint16_t*>(P->payload.p);
-    parallel_for(cn, ctx->threads, [&](uint32_t k) {
-      Encoder& e = ctx->enc[first + c0 + k];
-      e.set_output(hc + cmd_base[k], cap_cmds[k], hp + pay_base[k], cap_pay[k]);
-      size_t used = 0;
-      const EncodeResult res = e.add_wire(streams[c0 + k], bytes[c0 + k], &used);
-      e.finish_flush();
-      status[c0 + k] = (res == EncodeResult::Ok && !e.overflowed()) ? 0 : (res == EncodeResult::Barrier ? PSXGPU_E_UNSUPPORTED : PSXGPU_E_MALFORMED);
-      // records that were culled leave a gap at the end of the slot: make the setup pre-pass skip it
-      for (uint32_t g = e.n_cmds(); g < cap_cmds[k]; g++)
-        hc[cmd_base[k] + g].op = OP_NOP;
+    HostLayout layout;
+    layout.host_cmd_base.assign(cn, 0);
+    std::vector<uint64_t> inst_p(cn, 0), used_c(T, 0), used_p(T, 0);
+    parallel_ranges(cn, T, [&](uint32_t t, uint32_t lo, uint32_t hi) {
+      uint64_t cc = arena_c[t], cp = arena_p[t];
+      for (uint32_t k = lo; k < hi; k++)
+      {
+        Encoder& e = ctx->enc[first + c0 + k];
+        e.set_output(hc + cc, static_cast<uint32_t>(std::min<uint64_t>(arena_c[t + 1] - cc, 0xFFFFFFFFu)), hp + cp, arena_p[t + 1] - cp);
+        size_t used = 0;
+        const EncodeResult res = e.add_wire(streams[c0 + k], bytes[c0 + k], &used);
+        e.finish_flush();
+        status[c0 + k] = (res == EncodeResult::Ok && !e.overflowed()) ? 0 : (res == EncodeResult::Barrier ? PSXGPU_E_UNSUPPORTED : PSXGPU_E_MALFORMED);
+        layout.host_cmd_base[k] = cc;
+        inst_p[k] = cp;
+        cc += e.n_cmds();
+        cp += e.n_payload();
+      }
+      used_c[t] = cc - arena_c[t];
+      used_p[t] = cp - arena_p[t];
     });
     ctx->encode_ms_acc += now_ms() - t0;
     work.clear();
@@ -979,7 +1038,27 @@ int psxgpu_submit_batch(psxgpu_ctx* ctx, uint32_t first, uint32_t count, const v
       }
       work.push_back(first + c0 + k);
     }
-    rc = launch_chunk(ctx, work, cmd_base, pay_base, *P);
+    // device layout: the arenas' used prefixes, concatenated
+    cmd_base.assign(cn + 1, 0);
+    pay_base.assign(cn + 1, 0);
+    uint64_t dev_c = 0, dev_p = 0;
+    for (uint32_t t = 0; t < T; t++)
+    {
+      const uint32_t lo = static_cast<uint32_t>((static_cast<uint64_t>(cn) * t) / T);
+      const uint32_t hi = static_cast<uint32_t>((static_cast<uint64_t>(cn) * (t + 1)) / T);
+      for (uint32_t k = lo; k < hi; k++)
+      {
+        cmd_base[k] = dev_c + (layout.host_cmd_base[k] - arena_c[t]);
+        pay_base[k] = dev_p + (inst_p[k] - arena_p[t]);
+      }
+      layout.cmd_segs.push_back(CopySeg{arena_c[t], dev_c, used_c[t]});
+      layout.pay_segs.push_back(CopySeg{arena_p[t], dev_p, used_p[t]});
+      dev_c += used_c[t];
+      dev_p += used_p[t];
+    }
+    cmd_base[cn] = dev_c;
+    pay_base[cn] = dev_p;
+    rc = launch_chunk(ctx, work, cmd_base, pay_base, *P, &layout);
     if (rc != PSXGPU_OK)
       return rc;
   }

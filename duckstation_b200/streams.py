@@ -93,3 +93,37 @@ def make_update_display(left: int, top: int, width: int, height: int, *, is24: b
                       flags)
     assert len(rec) == 64
     return rec
+
+
+def to_precise(stream: bytes) -> bytes:
+    """Rewrites every DrawPolygon / DrawLine record as its DrawPrecisePolygon / DrawPreciseLine twin (the records the
+    reference's decoder emits with PGXP on, video_thread_commands.h:304-317, :352-362): float positions are filled with
+    garbage on purpose — the software renderer must only look at native_x / native_y (gpu_sw.cpp:118-139, :172-190)."""
+    out = bytearray()
+    for typ, off, size in iter_records(stream):
+        rec = stream[off:off + size]
+        if typ == 22:  # DrawPolygon -> DrawPrecisePolygon
+            nv = struct.unpack_from("<H", rec, 10)[0]
+            head = bytearray(rec[:20])
+            body = bytearray(head[8:20]) + bytearray(8)  # `params` copy of the draw header payload (unused)
+            verts = bytearray()
+            for i in range(nv):
+                x, y, color, tc = struct.unpack_from("<iiIH", rec, 20 + 16 * i)
+                verts += struct.pack("<fffiiIH2x", 1e9, -3.5, 0.0, x, y, color, tc)
+            new_size = (40 + len(verts) + 15) & ~15
+            struct.pack_into("<IB", head, 0, new_size, 23)
+            out += head + bytes(head[:20]) + verts + bytes(new_size - 40 - len(verts))
+            del body
+        elif typ == 25:  # DrawLine -> DrawPreciseLine
+            nv = struct.unpack_from("<H", rec, 10)[0]
+            head = bytearray(rec[:20])
+            verts = bytearray()
+            for i in range(nv):
+                x, y, color = struct.unpack_from("<iiI", rec, 20 + 12 * i)
+                verts += struct.pack("<fffiiI", -7.25, 1e6, 2.0, x, y, color)
+            new_size = (20 + len(verts) + 15) & ~15
+            struct.pack_into("<IB", head, 0, new_size, 26)
+            out += head + verts + bytes(new_size - 20 - len(verts))
+        else:
+            out += rec
+    return bytes(out)

@@ -270,3 +270,12 @@ def test_batch_chunking_is_transparent(oracle):
             assert [int(x) for x in ctx.hash()] == want, f"chunk={chunk}"
             ctx.run_staged()  # replays every chunk of the group
             assert [int(x) for x in ctx.hash()] == want, f"chunk={chunk} replay"
+
+
+def test_precise_record_types(oracle):
+    s = streams.to_precise(streams.generate(3, 6, 1500, 0))
+    want = oracle.render(s)
+    with _ctx() as ctx:
+        ctx.submit(s)
+        got = ctx.read_vram()
+    assert np.array_equal(got, want), describe_diff(got, want)

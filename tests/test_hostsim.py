@@ -110,3 +110,30 @@ def test_clut_cache_reuses_snapshots(sim):
     st = sim.stats()
     assert st["epochs"] == 2  # clear + atlas upload | all primitives
     assert st["clut_cache_hits"] > 10 * st["clut_ops"]
+
+
+def test_precise_records_use_native_coordinates(oracle, sim):
+    """DrawPrecisePolygon / DrawPreciseLine (PGXP record types) render exactly like their plain twins."""
+    from tests.helpers import Reference, have_reference
+
+    s = streams.generate(3, 6, 1500, 0)
+    p = streams.to_precise(s)
+    assert p != s and len(list(streams.iter_records(p))) == len(list(streams.iter_records(s)))
+    want = oracle.render(s)
+    assert np.array_equal(oracle.render(p), want)
+    assert np.array_equal(sim.render(p), want)
+    if have_reference():
+        assert np.array_equal(Reference().render(p), want)
+
+
+def test_degenerate_drawing_areas_and_extreme_sizes(oracle, sim):
+    big = _rect(-1024, -1024, 1023, 511, 0x1F3F5F) + _rect(1, 1, 1023, 511, 0x204060) + _fill(0, 0, 1024, 512, 0xFFFFFF)
+    cases = [
+        _area(600, 300, 100, 200) + big,      # left > right: nothing is clipped in, sprite culled
+        _area(0, 0, 1023, 1023) + big,        # bottom beyond VRAM: rows wrap at 512
+        _area(1023, 511, 1023, 511) + big,    # one pixel
+        _area(0, 0, 0, 0) + _copy(0, 0, 0, 0, 1024, 512) + _copy(5, 5, 1020, 508, 1024, 512),
+    ]
+    for s in cases:
+        got, want = sim.render(s), oracle.render(s)
+        assert np.array_equal(got, want), describe_diff(got, want)
