@@ -4,6 +4,7 @@ The product is ``libpsxgpu.so`` (CUDA kernels + host encoder + C ABI, ``include/
 the thin Python host layer used by the tests and the benchmark:
 
 * :mod:`duckstation_b200.context`  — ``Context``: ctypes wrapper of the C ABI (no CPU fallback)
+* :mod:`duckstation_b200.frontend` — ``Gp0Frontend`` / ``replay_dump``: GP0/GP1 port words and `.psxgpu` traces -> records
 * :mod:`duckstation_b200.streams`  — seeded synthetic command streams for the BASELINE.json configs
 * :mod:`duckstation_b200.sharding` — instance partition across ranks + NCCL/gloo gather of per-instance hashes
 * :mod:`duckstation_b200.build`    — in-tree build of every native library

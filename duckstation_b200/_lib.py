@@ -33,6 +33,14 @@ class Timing(C.Structure):
     ]
 
 
+class FrontendStats(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in (
+        "gp0_words", "gp1_words", "commands", "unknown_commands", "culled_primitives", "frames", "idle")] + [
+        ("reserved", C.c_uint64 * 5)]
+
+
+FRAME_CALLBACK = C.CFUNCTYPE(None, C.c_void_p, C.c_long)
+
 _lib = None
 
 
@@ -75,6 +83,24 @@ def load() -> C.CDLL:
     lib.psxgpu_reset_stats.argtypes = [P]
     lib.psxgpu_get_timing.argtypes = [P, C.POINTER(Timing)]
     lib.psxgpu_get_raster_launch_ms.argtypes = [P, C.POINTER(C.c_float), u32]
+    lib.psxgpu_frontend_create.argtypes = [u32, u32, C.POINTER(P)]
+    lib.psxgpu_frontend_destroy.argtypes = [P]
+    lib.psxgpu_frontend_destroy.restype = None
+    lib.psxgpu_frontend_gp0.argtypes = [P, C.c_void_p, C.c_size_t]
+    lib.psxgpu_frontend_gp1.argtypes = [P, u32]
+    lib.psxgpu_frontend_vsync.argtypes = [P]
+    lib.psxgpu_frontend_finish_read.argtypes = [P]
+    lib.psxgpu_frontend_records.argtypes = [P, C.POINTER(C.c_size_t)]
+    lib.psxgpu_frontend_records.restype = C.c_void_p
+    lib.psxgpu_frontend_clear.argtypes = [P]
+    lib.psxgpu_frontend_get_stats.argtypes = [P, C.POINTER(FrontendStats)]
+    lib.psxgpu_frontend_feed_dump.argtypes = [P, C.c_char_p, C.c_size_t]
+    lib.psxgpu_frontend_feed_dump.restype = C.c_long
+    lib.psxgpu_replay_dump.argtypes = [P, u32, C.c_char_p, C.c_size_t, u32, u32, FRAME_CALLBACK, C.c_void_p]
+    lib.psxgpu_replay_dump.restype = C.c_long
+    for name in ("psxgpu_frontend_create", "psxgpu_frontend_gp0", "psxgpu_frontend_gp1", "psxgpu_frontend_vsync",
+                 "psxgpu_frontend_finish_read", "psxgpu_frontend_clear", "psxgpu_frontend_get_stats"):
+        getattr(lib, name).restype = C.c_int
     for name in ("psxgpu_create", "psxgpu_submit_wire", "psxgpu_submit_batch", "psxgpu_flush", "psxgpu_sync",
                  "psxgpu_run_staged", "psxgpu_set_batch_chunk", "psxgpu_read_vram", "psxgpu_clear_vram", "psxgpu_load_state",
                  "psxgpu_save_state", "psxgpu_scanout", "psxgpu_hash", "psxgpu_hash_device", "psxgpu_get_stats",
@@ -90,4 +116,7 @@ EXPORTS = (
     "psxgpu_shadow_vram", "psxgpu_clear_vram", "psxgpu_load_state", "psxgpu_save_state", "psxgpu_scanout",
     "psxgpu_display", "psxgpu_hash", "psxgpu_hash_device", "psxgpu_get_stats", "psxgpu_reset_stats",
     "psxgpu_get_timing", "psxgpu_get_raster_launch_ms",
+    "psxgpu_frontend_create", "psxgpu_frontend_destroy", "psxgpu_frontend_gp0", "psxgpu_frontend_gp1",
+    "psxgpu_frontend_vsync", "psxgpu_frontend_finish_read", "psxgpu_frontend_records", "psxgpu_frontend_clear",
+    "psxgpu_frontend_get_stats", "psxgpu_frontend_feed_dump", "psxgpu_replay_dump",
 )

@@ -1,0 +1,145 @@
+// gp0_frontend.h — GP0/GP1 word-level front-end (SURVEY §8f rank 1 + the display half of rank 2).
+//
+// Turns raw PSX GPU port writes — what a `.psxgpu` trace (ps1dev GPUDUMP format) stores — into the backend command
+// records of include/psxgpu_wire.h, the way the reference's decoder does (src/core/gpu.cpp): FIFO + command table
+// (:2618-2666), draw-state registers E1..E6 (:2866-2954, :2202-2240), polygon / rectangle / line / polyline handlers
+// (:3099-3691), fill / VRAM<->VRAM / CPU->VRAM / VRAM->CPU (:3695-3891), CLUT reload tracking (:2157-2183), the
+// too-large-primitive culls, and — for scan-out — the GP1 display registers and UpdateCRTCDisplayParameters
+// (:1243-1431) + UpdateDisplay (:2451-2481).
+//
+// What is NOT restated: command timing (AddCommandTicks / max_run_ahead), DMA pacing, interrupts and the CRTC's
+// tick-accurate beam position.  Consequences, both documented in DESIGN.md §11: (1) the interlaced field / active line
+// toggles once per VSync instead of following the beam, (2) a VRAM->CPU read completes as soon as the trace says so.
+// Parity status: **unpinned** — the reference's gpu.cpp cannot be compiled outside the emulator, so this is checked
+// by round trip against an independent GP0 assembler (tests/gp0_assembler.py), not against executed reference code.
+#pragma once
+
+#include "../../include/psxgpu_wire.h"
+
+#include <cstddef>
+#include <cstdint>
+#include <vector>
+
+namespace psx {
+
+enum class CropMode : uint8_t
+{
+  None = 0,
+  Overscan = 1, // the reference's default (settings.cpp: DEFAULT_DISPLAY_CROP_MODE)
+  Borders = 2,
+};
+
+class Gp0Frontend
+{
+public:
+  Gp0Frontend();
+
+  void reset(bool pal_region = false); // power-on state == GP1(00h) SoftReset (gpu.cpp:526-571)
+  void set_crop_mode(CropMode m) { m_crop = m; }
+  /// display_deinterlacing_mode == Progressive (the reference's default, settings.h:238): no interlaced rendering or
+  /// field-split scan-out; 480i frames are shown whole (gpu.cpp:411, :1465-1478).
+  void set_force_progressive(bool v) { m_force_progressive = v; }
+
+  /// GP0 port: words are queued in the FIFO and executed as far as complete commands allow.
+  void write_gp0(const uint32_t* words, size_t count);
+  /// GP1 port (display control), gpu.cpp:1931-2106.
+  void write_gp1(uint32_t value);
+  /// End of frame (the trace's VSync packet, gpu.cpp:4151-4168): flips the interlace field and emits UpdateDisplay.
+  void vsync();
+  /// The trace's "discard GPUREAD" packet: the CPU has drained a VRAM->CPU transfer (gpu.cpp:1896-1929).
+  void finish_vram_read();
+
+  /// Backend records produced so far, in order; the caller hands them to psxgpu_submit_wire and clears.
+  std::vector<uint8_t>& output() { return m_out; }
+  void clear_output() { m_out.clear(); }
+
+  struct Stats
+  {
+    uint64_t gp0_words = 0, gp1_words = 0, commands = 0, unknown_commands = 0, culled_primitives = 0, frames = 0;
+  };
+  const Stats& stats() const { return m_stats; }
+  bool idle() const { return m_state == State::Idle && m_head == m_fifo.size(); }
+
+private:
+  enum class State : uint8_t
+  {
+    Idle,
+    WritingVRAM,
+    ReadingVRAM,
+    DrawingPolyLine,
+  };
+
+  template<typename T>
+  T* emit(size_t bytes, uint8_t type);
+  uint32_t fifo_size() const { return static_cast<uint32_t>(m_fifo.size() - m_head); }
+  uint32_t peek(uint32_t i = 0) const { return m_fifo[m_head + i]; }
+  uint32_t pop() { return m_fifo[m_head++]; }
+  void execute();
+  bool execute_command(); // false: not enough words yet
+  void end_command() { m_state = State::Idle; }
+
+  // state setters (gpu.cpp:2202-2240)
+  void set_draw_mode(uint16_t value);
+  void set_texture_window(uint32_t value);
+  void update_clut_if_needed();
+  void invalidate_clut();
+  void prepare_for_draw();
+  void fill_draw_header(psx_draw_header* d, int primitive, uint32_t rc);
+  bool interlaced_rendering() const;
+
+  bool handle_polygon(uint32_t rc);
+  bool handle_rectangle(uint32_t rc);
+  bool handle_line(uint32_t rc);
+  bool handle_polyline_start(uint32_t rc);
+  void finish_polyline();
+  void finish_vram_write();
+  void update_crtc_display();
+
+  std::vector<uint8_t> m_out;
+  std::vector<uint32_t> m_fifo;
+  size_t m_head = 0;
+  State m_state = State::Idle;
+  Stats m_stats;
+  CropMode m_crop = CropMode::Overscan;
+  bool m_force_progressive = true;
+
+  // draw state
+  uint16_t m_draw_mode = 0;
+  uint16_t m_palette = 0;
+  uint32_t m_texture_window_reg = 0xFFFFFFFFu;
+  psx_texture_window m_window{0xFF, 0xFF, 0, 0};
+  psx_drawing_area m_area{0, 0, 0, 0};
+  bool m_area_changed = true;
+  int32_t m_offset_x = 0, m_offset_y = 0;
+  bool m_set_mask = false, m_check_mask = false;
+  bool m_set_texture_disable_mask = false;
+  uint32_t m_clut_reg = 0xFFFFFFFFu;
+  bool m_clut_is_8bit = false;
+  uint32_t m_render_command = 0;
+
+  // transfers
+  std::vector<uint32_t> m_blit;
+  uint32_t m_blit_remaining = 0;
+  uint16_t m_xfer_x = 0, m_xfer_y = 0, m_xfer_w = 0, m_xfer_h = 0;
+  std::vector<uint32_t> m_polyline;
+
+  // display (GPUSTAT display bits + CRTC registers)
+  bool m_console_pal = false;
+  bool m_pal = false, m_display_disable = true, m_display_24 = false, m_vertical_interlace = false, m_vertical_res = false;
+  bool m_draw_to_displayed_field = false;
+  uint8_t m_hres1 = 0, m_hres2 = 0;
+  uint32_t m_display_address_start = 0, m_h_range = 0xC60260, m_v_range = 0x3FC10;
+  uint8_t m_interlaced_field = 0, m_active_line_lsb = 0;
+  struct
+  {
+    uint16_t display_width, display_height, origin_left, origin_top, vram_left, vram_top, vram_width, vram_height;
+  } m_crtc{};
+};
+
+/// Replays a `.psxgpu` trace (gpu_dump.cpp: magic "PSXGPUDUMPv1\0\0", then packets of `length | type << 24` + words).
+/// Every packet is fed to the front-end; `on_frame(user, frontend)` is called after each VSync packet with the
+/// frame's records in frontend.output() (the callee submits and clears them).  Returns the number of frames, or -1
+/// if the container is malformed.
+long replay_psxgpu_dump(const void* data, size_t bytes, Gp0Frontend& fe, void (*on_frame)(void*, Gp0Frontend&), void* user);
+
+} // namespace psx

@@ -1,0 +1,76 @@
+"""GP0/GP1 word-level front-end (include/psxgpu.h `psxgpu_frontend_*`): raw PSX GPU port writes and `.psxgpu` traces in,
+backend command records out.  Host-only; mirrors the decoder half of the reference's src/core/gpu.cpp."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+CROP_NONE, CROP_OVERSCAN, CROP_BORDERS = 0, 1, 2
+FE_PAL, FE_INTERLACED = 1, 2
+
+
+class Gp0Frontend:
+    def __init__(self, *, pal: bool = False, interlaced: bool = False, crop_mode: int = CROP_OVERSCAN):
+        self._lib = _lib.load()
+        self._h = C.c_void_p()
+        flags = (FE_PAL if pal else 0) | (FE_INTERLACED if interlaced else 0)
+        rc = self._lib.psxgpu_frontend_create(flags, crop_mode, C.byref(self._h))
+        if rc != 0:
+            raise ValueError(f"psxgpu_frontend_create failed ({rc})")
+
+    def close(self) -> None:
+        if self._h:
+            self._lib.psxgpu_frontend_destroy(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = close
+
+    def gp0(self, words) -> None:
+        """Writes words to the GP0 port (a single int or any sequence of them)."""
+        a = np.ascontiguousarray(np.atleast_1d(np.asarray(words, dtype=np.uint64)).astype(np.uint32))
+        self._lib.psxgpu_frontend_gp0(self._h, a.ctypes.data, a.size)
+
+    def gp1(self, value: int) -> None:
+        self._lib.psxgpu_frontend_gp1(self._h, value & 0xFFFFFFFF)
+
+    def vsync(self) -> None:
+        self._lib.psxgpu_frontend_vsync(self._h)
+
+    def finish_read(self) -> None:
+        self._lib.psxgpu_frontend_finish_read(self._h)
+
+    def feed_dump(self, data: bytes) -> int:
+        n = self._lib.psxgpu_frontend_feed_dump(self._h, data, len(data))
+        if n < 0:
+            raise ValueError(f"malformed .psxgpu trace ({n})")
+        return n
+
+    def records(self, clear: bool = True) -> bytes:
+        """Backend records decoded so far (the psxgpu_submit_wire format)."""
+        n = C.c_size_t()
+        p = self._lib.psxgpu_frontend_records(self._h, C.byref(n))
+        out = C.string_at(p, n.value) if n.value else b""
+        if clear:
+            self._lib.psxgpu_frontend_clear(self._h)
+        return out
+
+    def stats(self) -> dict:
+        s = _lib.FrontendStats()
+        self._lib.psxgpu_frontend_get_stats(self._h, C.byref(s))
+        return {n: int(getattr(s, n)) for n, _ in s._fields_ if n != "reserved"}
+
+
+def replay_dump(ctx, data: bytes, *, instance: int = 0, pal: bool = False, interlaced: bool = False,
+                crop_mode: int = CROP_OVERSCAN, on_frame=None) -> int:
+    """Replays a `.psxgpu` trace into `instance` of a Context (psxgpu_replay_dump).  `on_frame(frame_index)` runs after
+    each frame has been submitted; ctx.display() is that frame's scan-out."""
+    lib = _lib.load()
+    cb = _lib.FRAME_CALLBACK((lambda _u, i: on_frame(i)) if on_frame else (lambda _u, i: None))
+    flags = (FE_PAL if pal else 0) | (FE_INTERLACED if interlaced else 0)
+    n = lib.psxgpu_replay_dump(ctx._ctx, instance, data, len(data), flags, crop_mode, cb, None)
+    if n < 0:
+        raise ValueError(f"psxgpu_replay_dump failed ({n}): {lib.psxgpu_last_error(ctx._ctx).decode()}")
+    return n

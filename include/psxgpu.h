@@ -147,6 +147,43 @@ int psxgpu_get_timing(psxgpu_ctx* ctx, psxgpu_timing* out);
 /* Durations (ms) of the raster launches of the last profiled flush / run_staged; returns the count. */
 int psxgpu_get_raster_launch_ms(psxgpu_ctx* ctx, float* out, uint32_t max_count);
 
+/* ---- GP0/GP1 word-level front-end (host only, no device work) -------------------------------
+ * Restates the reference's port decoder, src/core/gpu.cpp: WriteGP0/ExecuteCommands (:2618-2812), the draw-state
+ * registers (:2866-2954), the primitive and transfer handlers (:3099-3891), WriteGP1 (:1931-2106) and the display
+ * half of UpdateCRTCDisplayParameters / UpdateDisplay (:1243-1431, :2451-2481).  Output is the backend record
+ * stream psxgpu_submit_wire consumes.  Parity status: unpinned. */
+typedef struct psxgpu_frontend psxgpu_frontend;
+typedef struct psxgpu_frontend_stats {
+  uint64_t gp0_words, gp1_words, commands, unknown_commands, culled_primitives, frames;
+  uint64_t idle; /* 1: FIFO empty and no transfer / polyline in flight */
+  uint64_t reserved[5];
+} psxgpu_frontend_stats;
+/* flags: PSXGPU_FE_*; crop_mode: 0 none, 1 overscan (the reference's default), 2 borders (settings.h DisplayCropMode). */
+enum {
+  PSXGPU_FE_PAL = 1,       /* PAL console region (System::IsPALRegion) */
+  PSXGPU_FE_INTERLACED = 2 /* display_deinterlacing_mode != Progressive: interlaced rendering + field scan-out on */
+};
+int psxgpu_frontend_create(uint32_t flags, uint32_t crop_mode, psxgpu_frontend** out);
+void psxgpu_frontend_destroy(psxgpu_frontend* fe);
+int psxgpu_frontend_gp0(psxgpu_frontend* fe, const uint32_t* words, size_t count); /* GPU::WriteRegister(0) / DMA */
+int psxgpu_frontend_gp1(psxgpu_frontend* fe, uint32_t value);                     /* GPU::WriteRegister(4) */
+int psxgpu_frontend_vsync(psxgpu_frontend* fe);        /* end of frame: emits UpdateDisplay, flips the field */
+int psxgpu_frontend_finish_read(psxgpu_frontend* fe);  /* the CPU has drained GPUREAD after a VRAM->CPU command */
+/* Records decoded so far (valid until the next frontend call); the caller submits them and clears. */
+const void* psxgpu_frontend_records(psxgpu_frontend* fe, size_t* bytes);
+int psxgpu_frontend_clear(psxgpu_frontend* fe);
+int psxgpu_frontend_get_stats(psxgpu_frontend* fe, psxgpu_frontend_stats* out);
+/* Feeds a whole `.psxgpu` trace (see psxgpu_replay_dump) through the front-end; the records of all frames, each
+ * closed by its UpdateDisplay, accumulate in psxgpu_frontend_records.  Returns frames or PSXGPU_E_MALFORMED. */
+long psxgpu_frontend_feed_dump(psxgpu_frontend* fe, const void* data, size_t bytes);
+
+/* Replays a `.psxgpu` trace (reference: src/core/gpu_dump.cpp, GPUDump::Player) into `instance`: every frame's
+ * records go through psxgpu_submit_wire, then on_frame(user, frame_index) is called (the display buffer of that
+ * frame is current, psxgpu_display).  Returns the number of frames or a negative PSXGPU_E_* code. */
+typedef void (*psxgpu_frame_callback)(void* user, long frame);
+long psxgpu_replay_dump(psxgpu_ctx* ctx, uint32_t instance, const void* data, size_t bytes, uint32_t flags,
+                        uint32_t crop_mode, psxgpu_frame_callback on_frame, void* user);
+
 #ifdef __cplusplus
 }
 #endif

@@ -279,3 +279,57 @@ def test_precise_record_types(oracle):
         ctx.submit(s)
         got = ctx.read_vram()
     assert np.array_equal(got, want), describe_diff(got, want)
+
+
+@pytest.mark.parametrize("interlaced", [False, True], ids=["progressive", "interlaced"])
+def test_psxgpu_trace_replay_through_the_gp0_frontend(oracle, interlaced):
+    """A `.psxgpu` trace (GP0/GP1 port words + VSync packets) replayed by psxgpu_replay_dump: after every frame the VRAM
+    and the scanned-out image equal what the oracle makes of the records the (host-only) front-end decodes."""
+    from duckstation_b200.frontend import CROP_BORDERS, Gp0Frontend, replay_dump
+    from tests import gp0_assembler as asm
+    from tests.test_gp0_frontend import gp1_mode, strip_interlaced_and_display
+
+    direct = strip_interlaced_and_display(streams.generate(0, 77, 900, 3))
+    offs = [off for typ, off, _ in streams.iter_records(direct) if typ != asm.CMD_CLUT]
+    cuts = [0] + [offs[len(offs) * k // 4] for k in (1, 2, 3)] + [len(direct)]
+    a = asm.Gp0Assembler()
+    a.gp1(0x00000000)
+    a.gp1(gp1_mode(hres1=1, vres=1 if interlaced else 0, interlace=1 if interlaced else 0))
+    a.gp1(0x06000000 | 0x260 | (0xC60 << 12))
+    a.gp1(0x07000000 | 16 | (256 << 10))
+    a.gp1(0x03000000)
+    for k in range(4):
+        a.gp1(0x05000000 | (k * 160) | ((k * 40) << 10))
+        if k == 2:
+            a.gp1(gp1_mode(hres1=1, depth24=1, vres=1 if interlaced else 0, interlace=1 if interlaced else 0))
+        a.add_stream(direct[cuts[k]:cuts[k + 1]])
+        if k == 1:  # interlaced rendering applies to these (line-skipping fill and rectangle)
+            a.gp0(0x02102030, 0, 64 | (64 << 16), 0x60FFFFFF, 8 | (8 << 16), 40 | (40 << 16))
+        a.vsync()
+    dump = asm.write_dump(a.events, max_gp0_words=13)
+
+    fe = Gp0Frontend(interlaced=interlaced, crop_mode=CROP_BORDERS)
+    assert fe.feed_dump(dump) == 4
+    frames = streams.split_frames(fe.records())
+    assert len(frames) == 4
+    want = []
+    oracle.reset()
+    for f in frames:
+        oracle.exec(f)
+        disp = [f[off:off + size] for typ, off, size in streams.iter_records(f) if typ == 9][-1]
+        img = oracle.scanout(disp, 0)
+        want.append((oracle.vram().copy(), None if img is None else img[:, : oracle.last_size[0] * 4].copy()))
+    if interlaced:
+        recs = [f[off:off + size] for f in frames for typ, off, size in streams.iter_records(f) if typ == 24]
+        assert any(r[8] & 1 for r in recs)
+
+    got = []
+    with _ctx() as ctx:
+        n = replay_dump(ctx, dump, interlaced=interlaced, crop_mode=CROP_BORDERS,
+                        on_frame=lambda i: got.append((ctx.read_vram(), ctx.display())))
+        assert n == 4 and len(got) == 4
+    for i, ((gv, gi), (wv, wi)) in enumerate(zip(got, want)):
+        assert np.array_equal(gv, wv), f"frame {i}: {describe_diff(gv, wv)}"
+        assert (gi is None) == (wi is None)
+        if wi is not None:
+            assert gi.shape == wi.shape and np.array_equal(gi, wi), f"frame {i} scan-out"
