@@ -6,12 +6,14 @@
 // wave k runs epoch k of every instance that has one, as a single grid of (instance, tile) CTAs.
 #include "../../include/psxgpu.h"
 
+#include "device_encoder.h"
 #include "encoder.h"
 #include "kernels.h"
 
 #include <algorithm>
 #include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <thread>
@@ -139,6 +141,18 @@ struct psxgpu_ctx
   uint32_t clut_slots = 256;
   uint32_t threads = 1;
   cudaStream_t stream = nullptr;
+  // batched path with device-side encoding: raw streams are uploaded on copy_stream, encoded on enc_stream, and the
+  // main stream picks the chunk up once its wave table is known
+  cudaStream_t copy_stream = nullptr, enc_streams[4] = {nullptr, nullptr, nullptr, nullptr};
+  // PSXGPU_TRACE=1: per-chunk device timeline of the batched path (copy, encode, waves), printed by psxgpu_sync
+  bool trace = false;
+  struct TraceChunk
+  {
+    cudaEvent_t copy0, copy1, enc1, run0, run1;
+  };
+  std::vector<TraceChunk> trace_chunks;
+  cudaEvent_t trace_origin = nullptr;
+  uint32_t encode_mode = 0; // opts.reserved[1]: 0 auto (device encoder for batches of >= 16 instances), 1 host, 2 device
 
   uint16_t* d_vram = nullptr;
   uint16_t* d_clut = nullptr;
@@ -147,6 +161,9 @@ struct psxgpu_ctx
 
   std::vector<Encoder> enc;
   std::vector<uint8_t> dirty;
+  // Encoder state of instances last encoded on the device (blob_truth[i] != 0): imported into enc[i] on demand.
+  std::vector<EncState> enc_blob;
+  std::vector<uint8_t> blob_truth;
 
   PinnedBuf h_misc;
   DevBuf d_scan;
@@ -157,6 +174,11 @@ struct psxgpu_ctx
   struct Chunk
   {
     DevBuf d_cmds, d_setups, d_bins, d_payload, d_clutops, d_items, d_misc;
+    // device-encoded chunks: d_payload holds the raw wire streams (upload pixels are read in place)
+    DevBuf d_recoff, d_inst, d_state, d_epochs, d_result, d_waves, d_cursor, d_summary, d_rects;
+    cudaEvent_t ev_copied = nullptr, ev_encoded = nullptr;
+    cudaEvent_t ev_done = nullptr; // main stream: last launch that reads this chunk's buffers
+    bool done_valid = false;
     uint32_t n_cmds = 0;
     bool persistent = false; // few instances: one cooperative launch for all waves (raster_persistent_kernel)
     uint32_t n_instances = 0;
@@ -176,6 +198,7 @@ struct psxgpu_ctx
   struct PinnedSet
   {
     PinnedBuf cmds, payload, clutops, items, misc;
+    PinnedBuf wire, recoff, inst, state, result; // device-encoded chunks (result = D2H: summary, wave table, states)
     cudaEvent_t free_ev = nullptr;
     bool in_flight = false;
   };
@@ -329,6 +352,11 @@ int run_chunk(psxgpu_ctx* ctx, psxgpu_ctx::Chunk& S)
       CK(cudaEventRecord(S.ev_raster[S.ev_raster_used++], ctx->stream), "event record");
   }
   ctx->counters.waves += waves;
+  if (S.ev_done)
+  {
+    CK(cudaEventRecord(S.ev_done, ctx->stream), "event record");
+    S.done_valid = true;
+  }
   return PSXGPU_OK;
 }
 
@@ -585,6 +613,481 @@ int flush_work(psxgpu_ctx* ctx, const std::vector<uint32_t>& work)
   return launch_chunk(ctx, work, cmd_base, pay_base, *P);
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Batched path with device-side encoding (device_encoder.h).  Per chunk the host validates the record framing, copies
+// the raw streams into pinned memory and uploads them on copy_stream; enc_stream encodes them (one warp per instance)
+// and builds the wave table; the host reads the small table back and launches setup + waves on the main stream.  The
+// read-back of chunk k is awaited after chunk k+1 has been staged, so the host never idles on the device.
+void ensure_host_state(psxgpu_ctx* ctx, uint32_t i)
+{
+  if (ctx->blob_truth[i])
+  {
+    ctx->enc[i].import_state(ctx->enc_blob[i]);
+    ctx->blob_truth[i] = 0;
+  }
+}
+
+struct WalkResult
+{
+  uint32_t n_rec = 0, cmd_cap = 0, clut_cap = 0;
+  int status = 0;
+};
+
+// Record framing exactly as Encoder::add_wire checks it; counts what the stream can produce at most.  With rec_off the
+// byte offset of every record (relative to the chunk's wire buffer) is written out as well.
+void walk_stream(const uint8_t* p, size_t bytes, WalkResult& r, uint32_t* rec_off, uint32_t base)
+{
+  const uint8_t* const begin = p;
+  const uint8_t* const end = p + bytes;
+  r = WalkResult();
+  while (p < end)
+  {
+    if (static_cast<size_t>(end - p) < sizeof(psx_cmd_header))
+    {
+      r.status = PSXGPU_E_MALFORMED;
+      return;
+    }
+    const psx_cmd_header* h = reinterpret_cast<const psx_cmd_header*>(p);
+    if (h->size < sizeof(psx_cmd_header) || (h->size & 3u) != 0 || h->size > static_cast<size_t>(end - p))
+    {
+      r.status = PSXGPU_E_MALFORMED;
+      return;
+    }
+    switch (h->type)
+    {
+      case PSX_CMD_CLEAR_VRAM:
+      case PSX_CMD_LOAD_STATE:
+      case PSX_CMD_READ_VRAM:
+      case PSX_CMD_UPDATE_DISPLAY: r.status = PSXGPU_E_UNSUPPORTED; return;
+      case PSX_CMD_DRAW_POLYGON:
+      case PSX_CMD_DRAW_PRECISE_POLYGON:
+        if (h->size >= sizeof(psx_draw_header))
+          r.cmd_cap += (reinterpret_cast<const psx_draw_header*>(p)->num_vertices > 3) ? 2u : 1u;
+        break;
+      case PSX_CMD_DRAW_LINE:
+      case PSX_CMD_DRAW_PRECISE_LINE:
+        if (h->size >= sizeof(psx_draw_header))
+          r.cmd_cap += reinterpret_cast<const psx_draw_header*>(p)->num_vertices / 2u;
+        break;
+      case PSX_CMD_DRAW_RECTANGLE:
+      case PSX_CMD_FILL_VRAM:
+      case PSX_CMD_COPY_VRAM:
+      case PSX_CMD_UPDATE_VRAM: r.cmd_cap += 1; break;
+      case PSX_CMD_UPDATE_CLUT: r.clut_cap += 1; break;
+      default: break;
+    }
+    if (rec_off)
+      rec_off[r.n_rec] = base + static_cast<uint32_t>(p - begin);
+    r.n_rec++;
+    p += h->size;
+  }
+}
+
+struct PendingChunk
+{
+  psxgpu_ctx::Chunk* S = nullptr;
+  psxgpu_ctx::PinnedSet* P = nullptr;
+  cudaStream_t es = nullptr;
+  psxgpu_ctx::TraceChunk trace{};
+  uint32_t first_instance = 0, cn = 0, wave_cap = 0;
+  size_t waves_off = 0, state_off = 0;
+  uint64_t cmd_total = 0;
+};
+
+int finalize_device_chunk(psxgpu_ctx* ctx, PendingChunk& pc)
+{
+  psxgpu_ctx::Chunk& S = *pc.S;
+  const double t0 = now_ms();
+  CK(cudaEventSynchronize(S.ev_encoded), "encode sync");
+  ctx->wait_ms_acc += now_ms() - t0;
+  const double t1 = now_ms();
+  const uint8_t* res = static_cast<const uint8_t*>(pc.P->result.p);
+  const EncSummary* sm = reinterpret_cast<const EncSummary*>(res);
+  if (sm->overflow)
+    return ctx->invalid("device encoder: output capacity exceeded");
+  const uint32_t M = std::min(sm->max_epochs, pc.wave_cap);
+  const EncWave* wv = reinterpret_cast<const EncWave*>(res + pc.waves_off);
+  std::vector<EncWave> big;
+  if (M > ENC_WAVES_INLINE)
+  {
+    big.resize(M);
+    CK(cudaMemcpyAsync(big.data(), S.d_waves.p, static_cast<size_t>(M) * sizeof(EncWave), cudaMemcpyDeviceToHost, pc.es),
+       "D2H wave table");
+    CK(cudaStreamSynchronize(pc.es), "encode sync");
+    ctx->counters.d2h_bytes += static_cast<uint64_t>(M) * sizeof(EncWave);
+    wv = big.data();
+  }
+  S.wave_off.assign(1, 0);
+  S.wave_has_clut.clear();
+  S.wave_has_tiled.clear();
+  S.wave_has_serial.clear();
+  for (uint32_t k = 0; k < M; k++)
+  {
+    S.wave_off.push_back(wv[k].item_off + wv[k].item_count);
+    S.wave_has_clut.push_back((wv[k].flags & 1u) ? 1 : 0);
+    S.wave_has_tiled.push_back((wv[k].flags & 2u) ? 1 : 0);
+    S.wave_has_serial.push_back((wv[k].flags & 4u) ? 1 : 0);
+  }
+  S.n_cmds = static_cast<uint32_t>(pc.cmd_total);
+  S.n_instances = pc.cn;
+  S.persistent = false;
+  const EncState* states = reinterpret_cast<const EncState*>(res + pc.state_off);
+  for (uint32_t k = 0; k < pc.cn; k++)
+  {
+    ctx->enc_blob[pc.first_instance + k] = states[k];
+    ctx->blob_truth[pc.first_instance + k] = 1;
+  }
+  psxgpu_stats& c = ctx->counters;
+  c.wire_commands += sm->stats[ENC_STAT_WIRE];
+  c.packed_prims += sm->stats[ENC_STAT_PRIMS];
+  c.epochs += sm->stats[ENC_STAT_EPOCHS];
+  c.cuts_raw += sm->stats[ENC_STAT_CUTS_RAW];
+  c.cuts_war += sm->stats[ENC_STAT_CUTS_WAR];
+  c.cuts_clut += sm->stats[ENC_STAT_CUTS_CLUT];
+  c.serial_self_sampling += sm->stats[ENC_STAT_SELF];
+  c.serial_copy += sm->stats[ENC_STAT_COPY];
+  c.serial_upload += sm->stats[ENC_STAT_UPLOAD];
+  c.clut_ops += sm->stats[ENC_STAT_CLUT_OPS];
+  c.clut_cache_hits += sm->stats[ENC_STAT_CLUT_HITS];
+  c.rejected += sm->stats[ENC_STAT_REJECTED];
+  CK(cudaStreamWaitEvent(ctx->stream, S.ev_encoded, 0), "stream wait");
+  if (ctx->trace)
+    cudaEventRecord(pc.trace.run0, ctx->stream);
+  const int rc = run_chunk(ctx, S);
+  if (ctx->trace)
+  {
+    cudaEventRecord(pc.trace.run1, ctx->stream);
+    ctx->trace_chunks.push_back(pc.trace);
+  }
+  ctx->launch_ms_acc += now_ms() - t1;
+  return rc;
+}
+
+// True if [p, p + bytes) starts and ends in page-locked host memory (cudaHostAlloc / cudaHostRegister).
+bool is_pinned_host(const void* p, size_t bytes)
+{
+  if (!p || bytes == 0)
+    return false;
+  cudaPointerAttributes a0{}, a1{};
+  if (cudaPointerGetAttributes(&a0, p) != cudaSuccess || cudaPointerGetAttributes(&a1, static_cast<const uint8_t*>(p) + bytes - 1) != cudaSuccess)
+  {
+    cudaGetLastError();
+    return false;
+  }
+  return a0.type == cudaMemoryTypeHost && a1.type == cudaMemoryTypeHost;
+}
+
+int submit_batch_device(psxgpu_ctx* ctx, uint32_t first, uint32_t count, const void* const* streams, const size_t* bytes)
+{
+  uint32_t per = ctx->batch_chunk;
+  if (per == 0)
+    per = (count <= 256) ? count : std::max<uint32_t>(128, (count + 7) / 8);
+  // Chunks whose wave table is still on its way back; the table of chunk k is awaited after chunk k+2 has been staged.
+  std::vector<PendingChunk> pending;
+  auto drain = [&](size_t keep) -> int {
+    while (pending.size() > keep)
+    {
+      PendingChunk pc = pending.front();
+      pending.erase(pending.begin());
+      const int rc = finalize_device_chunk(ctx, pc);
+      if (rc != PSXGPU_OK)
+        return rc;
+    }
+    return PSXGPU_OK;
+  };
+  std::vector<WalkResult> walk;
+  std::vector<uint64_t> wire_off, rec_host, rec_dev, cmd_base, clut_base, epoch_base;
+  struct Run
+  {
+    const uint8_t* src;
+    uint64_t dev_off, bytes;
+  };
+  std::vector<Run> runs;
+  uint32_t chunk_index = 0;
+  for (uint32_t c0 = 0; c0 < count; c0 += per, chunk_index++)
+  {
+    const uint32_t cn = std::min(per, count - c0);
+    int rc = open_group(ctx);
+    if (rc != PSXGPU_OK)
+      return rc;
+    psxgpu_ctx::PinnedSet* P = nullptr;
+    rc = acquire_pinned(ctx, P);
+    if (rc != PSXGPU_OK)
+      return rc;
+    const double t0 = now_ms();
+    const uint32_t T = std::max(1u, std::min(ctx->threads, cn));
+
+    // Where the streams go in the chunk's device wire buffer.  Streams that already sit in page-locked memory are
+    // copied from where they are (neighbours in one copy); anything else is packed into our pinned staging buffer.
+    bool direct = true;
+    for (uint32_t k = 0; k < cn && direct; k++)
+      direct = bytes[c0 + k] == 0 || ((reinterpret_cast<uintptr_t>(streams[c0 + k]) & 15u) == 0 && is_pinned_host(streams[c0 + k], bytes[c0 + k]));
+    wire_off.assign(cn + 1, 0);
+    runs.clear();
+    if (direct)
+    {
+      uint64_t dev = 0;
+      for (uint32_t k = 0; k < cn; k++)
+      {
+        const uint8_t* src = static_cast<const uint8_t*>(streams[c0 + k]);
+        const uint64_t n = bytes[c0 + k];
+        if (n == 0)
+        {
+          wire_off[k] = dev;
+          continue;
+        }
+        if (!runs.empty() && src >= runs.back().src + runs.back().bytes && src - (runs.back().src + runs.back().bytes) < 64)
+        {
+          wire_off[k] = runs.back().dev_off + static_cast<uint64_t>(src - runs.back().src);
+          runs.back().bytes = static_cast<uint64_t>(src - runs.back().src) + n;
+        }
+        else
+        {
+          dev = runs.empty() ? 0 : ((runs.back().dev_off + runs.back().bytes + 15u) & ~static_cast<uint64_t>(15));
+          wire_off[k] = dev;
+          runs.push_back(Run{src, dev, n});
+        }
+      }
+      wire_off[cn] = runs.empty() ? 0 : ((runs.back().dev_off + runs.back().bytes + 15u) & ~static_cast<uint64_t>(15));
+    }
+    else
+    {
+      for (uint32_t k = 0; k < cn; k++)
+        wire_off[k + 1] = wire_off[k] + ((bytes[c0 + k] + 15u) & ~static_cast<uint64_t>(15));
+    }
+    if (wire_off[cn] > 0xFFFFFF00ull)
+    {
+      rc = drain(0);
+      return rc != PSXGPU_OK ? rc : ctx->invalid("submit_batch: chunk larger than 4 GiB of records; use a smaller batch chunk");
+    }
+    const size_t wire_bytes = static_cast<size_t>(wire_off[cn]) + 256;
+
+    // One pass over the streams on the host threads: framing checks, record offsets (each thread appends to its own
+    // arena; a record is at least 8 bytes long), output capacities and — for pageable sources — the copy into pinned memory.
+    std::vector<uint64_t> arena(T + 1, 0), arena_used(T, 0);
+    for (uint32_t t = 0; t < T; t++)
+    {
+      const uint32_t lo = static_cast<uint32_t>((static_cast<uint64_t>(cn) * t) / T), hi = static_cast<uint32_t>((static_cast<uint64_t>(cn) * (t + 1)) / T);
+      uint64_t cap = 0;
+      for (uint32_t k = lo; k < hi; k++)
+        cap += bytes[c0 + k] / 8 + 2;
+      arena[t + 1] = arena[t] + cap;
+    }
+    CK(P->recoff.ensure(arena[T] * 4 + 16), "pinned alloc (record offsets)");
+    if (!direct)
+      CK(P->wire.ensure(wire_bytes), "pinned alloc (wire)");
+    uint8_t* hw = static_cast<uint8_t*>(P->wire.p);
+    uint32_t* hr = static_cast<uint32_t*>(P->recoff.p);
+    walk.assign(cn, WalkResult());
+    rec_host.assign(cn, 0);
+    parallel_ranges(cn, T, [&](uint32_t t, uint32_t lo, uint32_t hi) {
+      uint64_t at = arena[t];
+      for (uint32_t k = lo; k < hi; k++)
+      {
+        const uint8_t* src = static_cast<const uint8_t*>(streams[c0 + k]);
+        rec_host[k] = at;
+        walk_stream(src, bytes[c0 + k], walk[k], hr + at, static_cast<uint32_t>(wire_off[k]));
+        at += walk[k].n_rec;
+        if (!direct && bytes[c0 + k] && walk[k].status == 0)
+          std::memcpy(hw + wire_off[k], src, bytes[c0 + k]);
+      }
+      arena_used[t] = at - arena[t];
+    });
+    for (uint32_t k = 0; k < cn; k++)
+      if (walk[k].status != 0)
+      {
+        ctx->encode_ms_acc += now_ms() - t0;
+        rc = drain(0);
+        if (rc != PSXGPU_OK)
+          return rc;
+        ctx->error = (walk[k].status == PSXGPU_E_MALFORMED) ? "submit_batch: malformed record stream"
+                                                           : "submit_batch: read-back / state records are not allowed in a batch";
+        return walk[k].status;
+      }
+    // device layout of the record offsets: the arenas' used prefixes, concatenated
+    rec_dev.assign(cn, 0);
+    cmd_base.assign(cn + 1, 0);
+    clut_base.assign(cn + 1, 0);
+    epoch_base.assign(cn + 1, 0);
+    std::vector<uint64_t> arena_dev(T + 1, 0);
+    for (uint32_t t = 0; t < T; t++)
+      arena_dev[t + 1] = arena_dev[t] + arena_used[t];
+    uint32_t wave_cap = 1;
+    for (uint32_t t = 0; t < T; t++)
+    {
+      const uint32_t lo = static_cast<uint32_t>((static_cast<uint64_t>(cn) * t) / T), hi = static_cast<uint32_t>((static_cast<uint64_t>(cn) * (t + 1)) / T);
+      for (uint32_t k = lo; k < hi; k++)
+        rec_dev[k] = arena_dev[t] + (rec_host[k] - arena[t]);
+    }
+    for (uint32_t k = 0; k < cn; k++)
+    {
+      const uint32_t ecap = walk[k].cmd_cap + walk[k].clut_cap + 1;
+      cmd_base[k + 1] = cmd_base[k] + walk[k].cmd_cap;
+      clut_base[k + 1] = clut_base[k] + walk[k].clut_cap;
+      epoch_base[k + 1] = epoch_base[k] + ecap;
+      wave_cap = std::max(wave_cap, ecap);
+    }
+    const uint64_t n_rec_total = arena_dev[T];
+    if (cmd_base[cn] > 0xFFFFFFF0ull || epoch_base[cn] > 0xFFFFFFF0ull || n_rec_total > 0xFFFFFFF0ull)
+    {
+      rc = drain(0);
+      return rc != PSXGPU_OK ? rc : ctx->invalid("submit_batch: chunk holds more than 2^32 records; use a smaller batch chunk");
+    }
+    const size_t waves_off = 256, waves_inline = std::min<size_t>(wave_cap, ENC_WAVES_INLINE);
+    const size_t state_off = waves_off + ENC_WAVES_INLINE * sizeof(EncWave);
+    CK(P->inst.ensure(static_cast<size_t>(cn) * sizeof(EncInst)), "pinned alloc (instances)");
+    CK(P->state.ensure(static_cast<size_t>(cn) * sizeof(EncState)), "pinned alloc (encoder state)");
+    CK(P->result.ensure(state_off + static_cast<size_t>(cn) * sizeof(EncState)), "pinned alloc (encode result)");
+    EncInst* hi = static_cast<EncInst*>(P->inst.p);
+    EncState* hs = static_cast<EncState*>(P->state.p);
+    for (uint32_t k = 0; k < cn; k++)
+    {
+      EncInst& ii = hi[k];
+      std::memset(&ii, 0, sizeof(ii));
+      ii.instance = first + c0 + k;
+      ii.rec_begin = static_cast<uint32_t>(rec_dev[k]);
+      ii.n_records = walk[k].n_rec;
+      ii.cmd_base = static_cast<uint32_t>(cmd_base[k]);
+      ii.cmd_cap = walk[k].cmd_cap;
+      ii.clut_base = static_cast<uint32_t>(clut_base[k]);
+      ii.clut_cap = walk[k].clut_cap;
+      ii.epoch_base = static_cast<uint32_t>(epoch_base[k]);
+      ii.epoch_cap = walk[k].cmd_cap + walk[k].clut_cap + 1;
+      if (ctx->blob_truth[first + c0 + k])
+        hs[k] = ctx->enc_blob[first + c0 + k];
+      else
+        ctx->enc[first + c0 + k].export_state(hs[k]);
+    }
+    ctx->encode_ms_acc += now_ms() - t0;
+
+    const double t2 = now_ms();
+    if (ctx->group_n >= ctx->chunks.size())
+      ctx->chunks.push_back(new psxgpu_ctx::Chunk());
+    psxgpu_ctx::Chunk& S = *ctx->chunks[ctx->group_n++];
+    cudaStream_t es = ctx->enc_streams[chunk_index % 4];
+    for (cudaEvent_t* ev : {&S.ev_copied, &S.ev_encoded, &S.ev_done})
+      if (!*ev)
+        CK(cudaEventCreateWithFlags(ev, cudaEventDisableTiming), "event create");
+    // the chunk's device buffers may still be read by its previous user (the same slot of the previous group, or a replay)
+    if (!S.done_valid) // first device-encoded use of this slot: anything queued on the main stream may still read it
+    {
+      CK(cudaEventRecord(S.ev_done, ctx->stream), "event record");
+      S.done_valid = true;
+    }
+    CK(cudaStreamWaitEvent(ctx->copy_stream, S.ev_done, 0), "stream wait");
+    CK(cudaStreamWaitEvent(es, S.ev_done, 0), "stream wait");
+    CK(S.d_payload.ensure(wire_bytes), "device alloc (wire)");
+    CK(S.d_recoff.ensure(n_rec_total * 4 + 16), "device alloc (record offsets)");
+    CK(S.d_inst.ensure(static_cast<size_t>(cn) * sizeof(EncInst)), "device alloc (instances)");
+    CK(S.d_state.ensure(static_cast<size_t>(cn) * sizeof(EncState)), "device alloc (encoder state)");
+    CK(S.d_cmds.ensure(cmd_base[cn] * sizeof(PackedCmd) + 64), "device alloc (commands)");
+    CK(S.d_setups.ensure(cmd_base[cn] * sizeof(PrimSetup) + 64), "device alloc (setup records)");
+    CK(S.d_bins.ensure(cmd_base[cn] * sizeof(BinInfo) + 64), "device alloc (bins)");
+    CK(S.d_clutops.ensure(clut_base[cn] * sizeof(ClutOp) + 16), "device alloc (clut ops)");
+    CK(S.d_epochs.ensure(epoch_base[cn] * sizeof(Epoch) + 16), "device alloc (epochs)");
+    CK(S.d_items.ensure(epoch_base[cn] * sizeof(WaveItem) + 16), "device alloc (wave items)");
+    CK(S.d_result.ensure(static_cast<size_t>(cn) * sizeof(EncResult)), "device alloc (encode result)");
+    CK(S.d_waves.ensure(static_cast<size_t>(wave_cap) * sizeof(EncWave)), "device alloc (wave table)");
+    CK(S.d_cursor.ensure(static_cast<size_t>(wave_cap) * 4), "device alloc (wave cursors)");
+    CK(S.d_summary.ensure(sizeof(EncSummary)), "device alloc (summary)");
+    CK(S.d_rects.ensure(cmd_base[cn] * 16 + 64), "device alloc (footprints)");
+
+    psxgpu_ctx::TraceChunk tc{};
+    if (ctx->trace)
+    {
+      for (cudaEvent_t* ev : {&tc.copy0, &tc.copy1, &tc.enc1, &tc.run0, &tc.run1})
+        cudaEventCreate(ev);
+      if (!ctx->trace_origin)
+      {
+        cudaEventCreate(&ctx->trace_origin);
+        cudaEventRecord(ctx->trace_origin, ctx->stream);
+      }
+      cudaEventRecord(tc.copy0, ctx->copy_stream);
+    }
+    uint8_t* dw = static_cast<uint8_t*>(S.d_payload.p);
+    uint64_t copied = 0;
+    if (direct)
+    {
+      for (const Run& r : runs)
+      {
+        CK(cudaMemcpyAsync(dw + r.dev_off, r.src, r.bytes, cudaMemcpyHostToDevice, ctx->copy_stream), "H2D wire");
+        copied += r.bytes;
+      }
+      CK(cudaMemsetAsync(dw + wire_off[cn], 0, 256, ctx->copy_stream), "wire slack");
+    }
+    else
+    {
+      std::memset(hw + wire_off[cn], 0, 256);
+      CK(cudaMemcpyAsync(dw, hw, wire_bytes, cudaMemcpyHostToDevice, ctx->copy_stream), "H2D wire");
+      copied += wire_bytes;
+    }
+    for (uint32_t t = 0; t < T; t++)
+      if (arena_used[t])
+        CK(cudaMemcpyAsync(static_cast<uint32_t*>(S.d_recoff.p) + arena_dev[t], hr + arena[t], arena_used[t] * 4, cudaMemcpyHostToDevice,
+                           ctx->copy_stream),
+           "H2D record offsets");
+    CK(cudaMemcpyAsync(S.d_inst.p, hi, static_cast<size_t>(cn) * sizeof(EncInst), cudaMemcpyHostToDevice, ctx->copy_stream), "H2D instances");
+    CK(cudaMemcpyAsync(S.d_state.p, hs, static_cast<size_t>(cn) * sizeof(EncState), cudaMemcpyHostToDevice, ctx->copy_stream),
+       "H2D encoder state");
+    if (ctx->trace)
+      cudaEventRecord(tc.copy1, ctx->copy_stream);
+    CK(cudaEventRecord(S.ev_copied, ctx->copy_stream), "event record");
+    CK(cudaEventRecord(P->free_ev, ctx->copy_stream), "event record");
+    P->in_flight = true;
+    ctx->counters.h2d_bytes += copied + n_rec_total * 4 + static_cast<uint64_t>(cn) * (sizeof(EncInst) + sizeof(EncState));
+
+    CK(cudaStreamWaitEvent(es, S.ev_copied, 0), "stream wait");
+    EncodeArgs a{};
+    a.wire = dw;
+    a.rec_off = static_cast<const uint32_t*>(S.d_recoff.p);
+    a.inst = static_cast<const EncInst*>(S.d_inst.p);
+    a.n_inst = cn;
+    a.clut_slots = ctx->clut_slots;
+    a.modulation_crop = ctx->opts.modulation_crop ? 1u : 0u;
+    a.state = static_cast<EncState*>(S.d_state.p);
+    a.cmds = static_cast<PackedCmd*>(S.d_cmds.p);
+    a.rects = static_cast<uint4*>(S.d_rects.p);
+    a.clut_ops = static_cast<ClutOp*>(S.d_clutops.p);
+    a.epochs = static_cast<Epoch*>(S.d_epochs.p);
+    a.result = static_cast<EncResult*>(S.d_result.p);
+    a.summary = static_cast<EncSummary*>(S.d_summary.p);
+    a.waves = static_cast<EncWave*>(S.d_waves.p);
+    a.wave_cursor = static_cast<uint32_t*>(S.d_cursor.p);
+    a.wave_cap = wave_cap;
+    a.items = static_cast<WaveItem*>(S.d_items.p);
+    CK(launch_encode(a, es), "encode_kernel");
+    ctx->counters.kernel_launches += 3;
+    uint8_t* res = static_cast<uint8_t*>(P->result.p);
+    CK(cudaMemcpyAsync(res, S.d_summary.p, sizeof(EncSummary), cudaMemcpyDeviceToHost, es), "D2H summary");
+    CK(cudaMemcpyAsync(res + waves_off, S.d_waves.p, waves_inline * sizeof(EncWave), cudaMemcpyDeviceToHost, es), "D2H wave table");
+    CK(cudaMemcpyAsync(res + state_off, S.d_state.p, static_cast<size_t>(cn) * sizeof(EncState), cudaMemcpyDeviceToHost, es),
+       "D2H encoder state");
+    if (ctx->trace)
+      cudaEventRecord(tc.enc1, es);
+    CK(cudaEventRecord(S.ev_encoded, es), "event record");
+    ctx->counters.d2h_bytes += sizeof(EncSummary) + waves_inline * sizeof(EncWave) + static_cast<uint64_t>(cn) * sizeof(EncState);
+    ctx->launch_ms_acc += now_ms() - t2;
+
+    PendingChunk pc;
+    pc.S = &S;
+    pc.P = P;
+    pc.es = es;
+    pc.first_instance = first + c0;
+    pc.cn = cn;
+    pc.wave_cap = wave_cap;
+    pc.waves_off = waves_off;
+    pc.state_off = state_off;
+    pc.cmd_total = cmd_base[cn];
+    pc.trace = tc;
+    pending.push_back(pc);
+    rc = drain(2); // pinned sets rotate by three: the set of chunk k-2 is needed again for chunk k+1
+    if (rc != PSXGPU_OK)
+      return rc;
+  }
+  return drain(0);
+}
+
 // Flushes every instance that has queued work and closes the group.
 int do_flush(psxgpu_ctx* ctx)
 {
@@ -738,6 +1241,20 @@ int psxgpu_create(int device, uint32_t n_instances, const psxgpu_opts* opts, psx
     return bail(e, "cudaSetDevice");
   if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess)
     return bail(e, "stream");
+  // The encode kernels are small (one warp per instance) and sit on the critical path of their chunk: they go on
+  // high-priority streams so that their CTAs are placed ahead of the raster waves' CTAs of earlier chunks.
+  int prio_lo = 0, prio_hi = 0;
+  cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+  if (const char* pe = std::getenv("PSXGPU_ENC_PRIO")) // experiment knob: 0 = encode streams at default priority
+    if (pe[0] == '0')
+      prio_hi = prio_lo;
+  if ((e = cudaStreamCreateWithPriority(&ctx->copy_stream, cudaStreamNonBlocking, prio_hi)) != cudaSuccess)
+    return bail(e, "stream");
+  for (cudaStream_t& es : ctx->enc_streams)
+    if ((e = cudaStreamCreateWithPriority(&es, cudaStreamNonBlocking, prio_hi)) != cudaSuccess)
+      return bail(e, "stream");
+  ctx->encode_mode = ctx->opts.reserved[1];
+  ctx->trace = std::getenv("PSXGPU_TRACE") != nullptr;
   if ((e = cudaMalloc(&ctx->d_vram, static_cast<size_t>(n_instances) * VRAM_PIXELS * 2)) != cudaSuccess)
     return bail(e, "VRAM pool");
   if ((e = cudaMalloc(&ctx->d_clut, static_cast<size_t>(n_instances) * ctx->clut_slots * CLUT_ENTRIES * 2)) != cudaSuccess)
@@ -770,6 +1287,8 @@ int psxgpu_create(int device, uint32_t n_instances, const psxgpu_opts* opts, psx
     ctx->enc.back().begin_flush();
   }
   ctx->dirty.assign(n_instances, 0);
+  ctx->enc_blob.resize(n_instances);
+  ctx->blob_truth.assign(n_instances, 0);
   *out = ctx;
   return PSXGPU_OK;
 }
@@ -779,21 +1298,26 @@ void psxgpu_destroy(psxgpu_ctx* ctx)
   if (!ctx)
     return;
   cudaSetDevice(ctx->device);
-  if (ctx->stream)
-    cudaStreamSynchronize(ctx->stream);
+  for (cudaStream_t st : {ctx->copy_stream, ctx->enc_streams[0], ctx->enc_streams[1], ctx->enc_streams[2], ctx->enc_streams[3], ctx->stream})
+    if (st)
+      cudaStreamSynchronize(st);
   ctx->h_misc.release();
   ctx->d_scan.release();
   for (psxgpu_ctx::PinnedSet& ps : ctx->pinned)
   {
-    for (PinnedBuf* b : {&ps.cmds, &ps.payload, &ps.clutops, &ps.items, &ps.misc})
+    for (PinnedBuf* b : {&ps.cmds, &ps.payload, &ps.clutops, &ps.items, &ps.misc, &ps.wire, &ps.recoff, &ps.inst, &ps.state, &ps.result})
       b->release();
     if (ps.free_ev)
       cudaEventDestroy(ps.free_ev);
   }
   for (psxgpu_ctx::Chunk* ch : ctx->chunks)
   {
-    for (DevBuf* b : {&ch->d_cmds, &ch->d_setups, &ch->d_bins, &ch->d_payload, &ch->d_clutops, &ch->d_items, &ch->d_misc})
+    for (DevBuf* b : {&ch->d_cmds, &ch->d_setups, &ch->d_bins, &ch->d_payload, &ch->d_clutops, &ch->d_items, &ch->d_misc, &ch->d_recoff,
+                      &ch->d_inst, &ch->d_state, &ch->d_epochs, &ch->d_result, &ch->d_waves, &ch->d_cursor, &ch->d_summary, &ch->d_rects})
       b->release();
+    for (cudaEvent_t ev : {ch->ev_copied, ch->ev_encoded, ch->ev_done})
+      if (ev)
+        cudaEventDestroy(ev);
     for (cudaEvent_t ev : ch->ev_raster)
       cudaEventDestroy(ev);
     delete ch;
@@ -809,8 +1333,9 @@ void psxgpu_destroy(psxgpu_ctx* ctx)
   for (cudaEvent_t ev : {ctx->ev_start, ctx->ev_end, ctx->ev_hash0, ctx->ev_hash1})
     if (ev)
       cudaEventDestroy(ev);
-  if (ctx->stream)
-    cudaStreamDestroy(ctx->stream);
+  for (cudaStream_t st : {ctx->copy_stream, ctx->enc_streams[0], ctx->enc_streams[1], ctx->enc_streams[2], ctx->enc_streams[3], ctx->stream})
+    if (st)
+      cudaStreamDestroy(st);
   delete ctx;
 }
 
@@ -833,6 +1358,26 @@ int psxgpu_sync(psxgpu_ctx* ctx)
     return PSXGPU_E_INVALID;
   cudaSetDevice(ctx->device);
   CK(cudaStreamSynchronize(ctx->stream), "stream sync");
+  if (ctx->trace && !ctx->trace_chunks.empty())
+  {
+    std::fprintf(stderr, "psxgpu trace (ms since first chunk): chunk  copy[begin end]  encode_end  waves[begin end]\n");
+    uint32_t i = 0;
+    for (psxgpu_ctx::TraceChunk& tc : ctx->trace_chunks)
+    {
+      float t[5] = {0, 0, 0, 0, 0};
+      cudaEvent_t evs[5] = {tc.copy0, tc.copy1, tc.enc1, tc.run0, tc.run1};
+      for (int k = 0; k < 5; k++)
+      {
+        cudaEventSynchronize(evs[k]);
+        cudaEventElapsedTime(&t[k], ctx->trace_origin, evs[k]);
+        cudaEventDestroy(evs[k]);
+      }
+      std::fprintf(stderr, "  %2u  copy %7.2f %7.2f  enc %7.2f  waves %7.2f %7.2f\n", i++, t[0], t[1], t[2], t[3], t[4]);
+    }
+    ctx->trace_chunks.clear();
+    cudaEventDestroy(ctx->trace_origin);
+    ctx->trace_origin = nullptr;
+  }
   return collect_timing(ctx);
 }
 
@@ -872,6 +1417,7 @@ int psxgpu_submit_wire(psxgpu_ctx* ctx, uint32_t instance, const void* wire, siz
   if (!ctx || instance >= ctx->n || (!wire && bytes))
     return ctx ? ctx->invalid("submit_wire: bad instance or buffer") : PSXGPU_E_INVALID;
   cudaSetDevice(ctx->device);
+  ensure_host_state(ctx, instance);
   const uint8_t* p = static_cast<const uint8_t*>(wire);
   size_t off = 0;
   while (off < bytes)
@@ -962,8 +1508,12 @@ int psxgpu_submit_batch(psxgpu_ctx* ctx, uint32_t first, uint32_t count, const v
     if (rc != PSXGPU_OK)
       return rc;
   }
-  // Cut the batch into chunks: while the copy engine and the SMs work on chunk k, the host threads encode chunk k+1
-  // — straight into pinned memory, so nothing is copied twice.
+  if (ctx->encode_mode == 2 || (ctx->encode_mode == 0 && count >= 16))
+    return submit_batch_device(ctx, first, count, streams, bytes);
+  for (uint32_t i = 0; i < count; i++)
+    ensure_host_state(ctx, first + i);
+  // Host-encoded path (small batches: the latency mode).  Cut the batch into chunks: while the copy engine and the SMs
+  // work on chunk k, the host threads encode chunk k+1 — straight into pinned memory, so nothing is copied twice.
   uint32_t per = ctx->batch_chunk;
   if (per == 0)
     per = (count <= 256) ? count : std::max<uint32_t>(128, (count + 7) / 8);
@@ -1094,6 +1644,7 @@ int psxgpu_clear_vram(psxgpu_ctx* ctx, uint32_t instance)
     return rc;
   CK(cudaMemsetAsync(inst_vram(ctx, instance), 0, VRAM_PIXELS * 2, ctx->stream), "VRAM clear");
   CK(cudaMemsetAsync(inst_clut(ctx, instance, 0), 0, CLUT_ENTRIES * 2, ctx->stream), "CLUT clear");
+  ensure_host_state(ctx, instance);
   ctx->enc[instance].reset_clut_state();
   return PSXGPU_OK;
 }
@@ -1113,6 +1664,7 @@ int psxgpu_load_state(psxgpu_ctx* ctx, uint32_t instance, const uint16_t* vram, 
     CK(cudaMemsetAsync(inst_clut(ctx, instance, 0), 0, CLUT_ENTRIES * 2, ctx->stream), "CLUT clear");
   CK(cudaStreamSynchronize(ctx->stream), "stream sync"); // caller's buffers may be reused on return
   ctx->counters.h2d_bytes += VRAM_PIXELS * 2 + CLUT_ENTRIES * 2;
+  ensure_host_state(ctx, instance);
   ctx->enc[instance].reset_clut_state();
   return PSXGPU_OK;
 }
@@ -1128,6 +1680,7 @@ int psxgpu_save_state(psxgpu_ctx* ctx, uint32_t instance, uint16_t* vram, uint16
   CK(cudaMemcpyAsync(vram, inst_vram(ctx, instance), VRAM_PIXELS * 2, cudaMemcpyDeviceToHost, ctx->stream), "D2H VRAM");
   if (clut)
   {
+    ensure_host_state(ctx, instance);
     const Encoder& e = ctx->enc[instance];
     CK(cudaMemcpyAsync(clut, inst_clut(ctx, instance, e.clut_lo_slot()), 16 * 2, cudaMemcpyDeviceToHost, ctx->stream), "D2H CLUT");
     CK(cudaMemcpyAsync(clut + 16, inst_clut(ctx, instance, e.clut_hi_slot()) + 16, 240 * 2, cudaMemcpyDeviceToHost, ctx->stream),

@@ -1,0 +1,104 @@
+// device_encoder.h — the batched path's command encoder, run on the GPU (encode_kernel.cu).
+//
+// psxgpu_submit_batch hands the host N independent wire streams.  Encoding them on the host (encoder.cpp) costs more
+// than rasterising them on the device, so for batches the host only validates record sizes, copies the raw streams
+// into pinned memory and uploads them; one warp per instance then does everything Encoder::handle_record does
+// (src/core/gpu_backend.cpp:383-544 dispatch, drawing area, CLUT cache, quad split, culls) plus the hazard / epoch
+// splitter, and small follow-up kernels turn the per-instance epoch lists into wave descriptors.
+// Upload pixels are not copied again: OP_UPLOAD records point into the uploaded wire buffer.
+//
+// The encoder state that outlives a flush (drawing area, current CLUT slots, the CLUT snapshot table) travels as an
+// EncState blob per instance, so the host encoder (psxgpu_submit_wire path) and the device encoder can be mixed.
+#pragma once
+
+#include "encoder.h"
+#include "psx_types.h"
+
+#include <cuda_runtime.h>
+
+namespace psx {
+
+constexpr uint32_t ENC_SLOT_VALID = 0x80000000u; // slot_key: x | y << 10 | is8 << 19 | VALID
+
+// == EncoderStateBlob (encoder.h): raw drawing area l, t, r, b (clamped like Encoder::m_area), current CLUT slots,
+// allocation hand, snapshot table.
+using EncState = EncoderStateBlob;
+static_assert(sizeof(EncState) == 1040, "EncState");
+
+// One instance of a chunk: where its stream sits in the chunk's wire buffer and where its outputs go.
+struct alignas(16) EncInst
+{
+  uint32_t instance;  // VRAM instance
+  uint32_t rec_begin; // first entry of rec_off[]
+  uint32_t n_records;
+  uint32_t cmd_base, cmd_cap;
+  uint32_t clut_base, clut_cap;
+  uint32_t epoch_base, epoch_cap;
+  uint32_t pad[3];
+};
+static_assert(sizeof(EncInst) == 48, "EncInst");
+
+struct EncResult
+{
+  uint32_t n_cmds, n_clut, n_epochs, pad;
+};
+
+enum
+{
+  ENC_STAT_WIRE = 0,
+  ENC_STAT_PRIMS,
+  ENC_STAT_EPOCHS,
+  ENC_STAT_CUTS_RAW,
+  ENC_STAT_CUTS_WAR,
+  ENC_STAT_CUTS_CLUT,
+  ENC_STAT_SELF,
+  ENC_STAT_COPY,
+  ENC_STAT_UPLOAD,
+  ENC_STAT_CLUT_OPS,
+  ENC_STAT_CLUT_HITS,
+  ENC_STAT_REJECTED,
+  ENC_STAT_COUNT = 16
+};
+
+// D2H after a chunk has been encoded: everything the host needs to launch the chunk's waves.
+struct EncSummary
+{
+  uint32_t max_epochs;  // number of waves
+  uint32_t total_items; // sum of epochs
+  uint32_t overflow;    // an output capacity was exceeded (cannot happen with capacities from the host walk)
+  uint32_t pad;
+  unsigned long long stats[ENC_STAT_COUNT];
+};
+// Per wave k (D2H, first ENC_WAVES_INLINE entries with the summary): item offset, count and what it contains.
+struct EncWave
+{
+  uint32_t item_off, item_count;
+  uint32_t flags; // 1 has CLUT ops, 2 has tiled epochs, 4 has serial epochs
+  uint32_t pad;
+};
+constexpr uint32_t ENC_WAVES_INLINE = 2048;
+
+struct EncodeArgs
+{
+  const uint8_t* wire;     // chunk wire buffer (instances back to back, 16-byte aligned, 256 bytes of slack at the end)
+  const uint32_t* rec_off; // byte offset of every record in `wire`
+  const EncInst* inst;
+  uint32_t n_inst;
+  uint32_t clut_slots;
+  uint32_t modulation_crop;
+  EncState* state; // in/out, per chunk-local instance
+  PackedCmd* cmds;
+  uint4* rects; // per command slot: footprints of the open epoch (scratch of the encoder, see encode_kernel.cu)
+  ClutOp* clut_ops;
+  Epoch* epochs;
+  EncResult* result;
+  EncSummary* summary;
+  EncWave* waves;       // [wave_cap]: item_count / flags accumulate here, item_off filled by the scan
+  uint32_t* wave_cursor; // [wave_cap]
+  uint32_t wave_cap;
+  WaveItem* items;
+};
+
+cudaError_t launch_encode(const EncodeArgs& a, cudaStream_t st);
+
+} // namespace psx

@@ -192,6 +192,47 @@ void Encoder::reset_clut_state()
   m_alloc_hand = 1;
 }
 
+void Encoder::export_state(EncoderStateBlob& out) const
+{
+  std::memset(&out, 0, sizeof(out));
+  for (int i = 0; i < 4; i++)
+    out.area[i] = m_area[i];
+  out.cur_lo = static_cast<uint8_t>(m_cur_lo);
+  out.cur_hi = static_cast<uint8_t>(m_cur_hi);
+  out.alloc_hand = static_cast<uint16_t>(m_alloc_hand);
+  for (uint32_t i = 1; i < m_clut_slots; i++)
+  {
+    const ClutSlot& s = m_slots[i];
+    if (s.valid)
+      out.slot_key[i] = s.x | (static_cast<uint32_t>(s.y) << 10) | (s.is8 ? (1u << 19) : 0u) | 0x80000000u;
+  }
+}
+
+void Encoder::import_state(const EncoderStateBlob& in)
+{
+  reset_clut_state();
+  for (int i = 0; i < 4; i++)
+    m_area[i] = in.area[i];
+  m_cur_lo = std::min<uint32_t>(in.cur_lo, m_clut_slots - 1);
+  m_cur_hi = std::min<uint32_t>(in.cur_hi, m_clut_slots - 1);
+  m_alloc_hand = (in.alloc_hand >= 1 && in.alloc_hand < m_clut_slots) ? in.alloc_hand : 1;
+  for (uint32_t i = 1; i < m_clut_slots; i++)
+  {
+    const uint32_t k = in.slot_key[i];
+    if (!(k & 0x80000000u))
+      continue;
+    ClutSlot& s = m_slots[i];
+    s.x = static_cast<uint16_t>(k & 0x3FFu);
+    s.y = static_cast<uint16_t>((k >> 10) & 0x1FFu);
+    s.is8 = (k >> 19) & 1u;
+    s.valid = true;
+    chain_insert(i);
+    RectSet src;
+    src.add_wrapped(s.x, s.y, s.is8 ? 256u : 16u, 1);
+    m_clut_sources.add(src);
+  }
+}
+
 void Encoder::close_epoch(uint32_t kind)
 {
   Epoch e;

@@ -89,6 +89,16 @@ private:
   bool m_any = false;
 };
 
+// Encoder state that outlives a flush, in the form the device encoder (device_encoder.h, EncState) keeps it.
+struct EncoderStateBlob
+{
+  uint16_t area[4];
+  uint8_t cur_lo, cur_hi;
+  uint16_t alloc_hand;
+  uint32_t pad;
+  uint32_t slot_key[256]; // x | y << 10 | is8 << 19 | valid << 31
+};
+
 enum class EncodeResult
 {
   Ok,        // whole buffer consumed
@@ -130,6 +140,9 @@ public:
   EncoderStats stats;
 
   void set_modulation_crop(bool on) { m_modulation_crop = on; }
+  // Hand-over between this encoder and the device encoder of the batched path; only between flushes.
+  void export_state(EncoderStateBlob& out) const;
+  void import_state(const EncoderStateBlob& in);
   uint32_t clut_lo_slot() const { return m_cur_lo; }
   uint32_t clut_hi_slot() const { return m_cur_hi; }
 

@@ -52,7 +52,8 @@ typedef struct psxgpu_opts {
   uint32_t clut_slots;       /* CLUT snapshot slots per instance (4..256, 0 = 256) */
   uint32_t encode_threads;   /* host threads for psxgpu_submit_batch (0 = hardware concurrency) */
   uint32_t profile;          /* 1: time every raster wave with CUDA events (psxgpu_get_timing) */
-  uint32_t reserved[9];
+  uint32_t reserved[9];      /* [0] = 1: no persistent (latency-mode) kernel; [1]: where psxgpu_submit_batch encodes —
+                                0 auto (on the device for batches of >= 16 instances), 1 host threads, 2 device */
 } psxgpu_opts;
 
 typedef struct psxgpu_stats {
@@ -95,7 +96,8 @@ int psxgpu_abi_version(void);
  * UpdateDisplay scans out into the context's display buffer (psxgpu_display). */
 int psxgpu_submit_wire(psxgpu_ctx* ctx, uint32_t instance, const void* wire, size_t bytes);
 
-/* Batched form: streams[i] goes to instance first_instance + i.  Encoded in parallel on host threads.
+/* Batched form: streams[i] goes to instance first_instance + i.  Large batches are uploaded raw and encoded on the
+ * device (one warp per instance); small ones are encoded on host threads (latency mode).
  * Barrier records (ReadVRAM, LoadState, ClearVRAM, UpdateDisplay) are not allowed here. */
 int psxgpu_submit_batch(psxgpu_ctx* ctx, uint32_t first_instance, uint32_t count, const void* const* streams,
                         const size_t* bytes);

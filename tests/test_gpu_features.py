@@ -335,3 +335,81 @@ def test_psxgpu_trace_replay_through_the_gp0_frontend(oracle, interlaced):
         assert (gi is None) == (wi is None)
         if wi is not None:
             assert gi.shape == wi.shape and np.array_equal(gi, wi), f"frame {i} scan-out"
+
+
+DEVICE_ENCODER_CASES = ([(0, s, 600, f) for s in (3, 4, 5, 6, 7, 8) for f in (0, 1, 2, 3)] +
+                        [(1, 2, 1500, 0), (2, 2, 1500, 0), (3, 2, 800, 0), (4, 2, 800, 0), (5, 2, 6, 200)])
+
+
+def _strip_barriers(stream: bytes) -> bytes:
+    return b"".join(stream[off:off + size] for typ, off, size in streams.iter_records(stream) if typ not in (7, 9, 12, 15))
+
+
+def test_device_encoder_matches_oracle_and_host_encoder(oracle):
+    """psxgpu_submit_batch with the encoder on the device (one warp per instance) against the oracle, on every kind of
+    stream the generator makes; the host-encoded batch of the same streams must agree on the epoch statistics too."""
+    batch = [_strip_barriers(streams.generate(*c)) for c in DEVICE_ENCODER_CASES]
+    want = [oracle.hash64(oracle.render(s)) for s in batch]
+    stats = {}
+    for mode in (2, 1):
+        with _ctx(len(batch), encode_mode=mode, no_persistent=True) as ctx:
+            ctx.submit_batch(batch)
+            ctx.flush()
+            got = [int(h) for h in ctx.hash()]
+            bad = [DEVICE_ENCODER_CASES[i] for i in range(len(batch)) if got[i] != want[i]]
+            assert not bad, (mode, bad)
+            stats[mode] = ctx.stats()
+    for key in ("wire_commands", "packed_prims", "epochs", "cuts_raw", "cuts_war", "cuts_clut", "serial_self_sampling",
+                "serial_copy", "serial_upload", "clut_ops", "clut_cache_hits", "rejected"):
+        assert stats[2][key] == stats[1][key], (key, stats[2][key], stats[1][key])
+
+
+def test_device_encoder_state_carries_across_flushes_and_paths(oracle):
+    """Drawing area, current CLUT and the snapshot table survive a flush and the hand-over between the device encoder
+    (batches) and the host encoder (psxgpu_submit_wire), in both directions."""
+    n = 20
+    full = [_strip_barriers(streams.generate(0, 100 + i, 900, 3)) for i in range(n)]
+    cut = []
+    for s in full:
+        offs = [off for typ, off, _ in streams.iter_records(s)]
+        cut.append([offs[len(offs) // 3], offs[2 * len(offs) // 3]])
+    want = [oracle.hash64(oracle.render(s)) for s in full]
+    with _ctx(n, encode_mode=2) as ctx:
+        ctx.submit_batch([s[:c[0]] for s, c in zip(full, cut)])       # device
+        ctx.flush()
+        for i, (s, c) in enumerate(zip(full, cut)):                   # host, one instance at a time
+            ctx.submit(s[c[0]:c[1]], instance=i)
+        ctx.submit_batch([s[c[1]:] for s, c in zip(full, cut)])       # device again
+        ctx.flush()
+        got = [int(h) for h in ctx.hash()]
+    assert got == want
+    # several device-encoded flushes in a row, chunked
+    with _ctx(n, encode_mode=2) as ctx:
+        ctx.set_batch_chunk(7)
+        for part in range(3):
+            ctx.submit_batch([s[([0] + c)[part]:(c + [len(s)])[part]] for s, c in zip(full, cut)])
+            ctx.flush()
+        assert [int(h) for h in ctx.hash()] == want
+
+
+def test_device_encoder_rejects_bad_streams_and_handles_empty_ones(oracle):
+    from duckstation_b200 import PsxGpuError
+
+    good = _strip_barriers(streams.generate(2, 5, 300, 0))
+    with _ctx(4, encode_mode=2) as ctx:
+        with pytest.raises(PsxGpuError):
+            ctx.submit_batch([good, good[:-4], good, good])
+        with pytest.raises(PsxGpuError):
+            ctx.submit_batch([good, good + streams.make_update_display(0, 0, 320, 240), good, good])
+    with _ctx(4, encode_mode=2) as ctx:
+        ctx.submit_batch([good, b"", good, b""])
+        ctx.flush()
+        h = [int(x) for x in ctx.hash()]
+        assert h[0] == h[2] == oracle.hash64(oracle.render(good))
+        assert h[1] == h[3] == oracle.hash64(np.zeros((512, 1024), dtype=np.uint16))
+        ctx.run_staged()  # replaying a device-encoded flush on top of its own result must be deterministic
+        ctx.sync()
+        again = [int(x) for x in ctx.hash()]
+        oracle.render(good)
+        oracle.exec(good)
+        assert again[0] == oracle.hash64(oracle.vram())
