@@ -1346,6 +1346,177 @@ __global__ void __launch_bounds__(32 * ENC_WARPS) encode_kernel(EncodeArgs A)
       nb = static_cast<uint32_t>(__ffs(static_cast<int>(area_mask)));
     const uint32_t summary = cls | (nprim << 4) | (pf[0] << 8) | (pf[1] << 16);
 
+    // ---- Batch-parallel commit.  If bounding boxes alone prove that nothing in the batch can conflict — not with the
+    // open epoch's read / write sets, not with a CLUT source, not with another record of the batch — the hazard
+    // logic has nothing to decide: output slots are a prefix sum, every lane stores its own records, and only the
+    // CLUT-cache updates are walked in order.  Anything else takes the record-by-record loop below.
+    {
+      const bool in_batch = lane < nb;
+      const bool fast = in_batch && cls == CLS_FAST;
+      const bool e0 = fast && (pf[0] & FP_EMIT), e1 = fast && (pf[1] & FP_EMIT);
+      const bool t0 = e0 && (pf[0] & FP_TEXTURED), t1 = e1 && (pf[1] & FP_TEXTURED);
+      auto box_of = [&](uint32_t from, uint32_t (&wb)[4], uint32_t (&rb)[4]) {
+        uint32_t a[4] = {0xFFFFu, 0xFFFFu, 0u, 0u}, b[4] = {0xFFFFu, 0xFFFFu, 0u, 0u};
+        if (lane >= from)
+        {
+          if (e0)
+          {
+            a[0] = pwr0[0] & 0xFFFFu, a[1] = pwr0[0] >> 16, a[2] = pwr1[0] & 0xFFFFu, a[3] = pwr1[0] >> 16;
+          }
+          if (e1)
+          {
+            a[0] = min(a[0], pwr0[1] & 0xFFFFu), a[1] = min(a[1], pwr0[1] >> 16);
+            a[2] = max(a[2], pwr1[1] & 0xFFFFu), a[3] = max(a[3], pwr1[1] >> 16);
+          }
+          if (t0)
+          {
+            b[0] = prd0[0] & 0xFFFFu, b[1] = prd0[0] >> 16, b[2] = prd1[0] & 0xFFFFu, b[3] = prd1[0] >> 16;
+          }
+          if (t1)
+          {
+            b[0] = min(b[0], prd0[1] & 0xFFFFu), b[1] = min(b[1], prd0[1] >> 16);
+            b[2] = max(b[2], prd1[1] & 0xFFFFu), b[3] = max(b[3], prd1[1] >> 16);
+          }
+        }
+        wb[0] = __reduce_min_sync(FULL, a[0]);
+        wb[1] = __reduce_min_sync(FULL, a[1]);
+        wb[2] = __reduce_max_sync(FULL, a[2]);
+        wb[3] = __reduce_max_sync(FULL, a[3]);
+        rb[0] = __reduce_min_sync(FULL, b[0]);
+        rb[1] = __reduce_min_sync(FULL, b[1]);
+        rb[2] = __reduce_max_sync(FULL, b[2]);
+        rb[3] = __reduce_max_sync(FULL, b[3]);
+      };
+      auto boxes_meet = [](const uint32_t (&p)[4], uint32_t x0, uint32_t y0, uint32_t x1, uint32_t y1) -> bool {
+        return p[0] <= p[2] && x0 <= x1 && p[0] <= x1 && x0 <= p[2] && p[1] <= y1 && y0 <= p[3];
+      };
+      uint32_t wb[4], rb[4];
+      box_of(0, wb, rb);
+      const uint32_t mine_emit = (e0 ? 1u : 0u) + (e1 ? 1u : 0u);
+      uint32_t incl = mine_emit;
+#pragma unroll
+      for (uint32_t d = 1; d < 32; d <<= 1)
+      {
+        const uint32_t t = __shfl_up_sync(FULL, incl, d);
+        if (lane >= d)
+          incl += t;
+      }
+      const uint32_t rank = incl - mine_emit, total = __shfl_sync(FULL, incl, 31);
+      // per-lane obstacles
+      bool bad = in_batch && (cls == CLS_SLOW || (fast && ((pf[0] | pf[1]) & FP_SELF)));
+      if (in_batch && cls == CLS_CLUT)
+      {
+        // source row of the snapshot this record may take (whole row if it wraps)
+        const uint32_t reg = pv[0][0] & 0xFFFFu, is8 = (pv[0][0] >> 16) & 0xFFu;
+        uint32_t sx0 = PSX_PAL_X(reg), sx1 = sx0 + (is8 ? 255u : 15u);
+        const uint32_t sy = PSX_PAL_Y(reg);
+        if (sx1 >= VRAM_W)
+        {
+          sx0 = 0;
+          sx1 = VRAM_W - 1;
+        }
+        bad = bad || boxes_meet(wb, sx0, sy, sx1, sy) ||
+              (E.writes.any && sx0 <= E.writes.x1 && E.writes.x0 <= sx1 && sy <= E.writes.y1 && E.writes.y0 <= sy);
+      }
+      bool ok = !__any_sync(FULL, bad);
+      ok = ok && !boxes_meet(wb, rb[0], rb[1], rb[2], rb[3]);
+      ok = ok && !(E.reads.any && boxes_meet(wb, E.reads.x0, E.reads.y0, E.reads.x1, E.reads.y1));
+      ok = ok && !(E.writes.any && boxes_meet(rb, E.writes.x0, E.writes.y0, E.writes.x1, E.writes.y1));
+      ok = ok && !(E.clut_src.any && boxes_meet(wb, E.clut_src.x0, E.clut_src.y0, E.clut_src.x1, E.clut_src.y1));
+      ok = ok && (E.n_cmds - E.epoch_cmd_begin) + total < 65535u && E.n_cmds + total <= E.cmd_cap;
+      if (ok)
+      {
+        uint32_t mylo = E.cur_lo, myhi = E.cur_hi, myserial = E.epoch_serial;
+        const uint32_t n0 = E.n_cmds;
+        uint32_t clut_mask = __ballot_sync(FULL, in_batch && cls == CLS_CLUT);
+        uint32_t prev = 0, set_from = 0;
+        while (clut_mask)
+        {
+          const uint32_t c = static_cast<uint32_t>(__ffs(static_cast<int>(clut_mask))) - 1u;
+          clut_mask &= clut_mask - 1u;
+          // the primitives in front of this CLUT update use the slots that are current now
+          if (lane >= prev && lane < c && (t0 || t1))
+          {
+            E.last[mylo] = myserial;
+            E.last[myhi] = myserial;
+          }
+          __syncwarp();
+          E.n_cmds = n0 + __shfl_sync(FULL, rank, c);
+          const uint32_t epochs_before = E.n_epochs;
+          const uint32_t v = __shfl_sync(FULL, pv[0][0], c);
+          E.update_clut(v & 0xFFFFu, ((v >> 16) & 0xFFu) != 0, false);
+          if (E.n_epochs != epochs_before)
+            set_from = c; // slot pressure cut the epoch: everything in front of c belongs to the closed one
+          if (lane > c)
+          {
+            mylo = E.cur_lo;
+            myhi = E.cur_hi;
+            myserial = E.epoch_serial;
+          }
+          prev = c + 1;
+        }
+        if (lane >= prev && (t0 || t1))
+        {
+          E.last[mylo] = myserial;
+          E.last[myhi] = myserial;
+        }
+        __syncwarp();
+        const uint32_t w1 = hdm | (mylo << 16) | (myhi << 24);
+        const uint32_t w3 = E.area[0] | (E.area[1] << 16), w4 = E.area[2] | (E.area[3] << 16);
+        if (e0)
+        {
+          const uint32_t at = n0 + rank;
+          uint4* d = reinterpret_cast<uint4*>(E.cmds + at);
+          d[0] = make_uint4(hw0, w1, hwin, w3);
+          d[1] = make_uint4(w4, pv[0][0], pv[0][1], pv[0][2]);
+          d[2] = make_uint4(pv[0][3], pv[0][4], pv[0][5], pv[0][6]);
+          d[3] = make_uint4(pv[0][7], 0, 0, 0);
+          E.rects[at] = make_uint4(pwr0[0], pwr1[0], t0 ? prd0[0] : 0xFFFFFFFFu, prd1[0]);
+        }
+        if (e1)
+        {
+          const uint32_t at = n0 + rank + (e0 ? 1u : 0u);
+          uint4* d = reinterpret_cast<uint4*>(E.cmds + at);
+          d[0] = make_uint4(hw0, w1, hwin, w3);
+          d[1] = make_uint4(w4, pv[1][0], pv[1][1], pv[1][2]);
+          d[2] = make_uint4(pv[1][3], pv[1][4], pv[1][5], pv[1][6]);
+          d[3] = make_uint4(pv[1][7], 0, 0, 0);
+          E.rects[at] = make_uint4(pwr0[1], pwr1[1], t1 ? prd0[1] : 0xFFFFFFFFu, prd1[1]);
+        }
+        E.n_cmds = n0 + total;
+        E.st_prims += total;
+        E.st_rejected += __popc(__ballot_sync(FULL, fast && (pf[0] & FP_REJECTED))) + __popc(__ballot_sync(FULL, fast && (pf[1] & FP_REJECTED)));
+        if (set_from != 0)
+          box_of(set_from, wb, rb);
+        if (wb[0] <= wb[2])
+        {
+          E.writes.any = 1;
+          E.writes.x0 = min(E.writes.x0, wb[0]);
+          E.writes.y0 = min(E.writes.y0, wb[1]);
+          E.writes.x1 = max(E.writes.x1, wb[2]);
+          E.writes.y1 = max(E.writes.y1, wb[3]);
+        }
+        if (rb[0] <= rb[2])
+        {
+          E.reads.any = 1;
+          E.reads.x0 = min(E.reads.x0, rb[0]);
+          E.reads.y0 = min(E.reads.y0, rb[1]);
+          E.reads.x1 = max(E.reads.x1, rb[2]);
+          E.reads.y1 = max(E.reads.y1, rb[3]);
+        }
+        if (area_mask)
+        {
+          const uint32_t r = nb - 1;
+          E.area[0] = __shfl_sync(FULL, pv[0][0], r);
+          E.area[1] = __shfl_sync(FULL, pv[0][1], r);
+          E.area[2] = __shfl_sync(FULL, pv[0][2], r);
+          E.area[3] = __shfl_sync(FULL, pv[0][3], r);
+        }
+        base += nb;
+        continue;
+      }
+    }
+
     for (uint32_t r = 0; r < nb; r++)
     {
       const uint32_t sm = __shfl_sync(FULL, summary, r);
