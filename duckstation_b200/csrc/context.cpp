@@ -175,7 +175,9 @@ struct psxgpu_ctx
   {
     DevBuf d_cmds, d_setups, d_bins, d_payload, d_clutops, d_items, d_misc;
     // device-encoded chunks: d_payload holds the raw wire streams (upload pixels are read in place)
-    DevBuf d_recoff, d_inst, d_state, d_epochs, d_result, d_waves, d_cursor, d_summary, d_rects;
+    DevBuf d_recoff, d_inst, d_state, d_state_out, d_epochs, d_result, d_waves, d_cursor, d_summary, d_rects;
+    EncodeArgs enc_args{};
+    bool device_encoded = false; // psxgpu_run_staged replays the encode kernels too (from the resident wire streams)
     cudaEvent_t ev_copied = nullptr, ev_encoded = nullptr;
     cudaEvent_t ev_done = nullptr; // main stream: last launch that reads this chunk's buffers
     bool done_valid = false;
@@ -516,6 +518,7 @@ int launch_chunk_impl(psxgpu_ctx* ctx, const std::vector<uint32_t>& work, const 
     S.wave_has_serial.push_back(has_serial);
   }
   S.n_cmds = static_cast<uint32_t>(n_cmds);
+  S.device_encoded = false;
   S.n_instances = nw;
   const uint32_t n_waves = static_cast<uint32_t>(S.wave_off.size()) - 1;
   S.persistent = ctx->persist_max != 0 && nw <= ctx->persist_max && n_waves > 0 && !ctx->opts.profile;
@@ -981,6 +984,7 @@ int submit_batch_device(psxgpu_ctx* ctx, uint32_t first, uint32_t count, const v
     CK(S.d_recoff.ensure(n_rec_total * 4 + 16), "device alloc (record offsets)");
     CK(S.d_inst.ensure(static_cast<size_t>(cn) * sizeof(EncInst)), "device alloc (instances)");
     CK(S.d_state.ensure(static_cast<size_t>(cn) * sizeof(EncState)), "device alloc (encoder state)");
+    CK(S.d_state_out.ensure(static_cast<size_t>(cn) * sizeof(EncState)), "device alloc (encoder state)");
     CK(S.d_cmds.ensure(cmd_base[cn] * sizeof(PackedCmd) + 64), "device alloc (commands)");
     CK(S.d_setups.ensure(cmd_base[cn] * sizeof(PrimSetup) + 64), "device alloc (setup records)");
     CK(S.d_bins.ensure(cmd_base[cn] * sizeof(BinInfo) + 64), "device alloc (bins)");
@@ -1045,7 +1049,8 @@ int submit_batch_device(psxgpu_ctx* ctx, uint32_t first, uint32_t count, const v
     a.n_inst = cn;
     a.clut_slots = ctx->clut_slots;
     a.modulation_crop = ctx->opts.modulation_crop ? 1u : 0u;
-    a.state = static_cast<EncState*>(S.d_state.p);
+    a.state_in = static_cast<const EncState*>(S.d_state.p);
+    a.state_out = static_cast<EncState*>(S.d_state_out.p);
     a.cmds = static_cast<PackedCmd*>(S.d_cmds.p);
     a.rects = static_cast<uint4*>(S.d_rects.p);
     a.clut_ops = static_cast<ClutOp*>(S.d_clutops.p);
@@ -1058,10 +1063,12 @@ int submit_batch_device(psxgpu_ctx* ctx, uint32_t first, uint32_t count, const v
     a.items = static_cast<WaveItem*>(S.d_items.p);
     CK(launch_encode(a, es), "encode_kernel");
     ctx->counters.kernel_launches += 3;
+    S.enc_args = a;
+    S.device_encoded = true;
     uint8_t* res = static_cast<uint8_t*>(P->result.p);
     CK(cudaMemcpyAsync(res, S.d_summary.p, sizeof(EncSummary), cudaMemcpyDeviceToHost, es), "D2H summary");
     CK(cudaMemcpyAsync(res + waves_off, S.d_waves.p, waves_inline * sizeof(EncWave), cudaMemcpyDeviceToHost, es), "D2H wave table");
-    CK(cudaMemcpyAsync(res + state_off, S.d_state.p, static_cast<size_t>(cn) * sizeof(EncState), cudaMemcpyDeviceToHost, es),
+    CK(cudaMemcpyAsync(res + state_off, S.d_state_out.p, static_cast<size_t>(cn) * sizeof(EncState), cudaMemcpyDeviceToHost, es),
        "D2H encoder state");
     if (ctx->trace)
       cudaEventRecord(tc.enc1, es);
@@ -1313,7 +1320,7 @@ void psxgpu_destroy(psxgpu_ctx* ctx)
   for (psxgpu_ctx::Chunk* ch : ctx->chunks)
   {
     for (DevBuf* b : {&ch->d_cmds, &ch->d_setups, &ch->d_bins, &ch->d_payload, &ch->d_clutops, &ch->d_items, &ch->d_misc, &ch->d_recoff,
-                      &ch->d_inst, &ch->d_state, &ch->d_epochs, &ch->d_result, &ch->d_waves, &ch->d_cursor, &ch->d_summary, &ch->d_rects})
+                      &ch->d_inst, &ch->d_state, &ch->d_state_out, &ch->d_epochs, &ch->d_result, &ch->d_waves, &ch->d_cursor, &ch->d_summary, &ch->d_rects})
       b->release();
     for (cudaEvent_t ev : {ch->ev_copied, ch->ev_encoded, ch->ev_done})
       if (ev)
@@ -1394,6 +1401,12 @@ int psxgpu_run_staged(psxgpu_ctx* ctx)
   CK(cudaEventRecord(ctx->ev_start, ctx->stream), "event record");
   for (uint32_t c = 0; c < ctx->staged_n; c++)
   {
+    if (ctx->chunks[c]->device_encoded)
+    {
+      // the resident inputs of a device-encoded flush are the raw wire streams: encode them again
+      CK(launch_encode(ctx->chunks[c]->enc_args, ctx->stream), "encode_kernel");
+      ctx->counters.kernel_launches += 3;
+    }
     rc = run_chunk(ctx, *ctx->chunks[c]);
     if (rc != PSXGPU_OK)
       return rc;

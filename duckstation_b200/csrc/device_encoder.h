@@ -86,7 +86,8 @@ struct EncodeArgs
   uint32_t n_inst;
   uint32_t clut_slots;
   uint32_t modulation_crop;
-  EncState* state; // in/out, per chunk-local instance
+  const EncState* state_in; // per chunk-local instance: encoder state at the start of the flush ...
+  EncState* state_out;      // ... and after it (kept apart so that a flush can be replayed from its resident inputs)
   PackedCmd* cmds;
   uint4* rects; // per command slot: footprints of the open epoch (scratch of the encoder, see encode_kernel.cu)
   ClutOp* clut_ops;

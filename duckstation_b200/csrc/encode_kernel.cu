@@ -630,7 +630,8 @@ __global__ void __launch_bounds__(32 * ENC_WARPS) encode_kernel(EncodeArgs A)
   if (idx >= A.n_inst)
     return;
   const EncInst ii = A.inst[idx];
-  EncState* st = A.state + idx;
+  const EncState* st = A.state_in + idx;
+  EncState* st_out = A.state_out + idx;
 
   WarpEncoder E;
   E.lane = lane;
@@ -1614,10 +1615,11 @@ __global__ void __launch_bounds__(32 * ENC_WARPS) encode_kernel(EncodeArgs A)
   if (lane == 0)
   {
     for (int i = 0; i < 4; i++)
-      st->area[i] = static_cast<uint16_t>(E.area[i]);
-    st->cur_lo = static_cast<uint8_t>(E.cur_lo);
-    st->cur_hi = static_cast<uint8_t>(E.cur_hi);
-    st->alloc_hand = static_cast<uint16_t>(E.hand);
+      st_out->area[i] = static_cast<uint16_t>(E.area[i]);
+    st_out->cur_lo = static_cast<uint8_t>(E.cur_lo);
+    st_out->cur_hi = static_cast<uint8_t>(E.cur_hi);
+    st_out->alloc_hand = static_cast<uint16_t>(E.hand);
+    st_out->pad = 0;
     EncResult res;
     res.n_cmds = min(E.n_cmds, E.cmd_cap);
     res.n_clut = min(E.n_clut, E.clut_cap);
@@ -1643,7 +1645,7 @@ __global__ void __launch_bounds__(32 * ENC_WARPS) encode_kernel(EncodeArgs A)
     atomicAdd(&S[ENC_STAT_REJECTED], static_cast<unsigned long long>(E.st_rejected));
   }
   for (uint32_t s = lane; s < 256; s += 32)
-    st->slot_key[s] = E.key[s];
+    st_out->slot_key[s] = E.key[s];
   // wave k = epoch k of every instance: count the items and what they contain
   const uint32_t ne = min(E.n_epochs, E.epoch_cap);
   for (uint32_t k = lane; k < ne && k < A.wave_cap; k += 32)

@@ -111,8 +111,10 @@ int psxgpu_sync(psxgpu_ctx* ctx);
  * encoded, so that host encoding overlaps copies and kernels.  0 = automatic (count/8, at least 128). */
 int psxgpu_set_batch_chunk(psxgpu_ctx* ctx, uint32_t instances_per_chunk);
 
-/* Re-run the device part of the most recent flush (setup + all waves) from the command buffers that are still
- * resident in HBM.  For steady-state measurement; the caller is responsible for the VRAM state it starts from. */
+/* Re-run the device part of the most recent flush from the inputs that are still resident in HBM: for a
+ * device-encoded batch the raw wire streams (encode + setup + all waves), for host-encoded work the packed command
+ * buffers (setup + all waves).  For steady-state measurement; the caller is responsible for the VRAM state it
+ * starts from. */
 int psxgpu_run_staged(psxgpu_ctx* ctx);
 
 /* GPUBackend::ReadVRAM contract (gpu_backend.h:152, gpu_hw.cpp:3472-3515): after the call the pixels of the
