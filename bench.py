@@ -10,9 +10,11 @@ per-instance 64-bit VRAM hashes per step.
 
 A "step" = every instance's full command list executed to completion + hash.
   value : whole-job Gpixels/s (covered pixels = ShadePixel invocations + fill + upload destination pixels, counted by
-          the CPU oracle) with the packed command buffers already resident in HBM (psxgpu_run_staged + hash + gather).
-  e2e   : same metric through the reference-facing C ABI from HOST wire-format buffers: per step
-          psxgpu_submit_batch (host encode) + psxgpu_flush (pinned staging, H2D, kernels) + psxgpu_hash (D2H).
+          the CPU oracle) with the raw wire streams already resident in HBM: psxgpu_run_staged (encode kernels, setup,
+          all raster waves) + hash + gather.
+  e2e   : same metric through the reference-facing C ABI from HOST wire-format buffers (page-locked): per step
+          psxgpu_submit_batch (framing walk on the host, H2D of the raw streams, device encode, kernels) +
+          psxgpu_flush + psxgpu_hash (D2H).
 Parity gate: every per-instance hash is compared with the CPU oracle's (all instances at N=1, a 64-instance
 sample per rank otherwise); a mismatch makes the run fail.
 
@@ -288,7 +290,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     # ---- e2e: host wire buffers -> C ABI -> hashes on the host, every step ----
     host_hashes = None
     ctx.reset_stats()
-    ctx.set_batch_chunk(0)  # automatic chunking: host encoding of chunk k+1 overlaps copy + kernels of chunk k
+    ctx.set_batch_chunk(0)  # automatic chunking: the copy of chunk k+1 overlaps the encode + waves of chunk k
     for _ in range(max(1, args.warmup // 2)):
         ctx.submit_batch_raw(ptrs, sizes, n_inst)
         ctx.flush()
