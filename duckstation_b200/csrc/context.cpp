@@ -178,7 +178,7 @@ struct psxgpu_ctx
     DevBuf d_recoff, d_inst, d_state, d_state_out, d_epochs, d_result, d_waves, d_cursor, d_summary, d_rects;
     EncodeArgs enc_args{};
     bool device_encoded = false; // psxgpu_run_staged replays the encode kernels too (from the resident wire streams)
-    cudaEvent_t ev_copied = nullptr, ev_encoded = nullptr;
+    cudaEvent_t ev_copied = nullptr, ev_walked = nullptr, ev_encoded = nullptr;
     cudaEvent_t ev_done = nullptr; // main stream: last launch that reads this chunk's buffers
     bool done_valid = false;
     uint32_t n_cmds = 0;
@@ -631,62 +631,6 @@ void ensure_host_state(psxgpu_ctx* ctx, uint32_t i)
   }
 }
 
-struct WalkResult
-{
-  uint32_t n_rec = 0, cmd_cap = 0, clut_cap = 0;
-  int status = 0;
-};
-
-// Record framing exactly as Encoder::add_wire checks it; counts what the stream can produce at most.  With rec_off the
-// byte offset of every record (relative to the chunk's wire buffer) is written out as well.
-void walk_stream(const uint8_t* p, size_t bytes, WalkResult& r, uint32_t* rec_off, uint32_t base)
-{
-  const uint8_t* const begin = p;
-  const uint8_t* const end = p + bytes;
-  r = WalkResult();
-  while (p < end)
-  {
-    if (static_cast<size_t>(end - p) < sizeof(psx_cmd_header))
-    {
-      r.status = PSXGPU_E_MALFORMED;
-      return;
-    }
-    const psx_cmd_header* h = reinterpret_cast<const psx_cmd_header*>(p);
-    if (h->size < sizeof(psx_cmd_header) || (h->size & 3u) != 0 || h->size > static_cast<size_t>(end - p))
-    {
-      r.status = PSXGPU_E_MALFORMED;
-      return;
-    }
-    switch (h->type)
-    {
-      case PSX_CMD_CLEAR_VRAM:
-      case PSX_CMD_LOAD_STATE:
-      case PSX_CMD_READ_VRAM:
-      case PSX_CMD_UPDATE_DISPLAY: r.status = PSXGPU_E_UNSUPPORTED; return;
-      case PSX_CMD_DRAW_POLYGON:
-      case PSX_CMD_DRAW_PRECISE_POLYGON:
-        if (h->size >= sizeof(psx_draw_header))
-          r.cmd_cap += (reinterpret_cast<const psx_draw_header*>(p)->num_vertices > 3) ? 2u : 1u;
-        break;
-      case PSX_CMD_DRAW_LINE:
-      case PSX_CMD_DRAW_PRECISE_LINE:
-        if (h->size >= sizeof(psx_draw_header))
-          r.cmd_cap += reinterpret_cast<const psx_draw_header*>(p)->num_vertices / 2u;
-        break;
-      case PSX_CMD_DRAW_RECTANGLE:
-      case PSX_CMD_FILL_VRAM:
-      case PSX_CMD_COPY_VRAM:
-      case PSX_CMD_UPDATE_VRAM: r.cmd_cap += 1; break;
-      case PSX_CMD_UPDATE_CLUT: r.clut_cap += 1; break;
-      default: break;
-    }
-    if (rec_off)
-      rec_off[r.n_rec] = base + static_cast<uint32_t>(p - begin);
-    r.n_rec++;
-    p += h->size;
-  }
-}
-
 struct PendingChunk
 {
   psxgpu_ctx::Chunk* S = nullptr;
@@ -698,6 +642,266 @@ struct PendingChunk
   uint64_t cmd_total = 0;
 };
 
+// True if [p, p + bytes) starts and ends in page-locked host memory (cudaHostAlloc / cudaHostRegister).
+bool is_pinned_host(const void* p, size_t bytes)
+{
+  if (!p || bytes == 0)
+    return false;
+  cudaPointerAttributes a0{}, a1{};
+  if (cudaPointerGetAttributes(&a0, p) != cudaSuccess || cudaPointerGetAttributes(&a1, static_cast<const uint8_t*>(p) + bytes - 1) != cudaSuccess)
+  {
+    cudaGetLastError();
+    return false;
+  }
+  return a0.type == cudaMemoryTypeHost && a1.type == cudaMemoryTypeHost;
+}
+
+// Stage A of a device-encoded chunk: upload the raw streams (copy_stream) and check their framing on the device
+// (walk_kernel on the chunk's encode stream); the per-instance counts come back into the pinned set.
+int stage_upload(psxgpu_ctx* ctx, PendingChunk& pc, uint32_t chunk_index, const void* const* streams, const size_t* bytes)
+{
+  const uint32_t cn = pc.cn;
+  psxgpu_ctx::PinnedSet* P = nullptr;
+  int rc = acquire_pinned(ctx, P);
+  if (rc != PSXGPU_OK)
+    return rc;
+  pc.P = P;
+  const double t0 = now_ms();
+  // Where the streams go in the chunk's device wire buffer.  Streams that already sit in page-locked memory are
+  // copied from where they are (neighbours in one copy); anything else is packed into our pinned staging buffer.
+  bool direct = true;
+  for (uint32_t k = 0; k < cn && direct; k++)
+    direct = bytes[k] == 0 || ((reinterpret_cast<uintptr_t>(streams[k]) & 15u) == 0 && is_pinned_host(streams[k], bytes[k]));
+  struct Run
+  {
+    const uint8_t* src;
+    uint64_t dev_off, bytes;
+  };
+  std::vector<Run> runs;
+  std::vector<uint64_t> wire_off(cn + 1, 0);
+  if (direct)
+  {
+    uint64_t dev = 0;
+    for (uint32_t k = 0; k < cn; k++)
+    {
+      const uint8_t* src = static_cast<const uint8_t*>(streams[k]);
+      const uint64_t n = bytes[k];
+      if (n == 0)
+      {
+        wire_off[k] = dev;
+        continue;
+      }
+      if (!runs.empty() && src >= runs.back().src + runs.back().bytes && src - (runs.back().src + runs.back().bytes) < 64)
+      {
+        wire_off[k] = runs.back().dev_off + static_cast<uint64_t>(src - runs.back().src);
+        runs.back().bytes = static_cast<uint64_t>(src - runs.back().src) + n;
+      }
+      else
+      {
+        dev = runs.empty() ? 0 : ((runs.back().dev_off + runs.back().bytes + 15u) & ~static_cast<uint64_t>(15));
+        wire_off[k] = dev;
+        runs.push_back(Run{src, dev, n});
+      }
+    }
+    wire_off[cn] = runs.empty() ? 0 : ((runs.back().dev_off + runs.back().bytes + 15u) & ~static_cast<uint64_t>(15));
+  }
+  else
+  {
+    for (uint32_t k = 0; k < cn; k++)
+      wire_off[k + 1] = wire_off[k] + ((bytes[k] + 15u) & ~static_cast<uint64_t>(15));
+  }
+  for (uint32_t k = 0; k < cn; k++)
+    if (bytes[k] > 0xFFFFFF00ull)
+      return ctx->invalid("submit_batch: stream larger than 4 GiB");
+  if (wire_off[cn] > 0xFFFFFF00ull)
+    return ctx->invalid("submit_batch: chunk larger than 4 GiB of records; use a smaller batch chunk");
+  const size_t wire_bytes = static_cast<size_t>(wire_off[cn]) + 256;
+  CK(P->inst.ensure(static_cast<size_t>(cn) * sizeof(EncInst)), "pinned alloc (instances)");
+  CK(P->recoff.ensure(static_cast<size_t>(cn) * sizeof(WalkOut)), "pinned alloc (framing)");
+  CK(P->state.ensure(static_cast<size_t>(cn) * sizeof(EncState)), "pinned alloc (encoder state)");
+  EncInst* hi = static_cast<EncInst*>(P->inst.p);
+  EncState* hs = static_cast<EncState*>(P->state.p);
+  for (uint32_t k = 0; k < cn; k++)
+  {
+    std::memset(&hi[k], 0, sizeof(EncInst));
+    hi[k].instance = pc.first_instance + k;
+    hi[k].wire_off = static_cast<uint32_t>(wire_off[k]);
+    hi[k].wire_bytes = static_cast<uint32_t>(bytes[k]);
+    const uint32_t inst = pc.first_instance + k;
+    if (ctx->blob_truth[inst])
+      hs[k] = ctx->enc_blob[inst];
+    else
+      ctx->enc[inst].export_state(hs[k]);
+  }
+  uint8_t* hw = nullptr;
+  if (!direct)
+  {
+    CK(P->wire.ensure(wire_bytes), "pinned alloc (wire)");
+    hw = static_cast<uint8_t*>(P->wire.p);
+    parallel_for(cn, ctx->threads, [&](uint32_t k) {
+      if (bytes[k])
+        std::memcpy(hw + wire_off[k], streams[k], bytes[k]);
+    });
+    std::memset(hw + wire_off[cn], 0, 256);
+  }
+  ctx->encode_ms_acc += now_ms() - t0;
+
+  const double t2 = now_ms();
+  if (ctx->group_n >= ctx->chunks.size())
+    ctx->chunks.push_back(new psxgpu_ctx::Chunk());
+  psxgpu_ctx::Chunk& S = *ctx->chunks[ctx->group_n++];
+  pc.S = &S;
+  pc.es = ctx->enc_streams[chunk_index % 4];
+  for (cudaEvent_t* ev : {&S.ev_copied, &S.ev_walked, &S.ev_encoded, &S.ev_done})
+    if (!*ev)
+      CK(cudaEventCreateWithFlags(ev, cudaEventDisableTiming), "event create");
+  if (!S.done_valid) // first device-encoded use of this slot: anything queued on the main stream may still read it
+  {
+    CK(cudaEventRecord(S.ev_done, ctx->stream), "event record");
+    S.done_valid = true;
+  }
+  CK(cudaStreamWaitEvent(ctx->copy_stream, S.ev_done, 0), "stream wait");
+  CK(cudaStreamWaitEvent(pc.es, S.ev_done, 0), "stream wait");
+  CK(S.d_payload.ensure(wire_bytes), "device alloc (wire)");
+  CK(S.d_recoff.ensure(static_cast<size_t>(cn) * sizeof(WalkOut)), "device alloc (framing)");
+  CK(S.d_inst.ensure(static_cast<size_t>(cn) * sizeof(EncInst)), "device alloc (instances)");
+  CK(S.d_state.ensure(static_cast<size_t>(cn) * sizeof(EncState)), "device alloc (encoder state)");
+  if (ctx->trace)
+  {
+    for (cudaEvent_t* ev : {&pc.trace.copy0, &pc.trace.copy1, &pc.trace.enc1, &pc.trace.run0, &pc.trace.run1})
+      cudaEventCreate(ev);
+    if (!ctx->trace_origin)
+    {
+      cudaEventCreate(&ctx->trace_origin);
+      cudaEventRecord(ctx->trace_origin, ctx->stream);
+    }
+    cudaEventRecord(pc.trace.copy0, ctx->copy_stream);
+  }
+  uint8_t* dw = static_cast<uint8_t*>(S.d_payload.p);
+  uint64_t copied = 0;
+  // the small tables go first: nothing small should ever queue behind a 150 MB copy
+  CK(cudaMemcpyAsync(S.d_inst.p, hi, static_cast<size_t>(cn) * sizeof(EncInst), cudaMemcpyHostToDevice, ctx->copy_stream), "H2D instances");
+  CK(cudaMemcpyAsync(S.d_state.p, hs, static_cast<size_t>(cn) * sizeof(EncState), cudaMemcpyHostToDevice, ctx->copy_stream), "H2D encoder state");
+  if (direct)
+  {
+    for (const Run& r : runs)
+    {
+      CK(cudaMemcpyAsync(dw + r.dev_off, r.src, r.bytes, cudaMemcpyHostToDevice, ctx->copy_stream), "H2D wire");
+      copied += r.bytes;
+    }
+    CK(cudaMemsetAsync(dw + wire_off[cn], 0, 256, ctx->copy_stream), "wire slack");
+  }
+  else
+  {
+    CK(cudaMemcpyAsync(dw, hw, wire_bytes, cudaMemcpyHostToDevice, ctx->copy_stream), "H2D wire");
+    copied += wire_bytes;
+  }
+  if (ctx->trace)
+    cudaEventRecord(pc.trace.copy1, ctx->copy_stream);
+  CK(cudaEventRecord(S.ev_copied, ctx->copy_stream), "event record");
+  CK(cudaEventRecord(P->free_ev, ctx->copy_stream), "event record");
+  P->in_flight = true;
+  ctx->counters.h2d_bytes += copied + static_cast<uint64_t>(cn) * (sizeof(EncInst) + sizeof(EncState));
+
+  CK(cudaStreamWaitEvent(pc.es, S.ev_copied, 0), "stream wait");
+  WalkOut* d_wo = static_cast<WalkOut*>(S.d_recoff.p);
+  CK(launch_walk(dw, static_cast<const EncInst*>(S.d_inst.p), d_wo, cn, pc.es), "walk_kernel");
+  ctx->counters.kernel_launches++;
+  CK(cudaMemcpyAsync(P->recoff.p, d_wo, static_cast<size_t>(cn) * sizeof(WalkOut), cudaMemcpyDeviceToHost, pc.es), "D2H framing result");
+  CK(cudaEventRecord(S.ev_walked, pc.es), "event record");
+  ctx->counters.d2h_bytes += static_cast<uint64_t>(cn) * sizeof(WalkOut);
+  ctx->launch_ms_acc += now_ms() - t2;
+  return PSXGPU_OK;
+}
+
+// Stage B: the framing result is back — report errors, size the chunk's buffers exactly, launch encode + wave kernels.
+int stage_encode(psxgpu_ctx* ctx, PendingChunk& pc)
+{
+  psxgpu_ctx::Chunk& S = *pc.S;
+  psxgpu_ctx::PinnedSet* P = pc.P;
+  const uint32_t cn = pc.cn;
+  const double t0 = now_ms();
+  CK(cudaEventSynchronize(S.ev_walked), "framing sync");
+  ctx->wait_ms_acc += now_ms() - t0;
+  const double t1 = now_ms();
+  const WalkOut* wo = static_cast<const WalkOut*>(P->recoff.p);
+  for (uint32_t k = 0; k < cn; k++)
+    if (wo[k].status != 0)
+    {
+      ctx->error = (wo[k].status == PSXGPU_E_MALFORMED) ? "submit_batch: malformed record stream"
+                                                       : "submit_batch: read-back / state records are not allowed in a batch";
+      return wo[k].status == PSXGPU_E_MALFORMED ? PSXGPU_E_MALFORMED : PSXGPU_E_UNSUPPORTED;
+    }
+  uint64_t cmd = 0, clut = 0, epoch = 0;
+  uint32_t wave_cap = 1;
+  for (uint32_t k = 0; k < cn; k++)
+  {
+    const uint32_t ecap = wo[k].cmd_cap + wo[k].clut_cap + 1;
+    cmd += wo[k].cmd_cap;
+    clut += wo[k].clut_cap;
+    epoch += ecap;
+    wave_cap = std::max(wave_cap, ecap);
+  }
+  if (cmd > 0xFFFFFFF0ull || epoch > 0xFFFFFFF0ull)
+    return ctx->invalid("submit_batch: chunk holds more than 2^32 records; use a smaller batch chunk");
+  const size_t waves_off = 256, waves_inline = std::min<size_t>(wave_cap, ENC_WAVES_INLINE);
+  const size_t state_off = waves_off + ENC_WAVES_INLINE * sizeof(EncWave);
+  CK(P->result.ensure(state_off + static_cast<size_t>(cn) * sizeof(EncState)), "pinned alloc (encode result)");
+  CK(S.d_state_out.ensure(static_cast<size_t>(cn) * sizeof(EncState)), "device alloc (encoder state)");
+  CK(S.d_cmds.ensure(cmd * sizeof(PackedCmd) + 64), "device alloc (commands)");
+  CK(S.d_setups.ensure(cmd * sizeof(PrimSetup) + 64), "device alloc (setup records)");
+  CK(S.d_bins.ensure(cmd * sizeof(BinInfo) + 64), "device alloc (bins)");
+  CK(S.d_rects.ensure(cmd * 16 + 64), "device alloc (footprints)");
+  CK(S.d_clutops.ensure(clut * sizeof(ClutOp) + 16), "device alloc (clut ops)");
+  CK(S.d_epochs.ensure(epoch * sizeof(Epoch) + 16), "device alloc (epochs)");
+  CK(S.d_items.ensure(epoch * sizeof(WaveItem) + 16), "device alloc (wave items)");
+  CK(S.d_result.ensure(static_cast<size_t>(cn) * sizeof(EncResult)), "device alloc (encode result)");
+  CK(S.d_waves.ensure(static_cast<size_t>(wave_cap) * sizeof(EncWave)), "device alloc (wave table)");
+  CK(S.d_cursor.ensure(static_cast<size_t>(wave_cap) * 4), "device alloc (wave cursors)");
+  CK(S.d_summary.ensure(sizeof(EncSummary)), "device alloc (summary)");
+  // no host-to-device copy here: it would queue behind the next chunk's wire upload
+  CK(launch_layout(static_cast<const WalkOut*>(S.d_recoff.p), static_cast<EncInst*>(S.d_inst.p), cn, pc.es), "layout_kernel");
+  ctx->counters.kernel_launches++;
+  EncodeArgs a{};
+  a.wire = static_cast<const uint8_t*>(S.d_payload.p);
+  a.inst = static_cast<const EncInst*>(S.d_inst.p);
+  a.n_inst = cn;
+  a.clut_slots = ctx->clut_slots;
+  a.modulation_crop = ctx->opts.modulation_crop ? 1u : 0u;
+  a.state_in = static_cast<const EncState*>(S.d_state.p);
+  a.state_out = static_cast<EncState*>(S.d_state_out.p);
+  a.cmds = static_cast<PackedCmd*>(S.d_cmds.p);
+  a.rects = static_cast<uint4*>(S.d_rects.p);
+  a.clut_ops = static_cast<ClutOp*>(S.d_clutops.p);
+  a.epochs = static_cast<Epoch*>(S.d_epochs.p);
+  a.result = static_cast<EncResult*>(S.d_result.p);
+  a.summary = static_cast<EncSummary*>(S.d_summary.p);
+  a.waves = static_cast<EncWave*>(S.d_waves.p);
+  a.wave_cursor = static_cast<uint32_t*>(S.d_cursor.p);
+  a.wave_cap = wave_cap;
+  a.items = static_cast<WaveItem*>(S.d_items.p);
+  CK(launch_encode(a, pc.es), "encode_kernel");
+  ctx->counters.kernel_launches += 3;
+  S.enc_args = a;
+  S.device_encoded = true;
+  uint8_t* res = static_cast<uint8_t*>(P->result.p);
+  CK(cudaMemcpyAsync(res, S.d_summary.p, sizeof(EncSummary), cudaMemcpyDeviceToHost, pc.es), "D2H summary");
+  CK(cudaMemcpyAsync(res + waves_off, S.d_waves.p, waves_inline * sizeof(EncWave), cudaMemcpyDeviceToHost, pc.es), "D2H wave table");
+  CK(cudaMemcpyAsync(res + state_off, S.d_state_out.p, static_cast<size_t>(cn) * sizeof(EncState), cudaMemcpyDeviceToHost, pc.es),
+     "D2H encoder state");
+  if (ctx->trace)
+    cudaEventRecord(pc.trace.enc1, pc.es);
+  CK(cudaEventRecord(S.ev_encoded, pc.es), "event record");
+  ctx->counters.d2h_bytes += sizeof(EncSummary) + waves_inline * sizeof(EncWave) + static_cast<uint64_t>(cn) * sizeof(EncState);
+  pc.wave_cap = wave_cap;
+  pc.waves_off = waves_off;
+  pc.state_off = state_off;
+  pc.cmd_total = cmd;
+  ctx->launch_ms_acc += now_ms() - t1;
+  return PSXGPU_OK;
+}
+
+// Stage C: the wave table is back — launch setup + waves on the main stream.
 int finalize_device_chunk(psxgpu_ctx* ctx, PendingChunk& pc)
 {
   psxgpu_ctx::Chunk& S = *pc.S;
@@ -767,332 +971,84 @@ int finalize_device_chunk(psxgpu_ctx* ctx, PendingChunk& pc)
   return rc;
 }
 
-// True if [p, p + bytes) starts and ends in page-locked host memory (cudaHostAlloc / cudaHostRegister).
-bool is_pinned_host(const void* p, size_t bytes)
-{
-  if (!p || bytes == 0)
-    return false;
-  cudaPointerAttributes a0{}, a1{};
-  if (cudaPointerGetAttributes(&a0, p) != cudaSuccess || cudaPointerGetAttributes(&a1, static_cast<const uint8_t*>(p) + bytes - 1) != cudaSuccess)
-  {
-    cudaGetLastError();
-    return false;
-  }
-  return a0.type == cudaMemoryTypeHost && a1.type == cudaMemoryTypeHost;
-}
-
+// Three chunks are in flight: while chunk k is being uploaded and framed, chunk k-1 is sized and encoded and chunk k-2's
+// waves are launched — the host never walks a record and only waits for results that have had a whole stage to arrive.
 int submit_batch_device(psxgpu_ctx* ctx, uint32_t first, uint32_t count, const void* const* streams, const size_t* bytes)
 {
   uint32_t per = ctx->batch_chunk;
   if (per == 0)
     per = (count <= 256) ? count : std::max<uint32_t>(128, (count + 7) / 8);
-  // Chunks whose wave table is still on its way back; the table of chunk k is awaited after chunk k+2 has been staged.
-  std::vector<PendingChunk> pending;
-  auto drain = [&](size_t keep) -> int {
-    while (pending.size() > keep)
+  std::vector<PendingChunk> uploaded, encoded; // waiting for stage B / stage C, oldest first
+  int status = PSXGPU_OK;
+  auto finalize_front = [&]() {
+    PendingChunk pc = encoded.front();
+    encoded.erase(encoded.begin());
+    const int rc = finalize_device_chunk(ctx, pc);
+    if (rc != PSXGPU_OK && status == PSXGPU_OK)
+      status = rc;
+  };
+  auto advance = [&](size_t keep_uploaded, size_t keep_encoded) -> int {
+    while (uploaded.size() > keep_uploaded)
     {
-      PendingChunk pc = pending.front();
-      pending.erase(pending.begin());
-      const int rc = finalize_device_chunk(ctx, pc);
-      if (rc != PSXGPU_OK)
-        return rc;
+      PendingChunk pc = uploaded.front();
+      uploaded.erase(uploaded.begin());
+      if (status != PSXGPU_OK)
+        continue;
+      // wait for the framing result — and launch the waves of an older chunk the moment its encode completes, instead
+      // of leaving the main stream idle until this wait is over
+      const double t0 = now_ms();
+      for (;;)
+      {
+        if (!encoded.empty() && cudaEventQuery(encoded.front().S->ev_encoded) == cudaSuccess)
+        {
+          finalize_front();
+          continue;
+        }
+        const cudaError_t q = cudaEventQuery(pc.S->ev_walked);
+        if (q == cudaSuccess)
+          break;
+        if (q != cudaErrorNotReady)
+        {
+          status = ctx->fail(q, "framing sync");
+          break;
+        }
+        std::this_thread::yield();
+      }
+      ctx->wait_ms_acc += now_ms() - t0;
+      if (status != PSXGPU_OK)
+        continue;
+      status = stage_encode(ctx, pc);
+      if (status == PSXGPU_OK)
+        encoded.push_back(pc);
     }
-    return PSXGPU_OK;
+    while (encoded.size() > keep_encoded)
+      finalize_front();
+    return status;
   };
-  std::vector<WalkResult> walk;
-  std::vector<uint64_t> wire_off, rec_host, rec_dev, cmd_base, clut_base, epoch_base;
-  struct Run
-  {
-    const uint8_t* src;
-    uint64_t dev_off, bytes;
-  };
-  std::vector<Run> runs;
   uint32_t chunk_index = 0;
-  for (uint32_t c0 = 0; c0 < count; c0 += per, chunk_index++)
+  for (uint32_t c0 = 0; c0 < count && status == PSXGPU_OK; c0 += per, chunk_index++)
   {
     const uint32_t cn = std::min(per, count - c0);
     int rc = open_group(ctx);
     if (rc != PSXGPU_OK)
       return rc;
-    psxgpu_ctx::PinnedSet* P = nullptr;
-    rc = acquire_pinned(ctx, P);
-    if (rc != PSXGPU_OK)
-      return rc;
-    const double t0 = now_ms();
-    const uint32_t T = std::max(1u, std::min(ctx->threads, cn));
-
-    // Where the streams go in the chunk's device wire buffer.  Streams that already sit in page-locked memory are
-    // copied from where they are (neighbours in one copy); anything else is packed into our pinned staging buffer.
-    bool direct = true;
-    for (uint32_t k = 0; k < cn && direct; k++)
-      direct = bytes[c0 + k] == 0 || ((reinterpret_cast<uintptr_t>(streams[c0 + k]) & 15u) == 0 && is_pinned_host(streams[c0 + k], bytes[c0 + k]));
-    wire_off.assign(cn + 1, 0);
-    runs.clear();
-    if (direct)
-    {
-      uint64_t dev = 0;
-      for (uint32_t k = 0; k < cn; k++)
-      {
-        const uint8_t* src = static_cast<const uint8_t*>(streams[c0 + k]);
-        const uint64_t n = bytes[c0 + k];
-        if (n == 0)
-        {
-          wire_off[k] = dev;
-          continue;
-        }
-        if (!runs.empty() && src >= runs.back().src + runs.back().bytes && src - (runs.back().src + runs.back().bytes) < 64)
-        {
-          wire_off[k] = runs.back().dev_off + static_cast<uint64_t>(src - runs.back().src);
-          runs.back().bytes = static_cast<uint64_t>(src - runs.back().src) + n;
-        }
-        else
-        {
-          dev = runs.empty() ? 0 : ((runs.back().dev_off + runs.back().bytes + 15u) & ~static_cast<uint64_t>(15));
-          wire_off[k] = dev;
-          runs.push_back(Run{src, dev, n});
-        }
-      }
-      wire_off[cn] = runs.empty() ? 0 : ((runs.back().dev_off + runs.back().bytes + 15u) & ~static_cast<uint64_t>(15));
-    }
-    else
-    {
-      for (uint32_t k = 0; k < cn; k++)
-        wire_off[k + 1] = wire_off[k] + ((bytes[c0 + k] + 15u) & ~static_cast<uint64_t>(15));
-    }
-    if (wire_off[cn] > 0xFFFFFF00ull)
-    {
-      rc = drain(0);
-      return rc != PSXGPU_OK ? rc : ctx->invalid("submit_batch: chunk larger than 4 GiB of records; use a smaller batch chunk");
-    }
-    const size_t wire_bytes = static_cast<size_t>(wire_off[cn]) + 256;
-
-    // One pass over the streams on the host threads: framing checks, record offsets (each thread appends to its own
-    // arena; a record is at least 8 bytes long), output capacities and — for pageable sources — the copy into pinned memory.
-    std::vector<uint64_t> arena(T + 1, 0), arena_used(T, 0);
-    for (uint32_t t = 0; t < T; t++)
-    {
-      const uint32_t lo = static_cast<uint32_t>((static_cast<uint64_t>(cn) * t) / T), hi = static_cast<uint32_t>((static_cast<uint64_t>(cn) * (t + 1)) / T);
-      uint64_t cap = 0;
-      for (uint32_t k = lo; k < hi; k++)
-        cap += bytes[c0 + k] / 8 + 2;
-      arena[t + 1] = arena[t] + cap;
-    }
-    CK(P->recoff.ensure(arena[T] * 4 + 16), "pinned alloc (record offsets)");
-    if (!direct)
-      CK(P->wire.ensure(wire_bytes), "pinned alloc (wire)");
-    uint8_t* hw = static_cast<uint8_t*>(P->wire.p);
-    uint32_t* hr = static_cast<uint32_t*>(P->recoff.p);
-    walk.assign(cn, WalkResult());
-    rec_host.assign(cn, 0);
-    parallel_ranges(cn, T, [&](uint32_t t, uint32_t lo, uint32_t hi) {
-      uint64_t at = arena[t];
-      for (uint32_t k = lo; k < hi; k++)
-      {
-        const uint8_t* src = static_cast<const uint8_t*>(streams[c0 + k]);
-        rec_host[k] = at;
-        walk_stream(src, bytes[c0 + k], walk[k], hr + at, static_cast<uint32_t>(wire_off[k]));
-        at += walk[k].n_rec;
-        if (!direct && bytes[c0 + k] && walk[k].status == 0)
-          std::memcpy(hw + wire_off[k], src, bytes[c0 + k]);
-      }
-      arena_used[t] = at - arena[t];
-    });
-    for (uint32_t k = 0; k < cn; k++)
-      if (walk[k].status != 0)
-      {
-        ctx->encode_ms_acc += now_ms() - t0;
-        rc = drain(0);
-        if (rc != PSXGPU_OK)
-          return rc;
-        ctx->error = (walk[k].status == PSXGPU_E_MALFORMED) ? "submit_batch: malformed record stream"
-                                                           : "submit_batch: read-back / state records are not allowed in a batch";
-        return walk[k].status;
-      }
-    // device layout of the record offsets: the arenas' used prefixes, concatenated
-    rec_dev.assign(cn, 0);
-    cmd_base.assign(cn + 1, 0);
-    clut_base.assign(cn + 1, 0);
-    epoch_base.assign(cn + 1, 0);
-    std::vector<uint64_t> arena_dev(T + 1, 0);
-    for (uint32_t t = 0; t < T; t++)
-      arena_dev[t + 1] = arena_dev[t] + arena_used[t];
-    uint32_t wave_cap = 1;
-    for (uint32_t t = 0; t < T; t++)
-    {
-      const uint32_t lo = static_cast<uint32_t>((static_cast<uint64_t>(cn) * t) / T), hi = static_cast<uint32_t>((static_cast<uint64_t>(cn) * (t + 1)) / T);
-      for (uint32_t k = lo; k < hi; k++)
-        rec_dev[k] = arena_dev[t] + (rec_host[k] - arena[t]);
-    }
-    for (uint32_t k = 0; k < cn; k++)
-    {
-      const uint32_t ecap = walk[k].cmd_cap + walk[k].clut_cap + 1;
-      cmd_base[k + 1] = cmd_base[k] + walk[k].cmd_cap;
-      clut_base[k + 1] = clut_base[k] + walk[k].clut_cap;
-      epoch_base[k + 1] = epoch_base[k] + ecap;
-      wave_cap = std::max(wave_cap, ecap);
-    }
-    const uint64_t n_rec_total = arena_dev[T];
-    if (cmd_base[cn] > 0xFFFFFFF0ull || epoch_base[cn] > 0xFFFFFFF0ull || n_rec_total > 0xFFFFFFF0ull)
-    {
-      rc = drain(0);
-      return rc != PSXGPU_OK ? rc : ctx->invalid("submit_batch: chunk holds more than 2^32 records; use a smaller batch chunk");
-    }
-    const size_t waves_off = 256, waves_inline = std::min<size_t>(wave_cap, ENC_WAVES_INLINE);
-    const size_t state_off = waves_off + ENC_WAVES_INLINE * sizeof(EncWave);
-    CK(P->inst.ensure(static_cast<size_t>(cn) * sizeof(EncInst)), "pinned alloc (instances)");
-    CK(P->state.ensure(static_cast<size_t>(cn) * sizeof(EncState)), "pinned alloc (encoder state)");
-    CK(P->result.ensure(state_off + static_cast<size_t>(cn) * sizeof(EncState)), "pinned alloc (encode result)");
-    EncInst* hi = static_cast<EncInst*>(P->inst.p);
-    EncState* hs = static_cast<EncState*>(P->state.p);
-    for (uint32_t k = 0; k < cn; k++)
-    {
-      EncInst& ii = hi[k];
-      std::memset(&ii, 0, sizeof(ii));
-      ii.instance = first + c0 + k;
-      ii.rec_begin = static_cast<uint32_t>(rec_dev[k]);
-      ii.n_records = walk[k].n_rec;
-      ii.cmd_base = static_cast<uint32_t>(cmd_base[k]);
-      ii.cmd_cap = walk[k].cmd_cap;
-      ii.clut_base = static_cast<uint32_t>(clut_base[k]);
-      ii.clut_cap = walk[k].clut_cap;
-      ii.epoch_base = static_cast<uint32_t>(epoch_base[k]);
-      ii.epoch_cap = walk[k].cmd_cap + walk[k].clut_cap + 1;
-      if (ctx->blob_truth[first + c0 + k])
-        hs[k] = ctx->enc_blob[first + c0 + k];
-      else
-        ctx->enc[first + c0 + k].export_state(hs[k]);
-    }
-    ctx->encode_ms_acc += now_ms() - t0;
-
-    const double t2 = now_ms();
-    if (ctx->group_n >= ctx->chunks.size())
-      ctx->chunks.push_back(new psxgpu_ctx::Chunk());
-    psxgpu_ctx::Chunk& S = *ctx->chunks[ctx->group_n++];
-    cudaStream_t es = ctx->enc_streams[chunk_index % 4];
-    for (cudaEvent_t* ev : {&S.ev_copied, &S.ev_encoded, &S.ev_done})
-      if (!*ev)
-        CK(cudaEventCreateWithFlags(ev, cudaEventDisableTiming), "event create");
-    // the chunk's device buffers may still be read by its previous user (the same slot of the previous group, or a replay)
-    if (!S.done_valid) // first device-encoded use of this slot: anything queued on the main stream may still read it
-    {
-      CK(cudaEventRecord(S.ev_done, ctx->stream), "event record");
-      S.done_valid = true;
-    }
-    CK(cudaStreamWaitEvent(ctx->copy_stream, S.ev_done, 0), "stream wait");
-    CK(cudaStreamWaitEvent(es, S.ev_done, 0), "stream wait");
-    CK(S.d_payload.ensure(wire_bytes), "device alloc (wire)");
-    CK(S.d_recoff.ensure(n_rec_total * 4 + 16), "device alloc (record offsets)");
-    CK(S.d_inst.ensure(static_cast<size_t>(cn) * sizeof(EncInst)), "device alloc (instances)");
-    CK(S.d_state.ensure(static_cast<size_t>(cn) * sizeof(EncState)), "device alloc (encoder state)");
-    CK(S.d_state_out.ensure(static_cast<size_t>(cn) * sizeof(EncState)), "device alloc (encoder state)");
-    CK(S.d_cmds.ensure(cmd_base[cn] * sizeof(PackedCmd) + 64), "device alloc (commands)");
-    CK(S.d_setups.ensure(cmd_base[cn] * sizeof(PrimSetup) + 64), "device alloc (setup records)");
-    CK(S.d_bins.ensure(cmd_base[cn] * sizeof(BinInfo) + 64), "device alloc (bins)");
-    CK(S.d_clutops.ensure(clut_base[cn] * sizeof(ClutOp) + 16), "device alloc (clut ops)");
-    CK(S.d_epochs.ensure(epoch_base[cn] * sizeof(Epoch) + 16), "device alloc (epochs)");
-    CK(S.d_items.ensure(epoch_base[cn] * sizeof(WaveItem) + 16), "device alloc (wave items)");
-    CK(S.d_result.ensure(static_cast<size_t>(cn) * sizeof(EncResult)), "device alloc (encode result)");
-    CK(S.d_waves.ensure(static_cast<size_t>(wave_cap) * sizeof(EncWave)), "device alloc (wave table)");
-    CK(S.d_cursor.ensure(static_cast<size_t>(wave_cap) * 4), "device alloc (wave cursors)");
-    CK(S.d_summary.ensure(sizeof(EncSummary)), "device alloc (summary)");
-    CK(S.d_rects.ensure(cmd_base[cn] * 16 + 64), "device alloc (footprints)");
-
-    psxgpu_ctx::TraceChunk tc{};
-    if (ctx->trace)
-    {
-      for (cudaEvent_t* ev : {&tc.copy0, &tc.copy1, &tc.enc1, &tc.run0, &tc.run1})
-        cudaEventCreate(ev);
-      if (!ctx->trace_origin)
-      {
-        cudaEventCreate(&ctx->trace_origin);
-        cudaEventRecord(ctx->trace_origin, ctx->stream);
-      }
-      cudaEventRecord(tc.copy0, ctx->copy_stream);
-    }
-    uint8_t* dw = static_cast<uint8_t*>(S.d_payload.p);
-    uint64_t copied = 0;
-    if (direct)
-    {
-      for (const Run& r : runs)
-      {
-        CK(cudaMemcpyAsync(dw + r.dev_off, r.src, r.bytes, cudaMemcpyHostToDevice, ctx->copy_stream), "H2D wire");
-        copied += r.bytes;
-      }
-      CK(cudaMemsetAsync(dw + wire_off[cn], 0, 256, ctx->copy_stream), "wire slack");
-    }
-    else
-    {
-      std::memset(hw + wire_off[cn], 0, 256);
-      CK(cudaMemcpyAsync(dw, hw, wire_bytes, cudaMemcpyHostToDevice, ctx->copy_stream), "H2D wire");
-      copied += wire_bytes;
-    }
-    for (uint32_t t = 0; t < T; t++)
-      if (arena_used[t])
-        CK(cudaMemcpyAsync(static_cast<uint32_t*>(S.d_recoff.p) + arena_dev[t], hr + arena[t], arena_used[t] * 4, cudaMemcpyHostToDevice,
-                           ctx->copy_stream),
-           "H2D record offsets");
-    CK(cudaMemcpyAsync(S.d_inst.p, hi, static_cast<size_t>(cn) * sizeof(EncInst), cudaMemcpyHostToDevice, ctx->copy_stream), "H2D instances");
-    CK(cudaMemcpyAsync(S.d_state.p, hs, static_cast<size_t>(cn) * sizeof(EncState), cudaMemcpyHostToDevice, ctx->copy_stream),
-       "H2D encoder state");
-    if (ctx->trace)
-      cudaEventRecord(tc.copy1, ctx->copy_stream);
-    CK(cudaEventRecord(S.ev_copied, ctx->copy_stream), "event record");
-    CK(cudaEventRecord(P->free_ev, ctx->copy_stream), "event record");
-    P->in_flight = true;
-    ctx->counters.h2d_bytes += copied + n_rec_total * 4 + static_cast<uint64_t>(cn) * (sizeof(EncInst) + sizeof(EncState));
-
-    CK(cudaStreamWaitEvent(es, S.ev_copied, 0), "stream wait");
-    EncodeArgs a{};
-    a.wire = dw;
-    a.rec_off = static_cast<const uint32_t*>(S.d_recoff.p);
-    a.inst = static_cast<const EncInst*>(S.d_inst.p);
-    a.n_inst = cn;
-    a.clut_slots = ctx->clut_slots;
-    a.modulation_crop = ctx->opts.modulation_crop ? 1u : 0u;
-    a.state_in = static_cast<const EncState*>(S.d_state.p);
-    a.state_out = static_cast<EncState*>(S.d_state_out.p);
-    a.cmds = static_cast<PackedCmd*>(S.d_cmds.p);
-    a.rects = static_cast<uint4*>(S.d_rects.p);
-    a.clut_ops = static_cast<ClutOp*>(S.d_clutops.p);
-    a.epochs = static_cast<Epoch*>(S.d_epochs.p);
-    a.result = static_cast<EncResult*>(S.d_result.p);
-    a.summary = static_cast<EncSummary*>(S.d_summary.p);
-    a.waves = static_cast<EncWave*>(S.d_waves.p);
-    a.wave_cursor = static_cast<uint32_t*>(S.d_cursor.p);
-    a.wave_cap = wave_cap;
-    a.items = static_cast<WaveItem*>(S.d_items.p);
-    CK(launch_encode(a, es), "encode_kernel");
-    ctx->counters.kernel_launches += 3;
-    S.enc_args = a;
-    S.device_encoded = true;
-    uint8_t* res = static_cast<uint8_t*>(P->result.p);
-    CK(cudaMemcpyAsync(res, S.d_summary.p, sizeof(EncSummary), cudaMemcpyDeviceToHost, es), "D2H summary");
-    CK(cudaMemcpyAsync(res + waves_off, S.d_waves.p, waves_inline * sizeof(EncWave), cudaMemcpyDeviceToHost, es), "D2H wave table");
-    CK(cudaMemcpyAsync(res + state_off, S.d_state_out.p, static_cast<size_t>(cn) * sizeof(EncState), cudaMemcpyDeviceToHost, es),
-       "D2H encoder state");
-    if (ctx->trace)
-      cudaEventRecord(tc.enc1, es);
-    CK(cudaEventRecord(S.ev_encoded, es), "event record");
-    ctx->counters.d2h_bytes += sizeof(EncSummary) + waves_inline * sizeof(EncWave) + static_cast<uint64_t>(cn) * sizeof(EncState);
-    ctx->launch_ms_acc += now_ms() - t2;
-
+    // the pinned sets rotate by three: chunk k reuses the set of chunk k-3, whose waves must have been launched
+    advance(1, 1);
+    if (status != PSXGPU_OK)
+      break;
     PendingChunk pc;
-    pc.S = &S;
-    pc.P = P;
-    pc.es = es;
     pc.first_instance = first + c0;
     pc.cn = cn;
-    pc.wave_cap = wave_cap;
-    pc.waves_off = waves_off;
-    pc.state_off = state_off;
-    pc.cmd_total = cmd_base[cn];
-    pc.trace = tc;
-    pending.push_back(pc);
-    rc = drain(2); // pinned sets rotate by three: the set of chunk k-2 is needed again for chunk k+1
+    rc = stage_upload(ctx, pc, chunk_index, streams + c0, bytes + c0);
     if (rc != PSXGPU_OK)
-      return rc;
+    {
+      status = rc;
+      break;
+    }
+    uploaded.push_back(pc);
   }
-  return drain(0);
+  advance(0, 0);
+  return status;
 }
 
 // Flushes every instance that has queued work and closes the group.
@@ -1322,7 +1278,7 @@ void psxgpu_destroy(psxgpu_ctx* ctx)
     for (DevBuf* b : {&ch->d_cmds, &ch->d_setups, &ch->d_bins, &ch->d_payload, &ch->d_clutops, &ch->d_items, &ch->d_misc, &ch->d_recoff,
                       &ch->d_inst, &ch->d_state, &ch->d_state_out, &ch->d_epochs, &ch->d_result, &ch->d_waves, &ch->d_cursor, &ch->d_summary, &ch->d_rects})
       b->release();
-    for (cudaEvent_t ev : {ch->ev_copied, ch->ev_encoded, ch->ev_done})
+    for (cudaEvent_t ev : {ch->ev_copied, ch->ev_walked, ch->ev_encoded, ch->ev_done})
       if (ev)
         cudaEventDestroy(ev);
     for (cudaEvent_t ev : ch->ev_raster)

@@ -29,14 +29,22 @@ static_assert(sizeof(EncState) == 1040, "EncState");
 struct alignas(16) EncInst
 {
   uint32_t instance;  // VRAM instance
-  uint32_t rec_begin; // first entry of rec_off[]
-  uint32_t n_records;
+  uint32_t wire_off;  // byte offset of the stream in the chunk's wire buffer (16-byte aligned)
+  uint32_t wire_bytes;
   uint32_t cmd_base, cmd_cap;
   uint32_t clut_base, clut_cap;
   uint32_t epoch_base, epoch_cap;
   uint32_t pad[3];
 };
 static_assert(sizeof(EncInst) == 48, "EncInst");
+
+// Record framing, checked on the device right after the upload (walk_kernel): what Encoder::add_wire checks, plus the
+// exact output capacities the stream needs.  The host sizes the chunk's buffers from these.
+struct WalkOut
+{
+  uint32_t n_rec, cmd_cap, clut_cap;
+  int32_t status; // 0, PSXGPU_E_MALFORMED (-3) or PSXGPU_E_UNSUPPORTED (-5: a barrier record)
+};
 
 struct EncResult
 {
@@ -80,8 +88,7 @@ constexpr uint32_t ENC_WAVES_INLINE = 2048;
 
 struct EncodeArgs
 {
-  const uint8_t* wire;     // chunk wire buffer (instances back to back, 16-byte aligned, 256 bytes of slack at the end)
-  const uint32_t* rec_off; // byte offset of every record in `wire`
+  const uint8_t* wire; // chunk wire buffer (instances back to back, 16-byte aligned, 256 bytes of slack at the end)
   const EncInst* inst;
   uint32_t n_inst;
   uint32_t clut_slots;
@@ -100,6 +107,10 @@ struct EncodeArgs
   WaveItem* items;
 };
 
+// walk: reads inst[].wire_off / wire_bytes.  layout: exclusive prefix sums of the capacities into inst[].*_base / *_cap
+// (the same sums the host makes from the read-back WalkOut to size the buffers).
+cudaError_t launch_walk(const uint8_t* wire, const EncInst* inst, WalkOut* out, uint32_t n_inst, cudaStream_t st);
+cudaError_t launch_layout(const WalkOut* walk, EncInst* inst, uint32_t n_inst, cudaStream_t st);
 cudaError_t launch_encode(const EncodeArgs& a, cudaStream_t st);
 
 } // namespace psx

@@ -18,6 +18,44 @@ namespace {
 constexpr uint32_t ENC_WARPS = 4;
 constexpr uint32_t FULL = 0xFFFFFFFFu;
 
+// Following the record sizes is a chain of dependent loads, and on this part a global load that misses L1 costs
+// 600+ cycles even when it hits L2.  So the stream is staged through shared memory 4 KB at a time — one coalesced
+// round trip per window (128 bytes per lane) — and the chain runs on shared-memory latency instead.
+constexpr uint32_t WIN_BYTES = 4096;
+
+struct StreamWindow
+{
+  const uint8_t* wire;
+  uint32_t* smem;    // [WIN_BYTES / 4], this warp's
+  uint32_t base;     // byte offset of smem[0] in the wire buffer (128-byte aligned); base == end => empty
+  uint32_t limit;    // bytes of the wire buffer this warp may touch (stream end + slack)
+  uint32_t lane;
+
+  __device__ __forceinline__ void fill(uint32_t pos)
+  {
+    __syncwarp();
+    base = pos & ~127u;
+    const uint32_t at = base + lane * 128u;
+    const uint4* src = reinterpret_cast<const uint4*>(wire + at);
+    uint4* dst = reinterpret_cast<uint4*>(smem + lane * 32u);
+    if (at < limit)
+    {
+#pragma unroll
+      for (int i = 0; i < 8; i++)
+        dst[i] = __ldg(src + i);
+    }
+    __syncwarp();
+  }
+  // the 32-bit word at byte offset `pos` (4-byte aligned), refilling the window when pos lies outside it
+  __device__ __forceinline__ uint32_t word(uint32_t pos)
+  {
+    if (pos < base || pos + 4u > base + WIN_BYTES)
+      fill(pos);
+    return smem[(pos - base) >> 2];
+  }
+  __device__ __forceinline__ bool holds(uint32_t pos, uint32_t bytes) const { return pos >= base && pos + bytes <= base + WIN_BYTES; }
+};
+
 struct Rects // up to four wrapped pieces of one VRAM rectangle (RectSet in encoder.h); uniform across the warp
 {
   uint32_t n;
@@ -625,6 +663,7 @@ __global__ void __launch_bounds__(32 * ENC_WARPS) encode_kernel(EncodeArgs A)
   __shared__ uint32_t sh_last[ENC_WARPS][256];
   __shared__ unsigned long long sh_col[ENC_WARPS][32];
   __shared__ unsigned long long sh_col2[ENC_WARPS][32];
+  __shared__ __align__(16) uint32_t sh_win[ENC_WARPS][WIN_BYTES / 4];
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
   const uint32_t idx = blockIdx.x * ENC_WARPS + warp;
   if (idx >= A.n_inst)
@@ -669,7 +708,6 @@ __global__ void __launch_bounds__(32 * ENC_WARPS) encode_kernel(EncodeArgs A)
   E.rebuild_clut_sources();
 
   const uint32_t* wire32 = reinterpret_cast<const uint32_t*>(A.wire);
-  const uint32_t n_rec = ii.n_records;
   // Records that the lane-parallel parser below does not take (precise records, poly-lines, transfers, rectangles
   // that wrap, unaligned records) go through this warp-uniform path: one coalesced 128-byte load of the record,
   // fields handed round with shuffles.
@@ -1050,25 +1088,66 @@ __global__ void __launch_bounds__(32 * ENC_WARPS) encode_kernel(EncodeArgs A)
     FP_SELF = 4,
     FP_REJECTED = 8
   };
-  uint32_t base = 0;
-  while (base < n_rec)
+  // The framing was checked by walk_kernel; here the warp just follows the sizes (uniform loads, mostly L1 hits: the
+  // records are contiguous) to find where the next 32 records start.
+  uint32_t pos = ii.wire_off, n_seen = 0;
+  const uint32_t wire_end = ii.wire_off + ii.wire_bytes;
+  StreamWindow win;
+  win.wire = A.wire;
+  win.smem = sh_win[warp];
+  win.limit = wire_end + 128u; // the chunk's wire buffer has 256 bytes of slack behind its last stream
+  win.lane = lane;
+  win.base = 0xFFFFFF00u;
+  while (pos < wire_end)
   {
-    uint32_t nb = min(32u, n_rec - base);
+    uint32_t nb = 0, my_off = 0, my_size = 0, scan = pos;
+    for (uint32_t i = 0; i < 32; i++)
+    {
+      if (scan >= wire_end)
+        break;
+      const uint32_t sz = win.word(scan);
+      if (lane == i)
+      {
+        my_off = scan;
+        my_size = sz;
+      }
+      nb = i + 1;
+      scan += max(sz, 8u) & ~3u; // (cannot loop forever on a buffer that changed under us)
+      if (scan > win.base + WIN_BYTES && i >= 7)
+        break; // the next record starts outside the staged window: parse what we have first
+    }
     const bool have = lane < nb;
-    const uint32_t my_off = have ? A.rec_off[ii.rec_begin + base + lane] : 0u;
     uint32_t rw[24];
     {
-      const uint4* q = reinterpret_cast<const uint4*>(A.wire + (my_off & ~15u));
-#pragma unroll
-      for (int i = 0; i < 6; i++)
+      const uint32_t at = my_off & ~15u;
+      if (have && win.holds(at, 96u))
       {
-        const uint4 v = have ? __ldg(q + i) : make_uint4(0, 0, 0, 0);
-        rw[4 * i + 0] = v.x;
-        rw[4 * i + 1] = v.y;
-        rw[4 * i + 2] = v.z;
-        rw[4 * i + 3] = v.w;
+        const uint4* q = reinterpret_cast<const uint4*>(win.smem + ((at - win.base) >> 2));
+#pragma unroll
+        for (int i = 0; i < 6; i++)
+        {
+          const uint4 v = q[i];
+          rw[4 * i + 0] = v.x;
+          rw[4 * i + 1] = v.y;
+          rw[4 * i + 2] = v.z;
+          rw[4 * i + 3] = v.w;
+        }
+      }
+      else
+      {
+        const uint4* q = reinterpret_cast<const uint4*>(A.wire + at);
+#pragma unroll
+        for (int i = 0; i < 6; i++)
+        {
+          const uint4 v = have ? __ldg(q + i) : make_uint4(0, 0, 0, 0);
+          rw[4 * i + 0] = v.x;
+          rw[4 * i + 1] = v.y;
+          rw[4 * i + 2] = v.z;
+          rw[4 * i + 3] = v.w;
+        }
       }
     }
+    const uint32_t rw_size = my_size;
     uint32_t cls = CLS_IGNORE, nprim = 0, hw0 = 0, hdm = 0, hwin = 0;
     uint32_t pv[2][8], pwr0[2], pwr1[2], prd0[2], prd1[2], pf[2];
 #pragma unroll
@@ -1345,6 +1424,12 @@ __global__ void __launch_bounds__(32 * ENC_WARPS) encode_kernel(EncodeArgs A)
     const uint32_t area_mask = __ballot_sync(FULL, cls == CLS_AREA);
     if (area_mask)
       nb = static_cast<uint32_t>(__ffs(static_cast<int>(area_mask)));
+    // where the next batch starts: behind record nb-1
+    {
+      const uint32_t last_off = __shfl_sync(FULL, my_off, nb - 1), last_size = __shfl_sync(FULL, rw_size, nb - 1);
+      pos = last_off + (max(last_size, 8u) & ~3u);
+      n_seen += nb;
+    }
     const uint32_t summary = cls | (nprim << 4) | (pf[0] << 8) | (pf[1] << 16);
 
     // ---- Batch-parallel commit.  If bounding boxes alone prove that nothing in the batch can conflict — not with the
@@ -1513,7 +1598,6 @@ __global__ void __launch_bounds__(32 * ENC_WARPS) encode_kernel(EncodeArgs A)
           E.area[2] = __shfl_sync(FULL, pv[0][2], r);
           E.area[3] = __shfl_sync(FULL, pv[0][3], r);
         }
-        base += nb;
         continue;
       }
     }
@@ -1598,7 +1682,6 @@ __global__ void __launch_bounds__(32 * ENC_WARPS) encode_kernel(EncodeArgs A)
         generic_record(__shfl_sync(FULL, my_off, r));
       }
     }
-    base += nb;
   }
   if (E.n_cmds > E.epoch_cmd_begin || E.n_clut > E.epoch_clut_begin)
     E.close_epoch(EPOCH_TILED);
@@ -1631,7 +1714,7 @@ __global__ void __launch_bounds__(32 * ENC_WARPS) encode_kernel(EncodeArgs A)
     if (E.overflow)
       atomicOr(&A.summary->overflow, 1u);
     unsigned long long* S = A.summary->stats;
-    atomicAdd(&S[ENC_STAT_WIRE], static_cast<unsigned long long>(ii.n_records));
+    atomicAdd(&S[ENC_STAT_WIRE], static_cast<unsigned long long>(n_seen));
     atomicAdd(&S[ENC_STAT_PRIMS], static_cast<unsigned long long>(E.st_prims));
     atomicAdd(&S[ENC_STAT_EPOCHS], static_cast<unsigned long long>(E.n_epochs));
     atomicAdd(&S[ENC_STAT_CUTS_RAW], static_cast<unsigned long long>(E.st_raw));
@@ -1656,6 +1739,130 @@ __global__ void __launch_bounds__(32 * ENC_WARPS) encode_kernel(EncodeArgs A)
       f |= (e.kind == EPOCH_TILED) ? 2u : 4u;
     atomicAdd(&A.waves[k].item_count, 1u);
     atomicOr(&A.waves[k].flags, f);
+  }
+}
+
+// Record framing of one stream per warp (uniform control flow): sizes add up, no barrier records; counts what the
+// encoder can produce.
+__global__ void __launch_bounds__(128) walk_kernel(const uint8_t* __restrict__ wire, const EncInst* __restrict__ in, WalkOut* __restrict__ out,
+                                                   uint32_t n_inst)
+{
+  __shared__ __align__(16) uint32_t sh_win[4][WIN_BYTES / 4];
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+  const uint32_t idx = blockIdx.x * 4 + warp;
+  if (idx >= n_inst)
+    return;
+  const EncInst wi = in[idx];
+  WalkOut r;
+  r.n_rec = r.cmd_cap = r.clut_cap = 0;
+  r.status = 0;
+  uint32_t pos = wi.wire_off;
+  const uint32_t end = wi.wire_off + wi.wire_bytes;
+  StreamWindow win;
+  win.wire = wire;
+  win.smem = sh_win[warp];
+  win.limit = end + 128u;
+  win.lane = lane;
+  win.base = 0xFFFFFF00u;
+  while (pos < end)
+  {
+    if (end - pos < 8u)
+    {
+      r.status = -3;
+      break;
+    }
+    const uint32_t size = win.word(pos), type = win.word(pos + 4) & 0xFFu;
+    if (size < 8u || (size & 3u) != 0 || size > end - pos)
+    {
+      r.status = -3;
+      break;
+    }
+    if (type == PSX_CMD_CLEAR_VRAM || type == PSX_CMD_LOAD_STATE || type == PSX_CMD_READ_VRAM || type == PSX_CMD_UPDATE_DISPLAY)
+    {
+      r.status = -5;
+      break;
+    }
+    switch (type)
+    {
+      case PSX_CMD_DRAW_POLYGON:
+      case PSX_CMD_DRAW_PRECISE_POLYGON:
+        if (size >= 20u)
+          r.cmd_cap += ((win.word(pos + 8) >> 16) > 3u) ? 2u : 1u;
+        break;
+      case PSX_CMD_DRAW_LINE:
+      case PSX_CMD_DRAW_PRECISE_LINE:
+        if (size >= 20u)
+          r.cmd_cap += (win.word(pos + 8) >> 16) / 2u;
+        break;
+      case PSX_CMD_DRAW_RECTANGLE:
+      case PSX_CMD_FILL_VRAM:
+      case PSX_CMD_COPY_VRAM:
+      case PSX_CMD_UPDATE_VRAM: r.cmd_cap += 1; break;
+      case PSX_CMD_UPDATE_CLUT: r.clut_cap += 1; break;
+      default: break;
+    }
+    r.n_rec++;
+    pos += size;
+  }
+  if (lane == 0)
+    out[idx] = r;
+}
+
+// Block-wide exclusive scan of one value per thread (1024 threads); returns the block total through `total`.
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* warp_sums, uint32_t& total)
+{
+  uint32_t incl = v;
+#pragma unroll
+  for (uint32_t d = 1; d < 32; d <<= 1)
+  {
+    const uint32_t t = __shfl_up_sync(FULL, incl, d);
+    if ((threadIdx.x & 31u) >= d)
+      incl += t;
+  }
+  __syncthreads();
+  if ((threadIdx.x & 31u) == 31u)
+    warp_sums[threadIdx.x >> 5] = incl;
+  __syncthreads();
+  if (threadIdx.x < 32)
+  {
+    uint32_t s = warp_sums[threadIdx.x];
+#pragma unroll
+    for (uint32_t d = 1; d < 32; d <<= 1)
+    {
+      const uint32_t t = __shfl_up_sync(FULL, s, d);
+      if (threadIdx.x >= d)
+        s += t;
+    }
+    warp_sums[threadIdx.x] = s;
+  }
+  __syncthreads();
+  total = warp_sums[31];
+  return ((threadIdx.x >> 5) ? warp_sums[(threadIdx.x >> 5) - 1] : 0u) + (incl - v);
+}
+
+// Output layout of a chunk from the framing counts: instance k gets cmd / CLUT-op / epoch slots behind instance k-1's.
+__global__ void __launch_bounds__(1024) layout_kernel(const WalkOut* __restrict__ walk, EncInst* __restrict__ inst, uint32_t n_inst)
+{
+  __shared__ uint32_t sums[32];
+  uint32_t cmd_carry = 0, clut_carry = 0;
+  for (uint32_t base = 0; base < n_inst; base += 1024)
+  {
+    const uint32_t k = base + threadIdx.x;
+    const uint32_t c = (k < n_inst) ? walk[k].cmd_cap : 0u, u = (k < n_inst) ? walk[k].clut_cap : 0u;
+    uint32_t ctot, utot;
+    const uint32_t cpre = block_exclusive_scan(c, sums, ctot);
+    const uint32_t upre = block_exclusive_scan(u, sums, utot);
+    if (k < n_inst)
+    {
+      inst[k].cmd_base = cmd_carry + cpre;
+      inst[k].cmd_cap = c;
+      inst[k].clut_base = clut_carry + upre;
+      inst[k].clut_cap = u;
+      inst[k].epoch_base = cmd_carry + cpre + clut_carry + upre + k; // capacity c + u + 1 each
+      inst[k].epoch_cap = c + u + 1;
+    }
+    cmd_carry += ctot;
+    clut_carry += utot;
   }
 }
 
@@ -1730,6 +1937,22 @@ __global__ void __launch_bounds__(128) wave_fill_kernel(EncodeArgs A)
 }
 
 } // namespace
+
+cudaError_t launch_walk(const uint8_t* wire, const EncInst* inst, WalkOut* out, uint32_t n_inst, cudaStream_t st)
+{
+  if (n_inst == 0)
+    return cudaSuccess;
+  walk_kernel<<<(n_inst + 3) / 4, 128, 0, st>>>(wire, inst, out, n_inst);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_layout(const WalkOut* walk, EncInst* inst, uint32_t n_inst, cudaStream_t st)
+{
+  if (n_inst == 0)
+    return cudaSuccess;
+  layout_kernel<<<1, 1024, 0, st>>>(walk, inst, n_inst);
+  return cudaGetLastError();
+}
 
 cudaError_t launch_encode(const EncodeArgs& a, cudaStream_t st)
 {
