@@ -293,6 +293,7 @@ struct WarpEncoder
   uint32_t* last; // shared, [256]: serial of the last epoch that references the slot's contents
   unsigned long long* colscratch; // shared, [32]
   unsigned long long* colscratch2; // shared, [32]
+  uint8_t* quick; // shared, [64]: position hash -> slot it was last found in (validated against key[])
   // Footprints of the open epoch's commands, one uint4 per command slot: {wr0, wr1, rd0, rd1} packed x | y << 16
   // (0xFFFFFFFF = none).  `writes` / `reads` keep their bounding boxes exact at all times, but their cell grids cover
   // only commands below grid_upto; the rest is folded in from here the first time a box test is inconclusive.
@@ -423,9 +424,19 @@ struct WarpEncoder
       rebuild_clut_sources();
   }
 
+  static __device__ __forceinline__ uint32_t quick_index(uint32_t want) { return ((want >> 4) ^ (want >> 10) ^ (want >> 15)) & 63u; }
+
   __device__ __forceinline__ uint32_t find_slot(uint32_t x, uint32_t y, bool is8) const
   {
     const uint32_t want = x | (y << 10);
+    // Palettes repeat (946 of the 958 CLUT updates of a BASELINE config-4 stream hit the cache): a 64-entry table of
+    // "slot this position was last found in" answers those with two shared-memory loads instead of a table search.
+    const uint32_t qi = quick_index(want);
+    {
+      const uint32_t s = quick[qi], k = key[s];
+      if ((k & ENC_SLOT_VALID) && (k & 0x7FFFFu) == want && (((k >> 19) & 1u) || !is8))
+        return s;
+    }
     uint32_t best = 0xFFFFFFFFu;
     for (uint32_t s = lane; s < slots; s += 32)
     {
@@ -434,7 +445,15 @@ struct WarpEncoder
       if ((k & ENC_SLOT_VALID) && (k & 0x7FFFFu) == want && (((k >> 19) & 1u) || !is8))
         best = min(best, s);
     }
-    return __reduce_min_sync(FULL, best);
+    best = __reduce_min_sync(FULL, best);
+    if (best != 0xFFFFFFFFu)
+    {
+      __syncwarp();
+      if (lane == 0)
+        quick[qi] = static_cast<uint8_t>(best);
+      __syncwarp();
+    }
+    return best;
   }
 
   __device__ __forceinline__ uint32_t alloc_slot()
@@ -490,7 +509,10 @@ struct WarpEncoder
       slot = alloc_slot();
       __syncwarp();
       if (lane == 0)
+      {
         key[slot] = x | (y << 10) | (is8 ? (1u << 19) : 0u) | ENC_SLOT_VALID;
+        quick[quick_index(x | (y << 10))] = static_cast<uint8_t>(slot);
+      }
       __syncwarp();
       hz_add(clut_src, src, lane);
       if (n_clut < clut_cap)
@@ -664,6 +686,7 @@ __global__ void __launch_bounds__(32 * ENC_WARPS) encode_kernel(EncodeArgs A)
   __shared__ unsigned long long sh_col[ENC_WARPS][32];
   __shared__ unsigned long long sh_col2[ENC_WARPS][32];
   __shared__ __align__(16) uint32_t sh_win[ENC_WARPS][WIN_BYTES / 4];
+  __shared__ uint8_t sh_quick[ENC_WARPS][64];
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
   const uint32_t idx = blockIdx.x * ENC_WARPS + warp;
   if (idx >= A.n_inst)
@@ -693,6 +716,9 @@ __global__ void __launch_bounds__(32 * ENC_WARPS) encode_kernel(EncodeArgs A)
   E.last = sh_last[warp];
   E.colscratch = sh_col[warp];
   E.colscratch2 = sh_col2[warp];
+  E.quick = sh_quick[warp];
+  E.quick[lane] = 0;
+  E.quick[lane + 32] = 0;
   E.rects = A.rects + ii.cmd_base;
   E.grid_upto = 0;
   E.st_prims = E.st_raw = E.st_war = E.st_clutcut = E.st_self = E.st_copy = E.st_upload = E.st_clutops = E.st_hits = E.st_rejected = 0;
@@ -1771,7 +1797,20 @@ __global__ void __launch_bounds__(128) walk_kernel(const uint8_t* __restrict__ w
       r.status = -3;
       break;
     }
-    const uint32_t size = win.word(pos), type = win.word(pos + 4) & 0xFFu;
+    uint32_t size, type, w2;
+    if ((pos & 15u) == 0 && win.holds(pos, 16u))
+    {
+      const uint4 h = *reinterpret_cast<const uint4*>(win.smem + ((pos - win.base) >> 2)); // the usual case: one load
+      size = h.x;
+      type = h.y & 0xFFu;
+      w2 = h.z;
+    }
+    else
+    {
+      size = win.word(pos);
+      type = win.word(pos + 4) & 0xFFu;
+      w2 = (end - pos >= 12u) ? win.word(pos + 8) : 0u;
+    }
     if (size < 8u || (size & 3u) != 0 || size > end - pos)
     {
       r.status = -3;
@@ -1787,12 +1826,12 @@ __global__ void __launch_bounds__(128) walk_kernel(const uint8_t* __restrict__ w
       case PSX_CMD_DRAW_POLYGON:
       case PSX_CMD_DRAW_PRECISE_POLYGON:
         if (size >= 20u)
-          r.cmd_cap += ((win.word(pos + 8) >> 16) > 3u) ? 2u : 1u;
+          r.cmd_cap += ((w2 >> 16) > 3u) ? 2u : 1u;
         break;
       case PSX_CMD_DRAW_LINE:
       case PSX_CMD_DRAW_PRECISE_LINE:
         if (size >= 20u)
-          r.cmd_cap += (win.word(pos + 8) >> 16) / 2u;
+          r.cmd_cap += (w2 >> 16) / 2u;
         break;
       case PSX_CMD_DRAW_RECTANGLE:
       case PSX_CMD_FILL_VRAM:
