@@ -1026,9 +1026,15 @@ int submit_batch_device(psxgpu_ctx* ctx, uint32_t first, uint32_t count, const v
     return status;
   };
   uint32_t chunk_index = 0;
-  for (uint32_t c0 = 0; c0 < count && status == PSXGPU_OK; c0 += per, chunk_index++)
+  const bool ramp = ctx->batch_chunk == 0 && count > 256; // automatic chunking: small first chunks fill the pipeline sooner
+  for (uint32_t c0 = 0, cn = 0; c0 < count && status == PSXGPU_OK; c0 += cn, chunk_index++)
   {
-    const uint32_t cn = std::min(per, count - c0);
+    uint32_t want = per;
+    if (ramp && chunk_index == 0)
+      want = std::max<uint32_t>(64, per / 4);
+    else if (ramp && chunk_index == 1)
+      want = std::max<uint32_t>(64, per / 2);
+    cn = std::min(want, count - c0);
     int rc = open_group(ctx);
     if (rc != PSXGPU_OK)
       return rc;
