@@ -739,15 +739,30 @@ __device__ __forceinline__ void process_epoch_region(const WaveItem& it, RasterS
     __syncwarp();
 
     // ---- raster: walk the bin in order ----
-    if (!loaded)
-    {
-#pragma unroll 8
-      for (uint32_t r = 0; r < RH; r++)
-        sh.region[r * REGION_PITCH + lane] = kCoh ? __ldcg(gword + r * (VRAM_W / 2)) : gword[r * (VRAM_W / 2)];
-      loaded = true;
-    }
     const uint32_t* src = reinterpret_cast<const uint32_t*>(setups + it.cmd_begin + sh.list[0]);
     uint32_t w0 = __ldg(src + lane), w1 = (lane < SETUP_WORDS - 32) ? __ldg(src + 32 + lane) : 0u;
+    if (!loaded)
+    {
+      // A FillVRAM (not interlaced) or an unmasked upload that covers the whole region overwrites every pixel of it:
+      // the region's old contents need not be read (a frame clear would otherwise read all of VRAM first).
+      const uint32_t hw = __shfl_sync(0xFFFFFFFFu, w0, 0);
+      const uint32_t op = hw & 0xFFu;
+      bool overwritten = false;
+      if (op == OP_FILL || (op == OP_UPLOAD && !((hw >> 8) & F_CHECK_MASK)))
+      {
+        const uint32_t xy = __shfl_sync(0xFFFFFFFFu, w0, 8), wh = __shfl_sync(0xFFFFFFFFu, w0, 9), misc = __shfl_sync(0xFFFFFFFFu, w0, 10);
+        const bool interlaced = (op == OP_FILL) && ((misc >> 16) & 0xFFu);
+        overwritten = !interlaced && (((rx0 - (xy & 0xFFFFu)) & (VRAM_W - 1)) + TILE_W <= (wh & 0xFFFFu)) &&
+                      (((ry0 - (xy >> 16)) & (VRAM_H - 1)) + RH <= (wh >> 16));
+      }
+      if (!overwritten)
+      {
+#pragma unroll 8
+        for (uint32_t r = 0; r < RH; r++)
+          sh.region[r * REGION_PITCH + lane] = kCoh ? __ldcg(gword + r * (VRAM_W / 2)) : gword[r * (VRAM_W / 2)];
+      }
+      loaded = true;
+    }
     for (uint32_t e = 0; e < list_n; e++)
     {
       sh.stage[lane] = w0;
