@@ -144,6 +144,7 @@ struct psxgpu_ctx
   // batched path with device-side encoding: raw streams are uploaded on copy_stream, encoded on enc_stream, and the
   // main stream picks the chunk up once its wave table is known
   cudaStream_t copy_stream = nullptr, enc_streams[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaStream_t walk_stream = nullptr; // framing kernels: tiny, high priority (their result gates the host)
   // PSXGPU_TRACE=1: per-chunk device timeline of the batched path (copy, encode, waves), printed by psxgpu_sync
   bool trace = false;
   struct TraceChunk
@@ -204,8 +205,9 @@ struct psxgpu_ctx
     cudaEvent_t free_ev = nullptr;
     bool in_flight = false;
   };
-  PinnedSet pinned[3];
-  uint32_t pin_next = 0;
+  // sets 0-2: host-encoded flushes (triple buffered); sets 3-8: device-encoded chunks, up to six in flight
+  PinnedSet pinned[9];
+  uint32_t pin_next = 0, pin_next_dev = 0;
 
   std::unordered_map<uint32_t, std::vector<uint16_t>> shadow;
   std::vector<uint8_t> display;
@@ -395,10 +397,15 @@ int close_group(psxgpu_ctx* ctx)
   return PSXGPU_OK;
 }
 
-int acquire_pinned(psxgpu_ctx* ctx, psxgpu_ctx::PinnedSet*& out)
+int acquire_pinned(psxgpu_ctx* ctx, psxgpu_ctx::PinnedSet*& out, bool device_path = false)
 {
-  psxgpu_ctx::PinnedSet& P = ctx->pinned[ctx->pin_next];
-  ctx->pin_next = (ctx->pin_next + 1) % 3;
+  psxgpu_ctx::PinnedSet& P = device_path ? ctx->pinned[3 + ctx->pin_next_dev] : ctx->pinned[ctx->pin_next];
+  if (device_path)
+    ctx->pin_next_dev = (ctx->pin_next_dev + 1) % 6;
+  else
+    ctx->pin_next = (ctx->pin_next + 1) % 3;
+  if (!P.free_ev)
+    CK(cudaEventCreate(&P.free_ev), "event create");
   if (P.in_flight)
   {
     const double t0 = now_ms();
@@ -662,7 +669,7 @@ int stage_upload(psxgpu_ctx* ctx, PendingChunk& pc, uint32_t chunk_index, const 
 {
   const uint32_t cn = pc.cn;
   psxgpu_ctx::PinnedSet* P = nullptr;
-  int rc = acquire_pinned(ctx, P);
+  int rc = acquire_pinned(ctx, P, true);
   if (rc != PSXGPU_OK)
     return rc;
   pc.P = P;
@@ -761,7 +768,6 @@ int stage_upload(psxgpu_ctx* ctx, PendingChunk& pc, uint32_t chunk_index, const 
     S.done_valid = true;
   }
   CK(cudaStreamWaitEvent(ctx->copy_stream, S.ev_done, 0), "stream wait");
-  CK(cudaStreamWaitEvent(pc.es, S.ev_done, 0), "stream wait");
   CK(S.d_payload.ensure(wire_bytes), "device alloc (wire)");
   CK(S.d_recoff.ensure(static_cast<size_t>(cn) * sizeof(WalkOut)), "device alloc (framing)");
   CK(S.d_inst.ensure(static_cast<size_t>(cn) * sizeof(EncInst)), "device alloc (instances)");
@@ -803,12 +809,12 @@ int stage_upload(psxgpu_ctx* ctx, PendingChunk& pc, uint32_t chunk_index, const 
   P->in_flight = true;
   ctx->counters.h2d_bytes += copied + static_cast<uint64_t>(cn) * (sizeof(EncInst) + sizeof(EncState));
 
-  CK(cudaStreamWaitEvent(pc.es, S.ev_copied, 0), "stream wait");
+  CK(cudaStreamWaitEvent(ctx->walk_stream, S.ev_copied, 0), "stream wait");
   WalkOut* d_wo = static_cast<WalkOut*>(S.d_recoff.p);
-  CK(launch_walk(dw, static_cast<const EncInst*>(S.d_inst.p), d_wo, cn, pc.es), "walk_kernel");
+  CK(launch_walk(dw, static_cast<const EncInst*>(S.d_inst.p), d_wo, cn, ctx->walk_stream), "walk_kernel");
   ctx->counters.kernel_launches++;
-  CK(cudaMemcpyAsync(P->recoff.p, d_wo, static_cast<size_t>(cn) * sizeof(WalkOut), cudaMemcpyDeviceToHost, pc.es), "D2H framing result");
-  CK(cudaEventRecord(S.ev_walked, pc.es), "event record");
+  CK(cudaMemcpyAsync(P->recoff.p, d_wo, static_cast<size_t>(cn) * sizeof(WalkOut), cudaMemcpyDeviceToHost, ctx->walk_stream), "D2H framing result");
+  CK(cudaEventRecord(S.ev_walked, ctx->walk_stream), "event record");
   ctx->counters.d2h_bytes += static_cast<uint64_t>(cn) * sizeof(WalkOut);
   ctx->launch_ms_acc += now_ms() - t2;
   return PSXGPU_OK;
@@ -860,6 +866,7 @@ int stage_encode(psxgpu_ctx* ctx, PendingChunk& pc)
   CK(S.d_cursor.ensure(static_cast<size_t>(wave_cap) * 4), "device alloc (wave cursors)");
   CK(S.d_summary.ensure(sizeof(EncSummary)), "device alloc (summary)");
   // no host-to-device copy here: it would queue behind the next chunk's wire upload
+  CK(cudaStreamWaitEvent(pc.es, S.ev_walked, 0), "stream wait");
   CK(launch_layout(static_cast<const WalkOut*>(S.d_recoff.p), static_cast<EncInst*>(S.d_inst.p), cn, pc.es), "layout_kernel");
   ctx->counters.kernel_launches++;
   EncodeArgs a{};
@@ -971,8 +978,9 @@ int finalize_device_chunk(psxgpu_ctx* ctx, PendingChunk& pc)
   return rc;
 }
 
-// Three chunks are in flight: while chunk k is being uploaded and framed, chunk k-1 is sized and encoded and chunk k-2's
-// waves are launched — the host never walks a record and only waits for results that have had a whole stage to arrive.
+// Up to six chunks are in flight: while chunk k is being uploaded and framed, older chunks are sized and encoded and
+// still older ones have their waves launched — the host never walks a record, and it polls for whichever result
+// arrives first.
 int submit_batch_device(psxgpu_ctx* ctx, uint32_t first, uint32_t count, const void* const* streams, const size_t* bytes)
 {
   uint32_t per = ctx->batch_chunk;
@@ -1038,8 +1046,8 @@ int submit_batch_device(psxgpu_ctx* ctx, uint32_t first, uint32_t count, const v
     int rc = open_group(ctx);
     if (rc != PSXGPU_OK)
       return rc;
-    // the pinned sets rotate by three: chunk k reuses the set of chunk k-3, whose waves must have been launched
-    advance(1, 1);
+    // the pinned sets rotate by six: chunk k reuses the set of chunk k-6, whose waves must have been launched
+    advance(2, 3);
     if (status != PSXGPU_OK)
       break;
     PendingChunk pc;
@@ -1210,15 +1218,25 @@ int psxgpu_create(int device, uint32_t n_instances, const psxgpu_opts* opts, psx
     return bail(e, "cudaSetDevice");
   if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess)
     return bail(e, "stream");
-  // The encode kernels are small (one warp per instance) and sit on the critical path of their chunk: they go on
-  // high-priority streams so that their CTAs are placed ahead of the raster waves' CTAs of earlier chunks.
+  // Stream priorities: measured (profiles/README.md), high-priority encode streams make the co-running raster waves
+  // 60 % slower for the whole time an encode kernel is resident (its 168-register CTAs displace ten one-warp raster
+  // CTAs each); at equal priority the encodes take longer but six chunks in flight hide that.  PSXGPU_ENC_PRIO=1
+  // restores the high priority for experiments.
   int prio_lo = 0, prio_hi = 0;
   cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
-  if (const char* pe = std::getenv("PSXGPU_ENC_PRIO")) // experiment knob: 0 = encode streams at default priority
-    if (pe[0] == '0')
+  {
+    const char* pe = std::getenv("PSXGPU_ENC_PRIO");
+    if (!(pe && pe[0] == '1'))
       prio_hi = prio_lo;
+  }
   if ((e = cudaStreamCreateWithPriority(&ctx->copy_stream, cudaStreamNonBlocking, prio_hi)) != cudaSuccess)
     return bail(e, "stream");
+  {
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    if ((e = cudaStreamCreateWithPriority(&ctx->walk_stream, cudaStreamNonBlocking, hi)) != cudaSuccess)
+      return bail(e, "stream");
+  }
   for (cudaStream_t& es : ctx->enc_streams)
     if ((e = cudaStreamCreateWithPriority(&es, cudaStreamNonBlocking, prio_hi)) != cudaSuccess)
       return bail(e, "stream");
@@ -1237,8 +1255,7 @@ int psxgpu_create(int device, uint32_t n_instances, const psxgpu_opts* opts, psx
   if ((e = cudaMemsetAsync(ctx->d_clut, 0, static_cast<size_t>(n_instances) * ctx->clut_slots * CLUT_ENTRIES * 2, ctx->stream)) !=
       cudaSuccess)
     return bail(e, "CLUT clear");
-  for (cudaEvent_t* ev : {&ctx->ev_start, &ctx->ev_end, &ctx->ev_hash0, &ctx->ev_hash1, &ctx->pinned[0].free_ev, &ctx->pinned[1].free_ev,
-                          &ctx->pinned[2].free_ev})
+  for (cudaEvent_t* ev : {&ctx->ev_start, &ctx->ev_end, &ctx->ev_hash0, &ctx->ev_hash1})
     if ((e = cudaEventCreate(ev)) != cudaSuccess)
       return bail(e, "event");
   if ((e = ctx->h_misc.ensure(std::max<size_t>(static_cast<size_t>(n_instances) * 8, 4096))) != cudaSuccess)
@@ -1267,7 +1284,7 @@ void psxgpu_destroy(psxgpu_ctx* ctx)
   if (!ctx)
     return;
   cudaSetDevice(ctx->device);
-  for (cudaStream_t st : {ctx->copy_stream, ctx->enc_streams[0], ctx->enc_streams[1], ctx->enc_streams[2], ctx->enc_streams[3], ctx->stream})
+  for (cudaStream_t st : {ctx->copy_stream, ctx->walk_stream, ctx->enc_streams[0], ctx->enc_streams[1], ctx->enc_streams[2], ctx->enc_streams[3], ctx->stream})
     if (st)
       cudaStreamSynchronize(st);
   ctx->h_misc.release();
@@ -1302,7 +1319,7 @@ void psxgpu_destroy(psxgpu_ctx* ctx)
   for (cudaEvent_t ev : {ctx->ev_start, ctx->ev_end, ctx->ev_hash0, ctx->ev_hash1})
     if (ev)
       cudaEventDestroy(ev);
-  for (cudaStream_t st : {ctx->copy_stream, ctx->enc_streams[0], ctx->enc_streams[1], ctx->enc_streams[2], ctx->enc_streams[3], ctx->stream})
+  for (cudaStream_t st : {ctx->copy_stream, ctx->walk_stream, ctx->enc_streams[0], ctx->enc_streams[1], ctx->enc_streams[2], ctx->enc_streams[3], ctx->stream})
     if (st)
       cudaStreamDestroy(st);
   delete ctx;
