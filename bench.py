@@ -189,6 +189,8 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         import torch.distributed as dist_mod
 
         dist = dist_mod
+        # stdout carries exactly one JSON line: whatever NCCL logs (version banner, NCCL_DEBUG output) goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     from duckstation_b200 import Context
