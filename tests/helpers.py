@@ -114,6 +114,17 @@ class HostSim:
             raise ValueError("malformed stream")
         return np.frombuffer(C.string_at(self.lib.hostsim_vram(), 1 << 20), dtype=np.uint16).reshape(512, 1024).copy()
 
+    def render_parts(self, parts, handover: bool, modulation_crop: bool = False) -> np.ndarray:
+        """Executes the parts as separate flushes; with `handover` the encoder is replaced between flushes by a fresh
+        one that only knows the exported state blob (host encoder <-> device encoder hand-over)."""
+        self.lib.hostsim_reset(int(modulation_crop))
+        for i, part in enumerate(parts):
+            if i and handover:
+                self.lib.hostsim_handover(int(modulation_crop))
+            if self.lib.hostsim_exec(part, len(part)) < 0:
+                raise ValueError("malformed stream")
+        return np.frombuffer(C.string_at(self.lib.hostsim_vram(), 1 << 20), dtype=np.uint16).reshape(512, 1024).copy()
+
     def stats(self) -> dict:
         v = (C.c_uint64 * 12)()
         self.lib.hostsim_stats(v, 12)

@@ -349,6 +349,19 @@ long hostsim_exec(const void* wire, size_t bytes)
   return static_cast<long>(g_enc->epochs.size());
 }
 
+// Replaces the encoder by a fresh one that only knows the exported state blob — what happens when an instance moves
+// between the host encoder and the device encoder of the batched path (Encoder::export_state / import_state).
+void hostsim_handover(int modulation_crop)
+{
+  if (!g_enc)
+    return;
+  EncoderStateBlob blob;
+  g_enc->export_state(blob);
+  delete g_enc;
+  g_enc = new Encoder(SLOTS, modulation_crop != 0);
+  g_enc->import_state(blob);
+}
+
 void hostsim_stats(uint64_t* out, int n)
 {
   const uint64_t v[] = {g_stats.wire_commands, g_stats.packed_prims, g_stats.epochs, g_stats.cuts_raw, g_stats.cuts_war,

@@ -137,3 +137,21 @@ def test_degenerate_drawing_areas_and_extreme_sizes(oracle, sim):
     for s in cases:
         got, want = sim.render(s), oracle.render(s)
         assert np.array_equal(got, want), describe_diff(got, want)
+
+
+@pytest.mark.parametrize("case", [(0, 31, 900, 3), (0, 32, 900, 1), (2, 4, 1200, 0), (3, 6, 700, 0), (4, 9, 800, 0)],
+                         ids=lambda c: "cfg{}-seed{}".format(*c[:2]))
+def test_encoder_state_survives_flushes_and_hand_over(case):
+    """Drawing area, current CLUT slots and the snapshot table carry across flushes, and across
+    Encoder::export_state -> import_state into a fresh encoder (how an instance moves between the host encoder and the
+    device encoder of the batched path)."""
+    s = streams.generate(*case)
+    s = b"".join(s[off:off + size] for typ, off, size in streams.iter_records(s) if typ not in (7, 9, 12, 15))
+    offs = [off for _, off, _ in streams.iter_records(s)]
+    cuts = [0, offs[len(offs) // 5], offs[len(offs) // 2], offs[4 * len(offs) // 5], len(s)]
+    parts = [s[a:b] for a, b in zip(cuts, cuts[1:])]
+    want = Oracle().render(s)
+    sim = HostSim()
+    for handover in (False, True):
+        got = sim.render_parts(parts, handover)
+        assert np.array_equal(got, want), (handover, describe_diff(got, want))
