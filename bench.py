@@ -162,7 +162,7 @@ def run_reference(args, rank: int, world: int):
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit_result(line)
 
 
 # ------------------------------------------------------------------------------------------------ our arm
@@ -189,8 +189,6 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         import torch.distributed as dist_mod
 
         dist = dist_mod
-        # stdout carries exactly one JSON line: whatever NCCL logs (version banner, NCCL_DEBUG output) goes to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     from duckstation_b200 import Context
@@ -384,14 +382,32 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             "cpu_baseline": cpu_baseline,
             "clocks": clocks,
         }
-        print(json.dumps(line), flush=True)
+        emit_result(line)
     ctx.close()
     if dist is not None:
         dist.destroy_process_group()
 
 
+_RESULT_FD = None
+
+
+def emit_result(line: dict) -> None:
+    """The one JSON line goes to the process's real stdout; everything else that writes to fd 1 (native libraries:
+    NCCL prints its version banner with printf) has been pointed at stderr by main()."""
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
+
+
 def main():
+    global _RESULT_FD
     args = parse_args()
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
