@@ -556,27 +556,67 @@ template<int NT>
 __device__ void serial_copy_rows(uint16_t* vram, uint32_t sx, uint32_t sy, uint32_t dx, uint32_t dy, uint32_t w, uint32_t h,
                                  uint16_t mand, uint16_t mor)
 {
+  // No column wrap in here (the caller splits those).  The reference walks the rows in order; what that order can be
+  // observed through is limited to three things, with d = (dy - sy) mod 512:
+  //   d == 0: source and destination share rows; a row is read completely before it is written (memmove), and rows do
+  //           not interact  ->  one warp per row, all rows at once;
+  //   row r reads what row r - d wrote (if d < h), and row r + (512 - d) overwrites what row r read (if 512 - d < h)
+  //           ->  any G = min(d, 512 - d, h) consecutive rows are free of hazards and are copied as one parallel batch.
   volatile uint16_t* vv = vram;
-  for (uint32_t r = 0; r < h; r++)
+  const uint32_t d = (dy - sy) & (VRAM_H - 1);
+  if (d == 0)
   {
-    const uint32_t srow = ((sy + r) & (VRAM_H - 1)) * VRAM_W, drow = ((dy + r) & (VRAM_H - 1)) * VRAM_W;
-    uint16_t px[VRAM_W / NT];
-#pragma unroll
-    for (uint32_t k = 0; k < VRAM_W / NT; k++)
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    for (uint32_t r = warp; r < h; r += NT / 32)
     {
-      const uint32_t c = k * NT + threadIdx.x;
-      px[k] = (c < w) ? vv[srow + ((sx + c) & (VRAM_W - 1))] : uint16_t(0);
+      const uint32_t row = ((sy + r) & (VRAM_H - 1)) * VRAM_W;
+      uint16_t px[VRAM_W / 32];
+#pragma unroll
+      for (uint32_t k = 0; k < VRAM_W / 32; k++)
+      {
+        const uint32_t c = k * 32 + lane;
+        px[k] = (c < w) ? vv[row + sx + c] : uint16_t(0);
+      }
+      __syncwarp();
+#pragma unroll
+      for (uint32_t k = 0; k < VRAM_W / 32; k++)
+      {
+        const uint32_t c = k * 32 + lane;
+        if (c < w)
+        {
+          const uint32_t a = row + dx + c;
+          if ((vv[a] & mand) == 0)
+            vv[a] = static_cast<uint16_t>(px[k] | mor);
+        }
+      }
     }
     __syncthreads();
-#pragma unroll
-    for (uint32_t k = 0; k < VRAM_W / NT; k++)
+    return;
+  }
+  uint32_t G = h;
+  if (d < h)
+    G = min(G, d);
+  if (VRAM_H - d < h)
+    G = min(G, VRAM_H - d);
+  for (uint32_t r0 = 0; r0 < h; r0 += G)
+  {
+    const uint32_t rows = min(G, h - r0);
+    // (row, column) pairs of the batch, NT at a time; a thread keeps its row/column by stepping instead of dividing
+    uint32_t rr = threadIdx.x / w, c = threadIdx.x - rr * w;
+    const uint32_t step_r = NT / w, step_c = NT - step_r * w;
+    while (rr < rows)
     {
-      const uint32_t c = k * NT + threadIdx.x;
-      if (c < w)
+      const uint32_t y = r0 + rr;
+      const uint16_t src = vv[((sy + y) & (VRAM_H - 1)) * VRAM_W + sx + c];
+      const uint32_t a = ((dy + y) & (VRAM_H - 1)) * VRAM_W + dx + c;
+      if ((vv[a] & mand) == 0)
+        vv[a] = static_cast<uint16_t>(src | mor);
+      rr += step_r;
+      c += step_c;
+      if (c >= w)
       {
-        const uint32_t a = drow + ((dx + c) & (VRAM_W - 1));
-        if ((vv[a] & mand) == 0)
-          vv[a] = static_cast<uint16_t>(px[k] | mor);
+        c -= w;
+        rr++;
       }
     }
     __syncthreads();
@@ -613,46 +653,83 @@ __device__ void serial_copy(const PrimSetup& s, uint16_t* vram)
 }
 
 // mask-checked upload.  Source index of a pixel = its linear index minus the number of masked pixels
-// before it (in scan order) that sit in the scalar tail of their row (columns >= aw).
+// before it (in scan order) that sit in the scalar tail of their row (columns >= aw).  Rows never revisit a pixel
+// (w <= 1024, h <= 512), so the masked-tail count of every row can be taken up front, prefix-summed over the rows, and
+// all rows written at once — one warp per row.  `row_count`: shared, VRAM_H + 1 words.
 template<int NT>
 __device__ void serial_upload_masked(const PrimSetup& s, uint16_t* vram, const uint16_t* __restrict__ payload,
-                                     uint32_t* warp_count)
+                                     uint32_t* row_count)
 {
   const auto& U = s.upload;
   const uint32_t aw = min(static_cast<uint32_t>(U.w), VRAM_W - U.x) & ~7u;
   const uint16_t mor = (s.flags0 & F_SET_MASK) ? 0x8000u : 0;
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-  uint32_t deficit = 0; // uniform across the CTA
-  for (uint32_t r = 0; r < U.h; r++)
+  const uint32_t h = min(static_cast<uint32_t>(U.h), VRAM_H), w = U.w;
+  // pass 1: masked pixels in the tail of every row
+  for (uint32_t r = warp; r < h; r += NT / 32)
   {
     const uint32_t drow = ((U.y + r) & (VRAM_H - 1)) * VRAM_W;
-    for (uint32_t base = 0; base < U.w; base += NT)
+    uint32_t n = 0;
+    for (uint32_t base = aw; base < w; base += 32)
     {
-      const uint32_t c = base + threadIdx.x;
-      const bool in = c < U.w;
+      const uint32_t c = base + lane;
+      const bool masked = c < w && (vram[drow + ((U.x + c) & (VRAM_W - 1))] & 0x8000u);
+      n += __popc(__ballot_sync(0xFFFFFFFFu, masked));
+    }
+    if (lane == 0)
+      row_count[r] = n;
+  }
+  __syncthreads();
+  // pass 2: exclusive prefix over the rows (one warp, 16 rows per lane)
+  if (warp == 0)
+  {
+    uint32_t local[VRAM_H / 32], sum = 0;
+#pragma unroll
+    for (uint32_t k = 0; k < VRAM_H / 32; k++)
+    {
+      const uint32_t r = lane * (VRAM_H / 32) + k;
+      local[k] = sum;
+      sum += (r < h) ? row_count[r] : 0u;
+    }
+    uint32_t incl = sum;
+#pragma unroll
+    for (uint32_t o = 1; o < 32; o <<= 1)
+    {
+      const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+      if (lane >= o)
+        incl += t;
+    }
+    const uint32_t before = incl - sum;
+    __syncwarp();
+#pragma unroll
+    for (uint32_t k = 0; k < VRAM_H / 32; k++)
+    {
+      const uint32_t r = lane * (VRAM_H / 32) + k;
+      if (r < h)
+        row_count[r] = before + local[k];
+    }
+  }
+  __syncthreads();
+  // pass 3: every row on its own
+  for (uint32_t r = warp; r < h; r += NT / 32)
+  {
+    const uint32_t drow = ((U.y + r) & (VRAM_H - 1)) * VRAM_W;
+    uint32_t deficit = row_count[r];
+    for (uint32_t base = 0; base < w; base += 32)
+    {
+      const uint32_t c = base + lane;
+      const bool in = c < w;
       const uint32_t a = drow + ((U.x + c) & (VRAM_W - 1));
       const uint16_t d = in ? vram[a] : uint16_t(0);
       const bool masked = in && (d & 0x8000u);
-      const bool counts = masked && c >= aw;
-      const uint32_t bal = __ballot_sync(0xFFFFFFFFu, counts);
-      if (lane == 0)
-        warp_count[warp] = __popc(bal);
-      __syncthreads();
-      uint32_t before = __popc(bal & ((1u << lane) - 1u));
-      uint32_t total = 0;
-#pragma unroll
-      for (uint32_t k = 0; k < NT / 32; k++)
-      {
-        const uint32_t n = warp_count[k];
-        before += (k < warp) ? n : 0u;
-        total += n;
-      }
+      const uint32_t bal = __ballot_sync(0xFFFFFFFFu, masked && c >= aw);
+      const uint32_t before = __popc(bal & ((1u << lane) - 1u));
       if (in && !masked)
-        vram[a] = static_cast<uint16_t>(__ldg(payload + U.payload + r * U.w + c - (deficit + before)) | mor);
-      deficit += total;
-      __syncthreads();
+        vram[a] = static_cast<uint16_t>(__ldg(payload + U.payload + r * w + c - (deficit + before)) | mor);
+      deficit += __popc(bal);
     }
   }
+  __syncthreads();
 }
 
 // Epochs of a serial kind: one CTA per item, everything else returns at once.
@@ -661,7 +738,7 @@ __global__ void __launch_bounds__(SERIAL_THREADS) serial_kernel(const WaveItem* 
                                                                 const uint16_t* __restrict__ payload, uint32_t clut_slots)
 {
   __shared__ alignas(16) uint32_t stage[SETUP_WORDS];
-  __shared__ uint32_t warp_count[SERIAL_WARPS];
+  __shared__ uint32_t row_count[VRAM_H + 1];
   const WaveItem it = items[blockIdx.x];
   if (it.kind == EPOCH_TILED || it.cmd_begin == it.cmd_end)
     return;
@@ -678,7 +755,7 @@ __global__ void __launch_bounds__(SERIAL_THREADS) serial_kernel(const WaveItem* 
   else if (it.kind == EPOCH_COPY_OVERLAP)
     serial_copy<SERIAL_THREADS>(s, vram);
   else
-    serial_upload_masked<SERIAL_THREADS>(s, vram, payload, warp_count);
+    serial_upload_masked<SERIAL_THREADS>(s, vram, payload, row_count);
 }
 
 // One warp runs one epoch of one instance on its region: bins the epoch's primitives (submission order), stages the
@@ -856,7 +933,7 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 7) raster_persistent_kernel(
   uint16_t* clut_pool, const uint16_t* __restrict__ payload, uint32_t clut_slots, unsigned int* barrier_counter)
 {
   __shared__ RasterShared<PERSIST_RH> sh_all[PERSIST_WARPS];
-  __shared__ uint32_t warp_count[PERSIST_WARPS];
+  __shared__ uint32_t row_count[VRAM_H + 1];
   const unsigned int n_ctas = gridDim.x * gridDim.y;
   unsigned int generation = 0;
   const uint32_t instance = instances[blockIdx.y];
@@ -910,7 +987,7 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 7) raster_persistent_kernel(
           else if (it.kind == EPOCH_COPY_OVERLAP)
             serial_copy<PERSIST_THREADS>(s, vram);
           else
-            serial_upload_masked<PERSIST_THREADS>(s, vram, payload, warp_count);
+            serial_upload_masked<PERSIST_THREADS>(s, vram, payload, row_count);
         }
         __syncthreads();
       }
