@@ -42,6 +42,10 @@ class Gp0Assembler:
         self.mask = (0, 0)
         self.clut_reg = None
         self.clut8 = False
+        # display registers (only used when UpdateDisplay records are translated, see add_record)
+        self.display = False
+        self.disp_mode = None
+        self.disp_addr = None
 
     # ---------------------------------------------------------------- raw emitters
     def gp0(self, *words: int) -> None:
@@ -185,8 +189,32 @@ class Gp0Assembler:
             self.finish_read()
         elif typ in (CMD_POLY, CMD_RECT, CMD_LINE):
             self._add_draw(typ, rec)
+        elif typ == CMD_UPDATE_DISPLAY and self.display:
+            self._add_display(rec)
         else:
             raise Unsupported(f"record type {typ}")
+
+    def _add_display(self, rec: bytes) -> None:
+        """A progressive 320x240 frame whose display rectangle starts at the display address: GP1 writes a game would
+        make (ranges and enable once, mode and start address when they change) and the end of the frame.  With the
+        front-end in `borders` crop mode this yields the same UpdateDisplay geometry as the record."""
+        w, h, ol, ot, vl, vt, vw, vh = struct.unpack_from("<8H", rec, 8)
+        x, _busy, flags = struct.unpack_from("<HBB", rec, 28)
+        if (w, h, ol, ot, vw, vh) != (320, 240, 0, 0, 320, 240) or x != vl or (flags & 0x2F):
+            raise Unsupported("display geometry")
+        if self.disp_mode is None:
+            self.gp1(0x06000000 | 0x260 | (0xC60 << 12))
+            self.gp1(0x07000000 | 16 | (256 << 10))
+            self.gp1(0x03000000)
+        mode = 0x08000000 | 1 | (0x10 if flags & 0x10 else 0)
+        if mode != self.disp_mode:
+            self.gp1(mode)
+            self.disp_mode = mode
+        addr = vl | (vt << 10)
+        if addr != self.disp_addr:
+            self.gp1(0x05000000 | addr)
+            self.disp_addr = addr
+        self.vsync()
 
     def _add_draw(self, typ: int, rec: bytes) -> None:
         f0, f1, nv, draw_mode, palette = struct.unpack_from("<BBHHH", rec, 8)

@@ -5,6 +5,8 @@ emulator, so these tests pin it two other ways: (1) hand-assembled GP0 words who
 public PSX GPU command encodings, (2) a round trip — generator records (whose rendering IS pinned against the compiled
 reference) -> GP0 words via tests/gp0_assembler.py -> front-end -> records, which the oracle must render to the same
 VRAM.  Host-only; the GPU leg of the round trip is in test_gpu_features.py."""
+import json
+import os
 import struct
 
 import numpy as np
@@ -14,7 +16,9 @@ from duckstation_b200 import streams
 from duckstation_b200.frontend import CROP_BORDERS, CROP_NONE, CROP_OVERSCAN, Gp0Frontend
 
 from tests import gp0_assembler as asm
-from tests.helpers import Oracle, describe_diff
+from tests.helpers import Oracle, describe_diff, sha256
+
+GOLDEN = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden.json")))
 
 
 def records(stream: bytes):
@@ -418,3 +422,34 @@ def test_psxgpu_trace_container(oracle):
         fe.feed_dump(dump[:-3])
     with pytest.raises(ValueError):
         fe.feed_dump(dump + struct.pack("<I", 0x00FFFFFF))  # a packet header that promises more words than follow
+
+
+def config5_as_psxgpu_trace() -> bytes:
+    """BASELINE config 5 (the frame trace whose per-frame hashes in tests/golden were made by the compiled reference)
+    re-expressed as a `.psxgpu` trace: GP0 words for the records, GP1 writes + VSync packets for the UpdateDisplay
+    records ("stored both as backend-command streams and as .psxgpu")."""
+    s = streams.generate(5, 3, 12, 200)
+    a = asm.Gp0Assembler()
+    a.display = True
+    a.gp1(0x00000000)
+    a.add_stream(s)
+    return asm.write_dump(a.events, max_gp0_words=61)
+
+
+def test_config5_trace_reproduces_the_reference_goldens(oracle):
+    """`.psxgpu` trace -> front-end -> records -> oracle: every frame's VRAM and scanned-out image hash equals the
+    golden value the reference's own rasteriser produced from the record form of the same trace."""
+    fe = Gp0Frontend(crop_mode=CROP_BORDERS)
+    assert fe.feed_dump(config5_as_psxgpu_trace()) == len(GOLDEN["scanout"])
+    frames = streams.split_frames(fe.records())
+    assert len(frames) == len(GOLDEN["scanout"])
+    oracle.reset()
+    for entry, frame in zip(GOLDEN["scanout"], frames):
+        oracle.exec(frame)
+        assert sha256(oracle.vram()) == entry["vram_sha256"], f"frame {entry['frame']}"
+        if "scanout_sha256" in entry:
+            disp = [frame[o:o + z] for t, o, z in streams.iter_records(frame) if t == asm.CMD_UPDATE_DISPLAY][-1]
+            img = oracle.scanout(disp, 0)
+            w, h = oracle.last_size
+            assert [w, h] == entry["size"]
+            assert sha256(img[:, : w * 4]) == entry["scanout_sha256"], f"frame {entry['frame']}"

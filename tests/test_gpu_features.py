@@ -413,3 +413,21 @@ def test_device_encoder_rejects_bad_streams_and_handles_empty_ones(oracle):
         oracle.render(good)
         oracle.exec(good)
         assert again[0] == oracle.hash64(oracle.vram())
+
+
+def test_config5_psxgpu_trace_replay_matches_reference_goldens():
+    """The config-5 frame trace as a `.psxgpu` file through psxgpu_replay_dump: per-frame VRAM and display hashes are
+    the ones the reference's rasteriser produced (tests/golden)."""
+    from duckstation_b200.frontend import CROP_BORDERS, replay_dump
+    from tests.test_gp0_frontend import config5_as_psxgpu_trace
+
+    dump = config5_as_psxgpu_trace()
+    got = []
+    with _ctx() as ctx:
+        n = replay_dump(ctx, dump, crop_mode=CROP_BORDERS, on_frame=lambda i: got.append((sha256(ctx.read_vram()), ctx.display())))
+    assert n == len(GOLDEN["scanout"]) == len(got)
+    for entry, (vram_sha, img) in zip(GOLDEN["scanout"], got):
+        assert vram_sha == entry["vram_sha256"], f"frame {entry['frame']}"
+        if "scanout_sha256" in entry:
+            assert img is not None and list(img.shape) == [entry["size"][1], entry["size"][0] * 4]
+            assert sha256(img) == entry["scanout_sha256"], f"frame {entry['frame']}"
