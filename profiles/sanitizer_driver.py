@@ -15,3 +15,11 @@ with Context(6, profile=True) as ctx:  # throughput kernels
     ctx.submit_batch([streams.generate(4, i, 200, 0) for i in range(5)] + [mixed])
     ctx.flush()
     print("batch:", [hex(int(h)) for h in ctx.hash()])
+with Context(20, encode_mode=2) as ctx:  # device encoder: framing, layout, encode (fast + uniform paths), wave kernels
+    batch = [streams.generate(4, i, 150, 0) for i in range(10)] + [streams.generate(0, 40 + i, 200, 3) for i in range(8)] + [
+        b"".join(mixed[o:o + z] for t, o, z in streams.iter_records(mixed) if t not in (7, 9, 12, 15)), b""]
+    ctx.set_batch_chunk(7)
+    ctx.submit_batch(batch)
+    ctx.flush()
+    ctx.run_staged()
+    print("device-encoded:", [hex(int(h)) for h in ctx.hash()][:4])
