@@ -431,3 +431,45 @@ def test_config5_psxgpu_trace_replay_matches_reference_goldens():
         if "scanout_sha256" in entry:
             assert img is not None and list(img.shape) == [entry["size"][1], entry["size"][0] * 4]
             assert sha256(img) == entry["scanout_sha256"], f"frame {entry['frame']}"
+
+
+def _tight(stream: bytes) -> bytes:
+    """Re-frames a stream with every record cut to the bytes it needs, rounded to 4 (the reference rounds to 16): records
+    are then not 16-byte aligned any more, which the device encoder has to handle on its record-at-a-time path."""
+    import struct
+
+    out = bytearray()
+    for typ, off, size in streams.iter_records(stream):
+        rec = bytearray(stream[off:off + size])
+        if typ == 22:
+            need = 20 + 16 * struct.unpack_from("<H", rec, 10)[0]
+        elif typ == 25:
+            need = 20 + 12 * struct.unpack_from("<H", rec, 10)[0]
+        elif typ == 24:
+            need = 40
+        elif typ in (16, 18, 19):
+            need = 24
+        elif typ == 20:
+            need = 12
+        elif typ == 17:
+            w, h = struct.unpack_from("<HH", rec, 12)
+            need = 18 + 2 * w * h
+        else:
+            need = size
+        need = min(size, (need + 3) & ~3)
+        struct.pack_into("<I", rec, 0, need)
+        out += rec[:need]
+    return bytes(out)
+
+
+def test_device_encoder_precise_and_unaligned_records(oracle):
+    base = [_strip_barriers(streams.generate(*c)) for c in [(0, 60 + i, 500, 3) for i in range(6)] + [(3, 9, 700, 0), (2, 3, 700, 0)]]
+    batch = [streams.to_precise(s) for s in base] + [_tight(s) for s in base] + [_tight(streams.to_precise(s)) for s in base[:4]]
+    want = [oracle.hash64(oracle.render(s)) for s in base]
+    want = want + want + want[:4]
+    assert any(any(off % 16 for _, off, _ in streams.iter_records(s)) for s in batch[8:16])
+    with _ctx(len(batch), encode_mode=2) as ctx:
+        ctx.submit_batch(batch)
+        ctx.flush()
+        got = [int(h) for h in ctx.hash()]
+    assert got == want, [i for i in range(len(batch)) if got[i] != want[i]]
