@@ -75,10 +75,12 @@ typedef struct psxgpu_timing {
   uint32_t last_raster_launches;
   uint32_t last_waves;
   float last_hash_ms;           /* last psxgpu_hash* call */
-  float last_encode_ms;         /* host time spent in the encoder during the last submit(s) since the previous flush */
+  float last_encode_ms;         /* host time spent encoding (host-encoded work) or staging raw streams (device-encoded
+                                   batches) during the last submit(s) since the previous flush */
   float last_stage_ms;          /* host time spent packing pinned staging buffers in the last flush */
   float last_scan_ms;           /* batched submit: header scan that sizes the pinned slots */
-  float last_pinned_wait_ms;    /* batched submit: host waiting for a pinned staging set to be consumed by its H2D copy */
+  float last_pinned_wait_ms;    /* batched submit: host waiting for the device — a pinned staging set still being copied,
+                                   or (device-encoded batches) a chunk's framing result / wave table */
   float last_launch_ms;         /* host time building wave descriptors + enqueueing copies and kernels */
   float reserved[4];
 } psxgpu_timing;
