@@ -291,7 +291,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     host_hashes = None
     ctx.reset_stats()
     ctx.set_batch_chunk(0)  # automatic chunking: the copy of chunk k+1 overlaps the encode + waves of chunk k
-    for _ in range(max(1, args.warmup // 2)):
+    for _ in range(max(1, args.warmup)):
         ctx.submit_batch_raw(ptrs, sizes, n_inst)
         ctx.flush()
         host_hashes = ctx.hash()
