@@ -299,6 +299,12 @@ int run_chunk(psxgpu_ctx* ctx, psxgpu_ctx::Chunk& S)
   if (S.n_cmds)
     ctx->counters.kernel_launches++;
   const uint32_t waves = static_cast<uint32_t>(S.wave_off.size()) - 1;
+  if (!S.wave_off.empty() && S.wave_off.back() != 0)
+  {
+    CK(launch_item_union(static_cast<WaveItem*>(S.d_items.p), S.wave_off.back(), static_cast<const BinInfo*>(S.d_bins.p), ctx->stream),
+       "item_union_kernel");
+    ctx->counters.kernel_launches++;
+  }
   S.ev_raster_used = 0;
   if (S.persistent)
   {

@@ -882,12 +882,32 @@ __global__ void __launch_bounds__(32 * PSX_RASTER_WARPS, PSX_RASTER_MIN_CTAS) ra
   const WaveItem it = items[blockIdx.y];
   if (it.kind != EPOCH_TILED || it.cmd_begin == it.cmd_end)
     return;
-  uint16_t* vram = vram_pool + static_cast<size_t>(it.instance) * VRAM_PIXELS;
-  const uint16_t* cluts = clut_pool + static_cast<size_t>(it.instance) * clut_slots * CLUT_ENTRIES;
   const uint32_t tile = blockIdx.x * PSX_RASTER_WARPS + (threadIdx.x >> 5);
   const uint32_t tx = tile % TILES_X, ty = tile / TILES_X;
+  // pad[0] = union of the epoch's tile masks (item_union_kernel): a tile that no primitive of the epoch can touch
+  // leaves without scanning the bins (half of the tiles of a frame that draws into one half of VRAM)
+  const uint32_t tile_bits = (1u << tx) | (1u << (16 + ty));
+  if ((it.pad[0] & tile_bits) != tile_bits)
+    return;
+  uint16_t* vram = vram_pool + static_cast<size_t>(it.instance) * VRAM_PIXELS;
+  const uint16_t* cluts = clut_pool + static_cast<size_t>(it.instance) * clut_slots * CLUT_ENTRIES;
   process_epoch_region<TILE_H, false>(it, sh_all[threadIdx.x >> 5], tx, ty, ty * TILE_H, setups, bins, vram, cluts, payload,
                                       threadIdx.x & 31u);
+}
+
+// Union of the tile masks of every epoch (one warp per wave item), stored in WaveItem::pad[0].
+__global__ void __launch_bounds__(128) item_union_kernel(WaveItem* __restrict__ items, uint32_t n_items, const BinInfo* __restrict__ bins)
+{
+  const uint32_t idx = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31u;
+  if (idx >= n_items)
+    return;
+  const uint32_t b = items[idx].cmd_begin, e = items[idx].cmd_end;
+  uint32_t m = 0;
+  for (uint32_t i = b + lane; i < e; i += 32)
+    m |= bins[i].tilemask;
+  m = __reduce_or_sync(0xFFFFFFFFu, m);
+  if (lane == 0)
+    items[idx].pad[0] = m;
 }
 
 // ------------------------------------------------------------------------------------------------ persistent (latency) mode
@@ -1118,6 +1138,14 @@ cudaError_t launch_raster(const WaveItem* items, uint32_t n_items, const PrimSet
     const uint32_t n = (n_items - off) < 32768u ? (n_items - off) : 32768u;
     raster_kernel<<<dim3(NUM_TILES / PSX_RASTER_WARPS, n), 32 * PSX_RASTER_WARPS, 0, st>>>(items + off, setups, bins, vram_pool, clut_pool, payload, clut_slots);
   }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_item_union(WaveItem* items, uint32_t n_items, const BinInfo* bins, cudaStream_t st)
+{
+  if (n_items == 0)
+    return cudaSuccess;
+  item_union_kernel<<<(n_items + 3) / 4, 128, 0, st>>>(items, n_items, bins);
   return cudaGetLastError();
 }
 

@@ -19,6 +19,8 @@ struct ScanoutParams
 };
 
 cudaError_t launch_setup(const PackedCmd* cmds, PrimSetup* setups, BinInfo* bins, uint32_t n, cudaStream_t st);
+// After setup: WaveItem::pad[0] = union of the tile masks of the item's commands (raster CTAs of other tiles exit at once).
+cudaError_t launch_item_union(WaveItem* items, uint32_t n_items, const BinInfo* bins, cudaStream_t st);
 cudaError_t launch_clut(const WaveItem* items, uint32_t n_items, const ClutOp* ops, const uint16_t* vram_pool,
                         uint16_t* clut_pool, uint32_t clut_slots, cudaStream_t st);
 cudaError_t launch_raster(const WaveItem* items, uint32_t n_items, const PrimSetup* setups, const BinInfo* bins,
