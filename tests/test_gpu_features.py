@@ -473,3 +473,68 @@ def test_device_encoder_precise_and_unaligned_records(oracle):
         ctx.flush()
         got = [int(h) for h in ctx.hash()]
     assert got == want, [i for i in range(len(batch)) if got[i] != want[i]]
+
+
+def test_device_encoder_page_locked_inputs(oracle):
+    """Streams that already sit in page-locked memory are copied to the device from where they are: neighbours in one
+    copy, any order, gaps; a misaligned or pageable stream in the chunk sends the whole chunk through the staging copy."""
+    import ctypes as C
+
+    import torch
+
+    n = 24
+    batch = [_strip_barriers(streams.generate(*c)) for c in [(0, 200 + i, 250, 3) for i in range(12)] + [(4, 300 + i, 200, 0) for i in range(12)]]
+    want = [oracle.hash64(oracle.render(s)) for s in batch]
+
+    def run(layout):
+        """layout: list of byte offsets (into one pinned buffer) per stream"""
+        total = max(o + len(s) for o, s in zip(layout, batch)) + 64
+        pinned = torch.empty(total + 64, dtype=torch.uint8).pin_memory()
+        base = pinned.data_ptr()
+        base += (-base) % 16
+        view = np.ctypeslib.as_array((C.c_uint8 * total).from_address(base))
+        ptrs = (C.c_void_p * n)()
+        sizes = (C.c_size_t * n)()
+        for i, (o, s) in enumerate(zip(layout, batch)):
+            view[o:o + len(s)] = np.frombuffer(s, dtype=np.uint8)
+            ptrs[i] = base + o
+            sizes[i] = len(s)
+        with _ctx(n, encode_mode=2) as ctx:
+            ctx.set_batch_chunk(10)
+            ctx.submit_batch_raw(ptrs, sizes, n)
+            ctx.flush()
+            got = [int(h) for h in ctx.hash()]
+            h2d = ctx.stats()["h2d_bytes"]
+        del pinned
+        return got, h2d
+
+    a16 = lambda v: (v + 15) & ~15
+    # back to back
+    offs, at = [], 0
+    for s in batch:
+        offs.append(at)
+        at = a16(at + len(s))
+    got, h2d_packed = run(offs)
+    assert got == want
+    # gaps of 48 bytes (still one run) and of 4 KB (separate runs), streams in reverse address order
+    offs, at = [], 0
+    for i, s in enumerate(batch):
+        offs.append(at)
+        at = a16(at + len(s)) + (48 if i % 2 else 4096)
+    got, _ = run(offs)
+    assert got == want
+    # streams in decreasing address order
+    offs, at = [0] * n, 0
+    for i in reversed(range(n)):
+        offs[i] = at
+        at = a16(at + len(batch[i])) + 32
+    got, _ = run(offs)
+    assert got == want
+    # a misaligned stream: the chunk falls back to the staging copy, same result
+    offs, at = [], 4
+    for s in batch:
+        offs.append(at)
+        at = a16(at + len(s)) + 4
+    got, _ = run(offs)
+    assert got == want
+    assert h2d_packed >= sum(len(s) for s in batch)
