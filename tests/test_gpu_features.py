@@ -538,3 +538,53 @@ def test_device_encoder_page_locked_inputs(oracle):
     got, _ = run(offs)
     assert got == want
     assert h2d_packed >= sum(len(s) for s in batch)
+
+
+def _rec(typ: int, payload: bytes) -> bytes:
+    import struct
+
+    size = (8 + len(payload) + 15) & ~15
+    return struct.pack("<IB3x", size, typ) + payload + bytes(size - 8 - len(payload))
+
+
+def _clut_pressure_stream(seed: int, n: int) -> bytes:
+    """More distinct palettes than CLUT snapshot slots inside one hazard-free run: noise in the right half of VRAM,
+    then `n` small 4-bit textured sprites on the left, each with a palette register of its own."""
+    import struct
+
+    rng = np.random.default_rng(seed)
+    out = bytearray()
+    out += _rec(19, struct.pack("<4I", 0, 0, 511, 511))
+    noise = rng.integers(0, 65536, size=(512, 512), dtype=np.uint16)
+    out += _rec(17, struct.pack("<4HBB", 512, 0, 512, 512, 0, 0) + noise.tobytes())
+    for i in range(n):
+        reg = (32 + (i % 32)) | (((i // 32) % 512) << 6)  # x = 512 + 16*(i%32), y = i//32: all different
+        out += _rec(20, struct.pack("<HB", reg, 0))
+        flags0 = 0x10 | (0x20 if i % 3 == 0 else 0)
+        draw_mode = 8 | (0 << 7)  # texture page x = 512, 4-bit
+        hdr = struct.pack("<BBHHH4B", flags0, 0, 1, draw_mode, reg, 0xFF, 0xFF, 0, 0)
+        x, y = int(rng.integers(0, 480)), int(rng.integers(0, 480))
+        out += _rec(24, hdr + struct.pack("<HHH2xiiI", 12, 9, int(rng.integers(0, 65536)), x, y, 0x808080))
+    return bytes(out)
+
+
+def test_device_encoder_slot_pressure_and_long_epochs(oracle):
+    """Two paths that ordinary streams rarely take: more live palettes than snapshot slots (the CLUT cache cuts the
+    epoch) and more than 65535 primitives without a hazard (the epoch length cap)."""
+    long_run = _strip_barriers(streams.generate(1, 5, 70000, 0))
+    batch = [_clut_pressure_stream(1, 700), _clut_pressure_stream(2, 300), long_run] + [
+        _strip_barriers(streams.generate(4, 900 + i, 100, 0)) for i in range(13)]
+    want = [oracle.hash64(oracle.render(s)) for s in batch]
+    stats = {}
+    for mode, slots in ((2, 0), (1, 0), (2, 64), (1, 64)):
+        with _ctx(len(batch), encode_mode=mode, clut_slots=slots) as ctx:
+            ctx.submit_batch(batch)
+            ctx.flush()
+            got = [int(h) for h in ctx.hash()]
+            assert got == want, (mode, slots, [i for i in range(len(batch)) if got[i] != want[i]])
+            stats[(mode, slots)] = ctx.stats()
+    for slots in (0, 64):
+        for key in ("packed_prims", "epochs", "cuts_raw", "cuts_war", "cuts_clut", "clut_ops", "clut_cache_hits"):
+            assert stats[(2, slots)][key] == stats[(1, slots)][key], (slots, key, stats[(2, slots)][key], stats[(1, slots)][key])
+    assert stats[(2, 0)]["cuts_clut"] > 0 and stats[(2, 64)]["cuts_clut"] > stats[(2, 0)]["cuts_clut"]
+    assert stats[(2, 0)]["epochs"] > len(batch) + 2
