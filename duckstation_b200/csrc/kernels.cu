@@ -22,6 +22,9 @@
 
 #include <cuda_runtime.h>
 
+#include <algorithm>
+#include <cstdlib>
+
 namespace psx {
 
 // ------------------------------------------------------------------------------------------------ setup
@@ -895,6 +898,54 @@ __global__ void __launch_bounds__(32 * PSX_RASTER_WARPS, PSX_RASTER_MIN_CTAS) ra
                                       threadIdx.x & 31u);
 }
 
+// Same work as raster_kernel, other scheduling: exactly as many one-warp CTAs as the GPU holds (SMs x 32), each pulling
+// (item, tile) pairs from a global counter eight at a time until the wave is done — no CTA launch per tile, no idle
+// slot between a CTA's exit and its successor's start, dynamic balance between busy and empty tiles.
+constexpr uint32_t LOOP_GRAB = 8;
+__device__ unsigned int g_raster_loop_counter[64];
+
+__global__ void __launch_bounds__(32, PSX_RASTER_MIN_CTAS) raster_loop_kernel(
+  const WaveItem* __restrict__ items, uint32_t n_items, const PrimSetup* __restrict__ setups, const BinInfo* __restrict__ bins,
+  uint16_t* __restrict__ vram_pool, const uint16_t* __restrict__ clut_pool, const uint16_t* __restrict__ payload, uint32_t clut_slots,
+  uint32_t counter_slot)
+{
+  __shared__ RasterShared<TILE_H> sh;
+  const uint32_t lane = threadIdx.x;
+  const uint32_t total = n_items * NUM_TILES;
+  for (;;)
+  {
+    uint32_t first = 0, grab = 0;
+    if (lane == 0)
+    {
+      // guided self-scheduling: large grabs while there is plenty left, single tiles towards the end of the wave
+      const uint32_t seen = *reinterpret_cast<volatile unsigned int*>(&g_raster_loop_counter[counter_slot]);
+      const uint32_t left = (total > seen) ? (total - seen) : 0u;
+      grab = min(LOOP_GRAB, max(1u, left / (gridDim.x * 4u)));
+      first = atomicAdd(&g_raster_loop_counter[counter_slot], grab);
+    }
+    first = __shfl_sync(0xFFFFFFFFu, first, 0);
+    grab = __shfl_sync(0xFFFFFFFFu, grab, 0);
+    if (first >= total)
+      break;
+    const uint32_t last = min(first + grab, total);
+    for (uint32_t id = first; id < last; id++)
+    {
+      const WaveItem it = items[id / NUM_TILES];
+      if (it.kind != EPOCH_TILED || it.cmd_begin == it.cmd_end)
+        continue;
+      const uint32_t tile = id % NUM_TILES;
+      const uint32_t tx = tile % TILES_X, ty = tile / TILES_X;
+      const uint32_t tile_bits = (1u << tx) | (1u << (16 + ty));
+      if ((it.pad[0] & tile_bits) != tile_bits)
+        continue;
+      uint16_t* vram = vram_pool + static_cast<size_t>(it.instance) * VRAM_PIXELS;
+      const uint16_t* cluts = clut_pool + static_cast<size_t>(it.instance) * clut_slots * CLUT_ENTRIES;
+      process_epoch_region<TILE_H, false>(it, sh, tx, ty, ty * TILE_H, setups, bins, vram, cluts, payload, lane);
+      __syncwarp();
+    }
+  }
+}
+
 // Union of the tile masks of every epoch (one warp per wave item), stored in WaveItem::pad[0].
 __global__ void __launch_bounds__(128) item_union_kernel(WaveItem* __restrict__ items, uint32_t n_items, const BinInfo* __restrict__ bins)
 {
@@ -1132,6 +1183,34 @@ cudaError_t launch_raster(const WaveItem* items, uint32_t n_items, const PrimSet
                           uint16_t* vram_pool, const uint16_t* clut_pool, const uint16_t* payload, uint32_t clut_slots,
                           cudaStream_t st)
 {
+  // Waves with enough work use the persistent-loop kernel (PSXGPU_RASTER_LOOP=0 forces one CTA per tile everywhere).
+  static const int loop_mode = []() {
+    const char* e = std::getenv("PSXGPU_RASTER_LOOP");
+    return e ? std::atoi(e) : 1;
+  }();
+  if (loop_mode > 0 && n_items >= 16 && n_items * static_cast<uint64_t>(NUM_TILES) < 0xFFFF0000ull)
+  {
+    static int sms = 0;
+    static uint32_t slot = 0;
+    static unsigned int* counters = nullptr;
+    if (sms == 0)
+    {
+      int dev = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      void* sym = nullptr;
+      cudaGetSymbolAddress(&sym, g_raster_loop_counter);
+      counters = static_cast<unsigned int*>(sym);
+    }
+    slot = (slot + 1) % 64;
+    cudaError_t e = cudaMemsetAsync(counters + slot, 0, sizeof(unsigned int), st);
+    if (e != cudaSuccess)
+      return e;
+    const uint32_t total = n_items * NUM_TILES;
+    const uint32_t ctas = std::min<uint32_t>(static_cast<uint32_t>(sms) * 32u, total / 2u + 1u);
+    raster_loop_kernel<<<ctas, 32, 0, st>>>(items, n_items, setups, bins, vram_pool, clut_pool, payload, clut_slots, slot);
+    return cudaGetLastError();
+  }
   // gridDim.y is limited to 65535: chunk the wave
   for (uint32_t off = 0; off < n_items; off += 32768)
   {
