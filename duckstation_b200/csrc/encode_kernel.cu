@@ -15,7 +15,11 @@
 namespace psx {
 namespace {
 
-constexpr uint32_t ENC_WARPS = 4;
+#ifndef PSX_ENC_WARPS
+#define PSX_ENC_WARPS 4
+#endif
+constexpr uint32_t ENC_WARPS = PSX_ENC_WARPS;
+constexpr uint32_t WALK_WARPS = PSX_ENC_WARPS;
 constexpr uint32_t FULL = 0xFFFFFFFFu;
 
 // Following the record sizes is a chain of dependent loads, and on this part a global load that misses L1 costs
@@ -1770,12 +1774,12 @@ __global__ void __launch_bounds__(32 * ENC_WARPS) encode_kernel(EncodeArgs A)
 
 // Record framing of one stream per warp (uniform control flow): sizes add up, no barrier records; counts what the
 // encoder can produce.
-__global__ void __launch_bounds__(128) walk_kernel(const uint8_t* __restrict__ wire, const EncInst* __restrict__ in, WalkOut* __restrict__ out,
+__global__ void __launch_bounds__(32 * WALK_WARPS) walk_kernel(const uint8_t* __restrict__ wire, const EncInst* __restrict__ in, WalkOut* __restrict__ out,
                                                    uint32_t n_inst)
 {
-  __shared__ __align__(16) uint32_t sh_win[4][WIN_BYTES / 4];
+  __shared__ __align__(16) uint32_t sh_win[WALK_WARPS][WIN_BYTES / 4];
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
-  const uint32_t idx = blockIdx.x * 4 + warp;
+  const uint32_t idx = blockIdx.x * WALK_WARPS + warp;
   if (idx >= n_inst)
     return;
   const EncInst wi = in[idx];
@@ -1981,7 +1985,7 @@ cudaError_t launch_walk(const uint8_t* wire, const EncInst* inst, WalkOut* out, 
 {
   if (n_inst == 0)
     return cudaSuccess;
-  walk_kernel<<<(n_inst + 3) / 4, 128, 0, st>>>(wire, inst, out, n_inst);
+  walk_kernel<<<(n_inst + WALK_WARPS - 1) / WALK_WARPS, 32 * WALK_WARPS, 0, st>>>(wire, inst, out, n_inst);
   return cudaGetLastError();
 }
 
