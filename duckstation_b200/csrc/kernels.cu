@@ -23,6 +23,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cstdlib>
 
 namespace psx {
@@ -1190,19 +1191,17 @@ cudaError_t launch_raster(const WaveItem* items, uint32_t n_items, const PrimSet
   }();
   if (loop_mode > 0 && n_items >= 16 && n_items * static_cast<uint64_t>(NUM_TILES) < 0xFFFF0000ull)
   {
-    static int sms = 0;
-    static uint32_t slot = 0;
-    static unsigned int* counters = nullptr;
-    if (sms == 0)
-    {
-      int dev = 0;
-      cudaGetDevice(&dev);
-      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-      void* sym = nullptr;
-      cudaGetSymbolAddress(&sym, g_raster_loop_counter);
-      counters = static_cast<unsigned int*>(sym);
-    }
-    slot = (slot + 1) % 64;
+    // (contexts may be driven from different host threads: the slot counter is atomic, device attributes are per call)
+    static std::atomic<uint32_t> next_slot{0};
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    void* sym = nullptr;
+    cudaError_t se = cudaGetSymbolAddress(&sym, g_raster_loop_counter);
+    if (se != cudaSuccess)
+      return se;
+    unsigned int* counters = static_cast<unsigned int*>(sym);
+    const uint32_t slot = next_slot.fetch_add(1) % 64u;
     cudaError_t e = cudaMemsetAsync(counters + slot, 0, sizeof(unsigned int), st);
     if (e != cudaSuccess)
       return e;
