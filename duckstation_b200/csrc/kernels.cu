@@ -316,21 +316,13 @@ __device__ __forceinline__ void raster_prim_on_region(const PrimSetup& s, uint32
   {
     case OP_TRIANGLE:
     {
-      const bool shaded = (st.flags & F_SHADED) != 0, textured = (st.flags & F_TEXTURE) != 0;
-      if (textured)
-      {
-        if (shaded)
-          raster_triangle<RH, kCoh, true, true>(s, st, ctx, region16, x_min, ry0, lane);
-        else
-          raster_triangle<RH, kCoh, false, true>(s, st, ctx, region16, x_min, ry0, lane);
-      }
+      // A flat triangle is a Gouraud triangle with zero gradients (setup gives it base = colour, ddx = ddy = 0), so two
+      // instantiations instead of four: the extra three multiply-adds per pixel cost less than the instruction-cache
+      // misses of the larger kernel (draw wave 19.0 -> 18.6 ms)
+      if (st.flags & F_TEXTURE)
+        raster_triangle<RH, kCoh, true, true>(s, st, ctx, region16, x_min, ry0, lane);
       else
-      {
-        if (shaded)
-          raster_triangle<RH, kCoh, true, false>(s, st, ctx, region16, x_min, ry0, lane);
-        else
-          raster_triangle<RH, kCoh, false, false>(s, st, ctx, region16, x_min, ry0, lane);
-      }
+        raster_triangle<RH, kCoh, true, false>(s, st, ctx, region16, x_min, ry0, lane);
     }
     break;
 
