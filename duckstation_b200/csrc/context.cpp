@@ -176,7 +176,7 @@ struct psxgpu_ctx
   {
     DevBuf d_cmds, d_setups, d_bins, d_payload, d_clutops, d_items, d_misc;
     // device-encoded chunks: d_payload holds the raw wire streams (upload pixels are read in place)
-    DevBuf d_recoff, d_inst, d_state, d_state_out, d_epochs, d_result, d_waves, d_cursor, d_summary, d_rects;
+    DevBuf d_recoff, d_rec, d_inst, d_state, d_state_out, d_epochs, d_result, d_waves, d_cursor, d_summary, d_rects;
     EncodeArgs enc_args{};
     bool device_encoded = false; // psxgpu_run_staged replays the encode kernels too (from the resident wire streams)
     cudaEvent_t ev_copied = nullptr, ev_walked = nullptr, ev_encoded = nullptr;
@@ -734,12 +734,15 @@ int stage_upload(psxgpu_ctx* ctx, PendingChunk& pc, uint32_t chunk_index, const 
   CK(P->state.ensure(static_cast<size_t>(cn) * sizeof(EncState)), "pinned alloc (encoder state)");
   EncInst* hi = static_cast<EncInst*>(P->inst.p);
   EncState* hs = static_cast<EncState*>(P->state.p);
+  uint64_t rec_cap = 0;
   for (uint32_t k = 0; k < cn; k++)
   {
     std::memset(&hi[k], 0, sizeof(EncInst));
     hi[k].instance = pc.first_instance + k;
     hi[k].wire_off = static_cast<uint32_t>(wire_off[k]);
     hi[k].wire_bytes = static_cast<uint32_t>(bytes[k]);
+    hi[k].rec_base = static_cast<uint32_t>(rec_cap);
+    rec_cap += bytes[k] / 8 + 2;
     const uint32_t inst = pc.first_instance + k;
     if (ctx->blob_truth[inst])
       hs[k] = ctx->enc_blob[inst];
@@ -776,6 +779,7 @@ int stage_upload(psxgpu_ctx* ctx, PendingChunk& pc, uint32_t chunk_index, const 
   CK(cudaStreamWaitEvent(ctx->copy_stream, S.ev_done, 0), "stream wait");
   CK(S.d_payload.ensure(wire_bytes), "device alloc (wire)");
   CK(S.d_recoff.ensure(static_cast<size_t>(cn) * sizeof(WalkOut)), "device alloc (framing)");
+  CK(S.d_rec.ensure(rec_cap * 4 + 16), "device alloc (record offsets)");
   CK(S.d_inst.ensure(static_cast<size_t>(cn) * sizeof(EncInst)), "device alloc (instances)");
   CK(S.d_state.ensure(static_cast<size_t>(cn) * sizeof(EncState)), "device alloc (encoder state)");
   if (ctx->trace)
@@ -817,7 +821,7 @@ int stage_upload(psxgpu_ctx* ctx, PendingChunk& pc, uint32_t chunk_index, const 
 
   CK(cudaStreamWaitEvent(ctx->walk_stream, S.ev_copied, 0), "stream wait");
   WalkOut* d_wo = static_cast<WalkOut*>(S.d_recoff.p);
-  CK(launch_walk(dw, static_cast<const EncInst*>(S.d_inst.p), d_wo, cn, ctx->walk_stream), "walk_kernel");
+  CK(launch_walk(dw, static_cast<const EncInst*>(S.d_inst.p), d_wo, static_cast<uint32_t*>(S.d_rec.p), cn, ctx->walk_stream), "walk_kernel");
   ctx->counters.kernel_launches++;
   CK(cudaMemcpyAsync(P->recoff.p, d_wo, static_cast<size_t>(cn) * sizeof(WalkOut), cudaMemcpyDeviceToHost, ctx->walk_stream), "D2H framing result");
   CK(cudaEventRecord(S.ev_walked, ctx->walk_stream), "event record");
@@ -877,6 +881,8 @@ int stage_encode(psxgpu_ctx* ctx, PendingChunk& pc)
   ctx->counters.kernel_launches++;
   EncodeArgs a{};
   a.wire = static_cast<const uint8_t*>(S.d_payload.p);
+  a.rec_off = static_cast<const uint32_t*>(S.d_rec.p);
+  a.walk = static_cast<const WalkOut*>(S.d_recoff.p);
   a.inst = static_cast<const EncInst*>(S.d_inst.p);
   a.n_inst = cn;
   a.clut_slots = ctx->clut_slots;
@@ -1304,7 +1310,7 @@ void psxgpu_destroy(psxgpu_ctx* ctx)
   }
   for (psxgpu_ctx::Chunk* ch : ctx->chunks)
   {
-    for (DevBuf* b : {&ch->d_cmds, &ch->d_setups, &ch->d_bins, &ch->d_payload, &ch->d_clutops, &ch->d_items, &ch->d_misc, &ch->d_recoff,
+    for (DevBuf* b : {&ch->d_cmds, &ch->d_setups, &ch->d_bins, &ch->d_payload, &ch->d_clutops, &ch->d_items, &ch->d_misc, &ch->d_recoff, &ch->d_rec,
                       &ch->d_inst, &ch->d_state, &ch->d_state_out, &ch->d_epochs, &ch->d_result, &ch->d_waves, &ch->d_cursor, &ch->d_summary, &ch->d_rects})
       b->release();
     for (cudaEvent_t ev : {ch->ev_copied, ch->ev_walked, ch->ev_encoded, ch->ev_done})

@@ -34,7 +34,8 @@ struct alignas(16) EncInst
   uint32_t cmd_base, cmd_cap;
   uint32_t clut_base, clut_cap;
   uint32_t epoch_base, epoch_cap;
-  uint32_t pad[3];
+  uint32_t rec_base;  // first entry of this stream in rec_off[] (capacity wire_bytes / 8 + 2: a record is >= 8 bytes)
+  uint32_t pad[2];
 };
 static_assert(sizeof(EncInst) == 48, "EncInst");
 
@@ -89,6 +90,8 @@ constexpr uint32_t ENC_WAVES_INLINE = 2048;
 struct EncodeArgs
 {
   const uint8_t* wire; // chunk wire buffer (instances back to back, 16-byte aligned, 256 bytes of slack at the end)
+  const uint32_t* rec_off; // byte offset of every record in `wire`, written by walk_kernel (see EncInst::rec_base)
+  const WalkOut* walk;     // per instance: number of records
   const EncInst* inst;
   uint32_t n_inst;
   uint32_t clut_slots;
@@ -109,7 +112,7 @@ struct EncodeArgs
 
 // walk: reads inst[].wire_off / wire_bytes.  layout: exclusive prefix sums of the capacities into inst[].*_base / *_cap
 // (the same sums the host makes from the read-back WalkOut to size the buffers).
-cudaError_t launch_walk(const uint8_t* wire, const EncInst* inst, WalkOut* out, uint32_t n_inst, cudaStream_t st);
+cudaError_t launch_walk(const uint8_t* wire, const EncInst* inst, WalkOut* out, uint32_t* rec_off, uint32_t n_inst, cudaStream_t st);
 cudaError_t launch_layout(const WalkOut* walk, EncInst* inst, uint32_t n_inst, cudaStream_t st);
 cudaError_t launch_encode(const EncodeArgs& a, cudaStream_t st);
 

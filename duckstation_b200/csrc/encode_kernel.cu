@@ -689,7 +689,6 @@ __global__ void __launch_bounds__(32 * ENC_WARPS) encode_kernel(EncodeArgs A)
   __shared__ uint32_t sh_last[ENC_WARPS][256];
   __shared__ unsigned long long sh_col[ENC_WARPS][32];
   __shared__ unsigned long long sh_col2[ENC_WARPS][32];
-  __shared__ __align__(16) uint32_t sh_win[ENC_WARPS][WIN_BYTES / 4];
   __shared__ uint8_t sh_quick[ENC_WARPS][64];
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
   const uint32_t idx = blockIdx.x * ENC_WARPS + warp;
@@ -1118,66 +1117,29 @@ __global__ void __launch_bounds__(32 * ENC_WARPS) encode_kernel(EncodeArgs A)
     FP_SELF = 4,
     FP_REJECTED = 8
   };
-  // The framing was checked by walk_kernel; here the warp just follows the sizes (uniform loads, mostly L1 hits: the
-  // records are contiguous) to find where the next 32 records start.
-  uint32_t pos = ii.wire_off, n_seen = 0;
-  const uint32_t wire_end = ii.wire_off + ii.wire_bytes;
-  StreamWindow win;
-  win.wire = A.wire;
-  win.smem = sh_win[warp];
-  win.limit = wire_end + 128u; // the chunk's wire buffer has 256 bytes of slack behind its last stream
-  win.lane = lane;
-  win.base = 0xFFFFFF00u;
-  while (pos < wire_end)
+  // The framing was checked by walk_kernel, which also left the byte offset of every record: lane i takes record
+  // base + i.
+  const uint32_t n_rec = A.walk[idx].n_rec;
+  const uint32_t* rec_off = A.rec_off + ii.rec_base;
+  uint32_t base = 0, n_seen = 0;
+  while (base < n_rec)
   {
-    uint32_t nb = 0, my_off = 0, my_size = 0, scan = pos;
-    for (uint32_t i = 0; i < 32; i++)
-    {
-      if (scan >= wire_end)
-        break;
-      const uint32_t sz = win.word(scan);
-      if (lane == i)
-      {
-        my_off = scan;
-        my_size = sz;
-      }
-      nb = i + 1;
-      scan += max(sz, 8u) & ~3u; // (cannot loop forever on a buffer that changed under us)
-      if (scan > win.base + WIN_BYTES && i >= 7)
-        break; // the next record starts outside the staged window: parse what we have first
-    }
+    uint32_t nb = min(32u, n_rec - base);
     const bool have = lane < nb;
+    const uint32_t my_off = have ? rec_off[base + lane] : 0u;
     uint32_t rw[24];
     {
-      const uint32_t at = my_off & ~15u;
-      if (have && win.holds(at, 96u))
-      {
-        const uint4* q = reinterpret_cast<const uint4*>(win.smem + ((at - win.base) >> 2));
+      const uint4* q = reinterpret_cast<const uint4*>(A.wire + (my_off & ~15u));
 #pragma unroll
-        for (int i = 0; i < 6; i++)
-        {
-          const uint4 v = q[i];
-          rw[4 * i + 0] = v.x;
-          rw[4 * i + 1] = v.y;
-          rw[4 * i + 2] = v.z;
-          rw[4 * i + 3] = v.w;
-        }
-      }
-      else
+      for (int i = 0; i < 6; i++)
       {
-        const uint4* q = reinterpret_cast<const uint4*>(A.wire + at);
-#pragma unroll
-        for (int i = 0; i < 6; i++)
-        {
-          const uint4 v = have ? __ldg(q + i) : make_uint4(0, 0, 0, 0);
-          rw[4 * i + 0] = v.x;
-          rw[4 * i + 1] = v.y;
-          rw[4 * i + 2] = v.z;
-          rw[4 * i + 3] = v.w;
-        }
+        const uint4 v = have ? __ldg(q + i) : make_uint4(0, 0, 0, 0); // the wire buffer has slack behind its last stream
+        rw[4 * i + 0] = v.x;
+        rw[4 * i + 1] = v.y;
+        rw[4 * i + 2] = v.z;
+        rw[4 * i + 3] = v.w;
       }
     }
-    const uint32_t rw_size = my_size;
     uint32_t cls = CLS_IGNORE, nprim = 0, hw0 = 0, hdm = 0, hwin = 0;
     uint32_t pv[2][8], pwr0[2], pwr1[2], prd0[2], prd1[2], pf[2];
 #pragma unroll
@@ -1454,12 +1416,8 @@ __global__ void __launch_bounds__(32 * ENC_WARPS) encode_kernel(EncodeArgs A)
     const uint32_t area_mask = __ballot_sync(FULL, cls == CLS_AREA);
     if (area_mask)
       nb = static_cast<uint32_t>(__ffs(static_cast<int>(area_mask)));
-    // where the next batch starts: behind record nb-1
-    {
-      const uint32_t last_off = __shfl_sync(FULL, my_off, nb - 1), last_size = __shfl_sync(FULL, rw_size, nb - 1);
-      pos = last_off + (max(last_size, 8u) & ~3u);
-      n_seen += nb;
-    }
+    base += nb;
+    n_seen += nb;
     const uint32_t summary = cls | (nprim << 4) | (pf[0] << 8) | (pf[1] << 16);
 
     // ---- Batch-parallel commit.  If bounding boxes alone prove that nothing in the batch can conflict — not with the
@@ -1775,7 +1733,7 @@ __global__ void __launch_bounds__(32 * ENC_WARPS) encode_kernel(EncodeArgs A)
 // Record framing of one stream per warp (uniform control flow): sizes add up, no barrier records; counts what the
 // encoder can produce.
 __global__ void __launch_bounds__(32 * WALK_WARPS) walk_kernel(const uint8_t* __restrict__ wire, const EncInst* __restrict__ in, WalkOut* __restrict__ out,
-                                                   uint32_t n_inst)
+                                                   uint32_t* __restrict__ rec_off, uint32_t n_inst)
 {
   __shared__ __align__(16) uint32_t sh_win[WALK_WARPS][WIN_BYTES / 4];
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
@@ -1844,6 +1802,8 @@ __global__ void __launch_bounds__(32 * WALK_WARPS) walk_kernel(const uint8_t* __
       case PSX_CMD_UPDATE_CLUT: r.clut_cap += 1; break;
       default: break;
     }
+    if (lane == 0)
+      rec_off[wi.rec_base + r.n_rec] = pos; // the encoder reads these 32 at a time instead of following sizes again
     r.n_rec++;
     pos += size;
   }
@@ -1981,11 +1941,11 @@ __global__ void __launch_bounds__(128) wave_fill_kernel(EncodeArgs A)
 
 } // namespace
 
-cudaError_t launch_walk(const uint8_t* wire, const EncInst* inst, WalkOut* out, uint32_t n_inst, cudaStream_t st)
+cudaError_t launch_walk(const uint8_t* wire, const EncInst* inst, WalkOut* out, uint32_t* rec_off, uint32_t n_inst, cudaStream_t st)
 {
   if (n_inst == 0)
     return cudaSuccess;
-  walk_kernel<<<(n_inst + WALK_WARPS - 1) / WALK_WARPS, 32 * WALK_WARPS, 0, st>>>(wire, inst, out, n_inst);
+  walk_kernel<<<(n_inst + WALK_WARPS - 1) / WALK_WARPS, 32 * WALK_WARPS, 0, st>>>(wire, inst, out, rec_off, n_inst);
   return cudaGetLastError();
 }
 
