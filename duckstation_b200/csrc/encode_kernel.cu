@@ -1730,8 +1730,9 @@ __global__ void __launch_bounds__(32 * ENC_WARPS) encode_kernel(EncodeArgs A)
   }
 }
 
-// Record framing of one stream per warp (uniform control flow): sizes add up, no barrier records; counts what the
-// encoder can produce.
+// Record framing of one stream per warp: sizes add up, no barrier records; counts what the encoder can produce and
+// notes where every record starts.  Only following the sizes is sequential (a short loop on shared-memory latency, 32
+// records at a time); classifying the 32 records, counting and storing their offsets is done one record per lane.
 __global__ void __launch_bounds__(32 * WALK_WARPS) walk_kernel(const uint8_t* __restrict__ wire, const EncInst* __restrict__ in, WalkOut* __restrict__ out,
                                                    uint32_t* __restrict__ rec_off, uint32_t n_inst)
 {
@@ -1741,6 +1742,7 @@ __global__ void __launch_bounds__(32 * WALK_WARPS) walk_kernel(const uint8_t* __
   if (idx >= n_inst)
     return;
   const EncInst wi = in[idx];
+  const uint32_t* w32 = reinterpret_cast<const uint32_t*>(wire);
   WalkOut r;
   r.n_rec = r.cmd_cap = r.clut_cap = 0;
   r.status = 0;
@@ -1754,58 +1756,90 @@ __global__ void __launch_bounds__(32 * WALK_WARPS) walk_kernel(const uint8_t* __
   win.base = 0xFFFFFF00u;
   while (pos < end)
   {
-    if (end - pos < 8u)
+    // -- follow up to 32 sizes --
+    uint32_t nb = 0, my_off = 0, my_size = 0, scan = pos;
+    int32_t chase_status = 0;
+    for (uint32_t i = 0; i < 32; i++)
     {
-      r.status = -3;
-      break;
+      if (scan >= end)
+        break;
+      if (end - scan < 8u)
+      {
+        chase_status = -3;
+        break;
+      }
+      const uint32_t sz = win.word(scan);
+      if (sz < 8u || (sz & 3u) != 0 || sz > end - scan)
+      {
+        chase_status = -3;
+        break;
+      }
+      if (lane == i)
+      {
+        my_off = scan;
+        my_size = sz;
+      }
+      nb = i + 1;
+      scan += sz;
     }
-    uint32_t size, type, w2;
-    if ((pos & 15u) == 0 && win.holds(pos, 16u))
+    // -- one record per lane --
+    const bool have = lane < nb;
+    uint32_t type = 0, w2 = 0;
+    if (have)
     {
-      const uint4 h = *reinterpret_cast<const uint4*>(win.smem + ((pos - win.base) >> 2)); // the usual case: one load
-      size = h.x;
-      type = h.y & 0xFFu;
-      w2 = h.z;
+      if (win.holds(my_off, 12u))
+      {
+        type = win.smem[(my_off + 4u - win.base) >> 2] & 0xFFu;
+        w2 = win.smem[(my_off + 8u - win.base) >> 2];
+      }
+      else
+      {
+        type = __ldg(w32 + (my_off >> 2) + 1) & 0xFFu;
+        w2 = (my_size >= 12u) ? __ldg(w32 + (my_off >> 2) + 2) : 0u;
+      }
     }
-    else
+    const bool barrier =
+      have && (type == PSX_CMD_CLEAR_VRAM || type == PSX_CMD_LOAD_STATE || type == PSX_CMD_READ_VRAM || type == PSX_CMD_UPDATE_DISPLAY);
+    const uint32_t barrier_mask = __ballot_sync(FULL, barrier);
+    const uint32_t counted = barrier_mask ? (static_cast<uint32_t>(__ffs(static_cast<int>(barrier_mask))) - 1u) : nb; // stop in front of a barrier
+    uint32_t cmd_inc = 0, clut_inc = 0;
+    if (lane < counted)
     {
-      size = win.word(pos);
-      type = win.word(pos + 4) & 0xFFu;
-      w2 = (end - pos >= 12u) ? win.word(pos + 8) : 0u;
+      switch (type)
+      {
+        case PSX_CMD_DRAW_POLYGON:
+        case PSX_CMD_DRAW_PRECISE_POLYGON:
+          if (my_size >= 20u)
+            cmd_inc = ((w2 >> 16) > 3u) ? 2u : 1u;
+          break;
+        case PSX_CMD_DRAW_LINE:
+        case PSX_CMD_DRAW_PRECISE_LINE:
+          if (my_size >= 20u)
+            cmd_inc = (w2 >> 16) / 2u;
+          break;
+        case PSX_CMD_DRAW_RECTANGLE:
+        case PSX_CMD_FILL_VRAM:
+        case PSX_CMD_COPY_VRAM:
+        case PSX_CMD_UPDATE_VRAM: cmd_inc = 1; break;
+        case PSX_CMD_UPDATE_CLUT: clut_inc = 1; break;
+        default: break;
+      }
+      rec_off[wi.rec_base + r.n_rec + lane] = my_off; // the encoder reads these 32 at a time
     }
-    if (size < 8u || (size & 3u) != 0 || size > end - pos)
-    {
-      r.status = -3;
-      break;
-    }
-    if (type == PSX_CMD_CLEAR_VRAM || type == PSX_CMD_LOAD_STATE || type == PSX_CMD_READ_VRAM || type == PSX_CMD_UPDATE_DISPLAY)
+    r.cmd_cap += __reduce_add_sync(FULL, cmd_inc);
+    r.clut_cap += __reduce_add_sync(FULL, clut_inc);
+    r.n_rec += counted;
+    if (barrier_mask)
     {
       r.status = -5;
       break;
     }
-    switch (type)
+    if (chase_status)
     {
-      case PSX_CMD_DRAW_POLYGON:
-      case PSX_CMD_DRAW_PRECISE_POLYGON:
-        if (size >= 20u)
-          r.cmd_cap += ((w2 >> 16) > 3u) ? 2u : 1u;
-        break;
-      case PSX_CMD_DRAW_LINE:
-      case PSX_CMD_DRAW_PRECISE_LINE:
-        if (size >= 20u)
-          r.cmd_cap += (w2 >> 16) / 2u;
-        break;
-      case PSX_CMD_DRAW_RECTANGLE:
-      case PSX_CMD_FILL_VRAM:
-      case PSX_CMD_COPY_VRAM:
-      case PSX_CMD_UPDATE_VRAM: r.cmd_cap += 1; break;
-      case PSX_CMD_UPDATE_CLUT: r.clut_cap += 1; break;
-      default: break;
+      r.status = chase_status;
+      break;
     }
-    if (lane == 0)
-      rec_off[wi.rec_base + r.n_rec] = pos; // the encoder reads these 32 at a time instead of following sizes again
-    r.n_rec++;
-    pos += size;
+    pos = scan;
   }
   if (lane == 0)
     out[idx] = r;
