@@ -148,19 +148,38 @@ __device__ __forceinline__ uint32_t warp_inclusive_scan(uint32_t v, uint32_t lan
   return v;
 }
 
-// Given the inclusive prefix sums of per-row pixel counts (one row per lane), the row that owns compacted pixel j:
-// the first lane whose inclusive sum exceeds j.  Warp-wide binary search with shuffles; j < total required.
-__device__ __forceinline__ uint32_t row_of_pixel(uint32_t incl, uint32_t j)
+// Which row lane owns compacted pixel base + lane?  Row lane r starts at compacted index start_r (rows without pixels
+// carry ROW_EMPTY).  Rows that start inside this batch of 32 leave a mark at their first pixel's lane (one REDUX.OR);
+// rows that started at or before `base` are counted with a ballot; the sum is the pixel's ordinal among the rows that
+// have pixels, and `rowmap` (lane k = the k-th such row, see row_lane_map) turns the ordinal into the row lane.
+constexpr uint32_t ROW_EMPTY = 0x40000000u;
+__device__ __forceinline__ uint32_t row_of_pixel(uint32_t start, uint32_t base, uint32_t rowmap, uint32_t lane)
 {
-  uint32_t r = 0;
+  const uint32_t t = start - base;
+  const uint32_t marks = __reduce_or_sync(0xFFFFFFFFu, ((t - 1u) < 31u) ? (1u << t) : 0u);
+  const uint32_t before = __popc(__ballot_sync(0xFFFFFFFFu, static_cast<int32_t>(t) <= 0));
+  const uint32_t k = before - 1u + __popc(marks & ((2u << lane) - 1u));
+  return __shfl_sync(0xFFFFFFFFu, rowmap, k);
+}
+// lane k -> the row lane of the k-th set bit of `rows` (rows with pixels); usually one contiguous run.
+__device__ __forceinline__ uint32_t row_lane_map(uint32_t rows, uint32_t lane)
+{
+  const uint32_t first = static_cast<uint32_t>(__ffs(static_cast<int>(rows))) - 1u;
+  const uint32_t run = rows >> first;
+  if ((run & (run + 1u)) == 0)
+    return first + lane;
+  uint32_t pos = 0, rem = lane;
 #pragma unroll
   for (uint32_t step = 16; step >= 1; step >>= 1)
   {
-    const uint32_t v = __shfl_sync(0xFFFFFFFFu, incl, r + step - 1);
-    if (v <= j)
-      r += step;
+    const uint32_t c = __popc(rows & (((1u << step) - 1u) << pos));
+    if (rem >= c)
+    {
+      pos += step;
+      rem -= c;
+    }
   }
-  return r & 31u;
+  return pos & 31u;
 }
 
 // Triangle on one tile.  Lane r works out the span of tile row r (one pass for all 32 rows); the covered pixels of all
@@ -174,10 +193,13 @@ __device__ __forceinline__ void raster_triangle(const PrimSetup& s, const ShadeS
   const bool valid = (RH == 32 || lane < RH) && tri_row(s, ry0 + lane, row);
   const int32_t xs = valid ? imax(row.x_lo, x_min) : 0, xe = valid ? imin(row.x_hi, x_min + static_cast<int32_t>(TILE_W)) : 0;
   const uint32_t cnt = (xe > xs) ? static_cast<uint32_t>(xe - xs) : 0u;
+  const uint32_t rows = __ballot_sync(0xFFFFFFFFu, cnt != 0);
+  if (rows == 0)
+    return;
   const uint32_t incl = warp_inclusive_scan(cnt, lane);
   const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
-  if (total == 0)
-    return;
+  const uint32_t start = cnt ? (incl - cnt) : ROW_EMPTY;
+  const uint32_t rowmap = row_lane_map(rows, lane);
   const auto& T = s.tri;
   // px = xoff + j ; x_raw = px + xdelta (xdelta is a multiple of 2048 that fits 16 bits, xoff is within +-2048)
   const uint32_t packed = (static_cast<uint32_t>(xs - static_cast<int32_t>(incl - cnt)) & 0xFFFFu) | (static_cast<uint32_t>(row.xdelta) << 16);
@@ -208,7 +230,7 @@ __device__ __forceinline__ void raster_triangle(const PrimSetup& s, const ShadeS
   {
     const uint32_t j = base + lane;
     const bool active = j < total;
-    const uint32_t r = row_of_pixel(incl, active ? j : 0u);
+    const uint32_t r = row_of_pixel(start, base, rowmap, lane);
     const uint32_t pk = __shfl_sync(0xFFFFFFFFu, packed, r);
     const int32_t px = static_cast<int32_t>(static_cast<int16_t>(pk & 0xFFFFu)) + static_cast<int32_t>(j);
     const uint32_t xr = static_cast<uint32_t>(px + (static_cast<int32_t>(pk) >> 16));
@@ -249,10 +271,13 @@ __device__ __forceinline__ void raster_rect(const PrimSetup& s, const ShadeState
   const bool valid = (RH == 32 || lane < RH) && rect_row(s, ry0 + lane, row);
   const int32_t xs = valid ? imax(row.x_lo, x_min) : 0, xe = valid ? imin(row.x_hi, x_min + static_cast<int32_t>(TILE_W)) : 0;
   const uint32_t cnt = (xe > xs) ? static_cast<uint32_t>(xe - xs) : 0u;
+  const uint32_t rows = __ballot_sync(0xFFFFFFFFu, cnt != 0);
+  if (rows == 0)
+    return;
   const uint32_t incl = warp_inclusive_scan(cnt, lane);
   const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
-  if (total == 0)
-    return;
+  const uint32_t start = cnt ? (incl - cnt) : ROW_EMPTY;
+  const uint32_t rowmap = row_lane_map(rows, lane);
   const uint32_t packed = (static_cast<uint32_t>(xs - static_cast<int32_t>(incl - cnt)) & 0xFFFFu) | (row.v << 16);
   const uint32_t cr = s.rect.r, cg = s.rect.g, cb = s.rect.b;
   const uint32_t ubias = static_cast<uint32_t>(s.rect.u0) - static_cast<uint32_t>(static_cast<int32_t>(s.rect.x));
@@ -260,7 +285,7 @@ __device__ __forceinline__ void raster_rect(const PrimSetup& s, const ShadeState
   {
     const uint32_t j = base + lane;
     const bool active = j < total;
-    const uint32_t r = row_of_pixel(incl, active ? j : 0u);
+    const uint32_t r = row_of_pixel(start, base, rowmap, lane);
     const uint32_t pk = __shfl_sync(0xFFFFFFFFu, packed, r);
     const int32_t px = static_cast<int32_t>(static_cast<int16_t>(pk & 0xFFFFu)) + static_cast<int32_t>(j);
     if (active)
@@ -1198,7 +1223,7 @@ cudaError_t launch_raster(const WaveItem* items, uint32_t n_items, const PrimSet
     if (e != cudaSuccess)
       return e;
     const uint32_t total = n_items * NUM_TILES;
-    const uint32_t ctas = std::min<uint32_t>(static_cast<uint32_t>(sms) * 32u, total / 2u + 1u);
+    const uint32_t ctas = std::min<uint32_t>(static_cast<uint32_t>(sms) * PSX_RASTER_MIN_CTAS, total / 2u + 1u);
     raster_loop_kernel<<<ctas, 32, 0, st>>>(items, n_items, setups, bins, vram_pool, clut_pool, payload, clut_slots, slot);
     return cudaGetLastError();
   }
