@@ -76,6 +76,10 @@ def load() -> C.CDLL:
     lib.psxgpu_save_state.argtypes = [P, u32, C.c_void_p, C.c_void_p]
     lib.psxgpu_scanout.argtypes = [P, u32, C.c_void_p, C.c_void_p, u32, C.POINTER(u32), C.POINTER(u32)]
     lib.psxgpu_display.argtypes = [P, C.POINTER(u32), C.POINTER(u32), C.POINTER(u32), C.POINTER(u32)]
+    lib.psxgpu_presenter_create.argtypes = [P, u32, u32, C.POINTER(C.c_void_p)]
+    lib.psxgpu_presenter_destroy.argtypes = [C.c_void_p]
+    lib.psxgpu_presenter_destroy.restype = None
+    lib.psxgpu_present.argtypes = [C.c_void_p, u32, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(u32), C.POINTER(u32)]
     lib.psxgpu_display.restype = C.c_void_p
     lib.psxgpu_hash.argtypes = [P, u32, u32, u64p]
     lib.psxgpu_hash_device.argtypes = [P, u32, u32, C.c_void_p]
@@ -104,7 +108,8 @@ def load() -> C.CDLL:
     for name in ("psxgpu_create", "psxgpu_submit_wire", "psxgpu_submit_batch", "psxgpu_flush", "psxgpu_sync",
                  "psxgpu_run_staged", "psxgpu_set_batch_chunk", "psxgpu_read_vram", "psxgpu_clear_vram", "psxgpu_load_state",
                  "psxgpu_save_state", "psxgpu_scanout", "psxgpu_hash", "psxgpu_hash_device", "psxgpu_get_stats",
-                 "psxgpu_reset_stats", "psxgpu_get_timing", "psxgpu_get_raster_launch_ms"):
+                 "psxgpu_reset_stats", "psxgpu_get_timing", "psxgpu_get_raster_launch_ms", "psxgpu_presenter_create",
+                 "psxgpu_present"):
         getattr(lib, name).restype = C.c_int
     _lib = lib
     return lib
@@ -119,4 +124,5 @@ EXPORTS = (
     "psxgpu_frontend_create", "psxgpu_frontend_destroy", "psxgpu_frontend_gp0", "psxgpu_frontend_gp1",
     "psxgpu_frontend_vsync", "psxgpu_frontend_finish_read", "psxgpu_frontend_records", "psxgpu_frontend_clear",
     "psxgpu_frontend_get_stats", "psxgpu_frontend_feed_dump", "psxgpu_replay_dump",
+    "psxgpu_presenter_create", "psxgpu_presenter_destroy", "psxgpu_present",
 )

@@ -49,7 +49,7 @@ def _nvcc() -> str:
 
 def build_product(force: bool = False) -> str:
     out = os.path.join(ROOT, "duckstation_b200", "libpsxgpu.so")
-    srcs = [os.path.join(CSRC, f) for f in ("kernels.cu", "encode_kernel.cu", "context.cpp", "encoder.cpp", "backend.cpp", "gp0_frontend.cpp")]
+    srcs = [os.path.join(CSRC, f) for f in ("kernels.cu", "encode_kernel.cu", "presenter.cu", "context.cpp", "encoder.cpp", "backend.cpp", "gp0_frontend.cpp")]
     deps = srcs + [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [
         os.path.join(ROOT, "include", "psxgpu.h"), os.path.join(ROOT, "include", "psxgpu_wire.h")]
     if force or _newer(out, deps):

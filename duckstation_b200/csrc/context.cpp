@@ -1704,6 +1704,245 @@ int psxgpu_scanout(psxgpu_ctx* ctx, uint32_t instance, const psx_update_display*
   return do_scanout(ctx, instance, cmd, dst, dst_stride, out_width, out_height, nullptr);
 }
 
+// ---- presenter: GPU_SW::UpdateDisplay with the VideoPresenter steps (gpu_sw.cpp:386-441) ----
+struct psxgpu_presenter
+{
+  psxgpu_ctx* ctx = nullptr;
+  uint32_t mode = PSXGPU_DEINT_DISABLED;
+  bool chroma = false;
+  // s_locals.display_texture / display_texture_rect: what is shown (points at one of the buffers below, or nothing)
+  const uint32_t* shown = nullptr;
+  uint32_t shown_w = 0, shown_h = 0;
+  DevBuf scan, smooth, target;           // m_upload_texture, chroma_smoothing_texture, deinterlace_texture
+  uint32_t target_w = 0, target_h = 0;
+  DevBuf field_buf[4];                   // deinterlace_buffers
+  uint32_t field_w[4] = {0, 0, 0, 0}, field_h[4] = {0, 0, 0, 0};
+  bool field_live[4] = {false, false, false, false};
+  uint32_t current = 0;                  // current_deinterlace_buffer
+};
+
+namespace {
+
+PresentField field_of(const psxgpu_presenter* p, uint32_t i)
+{
+  if (!p->field_live[i])
+    return PresentField{nullptr, 0, 0};
+  return PresentField{static_cast<const uint32_t*>(p->field_buf[i].p), p->field_w[i], p->field_h[i]};
+}
+
+// DeinterlaceSetTargetSize (video_presenter.cpp:1373-1383): a resize with preserve keeps the overlapping part, a new
+// texture starts out cleared.
+int present_target_size(psxgpu_presenter* p, uint32_t w, uint32_t h, bool preserve)
+{
+  psxgpu_ctx* ctx = p->ctx;
+  if (p->target.p && p->target_w == w && p->target_h == h)
+    return PSXGPU_OK;
+  DevBuf fresh;
+  CK(fresh.ensure(static_cast<size_t>(w) * h * 4), "device alloc (deinterlace target)");
+  CK(cudaMemsetAsync(fresh.p, 0, static_cast<size_t>(w) * h * 4, ctx->stream), "clear deinterlace target");
+  if (preserve && p->target.p && p->target_w && p->target_h)
+    CK(cudaMemcpy2DAsync(fresh.p, static_cast<size_t>(w) * 4, p->target.p, static_cast<size_t>(p->target_w) * 4,
+                         static_cast<size_t>(std::min(w, p->target_w)) * 4, std::min(h, p->target_h), cudaMemcpyDeviceToDevice,
+                         ctx->stream),
+       "preserve deinterlace target");
+  CK(cudaStreamSynchronize(ctx->stream), "stream sync");
+  p->target.release();
+  p->target = fresh;
+  p->target_w = w;
+  p->target_h = h;
+  return PSXGPU_OK;
+}
+
+// VideoPresenter::Deinterlace (video_presenter.cpp:1208-1371).  p->shown is the field just scanned out, or nullptr
+// after ClearDisplayTexture.
+int present_deinterlace(psxgpu_presenter* p, uint32_t field)
+{
+  psxgpu_ctx* ctx = p->ctx;
+  const uint32_t* src = p->shown;
+  const uint32_t w = p->shown_w, h = p->shown_h;
+  auto copy_to_field_buffer = [&](uint32_t b) -> int {
+    CK(p->field_buf[b].ensure(static_cast<size_t>(w) * h * 4), "device alloc (field buffer)");
+    CK(cudaMemcpyAsync(p->field_buf[b].p, src, static_cast<size_t>(w) * h * 4, cudaMemcpyDeviceToDevice, ctx->stream), "field copy");
+    p->field_w[b] = w;
+    p->field_h[b] = h;
+    p->field_live[b] = true;
+    return PSXGPU_OK;
+  };
+  switch (p->mode)
+  {
+    case PSXGPU_DEINT_WEAVE:
+    {
+      if (src)
+      {
+        int rc = present_target_size(p, w, h * 2, true);
+        if (rc != PSXGPU_OK)
+          return rc;
+      }
+      else if (!p->target.p)
+        return PSXGPU_OK;
+      CK(launch_weave(PresentField{src, w, h}, field, static_cast<uint32_t*>(p->target.p), p->target_w, p->target_h, ctx->stream), "weave_kernel");
+      ctx->counters.kernel_launches++;
+    }
+    break;
+    case PSXGPU_DEINT_BLEND:
+    {
+      const uint32_t cur = p->current;
+      p->current = (p->current + 1u) % 2u;
+      if (src)
+      {
+        int rc = present_target_size(p, w, h, false);
+        if (rc == PSXGPU_OK)
+          rc = copy_to_field_buffer(cur);
+        if (rc != PSXGPU_OK)
+          return rc;
+      }
+      else
+      {
+        if (!p->target.p)
+          return PSXGPU_OK;
+        p->field_live[cur] = false; // recycled: samples black
+      }
+      CK(launch_blend(field_of(p, cur), field_of(p, (cur - 1u) % 2u), static_cast<uint32_t*>(p->target.p), p->target_w, p->target_h, ctx->stream),
+         "blend_kernel");
+      ctx->counters.kernel_launches++;
+    }
+    break;
+    case PSXGPU_DEINT_ADAPTIVE:
+    {
+      const uint32_t cur = p->current;
+      p->current = (p->current + 1u) % 4u;
+      if (src)
+      {
+        int rc = present_target_size(p, w, h * 2, false);
+        if (rc == PSXGPU_OK)
+          rc = copy_to_field_buffer(cur);
+        if (rc != PSXGPU_OK)
+          return rc;
+      }
+      else
+      {
+        if (!p->target.p)
+          return PSXGPU_OK;
+        p->field_live[cur] = false;
+      }
+      const PresentField f[4] = {field_of(p, cur), field_of(p, (cur - 1u) % 4u), field_of(p, (cur - 2u) % 4u), field_of(p, (cur - 3u) % 4u)};
+      CK(launch_adaptive(f, field, static_cast<uint32_t*>(p->target.p), p->target_w, p->target_h, ctx->stream), "adaptive_kernel");
+      ctx->counters.kernel_launches++;
+    }
+    break;
+    default: return PSXGPU_OK; // Disabled (and Progressive, which never produces interlaced frames): show the field
+  }
+  p->shown = static_cast<const uint32_t*>(p->target.p);
+  p->shown_w = p->target_w;
+  p->shown_h = p->target_h;
+  return PSXGPU_OK;
+}
+
+// VideoPresenter::ApplyChromaSmoothing (video_presenter.cpp:1385-1413)
+int present_chroma(psxgpu_presenter* p)
+{
+  psxgpu_ctx* ctx = p->ctx;
+  if (!p->shown || p->shown_w == 0 || p->shown_h == 0)
+    return PSXGPU_OK;
+  CK(p->smooth.ensure(static_cast<size_t>(p->shown_w) * p->shown_h * 4), "device alloc (chroma smoothing)");
+  CK(launch_chroma_smoothing(PresentField{p->shown, p->shown_w, p->shown_h}, static_cast<uint32_t*>(p->smooth.p), ctx->stream), "chroma_kernel");
+  ctx->counters.kernel_launches++;
+  p->shown = static_cast<const uint32_t*>(p->smooth.p);
+  return PSXGPU_OK;
+}
+
+} // namespace
+
+int psxgpu_presenter_create(psxgpu_ctx* ctx, uint32_t deinterlace_mode, uint32_t chroma_smoothing, psxgpu_presenter** out)
+{
+  if (!ctx || !out || deinterlace_mode > PSXGPU_DEINT_PROGRESSIVE)
+    return ctx ? ctx->invalid("presenter_create: bad arguments") : PSXGPU_E_INVALID;
+  psxgpu_presenter* p = new (std::nothrow) psxgpu_presenter();
+  if (!p)
+    return PSXGPU_E_NOMEM;
+  p->ctx = ctx;
+  p->mode = deinterlace_mode;
+  p->chroma = chroma_smoothing != 0;
+  *out = p;
+  return PSXGPU_OK;
+}
+
+void psxgpu_presenter_destroy(psxgpu_presenter* p)
+{
+  if (!p)
+    return;
+  cudaSetDevice(p->ctx->device);
+  cudaStreamSynchronize(p->ctx->stream);
+  p->scan.release();
+  p->smooth.release();
+  p->target.release();
+  for (DevBuf& b : p->field_buf)
+    b.release();
+  delete p;
+}
+
+int psxgpu_present(psxgpu_presenter* p, uint32_t instance, const psx_update_display* cmd, void* dst, size_t dst_bytes,
+                   uint32_t* out_width, uint32_t* out_height)
+{
+  if (!p || !cmd || instance >= p->ctx->n)
+    return p ? p->ctx->invalid("present: bad arguments") : PSXGPU_E_INVALID;
+  psxgpu_ctx* ctx = p->ctx;
+  cudaSetDevice(ctx->device);
+  ScanoutParams sp;
+  bool disabled;
+  scanout_params(ctx, cmd, sp, disabled);
+  const uint32_t field = (cmd->flags & PSX_UD_INTERLACED_FIELD) ? 1u : 0u;
+  const bool interlaced = (cmd->flags & PSX_UD_INTERLACED_ENABLED) != 0 && !ctx->opts.show_vram;
+  int rc = do_flush(ctx);
+  if (rc != PSXGPU_OK)
+    return rc;
+  if (disabled)
+  {
+    p->shown = nullptr; // ClearDisplayTexture
+    p->shown_w = p->shown_h = 0;
+    if (interlaced)
+      rc = present_deinterlace(p, field);
+  }
+  else
+  {
+    if (sp.width > 4096 || sp.height > 4096)
+      return ctx->invalid("scan-out size out of range");
+    sp.format = PSXGPU_FMT_RGBA8; // the presenter's shaders are defined on the RGBA8 display texture
+    sp.out_stride = sp.width * 4;
+    p->shown = nullptr;
+    p->shown_w = p->shown_h = 0;
+    if (sp.width && sp.height)
+    {
+      CK(p->scan.ensure(static_cast<size_t>(sp.out_stride) * sp.height), "device alloc (scan-out)");
+      CK(launch_scanout(inst_vram(ctx, instance), sp, static_cast<uint8_t*>(p->scan.p), ctx->stream), "scanout_kernel");
+      ctx->counters.kernel_launches++;
+      p->shown = static_cast<const uint32_t*>(p->scan.p);
+      p->shown_w = sp.width;
+      p->shown_h = sp.height;
+      if (sp.is24 && p->chroma && !ctx->opts.show_vram)
+        rc = present_chroma(p);
+      if (rc == PSXGPU_OK && interlaced)
+        rc = present_deinterlace(p, field);
+    }
+  }
+  if (rc != PSXGPU_OK)
+    return rc;
+  if (out_width)
+    *out_width = p->shown_w;
+  if (out_height)
+    *out_height = p->shown_h;
+  const size_t bytes = static_cast<size_t>(p->shown_w) * p->shown_h * 4;
+  if (bytes && dst)
+  {
+    if (dst_bytes < bytes)
+      return ctx->invalid("present: destination too small");
+    CK(cudaMemcpyAsync(dst, p->shown, bytes, cudaMemcpyDeviceToHost, ctx->stream), "D2H presented frame");
+    ctx->counters.d2h_bytes += bytes;
+  }
+  CK(cudaStreamSynchronize(ctx->stream), "stream sync");
+  return p->shown ? PSXGPU_OK : 1;
+}
+
 const void* psxgpu_display(psxgpu_ctx* ctx, uint32_t* width, uint32_t* height, uint32_t* stride, uint32_t* is_rgba8)
 {
   if (!ctx)

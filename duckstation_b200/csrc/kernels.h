@@ -38,4 +38,16 @@ cudaError_t launch_persistent(const WaveItem* items, const void* waves, uint32_t
 cudaError_t launch_hash(const uint16_t* vram_pool, uint32_t first, uint32_t count, unsigned long long* out, cudaStream_t st);
 cudaError_t launch_scanout(const uint16_t* vram, const ScanoutParams& p, uint8_t* out, cudaStream_t st);
 
+// presenter.cu: the presentation steps after scan-out, on tightly packed RGBA8 frames in device memory.
+struct PresentField
+{
+  const uint32_t* pixels; // nullptr: samples as zero (a field buffer that was never written / a cleared display)
+  uint32_t width, height;
+};
+cudaError_t launch_weave(const PresentField& src, uint32_t field, uint32_t* target, uint32_t width, uint32_t full_height, cudaStream_t st);
+cudaError_t launch_blend(const PresentField& cur, const PresentField& prev, uint32_t* target, uint32_t width, uint32_t height, cudaStream_t st);
+// f[0] = this field, f[1..3] = one, two and three fields back
+cudaError_t launch_adaptive(const PresentField f[4], uint32_t field, uint32_t* target, uint32_t width, uint32_t full_height, cudaStream_t st);
+cudaError_t launch_chroma_smoothing(const PresentField& src, uint32_t* out, cudaStream_t st);
+
 } // namespace psx

@@ -141,6 +141,26 @@ int psxgpu_scanout(psxgpu_ctx* ctx, uint32_t instance, const psx_update_display*
 /* Result of the last UpdateDisplay record seen by psxgpu_submit_wire. */
 const void* psxgpu_display(psxgpu_ctx* ctx, uint32_t* width, uint32_t* height, uint32_t* stride, uint32_t* is_rgba8);
 
+/* ---- presenter ------------------------------------------------------------------------------
+ * GPU_SW::UpdateDisplay including the steps it hands to VideoPresenter (gpu_sw.cpp:386-441): scan-out, then
+ * ApplyChromaSmoothing on 24-bit frames when enabled (video_presenter.cpp:1385-1413), then Deinterlace(field) on
+ * interlaced display (video_presenter.cpp:1208-1371).  The reference runs these as fragment shaders
+ * (video_shadergen.cpp:166-330); here they are CUDA kernels on RGBA8 frames that never leave the device in between.
+ * The object owns what the reference keeps in VideoPresenter's statics: the deinterlace target, up to four field
+ * buffers and the current-buffer index.  Parity status: pinned by our reading of the shader text. */
+typedef struct psxgpu_presenter psxgpu_presenter;
+enum { /* DisplayDeinterlacingMode, src/core/types.h:81-89 */
+  PSXGPU_DEINT_DISABLED = 0, PSXGPU_DEINT_WEAVE = 1, PSXGPU_DEINT_BLEND = 2, PSXGPU_DEINT_ADAPTIVE = 3,
+  PSXGPU_DEINT_PROGRESSIVE = 4
+};
+int psxgpu_presenter_create(psxgpu_ctx* ctx, uint32_t deinterlace_mode, uint32_t chroma_smoothing, psxgpu_presenter** out);
+void psxgpu_presenter_destroy(psxgpu_presenter* p);
+/* One UpdateDisplay: the frame that would be shown, tightly packed RGBA8, into dst (host).  Returns 0, 1 if nothing
+ * is shown (display disabled and no deinterlaced frame to keep), or a negative PSXGPU_E_* code.  The frame is always
+ * scanned out as RGBA8, whatever psxgpu_opts.display_format says. */
+int psxgpu_present(psxgpu_presenter* p, uint32_t instance, const psx_update_display* cmd, void* dst, size_t dst_bytes,
+                   uint32_t* out_width, uint32_t* out_height);
+
 /* vramhash64 of instances [first, first+count): sum over 32-bit words i of mix64((i<<32)|word) (include
  * psxgpu_hash.h semantics in DESIGN.md §7).  Flushes and waits. */
 int psxgpu_hash(psxgpu_ctx* ctx, uint32_t first_instance, uint32_t count, uint64_t* out_host);
