@@ -174,7 +174,7 @@ struct psxgpu_ctx
   // overlaps the copy + kernels of chunk k); psxgpu_run_staged replays the last closed group.
   struct Chunk
   {
-    DevBuf d_cmds, d_setups, d_bins, d_payload, d_clutops, d_items, d_misc;
+    DevBuf d_cmds, d_setups, d_bins, d_tilecmds, d_payload, d_clutops, d_items, d_misc;
     // device-encoded chunks: d_payload holds the raw wire streams (upload pixels are read in place)
     DevBuf d_recoff, d_rec, d_inst, d_state, d_state_out, d_epochs, d_result, d_waves, d_cursor, d_summary, d_rects;
     EncodeArgs enc_args{};
@@ -294,7 +294,7 @@ int collect_timing(psxgpu_ctx* ctx)
 int run_chunk(psxgpu_ctx* ctx, psxgpu_ctx::Chunk& S)
 {
   CK(launch_setup(static_cast<const PackedCmd*>(S.d_cmds.p), static_cast<PrimSetup*>(S.d_setups.p),
-                  static_cast<BinInfo*>(S.d_bins.p), S.n_cmds, ctx->stream),
+                  static_cast<BinInfo*>(S.d_bins.p), static_cast<uint32_t*>(S.d_tilecmds.p), S.n_cmds, ctx->stream),
      "setup_kernel");
   if (S.n_cmds)
     ctx->counters.kernel_launches++;
@@ -311,7 +311,7 @@ int run_chunk(psxgpu_ctx* ctx, psxgpu_ctx::Chunk& S)
     const uint8_t* misc = static_cast<const uint8_t*>(S.d_misc.p);
     CK(launch_persistent(static_cast<const WaveItem*>(S.d_items.p), misc, waves,
                          reinterpret_cast<const uint32_t*>(misc + static_cast<size_t>(waves) * 16), S.n_instances,
-                         static_cast<const PrimSetup*>(S.d_setups.p), static_cast<const BinInfo*>(S.d_bins.p),
+                         static_cast<const PrimSetup*>(S.d_setups.p), static_cast<const uint32_t*>(S.d_tilecmds.p),
                          static_cast<const ClutOp*>(S.d_clutops.p), ctx->d_vram, ctx->d_clut,
                          static_cast<const uint16_t*>(S.d_payload.p), ctx->clut_slots, ctx->d_barrier, ctx->stream),
        "raster_persistent_kernel");
@@ -346,7 +346,7 @@ int run_chunk(psxgpu_ctx* ctx, psxgpu_ctx::Chunk& S)
       CK(cudaEventRecord(S.ev_raster[S.ev_raster_used++], ctx->stream), "event record");
     if (S.wave_has_tiled[k])
     {
-      CK(launch_raster(items + off, cnt, static_cast<const PrimSetup*>(S.d_setups.p), static_cast<const BinInfo*>(S.d_bins.p),
+      CK(launch_raster(items + off, cnt, static_cast<const PrimSetup*>(S.d_setups.p), static_cast<const uint32_t*>(S.d_tilecmds.p),
                        ctx->d_vram, ctx->d_clut, static_cast<const uint16_t*>(S.d_payload.p), ctx->clut_slots, ctx->stream),
          "raster_kernel");
       ctx->counters.kernel_launches += (cnt + 32767) / 32768;
@@ -475,6 +475,7 @@ int launch_chunk_impl(psxgpu_ctx* ctx, const std::vector<uint32_t>& work, const 
   CK(S.d_cmds.ensure(n_cmds * sizeof(PackedCmd)), "device alloc (commands)");
   CK(S.d_setups.ensure(n_cmds * sizeof(PrimSetup)), "device alloc (setup records)");
   CK(S.d_bins.ensure(n_cmds * sizeof(BinInfo) + 64), "device alloc (bins)");
+  CK(S.d_tilecmds.ensure(tile_cmds_bytes(n_cmds)), "device alloc (tile command bitmaps)");
   CK(S.d_payload.ensure(n_pay * 2 + 16), "device alloc (payload)");
   CK(S.d_clutops.ensure(n_clut * sizeof(ClutOp) + 16), "device alloc (clut ops)");
   CK(S.d_items.ensure(total_epochs * sizeof(WaveItem) + 16), "device alloc (wave items)");
@@ -867,6 +868,7 @@ int stage_encode(psxgpu_ctx* ctx, PendingChunk& pc)
   CK(S.d_cmds.ensure(cmd * sizeof(PackedCmd) + 64), "device alloc (commands)");
   CK(S.d_setups.ensure(cmd * sizeof(PrimSetup) + 64), "device alloc (setup records)");
   CK(S.d_bins.ensure(cmd * sizeof(BinInfo) + 64), "device alloc (bins)");
+  CK(S.d_tilecmds.ensure(tile_cmds_bytes(cmd)), "device alloc (tile command bitmaps)");
   CK(S.d_rects.ensure(cmd * 16 + 64), "device alloc (footprints)");
   CK(S.d_clutops.ensure(clut * sizeof(ClutOp) + 16), "device alloc (clut ops)");
   CK(S.d_epochs.ensure(epoch * sizeof(Epoch) + 16), "device alloc (epochs)");
@@ -1310,7 +1312,7 @@ void psxgpu_destroy(psxgpu_ctx* ctx)
   }
   for (psxgpu_ctx::Chunk* ch : ctx->chunks)
   {
-    for (DevBuf* b : {&ch->d_cmds, &ch->d_setups, &ch->d_bins, &ch->d_payload, &ch->d_clutops, &ch->d_items, &ch->d_misc, &ch->d_recoff, &ch->d_rec,
+    for (DevBuf* b : {&ch->d_cmds, &ch->d_setups, &ch->d_bins, &ch->d_tilecmds, &ch->d_payload, &ch->d_clutops, &ch->d_items, &ch->d_misc, &ch->d_recoff, &ch->d_rec,
                       &ch->d_inst, &ch->d_state, &ch->d_state_out, &ch->d_epochs, &ch->d_result, &ch->d_waves, &ch->d_cursor, &ch->d_summary, &ch->d_rects})
       b->release();
     for (cudaEvent_t ev : {ch->ev_copied, ch->ev_walked, ch->ev_encoded, ch->ev_done})

@@ -29,31 +29,59 @@
 namespace psx {
 
 // ------------------------------------------------------------------------------------------------ setup
+// Besides the PrimSetup records the kernel leaves two views of "which tiles can this command touch" (bounding box):
+// BinInfo per command (column bits | row bits; item_union_kernel ORs them per epoch) and its transpose for the raster
+// warps, tile_cmds[group * NUM_TILES + tile] = bit c set if command group * 32 + c touches the tile — a tile then
+// finds its commands of an epoch with one 32-bit load per 32 commands instead of scanning every command's mask.
+// A warp of this kernel is exactly one group of 32 commands, so the transpose is 32 ballots.
 __global__ void __launch_bounds__(128) setup_kernel(const PackedCmd* __restrict__ cmds, PrimSetup* __restrict__ setups,
-                                                    BinInfo* __restrict__ bins, uint32_t n)
+                                                    BinInfo* __restrict__ bins, uint32_t* __restrict__ tile_cmds, uint32_t n)
 {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n)
-    return;
-  // 64-byte record as four 128-bit loads
-  PackedCmd c;
-  const uint4* src = reinterpret_cast<const uint4*>(cmds + i);
-  uint4* cdst = reinterpret_cast<uint4*>(&c);
+  const uint32_t lane = threadIdx.x & 31u;
+  uint32_t mask = 0;
+  if (i < n)
+  {
+    // 64-byte record as four 128-bit loads
+    PackedCmd c;
+    const uint4* src = reinterpret_cast<const uint4*>(cmds + i);
+    uint4* cdst = reinterpret_cast<uint4*>(&c);
 #pragma unroll
-  for (int k = 0; k < 4; k++)
-    cdst[k] = __ldg(src + k);
-  PrimSetup s;
-  uint4* sw = reinterpret_cast<uint4*>(&s);
+    for (int k = 0; k < 4; k++)
+      cdst[k] = __ldg(src + k);
+    PrimSetup s;
+    uint4* sw = reinterpret_cast<uint4*>(&s);
 #pragma unroll
-  for (int k = 0; k < 10; k++)
-    sw[k] = make_uint4(0, 0, 0, 0);
-  BinInfo b;
-  setup_prim(c, s, b);
-  uint4* dst = reinterpret_cast<uint4*>(setups + i);
+    for (int k = 0; k < 10; k++)
+      sw[k] = make_uint4(0, 0, 0, 0);
+    BinInfo b;
+    setup_prim(c, s, b);
+    uint4* dst = reinterpret_cast<uint4*>(setups + i);
 #pragma unroll
-  for (int k = 0; k < 10; k++)
-    dst[k] = sw[k];
-  bins[i].tilemask = b.tilemask;
+    for (int k = 0; k < 10; k++)
+      dst[k] = sw[k];
+    bins[i].tilemask = b.tilemask;
+    mask = b.tilemask;
+  }
+  if ((i & ~31u) >= n)
+    return; // the whole warp is past the end
+  // lane L writes tiles L, L + 32, ...: column L & 15, rows (L >> 4) + 2k
+  uint32_t colv = 0;
+#pragma unroll
+  for (uint32_t x = 0; x < TILES_X; x++)
+  {
+    const uint32_t v = __ballot_sync(0xFFFFFFFFu, (mask >> x) & 1u);
+    if ((lane & 15u) == x)
+      colv = v;
+  }
+  uint32_t* out = tile_cmds + static_cast<size_t>(i >> 5) * NUM_TILES + lane;
+#pragma unroll
+  for (uint32_t y = 0; y < TILES_Y; y++)
+  {
+    const uint32_t v = __ballot_sync(0xFFFFFFFFu, (mask >> (16u + y)) & 1u);
+    if ((y & 1u) == (lane >> 4))
+      out[(y >> 1) * 32u] = v & colv;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ CLUT snapshots
@@ -783,57 +811,69 @@ __global__ void __launch_bounds__(SERIAL_THREADS) serial_kernel(const WaveItem* 
 // region in shared memory on the first hit, rasterises, writes it back.
 template<uint32_t RH, bool kCoh>
 __device__ __forceinline__ void process_epoch_region(const WaveItem& it, RasterShared<RH>& sh, uint32_t tx, uint32_t ty, uint32_t ry0,
-                                                     const PrimSetup* __restrict__ setups, const BinInfo* __restrict__ bins,
+                                                     const PrimSetup* __restrict__ setups, const uint32_t* __restrict__ tile_cmds,
                                                      uint16_t* vram, const uint16_t* cluts, const uint16_t* __restrict__ payload,
                                                      uint32_t lane)
 {
   const uint32_t rx0 = tx * TILE_W;
-  const uint32_t tile_bits = (1u << tx) | (1u << (16 + ty));
   uint32_t* gword = reinterpret_cast<uint32_t*>(vram + ry0 * VRAM_W + rx0) + lane; // this lane's word of region row 0
   const PrimSetup& staged = *reinterpret_cast<const PrimSetup*>(sh.stage);
 
-  // Binning reads the epoch's BinInfo words 128 at a time: one 128-bit load per lane, the next one in flight.
-  const uint32_t first = it.cmd_begin & ~3u; // 16-byte aligned start; indices below cmd_begin are masked out
-  const uint4* bin4 = reinterpret_cast<const uint4*>(bins) + (first >> 2);
-  const uint32_t n4 = (it.cmd_end - first + 3u) >> 2;
-  uint4 cur = (lane < n4) ? __ldg(bin4 + lane) : make_uint4(0, 0, 0, 0);
-
+  // Binning: tile_cmds holds, per group of 32 commands, one word per tile (setup_kernel).  A step covers 32 groups
+  // (1024 commands), one load per lane; the set bits of the lanes expand into the list in command order, as many
+  // lanes at a time as the list has room for.  All that survives a raster pass is next_cmd (uniform).
   bool loaded = false;
   uint32_t clut_key = 0;
   uint32_t list_n = 0;
-  for (uint32_t q = 0; q < n4; q += 32)
+  uint32_t next_cmd = it.cmd_begin; // first command of the epoch that is not in a list yet
+#pragma unroll 1
+  for (;;)
   {
-    const uint32_t qn = q + 32 + lane;
-    const uint4 nxt = (qn < n4) ? __ldg(bin4 + qn) : make_uint4(0, 0, 0, 0);
-    // ---- bin: 4 consecutive primitives per lane, order = (lane, k) ----
-    const uint32_t gi = first + ((q + lane) << 2); // global index of cur.x
-    uint32_t h = 0;
-    h |= ((cur.x & tile_bits) == tile_bits && gi + 0 >= it.cmd_begin && gi + 0 < it.cmd_end) ? 1u : 0u;
-    h |= ((cur.y & tile_bits) == tile_bits && gi + 1 >= it.cmd_begin && gi + 1 < it.cmd_end) ? 2u : 0u;
-    h |= ((cur.z & tile_bits) == tile_bits && gi + 2 >= it.cmd_begin && gi + 2 < it.cmd_end) ? 4u : 0u;
-    h |= ((cur.w & tile_bits) == tile_bits && gi + 3 >= it.cmd_begin && gi + 3 < it.cmd_end) ? 8u : 0u;
-    if (__any_sync(0xFFFFFFFFu, h != 0))
+    // fill the list until the epoch's commands are all in it, or it is (nearly) full
+#pragma unroll 1
+    while (next_cmd < it.cmd_end)
     {
-      // exclusive prefix of per-lane hit counts via four ballots
-      const uint32_t lt = (1u << lane) - 1u;
-      const uint32_t b0 = __ballot_sync(0xFFFFFFFFu, h & 1u), b1 = __ballot_sync(0xFFFFFFFFu, h & 2u);
-      const uint32_t b2 = __ballot_sync(0xFFFFFFFFu, h & 4u), b3 = __ballot_sync(0xFFFFFFFFu, h & 8u);
-      uint32_t pos = list_n + __popc(b0 & lt) + __popc(b1 & lt) + __popc(b2 & lt) + __popc(b3 & lt);
-      const uint32_t rel = gi - it.cmd_begin;
-      if (h & 1u)
-        sh.list[pos++] = static_cast<uint16_t>(rel);
-      if (h & 2u)
-        sh.list[pos++] = static_cast<uint16_t>(rel + 1);
-      if (h & 4u)
-        sh.list[pos++] = static_cast<uint16_t>(rel + 2);
-      if (h & 8u)
-        sh.list[pos++] = static_cast<uint16_t>(rel + 3);
-      list_n += __popc(b0) + __popc(b1) + __popc(b2) + __popc(b3);
+      const uint32_t g = next_cmd >> 5, mine = g + lane;
+      const uint32_t c0 = mine << 5; // first command of this lane's group
+      uint32_t bits = 0;
+      if (c0 < it.cmd_end)
+      {
+        bits = __ldg(tile_cmds + (static_cast<size_t>(mine) * NUM_TILES + (ty * TILES_X + tx)));
+        if (c0 < next_cmd)
+          bits &= 0xFFFFFFFFu << (next_cmd - c0);
+        if (c0 + 32u > it.cmd_end)
+          bits &= (1u << (it.cmd_end - c0)) - 1u;
+      }
+      if (!__any_sync(0xFFFFFFFFu, bits != 0))
+      {
+        next_cmd = (g + 32u) << 5;
+        continue;
+      }
+      const uint32_t cnt = __popc(bits);
+      const uint32_t incl = warp_inclusive_scan(cnt, lane);
+      const bool fits = list_n + incl <= LIST_CAP;
+      const uint32_t n_fit = __popc(__ballot_sync(0xFFFFFFFFu, fits)); // a prefix of the lanes: incl is monotone
+      // (REDUX results are uniform for the compiler: the warp stays converged for the collectives of the raster code)
+      const uint32_t added = __reduce_add_sync(0xFFFFFFFFu, fits ? cnt : 0u);
+      const uint32_t rounds = __reduce_max_sync(0xFFFFFFFFu, fits ? cnt : 0u);
+      uint32_t pos = list_n + incl - cnt;
+      const uint32_t rel = c0 - it.cmd_begin; // (wraps for the first group: those bits are masked off)
+      for (uint32_t k = 0; k < rounds; k++)
+      {
+        if (fits && bits)
+        {
+          const uint32_t c = static_cast<uint32_t>(__ffs(static_cast<int>(bits))) - 1u;
+          bits &= bits - 1u;
+          sh.list[pos++] = static_cast<uint16_t>(rel + c);
+        }
+      }
+      list_n += added;
+      next_cmd = max(next_cmd, (g + n_fit) << 5);
+      if (n_fit != 32u || list_n + 128u > LIST_CAP)
+        break;
     }
-    cur = nxt;
-    const bool last = (q + 32) >= n4;
-    if (!(list_n > 0 && (last || (list_n + 128) > LIST_CAP)))
-      continue;
+    if (list_n == 0)
+      break;
     __syncwarp();
 
     // ---- raster: walk the bin in order ----
@@ -896,7 +936,7 @@ __device__ __forceinline__ void process_epoch_region(const WaveItem& it, RasterS
 #define PSX_RASTER_MIN_CTAS 32
 #endif
 __global__ void __launch_bounds__(32 * PSX_RASTER_WARPS, PSX_RASTER_MIN_CTAS) raster_kernel(
-  const WaveItem* __restrict__ items, const PrimSetup* __restrict__ setups, const BinInfo* __restrict__ bins,
+  const WaveItem* __restrict__ items, const PrimSetup* __restrict__ setups, const uint32_t* __restrict__ tile_cmds,
   uint16_t* __restrict__ vram_pool, const uint16_t* __restrict__ clut_pool, const uint16_t* __restrict__ payload, uint32_t clut_slots)
 {
   __shared__ RasterShared<TILE_H> sh_all[PSX_RASTER_WARPS];
@@ -912,7 +952,7 @@ __global__ void __launch_bounds__(32 * PSX_RASTER_WARPS, PSX_RASTER_MIN_CTAS) ra
     return;
   uint16_t* vram = vram_pool + static_cast<size_t>(it.instance) * VRAM_PIXELS;
   const uint16_t* cluts = clut_pool + static_cast<size_t>(it.instance) * clut_slots * CLUT_ENTRIES;
-  process_epoch_region<TILE_H, false>(it, sh_all[threadIdx.x >> 5], tx, ty, ty * TILE_H, setups, bins, vram, cluts, payload,
+  process_epoch_region<TILE_H, false>(it, sh_all[threadIdx.x >> 5], tx, ty, ty * TILE_H, setups, tile_cmds, vram, cluts, payload,
                                       threadIdx.x & 31u);
 }
 
@@ -923,7 +963,7 @@ constexpr uint32_t LOOP_GRAB = 8;
 __device__ unsigned int g_raster_loop_counter[64];
 
 __global__ void __launch_bounds__(32, PSX_RASTER_MIN_CTAS) raster_loop_kernel(
-  const WaveItem* __restrict__ items, uint32_t n_items, const PrimSetup* __restrict__ setups, const BinInfo* __restrict__ bins,
+  const WaveItem* __restrict__ items, uint32_t n_items, const PrimSetup* __restrict__ setups, const uint32_t* __restrict__ tile_cmds,
   uint16_t* __restrict__ vram_pool, const uint16_t* __restrict__ clut_pool, const uint16_t* __restrict__ payload, uint32_t clut_slots,
   uint32_t counter_slot)
 {
@@ -958,7 +998,7 @@ __global__ void __launch_bounds__(32, PSX_RASTER_MIN_CTAS) raster_loop_kernel(
         continue;
       uint16_t* vram = vram_pool + static_cast<size_t>(it.instance) * VRAM_PIXELS;
       const uint16_t* cluts = clut_pool + static_cast<size_t>(it.instance) * clut_slots * CLUT_ENTRIES;
-      process_epoch_region<TILE_H, false>(it, sh, tx, ty, ty * TILE_H, setups, bins, vram, cluts, payload, lane);
+      process_epoch_region<TILE_H, false>(it, sh, tx, ty, ty * TILE_H, setups, tile_cmds, vram, cluts, payload, lane);
       __syncwarp();
     }
   }
@@ -1018,7 +1058,7 @@ __device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int
 
 __global__ void __launch_bounds__(PERSIST_THREADS, 7) raster_persistent_kernel(
   const WaveItem* __restrict__ items, const PersistWave* __restrict__ waves, uint32_t n_waves, const uint32_t* __restrict__ instances,
-  const PrimSetup* __restrict__ setups, const BinInfo* __restrict__ bins, const ClutOp* __restrict__ clut_ops, uint16_t* vram_pool,
+  const PrimSetup* __restrict__ setups, const uint32_t* __restrict__ tile_cmds, const ClutOp* __restrict__ clut_ops, uint16_t* vram_pool,
   uint16_t* clut_pool, const uint16_t* __restrict__ payload, uint32_t clut_slots, unsigned int* barrier_counter)
 {
   __shared__ RasterShared<PERSIST_RH> sh_all[PERSIST_WARPS];
@@ -1059,7 +1099,7 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 7) raster_persistent_kernel(
     {
       if (it.kind == EPOCH_TILED)
       {
-        process_epoch_region<PERSIST_RH, true>(it, sh_all[warp], tx, ty, ty * TILE_H + warp * PERSIST_RH, setups, bins, vram, cluts,
+        process_epoch_region<PERSIST_RH, true>(it, sh_all[warp], tx, ty, ty * TILE_H + warp * PERSIST_RH, setups, tile_cmds, vram, cluts,
                                                payload, lane);
       }
       else if (blockIdx.x == 0)
@@ -1180,11 +1220,11 @@ __global__ void scanout_kernel(const uint16_t* __restrict__ vram, ScanoutParams 
 }
 
 // ------------------------------------------------------------------------------------------------ launchers
-cudaError_t launch_setup(const PackedCmd* cmds, PrimSetup* setups, BinInfo* bins, uint32_t n, cudaStream_t st)
+cudaError_t launch_setup(const PackedCmd* cmds, PrimSetup* setups, BinInfo* bins, uint32_t* tile_cmds, uint32_t n, cudaStream_t st)
 {
   if (n == 0)
     return cudaSuccess;
-  setup_kernel<<<(n + 127) / 128, 128, 0, st>>>(cmds, setups, bins, n);
+  setup_kernel<<<(n + 127) / 128, 128, 0, st>>>(cmds, setups, bins, tile_cmds, n);
   return cudaGetLastError();
 }
 
@@ -1197,7 +1237,7 @@ cudaError_t launch_clut(const WaveItem* items, uint32_t n_items, const ClutOp* o
   return cudaGetLastError();
 }
 
-cudaError_t launch_raster(const WaveItem* items, uint32_t n_items, const PrimSetup* setups, const BinInfo* bins,
+cudaError_t launch_raster(const WaveItem* items, uint32_t n_items, const PrimSetup* setups, const uint32_t* tile_cmds,
                           uint16_t* vram_pool, const uint16_t* clut_pool, const uint16_t* payload, uint32_t clut_slots,
                           cudaStream_t st)
 {
@@ -1224,14 +1264,14 @@ cudaError_t launch_raster(const WaveItem* items, uint32_t n_items, const PrimSet
       return e;
     const uint32_t total = n_items * NUM_TILES;
     const uint32_t ctas = std::min<uint32_t>(static_cast<uint32_t>(sms) * PSX_RASTER_MIN_CTAS, total / 2u + 1u);
-    raster_loop_kernel<<<ctas, 32, 0, st>>>(items, n_items, setups, bins, vram_pool, clut_pool, payload, clut_slots, slot);
+    raster_loop_kernel<<<ctas, 32, 0, st>>>(items, n_items, setups, tile_cmds, vram_pool, clut_pool, payload, clut_slots, slot);
     return cudaGetLastError();
   }
   // gridDim.y is limited to 65535: chunk the wave
   for (uint32_t off = 0; off < n_items; off += 32768)
   {
     const uint32_t n = (n_items - off) < 32768u ? (n_items - off) : 32768u;
-    raster_kernel<<<dim3(NUM_TILES / PSX_RASTER_WARPS, n), 32 * PSX_RASTER_WARPS, 0, st>>>(items + off, setups, bins, vram_pool, clut_pool, payload, clut_slots);
+    raster_kernel<<<dim3(NUM_TILES / PSX_RASTER_WARPS, n), 32 * PSX_RASTER_WARPS, 0, st>>>(items + off, setups, tile_cmds, vram_pool, clut_pool, payload, clut_slots);
   }
   return cudaGetLastError();
 }
@@ -1266,7 +1306,7 @@ int persistent_max_instances(int device)
 }
 
 cudaError_t launch_persistent(const WaveItem* items, const void* waves, uint32_t n_waves, const uint32_t* instances, uint32_t n_instances,
-                              const PrimSetup* setups, const BinInfo* bins, const ClutOp* clut_ops, uint16_t* vram_pool,
+                              const PrimSetup* setups, const uint32_t* tile_cmds, const ClutOp* clut_ops, uint16_t* vram_pool,
                               uint16_t* clut_pool, const uint16_t* payload, uint32_t clut_slots, unsigned int* barrier_counter,
                               cudaStream_t st)
 {
@@ -1276,7 +1316,7 @@ cudaError_t launch_persistent(const WaveItem* items, const void* waves, uint32_t
   if (e != cudaSuccess)
     return e;
   const PersistWave* wv = static_cast<const PersistWave*>(waves);
-  void* args[] = {&items, &wv, &n_waves, &instances, &setups, &bins, &clut_ops, &vram_pool, &clut_pool, &payload, &clut_slots,
+  void* args[] = {&items, &wv, &n_waves, &instances, &setups, &tile_cmds, &clut_ops, &vram_pool, &clut_pool, &payload, &clut_slots,
                   &barrier_counter};
   return cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(raster_persistent_kernel), dim3(NUM_TILES, n_instances),
                                      dim3(PERSIST_THREADS), args, 0, st);

@@ -18,12 +18,17 @@ struct ScanoutParams
   uint32_t out_stride; // bytes
 };
 
-cudaError_t launch_setup(const PackedCmd* cmds, PrimSetup* setups, BinInfo* bins, uint32_t n, cudaStream_t st);
+// tile_cmds: (n + 31) / 32 groups x NUM_TILES words, the transposed tile masks the raster kernels bin from.
+cudaError_t launch_setup(const PackedCmd* cmds, PrimSetup* setups, BinInfo* bins, uint32_t* tile_cmds, uint32_t n, cudaStream_t st);
+inline size_t tile_cmds_bytes(size_t n_cmds)
+{
+  return ((n_cmds + 31) / 32 + 1) * NUM_TILES * sizeof(uint32_t);
+}
 // After setup: WaveItem::pad[0] = union of the tile masks of the item's commands (raster CTAs of other tiles exit at once).
 cudaError_t launch_item_union(WaveItem* items, uint32_t n_items, const BinInfo* bins, cudaStream_t st);
 cudaError_t launch_clut(const WaveItem* items, uint32_t n_items, const ClutOp* ops, const uint16_t* vram_pool,
                         uint16_t* clut_pool, uint32_t clut_slots, cudaStream_t st);
-cudaError_t launch_raster(const WaveItem* items, uint32_t n_items, const PrimSetup* setups, const BinInfo* bins,
+cudaError_t launch_raster(const WaveItem* items, uint32_t n_items, const PrimSetup* setups, const uint32_t* tile_cmds,
                           uint16_t* vram_pool, const uint16_t* clut_pool, const uint16_t* payload, uint32_t clut_slots,
                           cudaStream_t st);
 cudaError_t launch_serial(const WaveItem* items, uint32_t n_items, const PrimSetup* setups, uint16_t* vram_pool,
@@ -32,7 +37,7 @@ cudaError_t launch_serial(const WaveItem* items, uint32_t n_items, const PrimSet
 // `waves`: n_waves records of {item_begin, item_count, has_clut, pad} (uint32 each) in device memory.
 int persistent_max_instances(int device);
 cudaError_t launch_persistent(const WaveItem* items, const void* waves, uint32_t n_waves, const uint32_t* instances, uint32_t n_instances,
-                              const PrimSetup* setups, const BinInfo* bins, const ClutOp* clut_ops, uint16_t* vram_pool,
+                              const PrimSetup* setups, const uint32_t* tile_cmds, const ClutOp* clut_ops, uint16_t* vram_pool,
                               uint16_t* clut_pool, const uint16_t* payload, uint32_t clut_slots, unsigned int* barrier_counter,
                               cudaStream_t st);
 cudaError_t launch_hash(const uint16_t* vram_pool, uint32_t first, uint32_t count, unsigned long long* out, cudaStream_t st);
