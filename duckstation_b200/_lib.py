@@ -39,6 +39,12 @@ class FrontendStats(C.Structure):
         ("reserved", C.c_uint64 * 5)]
 
 
+class StateFile(C.Structure):
+    _fields_ = [("version", C.c_uint32), ("data_compression", C.c_uint32), ("data_compressed_size", C.c_uint32),
+                ("data_uncompressed_size", C.c_uint32), ("offset_to_data", C.c_uint32), ("title", C.c_char * 128),
+                ("serial", C.c_char * 32)]
+
+
 FRAME_CALLBACK = C.CFUNCTYPE(None, C.c_void_p, C.c_long)
 
 _lib = None
@@ -102,6 +108,14 @@ def load() -> C.CDLL:
     lib.psxgpu_frontend_feed_dump.restype = C.c_long
     lib.psxgpu_replay_dump.argtypes = [P, u32, C.c_char_p, C.c_size_t, u32, u32, FRAME_CALLBACK, C.c_void_p]
     lib.psxgpu_replay_dump.restype = C.c_long
+    lib.psxgpu_state_file_info.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(StateFile)]
+    lib.psxgpu_state_file_info.restype = C.c_int
+    lib.psxgpu_state_find_gpu_section.argtypes = [C.c_char_p, C.c_size_t, u32]
+    lib.psxgpu_state_find_gpu_section.restype = C.c_long
+    lib.psxgpu_frontend_load_state.argtypes = [P, C.c_void_p, u32, C.c_char_p, C.c_size_t, u32, C.POINTER(C.c_size_t)]
+    lib.psxgpu_frontend_load_state.restype = C.c_int
+    lib.psxgpu_frontend_save_state.argtypes = [P, C.c_void_p, u32, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+    lib.psxgpu_frontend_save_state.restype = C.c_int
     for name in ("psxgpu_frontend_create", "psxgpu_frontend_gp0", "psxgpu_frontend_gp1", "psxgpu_frontend_vsync",
                  "psxgpu_frontend_finish_read", "psxgpu_frontend_clear", "psxgpu_frontend_get_stats"):
         getattr(lib, name).restype = C.c_int
@@ -125,4 +139,5 @@ EXPORTS = (
     "psxgpu_frontend_vsync", "psxgpu_frontend_finish_read", "psxgpu_frontend_records", "psxgpu_frontend_clear",
     "psxgpu_frontend_get_stats", "psxgpu_frontend_feed_dump", "psxgpu_replay_dump",
     "psxgpu_presenter_create", "psxgpu_presenter_destroy", "psxgpu_present",
+    "psxgpu_state_file_info", "psxgpu_state_find_gpu_section", "psxgpu_frontend_load_state", "psxgpu_frontend_save_state",
 )

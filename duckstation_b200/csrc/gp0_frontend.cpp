@@ -36,6 +36,7 @@ inline uint32_t rc_primitive(uint32_t rc) { return (rc >> 29) & 7u; }
 
 constexpr uint16_t DRAW_MODE_MASK = 0x1FFF;            // GPUDrawModeReg::MASK
 constexpr uint16_t POLYGON_TEXPAGE_MASK = 0x09FF;      // GPUDrawModeReg::POLYGON_TEXPAGE_MASK
+constexpr size_t VRAM_WORDS_MAX = (1024 * 512) / 2;    // MAX_BLIT_BUFFER_SIZE, gpu.cpp:108
 constexpr size_t MAX_POLYLINE_WORDS = 1024;            // sanity bound like the reference's MAX_POLYLINE_BUFFER_SIZE
 } // namespace
 
@@ -883,6 +884,330 @@ long replay_psxgpu_dump(const void* data, size_t bytes, Gp0Frontend& fe, void (*
 // ------------------------------------------------------------------------------------------------ C ABI (include/psxgpu.h)
 #include "../../include/psxgpu.h"
 
+// ------------------------------------------------------------------------------------------------ save states
+namespace psx {
+namespace {
+
+// StateWrapper in read mode (src/util/state_wrapper.h:42-228): raw little-endian values, bool = one byte,
+// strings / vectors / FIFOs = u32 count + elements; any short read poisons the rest.
+struct StateReader
+{
+  const uint8_t* p;
+  size_t size, pos = 0;
+  bool error = false;
+  template<typename T>
+  T get()
+  {
+    T v{};
+    if (error || size - pos < sizeof(T))
+    {
+      error = true;
+      return v;
+    }
+    std::memcpy(&v, p + pos, sizeof(T));
+    pos += sizeof(T);
+    return v;
+  }
+  bool get_bool() { return get<uint8_t>() != 0; }
+  void skip(size_t n)
+  {
+    if (error || size - pos < n)
+      error = true;
+    else
+      pos += n;
+  }
+  bool marker(const char* text) // DoMarker, state_wrapper.cpp:104-116
+  {
+    const uint32_t len = get<uint32_t>();
+    const size_t want = std::strlen(text);
+    if (error || len != want || size - pos < len || std::memcmp(p + pos, text, len) != 0)
+    {
+      error = true;
+      return false;
+    }
+    pos += len;
+    return true;
+  }
+};
+
+struct StateWriter
+{
+  std::vector<uint8_t>& out;
+  template<typename T>
+  void put(T v)
+  {
+    const uint8_t* b = reinterpret_cast<const uint8_t*>(&v);
+    out.insert(out.end(), b, b + sizeof(T));
+  }
+  void put_bool(bool v) { out.push_back(v ? 1 : 0); }
+  void marker(const char* text)
+  {
+    put<uint32_t>(static_cast<uint32_t>(std::strlen(text)));
+    out.insert(out.end(), text, text + std::strlen(text));
+  }
+};
+
+constexpr uint32_t TC_VRAM_WRITE_BYTES = 16 * 2 + 8 + 4;            // gpu_hw_texture_cache.cpp:62
+constexpr uint32_t TC_PALETTE_RECORD_BYTES = 16 + 4 + 4 + 8 + 2 * 256; // gpu_hw_texture_cache.cpp:63-64
+
+} // namespace
+
+bool Gp0Frontend::load_state(const uint8_t* data, size_t bytes, uint32_t version, LoadedState* out)
+{
+  if (!data || !out || version < 42 || version > SAVE_STATE_VERSION)
+    return false;
+  StateReader r{data, bytes};
+  const uint32_t gpustat = r.get<uint32_t>();
+  const uint16_t draw_mode = r.get<uint16_t>();
+  const uint16_t palette = r.get<uint16_t>();
+  const uint32_t window_reg = r.get<uint32_t>();
+  if (version < 62)
+    r.skip(16); // texture_page_x/y, texture_palette_x/y
+  psx_texture_window window;
+  window.and_x = r.get<uint8_t>();
+  window.and_y = r.get<uint8_t>();
+  window.or_x = r.get<uint8_t>();
+  window.or_y = r.get<uint8_t>();
+  r.get_bool(); // texture_x_flip / texture_y_flip: bits 12 / 13 of the draw mode again
+  r.get_bool();
+  psx_drawing_area area;
+  area.left = r.get<uint32_t>();
+  area.top = r.get<uint32_t>();
+  area.right = r.get<uint32_t>();
+  area.bottom = r.get<uint32_t>();
+  int32_t off_x = r.get<int32_t>();
+  const int32_t off_y = r.get<int32_t>();
+  off_x = r.get<int32_t>(); // the reference serialises drawing_offset.x a second time (gpu.cpp:609)
+  const bool console_pal = r.get_bool();
+  const bool set_texture_disable_mask = r.get_bool();
+  const uint32_t display_address_start = r.get<uint32_t>();
+  const uint32_t h_range = r.get<uint32_t>();
+  const uint32_t v_range = r.get<uint32_t>();
+  r.skip(2);      // dot_clock_divider
+  r.skip(2 * 8);  // display_width .. display_vram_height: recomputed from the registers
+  r.skip(2 * 10); // horizontal_total .. vertical_display_end
+  r.skip(4 + 4 + 4); // fractional_ticks, current_tick_in_scanline, current_scanline (as u32)
+  if (version >= 46)
+    r.skip(4); // fractional_dot_ticks
+  r.skip(2);   // in_hblank, in_vblank
+  const uint8_t interlaced_field = r.get<uint8_t>();
+  r.skip(1); // interlaced_display_field: follows interlaced_field at the next UpdateDisplay
+  const uint8_t active_line_lsb = r.get<uint8_t>();
+  uint8_t blitter = r.get<uint8_t>();
+  if (blitter > 3)
+    blitter = 3; // Do(T*, max_value), state_wrapper.h:78-96
+  r.skip(4 + 4 + 4); // pending_command_ticks, command_total_words, GPUREAD_latch
+  uint32_t clut_reg = 0xFFFFFFFFu;
+  bool clut_is_8bit = false;
+  out->clut_valid = false;
+  std::memset(out->clut, 0, sizeof(out->clut));
+  if (version >= 64)
+  {
+    clut_reg = r.get<uint32_t>();
+    clut_is_8bit = r.get_bool();
+    for (uint16_t& c : out->clut)
+      c = r.get<uint16_t>();
+    out->clut_valid = true;
+  }
+  const uint16_t xfer_x = r.get<uint16_t>(), xfer_y = r.get<uint16_t>(), xfer_w = r.get<uint16_t>(), xfer_h = r.get<uint16_t>();
+  r.skip(4); // col, row of a VRAM -> CPU read in flight
+  std::vector<uint32_t> fifo, blit, polyline;
+  {
+    const uint32_t n = r.get<uint32_t>();
+    if (n > 256 || (bytes - r.pos) / 8 < n)
+      r.error = true;
+    for (uint32_t i = 0; i < n && !r.error; i++)
+      fifo.push_back(static_cast<uint32_t>(r.get<uint64_t>())); // low half = the word, high half = its DMA address
+  }
+  {
+    const uint32_t n = r.get<uint32_t>();
+    if (n > VRAM_WORDS_MAX || (bytes - r.pos) / 4 < n)
+      r.error = true;
+    else
+    {
+      blit.resize(n);
+      if (n && !r.error)
+      {
+        std::memcpy(blit.data(), data + r.pos, static_cast<size_t>(n) * 4);
+        r.pos += static_cast<size_t>(n) * 4;
+      }
+    }
+  }
+  const uint32_t blit_remaining = r.get<uint32_t>();
+  const uint32_t render_command = r.get<uint32_t>();
+  if (version >= 85)
+  {
+    const uint32_t n = r.get<uint32_t>();
+    if (n > 0x200000u || (bytes - r.pos) / 8 < n)
+      r.error = true;
+    for (uint32_t i = 0; i < n && !r.error; i++)
+      polyline.push_back(static_cast<uint32_t>(r.get<uint64_t>()));
+  }
+  if (version < 83)
+    r.skip(8);
+  if (!r.marker("GPU-VRAM"))
+    return false;
+  out->vram = data + r.pos;
+  r.skip(PSX_VRAM_PIXELS * 2);
+  if (version >= 73) // GPUTextureCache::GetStateSize, gpu_hw_texture_cache.cpp:661-691
+  {
+    if (!r.marker("GPUTextureCache"))
+      return false;
+    const uint32_t writes = r.get<uint32_t>();
+    if (version >= 86)
+      r.skip(4);
+    for (uint32_t i = 0; i < writes && !r.error; i++)
+    {
+      r.skip(version < 86 ? TC_VRAM_WRITE_BYTES - 4 : TC_VRAM_WRITE_BYTES);
+      const uint32_t records = r.get<uint32_t>();
+      if (records > (bytes - r.pos) / TC_PALETTE_RECORD_BYTES)
+        r.error = true;
+      else
+        r.skip(static_cast<size_t>(records) * TC_PALETTE_RECORD_BYTES);
+    }
+  }
+  if (r.error)
+    return false;
+  out->consumed = r.pos;
+
+  // nothing failed: take the state over
+  m_out.clear();
+  m_fifo = std::move(fifo);
+  m_head = 0;
+  m_blit = std::move(blit);
+  m_blit_remaining = blit_remaining;
+  m_polyline = std::move(polyline);
+  static const State states[4] = {State::Idle, State::ReadingVRAM, State::WritingVRAM, State::DrawingPolyLine};
+  m_state = states[blitter];
+  m_render_command = render_command;
+  m_console_pal = console_pal;
+  m_set_texture_disable_mask = set_texture_disable_mask;
+  m_draw_mode = draw_mode;
+  m_palette = palette;
+  m_texture_window_reg = window_reg;
+  m_window = window;
+  m_area = area;
+  m_area_changed = true; // gpu.cpp:704
+  m_offset_x = off_x;
+  m_offset_y = off_y;
+  m_draw_to_displayed_field = (gpustat >> 10) & 1u;
+  m_set_mask = (gpustat >> 11) & 1u;
+  m_check_mask = (gpustat >> 12) & 1u;
+  m_hres2 = (gpustat >> 16) & 1u;
+  m_hres1 = (gpustat >> 17) & 3u;
+  m_vertical_res = (gpustat >> 19) & 1u;
+  m_pal = (gpustat >> 20) & 1u;
+  m_display_24 = (gpustat >> 21) & 1u;
+  m_vertical_interlace = (gpustat >> 22) & 1u;
+  m_display_disable = (gpustat >> 23) & 1u;
+  m_display_address_start = display_address_start;
+  m_h_range = h_range;
+  m_v_range = v_range;
+  m_interlaced_field = interlaced_field;
+  m_active_line_lsb = active_line_lsb;
+  m_clut_reg = clut_reg;
+  m_clut_is_8bit = clut_is_8bit;
+  m_xfer_x = xfer_x;
+  m_xfer_y = xfer_y;
+  m_xfer_w = xfer_w;
+  m_xfer_h = xfer_h;
+  update_crtc_display();
+  return true;
+}
+
+void Gp0Frontend::save_state(std::vector<uint8_t>& out, const uint16_t* vram, const uint16_t* clut) const
+{
+  StateWriter w{out};
+  // GPUSTAT: draw-mode bits 0-10 and 15 mirror the register (gpu.cpp:2210-2213); the rest from the display state
+  uint32_t gpustat = (m_draw_mode & 0x7FFu) | (((m_draw_mode >> 11) & 1u) << 15);
+  gpustat |= (m_set_mask ? 1u : 0u) << 11 | (m_check_mask ? 1u : 0u) << 12 | static_cast<uint32_t>(m_interlaced_field & 1u) << 13;
+  gpustat |= static_cast<uint32_t>(m_hres2) << 16 | static_cast<uint32_t>(m_hres1) << 17 | (m_vertical_res ? 1u : 0u) << 19 |
+             (m_pal ? 1u : 0u) << 20 | (m_display_24 ? 1u : 0u) << 21 | (m_vertical_interlace ? 1u : 0u) << 22 |
+             (m_display_disable ? 1u : 0u) << 23;
+  gpustat |= 0x14000000u; // ready to receive command / DMA: idle values of the dynamic bits (gpu.cpp:499)
+  w.put<uint32_t>(gpustat);
+  w.put<uint16_t>(m_draw_mode);
+  w.put<uint16_t>(m_palette);
+  w.put<uint32_t>(m_texture_window_reg);
+  w.put<uint8_t>(m_window.and_x);
+  w.put<uint8_t>(m_window.and_y);
+  w.put<uint8_t>(m_window.or_x);
+  w.put<uint8_t>(m_window.or_y);
+  w.put_bool((m_draw_mode >> 12) & 1u);
+  w.put_bool((m_draw_mode >> 13) & 1u);
+  w.put<uint32_t>(m_area.left);
+  w.put<uint32_t>(m_area.top);
+  w.put<uint32_t>(m_area.right);
+  w.put<uint32_t>(m_area.bottom);
+  w.put<int32_t>(m_offset_x);
+  w.put<int32_t>(m_offset_y);
+  w.put<int32_t>(m_offset_x);
+  w.put_bool(m_console_pal);
+  w.put_bool(m_set_texture_disable_mask);
+  w.put<uint32_t>(m_display_address_start);
+  w.put<uint32_t>(m_h_range);
+  w.put<uint32_t>(m_v_range);
+  static const uint16_t dividers[8] = {10, 8, 5, 4, 7, 7, 7, 7};
+  w.put<uint16_t>(dividers[m_hres1 | (m_hres2 << 2)]);
+  w.put<uint16_t>(m_crtc.display_width);
+  w.put<uint16_t>(m_crtc.display_height);
+  w.put<uint16_t>(m_crtc.origin_left);
+  w.put<uint16_t>(m_crtc.origin_top);
+  w.put<uint16_t>(m_crtc.vram_left);
+  w.put<uint16_t>(m_crtc.vram_top);
+  w.put<uint16_t>(m_crtc.vram_width);
+  w.put<uint16_t>(m_crtc.vram_height);
+  w.put<uint16_t>(m_pal ? 3406 : 3413); // horizontal_total
+  for (int i = 0; i < 4; i++)
+    w.put<uint16_t>(0); // horizontal_visible_start/end, horizontal_display_start/end (beam timing: not modelled)
+  w.put<uint16_t>(m_pal ? 314 : 263); // vertical_total
+  for (int i = 0; i < 4; i++)
+    w.put<uint16_t>(0);
+  w.put<int32_t>(0);  // fractional_ticks
+  w.put<int32_t>(0);  // current_tick_in_scanline
+  w.put<uint32_t>(0); // current_scanline
+  w.put<int32_t>(0);  // fractional_dot_ticks
+  w.put_bool(false);  // in_hblank
+  w.put_bool(false);  // in_vblank
+  w.put<uint8_t>(m_interlaced_field);
+  w.put<uint8_t>(m_interlaced_field);
+  w.put<uint8_t>(m_active_line_lsb);
+  static const uint8_t blitter_of[4] = {0, 2, 1, 3}; // State -> BlitterState (gpu.cpp:63-69)
+  w.put<uint8_t>(blitter_of[static_cast<uint8_t>(m_state)]);
+  w.put<int32_t>(0);  // pending_command_ticks
+  w.put<uint32_t>(0); // command_total_words
+  w.put<uint32_t>(0); // GPUREAD_latch
+  w.put<uint32_t>(m_clut_reg);
+  w.put_bool(m_clut_is_8bit);
+  for (int i = 0; i < 256; i++)
+    w.put<uint16_t>(clut ? clut[i] : 0);
+  w.put<uint16_t>(m_xfer_x);
+  w.put<uint16_t>(m_xfer_y);
+  w.put<uint16_t>(m_xfer_w);
+  w.put<uint16_t>(m_xfer_h);
+  w.put<uint16_t>(0);
+  w.put<uint16_t>(0);
+  w.put<uint32_t>(fifo_size());
+  for (size_t i = m_head; i < m_fifo.size(); i++)
+    w.put<uint64_t>(m_fifo[i]);
+  w.put<uint32_t>(static_cast<uint32_t>(m_blit.size()));
+  for (uint32_t v : m_blit)
+    w.put<uint32_t>(v);
+  w.put<uint32_t>(m_blit_remaining);
+  w.put<uint32_t>(m_render_command);
+  w.put<uint32_t>(static_cast<uint32_t>(m_polyline.size()));
+  for (uint32_t v : m_polyline)
+    w.put<uint64_t>(v);
+  w.marker("GPU-VRAM");
+  const uint8_t* vb = reinterpret_cast<const uint8_t*>(vram);
+  out.insert(out.end(), vb, vb + PSX_VRAM_PIXELS * 2);
+  w.marker("GPUTextureCache");
+  w.put<uint32_t>(0);           // num_vram_writes
+  w.put<uint32_t>(0xFFFFFFFFu); // last_vram_write_index = INVALID_VRAM_WRITE_INDEX
+}
+
+} // namespace psx
+
 struct psxgpu_frontend
 {
   psx::Gp0Frontend fe;
@@ -1025,6 +1350,99 @@ long psxgpu_replay_dump(psxgpu_ctx* ctx, uint32_t instance, const void* data, si
   if (r.err != PSXGPU_OK)
     return r.err;
   return frames;
+}
+
+
+// ---- save states ----
+int psxgpu_state_file_info(const void* file, size_t bytes, psxgpu_state_file* out)
+{
+  // SAVE_STATE_HEADER, src/core/save_state_version.h:14-56 (pack 4): magic, version, title[128], serial[32], then
+  // twelve u32: media path (length, offset, subimage), screenshot (compression, width, height, size, offset),
+  // data (compression, compressed size, uncompressed size, offset) — 216 bytes
+  constexpr size_t HEADER_BYTES = 8 + 128 + 32 + 12 * 4;
+  if (!file || !out || bytes < HEADER_BYTES)
+    return PSXGPU_E_INVALID;
+  const uint8_t* b = static_cast<const uint8_t*>(file);
+  uint32_t head[2], f[12];
+  std::memcpy(head, b, 8);
+  std::memcpy(f, b + 8 + 128 + 32, sizeof(f));
+  if (head[0] != 0x43435544u) // SAVE_STATE_MAGIC
+    return PSXGPU_E_MALFORMED;
+  std::memset(out, 0, sizeof(*out));
+  out->version = head[1];
+  std::memcpy(out->title, b + 8, 128);
+  out->title[127] = 0;
+  std::memcpy(out->serial, b + 8 + 128, 32);
+  out->serial[31] = 0;
+  out->data_compression = f[8];
+  out->data_compressed_size = f[9];
+  out->data_uncompressed_size = f[10];
+  out->offset_to_data = f[11];
+  if (static_cast<uint64_t>(out->offset_to_data) + out->data_compressed_size > bytes)
+    return PSXGPU_E_MALFORMED;
+  return PSXGPU_OK;
+}
+
+long psxgpu_state_find_gpu_section(const void* state, size_t bytes, uint32_t version)
+{
+  if (!state)
+    return PSXGPU_E_INVALID;
+  static const uint8_t gpu_marker[7] = {3, 0, 0, 0, 'G', 'P', 'U'};       // sw.DoMarker("GPU"), system.cpp:2497
+  static const uint8_t next_marker[9] = {5, 0, 0, 0, 'C', 'D', 'R', 'O', 'M'}; // system.cpp:2500
+  const uint8_t* b = static_cast<const uint8_t*>(state);
+  for (size_t i = 0; i + sizeof(gpu_marker) <= bytes; i++)
+  {
+    if (std::memcmp(b + i, gpu_marker, sizeof(gpu_marker)) != 0)
+      continue;
+    const size_t at = i + sizeof(gpu_marker);
+    psx::Gp0Frontend probe;
+    psx::Gp0Frontend::LoadedState ls;
+    if (!probe.load_state(b + at, bytes - at, version, &ls))
+      continue;
+    const size_t end = at + ls.consumed;
+    if (end == bytes || (end + sizeof(next_marker) <= bytes && std::memcmp(b + end, next_marker, sizeof(next_marker)) == 0))
+      return static_cast<long>(at);
+  }
+  return PSXGPU_E_MALFORMED;
+}
+
+int psxgpu_frontend_load_state(psxgpu_frontend* f, psxgpu_ctx* ctx, uint32_t instance, const void* section, size_t bytes,
+                               uint32_t version, size_t* consumed)
+{
+  if (!f || !section)
+    return PSXGPU_E_INVALID;
+  psx::Gp0Frontend::LoadedState ls;
+  if (!f->fe.load_state(static_cast<const uint8_t*>(section), bytes, version, &ls))
+    return PSXGPU_E_MALFORMED;
+  if (consumed)
+    *consumed = ls.consumed;
+  if (!ctx)
+    return PSXGPU_OK;
+  // the GPUBackendLoadStateCommand GPU::DoState pushes (gpu.cpp:692-701); `vram` may sit at any alignment in the file
+  std::vector<uint16_t> vram(PSX_VRAM_PIXELS);
+  std::memcpy(vram.data(), ls.vram, PSX_VRAM_PIXELS * 2);
+  return psxgpu_load_state(ctx, instance, vram.data(), ls.clut);
+}
+
+int psxgpu_frontend_save_state(psxgpu_frontend* f, psxgpu_ctx* ctx, uint32_t instance, void* dst, size_t capacity, size_t* written)
+{
+  if (!f || !written)
+    return PSXGPU_E_INVALID;
+  std::vector<uint16_t> vram(PSX_VRAM_PIXELS), clut(PSX_CLUT_ENTRIES);
+  if (ctx) // (without a context: registers only, VRAM and CLUT cache zero)
+  {
+    const int rc = psxgpu_save_state(ctx, instance, vram.data(), clut.data()); // GPU::DoState starts with a full ReadVRAM
+    if (rc != PSXGPU_OK)
+      return rc;
+  }
+  std::vector<uint8_t> out;
+  out.reserve(PSX_VRAM_PIXELS * 2 + 4096);
+  f->fe.save_state(out, vram.data(), clut.data());
+  *written = out.size();
+  if (!dst || capacity < out.size())
+    return dst ? PSXGPU_E_NOMEM : PSXGPU_OK; // dst == nullptr: size query
+  std::memcpy(dst, out.data(), out.size());
+  return PSXGPU_OK;
 }
 
 } // extern "C"

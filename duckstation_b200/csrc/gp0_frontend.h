@@ -53,6 +53,24 @@ public:
   std::vector<uint8_t>& output() { return m_out; }
   void clear_output() { m_out.clear(); }
 
+  /// The GPU section of a save state: what GPU::DoState reads / writes between the "GPU" and
+  /// "CDROM" markers of System::DoState (src/core/gpu.cpp:574-726, src/core/system.cpp:2497; field encodings
+  /// src/util/state_wrapper.{h,cpp}).  load: `version` is the file's SAVE_STATE_HEADER::version (42..86 accepted);
+  /// registers, FIFO, transfer and polyline state go into this front-end, VRAM and the CLUT cache come back as views
+  /// into `data` for the caller to hand to psxgpu_load_state (that is the GPUBackendLoadStateCommand the reference
+  /// pushes).  Timing fields (ticks, scanline, blanking flags) are skipped: the front-end has no beam.
+  struct LoadedState
+  {
+    const uint8_t* vram = nullptr; // 1 MiB
+    uint16_t clut[256] = {};       // all zero for versions < 64 (the reference invalidates the CLUT cache instead)
+    bool clut_valid = false;
+    size_t consumed = 0;           // bytes of the section incl. the texture-cache tail
+  };
+  bool load_state(const uint8_t* data, size_t bytes, uint32_t version, LoadedState* out);
+  /// Appends a version-86 GPU section to `out`; timing fields are written as zero, the texture-cache tail as empty.
+  void save_state(std::vector<uint8_t>& out, const uint16_t* vram, const uint16_t* clut) const;
+  static constexpr uint32_t SAVE_STATE_VERSION = 86; // src/core/save_state_version.h:9
+
   struct Stats
   {
     uint64_t gp0_words = 0, gp1_words = 0, commands = 0, unknown_commands = 0, culled_primitives = 0, frames = 0;

@@ -48,6 +48,29 @@ class Gp0Frontend:
             raise ValueError(f"malformed .psxgpu trace ({n})")
         return n
 
+    def load_state(self, section: bytes, version: int = 86, ctx=None, instance: int = 0) -> int:
+        """The GPU section of a save state (GPU::DoState, gpu.cpp:574-726): registers / FIFO / transfer state into this
+        front-end, VRAM + CLUT cache into `instance` of `ctx` (if given).  Returns the bytes consumed."""
+        n = C.c_size_t()
+        rc = self._lib.psxgpu_frontend_load_state(self._h, ctx._ctx if ctx is not None else None, instance, section,
+                                                  len(section), version, C.byref(n))
+        if rc != 0:
+            raise ValueError(f"psxgpu_frontend_load_state failed ({rc})")
+        return n.value
+
+    def save_state(self, ctx=None, instance: int = 0) -> bytes:
+        """A version-86 GPU section of the current state (VRAM / CLUT cache from `ctx`, zero without one)."""
+        n = C.c_size_t()
+        h = ctx._ctx if ctx is not None else None
+        rc = self._lib.psxgpu_frontend_save_state(self._h, h, instance, None, 0, C.byref(n))
+        if rc != 0:
+            raise ValueError(f"psxgpu_frontend_save_state failed ({rc})")
+        buf = C.create_string_buffer(n.value)
+        rc = self._lib.psxgpu_frontend_save_state(self._h, h, instance, buf, n.value, C.byref(n))
+        if rc != 0:
+            raise ValueError(f"psxgpu_frontend_save_state failed ({rc})")
+        return buf.raw[: n.value]
+
     def records(self, clear: bool = True) -> bytes:
         """Backend records decoded so far (the psxgpu_submit_wire format)."""
         n = C.c_size_t()
@@ -74,3 +97,39 @@ def replay_dump(ctx, data: bytes, *, instance: int = 0, pal: bool = False, inter
     if n < 0:
         raise ValueError(f"psxgpu_replay_dump failed ({n}): {lib.psxgpu_last_error(ctx._ctx).decode()}")
     return n
+
+
+def state_file_info(file_bytes: bytes) -> dict:
+    """SAVE_STATE_HEADER of a DuckStation `.sav` file (src/core/save_state_version.h)."""
+    info = _lib.StateFile()
+    rc = _lib.load().psxgpu_state_file_info(file_bytes, len(file_bytes), C.byref(info))
+    if rc != 0:
+        raise ValueError(f"not a save state ({rc})")
+    return {"version": info.version, "data_compression": info.data_compression,
+            "data_compressed_size": info.data_compressed_size, "data_uncompressed_size": info.data_uncompressed_size,
+            "offset_to_data": info.offset_to_data, "title": info.title.decode(errors="replace"),
+            "serial": info.serial.decode(errors="replace")}
+
+
+def find_gpu_section(state_data: bytes, version: int = 86) -> int:
+    """Offset of the GPU section in decompressed save-state data (after the "GPU" marker, system.cpp:2497)."""
+    off = _lib.load().psxgpu_state_find_gpu_section(state_data, len(state_data), version)
+    if off < 0:
+        raise ValueError(f"no GPU section found ({off})")
+    return off
+
+
+def load_save_state_file(file_bytes: bytes, fe: "Gp0Frontend", ctx=None, instance: int = 0) -> dict:
+    """Seeds `instance` (and the front-end's registers) from a DuckStation save state file: header, decompression
+    (none or zstd — through pyarrow's codec, there is no zstd binding of our own), GPU section search, load."""
+    info = state_file_info(file_bytes)
+    blob = file_bytes[info["offset_to_data"]: info["offset_to_data"] + info["data_compressed_size"]]
+    if info["data_compression"] == 2:
+        import pyarrow as pa
+
+        blob = pa.decompress(blob, decompressed_size=info["data_uncompressed_size"], codec="zstd").to_pybytes()
+    elif info["data_compression"] != 0:
+        raise ValueError("save state compression %d is not supported (none and zstd are)" % info["data_compression"])
+    off = find_gpu_section(blob, info["version"])
+    fe.load_state(blob[off:], info["version"], ctx, instance)
+    return info

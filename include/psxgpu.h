@@ -210,6 +210,31 @@ typedef void (*psxgpu_frame_callback)(void* user, long frame);
 long psxgpu_replay_dump(psxgpu_ctx* ctx, uint32_t instance, const void* data, size_t bytes, uint32_t flags,
                         uint32_t crop_mode, psxgpu_frame_callback on_frame, void* user);
 
+/* ---- save states ---------------------------------------------------------------------------
+ * The GPU's part of a DuckStation save state: what GPU::DoState reads / writes (src/core/gpu.cpp:574-726) between the
+ * "GPU" and "CDROM" markers of System::DoState (src/core/system.cpp:2497-2500), in StateWrapper encoding
+ * (src/util/state_wrapper.h).  Loading sets the front-end's registers / FIFO / transfer state and pushes VRAM + the
+ * CLUT cache into `instance` like the GPUBackendLoadStateCommand the reference issues; saving writes a version-86
+ * section (timing fields zero, empty texture-cache tail).  Parity status: unpinned (no save state to read here;
+ * DESIGN.md §13). */
+typedef struct psxgpu_state_file { /* the fields of SAVE_STATE_HEADER (src/core/save_state_version.h:14-56) a loader needs */
+  uint32_t version;
+  uint32_t data_compression; /* 0 none, 1 deflate, 2 zstd, 3 xz: decompress data[offset_to_data ..] before searching */
+  uint32_t data_compressed_size, data_uncompressed_size, offset_to_data;
+  char title[128];
+  char serial[32];
+} psxgpu_state_file;
+int psxgpu_state_file_info(const void* file, size_t bytes, psxgpu_state_file* out);
+/* Offset of the GPU section inside the (decompressed) state data: the byte after the "GPU" marker whose section
+ * parses completely and is followed by the "CDROM" marker (or by the end of the buffer).  Negative if none. */
+long psxgpu_state_find_gpu_section(const void* state, size_t bytes, uint32_t version);
+/* ctx may be NULL (registers only).  consumed: bytes of the section. */
+int psxgpu_frontend_load_state(psxgpu_frontend* fe, psxgpu_ctx* ctx, uint32_t instance, const void* section, size_t bytes,
+                               uint32_t version, size_t* consumed);
+/* dst NULL: only *written is set (size query).  ctx NULL: registers only, VRAM and the CLUT cache are written as zero. */
+int psxgpu_frontend_save_state(psxgpu_frontend* fe, psxgpu_ctx* ctx, uint32_t instance, void* dst, size_t capacity,
+                               size_t* written);
+
 #ifdef __cplusplus
 }
 #endif

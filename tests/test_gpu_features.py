@@ -588,3 +588,37 @@ def test_device_encoder_slot_pressure_and_long_epochs(oracle):
             assert stats[(2, slots)][key] == stats[(1, slots)][key], (slots, key, stats[(2, slots)][key], stats[(1, slots)][key])
     assert stats[(2, 0)]["cuts_clut"] > 0 and stats[(2, 64)]["cuts_clut"] > stats[(2, 0)]["cuts_clut"]
     assert stats[(2, 0)]["epochs"] > len(batch) + 2
+
+
+def test_every_command_on_every_tile_overflows_the_bin_lists(oracle):
+    """Binning reads one word per (32 commands, tile) and expands it into a 512-entry list: 1100 blended rectangles that
+    each cover all of VRAM fill every tile's list twice over, with the epoch starting and ending inside a 32-command
+    group (an odd number of state records in front) — and blending makes any reordering or loss visible."""
+    import struct
+
+    rng = np.random.default_rng(11)
+    out = bytearray()
+    out += _rec(19, struct.pack("<4I", 0, 0, 1023, 511))
+    for _ in range(3):  # FillVRAM records in front: the rectangles do not start at a multiple of 32
+        out += _rec(16, struct.pack("<4HIBB", int(rng.integers(0, 512)), int(rng.integers(0, 256)), 64, 64, int(rng.integers(0, 1 << 24)), 0, 0))
+    for i in range(1100):
+        mode = 0 if i % 10 < 7 else int(rng.integers(1, 4))  # mostly averaging: keeps the picture from saturating
+        if i % 3:  # all of VRAM, skipping pixels whose mask bit is set
+            flags0 = 0x40 | 0x08
+            x, y, w, h = int(rng.integers(-3, 3)), int(rng.integers(-3, 3)), 1023, 511
+        else:  # a small one that sets the mask bit: these pixels keep the value they have at this point of the order
+            flags0 = 0x40 | 0x04 | (0x08 if i % 2 else 0)
+            x, y, w, h = int(rng.integers(0, 1000)), int(rng.integers(0, 500)), int(rng.integers(8, 120)), int(rng.integers(8, 120))
+        hdr = struct.pack("<BBHHH4B", flags0, 0, 1, mode << 5, 0, 0xFF, 0xFF, 0, 0)
+        out += _rec(24, hdr + struct.pack("<HHH2xiiI", w, h, 0, x, y, int(rng.integers(0, 1 << 24))))
+    stream = bytes(out)
+    want = oracle.render(stream)
+    with _ctx() as ctx:
+        ctx.submit(stream)
+        got = ctx.read_vram()
+        assert np.array_equal(got, want), describe_diff(got, want)
+        assert ctx.stats()["epochs"] <= 3
+    with _ctx(16, encode_mode=2) as ctx:  # the same through the device encoder + raster_loop_kernel
+        ctx.submit_batch([stream] * 16)
+        ctx.flush()
+        assert [int(h) for h in ctx.hash()] == [oracle.hash64(want)] * 16
