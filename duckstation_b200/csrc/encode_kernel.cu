@@ -430,6 +430,14 @@ struct WarpEncoder
 
   static __device__ __forceinline__ uint32_t quick_index(uint32_t want) { return ((want >> 4) ^ (want >> 10) ^ (want >> 15)) & 63u; }
 
+  // The quick-table half of find_slot on its own: lane-private (no collectives), for probing several palettes at once.
+  __device__ __forceinline__ uint32_t quick_probe(uint32_t x, uint32_t y, bool is8) const
+  {
+    const uint32_t want = x | (y << 10);
+    const uint32_t s = quick[quick_index(want)], k = key[s];
+    return ((k & ENC_SLOT_VALID) && (k & 0x7FFFFu) == want && (((k >> 19) & 1u) || !is8)) ? s : 0xFFFFFFFFu;
+  }
+
   __device__ __forceinline__ uint32_t find_slot(uint32_t x, uint32_t y, bool is8) const
   {
     const uint32_t want = x | (y << 10);
@@ -1502,8 +1510,40 @@ __global__ void __launch_bounds__(32 * ENC_WARPS) encode_kernel(EncodeArgs A)
       {
         uint32_t mylo = E.cur_lo, myhi = E.cur_hi, myserial = E.epoch_serial;
         const uint32_t n0 = E.n_cmds;
-        uint32_t clut_mask = __ballot_sync(FULL, in_batch && cls == CLS_CLUT);
+        const bool is_clut = in_batch && cls == CLS_CLUT;
+        uint32_t clut_mask = __ballot_sync(FULL, is_clut);
         uint32_t prev = 0, set_from = 0;
+        // Palettes repeat: usually every CLUT update of the batch finds its snapshot in the quick table.  Then nothing
+        // is allocated and no epoch is cut — all that is left to decide is which slots are current for which record
+        // ("the nearest CLUT update in front of me"), which is a ballot and a shuffle instead of a walk in order.
+        uint32_t my_slot = 0xFFFFFFFFu;
+        bool my_is8 = false;
+        if (is_clut)
+        {
+          const uint32_t reg = pv[0][0] & 0xFFFFu;
+          my_is8 = ((pv[0][0] >> 16) & 0xFFu) != 0;
+          my_slot = E.quick_probe(PSX_PAL_X(reg), PSX_PAL_Y(reg), my_is8);
+        }
+        if (clut_mask != 0 && !__any_sync(FULL, is_clut && my_slot == 0xFFFFFFFFu))
+        {
+          if (is_clut)
+            E.last[my_slot] = myserial;
+          const uint32_t lt = (1u << lane) - 1u;
+          const uint32_t mask8 = __ballot_sync(FULL, is_clut && my_is8);
+          const uint32_t below = clut_mask & lt, below8 = mask8 & lt;
+          const uint32_t lo_v = __shfl_sync(FULL, my_slot, below ? (31u - static_cast<uint32_t>(__clz(static_cast<int>(below)))) : 0u);
+          const uint32_t hi_v = __shfl_sync(FULL, my_slot, below8 ? (31u - static_cast<uint32_t>(__clz(static_cast<int>(below8)))) : 0u);
+          if (below)
+            mylo = lo_v;
+          if (below8)
+            myhi = hi_v;
+          E.cur_lo = __shfl_sync(FULL, my_slot, 31u - static_cast<uint32_t>(__clz(static_cast<int>(clut_mask))));
+          if (mask8)
+            E.cur_hi = __shfl_sync(FULL, my_slot, 31u - static_cast<uint32_t>(__clz(static_cast<int>(mask8))));
+          E.st_hits += __popc(clut_mask);
+          clut_mask = 0;
+          __syncwarp();
+        }
         while (clut_mask)
         {
           const uint32_t c = static_cast<uint32_t>(__ffs(static_cast<int>(clut_mask))) - 1u;
