@@ -48,6 +48,8 @@ struct StreamWindow
       for (int i = 0; i < 8; i++)
         dst[i] = __ldg(src + i);
     }
+    if (at + WIN_BYTES < limit) // the stream arrives from HBM: have the next window on its way to L2
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(wire + at + WIN_BYTES));
     __syncwarp();
   }
   // the 32-bit word at byte offset `pos` (4-byte aligned), refilling the window when pos lies outside it
@@ -1147,6 +1149,14 @@ __global__ void __launch_bounds__(32 * ENC_WARPS) encode_kernel(EncodeArgs A)
         rw[4 * i + 2] = v.z;
         rw[4 * i + 3] = v.w;
       }
+    }
+    // The streams come straight from the H2D copy, i.e. from HBM: ask for the next batch's records now (two lines per
+    // record at most), so that its loads find them in L2 when this batch has been committed.
+    if (base + 32u + lane < n_rec)
+    {
+      const uint8_t* nx = A.wire + (rec_off[base + 32u + lane] & ~15u);
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(nx));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + 95));
     }
     uint32_t cls = CLS_IGNORE, nprim = 0, hw0 = 0, hdm = 0, hwin = 0;
     uint32_t pv[2][8], pwr0[2], pwr1[2], prd0[2], prd1[2], pf[2];
