@@ -47,3 +47,31 @@ def test_baseline_configs(ctx, oracle, config, seed, n, flags):
 @pytest.mark.parametrize("flags", [0, 1, 2, 3])
 def test_fuzz(ctx, oracle, seed, flags):
     _check(ctx, oracle, streams.generate(0, seed, 3000, flags))
+
+
+def test_fuzz_many_short_streams(oracle):
+    """A wider net than test_fuzz: 160 short fuzz streams (interlaced rendering, mask bits, wrapping transfers, all
+    primitive kinds) through the latency path, and 64 more as one device-encoded batch through the throughput kernels."""
+    from duckstation_b200 import Context
+
+    bad = []
+    with Context(1) as ctx:
+        for seed in range(100, 140):
+            for flags in (0, 1, 2, 3):
+                s = streams.generate(0, seed, 500, flags)
+                want = oracle.render(s)
+                ctx.clear_vram(0)
+                ctx.submit(s)
+                if not np.array_equal(ctx.read_vram(), want):
+                    bad.append((seed, flags))
+    assert not bad, bad
+    batch = []
+    for seed in range(200, 264):
+        s = streams.generate(0, seed, 400, seed % 4)
+        batch.append(b"".join(s[off:off + size] for typ, off, size in streams.iter_records(s) if typ not in (7, 9, 12, 15)))
+    want = [oracle.hash64(oracle.render(s)) for s in batch]
+    with Context(len(batch), encode_mode=2) as ctx:
+        ctx.submit_batch(batch)
+        ctx.flush()
+        got = [int(h) for h in ctx.hash()]
+    assert got == want, [i for i in range(len(batch)) if got[i] != want[i]]
