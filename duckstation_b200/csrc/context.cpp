@@ -999,7 +999,14 @@ int submit_batch_device(psxgpu_ctx* ctx, uint32_t first, uint32_t count, const v
 {
   uint32_t per = ctx->batch_chunk;
   if (per == 0)
-    per = (count <= 256) ? count : std::max<uint32_t>(128, (count + 7) / 8);
+  {
+    static const uint32_t div = []() {
+      const char* e = std::getenv("PSXGPU_CHUNK_DIV"); // experiments: chunks per batch in automatic mode
+      const int v = e ? std::atoi(e) : 0;
+      return v > 0 ? static_cast<uint32_t>(v) : 8u;
+    }();
+    per = (count <= 256) ? count : std::max<uint32_t>(128, (count + div - 1) / div);
+  }
   std::vector<PendingChunk> uploaded, encoded; // waiting for stage B / stage C, oldest first
   int status = PSXGPU_OK;
   auto finalize_front = [&]() {
@@ -1522,7 +1529,14 @@ int psxgpu_submit_batch(psxgpu_ctx* ctx, uint32_t first, uint32_t count, const v
   // work on chunk k, the host threads encode chunk k+1 — straight into pinned memory, so nothing is copied twice.
   uint32_t per = ctx->batch_chunk;
   if (per == 0)
-    per = (count <= 256) ? count : std::max<uint32_t>(128, (count + 7) / 8);
+  {
+    static const uint32_t div = []() {
+      const char* e = std::getenv("PSXGPU_CHUNK_DIV"); // experiments: chunks per batch in automatic mode
+      const int v = e ? std::atoi(e) : 0;
+      return v > 0 ? static_cast<uint32_t>(v) : 8u;
+    }();
+    per = (count <= 256) ? count : std::max<uint32_t>(128, (count + div - 1) / div);
+  }
   std::vector<int> status(count, 0);
   std::vector<uint32_t> work;
   std::vector<uint64_t> cmd_base, pay_base;
