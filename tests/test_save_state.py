@@ -231,3 +231,29 @@ def test_state_seeds_an_instance_and_comes_back_out():
         assert np.array_equal(back["clut"], clut)
         at = out.index(b"GPU-VRAM") + 8
         assert np.array_equal(np.frombuffer(out, dtype="<u2", count=512 * 1024, offset=at).reshape(512, 1024), got)
+
+
+def test_damaged_sections_are_rejected_or_survive():
+    """Random byte damage and truncation: the reader either refuses the section or yields a front-end that keeps
+    working — it never reads outside the buffer (sizes of the FIFO / blit / polyline / texture-cache parts are checked
+    against what is left before anything is taken over)."""
+    rng = np.random.default_rng(0)
+    vram = bytes(VRAM_BYTES)
+    for version in (86, 84, 72, 61):
+        f = dict(FIELDS, fifo=[1, 2, 3], blit=[5] * 10, polyline=[7] * 6, blitter=2, xfer=(8, 8, 4, 5), blit_remaining=3)
+        base = build_section(version, f, vram, np.zeros(256, np.uint16), tc_writes=(1, 2))
+        for _ in range(400):
+            b = bytearray(base)
+            for _ in range(int(rng.integers(1, 6))):
+                pos = int(rng.integers(0, 1400)) if rng.random() < 0.7 else len(b) - int(rng.integers(1, 2000))
+                b[pos] = int(rng.integers(0, 256))
+            if rng.random() < 0.3:
+                b = b[: int(rng.integers(0, len(b)))]
+            fe = Gp0Frontend()
+            try:
+                fe.load_state(bytes(b), version)
+            except ValueError:
+                continue
+            fe.gp0([0x02000000, 0, 0x00100010, 0xE1000000])
+            fe.vsync()
+            fe.records()
