@@ -187,6 +187,7 @@ struct psxgpu_ctx
     uint32_t n_instances = 0;
     std::vector<uint32_t> wave_off{0}; // wave k = items [wave_off[k], wave_off[k+1])
     std::vector<uint8_t> wave_has_clut, wave_has_tiled, wave_has_serial;
+    std::vector<uint32_t> wave_tiled_cmds; // commands of each wave's tiled epochs (raster loop grab size)
     std::vector<cudaEvent_t> ev_raster; // pairs, profile mode
     uint32_t ev_raster_used = 0;
   };
@@ -347,7 +348,8 @@ int run_chunk(psxgpu_ctx* ctx, psxgpu_ctx::Chunk& S)
     if (S.wave_has_tiled[k])
     {
       CK(launch_raster(items + off, cnt, static_cast<const PrimSetup*>(S.d_setups.p), static_cast<const uint32_t*>(S.d_tilecmds.p),
-                       ctx->d_vram, ctx->d_clut, static_cast<const uint16_t*>(S.d_payload.p), ctx->clut_slots, ctx->stream),
+                       ctx->d_vram, ctx->d_clut, static_cast<const uint16_t*>(S.d_payload.p), ctx->clut_slots, ctx->stream,
+                       S.wave_tiled_cmds[k]),
          "raster_kernel");
       ctx->counters.kernel_launches += (cnt + 32767) / 32768;
     }
@@ -499,10 +501,12 @@ int launch_chunk_impl(psxgpu_ctx* ctx, const std::vector<uint32_t>& work, const 
   S.wave_has_clut.clear();
   S.wave_has_tiled.clear();
   S.wave_has_serial.clear();
+  S.wave_tiled_cmds.clear();
   uint32_t n_items = 0;
   for (size_t k = 0; k < max_epochs; k++)
   {
     uint8_t has_clut = 0, has_tiled = 0, has_serial = 0;
+    uint64_t tiled_cmds = 0;
     for (uint32_t w = 0; w < nw; w++)
     {
       const Encoder& e = ctx->enc[work[w]];
@@ -520,7 +524,10 @@ int launch_chunk_impl(psxgpu_ctx* ctx, const std::vector<uint32_t>& work, const 
       if (it.cmd_end > it.cmd_begin)
       {
         if (ep.kind == EPOCH_TILED)
+        {
           has_tiled = 1;
+          tiled_cmds += it.cmd_end - it.cmd_begin;
+        }
         else
           has_serial = 1;
       }
@@ -530,6 +537,7 @@ int launch_chunk_impl(psxgpu_ctx* ctx, const std::vector<uint32_t>& work, const 
     S.wave_has_clut.push_back(has_clut);
     S.wave_has_tiled.push_back(has_tiled);
     S.wave_has_serial.push_back(has_serial);
+    S.wave_tiled_cmds.push_back(static_cast<uint32_t>(std::min<uint64_t>(tiled_cmds, 0xFFFFFFFFull)));
   }
   S.n_cmds = static_cast<uint32_t>(n_cmds);
   S.device_encoded = false;
@@ -950,12 +958,14 @@ int finalize_device_chunk(psxgpu_ctx* ctx, PendingChunk& pc)
   S.wave_has_clut.clear();
   S.wave_has_tiled.clear();
   S.wave_has_serial.clear();
+  S.wave_tiled_cmds.clear();
   for (uint32_t k = 0; k < M; k++)
   {
     S.wave_off.push_back(wv[k].item_off + wv[k].item_count);
     S.wave_has_clut.push_back((wv[k].flags & 1u) ? 1 : 0);
     S.wave_has_tiled.push_back((wv[k].flags & 2u) ? 1 : 0);
     S.wave_has_serial.push_back((wv[k].flags & 4u) ? 1 : 0);
+    S.wave_tiled_cmds.push_back(wv[k].tiled_cmds);
   }
   S.n_cmds = static_cast<uint32_t>(pc.cmd_total);
   S.n_instances = pc.cn;

@@ -83,7 +83,7 @@ struct EncWave
 {
   uint32_t item_off, item_count;
   uint32_t flags; // 1 has CLUT ops, 2 has tiled epochs, 4 has serial epochs
-  uint32_t pad;
+  uint32_t tiled_cmds; // commands of the wave's tiled epochs (how heavy is a tile of this wave: the raster loop's grab size)
 };
 constexpr uint32_t ENC_WAVES_INLINE = 2048;
 

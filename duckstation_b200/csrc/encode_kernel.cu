@@ -1777,6 +1777,8 @@ __global__ void __launch_bounds__(32 * ENC_WARPS) encode_kernel(EncodeArgs A)
       f |= (e.kind == EPOCH_TILED) ? 2u : 4u;
     atomicAdd(&A.waves[k].item_count, 1u);
     atomicOr(&A.waves[k].flags, f);
+    if (e.kind == EPOCH_TILED)
+      atomicAdd(&A.waves[k].tiled_cmds, e.cmd_end - e.cmd_begin);
   }
 }
 

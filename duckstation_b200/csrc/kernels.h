@@ -30,7 +30,7 @@ cudaError_t launch_clut(const WaveItem* items, uint32_t n_items, const ClutOp* o
                         uint16_t* clut_pool, uint32_t clut_slots, cudaStream_t st);
 cudaError_t launch_raster(const WaveItem* items, uint32_t n_items, const PrimSetup* setups, const uint32_t* tile_cmds,
                           uint16_t* vram_pool, const uint16_t* clut_pool, const uint16_t* payload, uint32_t clut_slots,
-                          cudaStream_t st);
+                          cudaStream_t st, uint32_t tiled_cmds = 0xFFFFFFFFu); // tiled_cmds: commands of the wave's tiled epochs
 cudaError_t launch_serial(const WaveItem* items, uint32_t n_items, const PrimSetup* setups, uint16_t* vram_pool,
                           const uint16_t* clut_pool, const uint16_t* payload, uint32_t clut_slots, cudaStream_t st);
 // Persistent (latency) mode: whole flush of up to persistent_max_instances() instances in one cooperative launch.
