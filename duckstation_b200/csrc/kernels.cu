@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(256) clut_kernel(const WaveItem* __restrict__ 
 // ------------------------------------------------------------------------------------------------ raster
 constexpr int SERIAL_THREADS = 256;                     // serial_kernel: one CTA per serial epoch
 constexpr int SERIAL_WARPS = SERIAL_THREADS / 32;
-constexpr uint32_t LIST_CAP = 512;                      // per-tile bin capacity between raster phases
+constexpr uint32_t LIST_CAP = 160;                      // per-tile bin capacity between raster phases (5216 B per warp: 32 warps fit the 196 KB shared-memory configuration, L1 keeps 60 KB)
 constexpr uint32_t SETUP_WORDS = sizeof(PrimSetup) / 4; // 40
 constexpr uint32_t REGION_PITCH = 33;                   // words per tile row in shared memory (+1: bank skew)
 constexpr uint32_t REGION_PITCH16 = REGION_PITCH * 2;   // same, in pixels
@@ -869,7 +869,7 @@ __device__ __forceinline__ void process_epoch_region(const WaveItem& it, RasterS
       }
       list_n += added;
       next_cmd = max(next_cmd, (g + n_fit) << 5);
-      if (n_fit != 32u || list_n + 128u > LIST_CAP)
+      if (n_fit != 32u || list_n + 32u > LIST_CAP)
         break;
     }
     if (list_n == 0)
@@ -897,7 +897,7 @@ __device__ __forceinline__ void process_epoch_region(const WaveItem& it, RasterS
       {
 #pragma unroll 8
         for (uint32_t r = 0; r < RH; r++)
-          sh.region[r * REGION_PITCH + lane] = kCoh ? __ldcg(gword + r * (VRAM_W / 2)) : gword[r * (VRAM_W / 2)];
+          sh.region[r * REGION_PITCH + lane] = kCoh ? __ldcg(gword + r * (VRAM_W / 2)) : __ldcs(gword + r * (VRAM_W / 2)); // read once: keep it out of L1
       }
       loaded = true;
     }

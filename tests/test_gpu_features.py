@@ -591,8 +591,8 @@ def test_device_encoder_slot_pressure_and_long_epochs(oracle):
 
 
 def test_every_command_on_every_tile_overflows_the_bin_lists(oracle):
-    """Binning reads one word per (32 commands, tile) and expands it into a 512-entry list: 1100 blended rectangles that
-    each cover all of VRAM fill every tile's list twice over, with the epoch starting and ending inside a 32-command
+    """Binning reads one word per (32 commands, tile) and expands it into a 160-entry list: 1100 blended rectangles that
+    each cover all of VRAM fill every tile's list seven times over, with the epoch starting and ending inside a 32-command
     group (an odd number of state records in front) — and blending makes any reordering or loss visible."""
     import struct
 
