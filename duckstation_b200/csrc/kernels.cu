@@ -476,6 +476,29 @@ __device__ __forceinline__ void raster_prim_on_region(const PrimSetup& s, uint32
     case OP_UPLOAD:
     {
       const uint32_t px0 = rx0 + 2 * lane;
+      // whole tile inside the rectangle and no mask test: a straight copy of 32 payload rows, the loads of eight rows in
+      // flight at a time (the general loop below has one dependent payload load per row and lane)
+      {
+        const uint32_t cx = (rx0 - s.upload.x) & (VRAM_W - 1), cy = (ry0 - s.upload.y) & (VRAM_H - 1);
+        if (!(s.flags0 & F_CHECK_MASK) && cx + TILE_W <= s.upload.w && cy + RH <= s.upload.h)
+        {
+          const uint32_t mask_or = (s.flags0 & F_SET_MASK) ? 0x80008000u : 0u;
+          const uint32_t w = s.upload.w;
+          uint32_t idx = s.upload.payload + cy * w + cx + 2 * lane;
+#pragma unroll 8
+          for (uint32_t r = 0; r < RH; r++)
+          {
+            uint32_t word;
+            if (idx & 1u) // (the same for every lane of the row)
+              word = static_cast<uint32_t>(__ldg(payload + idx)) | (static_cast<uint32_t>(__ldg(payload + idx + 1)) << 16);
+            else
+              word = __ldg(reinterpret_cast<const uint32_t*>(payload + idx));
+            region[r * REGION_PITCH + lane] = word | mask_or;
+            idx += w;
+          }
+          break;
+        }
+      }
 #pragma unroll 2
       for (uint32_t r = 0; r < RH; r++)
       {

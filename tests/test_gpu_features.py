@@ -622,3 +622,33 @@ def test_every_command_on_every_tile_overflows_the_bin_lists(oracle):
         ctx.submit_batch([stream] * 16)
         ctx.flush()
         assert [int(h) for h in ctx.hash()] == [oracle.hash64(want)] * 16
+
+
+def test_full_tile_uploads_with_odd_strides_and_mask_set(oracle):
+    """Uploads large enough to cover whole 64x32 tiles take a straight-copy path (32-bit payload loads when the row
+    starts on an even halfword): odd widths make the parity alternate row by row, odd origins shift the tile phase,
+    set_mask ORs bit 15 in, check_mask must fall back to the general path — through both encoders."""
+    import struct
+
+    rng = np.random.default_rng(31)
+    out = bytearray()
+    out += _rec(16, struct.pack("<4HIBB", 0, 0, 1023, 511, 0x123456, 0, 0))
+    for (x, y, w, h, set_mask, check_mask) in [(0, 0, 256, 128, 0, 0), (3, 5, 131, 97, 1, 0), (700, 300, 199, 64, 0, 0),
+                                               (64, 32, 64, 32, 1, 0), (500, 100, 301, 130, 0, 1), (129, 257, 385, 200, 1, 1),
+                                               (900, 480, 200, 60, 0, 0)]:
+        pix = rng.integers(0, 65536, size=w * h, dtype=np.uint16)
+        out += _rec(17, struct.pack("<4HBB", x, y, w, h, set_mask, check_mask) + pix.tobytes())
+    stream = bytes(out)
+    want = oracle.render(stream)
+    with _ctx() as ctx:
+        ctx.submit(stream)
+        got = ctx.read_vram()
+        assert np.array_equal(got, want), describe_diff(got, want)
+    with _ctx(16, encode_mode=2) as ctx:
+        ctx.submit_batch([stream] * 16)
+        ctx.flush()
+        assert [int(h) for h in ctx.hash()] == [oracle.hash64(want)] * 16
+    with _ctx(16, encode_mode=1) as ctx:
+        ctx.submit_batch([stream] * 16)
+        ctx.flush()
+        assert [int(h) for h in ctx.hash()] == [oracle.hash64(want)] * 16
