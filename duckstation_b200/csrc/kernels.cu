@@ -455,6 +455,29 @@ __device__ __forceinline__ void raster_prim_on_region(const PrimSetup& s, uint32
     case OP_COPY:
     {
       const uint32_t px0 = rx0 + 2 * lane;
+      // whole tile inside the destination rectangle, no mask test, the 64 source columns do not wrap: a straight copy
+      // (the same shape as the upload path below; source rows may wrap, they are addressed one by one)
+      {
+        const uint32_t cx = (rx0 - s.copy.dx) & (VRAM_W - 1), cy = (ry0 - s.copy.dy) & (VRAM_H - 1);
+        const uint32_t sx = (s.copy.sx + cx) & (VRAM_W - 1);
+        if (!(s.flags0 & F_CHECK_MASK) && cx + TILE_W <= s.copy.w && cy + RH <= s.copy.h && sx + TILE_W <= VRAM_W)
+        {
+          const uint32_t mask_or = (s.flags0 & F_SET_MASK) ? 0x80008000u : 0u;
+          const uint32_t col = sx + 2 * lane;
+#pragma unroll 8
+          for (uint32_t r = 0; r < RH; r++)
+          {
+            const uint16_t* src = vram + ((s.copy.sy + cy + r) & (VRAM_H - 1)) * VRAM_W + col;
+            uint32_t word;
+            if (sx & 1u) // (the same for every lane and row)
+              word = static_cast<uint32_t>(ld_ro<kCoh>(src)) | (static_cast<uint32_t>(ld_ro<kCoh>(src + 1)) << 16);
+            else
+              word = ld_ro<kCoh>(reinterpret_cast<const uint32_t*>(src));
+            region[r * REGION_PITCH + lane] = word | mask_or;
+          }
+          break;
+        }
+      }
 #pragma unroll 2
       for (uint32_t r = 0; r < RH; r++)
       {

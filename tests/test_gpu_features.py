@@ -652,3 +652,30 @@ def test_full_tile_uploads_with_odd_strides_and_mask_set(oracle):
         ctx.submit_batch([stream] * 16)
         ctx.flush()
         assert [int(h) for h in ctx.hash()] == [oracle.hash64(want)] * 16
+
+
+def test_full_tile_copies(oracle):
+    """Non-overlapping VRAM-to-VRAM copies large enough to cover whole tiles: even / odd source phase, source rows and
+    columns that wrap (rows are fine for the straight-copy path, wrapping columns are not), mask set and mask test."""
+    import struct
+
+    rng = np.random.default_rng(41)
+    out = bytearray()
+    noise = rng.integers(0, 65536, size=(512, 512), dtype=np.uint16)
+    out += _rec(17, struct.pack("<4HBB", 0, 0, 512, 512, 0, 0) + noise.tobytes())
+    for (sx, sy, dx, dy, w, h, set_mask, check_mask) in [(0, 0, 512, 0, 256, 128, 0, 0), (3, 7, 515, 130, 199, 97, 1, 0),
+                                                         (100, 400, 640, 256, 300, 200, 0, 0),   # source rows wrap past 511
+                                                         (10, 10, 520, 300, 129, 65, 0, 1), (64, 64, 768, 384, 128, 64, 1, 1),
+                                                         (900, 20, 512, 40, 250, 100, 0, 0)]:    # source columns wrap past 1023
+        out += _rec(18, struct.pack("<6HBB", sx, sy, dx, dy, w, h, set_mask, check_mask))
+    stream = bytes(out)
+    want = oracle.render(stream)
+    with _ctx() as ctx:
+        ctx.submit(stream)
+        got = ctx.read_vram()
+        assert np.array_equal(got, want), describe_diff(got, want)
+    for mode in (2, 1):
+        with _ctx(16, encode_mode=mode) as ctx:
+            ctx.submit_batch([stream] * 16)
+            ctx.flush()
+            assert [int(h) for h in ctx.hash()] == [oracle.hash64(want)] * 16, mode
