@@ -356,9 +356,9 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             achieved = algo / (avg[dom] * 1e-3) / 1e9
             roofline = {"bound": "hbm", "kernel": "raster_loop_kernel (draw wave)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                         "frac": achieved / peak, "traffic": recorded_traffic(), "peak_source": peak_src,
-                        "limiter": "integer instruction issue + dependent-load latency, not memory: 78 % of issue slots busy at 31 "
-                                   "resident warps/SM, L2 hit rate 81 %, DRAM throughput 5 % (ncu --set full, "
-                                   "profiles/r01_raster_kernel_v12_ncu_raw.csv)",
+                        "limiter": "integer instruction issue + dependent-load latency, not memory: 79 % of issue slots busy at 31 "
+                                   "resident warps/SM, L2 hit rate 76 %, DRAM throughput 5 % (ncu --set full, "
+                                   "profiles/r01_raster_kernel_v13_ncu_raw.csv)",
                         "algorithmic_bytes_per_launch": algo, "launch_ms": avg[dom], "raster_launch_ms": avg,
                         "whole_step_algorithmic_frac": (bm["total"] / (ms_step * 1e-3) / 1e9) / peak,
                         "compulsory_hbm_frac": ((2 * (1 << 20) * n_inst + staged_stats["h2d_bytes"]) / (ms_step * 1e-3) / 1e9) / peak}
