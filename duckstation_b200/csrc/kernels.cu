@@ -1,15 +1,20 @@
 // kernels.cu — sm_100a kernels of the PSX rasteriser.
 //
-//   setup_kernel    one thread per primitive: PackedCmd -> PrimSetup + BinInfo (all divisions happen here)
+//   setup_kernel    one thread per primitive: PackedCmd -> PrimSetup + BinInfo (all divisions happen here); one warp =
+//                   32 consecutive commands also leaves the transpose of their tile masks (tile_cmds) for binning
 //   clut_kernel     CLUT snapshot pass of an epoch wave (reference: UpdateCLUT, gpu_sw_rasterizer.cpp:43-66)
-//   raster_kernel   one warp (= one CTA of 32 threads) per (instance, 64x32 VRAM tile): bins the epoch's
-//                   primitives for its tile in submission order (ballot + popc), stages the tile in shared
-//                   memory and walks the bin in order; no block-level barrier exists, so the hardware CTA
-//                   scheduler balances tiles and 32 CTAs stay resident per SM.  Per primitive the 32 lanes
-//                   compute the 32 row spans in one pass, a warp prefix sum compacts the covered pixels and
-//                   they are shaded 32 at a time (one pixel per lane), so small primitives keep the lanes
-//                   busy.  Tiles are read/written as coalesced 128-byte rows.  Texels and CLUT entries come
-//                   from global memory through the read-only path (L1/L2 resident).
+//   raster_kernel / raster_loop_kernel
+//                   one warp (= one CTA of 32 threads) per (instance, 64x32 VRAM tile): lists the epoch's
+//                   primitives for its tile in submission order from tile_cmds (one word per 32 commands), stages
+//                   the tile in shared memory and walks the list in order; no block-level barrier exists.  Per
+//                   primitive the 32 lanes compute the 32 row spans in one pass, a warp prefix sum compacts the
+//                   covered pixels and they are shaded 32 at a time (one pixel per lane), so small primitives keep
+//                   the lanes busy.  Tiles are read/written as coalesced 128-byte rows.  Texels come from global
+//                   memory through the read-only path (L2), palettes are staged in shared memory.  The loop
+//                   variant (waves of 16+ instances) is SMs x 32 persistent CTAs pulling tiles from a counter.
+//   raster_persistent_kernel
+//                   latency mode (up to 4 instances): one cooperative launch for a whole flush, grid barrier
+//                   between epochs, four warps per tile
 //   serial_kernel   epochs of a serial kind (self-sampling primitive, aliasing copy, mask-checked upload tail):
 //                   one CTA each, in the reference's own order.
 //   hash_kernel     vramhash64 per instance
@@ -1003,8 +1008,8 @@ __global__ void __launch_bounds__(32 * PSX_RASTER_WARPS, PSX_RASTER_MIN_CTAS) ra
 }
 
 // Same work as raster_kernel, other scheduling: exactly as many one-warp CTAs as the GPU holds (SMs x 32), each pulling
-// (item, tile) pairs from a global counter eight at a time until the wave is done — no CTA launch per tile, no idle
-// slot between a CTA's exit and its successor's start, dynamic balance between busy and empty tiles.
+// (item, tile) pairs from a global counter until the wave is done — no CTA launch per tile, no idle slot between a
+// CTA's exit and its successor's start, dynamic balance between busy and empty tiles.
 // Tiles per trip to the counter (kernel argument).  Neighbouring tiles share primitives, texture pages and palettes:
 // with small grabs the warps of an SM work on the same neighbourhood at the same time and find that data in L1 / L2
 // (draw wave of the batched config 17.5 -> 16.5 ms at 2 instead of 8) — but a wave of trivial tiles (a clear, an
