@@ -22,6 +22,7 @@
 //
 // Integer work only; bound by memory traffic and issue rate, so no tensor-core path.
 #include "kernels.h"
+#include "psx_pair.h"
 #include "psx_pixel.h"
 #include "psx_setup.h"
 
@@ -215,95 +216,61 @@ __device__ __forceinline__ uint32_t row_lane_map(uint32_t rows, uint32_t lane)
   return pos & 31u;
 }
 
-// Triangle on one tile.  Lane r works out the span of tile row r (one pass for all 32 rows); the covered pixels of all
-// rows are compacted with a prefix sum and shaded 32 at a time, one per lane.  What a pixel lane needs from its row
-// lane travels by shuffle: the column offset (+ raw-x delta) in one word and the per-row interpolant bases.
-template<uint32_t RH, bool kCoh, bool kShaded, bool kTextured>
-__device__ __forceinline__ void raster_triangle(const PrimSetup& s, const ShadeState st, const PixelCtx& ctx,
-                                                uint16_t* __restrict__ region16, int32_t x_min, uint32_t ry0, uint32_t lane)
+// Triangle or rectangle on one tile, two pixels per lane.
+//
+// Lane r works out the span of tile row r (one pass for all 32 rows).  The spans are cut into the 32-bit words of the
+// tile they touch (a word = an even / odd column pair), a warp prefix sum compacts the words of all rows, and they are
+// shaded 32 words at a time, one word per lane, with the packed pipeline of psx_pair.h: one shared-memory load and
+// store, one dither / clamp per channel and one blend for both pixels.  What a word's lane needs from its row lane
+// travels by shuffle: the word offset and the span's ends in one register, the per-row interpolant bases.
+// Everything that depends only on the primitive (texture mode, raw / modulated, flat / Gouraud, transparency) is a
+// warp-uniform branch around a short block, so each word runs exactly the blocks its primitive needs.
+template<uint32_t RH, bool kCoh>
+__device__ __forceinline__ void raster_spans(const PrimSetup& s, const ShadeState st, const uint16_t* __restrict__ vram,
+                                             const uint16_t* clut_smem, uint32_t* __restrict__ region, int32_t x_min, uint32_t ry0,
+                                             uint32_t lane)
 {
-  TriRow row;
-  const bool valid = (RH == 32 || lane < RH) && tri_row(s, ry0 + lane, row);
-  const int32_t xs = valid ? imax(row.x_lo, x_min) : 0, xe = valid ? imin(row.x_hi, x_min + static_cast<int32_t>(TILE_W)) : 0;
-  const uint32_t cnt = (xe > xs) ? static_cast<uint32_t>(xe - xs) : 0u;
-  const uint32_t rows = __ballot_sync(0xFFFFFFFFu, cnt != 0);
-  if (rows == 0)
-    return;
-  const uint32_t incl = warp_inclusive_scan(cnt, lane);
-  const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
-  const uint32_t start = cnt ? (incl - cnt) : ROW_EMPTY;
-  const uint32_t rowmap = row_lane_map(rows, lane);
+  const bool is_tri = s.op == OP_TRIANGLE;
+  const bool textured = (st.flags & F_TEXTURE) != 0;
+  const bool modulated = !(textured && (st.flags & F_RAW));        // colours matter
+  const bool gouraud = is_tri && modulated && (st.flags & F_SHADED); // per-pixel colours
   const auto& T = s.tri;
-  // px = xoff + j ; x_raw = px + xdelta (xdelta is a multiple of 2048 that fits 16 bits, xoff is within +-2048)
-  const uint32_t packed = (static_cast<uint32_t>(xs - static_cast<int32_t>(incl - cnt)) & 0xFFFFu) | (static_cast<uint32_t>(row.xdelta) << 16);
-  const uint32_t cy = static_cast<uint32_t>(row.cy);
-  uint32_t rb_r = 0, rb_g = 0, rb_b = 0, rb_u = 0, rb_v = 0, dx_r = 0, dx_g = 0, dx_b = 0, dx_u = 0, dx_v = 0;
-  uint32_t flat = 0;
-  if (kShaded)
+
+  // ---- spans: lane = tile row ----
+  int32_t xs = 0, xe = 0;
+  uint32_t rb_r = 0, rb_g = 0, rb_b = 0, rb_u = 0, rb_v = 0; // triangle: interpolant at tile column 0 of this row; rectangle: rb_v = v
+  if (is_tri)
   {
-    rb_r = T.base[0] + T.ddy[0] * cy;
-    rb_g = T.base[1] + T.ddy[1] * cy;
-    rb_b = T.base[2] + T.ddy[2] * cy;
-    dx_r = T.ddx[0];
-    dx_g = T.ddx[1];
-    dx_b = T.ddx[2];
+    TriRow row;
+    if ((RH == 32 || lane < RH) && tri_row(s, ry0 + lane, row))
+    {
+      xs = imax(row.x_lo, x_min) - x_min;
+      xe = imin(row.x_hi, x_min + static_cast<int32_t>(TILE_W)) - x_min;
+      const uint32_t cy = static_cast<uint32_t>(row.cy), x0 = static_cast<uint32_t>(x_min + row.xdelta);
+      if (gouraud)
+      {
+        rb_r = T.base[0] + T.ddy[0] * cy + T.ddx[0] * x0;
+        rb_g = T.base[1] + T.ddy[1] * cy + T.ddx[1] * x0;
+        rb_b = T.base[2] + T.ddy[2] * cy + T.ddx[2] * x0;
+      }
+      if (textured)
+      {
+        rb_u = T.base[3] + T.ddy[3] * cy + T.ddx[3] * x0;
+        rb_v = T.base[4] + T.ddy[4] * cy + T.ddx[4] * x0;
+      }
+    }
   }
   else
   {
-    flat = static_cast<uint32_t>(T.flat_r) | (static_cast<uint32_t>(T.flat_g) << 8) | (static_cast<uint32_t>(T.flat_b) << 16);
-  }
-  if (kTextured)
-  {
-    rb_u = T.base[3] + T.ddy[3] * cy;
-    rb_v = T.base[4] + T.ddy[4] * cy;
-    dx_u = T.ddx[3];
-    dx_v = T.ddx[4];
-  }
-  for (uint32_t base = 0; base < total; base += 32)
-  {
-    const uint32_t j = base + lane;
-    const bool active = j < total;
-    const uint32_t r = row_of_pixel(start, base, rowmap, lane);
-    const uint32_t pk = __shfl_sync(0xFFFFFFFFu, packed, r);
-    const int32_t px = static_cast<int32_t>(static_cast<int16_t>(pk & 0xFFFFu)) + static_cast<int32_t>(j);
-    const uint32_t xr = static_cast<uint32_t>(px + (static_cast<int32_t>(pk) >> 16));
-    uint32_t cr, cg, cb, cu = 0, cv = 0;
-    if (kShaded)
+    RectRow row;
+    if ((RH == 32 || lane < RH) && rect_row(s, ry0 + lane, row))
     {
-      cr = (__shfl_sync(0xFFFFFFFFu, rb_r, r) + dx_r * xr) >> 24;
-      cg = (__shfl_sync(0xFFFFFFFFu, rb_g, r) + dx_g * xr) >> 24;
-      cb = (__shfl_sync(0xFFFFFFFFu, rb_b, r) + dx_b * xr) >> 24;
-    }
-    else
-    {
-      cr = flat & 0xFFu;
-      cg = (flat >> 8) & 0xFFu;
-      cb = flat >> 16;
-    }
-    if (kTextured)
-    {
-      cu = (__shfl_sync(0xFFFFFFFFu, rb_u, r) + dx_u * xr) >> 24;
-      cv = (__shfl_sync(0xFFFFFFFFu, rb_v, r) + dx_v * xr) >> 24;
-    }
-    if (active)
-    {
-      uint16_t* p = region16 + r * REGION_PITCH16 + (px - x_min);
-      const uint32_t bg = *p;
-      const uint32_t out = shade_pixel<kCoh>(st, ctx, static_cast<uint32_t>(px), ry0 + r, cr, cg, cb, cu, cv, bg);
-      if (out != bg)
-        *p = static_cast<uint16_t>(out);
+      xs = imax(row.x_lo, x_min) - x_min;
+      xe = imin(row.x_hi, x_min + static_cast<int32_t>(TILE_W)) - x_min;
+      rb_v = row.v * 0x10001u;
     }
   }
-}
-
-template<uint32_t RH, bool kCoh>
-__device__ __forceinline__ void raster_rect(const PrimSetup& s, const ShadeState st, const PixelCtx& ctx,
-                                            uint16_t* __restrict__ region16, int32_t x_min, uint32_t ry0, uint32_t lane)
-{
-  RectRow row;
-  const bool valid = (RH == 32 || lane < RH) && rect_row(s, ry0 + lane, row);
-  const int32_t xs = valid ? imax(row.x_lo, x_min) : 0, xe = valid ? imin(row.x_hi, x_min + static_cast<int32_t>(TILE_W)) : 0;
-  const uint32_t cnt = (xe > xs) ? static_cast<uint32_t>(xe - xs) : 0u;
+  const uint32_t cnt = (xe > xs) ? static_cast<uint32_t>(((xe - 1) >> 1) - (xs >> 1) + 1) : 0u; // words touched
   const uint32_t rows = __ballot_sync(0xFFFFFFFFu, cnt != 0);
   if (rows == 0)
     return;
@@ -311,24 +278,137 @@ __device__ __forceinline__ void raster_rect(const PrimSetup& s, const ShadeState
   const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
   const uint32_t start = cnt ? (incl - cnt) : ROW_EMPTY;
   const uint32_t rowmap = row_lane_map(rows, lane);
-  const uint32_t packed = (static_cast<uint32_t>(xs - static_cast<int32_t>(incl - cnt)) & 0xFFFFu) | (row.v << 16);
-  const uint32_t cr = s.rect.r, cg = s.rect.g, cb = s.rect.b;
-  const uint32_t ubias = static_cast<uint32_t>(s.rect.u0) - static_cast<uint32_t>(static_cast<int32_t>(s.rect.x));
+  // word of compacted index j = wrel + j; the span is [xs, xe) in tile columns
+  const uint32_t packed = (static_cast<uint32_t>((xs >> 1) - static_cast<int32_t>(incl - cnt)) & 0xFFFFu) |
+                          (static_cast<uint32_t>(xs) << 16) | (static_cast<uint32_t>(xe) << 24);
+
+  // ---- warp-uniform constants of the primitive ----
+  const PairState ps = make_pair_state(st);
+  const bool dither = (st.flags & (F1_DITHER << 8)) != 0;
+  const bool mod5 = (st.flags & (F1_MOD5 << 8)) != 0;
+  // flat colours: 8-bit values for the modulation, or (untextured) the products 16 c in both halves
+  uint32_t fr = 0, fg = 0, fb = 0;
+  if (!gouraud && modulated)
+  {
+    fr = is_tri ? T.flat_r : s.rect.r;
+    fg = is_tri ? T.flat_g : s.rect.g;
+    fb = is_tri ? T.flat_b : s.rect.b;
+    if (textured)
+    {
+      if (mod5)
+      {
+        fr &= 0xF8u;
+        fg &= 0xF8u;
+        fb &= 0xF8u;
+      }
+    }
+    else
+    {
+      fr *= 0x00100010u;
+      fg *= 0x00100010u;
+      fb *= 0x00100010u;
+    }
+  }
+  // texture addressing (psx_pixel.h:texel_addr on both pixels at once)
+  const uint32_t mode = st.modes & 0xFFu, tsh = 2u - mode;
+  const uint32_t idxmask = (1u << (4u << mode)) - 1u;
+  const uint16_t* texrows = vram + (st.texbase >> 16) * VRAM_W; // page base row (0 or 256): row + v never wraps
+  // rectangle: u of tile column 0, reduced mod 256 so that (ubase + column) * 0x10001 cannot carry between the halves
+  const uint32_t ubase = is_tri ? 0u : ((static_cast<uint32_t>(s.rect.u0) - static_cast<uint32_t>(static_cast<int32_t>(s.rect.x)) + static_cast<uint32_t>(x_min)) & 0xFFu);
+
   for (uint32_t base = 0; base < total; base += 32)
   {
     const uint32_t j = base + lane;
     const bool active = j < total;
     const uint32_t r = row_of_pixel(start, base, rowmap, lane);
     const uint32_t pk = __shfl_sync(0xFFFFFFFFu, packed, r);
-    const int32_t px = static_cast<int32_t>(static_cast<int16_t>(pk & 0xFFFFu)) + static_cast<int32_t>(j);
-    if (active)
+    const uint32_t w = pk_prmt<0x9910>(pk, 0) + j; // sign-extended word offset + j = word of the tile row, 0..31
+    // coverage of the two halves: column 2w >= xs, column 2w + 1 < xe (bit 15 of each half; the bias keeps halves apart)
+    const uint32_t pos = w * 0x00020002u + 0x80018000u;
+    const uint32_t ge_xs = pos - __byte_perm(pk, 0, 0x4242), ge_xe = pos - __byte_perm(pk, 0, 0x4343);
+    const uint32_t cov15 = active ? (ge_xs & ~ge_xe & 0x80008000u) : 0u;
+    uint32_t* const wp = region + r * REGION_PITCH + w;
+    const uint32_t bg = active ? *wp : 0u;
+
+    uint32_t d16 = 0;
+    if (dither)
     {
-      uint16_t* p = region16 + r * REGION_PITCH16 + (px - x_min);
-      const uint32_t bg = *p;
-      const uint32_t out = shade_pixel<kCoh>(st, ctx, static_cast<uint32_t>(px), ry0 + r, cr, cg, cb,
-                                             (ubias + static_cast<uint32_t>(px)) & 0xFFu, pk >> 16, bg);
+      // pair_dither_entry in closed form: rows 2, 3 are rows 0, 1 with the column pairs swapped
+      const uint32_t p = (w ^ (r >> 1)) & 1u;
+      d16 = ((r & 1u) ? 0xFFE00020u : 0x0000FFC0u) + p * 0x00100010u;
+    }
+
+    uint32_t tex = 0;
+    if (textured)
+    {
+      uint32_t U, V;
+      if (is_tri)
+      {
+        const uint32_t u0 = __shfl_sync(0xFFFFFFFFu, rb_u, r) + T.ddx[3] * (2u * w), u1 = u0 + T.ddx[3];
+        const uint32_t v0 = __shfl_sync(0xFFFFFFFFu, rb_v, r) + T.ddx[4] * (2u * w), v1 = v0 + T.ddx[4];
+        U = __byte_perm(u0, u1, 0x7733); // top bytes; the odd bytes are cleared by the window masks below
+        V = __byte_perm(v0, v1, 0x7733);
+      }
+      else
+      {
+        U = (ubase + 2u * w) * 0x00010001u + 0x00010000u;
+        V = __shfl_sync(0xFFFFFFFFu, rb_v, r);
+      }
+      U = (U & __byte_perm(st.window, 0, 0x4040)) | __byte_perm(st.window, 0, 0x4242);
+      V = (V & __byte_perm(st.window, 0, 0x4141)) | __byte_perm(st.window, 0, 0x4343);
+      const uint32_t sub = (U & (((1u << tsh) - 1u) * 0x00010001u)) << (2u + mode); // bit offset of the index in its word
+      const uint32_t tx = ((U >> tsh) + (st.texbase & 0xFFFFu) * 0x00010001u) & 0x03FF03FFu;
+      const uint32_t a0 = ((V & 0xFFFFu) << 10) + (tx & 0xFFFFu), a1 = ((V >> 16) << 10) + (tx >> 16);
+      uint32_t t0 = ld_ro<kCoh>(texrows + a0), t1 = ld_ro<kCoh>(texrows + a1);
+      if (mode < 2u)
+      {
+        t0 = clut_smem[(t0 >> (sub & 0xFFFFu)) & idxmask];
+        t1 = clut_smem[(t1 >> (sub >> 16)) & idxmask];
+      }
+      tex = t0 | (t1 << 16);
+    }
+
+    uint32_t col15, t15 = 0, we15;
+    if (textured)
+    {
+      we15 = pair_we_textured(ps, bg, tex, cov15);
+      t15 = tex & 0x80008000u;
+      if (!modulated)
+        col15 = tex & 0x7FFF7FFFu;
+      else if (!gouraud)
+        col15 = pair_modulate<true>(tex, fr, fg, fb, d16);
+      else
+      {
+        const uint32_t c0 = mod5 ? 0xF8u : 0xFFu;
+        const uint32_t ar = __shfl_sync(0xFFFFFFFFu, rb_r, r) + T.ddx[0] * (2u * w), ag = __shfl_sync(0xFFFFFFFFu, rb_g, r) + T.ddx[1] * (2u * w),
+                       ab = __shfl_sync(0xFFFFFFFFu, rb_b, r) + T.ddx[2] * (2u * w);
+        const uint32_t tr = tex & 0x001F001Fu, tg = (tex >> 5) & 0x001F001Fu, tb = (tex >> 10) & 0x001F001Fu;
+        const uint32_t pr = (tr & 0xFFFFu) * ((ar >> 24) & c0) + (tr & 0xFFFF0000u) * (((ar + T.ddx[0]) >> 24) & c0);
+        const uint32_t pg = (tg & 0xFFFFu) * ((ag >> 24) & c0) + (tg & 0xFFFF0000u) * (((ag + T.ddx[1]) >> 24) & c0);
+        const uint32_t pb = (tb & 0xFFFFu) * ((ab >> 24) & c0) + (tb & 0xFFFF0000u) * (((ab + T.ddx[2]) >> 24) & c0);
+        col15 = pair_pack15(pr, pg, pb, d16);
+      }
+    }
+    else
+    {
+      we15 = pair_we_untextured(ps, bg, cov15);
+      if (!gouraud)
+        col15 = pair_pack15(fr, fg, fb, d16);
+      else
+      {
+        const uint32_t ar = __shfl_sync(0xFFFFFFFFu, rb_r, r) + T.ddx[0] * (2u * w), ag = __shfl_sync(0xFFFFFFFFu, rb_g, r) + T.ddx[1] * (2u * w),
+                       ab = __shfl_sync(0xFFFFFFFFu, rb_b, r) + T.ddx[2] * (2u * w);
+        const uint32_t pr = ((ar >> 24) << 4) + (((ar + T.ddx[0]) >> 24) << 20);
+        const uint32_t pg = ((ag >> 24) << 4) + (((ag + T.ddx[1]) >> 24) << 20);
+        const uint32_t pb = ((ab >> 24) << 4) + (((ab + T.ddx[2]) >> 24) << 20);
+        col15 = pair_pack15(pr, pg, pb, d16);
+      }
+    }
+    if (we15)
+    {
+      const uint32_t out = pair_finish(ps, bg, col15, t15, we15);
       if (out != bg)
-        *p = static_cast<uint16_t>(out);
+        *wp = out;
     }
   }
 }
@@ -373,18 +453,7 @@ __device__ __forceinline__ void raster_prim_on_region(const PrimSetup& s, uint32
   switch (op)
   {
     case OP_TRIANGLE:
-    {
-      // A flat triangle is a Gouraud triangle with zero gradients (setup gives it base = colour, ddx = ddy = 0), so two
-      // instantiations instead of four: the extra three multiply-adds per pixel cost less than the instruction-cache
-      // misses of the larger kernel (draw wave 19.0 -> 18.6 ms)
-      if (st.flags & F_TEXTURE)
-        raster_triangle<RH, kCoh, true, true>(s, st, ctx, region16, x_min, ry0, lane);
-      else
-        raster_triangle<RH, kCoh, true, false>(s, st, ctx, region16, x_min, ry0, lane);
-    }
-    break;
-
-    case OP_RECT: raster_rect<RH, kCoh>(s, st, ctx, region16, x_min, ry0, lane); break;
+    case OP_RECT: raster_spans<RH, kCoh>(s, st, vram, clut_smem, region, x_min, ry0, lane); break;
 
     case OP_LINE:
     {

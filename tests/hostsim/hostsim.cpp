@@ -8,6 +8,7 @@
 //   * inside an epoch primitives are applied in order, pixel by pixel, in arbitrary (here: raster) pixel order.
 // It is not part of the product library and nothing in duckstation_b200/ links it.
 #include "../../duckstation_b200/csrc/encoder.h"
+#include "../../duckstation_b200/csrc/psx_pair.h"
 #include "../../duckstation_b200/csrc/psx_pixel.h"
 #include "../../duckstation_b200/csrc/psx_setup.h"
 #include "../../include/psxgpu_wire.h"
@@ -371,3 +372,86 @@ void hostsim_stats(uint64_t* out, int n)
     out[i] = v[i];
 }
 }
+
+// ---- psx_pair.h (two pixels per register) against the scalar pipeline of psx_pixel.h ----
+namespace {
+uint64_t pair_rng(uint64_t& s)
+{
+  s += 0x9E3779B97F4A7C15ull;
+  return mix64(s);
+}
+} // namespace
+
+extern "C" {
+
+// n random pairs: random flags / transparency mode / background / texels / colours / position / coverage.
+// Returns the number of pairs whose result differs from shade_colour + blend_mask applied to each half.
+uint64_t hostsim_pair_selftest(uint64_t seed, uint64_t n)
+{
+  uint64_t bad = 0, s = seed;
+  for (uint64_t i = 0; i < n; i++)
+  {
+    const uint64_t a = pair_rng(s), b = pair_rng(s), c = pair_rng(s);
+    ShadeState st;
+    st.flags = static_cast<uint32_t>(a) & 0xFFu;
+    st.flags |= (static_cast<uint32_t>(a >> 8) & 1u) ? (F1_DITHER << 8) : 0u;
+    st.flags |= ((static_cast<uint32_t>(a >> 9) & 7u) == 0) ? (F1_MOD5 << 8) : 0u;
+    st.modes = (static_cast<uint32_t>(a >> 12) & 3u) << 8;
+    st.window = 0x0000FFFFu;
+    st.texbase = 0;
+    uint32_t bg = static_cast<uint32_t>(b), T = static_cast<uint32_t>(b >> 32);
+    if (((a >> 16) & 7u) == 0)
+      T &= 0xFFFF0000u; // transparent texel in the low half
+    if (((a >> 19) & 7u) == 0)
+      T &= 0x0000FFFFu;
+    if (((a >> 22) & 3u) == 0)
+      T &= 0x80008000u | static_cast<uint32_t>(c >> 40); // mask bit alone stays: texel != 0 but colour 0
+    const uint32_t cov = static_cast<uint32_t>(a >> 24) & 3u;
+    const uint32_t cov15 = ((cov & 1u) ? 0x8000u : 0u) | ((cov & 2u) ? 0x80000000u : 0u);
+    const uint32_t cr = static_cast<uint32_t>(c) & 0x00FF00FFu, cg = static_cast<uint32_t>(c >> 8) & 0x00FF00FFu,
+                   cb = static_cast<uint32_t>(c >> 32) & 0x00FF00FFu;
+    const uint32_t px = (static_cast<uint32_t>(a >> 32) & 1023u) & ~1u, Y = static_cast<uint32_t>(a >> 42) & 511u;
+    const bool dither = (st.flags & (F1_DITHER << 8)) != 0;
+    const uint32_t d16 = pair_dither_entry(dither ? ((Y & 3u) * 2u + ((px >> 1) & 1u)) : 8u);
+    const PairState ps = make_pair_state(st);
+    const uint32_t got = pair_shade(ps, bg, cov15, T, cr, cg, cb, d16);
+    uint32_t want = bg;
+    for (uint32_t h = 0; h < 2; h++)
+    {
+      if (!((cov >> h) & 1u))
+        continue;
+      const uint32_t sh = 16u * h;
+      uint32_t colour;
+      if (!shade_colour(st, px + h, Y, (cr >> sh) & 0xFFu, (cg >> sh) & 0xFFu, (cb >> sh) & 0xFFu, (T >> sh) & 0xFFFFu, colour))
+        continue;
+      const uint32_t out = blend_mask(st, (bg >> sh) & 0xFFFFu, colour) & 0xFFFFu;
+      want = (want & ~(0xFFFFu << sh)) | (out << sh);
+    }
+    bad += (got != want);
+  }
+  return bad;
+}
+
+// Exhaustive: every (background, foreground) pair of 15-bit colours through the four blend equations, the other half
+// of the register filled with noise; compared with blend_mask (textured, texel bit 15 set).
+uint64_t hostsim_pair_blend_exhaustive(uint32_t mode, uint32_t bg_step)
+{
+  uint64_t bad = 0, s = 1234 + mode;
+  ShadeState st;
+  st.flags = F_TEXTURE | F_TRANSP;
+  st.modes = mode << 8;
+  st.window = 0x0000FFFFu;
+  st.texbase = 0;
+  for (uint32_t bg = 0; bg < 0x10000u; bg += bg_step)
+    for (uint32_t fg = 0; fg < 0x8000u; fg++)
+    {
+      const uint32_t noise = static_cast<uint32_t>(pair_rng(s));
+      const uint32_t b2 = (bg & 0x7FFFu) | ((noise & 0x7FFFu) << 16), f2 = fg | (noise & 0x7FFF0000u);
+      const uint32_t got = pair_blend15(mode, b2, f2);
+      const uint32_t w0 = blend_mask(st, bg, fg | 0x8000u), w1 = blend_mask(st, noise & 0x7FFFu, (noise >> 16) | 0x8000u);
+      bad += ((got & 0xFFFFu) != (w0 & 0x7FFFu)) + ((got >> 16) != (w1 & 0x7FFFu)) + ((w0 & 0x8000u) == 0);
+    }
+  return bad;
+}
+
+} // extern "C"
