@@ -58,13 +58,13 @@ __global__ void __launch_bounds__(128) setup_kernel(const PackedCmd* __restrict_
     PrimSetup s;
     uint4* sw = reinterpret_cast<uint4*>(&s);
 #pragma unroll
-    for (int k = 0; k < 10; k++)
+    for (int k = 0; k < static_cast<int>(sizeof(PrimSetup) / 16); k++)
       sw[k] = make_uint4(0, 0, 0, 0);
     BinInfo b;
     setup_prim(c, s, b);
     uint4* dst = reinterpret_cast<uint4*>(setups + i);
 #pragma unroll
-    for (int k = 0; k < 10; k++)
+    for (int k = 0; k < static_cast<int>(sizeof(PrimSetup) / 16); k++)
       dst[k] = sw[k];
     bins[i].tilemask = b.tilemask;
     mask = b.tilemask;
@@ -111,20 +111,36 @@ __global__ void __launch_bounds__(256) clut_kernel(const WaveItem* __restrict__ 
 constexpr int SERIAL_THREADS = 256;                     // serial_kernel: one CTA per serial epoch
 constexpr int SERIAL_WARPS = SERIAL_THREADS / 32;
 constexpr uint32_t LIST_CAP = 160;                      // per-tile bin capacity between raster phases (5216 B per warp: 32 warps fit the 196 KB shared-memory configuration, L1 keeps 60 KB)
-constexpr uint32_t SETUP_WORDS = sizeof(PrimSetup) / 4; // 40
+constexpr uint32_t SETUP_WORDS = sizeof(PrimSetup) / 4; // 60
+constexpr uint32_t SETUP_VECS = sizeof(PrimSetup) / 16; // 15
 constexpr uint32_t REGION_PITCH = 33;                   // words per tile row in shared memory (+1: bank skew)
 constexpr uint32_t REGION_PITCH16 = REGION_PITCH * 2;   // same, in pixels
 
-// Per-warp shared memory.  raster_kernel: one warp == one CTA == one 64x32 tile (RH = 32), 5.9 KiB, so 32 CTAs fit an SM.
+// Per-warp shared memory.  raster_kernel: one warp == one CTA == one 64x32 tile (RH = 32), 5.5 KiB, so 32 CTAs fit an SM.
 // raster_persistent_kernel: four warps per CTA, each owning a 64x8 strip of the tile (RH = 8).
 template<uint32_t RH>
 struct alignas(16) RasterShared
 {
   uint32_t region[RH * REGION_PITCH];     // the region, 2 pixels per word (4224 B at RH = 32)
-  uint32_t stage[SETUP_WORDS];            // the primitive being rasterised
+  uint32_t stage[2][SETUP_WORDS];         // the primitive being rasterised and the next one (cp.async double buffer)
   uint16_t clut[CLUT_ENTRIES];            // merged palette of the current primitive (entries 0-15 lo slot, 16-255 hi slot)
   uint16_t list[LIST_CAP];                // bin: primitive indices (relative to the epoch), submission order
 };
+
+// 16-byte asynchronous copy global -> shared (LDGSTS): no register holds the data while it is in flight.
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem)
+{
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(smem))), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit()
+{
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+template<int kPending>
+__device__ __forceinline__ void cp_async_wait()
+{
+  asm volatile("cp.async.wait_group %0;" ::"n"(kPending) : "memory");
+}
 
 struct PixelCtx
 {
@@ -170,15 +186,12 @@ __device__ __forceinline__ uint32_t set_half(uint32_t word, uint32_t half, uint3
   return half ? ((word & 0x0000FFFFu) | (value << 16)) : ((word & 0xFFFF0000u) | (value & 0xFFFFu));
 }
 
-__device__ __forceinline__ uint32_t warp_inclusive_scan(uint32_t v, uint32_t lane)
+__device__ __forceinline__ uint32_t warp_inclusive_scan(uint32_t v, uint32_t)
 {
+  // shfl.up hands back a predicate "the source lane exists": add under it, no lane compare needed
 #pragma unroll
   for (uint32_t o = 1; o < 32; o <<= 1)
-  {
-    const uint32_t n = __shfl_up_sync(0xFFFFFFFFu, v, o);
-    if (lane >= o)
-      v += n;
-  }
+    asm volatile("{ .reg .pred p; .reg .u32 t; shfl.sync.up.b32 t|p, %0, %1, 0, 0xffffffff; @p add.u32 %0, %0, t; }" : "+r"(v) : "r"(o));
   return v;
 }
 
@@ -224,40 +237,50 @@ __device__ __forceinline__ uint32_t row_lane_map(uint32_t rows, uint32_t lane)
 // store, one dither / clamp per channel and one blend for both pixels.  What a word's lane needs from its row lane
 // travels by shuffle: the word offset and the span's ends in one register, the per-row interpolant bases.
 // Everything that depends only on the primitive (texture mode, raw / modulated, flat / Gouraud, transparency) is a
-// warp-uniform branch around a short block, so each word runs exactly the blocks its primitive needs.
+// warp-uniform branch around a short block, and the constants those blocks use come ready-made from the staged record
+// (LoopDesc, written by setup_kernel): the loop keeps few registers live, so nothing is rematerialised per word.
 template<uint32_t RH, bool kCoh>
-__device__ __forceinline__ void raster_spans(const PrimSetup& s, const ShadeState st, const uint16_t* __restrict__ vram,
-                                             const uint16_t* clut_smem, uint32_t* __restrict__ region, int32_t x_min, uint32_t ry0,
-                                             uint32_t lane)
+__device__ __forceinline__ void raster_spans(const PrimSetup& s, const uint16_t* vram, const uint16_t* clut_smem, uint32_t* region,
+                                             uint32_t rx0, uint32_t ry0, uint32_t lane)
 {
-  const bool is_tri = s.op == OP_TRIANGLE;
-  const bool textured = (st.flags & F_TEXTURE) != 0;
-  const bool modulated = !(textured && (st.flags & F_RAW));        // colours matter
-  const bool gouraud = is_tri && modulated && (st.flags & F_SHADED); // per-pixel colours
+  const LoopDesc& D = s.desc;
+  const uint32_t path = D.path;
   const auto& T = s.tri;
 
   // ---- spans: lane = tile row ----
   int32_t xs = 0, xe = 0;
   uint32_t rb_r = 0, rb_g = 0, rb_b = 0, rb_u = 0, rb_v = 0; // triangle: interpolant at tile column 0 of this row; rectangle: rb_v = v
-  if (is_tri)
+  if (path & LP_TRI)
   {
-    TriRow row;
-    if ((RH == 32 || lane < RH) && tri_row(s, ry0 + lane, row))
+    // tri_row (psx_pixel.h) with the clip against the tile folded in
+    const int32_t cy = T.y0 + static_cast<int32_t>((ry0 + lane - static_cast<uint32_t>(static_cast<int32_t>(T.y0))) & (VRAM_H - 1));
+    const uint32_t p = (cy >= T.y1) ? 1u : 0u;
+    const uint32_t k = static_cast<uint32_t>(cy - T.lo[p]);
+    const int32_t y = sext11(cy);
+    const bool ok = (RH == 32 || lane < RH) && k < static_cast<uint32_t>(T.hi[p] - T.lo[p]) && y >= s.clip_t && y <= s.clip_b &&
+                    !interlace_skip(s, static_cast<uint32_t>(cy));
+    const TriPart& P = T.part[p];
+    const int32_t x_start = static_cast<int32_t>((P.l_start + static_cast<uint64_t>(k) * P.l_step) >> 32);
+    const int32_t x_bound = static_cast<int32_t>((P.r_start + static_cast<uint64_t>(k) * P.r_step) >> 32);
+    const int32_t cx = sext11(x_start);
+    const int32_t lo = imax(imax(cx, s.clip_l), static_cast<int32_t>(rx0));
+    const int32_t hi = imin(imin(cx + (x_bound - x_start), s.clip_r + 1), static_cast<int32_t>(rx0 + TILE_W));
+    if (ok && hi > lo)
     {
-      xs = imax(row.x_lo, x_min) - x_min;
-      xe = imin(row.x_hi, x_min + static_cast<int32_t>(TILE_W)) - x_min;
-      const uint32_t cy = static_cast<uint32_t>(row.cy), x0 = static_cast<uint32_t>(x_min + row.xdelta);
-      if (gouraud)
-      {
-        rb_r = T.base[0] + T.ddy[0] * cy + T.ddx[0] * x0;
-        rb_g = T.base[1] + T.ddy[1] * cy + T.ddx[1] * x0;
-        rb_b = T.base[2] + T.ddy[2] * cy + T.ddx[2] * x0;
-      }
-      if (textured)
-      {
-        rb_u = T.base[3] + T.ddy[3] * cy + T.ddx[3] * x0;
-        rb_v = T.base[4] + T.ddy[4] * cy + T.ddx[4] * x0;
-      }
+      xs = lo - static_cast<int32_t>(rx0);
+      xe = hi - static_cast<int32_t>(rx0);
+    }
+    const uint32_t ucy = static_cast<uint32_t>(cy), x0 = rx0 + static_cast<uint32_t>(x_start - cx);
+    if (path & LP_GOURAUD)
+    {
+      rb_r = T.base[0] + T.ddy[0] * ucy + T.ddx[0] * x0;
+      rb_g = T.base[1] + T.ddy[1] * ucy + T.ddx[1] * x0;
+      rb_b = T.base[2] + T.ddy[2] * ucy + T.ddx[2] * x0;
+    }
+    if (path & LP_TEXTURED)
+    {
+      rb_u = T.base[3] + T.ddy[3] * ucy + T.ddx[3] * x0;
+      rb_v = T.base[4] + T.ddy[4] * ucy + T.ddx[4] * x0;
     }
   }
   else
@@ -265,8 +288,8 @@ __device__ __forceinline__ void raster_spans(const PrimSetup& s, const ShadeStat
     RectRow row;
     if ((RH == 32 || lane < RH) && rect_row(s, ry0 + lane, row))
     {
-      xs = imax(row.x_lo, x_min) - x_min;
-      xe = imin(row.x_hi, x_min + static_cast<int32_t>(TILE_W)) - x_min;
+      xs = imax(row.x_lo, static_cast<int32_t>(rx0)) - static_cast<int32_t>(rx0);
+      xe = imin(row.x_hi, static_cast<int32_t>(rx0 + TILE_W)) - static_cast<int32_t>(rx0);
       rb_v = row.v * 0x10001u;
     }
   }
@@ -281,134 +304,126 @@ __device__ __forceinline__ void raster_spans(const PrimSetup& s, const ShadeStat
   // word of compacted index j = wrel + j; the span is [xs, xe) in tile columns
   const uint32_t packed = (static_cast<uint32_t>((xs >> 1) - static_cast<int32_t>(incl - cnt)) & 0xFFFFu) |
                           (static_cast<uint32_t>(xs) << 16) | (static_cast<uint32_t>(xe) << 24);
+  const uint32_t ub = ((D.misc2 >> 8) + rx0) & 0xFFu; // rectangle: u of tile column 0 (mod 256: (ub + column) * 0x10001 cannot carry)
 
-  // ---- warp-uniform constants of the primitive ----
-  const PairState ps = make_pair_state(st);
-  const bool dither = (st.flags & (F1_DITHER << 8)) != 0;
-  const bool mod5 = (st.flags & (F1_MOD5 << 8)) != 0;
-  // flat colours: 8-bit values for the modulation, or (untextured) the products 16 c in both halves
-  uint32_t fr = 0, fg = 0, fb = 0;
-  if (!gouraud && modulated)
-  {
-    fr = is_tri ? T.flat_r : s.rect.r;
-    fg = is_tri ? T.flat_g : s.rect.g;
-    fb = is_tri ? T.flat_b : s.rect.b;
-    if (textured)
-    {
-      if (mod5)
-      {
-        fr &= 0xF8u;
-        fg &= 0xF8u;
-        fb &= 0xF8u;
-      }
-    }
-    else
-    {
-      fr *= 0x00100010u;
-      fg *= 0x00100010u;
-      fb *= 0x00100010u;
-    }
-  }
-  // texture addressing (psx_pixel.h:texel_addr on both pixels at once)
-  const uint32_t mode = st.modes & 0xFFu, tsh = 2u - mode;
-  const uint32_t idxmask = (1u << (4u << mode)) - 1u;
-  const uint16_t* texrows = vram + (st.texbase >> 16) * VRAM_W; // page base row (0 or 256): row + v never wraps
-  // rectangle: u of tile column 0, reduced mod 256 so that (ubase + column) * 0x10001 cannot carry between the halves
-  const uint32_t ubase = is_tri ? 0u : ((static_cast<uint32_t>(s.rect.u0) - static_cast<uint32_t>(static_cast<int32_t>(s.rect.x)) + static_cast<uint32_t>(x_min)) & 0xFFu);
-
+#pragma unroll 1
   for (uint32_t base = 0; base < total; base += 32)
   {
-    const uint32_t j = base + lane;
-    const bool active = j < total;
     const uint32_t r = row_of_pixel(start, base, rowmap, lane);
     const uint32_t pk = __shfl_sync(0xFFFFFFFFu, packed, r);
-    const uint32_t w = pk_prmt<0x9910>(pk, 0) + j; // sign-extended word offset + j = word of the tile row, 0..31
-    // coverage of the two halves: column 2w >= xs, column 2w + 1 < xe (bit 15 of each half; the bias keeps halves apart)
+    const uint32_t w = pk_prmt<0x9910>(pk, 0) + base + lane; // sign-extended word offset + j = word of the tile row
+    // coverage of the two halves: column 2w >= xs, column 2w + 1 < xe (bit 15 of each half; the bias keeps the halves
+    // apart).  Lanes past the last word of the batch land behind their row's last word: not covered.
     const uint32_t pos = w * 0x00020002u + 0x80018000u;
-    const uint32_t ge_xs = pos - __byte_perm(pk, 0, 0x4242), ge_xe = pos - __byte_perm(pk, 0, 0x4343);
-    const uint32_t cov15 = active ? (ge_xs & ~ge_xe & 0x80008000u) : 0u;
+    const uint32_t cov15 = (pos - pk_prmt<0x4242>(pk, 0)) & ~(pos - pk_prmt<0x4343>(pk, 0)) & 0x80008000u;
     uint32_t* const wp = region + r * REGION_PITCH + w;
-    const uint32_t bg = active ? *wp : 0u;
+    const uint32_t bg = *wp; // (lanes past the end read at most 31 words behind their row: still inside this warp's shared memory)
 
     uint32_t d16 = 0;
-    if (dither)
+    if (path & LP_DITHER)
     {
       // pair_dither_entry in closed form: rows 2, 3 are rows 0, 1 with the column pairs swapped
-      const uint32_t p = (w ^ (r >> 1)) & 1u;
-      d16 = ((r & 1u) ? 0xFFE00020u : 0x0000FFC0u) + p * 0x00100010u;
+      d16 = 0x0000FFC0u + (r & 1u) * 0xFFDF0060u + ((w ^ (r >> 1)) & 1u) * 0x00100010u;
     }
 
-    uint32_t tex = 0;
-    if (textured)
+    uint32_t tex = 0, we15;
+    if (path & LP_TEXTURED)
     {
       uint32_t U, V;
-      if (is_tri)
+      if (path & LP_TRI)
       {
-        const uint32_t u0 = __shfl_sync(0xFFFFFFFFu, rb_u, r) + T.ddx[3] * (2u * w), u1 = u0 + T.ddx[3];
-        const uint32_t v0 = __shfl_sync(0xFFFFFFFFu, rb_v, r) + T.ddx[4] * (2u * w), v1 = v0 + T.ddx[4];
-        U = __byte_perm(u0, u1, 0x7733); // top bytes; the odd bytes are cleared by the window masks below
-        V = __byte_perm(v0, v1, 0x7733);
+        const uint32_t du = T.ddx[3], dv = T.ddx[4];
+        const uint32_t u0 = __shfl_sync(0xFFFFFFFFu, rb_u, r) + du * (2u * w);
+        const uint32_t v0 = __shfl_sync(0xFFFFFFFFu, rb_v, r) + dv * (2u * w);
+        U = __byte_perm(u0, u0 + du, 0x7733); // top bytes; the odd bytes are cleared by the masks below
+        V = __byte_perm(v0, v0 + dv, 0x7733);
       }
       else
       {
-        U = (ubase + 2u * w) * 0x00010001u + 0x00010000u;
+        U = (ub + 2u * w) * 0x00010001u + 0x00010000u;
         V = __shfl_sync(0xFFFFFFFFu, rb_v, r);
       }
-      U = (U & __byte_perm(st.window, 0, 0x4040)) | __byte_perm(st.window, 0, 0x4242);
-      V = (V & __byte_perm(st.window, 0, 0x4141)) | __byte_perm(st.window, 0, 0x4343);
-      const uint32_t sub = (U & (((1u << tsh) - 1u) * 0x00010001u)) << (2u + mode); // bit offset of the index in its word
-      const uint32_t tx = ((U >> tsh) + (st.texbase & 0xFFFFu) * 0x00010001u) & 0x03FF03FFu;
-      const uint32_t a0 = ((V & 0xFFFFu) << 10) + (tx & 0xFFFFu), a1 = ((V >> 16) << 10) + (tx >> 16);
-      uint32_t t0 = ld_ro<kCoh>(texrows + a0), t1 = ld_ro<kCoh>(texrows + a1);
-      if (mode < 2u)
+      if (path & LP_WINDOW)
       {
-        t0 = clut_smem[(t0 >> (sub & 0xFFFFu)) & idxmask];
-        t1 = clut_smem[(t1 >> (sub >> 16)) & idxmask];
+        U = (U & D.and_x2) | D.or_x2;
+        V = (V & D.and_y2) | D.or_y2;
+      }
+      else
+      {
+        U &= 0x00FF00FFu;
+        V &= 0x00FF00FFu;
+      }
+      // psx_pixel.h:texel_addr on both pixels at once
+      const uint32_t misc = D.tex_misc;
+      const uint32_t tx = ((U >> (misc & 0xFFu)) + D.tex_bx2) & 0x03FF03FFu;
+      const uint16_t* texrows = vram + D.tex_rows; // page base row (0 or 256): row + v never wraps
+      uint32_t t0 = ld_ro<kCoh>(texrows + (((V & 0xFFFFu) << 10) + (tx & 0xFFFFu)));
+      uint32_t t1 = ld_ro<kCoh>(texrows + (((V >> 16) << 10) + (tx >> 16)));
+      if (path & LP_PALETTED)
+      {
+        const uint32_t sub = (U & D.sub_mask2) << ((misc >> 8) & 0xFFu); // bit offset of the index in its word
+        t0 = clut_smem[(t0 >> (sub & 0xFFFFu)) & (misc >> 16)];
+        t1 = clut_smem[(t1 >> (sub >> 16)) & (misc >> 16)];
       }
       tex = t0 | (t1 << 16);
-    }
-
-    uint32_t col15, t15 = 0, we15;
-    if (textured)
-    {
-      we15 = pair_we_textured(ps, bg, tex, cov15);
-      t15 = tex & 0x80008000u;
-      if (!modulated)
-        col15 = tex & 0x7FFF7FFFu;
-      else if (!gouraud)
-        col15 = pair_modulate<true>(tex, fr, fg, fb, d16);
-      else
-      {
-        const uint32_t c0 = mod5 ? 0xF8u : 0xFFu;
-        const uint32_t ar = __shfl_sync(0xFFFFFFFFu, rb_r, r) + T.ddx[0] * (2u * w), ag = __shfl_sync(0xFFFFFFFFu, rb_g, r) + T.ddx[1] * (2u * w),
-                       ab = __shfl_sync(0xFFFFFFFFu, rb_b, r) + T.ddx[2] * (2u * w);
-        const uint32_t tr = tex & 0x001F001Fu, tg = (tex >> 5) & 0x001F001Fu, tb = (tex >> 10) & 0x001F001Fu;
-        const uint32_t pr = (tr & 0xFFFFu) * ((ar >> 24) & c0) + (tr & 0xFFFF0000u) * (((ar + T.ddx[0]) >> 24) & c0);
-        const uint32_t pg = (tg & 0xFFFFu) * ((ag >> 24) & c0) + (tg & 0xFFFF0000u) * (((ag + T.ddx[1]) >> 24) & c0);
-        const uint32_t pb = (tb & 0xFFFFu) * ((ab >> 24) & c0) + (tb & 0xFFFF0000u) * (((ab + T.ddx[2]) >> 24) & c0);
-        col15 = pair_pack15(pr, pg, pb, d16);
-      }
+      we15 = cov15 & (((tex & 0x7FFF7FFFu) + 0x7FFF7FFFu) | tex) & ~(bg & D.chk15); // pair_we_textured
     }
     else
+      we15 = cov15 & ~(bg & D.chk15);
+
     {
-      we15 = pair_we_untextured(ps, bg, cov15);
-      if (!gouraud)
-        col15 = pair_pack15(fr, fg, fb, d16);
+      // (no per-lane condition around this block: it shuffles)
+      uint32_t col15;
+      if (!(path & LP_MODULATED))
+        col15 = tex & 0x7FFF7FFFu;
       else
       {
-        const uint32_t ar = __shfl_sync(0xFFFFFFFFu, rb_r, r) + T.ddx[0] * (2u * w), ag = __shfl_sync(0xFFFFFFFFu, rb_g, r) + T.ddx[1] * (2u * w),
-                       ab = __shfl_sync(0xFFFFFFFFu, rb_b, r) + T.ddx[2] * (2u * w);
-        const uint32_t pr = ((ar >> 24) << 4) + (((ar + T.ddx[0]) >> 24) << 20);
-        const uint32_t pg = ((ag >> 24) << 4) + (((ag + T.ddx[1]) >> 24) << 20);
-        const uint32_t pb = ((ab >> 24) << 4) + (((ab + T.ddx[2]) >> 24) << 20);
+        uint32_t pr, pg, pb;
+        if (path & LP_GOURAUD)
+        {
+          const uint32_t dr = T.ddx[0], dg = T.ddx[1], db = T.ddx[2], cm = D.misc2 & 0xFFu;
+          const uint32_t ar = __shfl_sync(0xFFFFFFFFu, rb_r, r) + dr * (2u * w), ag = __shfl_sync(0xFFFFFFFFu, rb_g, r) + dg * (2u * w),
+                         ab = __shfl_sync(0xFFFFFFFFu, rb_b, r) + db * (2u * w);
+          if (path & LP_TEXTURED)
+          {
+            const uint32_t tr = tex & 0x001F001Fu, tg = (tex >> 5) & 0x001F001Fu, tb = (tex >> 10) & 0x001F001Fu;
+            pr = (tr & 0xFFFFu) * ((ar >> 24) & cm) + (tr & 0xFFFF0000u) * (((ar + dr) >> 24) & cm);
+            pg = (tg & 0xFFFFu) * ((ag >> 24) & cm) + (tg & 0xFFFF0000u) * (((ag + dg) >> 24) & cm);
+            pb = (tb & 0xFFFFu) * ((ab >> 24) & cm) + (tb & 0xFFFF0000u) * (((ab + db) >> 24) & cm);
+          }
+          else
+          {
+            pr = ((ar >> 24) << 4) + (((ar + dr) >> 24) << 20);
+            pg = ((ag >> 24) << 4) + (((ag + dg) >> 24) << 20);
+            pb = ((ab >> 24) << 4) + (((ab + db) >> 24) << 20);
+          }
+        }
+        else if (path & LP_TEXTURED)
+        {
+          pr = (tex & 0x001F001Fu) * D.fr;
+          pg = ((tex >> 5) & 0x001F001Fu) * D.fg;
+          pb = ((tex >> 10) & 0x001F001Fu) * D.fb;
+        }
+        else
+        {
+          pr = D.fr;
+          pg = D.fg;
+          pb = D.fb;
+        }
         col15 = pair_pack15(pr, pg, pb, d16);
       }
-    }
-    if (we15)
-    {
-      const uint32_t out = pair_finish(ps, bg, col15, t15, we15);
-      if (out != bg)
-        *wp = out;
+      const uint32_t t15 = tex & 0x80008000u;
+      if (path & LP_TRANSP)
+      {
+        const uint32_t blended = pair_blend15((path >> LP_TMODE_SHIFT) & 3u, bg & 0x7FFF7FFFu, col15);
+        const uint32_t bm = (path & LP_TEXTURED) ? pk_expand15(t15) : 0xFFFFFFFFu;
+        col15 = (col15 & ~bm) | (blended & bm);
+      }
+      if (we15)
+      {
+        const uint32_t wm = pk_expand15(we15);
+        *wp = (bg & ~wm) | ((col15 | t15 | D.set15) & wm);
+      }
     }
   }
 }
@@ -421,21 +436,15 @@ __device__ __forceinline__ void raster_prim_on_region(const PrimSetup& s, uint32
                                                       const uint16_t* __restrict__ payload, uint16_t* clut_smem, uint32_t& clut_key,
                                                       uint32_t lane)
 {
-  const uint32_t* words = reinterpret_cast<const uint32_t*>(&s);
-  const uint32_t w0 = words[0], w1 = words[1];
-  const uint32_t op = w0 & 0xFFu;
-  const ShadeState st = shade_state_from_words(words);
-  PixelCtx ctx;
-  ctx.vram = vram;
-  ctx.clut = clut_smem;
-  if ((st.flags & F_TEXTURE) && (st.modes & 0xFFu) < 2u)
+  const uint32_t op = s.op;
+  if (op <= OP_RECT) // OP_TRIANGLE, OP_RECT
   {
     // paletted: make sure the merged palette is in shared memory (one coalesced 512-byte read when it changes)
-    const uint32_t lo = (w1 >> 16) & 0xFFu, hi = w1 >> 24, is8 = st.modes & 1u;
-    const uint32_t key = lo | ((is8 ? hi : lo) << 8) | (is8 << 16) | 0x80000000u;
-    if (key != clut_key)
+    const uint32_t key = s.desc.clut_key; // lo slot | hi slot << 8 | 8-bit << 16 | 1 << 31, 0 = no palette
+    if (key != 0 && key != clut_key)
     {
       clut_key = key;
+      const uint32_t lo = key & 0xFFu, hi = (key >> 8) & 0xFFu, is8 = (key >> 16) & 1u;
       uint4* dst = reinterpret_cast<uint4*>(clut_smem);
       if (is8)
       {
@@ -446,15 +455,18 @@ __device__ __forceinline__ void raster_prim_on_region(const PrimSetup& s, uint32
         dst[lane] = ld_ro<kCoh>(reinterpret_cast<const uint4*>(clut_pool_inst + lo * CLUT_ENTRIES) + lane);
       __syncwarp();
     }
+    raster_spans<RH, kCoh>(s, vram, clut_smem, region, rx0, ry0, lane);
+    return;
   }
+  const ShadeState st = shade_state_from_words(reinterpret_cast<const uint32_t*>(&s));
+  PixelCtx ctx;
+  ctx.vram = vram;
+  ctx.clut = clut_smem;
   uint16_t* region16 = reinterpret_cast<uint16_t*>(region);
   const int32_t x_min = static_cast<int32_t>(rx0);
 
   switch (op)
   {
-    case OP_TRIANGLE:
-    case OP_RECT: raster_spans<RH, kCoh>(s, st, vram, clut_smem, region, x_min, ry0, lane); break;
-
     case OP_LINE:
     {
       if (s.line.x_major)
@@ -697,7 +709,7 @@ __device__ void serial_self_sampling(const PrimSetup& s, uint16_t* vram, const u
   for (int part = 0; part < 2; part++)
   {
     const bool is_upper = (part == 0) != upper_up;
-    const int32_t lo = is_upper ? T.up_lo : T.lo_lo, hi = is_upper ? T.up_hi : T.lo_hi;
+    const int32_t lo = T.lo[is_upper ? 0 : 1], hi = T.hi[is_upper ? 0 : 1];
     const bool up = is_upper ? upper_up : lower_up;
     for (int32_t k = 0; k < hi - lo; k++)
     {
@@ -937,7 +949,6 @@ __device__ __forceinline__ void process_epoch_region(const WaveItem& it, RasterS
 {
   const uint32_t rx0 = tx * TILE_W;
   uint32_t* gword = reinterpret_cast<uint32_t*>(vram + ry0 * VRAM_W + rx0) + lane; // this lane's word of region row 0
-  const PrimSetup& staged = *reinterpret_cast<const PrimSetup*>(sh.stage);
 
   // Binning: tile_cmds holds, per group of 32 commands, one word per tile (setup_kernel).  A step covers 32 groups
   // (1024 commands), one load per lane; the set bits of the lanes expand into the list in command order, as many
@@ -997,21 +1008,27 @@ __device__ __forceinline__ void process_epoch_region(const WaveItem& it, RasterS
     __syncwarp();
 
     // ---- raster: walk the bin in order ----
-    const uint32_t* src = reinterpret_cast<const uint32_t*>(setups + it.cmd_begin + sh.list[0]);
-    uint32_t w0 = __ldg(src + lane), w1 = (lane < SETUP_WORDS - 32) ? __ldg(src + 32 + lane) : 0u;
+    // The 240-byte setup records travel global -> shared with 16-byte asynchronous copies (lanes 0-14), the next
+    // primitive's while the current one is rasterised: no register holds a record in flight.
+    const uint4* const setup_vecs = reinterpret_cast<const uint4*>(setups + it.cmd_begin);
+    if (lane < SETUP_VECS)
+      cp_async16(reinterpret_cast<uint4*>(sh.stage[0]) + lane, setup_vecs + static_cast<size_t>(sh.list[0]) * SETUP_VECS + lane);
+    cp_async_commit();
     if (!loaded)
     {
       // A FillVRAM (not interlaced) or an unmasked upload that covers the whole region overwrites every pixel of it:
       // the region's old contents need not be read (a frame clear would otherwise read all of VRAM first).
-      const uint32_t hw = __shfl_sync(0xFFFFFFFFu, w0, 0);
-      const uint32_t op = hw & 0xFFu;
+      cp_async_wait<0>();
+      __syncwarp();
+      const PrimSetup& first = *reinterpret_cast<const PrimSetup*>(sh.stage[0]);
+      const uint32_t op = first.op;
       bool overwritten = false;
-      if (op == OP_FILL || (op == OP_UPLOAD && !((hw >> 8) & F_CHECK_MASK)))
+      if (op == OP_FILL || (op == OP_UPLOAD && !(first.flags0 & F_CHECK_MASK)))
       {
-        const uint32_t xy = __shfl_sync(0xFFFFFFFFu, w0, 8), wh = __shfl_sync(0xFFFFFFFFu, w0, 9), misc = __shfl_sync(0xFFFFFFFFu, w0, 10);
-        const bool interlaced = (op == OP_FILL) && ((misc >> 16) & 0xFFu);
-        overwritten = !interlaced && (((rx0 - (xy & 0xFFFFu)) & (VRAM_W - 1)) + TILE_W <= (wh & 0xFFFFu)) &&
-                      (((ry0 - (xy >> 16)) & (VRAM_H - 1)) + RH <= (wh >> 16));
+        // (fill and upload share the x, y, w, h layout)
+        const bool interlaced = (op == OP_FILL) && first.fill.interlaced;
+        overwritten = !interlaced && (((rx0 - first.fill.x) & (VRAM_W - 1)) + TILE_W <= first.fill.w) &&
+                      (((ry0 - first.fill.y) & (VRAM_H - 1)) + RH <= first.fill.h);
       }
       if (!overwritten)
       {
@@ -1021,21 +1038,21 @@ __device__ __forceinline__ void process_epoch_region(const WaveItem& it, RasterS
       }
       loaded = true;
     }
+#pragma unroll 1
     for (uint32_t e = 0; e < list_n; e++)
     {
-      sh.stage[lane] = w0;
-      if (lane < SETUP_WORDS - 32)
-        sh.stage[32 + lane] = w1;
       if (e + 1 < list_n)
       {
-        // next primitive: issue its loads now, they complete while this one is rasterised
-        src = reinterpret_cast<const uint32_t*>(setups + it.cmd_begin + sh.list[e + 1]);
-        w0 = __ldg(src + lane);
-        if (lane < SETUP_WORDS - 32)
-          w1 = __ldg(src + 32 + lane);
+        if (lane < SETUP_VECS)
+          cp_async16(reinterpret_cast<uint4*>(sh.stage[(e + 1) & 1u]) + lane, setup_vecs + static_cast<size_t>(sh.list[e + 1]) * SETUP_VECS + lane);
+        cp_async_commit();
+        cp_async_wait<1>(); // this primitive's record has landed, the next one's stays in flight
       }
+      else
+        cp_async_wait<0>();
       __syncwarp();
-      raster_prim_on_region<RH, kCoh>(staged, sh.region, rx0, ry0, vram, cluts, payload, sh.clut, clut_key, lane);
+      raster_prim_on_region<RH, kCoh>(*reinterpret_cast<const PrimSetup*>(sh.stage[e & 1u]), sh.region, rx0, ry0, vram, cluts, payload, sh.clut,
+                                      clut_key, lane);
       __syncwarp();
     }
     list_n = 0;

@@ -204,19 +204,16 @@ PSX_HD bool tri_row(const PrimSetup& s, uint32_t Y, TriRow& row)
 {
   const auto& T = s.tri;
   const int32_t cy = T.y0 + static_cast<int32_t>((Y - static_cast<uint32_t>(static_cast<int32_t>(T.y0))) & (VRAM_H - 1));
-  uint64_t sx;
-  if (cy >= T.up_lo && cy < T.up_hi)
-    sx = T.up_start + static_cast<uint64_t>(static_cast<int64_t>(cy - T.up_anchor)) * T.up_step;
-  else if (cy >= T.lo_lo && cy < T.lo_hi)
-    sx = T.lo_start + static_cast<uint64_t>(static_cast<int64_t>(cy - T.lo_anchor)) * T.lo_step;
-  else
+  const uint32_t p = (cy >= T.y1) ? 1u : 0u;
+  const uint32_t k = static_cast<uint32_t>(cy - T.lo[p]); // row within the part
+  if (k >= static_cast<uint32_t>(T.hi[p] - T.lo[p]))
     return false;
   const int32_t y = sext11(cy);
   if (y < s.clip_t || y > s.clip_b || interlace_skip(s, static_cast<uint32_t>(cy)))
     return false;
-  const uint64_t lx = T.long_start + static_cast<uint64_t>(static_cast<int64_t>(cy - T.y0)) * T.long_step;
-  const int32_t x_start = static_cast<int32_t>(((T.tflags & TRI_SHORT_IS_RIGHT) ? lx : sx) >> 32);
-  const int32_t x_bound = static_cast<int32_t>(((T.tflags & TRI_SHORT_IS_RIGHT) ? sx : lx) >> 32);
+  const TriPart& P = T.part[p];
+  const int32_t x_start = static_cast<int32_t>((P.l_start + static_cast<uint64_t>(k) * P.l_step) >> 32);
+  const int32_t x_bound = static_cast<int32_t>((P.r_start + static_cast<uint64_t>(k) * P.r_step) >> 32);
   int32_t width = x_bound - x_start;
   int32_t cx = sext11(x_start);
   row.xdelta = x_start - cx;

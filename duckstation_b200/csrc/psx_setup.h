@@ -113,32 +113,88 @@ PSX_HD int32_t last_row_above_area(int32_t a, int32_t b, int32_t top)
   return a;
 }
 
+// Everything the raster kernel's word loop reads per primitive, derived once here (psx_types.h:LoopDesc).
+PSX_HD void make_loop_desc(PrimSetup& s)
+{
+  LoopDesc& D = s.desc;
+  const bool tri = s.op == OP_TRIANGLE;
+  const bool textured = (s.flags0 & F_TEXTURE) != 0, raw = textured && (s.flags0 & F_RAW);
+  const bool mod5 = (s.flags1 & F1_MOD5) != 0;
+  const uint32_t mode = s.texmode, tsh = 2u - mode;
+  D.and_x2 = s.win_and_x * 0x00010001u;
+  D.or_x2 = s.win_or_x * 0x00010001u;
+  D.and_y2 = s.win_and_y * 0x00010001u;
+  D.or_y2 = s.win_or_y * 0x00010001u;
+  D.tex_bx2 = s.tex_bx * 0x00010001u;
+  D.sub_mask2 = ((1u << tsh) - 1u) * 0x00010001u;
+  D.tex_rows = static_cast<uint32_t>(s.tex_by) * VRAM_W;
+  D.tex_misc = tsh | ((2u + mode) << 8) | ((mode < 2u ? ((1u << (4u << mode)) - 1u) : 0u) << 16);
+  uint32_t r = tri ? s.tri.flat_r : s.rect.r, g = tri ? s.tri.flat_g : s.rect.g, b = tri ? s.tri.flat_b : s.rect.b;
+  if (textured)
+  {
+    if (mod5)
+    {
+      r &= 0xF8u; // Modulate5Bit: (t * (c >> 3)) >> 1 == (t * (c & 0xF8)) >> 4
+      g &= 0xF8u;
+      b &= 0xF8u;
+    }
+  }
+  else
+  {
+    r *= 0x00100010u;
+    g *= 0x00100010u;
+    b *= 0x00100010u;
+  }
+  D.fr = r;
+  D.fg = g;
+  D.fb = b;
+  D.chk15 = (s.flags0 & F_CHECK_MASK) ? 0x80008000u : 0u;
+  D.set15 = (s.flags0 & F_SET_MASK) ? 0x80008000u : 0u;
+  uint32_t path = tri ? LP_TRI : 0u;
+  if (textured)
+    path |= LP_TEXTURED | (mode < 2u ? LP_PALETTED : 0u);
+  if (!raw)
+    path |= LP_MODULATED | ((tri && (s.flags0 & F_SHADED)) ? LP_GOURAUD : 0u);
+  if (s.flags1 & F1_DITHER)
+    path |= LP_DITHER;
+  if (s.flags0 & F_TRANSP)
+    path |= LP_TRANSP;
+  path |= ((static_cast<uint32_t>(s.draw_mode) >> 5) & 3u) << LP_TMODE_SHIFT;
+  if (s.win_and_x != 0xFF || s.win_and_y != 0xFF || s.win_or_x != 0 || s.win_or_y != 0)
+    path |= LP_WINDOW;
+  D.path = path;
+  const uint32_t ubase = tri ? 0u : ((static_cast<uint32_t>(s.rect.u0) - static_cast<uint32_t>(static_cast<int32_t>(s.rect.x))) & 0xFFu);
+  D.misc2 = ((textured && mod5) ? 0xF8u : 0xFFu) | (ubase << 8);
+  const uint32_t is8 = mode & 1u;
+  D.clut_key = (textured && mode < 2u) ? (s.clut_lo | (static_cast<uint32_t>(is8 ? s.clut_hi : s.clut_lo) << 8) | (is8 << 16) | 0x80000000u) : 0u;
+}
+
 PSX_HD void setup_triangle(const PackedCmd& c, PrimSetup& s, BinInfo& bin)
 {
-  PackedVertex v0 = c.v[0], v1 = c.v[1], v2 = c.v[2], t;
-  uint32_t tl;
-  if (v1.x <= v0.x)
-    tl = (v2.x <= v1.x) ? 4u : 2u;
-  else if (v2.x < v0.x)
-    tl = 4u;
+  // The reference picks a "core" vertex from the x order of the vertices as submitted (inl:1432-1441: the leftmost,
+  // with its tie rules), then sorts the three by y with three neighbour swaps and keeps track of where the core
+  // vertex goes (inl:1443-1456).  Here: the core vertex by its submitted index, and the same three swaps on an index
+  // permutation.
+  const PackedVertex in[3] = {c.v[0], c.v[1], c.v[2]};
+  uint32_t core;
+  if (in[1].x <= in[0].x)
+    core = (in[2].x <= in[1].x) ? 2u : 1u;
   else
-    tl = 1u;
-  if (v2.y < v1.y)
-  {
-    t = v2, v2 = v1, v1 = t;
-    tl = ((tl >> 1) & 2u) | ((tl << 1) & 4u) | (tl & 1u);
-  }
-  if (v1.y < v0.y)
-  {
-    t = v1, v1 = v0, v0 = t;
-    tl = ((tl >> 1) & 1u) | ((tl << 1) & 2u) | (tl & 4u);
-  }
-  if (v2.y < v1.y)
-  {
-    t = v2, v2 = v1, v1 = t;
-    tl = ((tl >> 1) & 2u) | ((tl << 1) & 4u) | (tl & 1u);
-  }
-  tl >>= 1;
+    core = (in[2].x < in[0].x) ? 2u : 0u;
+  uint32_t order[3] = {0, 1, 2};
+  auto swap_if_above = [&](uint32_t a, uint32_t b) {
+    if (in[order[b]].y < in[order[a]].y)
+    {
+      const uint32_t t = order[a];
+      order[a] = order[b];
+      order[b] = t;
+    }
+  };
+  swap_if_above(1, 2);
+  swap_if_above(0, 1);
+  swap_if_above(1, 2);
+  const PackedVertex v0 = in[order[0]], v1 = in[order[1]], v2 = in[order[2]];
+  const uint32_t tl = (order[0] == core) ? 0u : ((order[1] == core) ? 1u : 2u); // position of the core vertex after the sort
   if (v0.y == v2.y)
     return set_nop(s, bin);
   const int32_t det = static_cast<int32_t>((static_cast<uint32_t>(v1.x - v0.x) * static_cast<uint32_t>(v2.y - v1.y)) -
@@ -154,38 +210,53 @@ PSX_HD void setup_triangle(const PackedCmd& c, PrimSetup& s, BinInfo& bin)
   const bool right_facing = (v1.y == v0.y) ? (v1.x > v0.x) : (bound_us > base_step);
 
   auto& T = s.tri;
-  T.long_start = static_cast<uint64_t>(makefp_xy(v0.x));
-  T.long_step = static_cast<uint64_t>(base_step);
   T.y0 = v0.y;
   T.y1 = v1.y;
-  T.up_start = static_cast<uint64_t>(makefp_xy(upper_up ? v1.x : v0.x));
-  T.up_anchor = upper_up ? v1.y : v0.y;
-  T.up_step = static_cast<uint64_t>(bound_us);
-  T.lo_start = static_cast<uint64_t>(makefp_xy(lower_up ? v2.x : v1.x));
-  T.lo_anchor = lower_up ? v2.y : v1.y;
-  T.lo_step = static_cast<uint64_t>(bound_ls);
   T.tflags = static_cast<uint8_t>((right_facing ? TRI_SHORT_IS_RIGHT : 0) | (upper_up ? TRI_UPPER_UP : 0) | (lower_up ? TRI_LOWER_UP : 0));
 
+  // effective row ranges (break emulation, inl:1351-1353 / 1391-1394)
   const int32_t top = c.clip_t, bottom = c.clip_b;
+  int32_t lo[2], hi[2];
   if (upper_up)
   {
-    T.up_lo = static_cast<int16_t>(last_row_above_area(v0.y, v1.y, top));
-    T.up_hi = v1.y;
+    lo[0] = last_row_above_area(v0.y, v1.y, top);
+    hi[0] = v1.y;
   }
   else
   {
-    T.up_lo = v0.y;
-    T.up_hi = static_cast<int16_t>(first_row_below_area(v0.y, v1.y, bottom));
+    lo[0] = v0.y;
+    hi[0] = first_row_below_area(v0.y, v1.y, bottom);
   }
   if (lower_up)
   {
-    T.lo_lo = static_cast<int16_t>(last_row_above_area(v1.y, v2.y, top));
-    T.lo_hi = v2.y;
+    lo[1] = last_row_above_area(v1.y, v2.y, top);
+    hi[1] = v2.y;
   }
   else
   {
-    T.lo_lo = v1.y;
-    T.lo_hi = static_cast<int16_t>(first_row_below_area(v1.y, v2.y, bottom));
+    lo[1] = v1.y;
+    hi[1] = first_row_below_area(v1.y, v2.y, bottom);
+  }
+  // The long edge is one line over both parts (both TriangleParts start it at base + (start_y - v0.y) * step); a short
+  // edge is anchored at the vertex its part is walked from (the steps are truncated quotients, so the anchor matters).
+  // Both are re-anchored at the part's first effective row, in modular arithmetic, so that the kernel multiplies by a
+  // row offset >= 0.
+  const uint64_t long_start = static_cast<uint64_t>(makefp_xy(v0.x)), long_step = static_cast<uint64_t>(base_step);
+  const uint64_t short_start[2] = {static_cast<uint64_t>(makefp_xy(upper_up ? v1.x : v0.x)), static_cast<uint64_t>(makefp_xy(lower_up ? v2.x : v1.x))};
+  const int32_t short_anchor[2] = {upper_up ? v1.y : v0.y, lower_up ? v2.y : v1.y};
+  const uint64_t short_step[2] = {static_cast<uint64_t>(bound_us), static_cast<uint64_t>(bound_ls)};
+  for (int p = 0; p < 2; p++)
+  {
+    if (hi[p] < lo[p])
+      hi[p] = lo[p];
+    T.lo[p] = static_cast<int16_t>(lo[p]);
+    T.hi[p] = static_cast<int16_t>(hi[p]);
+    const uint64_t ls = long_start + static_cast<uint64_t>(static_cast<int64_t>(lo[p] - v0.y)) * long_step;
+    const uint64_t ss = short_start[p] + static_cast<uint64_t>(static_cast<int64_t>(lo[p] - short_anchor[p])) * short_step[p];
+    T.part[p].l_start = right_facing ? ls : ss;
+    T.part[p].l_step = right_facing ? long_step : short_step[p];
+    T.part[p].r_start = right_facing ? ss : ls;
+    T.part[p].r_step = right_facing ? short_step[p] : long_step;
   }
 
   const PackedVertex tv = (tl == 0) ? v0 : ((tl == 1) ? v1 : v2);
@@ -238,6 +309,7 @@ PSX_HD void setup_triangle(const PackedCmd& c, PrimSetup& s, BinInfo& bin)
   if (x1 < x0 || rc <= 0)
     return set_nop(s, bin);
   set_bins(s, bin, x0, x1, static_cast<uint32_t>(r0), static_cast<uint32_t>(rc), false, 0, 0);
+  make_loop_desc(s);
 }
 
 PSX_HD void setup_rect(const PackedCmd& c, PrimSetup& s, BinInfo& bin)
@@ -273,6 +345,7 @@ PSX_HD void setup_rect(const PackedCmd& c, PrimSetup& s, BinInfo& bin)
   if (x1 < x0 || y1 < y0)
     return set_nop(s, bin);
   set_bins(s, bin, x0, x1, static_cast<uint32_t>(y0), static_cast<uint32_t>(y1 - y0 + 1), false, 0, 0);
+  make_loop_desc(s);
 }
 
 PSX_HD int32_t iabs(int32_t v)

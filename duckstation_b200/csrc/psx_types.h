@@ -144,7 +144,43 @@ struct ClutOp
 };
 static_assert(sizeof(ClutOp) == 8, "ClutOp");
 
-// ---- device-side setup record: 160 bytes, read by the raster kernel ----
+// What the raster kernel's word loop needs from a triangle / rectangle, every derived constant ready to use (the loop
+// reads them from the staged record with LDS instead of holding them in registers; psx_setup.h:make_loop_desc).
+enum : uint32_t
+{
+  LP_TEXTURED = 0x001,
+  LP_PALETTED = 0x002,  // 4- or 8-bit texture: the texel is a palette index
+  LP_MODULATED = 0x004, // the colours matter: untextured, or textured and not raw
+  LP_GOURAUD = 0x008,   // per-pixel colours (shaded triangle whose colours matter)
+  LP_DITHER = 0x010,
+  LP_TRANSP = 0x020,
+  LP_TMODE_SHIFT = 6,   // bits 6-7: semi-transparency mode
+  LP_TRI = 0x100,
+  LP_WINDOW = 0x200,    // a texture window other than and = 0xFF, or = 0
+};
+struct alignas(16) LoopDesc
+{
+  uint32_t and_x2, or_x2, and_y2, or_y2; // texture window, each byte value in both halves
+  uint32_t tex_bx2;   // texture page base column in both halves
+  uint32_t sub_mask2; // (texels per VRAM word - 1) in both halves
+  uint32_t tex_rows;  // texture page base row * 1024
+  uint32_t tex_misc;  // log2(texels per word) | log2(bits per texel) << 8 | palette index mask << 16
+  uint32_t fr, fg, fb; // flat colour: textured = the 8-bit values (Modulate5Bit crop applied), untextured = 16 c in both halves
+  uint32_t chk15;     // 0x80008000 if the mask bit is tested
+  uint32_t set15;     // 0x80008000 if the mask bit is set
+  uint32_t path;      // LP_*
+  uint32_t misc2;     // bits 0-7: 0xFF, or 0xF8 with Modulate5Bit (applied to interpolated colours); bits 8-15: rectangle (u0 - x) & 0xFF
+  uint32_t clut_key;  // paletted: lo slot | hi slot << 8 | 8-bit << 16 | 1 << 31 (which palette the loop wants staged); else 0
+};
+static_assert(sizeof(LoopDesc) == 64, "LoopDesc");
+
+// One y-range of a triangle: both edges as x(cy) = start + (cy - lo) * step (mod 2^64, then >> 32), lo = first row.
+struct TriPart
+{
+  uint64_t l_start, l_step, r_start, r_step;
+};
+
+// ---- device-side setup record: 240 bytes, read by the raster kernel ----
 struct alignas(16) PrimSetup
 {
   // 32-byte common header
@@ -161,17 +197,14 @@ struct alignas(16) PrimSetup
   {
     struct
     {
-      // edges: x(cy) = start + (cy - anchor) * step   (mod 2^64), then >> 32
-      uint64_t long_start, long_step; // anchored at y0
-      uint64_t up_start, up_step;     // rows cy < y1
-      uint64_t lo_start, lo_step;     // rows cy >= y1
+      TriPart part[2];  // [0] rows cy < y1, [1] rows cy >= y1; left / right edge, anchored at the part's first row
       int16_t y0, y1;
-      int16_t up_anchor, lo_anchor;
-      int16_t up_lo, up_hi, lo_lo, lo_hi; // effective row ranges [lo, hi) after break emulation
-      uint32_t base[5], ddx[5], ddy[5];   // r g b u v : value(x,cy) = base + ddx*x + ddy*cy, top byte
-      uint8_t tflags;                     // TRI_SHORT_IS_RIGHT | TRI_UPPER_UP | TRI_LOWER_UP
+      int16_t lo[2], hi[2]; // effective row range [lo, hi) of each part after break emulation (hi >= lo)
+      uint8_t tflags;       // TRI_SHORT_IS_RIGHT | TRI_UPPER_UP | TRI_LOWER_UP
       uint8_t flat_r, flat_g, flat_b;
-    } tri; // 48 + 16 + 60 + 4 = 128
+      uint32_t base[5], ddx[5], ddy[5]; // r g b u v : value(x,cy) = base + ddx*x + ddy*cy, top byte
+      uint32_t pad;
+    } tri; // 64 + 16 + 60 + 4 = 144
     struct
     {
       int16_t x, y;
@@ -202,10 +235,11 @@ struct alignas(16) PrimSetup
       uint16_t x, y, w, h;
       uint32_t payload;
     } upload;
-    uint32_t words[32];
+    uint32_t words[36];
   };
+  LoopDesc desc; // triangles and rectangles
 };
-static_assert(sizeof(PrimSetup) == 160, "PrimSetup must be 160 bytes");
+static_assert(sizeof(PrimSetup) == 240, "PrimSetup must be 240 bytes");
 
 // Binning words produced by setup, read by every tile CTA of the epoch.
 struct BinInfo

@@ -179,7 +179,7 @@ void run_self_sampling(const PrimSetup& s)
     bool up;
   };
   const bool upper_is_up = (T.tflags & TRI_UPPER_UP) != 0, lower_is_up = (T.tflags & TRI_LOWER_UP) != 0;
-  Part upper{T.up_lo, T.up_hi, upper_is_up}, lower{T.lo_lo, T.lo_hi, lower_is_up};
+  Part upper{T.lo[0], T.hi[0], upper_is_up}, lower{T.lo[1], T.hi[1], lower_is_up};
   Part order[2];
   if (upper_is_up)
   {
