@@ -112,8 +112,11 @@ constexpr int SERIAL_THREADS = 256;                     // serial_kernel: one CT
 constexpr int SERIAL_WARPS = SERIAL_THREADS / 32;
 constexpr uint32_t LIST_CAP = 160;                      // per-tile bin capacity between raster phases (5216 B per warp: 32 warps fit the 196 KB shared-memory configuration, L1 keeps 60 KB)
 constexpr uint32_t SETUP_WORDS = sizeof(PrimSetup) / 4; // 60
-constexpr uint32_t SETUP_VECS = sizeof(PrimSetup) / 16; // 15
-constexpr uint32_t REGION_PITCH = 33;                   // words per tile row in shared memory (+1: bank skew)
+constexpr uint32_t SETUP_VECS = sizeof(PrimSetup) / 16; // 16
+#ifndef PSX_REGION_PITCH
+#define PSX_REGION_PITCH 36
+#endif
+constexpr uint32_t REGION_PITCH = PSX_REGION_PITCH;     // words per tile row in shared memory (+4: the same column of eight consecutive rows lands in eight different groups of four banks — narrow spans stacked over rows are what the word loop touches)
 constexpr uint32_t REGION_PITCH16 = REGION_PITCH * 2;   // same, in pixels
 
 // Per-warp shared memory.  raster_kernel: one warp == one CTA == one 64x32 tile (RH = 32), 5.5 KiB, so 32 CTAs fit an SM.
@@ -121,7 +124,7 @@ constexpr uint32_t REGION_PITCH16 = REGION_PITCH * 2;   // same, in pixels
 template<uint32_t RH>
 struct alignas(16) RasterShared
 {
-  uint32_t region[RH * REGION_PITCH];     // the region, 2 pixels per word (4224 B at RH = 32)
+  uint32_t region[RH * REGION_PITCH];     // the region, 2 pixels per word (4608 B at RH = 32)
   uint32_t stage[2][SETUP_WORDS];         // the primitive being rasterised and the next one (cp.async double buffer)
   uint16_t clut[CLUT_ENTRIES];            // merged palette of the current primitive (entries 0-15 lo slot, 16-255 hi slot)
   uint16_t list[LIST_CAP];                // bin: primitive indices (relative to the epoch), submission order
@@ -203,8 +206,10 @@ constexpr uint32_t ROW_EMPTY = 0x40000000u;
 __device__ __forceinline__ uint32_t row_of_pixel(uint32_t start, uint32_t base, uint32_t rowmap, uint32_t lane)
 {
   const uint32_t t = start - base;
-  const uint32_t marks = __reduce_or_sync(0xFFFFFFFFu, ((t - 1u) < 31u) ? (1u << t) : 0u);
-  const uint32_t before = __popc(__ballot_sync(0xFFFFFFFFu, static_cast<int32_t>(t) <= 0));
+  uint32_t mark;
+  asm("shl.b32 %0, 1, %1;" : "=r"(mark) : "r"(t)); // PTX shl clamps the amount: 0 for t >= 32 (later batches, empty rows) and for "negative" t
+  const uint32_t marks = __reduce_or_sync(0xFFFFFFFFu, mark);
+  const uint32_t before = __popc(__ballot_sync(0xFFFFFFFFu, static_cast<int32_t>(t) < 0));
   const uint32_t k = before - 1u + __popc(marks & ((2u << lane) - 1u));
   return __shfl_sync(0xFFFFFFFFu, rowmap, k);
 }
@@ -252,25 +257,39 @@ __device__ __forceinline__ void raster_spans(const PrimSetup& s, const uint16_t*
   uint32_t rb_r = 0, rb_g = 0, rb_b = 0, rb_u = 0, rb_v = 0; // triangle: interpolant at tile column 0 of this row; rectangle: rb_v = v
   if (path & LP_TRI)
   {
-    // tri_row (psx_pixel.h) with the clip against the tile folded in
-    const int32_t cy = T.y0 + static_cast<int32_t>((ry0 + lane - static_cast<uint32_t>(static_cast<int32_t>(T.y0))) & (VRAM_H - 1));
-    const uint32_t p = (cy >= T.y1) ? 1u : 0u;
-    const uint32_t k = static_cast<uint32_t>(cy - T.lo[p]);
-    const int32_t y = sext11(cy);
-    const bool ok = (RH == 32 || lane < RH) && k < static_cast<uint32_t>(T.hi[p] - T.lo[p]) && y >= s.clip_t && y <= s.clip_b &&
-                    !interlace_skip(s, static_cast<uint32_t>(cy));
-    const TriPart& P = T.part[p];
-    const int32_t x_start = static_cast<int32_t>((P.l_start + static_cast<uint64_t>(k) * P.l_step) >> 32);
-    const int32_t x_bound = static_cast<int32_t>((P.r_start + static_cast<uint64_t>(k) * P.r_step) >> 32);
-    const int32_t cx = sext11(x_start);
-    const int32_t lo = imax(imax(cx, s.clip_l), static_cast<int32_t>(rx0));
-    const int32_t hi = imin(imin(cx + (x_bound - x_start), s.clip_r + 1), static_cast<int32_t>(rx0 + TILE_W));
-    if (ok && hi > lo)
+    int32_t lo, hi, cy, xdelta = 0;
+    bool ok;
+    if (!(path & LP_COMPLEX))
+    {
+      // tri_row (psx_pixel.h) for a triangle whose coordinates stay inside 11 bits: no wrap of rows or columns, and
+      // the drawing area's rows are already cut into the row ranges (psx_setup.h)
+      cy = T.y0 + static_cast<int32_t>((ry0 + lane - static_cast<uint32_t>(static_cast<int32_t>(T.y0))) & (VRAM_H - 1));
+      const uint32_t p = (cy >= T.y1) ? 1u : 0u;
+      const uint32_t k = static_cast<uint32_t>(cy - T.lo[p]);
+      ok = (RH == 32 || lane < RH) & (k < static_cast<uint32_t>(T.hi[p] - T.lo[p]));
+      if (path & LP_INTERLACED)
+        ok = ok & !interlace_skip(s, static_cast<uint32_t>(cy));
+      const TriPart& P = T.part[p];
+      const int32_t x_start = static_cast<int32_t>((P.l_start + static_cast<uint64_t>(k) * P.l_step) >> 32);
+      const int32_t x_bound = static_cast<int32_t>((P.r_start + static_cast<uint64_t>(k) * P.r_step) >> 32);
+      lo = imax(imax(x_start, s.clip_l), static_cast<int32_t>(rx0));
+      hi = imin(imin(x_bound, s.clip_r + 1), static_cast<int32_t>(rx0 + TILE_W));
+    }
+    else
+    {
+      TriRow row;
+      ok = (RH == 32 || lane < RH) && tri_row(s, ry0 + lane, row);
+      cy = row.cy;
+      xdelta = row.xdelta;
+      lo = imax(row.x_lo, static_cast<int32_t>(rx0));
+      hi = imin(row.x_hi, static_cast<int32_t>(rx0 + TILE_W));
+    }
+    if (ok & (hi > lo))
     {
       xs = lo - static_cast<int32_t>(rx0);
       xe = hi - static_cast<int32_t>(rx0);
     }
-    const uint32_t ucy = static_cast<uint32_t>(cy), x0 = rx0 + static_cast<uint32_t>(x_start - cx);
+    const uint32_t ucy = static_cast<uint32_t>(cy), x0 = rx0 + static_cast<uint32_t>(xdelta);
     if (path & LP_GOURAUD)
     {
       rb_r = T.base[0] + T.ddy[0] * ucy + T.ddx[0] * x0;
@@ -304,13 +323,19 @@ __device__ __forceinline__ void raster_spans(const PrimSetup& s, const uint16_t*
   // word of compacted index j = wrel + j; the span is [xs, xe) in tile columns
   const uint32_t packed = (static_cast<uint32_t>((xs >> 1) - static_cast<int32_t>(incl - cnt)) & 0xFFFFu) |
                           (static_cast<uint32_t>(xs) << 16) | (static_cast<uint32_t>(xe) << 24);
-  const uint32_t ub = ((D.misc2 >> 8) + rx0) & 0xFFu; // rectangle: u of tile column 0 (mod 256: (ub + column) * 0x10001 cannot carry)
+  const uint32_t ub = (D.ubase + rx0) & 0xFFu; // rectangle: u of tile column 0 (mod 256: (ub + column) * 0x10001 cannot carry)
 
+  // The loop is software-pipelined by hand: the row lookup of the next batch (a REDUX, two POPC and two dependent
+  // shuffles) is issued right after this batch's texel loads, so that it runs while they are in flight.
+  // warp-uniform constants of the loop, read once (the compiler keeps them in uniform registers)
+  const uint32_t c_chk15 = D.chk15, c_set15 = D.set15, c_tex_shift = D.tex_shift, c_tex_bx2 = D.tex_bx2, c_trow = D.tex_rows;
+  const uint32_t c_sub_mask2 = D.sub_mask2, c_sub_shift = D.sub_shift, c_im = D.idx_mask, c_fr = D.fr, c_fg = D.fg, c_fb = D.fb;
+  const uint32_t c_du = T.ddx[3], c_dv = T.ddx[4];
+  uint32_t r = row_of_pixel(start, 0, rowmap, lane);
+  uint32_t pk = __shfl_sync(0xFFFFFFFFu, packed, r);
 #pragma unroll 1
   for (uint32_t base = 0; base < total; base += 32)
   {
-    const uint32_t r = row_of_pixel(start, base, rowmap, lane);
-    const uint32_t pk = __shfl_sync(0xFFFFFFFFu, packed, r);
     const uint32_t w = pk_prmt<0x9910>(pk, 0) + base + lane; // sign-extended word offset + j = word of the tile row
     // coverage of the two halves: column 2w >= xs, column 2w + 1 < xe (bit 15 of each half; the bias keeps the halves
     // apart).  Lanes past the last word of the batch land behind their row's last word: not covered.
@@ -326,13 +351,13 @@ __device__ __forceinline__ void raster_spans(const PrimSetup& s, const uint16_t*
       d16 = 0x0000FFC0u + (r & 1u) * 0xFFDF0060u + ((w ^ (r >> 1)) & 1u) * 0x00100010u;
     }
 
-    uint32_t tex = 0, we15;
+    uint32_t t0 = 0, t1 = 0, U = 0;
     if (path & LP_TEXTURED)
     {
-      uint32_t U, V;
+      uint32_t V;
       if (path & LP_TRI)
       {
-        const uint32_t du = T.ddx[3], dv = T.ddx[4];
+        const uint32_t du = c_du, dv = c_dv;
         const uint32_t u0 = __shfl_sync(0xFFFFFFFFu, rb_u, r) + du * (2u * w);
         const uint32_t v0 = __shfl_sync(0xFFFFFFFFu, rb_v, r) + dv * (2u * w);
         U = __byte_perm(u0, u0 + du, 0x7733); // top bytes; the odd bytes are cleared by the masks below
@@ -353,77 +378,92 @@ __device__ __forceinline__ void raster_spans(const PrimSetup& s, const uint16_t*
         U &= 0x00FF00FFu;
         V &= 0x00FF00FFu;
       }
-      // psx_pixel.h:texel_addr on both pixels at once
-      const uint32_t misc = D.tex_misc;
-      const uint32_t tx = ((U >> (misc & 0xFFu)) + D.tex_bx2) & 0x03FF03FFu;
-      const uint16_t* texrows = vram + D.tex_rows; // page base row (0 or 256): row + v never wraps
-      uint32_t t0 = ld_ro<kCoh>(texrows + (((V & 0xFFFFu) << 10) + (tx & 0xFFFFu)));
-      uint32_t t1 = ld_ro<kCoh>(texrows + (((V >> 16) << 10) + (tx >> 16)));
+      // psx_pixel.h:texel_addr on both pixels at once; page base row (0 or 256) + v never wraps
+      const uint32_t tx = ((U >> c_tex_shift) + c_tex_bx2) & 0x03FF03FFu;
+      const uint32_t trow = c_trow;
+      t0 = ld_ro<kCoh>(vram + (trow + ((V & 0xFFFFu) << 10) + (tx & 0xFFFFu)));
+      t1 = ld_ro<kCoh>(vram + (trow + ((V >> 16) << 10) + (tx >> 16)));
+    }
+    // per-pixel colours (before the row lookup moves on)
+    uint32_t ar = 0, ag = 0, ab = 0;
+    if (path & LP_GOURAUD)
+    {
+      ar = __shfl_sync(0xFFFFFFFFu, rb_r, r) + T.ddx[0] * (2u * w);
+      ag = __shfl_sync(0xFFFFFFFFu, rb_g, r) + T.ddx[1] * (2u * w);
+      ab = __shfl_sync(0xFFFFFFFFu, rb_b, r) + T.ddx[2] * (2u * w);
+    }
+    // next batch's row lookup, while the texel loads are in flight
+    if (base + 32 < total)
+    {
+      r = row_of_pixel(start, base + 32, rowmap, lane);
+      pk = __shfl_sync(0xFFFFFFFFu, packed, r);
+    }
+
+    uint32_t tex = 0, we15;
+    if (path & LP_TEXTURED)
+    {
       if (path & LP_PALETTED)
       {
-        const uint32_t sub = (U & D.sub_mask2) << ((misc >> 8) & 0xFFu); // bit offset of the index in its word
-        t0 = clut_smem[(t0 >> (sub & 0xFFFFu)) & (misc >> 16)];
-        t1 = clut_smem[(t1 >> (sub >> 16)) & (misc >> 16)];
+        const uint32_t sub = (U & c_sub_mask2) << c_sub_shift; // bit offset of the index in its word
+        const uint32_t im = c_im;
+        t0 = clut_smem[(t0 >> (sub & 0xFFFFu)) & im];
+        t1 = clut_smem[(t1 >> (sub >> 16)) & im];
       }
-      tex = t0 | (t1 << 16);
-      we15 = cov15 & (((tex & 0x7FFF7FFFu) + 0x7FFF7FFFu) | tex) & ~(bg & D.chk15); // pair_we_textured
+      tex = __byte_perm(t0, t1, 0x5410);
+      we15 = cov15 & (((tex & 0x7FFF7FFFu) + 0x7FFF7FFFu) | tex) & ~(bg & c_chk15); // pair_we_textured
     }
     else
-      we15 = cov15 & ~(bg & D.chk15);
+      we15 = cov15 & ~(bg & c_chk15);
 
+    uint32_t col15;
+    if (!(path & LP_MODULATED))
+      col15 = tex & 0x7FFF7FFFu;
+    else
     {
-      // (no per-lane condition around this block: it shuffles)
-      uint32_t col15;
-      if (!(path & LP_MODULATED))
-        col15 = tex & 0x7FFF7FFFu;
-      else
+      uint32_t pr, pg, pb;
+      if (path & LP_GOURAUD)
       {
-        uint32_t pr, pg, pb;
-        if (path & LP_GOURAUD)
+        const uint32_t dr = T.ddx[0], dg = T.ddx[1], db = T.ddx[2];
+        if (path & LP_TEXTURED)
         {
-          const uint32_t dr = T.ddx[0], dg = T.ddx[1], db = T.ddx[2], cm = D.misc2 & 0xFFu;
-          const uint32_t ar = __shfl_sync(0xFFFFFFFFu, rb_r, r) + dr * (2u * w), ag = __shfl_sync(0xFFFFFFFFu, rb_g, r) + dg * (2u * w),
-                         ab = __shfl_sync(0xFFFFFFFFu, rb_b, r) + db * (2u * w);
-          if (path & LP_TEXTURED)
-          {
-            const uint32_t tr = tex & 0x001F001Fu, tg = (tex >> 5) & 0x001F001Fu, tb = (tex >> 10) & 0x001F001Fu;
-            pr = (tr & 0xFFFFu) * ((ar >> 24) & cm) + (tr & 0xFFFF0000u) * (((ar + dr) >> 24) & cm);
-            pg = (tg & 0xFFFFu) * ((ag >> 24) & cm) + (tg & 0xFFFF0000u) * (((ag + dg) >> 24) & cm);
-            pb = (tb & 0xFFFFu) * ((ab >> 24) & cm) + (tb & 0xFFFF0000u) * (((ab + db) >> 24) & cm);
-          }
-          else
-          {
-            pr = ((ar >> 24) << 4) + (((ar + dr) >> 24) << 20);
-            pg = ((ag >> 24) << 4) + (((ag + dg) >> 24) << 20);
-            pb = ((ab >> 24) << 4) + (((ab + db) >> 24) << 20);
-          }
-        }
-        else if (path & LP_TEXTURED)
-        {
-          pr = (tex & 0x001F001Fu) * D.fr;
-          pg = ((tex >> 5) & 0x001F001Fu) * D.fg;
-          pb = ((tex >> 10) & 0x001F001Fu) * D.fb;
+          const uint32_t cm = D.cmask;
+          const uint32_t tr = tex & 0x001F001Fu, tg = (tex >> 5) & 0x001F001Fu, tb = (tex >> 10) & 0x001F001Fu;
+          pr = (tr & 0xFFFFu) * ((ar >> 24) & cm) + (tr & 0xFFFF0000u) * (((ar + dr) >> 24) & cm);
+          pg = (tg & 0xFFFFu) * ((ag >> 24) & cm) + (tg & 0xFFFF0000u) * (((ag + dg) >> 24) & cm);
+          pb = (tb & 0xFFFFu) * ((ab >> 24) & cm) + (tb & 0xFFFF0000u) * (((ab + db) >> 24) & cm);
         }
         else
         {
-          pr = D.fr;
-          pg = D.fg;
-          pb = D.fb;
+          pr = ((ar >> 24) << 4) + (((ar + dr) >> 24) << 20);
+          pg = ((ag >> 24) << 4) + (((ag + dg) >> 24) << 20);
+          pb = ((ab >> 24) << 4) + (((ab + db) >> 24) << 20);
         }
-        col15 = pair_pack15(pr, pg, pb, d16);
       }
-      const uint32_t t15 = tex & 0x80008000u;
-      if (path & LP_TRANSP)
+      else if (path & LP_TEXTURED)
       {
-        const uint32_t blended = pair_blend15((path >> LP_TMODE_SHIFT) & 3u, bg & 0x7FFF7FFFu, col15);
-        const uint32_t bm = (path & LP_TEXTURED) ? pk_expand15(t15) : 0xFFFFFFFFu;
-        col15 = (col15 & ~bm) | (blended & bm);
+        pr = (tex & 0x001F001Fu) * c_fr;
+        pg = ((tex >> 5) & 0x001F001Fu) * c_fg;
+        pb = ((tex >> 10) & 0x001F001Fu) * c_fb;
       }
-      if (we15)
+      else
       {
-        const uint32_t wm = pk_expand15(we15);
-        *wp = (bg & ~wm) | ((col15 | t15 | D.set15) & wm);
+        pr = c_fr;
+        pg = c_fg;
+        pb = c_fb;
       }
+      col15 = pair_pack15(pr, pg, pb, d16);
+    }
+    const uint32_t t15 = tex & 0x80008000u;
+    if (path & LP_TRANSP)
+    {
+      const uint32_t blended = pair_blend15((path >> LP_TMODE_SHIFT) & 3u, bg & 0x7FFF7FFFu, col15);
+      const uint32_t bm = (path & LP_TEXTURED) ? pk_expand15(t15) : 0xFFFFFFFFu;
+      col15 = (col15 & ~bm) | (blended & bm);
+    }
+    if (we15)
+    {
+      const uint32_t wm = pk_expand15(we15);
+      *wp = (bg & ~wm) | ((col15 | t15 | c_set15) & wm);
     }
   }
 }

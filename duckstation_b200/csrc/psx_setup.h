@@ -114,7 +114,7 @@ PSX_HD int32_t last_row_above_area(int32_t a, int32_t b, int32_t top)
 }
 
 // Everything the raster kernel's word loop reads per primitive, derived once here (psx_types.h:LoopDesc).
-PSX_HD void make_loop_desc(PrimSetup& s)
+PSX_HD void make_loop_desc(PrimSetup& s, bool complex_tri)
 {
   LoopDesc& D = s.desc;
   const bool tri = s.op == OP_TRIANGLE;
@@ -128,7 +128,9 @@ PSX_HD void make_loop_desc(PrimSetup& s)
   D.tex_bx2 = s.tex_bx * 0x00010001u;
   D.sub_mask2 = ((1u << tsh) - 1u) * 0x00010001u;
   D.tex_rows = static_cast<uint32_t>(s.tex_by) * VRAM_W;
-  D.tex_misc = tsh | ((2u + mode) << 8) | ((mode < 2u ? ((1u << (4u << mode)) - 1u) : 0u) << 16);
+  D.tex_shift = tsh;
+  D.sub_shift = 2u + mode;
+  D.idx_mask = mode < 2u ? ((1u << (4u << mode)) - 1u) : 0u;
   uint32_t r = tri ? s.tri.flat_r : s.rect.r, g = tri ? s.tri.flat_g : s.rect.g, b = tri ? s.tri.flat_b : s.rect.b;
   if (textured)
   {
@@ -162,9 +164,15 @@ PSX_HD void make_loop_desc(PrimSetup& s)
   path |= ((static_cast<uint32_t>(s.draw_mode) >> 5) & 3u) << LP_TMODE_SHIFT;
   if (s.win_and_x != 0xFF || s.win_and_y != 0xFF || s.win_or_x != 0 || s.win_or_y != 0)
     path |= LP_WINDOW;
+  if (s.flags0 & F_INTERLACED)
+    path |= LP_INTERLACED;
+  if (complex_tri)
+    path |= LP_COMPLEX;
   D.path = path;
   const uint32_t ubase = tri ? 0u : ((static_cast<uint32_t>(s.rect.u0) - static_cast<uint32_t>(static_cast<int32_t>(s.rect.x))) & 0xFFu);
-  D.misc2 = ((textured && mod5) ? 0xF8u : 0xFFu) | (ubase << 8);
+  D.cmask = (textured && mod5) ? 0xF8u : 0xFFu;
+  D.ubase = ubase;
+  D.pad = 0;
   const uint32_t is8 = mode & 1u;
   D.clut_key = (textured && mode < 2u) ? (s.clut_lo | (static_cast<uint32_t>(is8 ? s.clut_hi : s.clut_lo) << 8) | (is8 << 16) | 0x80000000u) : 0u;
 }
@@ -245,8 +253,17 @@ PSX_HD void setup_triangle(const PackedCmd& c, PrimSetup& s, BinInfo& bin)
   const uint64_t short_start[2] = {static_cast<uint64_t>(makefp_xy(upper_up ? v1.x : v0.x)), static_cast<uint64_t>(makefp_xy(lower_up ? v2.x : v1.x))};
   const int32_t short_anchor[2] = {upper_up ? v1.y : v0.y, lower_up ? v2.y : v1.y};
   const uint64_t short_step[2] = {static_cast<uint64_t>(bound_us), static_cast<uint64_t>(bound_ls)};
+  // All coordinates inside 11 bits (with a pixel to spare for the edges' rounding): sext11 is the identity on every
+  // row and column the walk can produce, so the drawing area's rows can be cut into the ranges here and the kernel
+  // needs neither the row clip nor the column wrap.  Otherwise the kernel takes the general tri_row.
+  const bool simple = v0.y >= -1024 && v2.y <= 1024 && imin(v0.x, imin(v1.x, v2.x)) >= -1023 && imax(v0.x, imax(v1.x, v2.x)) <= 1022;
   for (int p = 0; p < 2; p++)
   {
+    if (simple)
+    {
+      lo[p] = imax(lo[p], top);
+      hi[p] = imin(hi[p], bottom + 1);
+    }
     if (hi[p] < lo[p])
       hi[p] = lo[p];
     T.lo[p] = static_cast<int16_t>(lo[p]);
@@ -309,7 +326,7 @@ PSX_HD void setup_triangle(const PackedCmd& c, PrimSetup& s, BinInfo& bin)
   if (x1 < x0 || rc <= 0)
     return set_nop(s, bin);
   set_bins(s, bin, x0, x1, static_cast<uint32_t>(r0), static_cast<uint32_t>(rc), false, 0, 0);
-  make_loop_desc(s);
+  make_loop_desc(s, !simple);
 }
 
 PSX_HD void setup_rect(const PackedCmd& c, PrimSetup& s, BinInfo& bin)
@@ -345,7 +362,7 @@ PSX_HD void setup_rect(const PackedCmd& c, PrimSetup& s, BinInfo& bin)
   if (x1 < x0 || y1 < y0)
     return set_nop(s, bin);
   set_bins(s, bin, x0, x1, static_cast<uint32_t>(y0), static_cast<uint32_t>(y1 - y0 + 1), false, 0, 0);
-  make_loop_desc(s);
+  make_loop_desc(s, false);
 }
 
 PSX_HD int32_t iabs(int32_t v)

@@ -157,6 +157,8 @@ enum : uint32_t
   LP_TMODE_SHIFT = 6,   // bits 6-7: semi-transparency mode
   LP_TRI = 0x100,
   LP_WINDOW = 0x200,    // a texture window other than and = 0xFF, or = 0
+  LP_INTERLACED = 0x400, // interlaced rendering: rows of the displayed field are skipped
+  LP_COMPLEX = 0x800,   // triangle with a coordinate outside 11 bits: rows / columns wrap, the general tri_row decides
 };
 struct alignas(16) LoopDesc
 {
@@ -164,15 +166,19 @@ struct alignas(16) LoopDesc
   uint32_t tex_bx2;   // texture page base column in both halves
   uint32_t sub_mask2; // (texels per VRAM word - 1) in both halves
   uint32_t tex_rows;  // texture page base row * 1024
-  uint32_t tex_misc;  // log2(texels per word) | log2(bits per texel) << 8 | palette index mask << 16
-  uint32_t fr, fg, fb; // flat colour: textured = the 8-bit values (Modulate5Bit crop applied), untextured = 16 c in both halves
+  uint32_t tex_shift; // log2(texels per VRAM word)
+  uint32_t sub_shift; // log2(bits per texel)
+  uint32_t idx_mask;  // palette index mask (15 / 255)
   uint32_t chk15;     // 0x80008000 if the mask bit is tested
   uint32_t set15;     // 0x80008000 if the mask bit is set
+  uint32_t fr, fg, fb; // flat colour: textured = the 8-bit values (Modulate5Bit crop applied), untextured = 16 c in both halves
+  uint32_t cmask;     // 0xFF, or 0xF8 with Modulate5Bit: applied to interpolated colours
   uint32_t path;      // LP_*
-  uint32_t misc2;     // bits 0-7: 0xFF, or 0xF8 with Modulate5Bit (applied to interpolated colours); bits 8-15: rectangle (u0 - x) & 0xFF
+  uint32_t ubase;     // rectangle: (u0 - x) & 0xFF
   uint32_t clut_key;  // paletted: lo slot | hi slot << 8 | 8-bit << 16 | 1 << 31 (which palette the loop wants staged); else 0
+  uint32_t pad;
 };
-static_assert(sizeof(LoopDesc) == 64, "LoopDesc");
+static_assert(sizeof(LoopDesc) == 80, "LoopDesc");
 
 // One y-range of a triangle: both edges as x(cy) = start + (cy - lo) * step (mod 2^64, then >> 32), lo = first row.
 struct TriPart
@@ -180,7 +186,7 @@ struct TriPart
   uint64_t l_start, l_step, r_start, r_step;
 };
 
-// ---- device-side setup record: 240 bytes, read by the raster kernel ----
+// ---- device-side setup record: 256 bytes, read by the raster kernel ----
 struct alignas(16) PrimSetup
 {
   // 32-byte common header
@@ -199,7 +205,8 @@ struct alignas(16) PrimSetup
     {
       TriPart part[2];  // [0] rows cy < y1, [1] rows cy >= y1; left / right edge, anchored at the part's first row
       int16_t y0, y1;
-      int16_t lo[2], hi[2]; // effective row range [lo, hi) of each part after break emulation (hi >= lo)
+      int16_t lo[2], hi[2]; // effective row range [lo, hi) of each part after break emulation (hi >= lo); unless
+                            // LP_COMPLEX also cut to the drawing area's rows
       uint8_t tflags;       // TRI_SHORT_IS_RIGHT | TRI_UPPER_UP | TRI_LOWER_UP
       uint8_t flat_r, flat_g, flat_b;
       uint32_t base[5], ddx[5], ddy[5]; // r g b u v : value(x,cy) = base + ddx*x + ddy*cy, top byte
@@ -239,7 +246,7 @@ struct alignas(16) PrimSetup
   };
   LoopDesc desc; // triangles and rectangles
 };
-static_assert(sizeof(PrimSetup) == 240, "PrimSetup must be 240 bytes");
+static_assert(sizeof(PrimSetup) == 256, "PrimSetup must be 256 bytes");
 
 // Binning words produced by setup, read by every tile CTA of the epoch.
 struct BinInfo
