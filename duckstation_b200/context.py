@@ -20,8 +20,10 @@ class Context:
 
     def __init__(self, n_instances: int = 1, device: int = 0, *, modulation_crop: bool = False, show_vram: bool = False,
                  display_format: int = 0, clut_slots: int = 0, encode_threads: int = 0, profile: bool = False,
-                 no_persistent: bool = False, encode_mode: int = 0):
-        """encode_mode: where submit_batch encodes — 0 auto (device for >= 16 instances), 1 host, 2 device."""
+                 no_persistent: bool = False, encode_mode: int = 0, launch_per_epoch: bool = False):
+        """encode_mode: where submit_batch encodes — 0 auto (device for >= 16 instances), 1 host, 2 device.
+        no_persistent: never use the cooperative latency-mode kernel; launch_per_epoch: neither that nor the instance-mode
+        kernel (every epoch wave is its own launch)."""
         self._lib = _lib.load()
         self._ctx = C.c_void_p()
         opts = _lib.Opts()
@@ -32,7 +34,7 @@ class Context:
         opts.clut_slots = clut_slots
         opts.encode_threads = encode_threads
         opts.profile = int(profile)
-        opts.reserved[0] = int(no_persistent)
+        opts.reserved[0] = 3 if launch_per_epoch else int(no_persistent)
         opts.reserved[1] = encode_mode
         rc = self._lib.psxgpu_create(device, n_instances, C.byref(opts), C.byref(self._ctx))
         if rc != 0 or not self._ctx:

@@ -11,6 +11,7 @@
 #include "kernels.h"
 
 #include <algorithm>
+#include <new>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -177,6 +178,9 @@ struct psxgpu_ctx
     DevBuf d_cmds, d_setups, d_bins, d_tilecmds, d_payload, d_clutops, d_items, d_misc;
     // device-encoded chunks: d_payload holds the raw wire streams (upload pixels are read in place)
     DevBuf d_recoff, d_rec, d_inst, d_state, d_state_out, d_epochs, d_result, d_waves, d_cursor, d_summary, d_rects;
+    DevBuf d_instwork; // per instance: where its epochs / commands / CLUT ops start (instance mode; d_epochs holds the epochs)
+    bool instance_mode = false; // many short epochs per instance: one CTA per instance for the whole flush (raster_instance_kernel)
+    bool instance_wide = false; // ... with 32 warps per CTA (a handful of instances)
     EncodeArgs enc_args{};
     bool device_encoded = false; // psxgpu_run_staged replays the encode kernels too (from the resident wire streams)
     cudaEvent_t ev_copied = nullptr, ev_walked = nullptr, ev_encoded = nullptr;
@@ -291,6 +295,23 @@ int collect_timing(psxgpu_ctx* ctx)
   return PSXGPU_OK;
 }
 
+// Instance mode pays off when a chunk's instances are cut into many short epochs: per epoch the wave modes pay a
+// kernel launch (or a grid barrier) and one pass over every touched tile.  PSXGPU_INSTANCE_MODE = 0 / 1 forces it.
+bool instance_mode_wanted(psxgpu_ctx* ctx, uint64_t total_epochs, uint32_t n_instances, uint64_t n_cmds)
+{
+  static const int forced = []() {
+    const char* e = std::getenv("PSXGPU_INSTANCE_MODE");
+    return e ? std::atoi(e) : -1;
+  }();
+  if (ctx->opts.reserved[0] & 2u) // instance mode disabled (tests: one launch per epoch wanted)
+    return false;
+  if (forced >= 0)
+    return forced != 0 && total_epochs > 0;
+  if (n_instances == 0 || total_epochs < 8ull * n_instances)
+    return false;
+  return n_cmds < 64ull * total_epochs; // fewer than 64 commands per epoch on average
+}
+
 // setup + all waves of one chunk, on ctx->stream
 int run_chunk(psxgpu_ctx* ctx, psxgpu_ctx::Chunk& S)
 {
@@ -300,13 +321,42 @@ int run_chunk(psxgpu_ctx* ctx, psxgpu_ctx::Chunk& S)
   if (S.n_cmds)
     ctx->counters.kernel_launches++;
   const uint32_t waves = static_cast<uint32_t>(S.wave_off.size()) - 1;
-  if (!S.wave_off.empty() && S.wave_off.back() != 0)
+  if (!S.instance_mode && !S.wave_off.empty() && S.wave_off.back() != 0)
   {
     CK(launch_item_union(static_cast<WaveItem*>(S.d_items.p), S.wave_off.back(), static_cast<const BinInfo*>(S.d_bins.p), ctx->stream),
        "item_union_kernel");
     ctx->counters.kernel_launches++;
   }
   S.ev_raster_used = 0;
+  if (S.instance_mode)
+  {
+    const bool prof_i = ctx->opts.profile != 0;
+    while (prof_i && S.ev_raster.size() < 2)
+    {
+      cudaEvent_t e;
+      CK(cudaEventCreate(&e), "event create");
+      S.ev_raster.push_back(e);
+    }
+    if (prof_i)
+      CK(cudaEventRecord(S.ev_raster[S.ev_raster_used++], ctx->stream), "event record");
+    CK(launch_instances(static_cast<const InstWork*>(S.d_instwork.p), S.n_instances, static_cast<const Epoch*>(S.d_epochs.p),
+                        static_cast<uint32_t*>(S.d_items.p), // (the wave items are not used in this mode: their buffer, 32 bytes per
+                                                             // epoch, holds the epochs' tile sets)
+                        static_cast<const PrimSetup*>(S.d_setups.p),
+                        static_cast<const uint32_t*>(S.d_tilecmds.p), static_cast<const ClutOp*>(S.d_clutops.p), ctx->d_vram, ctx->d_clut,
+                        static_cast<const uint16_t*>(S.d_payload.p), ctx->clut_slots, S.instance_wide, ctx->stream),
+       "raster_instance_kernel");
+    if (prof_i)
+      CK(cudaEventRecord(S.ev_raster[S.ev_raster_used++], ctx->stream), "event record");
+    ctx->counters.kernel_launches += 2;
+    ctx->counters.waves += waves;
+    if (S.ev_done)
+    {
+      CK(cudaEventRecord(S.ev_done, ctx->stream), "event record");
+      S.done_valid = true;
+    }
+    return PSXGPU_OK;
+  }
   if (S.persistent)
   {
     const uint8_t* misc = static_cast<const uint8_t*>(S.d_misc.p);
@@ -349,7 +399,7 @@ int run_chunk(psxgpu_ctx* ctx, psxgpu_ctx::Chunk& S)
     {
       CK(launch_raster(items + off, cnt, static_cast<const PrimSetup*>(S.d_setups.p), static_cast<const uint32_t*>(S.d_tilecmds.p),
                        ctx->d_vram, ctx->d_clut, static_cast<const uint16_t*>(S.d_payload.p), ctx->clut_slots, ctx->stream,
-                       S.wave_tiled_cmds[k]),
+                       S.wave_tiled_cmds[k], ctx->d_barrier + 4),
          "raster_kernel");
       ctx->counters.kernel_launches += (cnt + 32767) / 32768;
     }
@@ -543,7 +593,30 @@ int launch_chunk_impl(psxgpu_ctx* ctx, const std::vector<uint32_t>& work, const 
   S.device_encoded = false;
   S.n_instances = nw;
   const uint32_t n_waves = static_cast<uint32_t>(S.wave_off.size()) - 1;
-  S.persistent = ctx->persist_max != 0 && nw <= ctx->persist_max && n_waves > 0 && !ctx->opts.profile;
+  S.instance_mode = instance_mode_wanted(ctx, total_epochs, nw, n_cmds);
+  S.instance_wide = nw <= 64;
+  size_t inst_bytes = 0;
+  if (S.instance_mode)
+  {
+    // the same epochs, instance by instance
+    inst_bytes = static_cast<size_t>(nw) * sizeof(InstWork) + total_epochs * sizeof(Epoch);
+    CK(P.inst.ensure(inst_bytes), "pinned alloc (instance table)");
+    CK(S.d_instwork.ensure(static_cast<size_t>(nw) * sizeof(InstWork)), "device alloc (instance table)");
+    CK(S.d_epochs.ensure(total_epochs * sizeof(Epoch) + 16), "device alloc (epochs)");
+    InstWork* hw = static_cast<InstWork*>(P.inst.p);
+    Epoch* he = reinterpret_cast<Epoch*>(hw + nw);
+    uint32_t first = 0;
+    for (uint32_t w = 0; w < nw; w++)
+    {
+      const Encoder& e = ctx->enc[work[w]];
+      hw[w] = InstWork{work[w], static_cast<uint32_t>(cmd_base[w]), static_cast<uint32_t>(clut_base[w]), first,
+                       static_cast<uint32_t>(e.epochs.size()), {0, 0, 0}};
+      if (!e.epochs.empty())
+        std::memcpy(he + first, e.epochs.data(), e.epochs.size() * sizeof(Epoch));
+      first += static_cast<uint32_t>(e.epochs.size());
+    }
+  }
+  S.persistent = !S.instance_mode && ctx->persist_max != 0 && nw <= ctx->persist_max && n_waves > 0 && !ctx->opts.profile;
   size_t misc_bytes = 0;
   if (S.persistent)
   {
@@ -594,6 +667,15 @@ int launch_chunk_impl(psxgpu_ctx* ctx, const std::vector<uint32_t>& work, const 
     CK(cudaMemcpyAsync(S.d_items.p, hi, n_items * sizeof(WaveItem), cudaMemcpyHostToDevice, ctx->stream), "H2D wave items");
   if (misc_bytes)
     CK(cudaMemcpyAsync(S.d_misc.p, P.misc.p, misc_bytes, cudaMemcpyHostToDevice, ctx->stream), "H2D wave table");
+  if (inst_bytes)
+  {
+    CK(cudaMemcpyAsync(S.d_instwork.p, P.inst.p, static_cast<size_t>(nw) * sizeof(InstWork), cudaMemcpyHostToDevice, ctx->stream),
+       "H2D instance table");
+    if (total_epochs)
+      CK(cudaMemcpyAsync(S.d_epochs.p, static_cast<const uint8_t*>(P.inst.p) + static_cast<size_t>(nw) * sizeof(InstWork),
+                         total_epochs * sizeof(Epoch), cudaMemcpyHostToDevice, ctx->stream),
+         "H2D epochs");
+  }
   CK(cudaEventRecord(P.free_ev, ctx->stream), "event record");
   P.in_flight = true;
   ctx->counters.h2d_bytes += n_cmds * sizeof(PackedCmd) + n_pay * 2 + n_clut * sizeof(ClutOp) + n_items * sizeof(WaveItem);
@@ -885,6 +967,7 @@ int stage_encode(psxgpu_ctx* ctx, PendingChunk& pc)
   CK(S.d_waves.ensure(static_cast<size_t>(wave_cap) * sizeof(EncWave)), "device alloc (wave table)");
   CK(S.d_cursor.ensure(static_cast<size_t>(wave_cap) * 4), "device alloc (wave cursors)");
   CK(S.d_summary.ensure(sizeof(EncSummary)), "device alloc (summary)");
+  CK(S.d_instwork.ensure(static_cast<size_t>(cn) * sizeof(InstWork)), "device alloc (instance table)");
   // no host-to-device copy here: it would queue behind the next chunk's wire upload
   CK(cudaStreamWaitEvent(pc.es, S.ev_walked, 0), "stream wait");
   CK(launch_layout(static_cast<const WalkOut*>(S.d_recoff.p), static_cast<EncInst*>(S.d_inst.p), cn, pc.es), "layout_kernel");
@@ -909,6 +992,7 @@ int stage_encode(psxgpu_ctx* ctx, PendingChunk& pc)
   a.wave_cursor = static_cast<uint32_t*>(S.d_cursor.p);
   a.wave_cap = wave_cap;
   a.items = static_cast<WaveItem*>(S.d_items.p);
+  a.inst_work = static_cast<InstWork*>(S.d_instwork.p);
   CK(launch_encode(a, pc.es), "encode_kernel");
   ctx->counters.kernel_launches += 3;
   S.enc_args = a;
@@ -970,6 +1054,9 @@ int finalize_device_chunk(psxgpu_ctx* ctx, PendingChunk& pc)
   S.n_cmds = static_cast<uint32_t>(pc.cmd_total);
   S.n_instances = pc.cn;
   S.persistent = false;
+  // many short epochs per instance (render-to-texture feedback): a launch per epoch costs more than the epochs' work
+  S.instance_mode = instance_mode_wanted(ctx, sm->total_items, pc.cn, pc.cmd_total) && M <= pc.wave_cap;
+  S.instance_wide = pc.cn <= 64;
   const EncState* states = reinterpret_cast<const EncState*>(res + pc.state_off);
   for (uint32_t k = 0; k < pc.cn; k++)
   {
@@ -1295,7 +1382,7 @@ int psxgpu_create(int device, uint32_t n_instances, const psxgpu_opts* opts, psx
     return bail(e, "sync");
 
   ctx->persist_max = static_cast<uint32_t>(std::max(0, persistent_max_instances(device)));
-  if (ctx->opts.reserved[0] == 1) // latency mode disabled (opts.reserved[0] = no_persistent)
+  if (ctx->opts.reserved[0] & 1u) // latency mode disabled (opts.reserved[0] bit 0 = no_persistent)
     ctx->persist_max = 0;
   ctx->enc.reserve(n_instances);
   for (uint32_t i = 0; i < n_instances; i++)
@@ -1330,7 +1417,8 @@ void psxgpu_destroy(psxgpu_ctx* ctx)
   for (psxgpu_ctx::Chunk* ch : ctx->chunks)
   {
     for (DevBuf* b : {&ch->d_cmds, &ch->d_setups, &ch->d_bins, &ch->d_tilecmds, &ch->d_payload, &ch->d_clutops, &ch->d_items, &ch->d_misc, &ch->d_recoff, &ch->d_rec,
-                      &ch->d_inst, &ch->d_state, &ch->d_state_out, &ch->d_epochs, &ch->d_result, &ch->d_waves, &ch->d_cursor, &ch->d_summary, &ch->d_rects})
+                      &ch->d_inst, &ch->d_state, &ch->d_state_out, &ch->d_epochs, &ch->d_result, &ch->d_waves, &ch->d_cursor, &ch->d_summary, &ch->d_rects,
+                      &ch->d_instwork})
       b->release();
     for (cudaEvent_t ev : {ch->ev_copied, ch->ev_walked, ch->ev_encoded, ch->ev_done})
       if (ev)
@@ -1361,12 +1449,33 @@ const char* psxgpu_last_error(const psxgpu_ctx* ctx)
   return ctx ? ctx->error.c_str() : "null context";
 }
 
-int psxgpu_flush(psxgpu_ctx* ctx)
+static int psxgpu_flush_impl(psxgpu_ctx* ctx)
 {
   if (!ctx)
     return PSXGPU_E_INVALID;
   cudaSetDevice(ctx->device);
   return do_flush(ctx);
+}
+
+// The C ABI never throws: an allocation failure inside becomes PSXGPU_E_NOMEM.
+int psxgpu_flush(psxgpu_ctx* ctx)
+{
+  try
+  {
+    return psxgpu_flush_impl(ctx);
+  }
+  catch (const std::bad_alloc&)
+  {
+    if (ctx)
+      ctx->error = "psxgpu_flush: out of host memory";
+    return PSXGPU_E_NOMEM;
+  }
+  catch (...)
+  {
+    if (ctx)
+      ctx->error = "psxgpu_flush: unexpected exception";
+    return PSXGPU_E_INVALID;
+  }
 }
 
 int psxgpu_sync(psxgpu_ctx* ctx)
@@ -1435,7 +1544,7 @@ int psxgpu_set_batch_chunk(psxgpu_ctx* ctx, uint32_t instances_per_chunk)
   return PSXGPU_OK;
 }
 
-int psxgpu_submit_wire(psxgpu_ctx* ctx, uint32_t instance, const void* wire, size_t bytes)
+static int psxgpu_submit_wire_impl(psxgpu_ctx* ctx, uint32_t instance, const void* wire, size_t bytes)
 {
   if (!ctx || instance >= ctx->n || (!wire && bytes))
     return ctx ? ctx->invalid("submit_wire: bad instance or buffer") : PSXGPU_E_INVALID;
@@ -1474,7 +1583,11 @@ int psxgpu_submit_wire(psxgpu_ctx* ctx, uint32_t instance, const void* wire, siz
       break;
       case PSX_CMD_READ_VRAM:
       {
+        if (h->size < sizeof(psx_read_vram))
+          return ctx->invalid("ReadVRAM record too small");
         const psx_read_vram* rv = reinterpret_cast<const psx_read_vram*>(h);
+        if (rv->width > VRAM_W || rv->height > VRAM_H)
+          return ctx->invalid("ReadVRAM rectangle larger than VRAM");
         uint16_t* sh = psxgpu_shadow_vram(ctx, instance);
         // refresh the shadow rectangle in place (wrapping): row by row pieces handled by do_read_vram into a temp
         std::vector<uint16_t> tmp(static_cast<size_t>(rv->width) * rv->height);
@@ -1487,10 +1600,14 @@ int psxgpu_submit_wire(psxgpu_ctx* ctx, uint32_t instance, const void* wire, siz
       break;
       case PSX_CMD_UPDATE_DISPLAY:
       {
+        if (h->size < sizeof(psx_update_display))
+          return ctx->invalid("UpdateDisplay record too small");
         const psx_update_display* ud = reinterpret_cast<const psx_update_display*>(h);
         ScanoutParams sp;
         bool disabled;
         scanout_params(ctx, ud, sp, disabled);
+        if (!disabled && (sp.width > 4096 || sp.height > 4096))
+          return ctx->invalid("UpdateDisplay larger than 4096 x 4096");
         if (disabled)
         {
           ctx->disp_w = ctx->disp_h = 0;
@@ -1516,7 +1633,28 @@ int psxgpu_submit_wire(psxgpu_ctx* ctx, uint32_t instance, const void* wire, siz
   return PSXGPU_OK;
 }
 
-int psxgpu_submit_batch(psxgpu_ctx* ctx, uint32_t first, uint32_t count, const void* const* streams, const size_t* bytes)
+// The C ABI never throws: an allocation failure inside becomes PSXGPU_E_NOMEM.
+int psxgpu_submit_wire(psxgpu_ctx* ctx, uint32_t instance, const void* wire, size_t bytes)
+{
+  try
+  {
+    return psxgpu_submit_wire_impl(ctx, instance, wire, bytes);
+  }
+  catch (const std::bad_alloc&)
+  {
+    if (ctx)
+      ctx->error = "psxgpu_submit_wire: out of host memory";
+    return PSXGPU_E_NOMEM;
+  }
+  catch (...)
+  {
+    if (ctx)
+      ctx->error = "psxgpu_submit_wire: unexpected exception";
+    return PSXGPU_E_INVALID;
+  }
+}
+
+static int psxgpu_submit_batch_impl(psxgpu_ctx* ctx, uint32_t first, uint32_t count, const void* const* streams, const size_t* bytes)
 {
   if (!ctx || !streams || !bytes || first + count > ctx->n || first + count < first)
     return ctx ? ctx->invalid("submit_batch: bad arguments") : PSXGPU_E_INVALID;
@@ -1643,6 +1781,27 @@ int psxgpu_submit_batch(psxgpu_ctx* ctx, uint32_t first, uint32_t count, const v
       return rc;
   }
   return PSXGPU_OK;
+}
+
+// The C ABI never throws: an allocation failure inside becomes PSXGPU_E_NOMEM.
+int psxgpu_submit_batch(psxgpu_ctx* ctx, uint32_t first, uint32_t count, const void* const* streams, const size_t* bytes)
+{
+  try
+  {
+    return psxgpu_submit_batch_impl(ctx, first, count, streams, bytes);
+  }
+  catch (const std::bad_alloc&)
+  {
+    if (ctx)
+      ctx->error = "psxgpu_submit_batch: out of host memory";
+    return PSXGPU_E_NOMEM;
+  }
+  catch (...)
+  {
+    if (ctx)
+      ctx->error = "psxgpu_submit_batch: unexpected exception";
+    return PSXGPU_E_INVALID;
+  }
 }
 
 int psxgpu_read_vram(psxgpu_ctx* ctx, uint32_t instance, uint32_t x, uint32_t y, uint32_t w, uint32_t h, uint16_t* dst,

@@ -108,6 +108,7 @@ struct EncodeArgs
   uint32_t* wave_cursor; // [wave_cap]
   uint32_t wave_cap;
   WaveItem* items;
+  InstWork* inst_work; // [n_inst]: the same epochs, instance by instance (raster_instance_kernel)
 };
 
 // walk: reads inst[].wire_off / wire_bytes.  layout: exclusive prefix sums of the capacities into inst[].*_base / *_cap

@@ -2009,6 +2009,17 @@ __global__ void __launch_bounds__(128) wave_fill_kernel(EncodeArgs A)
     return;
   const EncInst ii = A.inst[idx];
   const uint32_t ne = A.result[idx].n_epochs;
+  if (lane == 0)
+  {
+    InstWork w;
+    w.instance = ii.instance;
+    w.cmd_base = ii.cmd_base;
+    w.clut_base = ii.clut_base;
+    w.epoch_first = ii.epoch_base;
+    w.n_epochs = min(ne, A.wave_cap);
+    w.pad[0] = w.pad[1] = w.pad[2] = 0;
+    A.inst_work[idx] = w;
+  }
   for (uint32_t k = lane; k < ne && k < A.wave_cap; k += 32)
   {
     const Epoch e = A.epochs[ii.epoch_base + k];

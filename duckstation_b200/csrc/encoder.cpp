@@ -385,6 +385,8 @@ void Encoder::push_cmd(const PackedCmd& c)
   m_n_cmds++;
 }
 
+static uint64_t record_bytes_needed(const uint8_t* rec, uint32_t size);
+
 bool Encoder::scan_wire(const void* wire, size_t bytes, uint32_t* max_cmds, uint64_t* max_payload)
 {
   const uint8_t* p = static_cast<const uint8_t*>(wire);
@@ -398,6 +400,11 @@ bool Encoder::scan_wire(const void* wire, size_t bytes, uint32_t* max_cmds, uint
     const psx_cmd_header* h = reinterpret_cast<const psx_cmd_header*>(p);
     if (h->size < sizeof(psx_cmd_header) || (h->size & 3u) != 0 || h->size > static_cast<size_t>(end - p))
       return false;
+    if (record_bytes_needed(p, h->size) > h->size)
+    {
+      p += h->size; // handle_record drops it
+      continue;
+    }
     switch (h->type)
     {
       case PSX_CMD_DRAW_POLYGON:
@@ -583,10 +590,55 @@ static inline bool vertex_ok(int32_t x, int32_t y)
   return x >= -32768 && x <= 32767 && y >= -32768 && y <= 32767;
 }
 
+// Bytes a record of this type must hold before any of its fields is read (its fixed part plus, for polygons, lines
+// and uploads, what its own counts ask for).  `size` = the record's framed size.  0 = nothing to check.
+// The same rules as the device encoder (encode_kernel.cu: every `size <` test): a record that is too short is dropped
+// — counted as rejected if it is a primitive or a transfer, ignored if it is a state record — never read past.
+static uint64_t record_bytes_needed(const uint8_t* rec, uint32_t size)
+{
+  const psx_cmd_header* h = reinterpret_cast<const psx_cmd_header*>(rec);
+  switch (h->type)
+  {
+    case PSX_CMD_SET_DRAWING_AREA: return sizeof(psx_set_drawing_area);
+    case PSX_CMD_UPDATE_CLUT: return sizeof(psx_update_clut);
+    case PSX_CMD_DRAW_RECTANGLE: return sizeof(psx_draw_rectangle);
+    case PSX_CMD_FILL_VRAM: return sizeof(psx_fill_vram);
+    case PSX_CMD_COPY_VRAM: return sizeof(psx_copy_vram);
+    case PSX_CMD_DRAW_POLYGON:
+    case PSX_CMD_DRAW_PRECISE_POLYGON:
+    case PSX_CMD_DRAW_LINE:
+    case PSX_CMD_DRAW_PRECISE_LINE:
+    {
+      if (size < sizeof(psx_draw_header))
+        return sizeof(psx_draw_header);
+      const uint64_t nv = reinterpret_cast<const psx_draw_header*>(rec)->num_vertices;
+      if (h->type == PSX_CMD_DRAW_POLYGON)
+        return sizeof(psx_draw_header) + sizeof(psx_poly_vertex) * (nv < 4 ? nv : 4);
+      if (h->type == PSX_CMD_DRAW_PRECISE_POLYGON)
+        return offsetof(psx_draw_precise_polygon, vertices) + sizeof(psx_precise_poly_vertex) * (nv < 4 ? nv : 4);
+      return sizeof(psx_draw_header) + (h->type == PSX_CMD_DRAW_LINE ? sizeof(psx_line_vertex) : sizeof(psx_precise_line_vertex)) * nv;
+    }
+    case PSX_CMD_UPDATE_VRAM:
+    {
+      if (size < 20)
+        return 20;
+      const psx_update_vram* u = reinterpret_cast<const psx_update_vram*>(rec);
+      return PSX_UPDATE_VRAM_DATA_OFFSET + static_cast<uint64_t>(u->width) * u->height * 2u;
+    }
+    default: return 0;
+  }
+}
+
 void Encoder::handle_record(const uint8_t* rec)
 {
   const psx_cmd_header* h = reinterpret_cast<const psx_cmd_header*>(rec);
   stats.wire_commands++;
+  if (record_bytes_needed(rec, h->size) > h->size)
+  {
+    if (h->type != PSX_CMD_SET_DRAWING_AREA && h->type != PSX_CMD_UPDATE_CLUT)
+      stats.rejected++;
+    return;
+  }
   switch (h->type)
   {
     case PSX_CMD_SET_DRAWING_AREA:

@@ -20,12 +20,7 @@
 
 namespace psx {
 
-struct Epoch
-{
-  uint32_t cmd_begin, cmd_end; // indices into cmds
-  uint32_t kind;               // EpochKind
-  uint32_t clut_begin, clut_end;
-};
+// (struct Epoch: psx_types.h)
 
 struct EncoderStats
 {

@@ -135,6 +135,10 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem)
 {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(smem))), "l"(gmem) : "memory");
 }
+__device__ __forceinline__ void cp_async16_l2(void* smem, const void* gmem) // .cg: from L2, never a stale L1 line
+{
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(smem))), "l"(gmem) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit()
 {
   asm volatile("cp.async.commit_group;" ::: "memory");
@@ -704,7 +708,7 @@ __device__ void serial_self_sampling(const PrimSetup& s, uint16_t* vram, const u
         if (idxmask != 0)
         {
           const uint32_t idx = (w >> shift) & idxmask;
-          texel = __ldg((idx < 16u ? clut_lo : clut_hi) + idx);
+          texel = __ldcg((idx < 16u ? clut_lo : clut_hi) + idx); // (coherent: the kernels that stay resident rewrite CLUT slots between epochs)
         }
       }
       __syncwarp();
@@ -997,6 +1001,17 @@ __device__ __forceinline__ void process_epoch_region(const WaveItem& it, RasterS
   uint32_t clut_key = 0;
   uint32_t list_n = 0;
   uint32_t next_cmd = it.cmd_begin; // first command of the epoch that is not in a list yet
+  if (kCoh)
+  {
+    // The kernels that stay resident over many short epochs are bound by the chain of dependent round trips per tile
+    // (bins -> setup record -> tile -> texel): the tile's rows are requested first, asynchronously, and arrive while the
+    // bins and the first setup record are fetched.
+    const uint16_t* gtile = vram + ry0 * VRAM_W + rx0;
+#pragma unroll
+    for (uint32_t c = lane; c < RH * (TILE_W / 8); c += 32)
+      cp_async16_l2(sh.region + (c / (TILE_W / 8)) * REGION_PITCH + (c % (TILE_W / 8)) * 4, gtile + (c / (TILE_W / 8)) * VRAM_W + (c % (TILE_W / 8)) * 8);
+    cp_async_commit();
+  }
 #pragma unroll 1
   for (;;)
   {
@@ -1070,11 +1085,11 @@ __device__ __forceinline__ void process_epoch_region(const WaveItem& it, RasterS
         overwritten = !interlaced && (((rx0 - first.fill.x) & (VRAM_W - 1)) + TILE_W <= first.fill.w) &&
                       (((ry0 - first.fill.y) & (VRAM_H - 1)) + RH <= first.fill.h);
       }
-      if (!overwritten)
+      if (!kCoh && !overwritten) // (kCoh: the rows were requested on entry and the wait above covers them)
       {
 #pragma unroll 8
         for (uint32_t r = 0; r < RH; r++)
-          sh.region[r * REGION_PITCH + lane] = kCoh ? __ldcg(gword + r * (VRAM_W / 2)) : __ldcs(gword + r * (VRAM_W / 2)); // read once: keep it out of L1
+          sh.region[r * REGION_PITCH + lane] = __ldcs(gword + r * (VRAM_W / 2)); // read once: keep it out of L1
       }
       loaded = true;
     }
@@ -1096,6 +1111,11 @@ __device__ __forceinline__ void process_epoch_region(const WaveItem& it, RasterS
       __syncwarp();
     }
     list_n = 0;
+  }
+  if (kCoh && !loaded)
+  {
+    cp_async_wait<0>(); // nothing to do here after all: let the requested rows land before the next tile reuses the buffer
+    __syncwarp();
   }
   if (loaded)
   {
@@ -1142,12 +1162,11 @@ __global__ void __launch_bounds__(32 * PSX_RASTER_WARPS, PSX_RASTER_MIN_CTAS) ra
 // upload: a primitive or two per epoch) is then bound by the counter itself (1.2 -> 1.4 ms at 2, 2.6 ms at 1).  The
 // launcher picks by the wave's commands per epoch.
 constexpr uint32_t LOOP_GRAB_LIGHT = 8, LOOP_GRAB_HEAVY = 2, LOOP_LIGHT_CMDS_PER_ITEM = 8;
-__device__ unsigned int g_raster_loop_counter[64];
 
 __global__ void __launch_bounds__(32, PSX_RASTER_MIN_CTAS) raster_loop_kernel(
   const WaveItem* __restrict__ items, uint32_t n_items, const PrimSetup* __restrict__ setups, const uint32_t* __restrict__ tile_cmds,
   uint16_t* __restrict__ vram_pool, const uint16_t* __restrict__ clut_pool, const uint16_t* __restrict__ payload, uint32_t clut_slots,
-  uint32_t counter_slot, uint32_t want)
+  unsigned int* __restrict__ work_counter, uint32_t want)
 {
   __shared__ RasterShared<TILE_H> sh;
   const uint32_t lane = threadIdx.x;
@@ -1158,10 +1177,10 @@ __global__ void __launch_bounds__(32, PSX_RASTER_MIN_CTAS) raster_loop_kernel(
     if (lane == 0)
     {
       // guided self-scheduling: large grabs while there is plenty left, single tiles towards the end of the wave
-      const uint32_t seen = *reinterpret_cast<volatile unsigned int*>(&g_raster_loop_counter[counter_slot]);
+      const uint32_t seen = *reinterpret_cast<volatile unsigned int*>(work_counter);
       const uint32_t left = (total > seen) ? (total - seen) : 0u;
       grab = min(want, max(1u, left / (gridDim.x * 4u)));
-      first = atomicAdd(&g_raster_loop_counter[counter_slot], grab);
+      first = atomicAdd(work_counter, grab);
     }
     first = __shfl_sync(0xFFFFFFFFu, first, 0);
     grab = __shfl_sync(0xFFFFFFFFu, grab, 0);
@@ -1307,6 +1326,174 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 7) raster_persistent_kernel(
   }
 }
 
+// ------------------------------------------------------------------------------------------------ instance mode
+// Streams that the hazard splitter cuts into many short epochs (render-to-texture feedback, transfers between draws)
+// pay one kernel launch — or one grid-wide barrier — per epoch in the modes above, and the work between two cuts is a
+// handful of primitives.  Here ONE CTA owns one instance for a whole flush: it walks the instance's epochs in order,
+// its warps pull the epoch's tiles from a shared-memory counter, and what separates two epochs is a __syncthreads()
+// (which also orders the CTA's global stores of epoch k before its loads of epoch k + 1: VRAM and CLUT-slot reads go
+// to L2, kCoh).  No cross-CTA synchronisation exists: instances are independent.  WARPS = 8 for batches (four CTAs
+// per SM), 32 for a handful of instances (one CTA per SM, 1024 threads on the serial epochs).
+constexpr uint32_t INST_EPOCH_WINDOW = 64; // epochs whose descriptors are staged in shared memory at a time
+
+struct InstanceShared
+{
+  uint32_t row_count[VRAM_H + 1];
+  alignas(16) uint32_t stage[SETUP_WORDS];
+  Epoch epochs[INST_EPOCH_WINDOW];
+  uint32_t tile_sets[INST_EPOCH_WINDOW][8];
+  uint32_t next_tile[2];
+};
+
+// Which tiles does each epoch of each instance touch?  One warp per epoch, lane L looks after tiles 8 L .. 8 L + 7: the
+// OR of their tile_cmds words over the epoch's command groups (first and last group trimmed to the epoch) — exact at the
+// binning's own granularity, where the union of the commands' column and row masks would name every tile of the
+// drawing area.  Eight words (256 bits) per epoch, for raster_instance_kernel.
+__global__ void __launch_bounds__(128) epoch_tiles_kernel(const InstWork* __restrict__ work, const Epoch* __restrict__ epochs,
+                                                          const uint32_t* __restrict__ tile_cmds, uint32_t* __restrict__ tile_sets)
+{
+  const InstWork w = work[blockIdx.x];
+  const uint32_t lane = threadIdx.x & 31u;
+  for (uint32_t k = threadIdx.x >> 5; k < w.n_epochs; k += 4)
+  {
+    const Epoch ep = epochs[w.epoch_first + k];
+    uint32_t byte = 0; // bit j: tile 8 * lane + j is touched
+    if (ep.kind == EPOCH_TILED && ep.cmd_end > ep.cmd_begin)
+    {
+      const uint32_t b = w.cmd_base + ep.cmd_begin, e = w.cmd_base + ep.cmd_end;
+      for (uint32_t g = b >> 5; g <= (e - 1) >> 5; g++)
+      {
+        uint32_t keep = 0xFFFFFFFFu;
+        if ((g << 5) < b)
+          keep &= 0xFFFFFFFFu << (b - (g << 5));
+        if ((g << 5) + 32u > e)
+          keep &= (1u << (e - (g << 5))) - 1u;
+        const uint4* p = reinterpret_cast<const uint4*>(tile_cmds + static_cast<size_t>(g) * NUM_TILES + lane * 8);
+        const uint4 a = __ldg(p), c = __ldg(p + 1);
+        byte |= ((a.x & keep) ? 1u : 0u) | ((a.y & keep) ? 2u : 0u) | ((a.z & keep) ? 4u : 0u) | ((a.w & keep) ? 8u : 0u) |
+                ((c.x & keep) ? 16u : 0u) | ((c.y & keep) ? 32u : 0u) | ((c.z & keep) ? 64u : 0u) | ((c.w & keep) ? 128u : 0u);
+      }
+    }
+    // four lanes make one word
+    uint32_t word = byte << (8u * (lane & 3u));
+    word |= __shfl_xor_sync(0xFFFFFFFFu, word, 1);
+    word |= __shfl_xor_sync(0xFFFFFFFFu, word, 2);
+    if ((lane & 3u) == 0)
+      tile_sets[static_cast<size_t>(w.epoch_first + k) * 8 + (lane >> 2)] = word;
+  }
+}
+
+template<uint32_t WARPS>
+__global__ void __launch_bounds__(32 * WARPS, WARPS == 32 ? 1 : (32 / WARPS)) raster_instance_kernel(
+  const InstWork* __restrict__ work, const Epoch* __restrict__ epochs, const uint32_t* __restrict__ tile_sets,
+  const PrimSetup* __restrict__ setups, const uint32_t* __restrict__ tile_cmds, const ClutOp* __restrict__ clut_ops, uint16_t* vram_pool,
+  uint16_t* clut_pool, const uint16_t* __restrict__ payload, uint32_t clut_slots)
+{
+  extern __shared__ __align__(16) unsigned char dyn_smem[];
+  RasterShared<TILE_H>* sh_all = reinterpret_cast<RasterShared<TILE_H>*>(dyn_smem);
+  InstanceShared& cs = *reinterpret_cast<InstanceShared*>(dyn_smem + sizeof(RasterShared<TILE_H>) * WARPS);
+  constexpr uint32_t NT = 32 * WARPS;
+  const InstWork w = work[blockIdx.x];
+  uint16_t* vram = vram_pool + static_cast<size_t>(w.instance) * VRAM_PIXELS;
+  uint16_t* cluts = clut_pool + static_cast<size_t>(w.instance) * clut_slots * CLUT_ENTRIES;
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+  if (threadIdx.x < 2)
+    cs.next_tile[threadIdx.x] = 0;
+
+  for (uint32_t k = 0; k < w.n_epochs; k++)
+  {
+    const uint32_t slot = k % INST_EPOCH_WINDOW;
+    if (slot == 0)
+    {
+      // the next window of epoch descriptors and tile-mask unions: they do not depend on anything this kernel writes
+      const uint32_t n = min(INST_EPOCH_WINDOW, w.n_epochs - k);
+      const uint32_t* src = reinterpret_cast<const uint32_t*>(epochs + w.epoch_first + k);
+      for (uint32_t i = threadIdx.x; i < n * (sizeof(Epoch) / 4); i += NT)
+        reinterpret_cast<uint32_t*>(cs.epochs)[i] = __ldg(src + i);
+      for (uint32_t i = threadIdx.x; i < n * 8; i += NT)
+        (&cs.tile_sets[0][0])[i] = __ldg(tile_sets + static_cast<size_t>(w.epoch_first + k) * 8 + i);
+      __syncthreads();
+    }
+    const Epoch ep = cs.epochs[slot];
+    WaveItem it;
+    it.instance = w.instance;
+    it.cmd_begin = w.cmd_base + ep.cmd_begin;
+    it.cmd_end = w.cmd_base + ep.cmd_end;
+    it.kind = ep.kind;
+    it.clut_begin = w.clut_base + ep.clut_begin;
+    it.clut_end = w.clut_base + ep.clut_end;
+    if (it.clut_end > it.clut_begin) // uniform over the CTA
+    {
+      for (uint32_t o = it.clut_begin; o < it.clut_end; o++)
+      {
+        const ClutOp op = clut_ops[o];
+        for (uint32_t t = threadIdx.x; t < (op.is8bit ? 256u : 16u); t += NT)
+          cluts[op.dst_slot * CLUT_ENTRIES + t] = __ldcg(vram + op.y * VRAM_W + ((op.x + t) & (VRAM_W - 1)));
+      }
+      __syncthreads();
+    }
+    if (it.cmd_end > it.cmd_begin)
+    {
+      if (it.kind == EPOCH_TILED)
+      {
+        // the tiles the epoch touches (epoch_tiles_kernel), pulled from a counter; the counters of even and odd epochs
+        // alternate, so that resetting one needs no barrier of its own
+        if (threadIdx.x == 0)
+          cs.next_tile[(k + 1) & 1u] = 0;
+        const uint32_t mine = (lane < 8) ? cs.tile_sets[slot][lane] : 0u; // lane L: tiles 32 L .. 32 L + 31
+        const uint32_t cnt = __popc(mine);
+        uint32_t before = cnt; // exclusive prefix over lanes 0..7
+#pragma unroll
+        for (uint32_t o = 1; o < 8; o <<= 1)
+        {
+          const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, before, o);
+          if (lane >= o)
+            before += t;
+        }
+        const uint32_t total = __shfl_sync(0xFFFFFFFFu, before, 7);
+        before -= cnt;
+        for (;;)
+        {
+          uint32_t j = 0;
+          if (lane == 0)
+            j = atomicAdd(&cs.next_tile[k & 1u], 1u);
+          j = __shfl_sync(0xFFFFFFFFu, j, 0);
+          if (j >= total)
+            break;
+          // the j-th set bit of the 256: the lane whose range holds it answers
+          const bool here = lane < 8 && j >= before && j < before + cnt;
+          const uint32_t src = static_cast<uint32_t>(__ffs(static_cast<int>(__ballot_sync(0xFFFFFFFFu, here)))) - 1u;
+          const uint32_t tile = __shfl_sync(0xFFFFFFFFu, lane * 32u + __fns(mine, 0, static_cast<int>(j - before) + 1), src);
+          const uint32_t tx = tile % TILES_X, ty = tile / TILES_X;
+          process_epoch_region<TILE_H, true>(it, sh_all[warp], tx, ty, ty * TILE_H, setups, tile_cmds, vram, cluts, payload, lane);
+          __syncwarp();
+        }
+      }
+      else
+      {
+        if (threadIdx.x == 0)
+          cs.next_tile[(k + 1) & 1u] = 0;
+        if (threadIdx.x < SETUP_WORDS)
+          cs.stage[threadIdx.x] = reinterpret_cast<const uint32_t*>(setups + it.cmd_begin)[threadIdx.x];
+        __syncthreads();
+        const PrimSetup& s = *reinterpret_cast<const PrimSetup*>(cs.stage);
+        if (s.op != OP_NOP)
+        {
+          if (it.kind == EPOCH_SELF_SAMPLING)
+            serial_self_sampling(s, vram, cluts);
+          else if (it.kind == EPOCH_COPY_OVERLAP)
+            serial_copy<NT>(s, vram);
+          else
+            serial_upload_masked<NT>(s, vram, payload, cs.row_count);
+        }
+      }
+    }
+    else if (threadIdx.x == 0)
+      cs.next_tile[(k + 1) & 1u] = 0;
+    __syncthreads();
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ hash
 constexpr uint32_t HASH_BLOCKS_PER_INSTANCE = 32;
 
@@ -1421,33 +1608,27 @@ cudaError_t launch_clut(const WaveItem* items, uint32_t n_items, const ClutOp* o
 
 cudaError_t launch_raster(const WaveItem* items, uint32_t n_items, const PrimSetup* setups, const uint32_t* tile_cmds,
                           uint16_t* vram_pool, const uint16_t* clut_pool, const uint16_t* payload, uint32_t clut_slots,
-                          cudaStream_t st, uint32_t tiled_cmds)
+                          cudaStream_t st, uint32_t tiled_cmds, unsigned int* loop_counter)
 {
   // Waves with enough work use the persistent-loop kernel (PSXGPU_RASTER_LOOP=0 forces one CTA per tile everywhere).
   static const int loop_mode = []() {
     const char* e = std::getenv("PSXGPU_RASTER_LOOP");
     return e ? std::atoi(e) : 1;
   }();
-  if (loop_mode > 0 && n_items >= 16 && n_items * static_cast<uint64_t>(NUM_TILES) < 0xFFFF0000ull)
+  if (loop_mode > 0 && loop_counter != nullptr && n_items >= 16 && n_items * static_cast<uint64_t>(NUM_TILES) < 0xFFFF0000ull)
   {
-    // (contexts may be driven from different host threads: the slot counter is atomic, device attributes are per call)
-    static std::atomic<uint32_t> next_slot{0};
+    // The work counter belongs to the caller's context (one per stream: the reset, the wave and the next reset are
+    // ordered by the stream), so contexts on other streams or host threads never share one.
     int dev = 0, sms = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    void* sym = nullptr;
-    cudaError_t se = cudaGetSymbolAddress(&sym, g_raster_loop_counter);
-    if (se != cudaSuccess)
-      return se;
-    unsigned int* counters = static_cast<unsigned int*>(sym);
-    const uint32_t slot = next_slot.fetch_add(1) % 64u;
-    cudaError_t e = cudaMemsetAsync(counters + slot, 0, sizeof(unsigned int), st);
+    cudaError_t e = cudaMemsetAsync(loop_counter, 0, sizeof(unsigned int), st);
     if (e != cudaSuccess)
       return e;
     const uint32_t total = n_items * NUM_TILES;
     const uint32_t ctas = std::min<uint32_t>(static_cast<uint32_t>(sms) * PSX_RASTER_MIN_CTAS, total / 2u + 1u);
     const uint32_t grab = (tiled_cmds <= static_cast<uint64_t>(n_items) * LOOP_LIGHT_CMDS_PER_ITEM) ? LOOP_GRAB_LIGHT : LOOP_GRAB_HEAVY;
-    raster_loop_kernel<<<ctas, 32, 0, st>>>(items, n_items, setups, tile_cmds, vram_pool, clut_pool, payload, clut_slots, slot, grab);
+    raster_loop_kernel<<<ctas, 32, 0, st>>>(items, n_items, setups, tile_cmds, vram_pool, clut_pool, payload, clut_slots, loop_counter, grab);
     return cudaGetLastError();
   }
   // gridDim.y is limited to 65535: chunk the wave
@@ -1503,6 +1684,35 @@ cudaError_t launch_persistent(const WaveItem* items, const void* waves, uint32_t
                   &barrier_counter};
   return cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(raster_persistent_kernel), dim3(NUM_TILES, n_instances),
                                      dim3(PERSIST_THREADS), args, 0, st);
+}
+
+cudaError_t launch_instances(const InstWork* work, uint32_t n_instances, const Epoch* epochs, uint32_t* tile_sets, const PrimSetup* setups,
+                             const uint32_t* tile_cmds, const ClutOp* clut_ops, uint16_t* vram_pool, uint16_t* clut_pool,
+                             const uint16_t* payload, uint32_t clut_slots, bool wide, cudaStream_t st)
+{
+  if (n_instances == 0)
+    return cudaSuccess;
+  epoch_tiles_kernel<<<n_instances, 128, 0, st>>>(work, epochs, tile_cmds, tile_sets);
+  cudaError_t e;
+  if (wide)
+  {
+    constexpr uint32_t W = 32;
+    const size_t smem = sizeof(RasterShared<TILE_H>) * W + sizeof(InstanceShared);
+    if ((e = cudaFuncSetAttribute(raster_instance_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))) != cudaSuccess)
+      return e;
+    raster_instance_kernel<W><<<n_instances, 32 * W, smem, st>>>(work, epochs, tile_sets, setups, tile_cmds, clut_ops, vram_pool, clut_pool,
+                                                                 payload, clut_slots);
+  }
+  else
+  {
+    constexpr uint32_t W = 8;
+    const size_t smem = sizeof(RasterShared<TILE_H>) * W + sizeof(InstanceShared);
+    if ((e = cudaFuncSetAttribute(raster_instance_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))) != cudaSuccess)
+      return e;
+    raster_instance_kernel<W><<<n_instances, 32 * W, smem, st>>>(work, epochs, tile_sets, setups, tile_cmds, clut_ops, vram_pool, clut_pool,
+                                                                 payload, clut_slots);
+  }
+  return cudaGetLastError();
 }
 
 cudaError_t launch_hash(const uint16_t* vram_pool, uint32_t first, uint32_t count, unsigned long long* out, cudaStream_t st)

@@ -30,7 +30,9 @@ cudaError_t launch_clut(const WaveItem* items, uint32_t n_items, const ClutOp* o
                         uint16_t* clut_pool, uint32_t clut_slots, cudaStream_t st);
 cudaError_t launch_raster(const WaveItem* items, uint32_t n_items, const PrimSetup* setups, const uint32_t* tile_cmds,
                           uint16_t* vram_pool, const uint16_t* clut_pool, const uint16_t* payload, uint32_t clut_slots,
-                          cudaStream_t st, uint32_t tiled_cmds = 0xFFFFFFFFu); // tiled_cmds: commands of the wave's tiled epochs
+                          cudaStream_t st, uint32_t tiled_cmds, unsigned int* loop_counter);
+// tiled_cmds: commands of the wave's tiled epochs; loop_counter: one device word owned by the caller's context / stream
+// (work counter of raster_loop_kernel; nullptr = one CTA per tile)
 cudaError_t launch_serial(const WaveItem* items, uint32_t n_items, const PrimSetup* setups, uint16_t* vram_pool,
                           const uint16_t* clut_pool, const uint16_t* payload, uint32_t clut_slots, cudaStream_t st);
 // Persistent (latency) mode: whole flush of up to persistent_max_instances() instances in one cooperative launch.
@@ -40,6 +42,12 @@ cudaError_t launch_persistent(const WaveItem* items, const void* waves, uint32_t
                               const PrimSetup* setups, const uint32_t* tile_cmds, const ClutOp* clut_ops, uint16_t* vram_pool,
                               uint16_t* clut_pool, const uint16_t* payload, uint32_t clut_slots, unsigned int* barrier_counter,
                               cudaStream_t st);
+// Instance mode (many short epochs per instance): one CTA per instance for a whole flush, __syncthreads() between
+// epochs.  `work` / `epochs`: device arrays (psx_types.h).  wide = 32 warps per CTA (a handful of instances), else 8.
+// `tile_sets`: scratch, eight words per epoch slot (filled here by epoch_tiles_kernel: the tiles each epoch touches).
+cudaError_t launch_instances(const InstWork* work, uint32_t n_instances, const Epoch* epochs, uint32_t* tile_sets, const PrimSetup* setups,
+                             const uint32_t* tile_cmds, const ClutOp* clut_ops, uint16_t* vram_pool, uint16_t* clut_pool,
+                             const uint16_t* payload, uint32_t clut_slots, bool wide, cudaStream_t st);
 cudaError_t launch_hash(const uint16_t* vram_pool, uint32_t first, uint32_t count, unsigned long long* out, cudaStream_t st);
 cudaError_t launch_scanout(const uint16_t* vram, const ScanoutParams& p, uint8_t* out, cudaStream_t st);
 

@@ -125,6 +125,24 @@ enum EpochKind : uint32_t
   EPOCH_UPLOAD_MASKED = 3, // one mask-checked CPU->VRAM upload
 };
 
+// One epoch of one instance, indices relative to the instance's own commands / CLUT ops.
+struct Epoch
+{
+  uint32_t cmd_begin, cmd_end; // indices into cmds
+  uint32_t kind;               // EpochKind
+  uint32_t clut_begin, clut_end;
+};
+
+// One instance of a chunk for raster_instance_kernel: where its epochs, commands and CLUT ops start in the chunk's arrays.
+struct InstWork
+{
+  uint32_t instance;
+  uint32_t cmd_base, clut_base;
+  uint32_t epoch_first, n_epochs;
+  uint32_t pad[3];
+};
+static_assert(sizeof(InstWork) == 32, "InstWork");
+
 struct WaveItem
 {
   uint32_t instance;

@@ -606,6 +606,54 @@ void gen_config4(Builder& b, Rng& r, uint32_t n)
     emit_mix_prim(b, r, L, P, false);
 }
 
+// ---- config 6: config 4 with hazards — the same clear + atlas + mix, plus config 2's 1 % self-sampling slice (Q1) and a
+// render-to-texture pair every 100 primitives (an untextured triangle drawn INTO a texture page of the atlas, then
+// a sprite that samples that page through a palette fetched from the pixels just drawn): every pair forces a
+// write-after-read and a read-after-write cut, so an instance runs in tens of epochs instead of two ----
+void gen_config6(Builder& b, Rng& r, uint32_t n)
+{
+  const TexLayout L{512, 0, 256, 256};
+  b.fill(0, 0, 512, 511, r.next());
+  noise_upload(b, r, 512, 0, 256, 256);
+  b.set_area(0, 0, 511, 510);
+  const MixParams P{0, 0, 512, 511, 29, 8, 24, 70, 20, true};
+  for (uint32_t i = 0; i < n; i++)
+  {
+    if (i % 100 == 99)
+    {
+      const uint32_t page = 8 + r.below(4); // the atlas covers pages 8..11 (x 512..767), rows 0..255
+      const int x0 = static_cast<int>(page) * 64;
+      b.set_mask = b.check_mask = false;
+      b.window = psx_texture_window{0xFF, 0xFF, 0, 0};
+      b.set_area(static_cast<uint32_t>(x0), 0, static_cast<uint32_t>(x0 + 63), 255);
+      b.draw_mode = make_draw_mode(0, 0, 0, 0, true);
+      psx_poly_vertex v[3];
+      std::memset(v, 0, sizeof(v));
+      const int cx = x0 + r.range(8, 56), cy = r.range(16, 240);
+      for (auto& p : v)
+      {
+        p.x = cx + r.range(-29, 29);
+        p.y = cy + r.range(-29, 29);
+        const uint32_t c = r.next();
+        p.r = static_cast<uint8_t>(c);
+        p.g = static_cast<uint8_t>(c >> 8);
+        p.b = static_cast<uint8_t>(c >> 16);
+      }
+      b.polygon(3, v, false, false, false, true, 0);
+      b.set_area(0, 0, 511, 510);
+      const uint32_t tex_mode = r.below(2); // 4- or 8-bit: the palette row lies inside the page just drawn
+      b.draw_mode = make_draw_mode(tex_mode == 1 && page > 10 ? 10 : page, 0, r.below(4), tex_mode, false);
+      const uint16_t pal = static_cast<uint16_t>(((x0 / 16) & 0x3F) | (static_cast<uint32_t>(r.below(256)) << 6));
+      b.clut_reg = 0xFFFFFFFFu; // GP0(01h)-style invalidation: UpdateCLUT re-reads the fresh pixels
+      b.clut_is_8bit = false;
+      b.rectangle(r.range(0, 480), r.range(0, 480), r.range(8, 24), r.range(8, 24), r.next(), static_cast<uint8_t>(r.next()),
+                  static_cast<uint8_t>(r.next()), true, r.chance(50), r.chance(50), pal);
+      continue;
+    }
+    emit_mix_prim(b, r, L, P, r.chance(1));
+  }
+}
+
 // ---- config 5: game-like frames; n = number of frames ----
 void gen_config5(Builder& b, Rng& r, uint32_t frames, uint32_t prims_per_frame)
 {
@@ -847,7 +895,7 @@ void gen_fuzz(Builder& b, Rng& r, uint32_t n, uint32_t flags)
 
 extern "C" {
 
-// config: 0 fuzz, 1..5 the BASELINE.json configs (1-based).  n: primitives / commands / frames (config 5).
+// config: 0 fuzz, 1..5 the BASELINE.json configs (1-based), 6 = config 4 with hazards.  n: primitives / commands / frames (config 5).
 // flags: config 0 -> bit0 textures may overlap the draw area (Q1), bit1 include transfers;
 //        config 5 -> primitives per frame (0 = 1500).
 uint8_t* psxgen_config(int config, uint32_t seed, uint32_t n, uint32_t flags, size_t* out_bytes)
@@ -862,6 +910,7 @@ uint8_t* psxgen_config(int config, uint32_t seed, uint32_t n, uint32_t flags, si
     case 3: gen_config3(b, r, n); break;
     case 4: gen_config4(b, r, n); break;
     case 5: gen_config5(b, r, n, flags ? flags : 1500u); break;
+    case 6: gen_config6(b, r, n); break;
     default: *out_bytes = 0; return nullptr;
   }
   uint8_t* p = static_cast<uint8_t*>(std::malloc(b.out.size() ? b.out.size() : 1));

@@ -52,7 +52,8 @@ typedef struct psxgpu_opts {
   uint32_t clut_slots;       /* CLUT snapshot slots per instance (4..256, 0 = 256) */
   uint32_t encode_threads;   /* host threads for psxgpu_submit_batch (0 = hardware concurrency) */
   uint32_t profile;          /* 1: time every raster wave with CUDA events (psxgpu_get_timing) */
-  uint32_t reserved[9];      /* [0] = 1: no persistent (latency-mode) kernel; [1]: where psxgpu_submit_batch encodes —
+  uint32_t reserved[9];      /* [0] bit 0: no persistent (latency-mode) kernel, bit 1: no instance-mode kernel (one launch per
+                                epoch wave; tests and profiling); [1]: where psxgpu_submit_batch encodes —
                                 0 auto (on the device for batches of >= 16 instances), 1 host threads, 2 device */
 } psxgpu_opts;
 

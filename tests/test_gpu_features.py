@@ -233,21 +233,22 @@ def test_full_size_properties(oracle):
 
 @pytest.mark.parametrize("case", [(3, 8, 2500, 0), (2, 8, 3000, 0), (0, 51, 2500, 3)], ids=["mixed", "textured", "fuzz"])
 def test_latency_mode_equals_launch_per_epoch(oracle, case):
-    """The persistent cooperative kernel (flushes of <= 4 instances) and the launch-per-epoch path (forced here by
-    profile=True, or by more instances) must produce the same VRAM as the oracle."""
+    """The resident kernels (the cooperative latency-mode kernel, or the instance-mode kernel when the stream is cut into
+    many short epochs) and the launch-per-epoch path must produce the same VRAM as the oracle."""
     s = streams.generate(*case)
     want = oracle.render(s)
     with _ctx(1) as ctx:  # latency mode
         ctx.submit(s)
         a = ctx.read_vram()
         launches_persistent = ctx.stats()["kernel_launches"]
-    with _ctx(1, profile=True) as ctx:  # one launch per epoch
+    with _ctx(1, profile=True, launch_per_epoch=True) as ctx:  # one launch per epoch
         ctx.submit(s)
         b = ctx.read_vram()
         launches_per_epoch = ctx.stats()["kernel_launches"]
     assert np.array_equal(a, want), describe_diff(a, want)
     assert np.array_equal(b, want), describe_diff(b, want)
-    assert launches_persistent < launches_per_epoch
+    if "PSXGPU_INSTANCE_MODE" not in os.environ:  # (forced instance mode: one launch either way)
+        assert launches_persistent < launches_per_epoch
     with _ctx(6) as ctx:  # six instances: throughput kernels
         ctx.submit_batch([s] * 6)
         ctx.flush()
@@ -338,7 +339,7 @@ def test_psxgpu_trace_replay_through_the_gp0_frontend(oracle, interlaced):
 
 
 DEVICE_ENCODER_CASES = ([(0, s, 600, f) for s in (3, 4, 5, 6, 7, 8) for f in (0, 1, 2, 3)] +
-                        [(1, 2, 1500, 0), (2, 2, 1500, 0), (3, 2, 800, 0), (4, 2, 800, 0), (5, 2, 6, 200)])
+                        [(1, 2, 1500, 0), (2, 2, 1500, 0), (3, 2, 800, 0), (4, 2, 800, 0), (5, 2, 6, 200), (6, 2, 1200, 0), (6, 3, 2000, 0)])
 
 
 def _strip_barriers(stream: bytes) -> bytes:
@@ -362,6 +363,44 @@ def test_device_encoder_matches_oracle_and_host_encoder(oracle):
     for key in ("wire_commands", "packed_prims", "epochs", "cuts_raw", "cuts_war", "cuts_clut", "serial_self_sampling",
                 "serial_copy", "serial_upload", "clut_ops", "clut_cache_hits", "rejected"):
         assert stats[2][key] == stats[1][key], (key, stats[2][key], stats[1][key])
+
+
+def test_instance_mode_batch_with_hazards(oracle):
+    """Generator config 6 (config 4 + self-sampling primitives + render-to-texture pairs: tens of epochs per instance):
+    a device-encoded batch takes the instance-mode kernel (one CTA per instance, one launch for all epochs) and must
+    match the oracle, and the launch-per-epoch path must give the same hashes."""
+    batch = [streams.generate(6, 40 + i, 1500, 0) for i in range(24)]
+    want = [oracle.hash64(oracle.render(s)) for s in batch]
+    launches = {}
+    for per_epoch in (False, True):
+        with _ctx(len(batch), launch_per_epoch=per_epoch) as ctx:
+            ctx.submit_batch(batch)
+            ctx.flush()
+            assert [int(h) for h in ctx.hash()] == want, per_epoch
+            st = ctx.stats()
+            assert st["epochs"] > 20 * len(batch)
+            launches[per_epoch] = st["kernel_launches"]
+    if "PSXGPU_INSTANCE_MODE" not in os.environ:
+        assert launches[False] < launches[True] // 4
+
+
+def test_truncated_records_host_and_device_encoders_agree(oracle):
+    """A record that is shorter than its own counts ask for is dropped and counted by both encoders (never read past)."""
+    from tests.test_hostsim import _area, _rect, _truncated_records
+    good = _area(0, 0, 1023, 511) + _rect(10, 10, 50, 50, 0x3050F0)
+    tail = _rect(100, 100, 20, 20, 0x10F010)
+    s = good + b"".join(_truncated_records()) + tail
+    want = oracle.hash64(oracle.render(good + tail))
+    batch = [s] * 16
+    for mode in (2, 1):
+        with _ctx(len(batch), encode_mode=mode, no_persistent=True) as ctx:
+            ctx.submit_batch(batch)
+            ctx.flush()
+            assert [int(h) for h in ctx.hash()] == [want] * len(batch), mode
+            assert ctx.stats()["rejected"] == 4 * len(batch), (mode, ctx.stats()["rejected"])
+    with _ctx(1) as ctx:
+        ctx.submit(s)
+        assert int(ctx.hash()[0]) == want and ctx.stats()["rejected"] == 4
 
 
 def test_device_encoder_state_carries_across_flushes_and_paths(oracle):

@@ -48,6 +48,24 @@ def test_malformed_stream_rejected(sim):
         sim.render(bad[:10])
 
 
+def _truncated_records():
+    """Records whose framed size is smaller than what their own fields ask for (a polygon that claims four vertices and
+    carries one, a poly-line of 65535 vertices in 32 bytes, a rectangle cut in half, an upload without its pixels)."""
+    poly = struct.pack("<IB3x", 36, 22) + struct.pack("<BBHHH4B", 0, 0, 4, 0, 0, 0xFF, 0xFF, 0, 0) + b"\x11" * 16
+    line = struct.pack("<IB3x", 32, 25) + struct.pack("<BBHHH4B", 0, 0, 65535, 0, 0, 0xFF, 0xFF, 0, 0) + b"\x22" * 12
+    rect = struct.pack("<IB3x", 24, 24) + b"\x33" * 16
+    upload = struct.pack("<IB3x", 20, 17) + struct.pack("<4HBB2x", 0, 0, 64, 64, 0, 0)
+    return [poly, line, rect, upload]
+
+
+def test_truncated_records_are_dropped_not_read_past(oracle, sim):
+    good = _area(0, 0, 1023, 511) + _rect(10, 10, 50, 50, 0x3050F0)
+    s = good + b"".join(_truncated_records()) + _rect(100, 100, 20, 20, 0x10F010)
+    got = sim.render(s)
+    assert sim.stats()["rejected"] == 4
+    assert np.array_equal(got, oracle.render(good + _rect(100, 100, 20, 20, 0x10F010)))
+
+
 # ---- epoch splitter behaviour (stats come from the encoder) ----
 def _rec(fmt, typ, *vals):
     body = struct.pack(fmt, *vals)
