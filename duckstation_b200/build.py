@@ -5,6 +5,8 @@
 * ``oracle/libpsxoracle.so``         — CPU restatement used as the parity oracle (gcc; test infrastructure)
 * ``oracle/_ref/libpsxref.so``       — the reference's own rasteriser TU compiled in place (only where
                                         ``/root/reference`` exists; test infrastructure)
+* ``oracle/_ref/libpsxdec.so``       — the reference's own GP0/GP1 decoder, CRTC and GPU::DoState (gpu.cpp) compiled in
+                                        place with link stubs (same condition; test infrastructure)
 * ``tests/hostsim/libhostsim.so``    — host build of the device headers for CPU-only tests
 
 nvcc cross-compiles without a GPU, so this runs on the CPU-only build box too.
@@ -84,6 +86,18 @@ def build_reference(force: bool = False) -> str | None:
     return out
 
 
+def build_decoder_reference(force: bool = False) -> str | None:
+    """oracle/_ref/libpsxdec.so: the reference's own GP0/GP1 decoder + CRTC + save-state code (src/core/gpu.cpp) compiled
+    in place with link stubs (oracle/ref_build/dec_harness.cpp).  Only where the reference checkout is mounted."""
+    out = os.path.join(ROOT, "oracle", "_ref", "libpsxdec.so")
+    if not os.path.isfile(os.path.join(REFERENCE, "src", "core", "gpu.cpp")):
+        return out if os.path.exists(out) else None
+    if force:
+        _run(["make", "-f", "Makefile.decoder", "clean"], cwd=os.path.join(ROOT, "oracle", "ref_build"))
+    _run(["make", "-f", "Makefile.decoder"], cwd=os.path.join(ROOT, "oracle", "ref_build"))
+    return out
+
+
 def build_hostsim(force: bool = False) -> str:
     out = os.path.join(ROOT, "tests", "hostsim", "libhostsim.so")
     srcs = [os.path.join(ROOT, "tests", "hostsim", "hostsim.cpp"), os.path.join(CSRC, "encoder.cpp")]
@@ -105,6 +119,7 @@ def build_all(force: bool = False) -> dict[str, str | None]:
                 "generator": build_generator(force),
                 "oracle": build_oracle(force),
                 "reference": build_reference(force),
+                "decoder_reference": build_decoder_reference(force),
                 "hostsim": build_hostsim(force),
             }
         finally:

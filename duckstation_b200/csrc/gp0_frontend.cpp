@@ -48,6 +48,7 @@ Gp0Frontend::Gp0Frontend()
 void Gp0Frontend::reset(bool pal_region)
 {
   m_console_pal = pal_region;
+  m_gpustat_unmodelled = 0x14802000u & GPUSTAT_UNMODELLED;
   if (m_state == State::WritingVRAM)
     finish_vram_write();
   m_fifo.clear();
@@ -508,7 +509,7 @@ bool Gp0Frontend::handle_rectangle(uint32_t rc) // gpu.cpp:3359-3436
   prepare_for_draw();
   auto* c = emit<psx_draw_rectangle>(sizeof(psx_draw_rectangle), PSX_CMD_DRAW_RECTANGLE);
   fill_draw_header(&c->d, 1, rc);
-  c->d.num_vertices = 1;
+  c->d.num_vertices = 0; // (the reference leaves the field of a rectangle record unset: gpu.cpp:3424-3470 never writes it)
   c->color = rc & 0x00FFFFFFu;
   const uint32_t pos = pop();
   c->x = sext11(static_cast<uint32_t>(m_offset_x + vertex_x(pos)));
@@ -712,7 +713,7 @@ void Gp0Frontend::write_gp1(uint32_t value) // gpu.cpp:1931-2106
     case 0x03: m_display_disable = value & 1u; break;
     case 0x05:
     {
-      const uint32_t nv = param & 0x7FFFFu;
+      const uint32_t nv = param & 0x7FFFEu; // CRTCState::Regs::DISPLAY_ADDRESS_START_MASK (gpu.cpp:242): bit 0 is not kept
       if (m_display_address_start != nv)
       {
         m_display_address_start = nv;
@@ -831,6 +832,8 @@ void Gp0Frontend::vsync() // GPU::UpdateDisplay (gpu.cpp:2451-2481) + the field 
                                   (in_480i ? PSX_UD_480I_MODE : 0) | (m_display_24 ? PSX_UD_DISPLAY_24BIT : 0) |
                                   (disabled ? PSX_UD_DISPLAY_DISABLED : 0) | PSX_UD_SUBMIT_FRAME);
   m_stats.frames++;
+  if (!m_field_per_vsync)
+    return; // (the reference's trace replay: the beam does not run, the field bits stay)
   // next frame's field / active line
   const uint8_t display_field = in_480i ? (m_interlaced_field ^ 1u) : 0u;
   m_interlaced_field = m_vertical_interlace ? (m_interlaced_field ^ 1u) : 0u;
@@ -1090,6 +1093,7 @@ bool Gp0Frontend::load_state(const uint8_t* data, size_t bytes, uint32_t version
   m_area_changed = true; // gpu.cpp:704
   m_offset_x = off_x;
   m_offset_y = off_y;
+  m_gpustat_unmodelled = gpustat & GPUSTAT_UNMODELLED;
   m_draw_to_displayed_field = (gpustat >> 10) & 1u;
   m_set_mask = (gpustat >> 11) & 1u;
   m_check_mask = (gpustat >> 12) & 1u;
@@ -1120,11 +1124,13 @@ void Gp0Frontend::save_state(std::vector<uint8_t>& out, const uint16_t* vram, co
   StateWriter w{out};
   // GPUSTAT: draw-mode bits 0-10 and 15 mirror the register (gpu.cpp:2210-2213); the rest from the display state
   uint32_t gpustat = (m_draw_mode & 0x7FFu) | (((m_draw_mode >> 11) & 1u) << 15);
-  gpustat |= (m_set_mask ? 1u : 0u) << 11 | (m_check_mask ? 1u : 0u) << 12 | static_cast<uint32_t>(m_interlaced_field & 1u) << 13;
+  gpustat |= (m_set_mask ? 1u : 0u) << 11 | (m_check_mask ? 1u : 0u) << 12;
   gpustat |= static_cast<uint32_t>(m_hres2) << 16 | static_cast<uint32_t>(m_hres1) << 17 | (m_vertical_res ? 1u : 0u) << 19 |
              (m_pal ? 1u : 0u) << 20 | (m_display_24 ? 1u : 0u) << 21 | (m_vertical_interlace ? 1u : 0u) << 22 |
              (m_display_disable ? 1u : 0u) << 23;
-  gpustat |= 0x14000000u; // ready to receive command / DMA: idle values of the dynamic bits (gpu.cpp:499)
+  // bits this front-end does not model (13 field status, 14 reverse flag, 24-31 the dynamic ready / DMA bits): as loaded,
+  // or their reset values (gpu.cpp:499: 0x14802000)
+  gpustat |= m_gpustat_unmodelled & GPUSTAT_UNMODELLED;
   w.put<uint32_t>(gpustat);
   w.put<uint16_t>(m_draw_mode);
   w.put<uint16_t>(m_palette);
@@ -1224,6 +1230,7 @@ int psxgpu_frontend_create(uint32_t flags, uint32_t crop_mode, psxgpu_frontend**
     return PSXGPU_E_NOMEM;
   f->fe.set_crop_mode(static_cast<psx::CropMode>(crop_mode));
   f->fe.set_force_progressive(!(flags & PSXGPU_FE_INTERLACED));
+  f->fe.set_field_per_vsync((flags & PSXGPU_FE_FIELD_PER_VSYNC) != 0);
   f->fe.reset((flags & PSXGPU_FE_PAL) != 0);
   f->fe.clear_output();
   *out = f;
@@ -1339,6 +1346,7 @@ long psxgpu_replay_dump(psxgpu_ctx* ctx, uint32_t instance, const void* data, si
   psx::Gp0Frontend fe;
   fe.set_crop_mode(static_cast<psx::CropMode>(crop_mode));
   fe.set_force_progressive(!(flags & PSXGPU_FE_INTERLACED));
+  fe.set_field_per_vsync((flags & PSXGPU_FE_FIELD_PER_VSYNC) != 0);
   fe.reset((flags & PSXGPU_FE_PAL) != 0);
   fe.clear_output();
   ReplayCtx r{ctx, instance, on_frame, user, 0, PSXGPU_OK};

@@ -39,6 +39,9 @@ public:
   /// display_deinterlacing_mode == Progressive (the reference's default, settings.h:238): no interlaced rendering or
   /// field-split scan-out; 480i frames are shown whole (gpu.cpp:411, :1465-1478).
   void set_force_progressive(bool v) { m_force_progressive = v; }
+  /// PSXGPU_FE_FIELD_PER_VSYNC: flip the interlace field / active-line bit at every vsync() (stand-in for a running CRTC);
+  /// off = the reference's trace-replay behaviour (the bits only change through GP1 or a loaded state).
+  void set_field_per_vsync(bool v) { m_field_per_vsync = v; }
 
   /// GP0 port: words are queued in the FIFO and executed as far as complete commands allow.
   void write_gp0(const uint32_t* words, size_t count);
@@ -119,6 +122,9 @@ private:
   State m_state = State::Idle;
   Stats m_stats;
   CropMode m_crop = CropMode::Overscan;
+  bool m_field_per_vsync = false;
+  static constexpr uint32_t GPUSTAT_UNMODELLED = 0xFF006000u;
+  uint32_t m_gpustat_unmodelled = 0x14802000u & GPUSTAT_UNMODELLED; // GPU::SoftReset, gpu.cpp:499
   bool m_force_progressive = true;
 
   // draw state

@@ -9,14 +9,15 @@ import numpy as np
 from . import _lib
 
 CROP_NONE, CROP_OVERSCAN, CROP_BORDERS = 0, 1, 2
-FE_PAL, FE_INTERLACED = 1, 2
+FE_PAL, FE_INTERLACED, FE_FIELD_PER_VSYNC = 1, 2, 4
 
 
 class Gp0Frontend:
-    def __init__(self, *, pal: bool = False, interlaced: bool = False, crop_mode: int = CROP_OVERSCAN):
+    def __init__(self, *, pal: bool = False, interlaced: bool = False, crop_mode: int = CROP_OVERSCAN,
+                 field_per_vsync: bool = False):
         self._lib = _lib.load()
         self._h = C.c_void_p()
-        flags = (FE_PAL if pal else 0) | (FE_INTERLACED if interlaced else 0)
+        flags = (FE_PAL if pal else 0) | (FE_INTERLACED if interlaced else 0) | (FE_FIELD_PER_VSYNC if field_per_vsync else 0)
         rc = self._lib.psxgpu_frontend_create(flags, crop_mode, C.byref(self._h))
         if rc != 0:
             raise ValueError(f"psxgpu_frontend_create failed ({rc})")
@@ -87,12 +88,12 @@ class Gp0Frontend:
 
 
 def replay_dump(ctx, data: bytes, *, instance: int = 0, pal: bool = False, interlaced: bool = False,
-                crop_mode: int = CROP_OVERSCAN, on_frame=None) -> int:
+                crop_mode: int = CROP_OVERSCAN, on_frame=None, field_per_vsync: bool = False) -> int:
     """Replays a `.psxgpu` trace into `instance` of a Context (psxgpu_replay_dump).  `on_frame(frame_index)` runs after
     each frame has been submitted; ctx.display() is that frame's scan-out."""
     lib = _lib.load()
     cb = _lib.FRAME_CALLBACK((lambda _u, i: on_frame(i)) if on_frame else (lambda _u, i: None))
-    flags = (FE_PAL if pal else 0) | (FE_INTERLACED if interlaced else 0)
+    flags = (FE_PAL if pal else 0) | (FE_INTERLACED if interlaced else 0) | (FE_FIELD_PER_VSYNC if field_per_vsync else 0)
     n = lib.psxgpu_replay_dump(ctx._ctx, instance, data, len(data), flags, crop_mode, cb, None)
     if n < 0:
         raise ValueError(f"psxgpu_replay_dump failed ({n}): {lib.psxgpu_last_error(ctx._ctx).decode()}")

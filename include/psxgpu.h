@@ -188,7 +188,12 @@ typedef struct psxgpu_frontend_stats {
 /* flags: PSXGPU_FE_*; crop_mode: 0 none, 1 overscan (the reference's default), 2 borders (settings.h DisplayCropMode). */
 enum {
   PSXGPU_FE_PAL = 1,       /* PAL console region (System::IsPALRegion) */
-  PSXGPU_FE_INTERLACED = 2 /* display_deinterlacing_mode != Progressive: interlaced rendering + field scan-out on */
+  PSXGPU_FE_INTERLACED = 2, /* display_deinterlacing_mode != Progressive: interlaced rendering + field scan-out on */
+  PSXGPU_FE_FIELD_PER_VSYNC = 4 /* flip the interlace field and the active-line bit at every psxgpu_frontend_vsync: a stand-in
+                                   for the beam-accurate CRTC of a running console (gpu.cpp:1679-1721).  Without it the two
+                                   bits only change through GP1 / a loaded state — what the reference itself does while it
+                                   replays a .psxgpu trace (GPU::ProcessGPUDumpPacket, gpu.cpp:4151-4168: the CRTC event is
+                                   not running), and what the decoder parity tests pin. */
 };
 int psxgpu_frontend_create(uint32_t flags, uint32_t crop_mode, psxgpu_frontend** out);
 void psxgpu_frontend_destroy(psxgpu_frontend* fe);

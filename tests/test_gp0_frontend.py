@@ -304,7 +304,7 @@ def test_display_crop_modes_pal_24bit_and_disable():
 
 
 def test_480i_field_toggle_and_interlaced_rendering():
-    fe = Gp0Frontend(interlaced=True)
+    fe = Gp0Frontend(interlaced=True, field_per_vsync=True)
     fe.gp1(gp1_mode(hres1=3, vres=1, interlace=1))
     fe.gp1(0x06000000 | 0x260 | (0xC60 << 12))
     fe.gp1(0x07000000 | 16 | (256 << 10))
