@@ -85,3 +85,26 @@ def test_generator_records_have_the_reference_layout():
         w, h = struct.unpack_from("<HH", s, off + 12)
         assert size == ((18 + 2 * w * h + 15) & ~15)
     assert {16, 18, 19, 20} <= set(seen)  # fill, copy, drawing area, CLUT
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/src/core"), reason="needs the reference headers")
+def test_boundary_subclass_compiles_against_the_reference_header():
+    """INTEGRATION.md §2's `GPU_CUDA final : public GPUBackend` (oracle/ref_build/boundary_check.cpp) compiles against
+    the real src/core/gpu_backend.h — every virtual it overrides exists with that signature, UpdateSettings included —
+    and stops compiling when a signature drifts (negative control)."""
+    import subprocess
+
+    d = os.path.join(ROOT, "oracle", "ref_build")
+    obj = os.path.join(ROOT, "oracle", "_ref", "boundary_check.o")
+    if os.path.exists(obj):
+        os.remove(obj)
+    r = subprocess.run(["make", "-f", "Makefile.decoder", "boundary_check"], cwd=d, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    syms = subprocess.run(["nm", "-C", obj], capture_output=True, text=True, check=True).stdout
+    for name in ("GPU_CUDA::UpdateSettings", "GPU_CUDA::DrawPolygon", "GPU_CUDA::UpdateDisplay", "GPU_CUDA::DoMemoryState",
+                 "GPU_CUDA::DrawingAreaChanged", "CreateCUDABackend"):
+        assert name in syms, name
+    assert "psxgpu_submit_wire" in syms  # undefined reference to the C ABI: that is what it forwards to
+    r = subprocess.run(["make", "-f", "Makefile.decoder", "boundary_check", "OUT=/tmp/_boundary_drift",
+                        "CXX=g++ -DBOUNDARY_DRIFT"], cwd=d, capture_output=True, text=True)
+    assert r.returncode != 0 and "override" in r.stderr
