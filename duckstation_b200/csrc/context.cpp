@@ -1556,11 +1556,25 @@ static int psxgpu_submit_wire_impl(psxgpu_ctx* ctx, uint32_t instance, const voi
   {
     size_t used = 0;
     const double t0 = now_ms();
+    // A long stream is flushed every AUTO_FLUSH primitives (asynchronously: nothing waits for the device), so that the
+    // device works on the first part while the host encodes the rest; PSXGPU_AUTO_FLUSH=0 turns that off.
+    static const uint32_t auto_flush = []() {
+      const char* e = std::getenv("PSXGPU_AUTO_FLUSH");
+      return e ? static_cast<uint32_t>(std::atoi(e)) : 2048u;
+    }();
+    ctx->enc[instance].set_cmd_budget(auto_flush);
     const EncodeResult res = ctx->enc[instance].add_wire(p + off, bytes - off, &used);
+    ctx->enc[instance].set_cmd_budget(0);
     ctx->encode_ms_acc += now_ms() - t0;
     if (used)
       ctx->dirty[instance] = 1;
     off += used;
+    if (res == EncodeResult::Ok && auto_flush != 0 && ctx->enc[instance].n_cmds() >= auto_flush)
+    {
+      const int frc = flush_work(ctx, std::vector<uint32_t>{instance});
+      if (frc != PSXGPU_OK)
+        return frc;
+    }
     if (res == EncodeResult::Malformed)
     {
       ctx->error = "submit_wire: malformed record stream";

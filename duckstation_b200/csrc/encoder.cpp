@@ -992,6 +992,13 @@ EncodeResult Encoder::add_wire(const void* wire, size_t bytes, size_t* consumed)
     }
     handle_record(p);
     p += h->size;
+    if (m_cmd_budget != 0 && m_n_cmds >= m_cmd_budget)
+    {
+      // the caller wants to flush every so many primitives (psxgpu_submit_wire: the device starts on the first part of a
+      // long stream while the host encodes the rest)
+      *consumed = static_cast<size_t>(p - static_cast<const uint8_t*>(wire));
+      return EncodeResult::Ok;
+    }
   }
   *consumed = bytes;
   return EncodeResult::Ok;

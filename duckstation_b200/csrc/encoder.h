@@ -135,6 +135,8 @@ public:
   EncoderStats stats;
 
   void set_modulation_crop(bool on) { m_modulation_crop = on; }
+  // add_wire returns (Ok, *consumed < bytes) once the open flush holds this many primitives; 0 = no limit.
+  void set_cmd_budget(uint32_t n) { m_cmd_budget = n; }
   // Hand-over between this encoder and the device encoder of the batched path; only between flushes.
   void export_state(EncoderStateBlob& out) const;
   void import_state(const EncoderStateBlob& in);
@@ -163,6 +165,7 @@ private:
   uint32_t m_n_cmds = 0;
   uint64_t m_n_payload = 0;
   bool m_overflow = false;
+  uint32_t m_cmd_budget = 0;
 
   // GPU state mirrored from the command stream
   uint16_t m_area[4] = {0, 0, 0, 0}; // raw drawing area l, t, r, b

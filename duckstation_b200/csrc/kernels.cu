@@ -677,26 +677,47 @@ __device__ __forceinline__ void raster_prim_on_region(const PrimSetup& s, uint32
 // ---- serial epoch kinds: one CTA, the reference's own order ----
 
 // a textured primitive that samples pixels it writes.  The reference (4-wide vector build) gathers the
-// texels of 4 pixels, then stores those 4 pixels; rows and groups are visited in walk order.  One warp, lanes 0..3.
+// texels of 4 pixels, then stores those 4 pixels; rows and groups are visited in walk order.
+//
+// The splitter sends a primitive here when its texture footprint RECTANGLE meets its write rectangle; whether a texel
+// that is actually fetched is a pixel the primitive writes is only known per pixel.  So the CTA first walks the
+// primitive without touching memory (all warps, rows dealt round-robin) and asks of every texel address whether it
+// lies inside the write bounding box.  If none does — the usual case — no fetch can see one of the primitive's own
+// stores, order is unobservable and the rows are shaded by all warps at once.  Otherwise warp 0 replays the
+// reference's order: eight consecutive 4-pixel groups of a row per step, group by group where a texel of group k is
+// one of the pixels that groups 0..k-1 of the step store.
+template<int NT>
 __device__ void serial_self_sampling(const PrimSetup& s, uint16_t* vram, const uint16_t* clut_pool_inst)
 {
-  if (threadIdx.x >= 32)
-    return;
-  const uint32_t lane = threadIdx.x;
+  constexpr uint32_t N_WARPS = NT / 32;
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   const uint16_t* clut_lo = clut_pool_inst + s.clut_lo * CLUT_ENTRIES;
   const uint16_t* clut_hi = clut_pool_inst + s.clut_hi * CLUT_ENTRIES;
   volatile uint16_t* vv = vram;
   const ShadeState st = make_shade_state(s);
+  enum Mode : uint32_t { CHECK, PARALLEL, ORDERED };
+  bool conflict_seen = false;
 
-  // Eight consecutive 4-pixel groups of one row (pixels x0 .. x0+31, lane = pixel).  The reference runs them one after
-  // the other; running them together is the same thing unless a texel of group k is one of the pixels that groups
-  // 0..k-1 of this batch store.  That is checked on the addresses; only then the batch is replayed group by group.
-  auto batch = [&](int32_t x0, uint32_t Y, bool active, uint32_t r, uint32_t g, uint32_t b, uint32_t u, uint32_t v) {
+  // 32 pixels of one row: x0 .. x0+31, lane = pixel
+  auto batch = [&](uint32_t mode, int32_t x0, uint32_t Y, bool active, uint32_t r, uint32_t g, uint32_t b, uint32_t u, uint32_t v) {
     uint32_t shift, idxmask;
     const uint32_t addr = texel_addr(st, u, v, shift, idxmask);
+    if (mode == CHECK)
+    {
+      const uint32_t tcol = addr & (VRAM_W - 1), trow = addr >> 10;
+      conflict_seen |= active && static_cast<int32_t>(tcol) >= s.bx0 && static_cast<int32_t>(tcol) <= s.bx1 &&
+                       ((trow - s.by0) & (VRAM_H - 1)) < s.bycount;
+      return;
+    }
     const uint32_t first_px = Y * VRAM_W + static_cast<uint32_t>(x0);
-    const bool conflict = active && (addr - first_px) < (lane & ~3u); // texel in [first_px, first_px + 4k), k = lane / 4
-    const bool serial = __any_sync(0xFFFFFFFFu, conflict);
+    // the lane's own pixel is written by nobody else in this step: its old value can be fetched with the texel
+    const uint16_t bg = active ? vv[first_px + lane] : uint16_t(0);
+    bool serial = false;
+    if (mode == ORDERED)
+    {
+      const bool conflict = active && (addr - first_px) < (lane & ~3u); // texel in [first_px, first_px + 4k), k = lane / 4
+      serial = __any_sync(0xFFFFFFFFu, conflict);
+    }
     for (uint32_t k = 0; k < (serial ? 8u : 1u); k++)
     {
       const bool mine = active && (!serial || (lane >> 2) == k);
@@ -711,68 +732,86 @@ __device__ void serial_self_sampling(const PrimSetup& s, uint16_t* vram, const u
           texel = __ldcg((idx < 16u ? clut_lo : clut_hi) + idx); // (coherent: the kernels that stay resident rewrite CLUT slots between epochs)
         }
       }
-      __syncwarp();
+      if (mode == ORDERED)
+        __syncwarp();
       if (mine)
       {
         uint32_t colour;
         const uint32_t px = static_cast<uint32_t>(x0) + lane;
         if (shade_colour(st, px, Y, r, g, b, texel, colour))
-        {
-          const uint16_t bg = vv[Y * VRAM_W + px];
           vv[Y * VRAM_W + px] = static_cast<uint16_t>(blend_mask(st, bg, colour));
-        }
       }
-      __syncwarp();
+      if (mode == ORDERED)
+        __syncwarp();
     }
   };
 
-  if (s.op == OP_RECT)
-  {
-    for (uint32_t oy = 0; oy < s.rect.h; oy++)
+  // rows in walk order; in CHECK / PARALLEL mode warp w takes the rows whose ordinal is w mod N_WARPS
+  auto walk = [&](uint32_t mode) {
+    uint32_t ordinal = 0;
+    auto my_row = [&]() {
+      const bool take = mode == ORDERED || (ordinal % N_WARPS) == warp;
+      ordinal++;
+      return take;
+    };
+    if (s.op == OP_RECT)
     {
-      const int32_t y = s.rect.y + static_cast<int32_t>(oy);
-      const uint32_t Y = static_cast<uint32_t>(y) & (VRAM_H - 1);
-      RectRow row;
-      if (!rect_row(s, Y, row) || row.y != y)
-        continue;
-      // groups are counted from the unclipped origin (inl:777-779); 32 is a multiple of 4, so batches keep that phase
-      for (uint32_t ox = 0; ox < s.rect.w; ox += 32)
+      for (uint32_t oy = 0; oy < s.rect.h; oy++)
       {
-        const int32_t x = s.rect.x + static_cast<int32_t>(ox + lane);
-        const bool active = (ox + lane) < s.rect.w && x >= row.x_lo && x < row.x_hi;
-        batch(s.rect.x + static_cast<int32_t>(ox), Y, active, s.rect.r, s.rect.g, s.rect.b, (s.rect.u0 + ox + lane) & 0xFFu, row.v);
+        if (!my_row())
+          continue;
+        const int32_t y = s.rect.y + static_cast<int32_t>(oy);
+        const uint32_t Y = static_cast<uint32_t>(y) & (VRAM_H - 1);
+        RectRow row;
+        if (!rect_row(s, Y, row) || row.y != y)
+          continue;
+        // groups are counted from the unclipped origin (inl:777-779); 32 is a multiple of 4, so batches keep that phase
+        for (uint32_t ox = 0; ox < s.rect.w; ox += 32)
+        {
+          const int32_t x = s.rect.x + static_cast<int32_t>(ox + lane);
+          const bool active = (ox + lane) < s.rect.w && x >= row.x_lo && x < row.x_hi;
+          batch(mode, s.rect.x + static_cast<int32_t>(ox), Y, active, s.rect.r, s.rect.g, s.rect.b, (s.rect.u0 + ox + lane) & 0xFFu, row.v);
+        }
+      }
+      return;
+    }
+    if (s.op != OP_TRIANGLE)
+      return;
+    const auto& T = s.tri;
+    const bool upper_up = (T.tflags & TRI_UPPER_UP) != 0, lower_up = (T.tflags & TRI_LOWER_UP) != 0;
+    // part order = triparts[0], triparts[1] (inl:1557-1560); the upper part is triparts[vo]
+    for (int part = 0; part < 2; part++)
+    {
+      const bool is_upper = (part == 0) != upper_up;
+      const int32_t lo = T.lo[is_upper ? 0 : 1], hi = T.hi[is_upper ? 0 : 1];
+      const bool up = is_upper ? upper_up : lower_up;
+      for (int32_t k = 0; k < hi - lo; k++)
+      {
+        if (!my_row())
+          continue;
+        const int32_t cy = up ? (hi - 1 - k) : (lo + k);
+        const uint32_t Y = static_cast<uint32_t>(sext11(cy)) & (VRAM_H - 1);
+        TriRow row;
+        if (!tri_row(s, Y, row) || row.cy != cy)
+          continue;
+        // groups are counted from the clipped span start (inl:1262-1268)
+        for (int32_t gx = row.x_lo; gx < row.x_hi; gx += 32)
+        {
+          const int32_t px = gx + static_cast<int32_t>(lane);
+          const bool active = px < row.x_hi;
+          uint32_t r, g, b, u, v;
+          tri_attrs(s, row, px, r, g, b, u, v);
+          batch(mode, gx, Y, active, r, g, b, u, v);
+        }
       }
     }
-    return;
-  }
-  if (s.op != OP_TRIANGLE)
-    return;
-  const auto& T = s.tri;
-  const bool upper_up = (T.tflags & TRI_UPPER_UP) != 0, lower_up = (T.tflags & TRI_LOWER_UP) != 0;
-  // part order = triparts[0], triparts[1] (inl:1557-1560); the upper part is triparts[vo]
-  for (int part = 0; part < 2; part++)
-  {
-    const bool is_upper = (part == 0) != upper_up;
-    const int32_t lo = T.lo[is_upper ? 0 : 1], hi = T.hi[is_upper ? 0 : 1];
-    const bool up = is_upper ? upper_up : lower_up;
-    for (int32_t k = 0; k < hi - lo; k++)
-    {
-      const int32_t cy = up ? (hi - 1 - k) : (lo + k);
-      const uint32_t Y = static_cast<uint32_t>(sext11(cy)) & (VRAM_H - 1);
-      TriRow row;
-      if (!tri_row(s, Y, row) || row.cy != cy)
-        continue;
-      // groups are counted from the clipped span start (inl:1262-1268)
-      for (int32_t gx = row.x_lo; gx < row.x_hi; gx += 32)
-      {
-        const int32_t px = gx + static_cast<int32_t>(lane);
-        const bool active = px < row.x_hi;
-        uint32_t r, g, b, u, v;
-        tri_attrs(s, row, px, r, g, b, u, v);
-        batch(gx, Y, active, r, g, b, u, v);
-      }
-    }
-  }
+  };
+
+  walk(CHECK);
+  if (!__syncthreads_or(conflict_seen ? 1 : 0))
+    walk(PARALLEL);
+  else if (warp == 0)
+    walk(ORDERED);
 }
 
 // CopyVRAM whose source and destination alias: wrap split in the reference's order, rows sequential, each row
@@ -976,12 +1015,69 @@ __global__ void __launch_bounds__(SERIAL_THREADS) serial_kernel(const WaveItem* 
   if (s.op == OP_NOP)
     return;
   if (it.kind == EPOCH_SELF_SAMPLING)
-    serial_self_sampling(s, vram, cluts);
+    serial_self_sampling<SERIAL_THREADS>(s, vram, cluts);
   else if (it.kind == EPOCH_COPY_OVERLAP)
     serial_copy<SERIAL_THREADS>(s, vram);
   else
     serial_upload_masked<SERIAL_THREADS>(s, vram, payload, row_count);
 }
+
+// Binning step of a region's warp: appends the commands of [next_cmd, it.cmd_end) that can touch tile (tx, ty) to the
+// shared list, in command order, until the epoch's commands are all in it or the list is (nearly) full.
+__device__ __forceinline__ void bin_fill(const WaveItem& it, uint16_t* list, uint32_t tx, uint32_t ty, const uint32_t* __restrict__ tile_cmds,
+                                         uint32_t& list_n, uint32_t& next_cmd, uint32_t lane)
+{
+  // fill the list until the epoch's commands are all in it, or it is (nearly) full
+#pragma unroll 1
+  while (next_cmd < it.cmd_end)
+  {
+    const uint32_t g = next_cmd >> 5, mine = g + lane;
+    const uint32_t c0 = mine << 5; // first command of this lane's group
+    uint32_t bits = 0;
+    if (c0 < it.cmd_end)
+    {
+      bits = __ldg(tile_cmds + (static_cast<size_t>(mine) * NUM_TILES + (ty * TILES_X + tx)));
+      if (c0 < next_cmd)
+        bits &= 0xFFFFFFFFu << (next_cmd - c0);
+      if (c0 + 32u > it.cmd_end)
+        bits &= (1u << (it.cmd_end - c0)) - 1u;
+    }
+    if (!__any_sync(0xFFFFFFFFu, bits != 0))
+    {
+      next_cmd = (g + 32u) << 5;
+      continue;
+    }
+    const uint32_t cnt = __popc(bits);
+    const uint32_t incl = warp_inclusive_scan(cnt, lane);
+    const bool fits = list_n + incl <= LIST_CAP;
+    const uint32_t n_fit = __popc(__ballot_sync(0xFFFFFFFFu, fits)); // a prefix of the lanes: incl is monotone
+    // (REDUX results are uniform for the compiler: the warp stays converged for the collectives of the raster code)
+    const uint32_t added = __reduce_add_sync(0xFFFFFFFFu, fits ? cnt : 0u);
+    const uint32_t rounds = __reduce_max_sync(0xFFFFFFFFu, fits ? cnt : 0u);
+    uint32_t pos = list_n + incl - cnt;
+    const uint32_t rel = c0 - it.cmd_begin; // (wraps for the first group: those bits are masked off)
+    for (uint32_t k = 0; k < rounds; k++)
+    {
+      if (fits && bits)
+      {
+        const uint32_t c = static_cast<uint32_t>(__ffs(static_cast<int>(bits))) - 1u;
+        bits &= bits - 1u;
+        list[pos++] = static_cast<uint16_t>(rel + c);
+      }
+    }
+    list_n += added;
+    next_cmd = max(next_cmd, (g + n_fit) << 5);
+    if (n_fit != 32u || list_n + 32u > LIST_CAP)
+      break;
+  }
+}
+
+// What a warp can do for its next region before the barrier that ends the current epoch opens: bin the region (the
+// bins and the setup records do not change while the kernel runs) and request the first command's setup record.
+struct PreBin
+{
+  uint32_t list_n, next_cmd;
+};
 
 // One warp runs one epoch of one instance on its region: bins the epoch's primitives (submission order), stages the
 // region in shared memory on the first hit, rasterises, writes it back.
@@ -989,7 +1085,7 @@ template<uint32_t RH, bool kCoh>
 __device__ __forceinline__ void process_epoch_region(const WaveItem& it, RasterShared<RH>& sh, uint32_t tx, uint32_t ty, uint32_t ry0,
                                                      const PrimSetup* __restrict__ setups, const uint32_t* __restrict__ tile_cmds,
                                                      uint16_t* vram, const uint16_t* cluts, const uint16_t* __restrict__ payload,
-                                                     uint32_t lane)
+                                                     uint32_t lane, const PreBin* pre = nullptr, uint32_t* clut_key_io = nullptr)
 {
   const uint32_t rx0 = tx * TILE_W;
   uint32_t* gword = reinterpret_cast<uint32_t*>(vram + ry0 * VRAM_W + rx0) + lane; // this lane's word of region row 0
@@ -998,9 +1094,12 @@ __device__ __forceinline__ void process_epoch_region(const WaveItem& it, RasterS
   // (1024 commands), one load per lane; the set bits of the lanes expand into the list in command order, as many
   // lanes at a time as the list has room for.  All that survives a raster pass is next_cmd (uniform).
   bool loaded = false;
-  uint32_t clut_key = 0;
-  uint32_t list_n = 0;
-  uint32_t next_cmd = it.cmd_begin; // first command of the epoch that is not in a list yet
+  uint32_t clut_key = clut_key_io ? *clut_key_io : 0u; // (a caller that knows the palette slots did not change keeps the staged palette)
+  uint32_t list_n = pre ? pre->list_n : 0u;
+  uint32_t next_cmd = pre ? pre->next_cmd : it.cmd_begin; // first command of the epoch that is not in a list yet
+  bool first_requested = pre != nullptr; // pre-binned: the list's first setup record is already on its way to stage[0]
+  if (pre && list_n == 0)
+    return; // pre-binned and nothing of the epoch touches the region
   if (kCoh)
   {
     // The kernels that stay resident over many short epochs are bound by the chain of dependent round trips per tile
@@ -1015,49 +1114,7 @@ __device__ __forceinline__ void process_epoch_region(const WaveItem& it, RasterS
 #pragma unroll 1
   for (;;)
   {
-    // fill the list until the epoch's commands are all in it, or it is (nearly) full
-#pragma unroll 1
-    while (next_cmd < it.cmd_end)
-    {
-      const uint32_t g = next_cmd >> 5, mine = g + lane;
-      const uint32_t c0 = mine << 5; // first command of this lane's group
-      uint32_t bits = 0;
-      if (c0 < it.cmd_end)
-      {
-        bits = __ldg(tile_cmds + (static_cast<size_t>(mine) * NUM_TILES + (ty * TILES_X + tx)));
-        if (c0 < next_cmd)
-          bits &= 0xFFFFFFFFu << (next_cmd - c0);
-        if (c0 + 32u > it.cmd_end)
-          bits &= (1u << (it.cmd_end - c0)) - 1u;
-      }
-      if (!__any_sync(0xFFFFFFFFu, bits != 0))
-      {
-        next_cmd = (g + 32u) << 5;
-        continue;
-      }
-      const uint32_t cnt = __popc(bits);
-      const uint32_t incl = warp_inclusive_scan(cnt, lane);
-      const bool fits = list_n + incl <= LIST_CAP;
-      const uint32_t n_fit = __popc(__ballot_sync(0xFFFFFFFFu, fits)); // a prefix of the lanes: incl is monotone
-      // (REDUX results are uniform for the compiler: the warp stays converged for the collectives of the raster code)
-      const uint32_t added = __reduce_add_sync(0xFFFFFFFFu, fits ? cnt : 0u);
-      const uint32_t rounds = __reduce_max_sync(0xFFFFFFFFu, fits ? cnt : 0u);
-      uint32_t pos = list_n + incl - cnt;
-      const uint32_t rel = c0 - it.cmd_begin; // (wraps for the first group: those bits are masked off)
-      for (uint32_t k = 0; k < rounds; k++)
-      {
-        if (fits && bits)
-        {
-          const uint32_t c = static_cast<uint32_t>(__ffs(static_cast<int>(bits))) - 1u;
-          bits &= bits - 1u;
-          sh.list[pos++] = static_cast<uint16_t>(rel + c);
-        }
-      }
-      list_n += added;
-      next_cmd = max(next_cmd, (g + n_fit) << 5);
-      if (n_fit != 32u || list_n + 32u > LIST_CAP)
-        break;
-    }
+    bin_fill(it, sh.list, tx, ty, tile_cmds, list_n, next_cmd, lane);
     if (list_n == 0)
       break;
     __syncwarp();
@@ -1066,9 +1123,13 @@ __device__ __forceinline__ void process_epoch_region(const WaveItem& it, RasterS
     // The 240-byte setup records travel global -> shared with 16-byte asynchronous copies (lanes 0-14), the next
     // primitive's while the current one is rasterised: no register holds a record in flight.
     const uint4* const setup_vecs = reinterpret_cast<const uint4*>(setups + it.cmd_begin);
-    if (lane < SETUP_VECS)
-      cp_async16(reinterpret_cast<uint4*>(sh.stage[0]) + lane, setup_vecs + static_cast<size_t>(sh.list[0]) * SETUP_VECS + lane);
-    cp_async_commit();
+    if (!first_requested)
+    {
+      if (lane < SETUP_VECS)
+        cp_async16(reinterpret_cast<uint4*>(sh.stage[0]) + lane, setup_vecs + static_cast<size_t>(sh.list[0]) * SETUP_VECS + lane);
+      cp_async_commit();
+    }
+    first_requested = false;
     if (!loaded)
     {
       // A FillVRAM (not interlaced) or an unmasked upload that covers the whole region overwrites every pixel of it:
@@ -1123,6 +1184,28 @@ __device__ __forceinline__ void process_epoch_region(const WaveItem& it, RasterS
     for (uint32_t r = 0; r < RH; r++)
       gword[r * (VRAM_W / 2)] = sh.region[r * REGION_PITCH + lane];
   }
+  if (clut_key_io)
+    *clut_key_io = clut_key;
+}
+
+// The binning half of process_epoch_region, run ahead of time (see PreBin).
+template<uint32_t RH>
+__device__ __forceinline__ PreBin prebin_region(const WaveItem& it, RasterShared<RH>& sh, uint32_t tx, uint32_t ty,
+                                                const PrimSetup* __restrict__ setups, const uint32_t* __restrict__ tile_cmds, uint32_t lane)
+{
+  PreBin pb;
+  pb.list_n = 0;
+  pb.next_cmd = it.cmd_begin;
+  bin_fill(it, sh.list, tx, ty, tile_cmds, pb.list_n, pb.next_cmd, lane);
+  if (pb.list_n != 0)
+  {
+    __syncwarp();
+    const uint4* const setup_vecs = reinterpret_cast<const uint4*>(setups + it.cmd_begin);
+    if (lane < SETUP_VECS)
+      cp_async16(reinterpret_cast<uint4*>(sh.stage[0]) + lane, setup_vecs + static_cast<size_t>(sh.list[0]) * SETUP_VECS + lane);
+    cp_async_commit();
+  }
+  return pb;
 }
 
 // One warp per (instance, tile).  No block-level barrier anywhere: the hardware CTA scheduler balances tiles.
@@ -1313,7 +1396,7 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 7) raster_persistent_kernel(
         if (s.op != OP_NOP)
         {
           if (it.kind == EPOCH_SELF_SAMPLING)
-            serial_self_sampling(s, vram, cluts);
+            serial_self_sampling<PERSIST_THREADS>(s, vram, cluts);
           else if (it.kind == EPOCH_COPY_OVERLAP)
             serial_copy<PERSIST_THREADS>(s, vram);
           else
@@ -1342,6 +1425,7 @@ struct InstanceShared
   alignas(16) uint32_t stage[SETUP_WORDS];
   Epoch epochs[INST_EPOCH_WINDOW];
   uint32_t tile_sets[INST_EPOCH_WINDOW][8];
+  uint32_t tile_total[INST_EPOCH_WINDOW]; // tiles in each set (cluster mode)
   uint32_t next_tile[2];
 };
 
@@ -1480,7 +1564,7 @@ __global__ void __launch_bounds__(32 * WARPS, WARPS == 32 ? 1 : (32 / WARPS)) ra
         if (s.op != OP_NOP)
         {
           if (it.kind == EPOCH_SELF_SAMPLING)
-            serial_self_sampling(s, vram, cluts);
+            serial_self_sampling<NT>(s, vram, cluts);
           else if (it.kind == EPOCH_COPY_OVERLAP)
             serial_copy<NT>(s, vram);
           else
@@ -1491,6 +1575,271 @@ __global__ void __launch_bounds__(32 * WARPS, WARPS == 32 ? 1 : (32 / WARPS)) ra
     else if (threadIdx.x == 0)
       cs.next_tile[(k + 1) & 1u] = 0;
     __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ cluster mode
+// A single VRAM (or a handful) whose stream is cut into thousands of short epochs: one CTA cannot win (one SM's issue
+// rate), and a grid-wide barrier per epoch costs more than the epoch's work (≈7 µs through L2 atomics).  Here one
+// thread-block CLUSTER owns an instance: 8 or 16 CTAs of 32 warps on neighbouring SMs, the hardware cluster barrier
+// (barrier.cluster, release / acquire at cluster scope, ≈0.2 µs) between epochs, and every touched tile cut into four
+// 64x8 strips that are dealt round-robin over the cluster's warps — strips of one tile land on different SMs, so the
+// per-epoch latency is that of the busiest strip.  CLUT snapshot ops are dealt over the CTAs; serial epochs run on CTA
+// 0 (1024 threads).  VRAM / CLUT-slot reads go to L2 (kCoh), like in the other kernels that outlive an epoch.
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_nctarank()
+{
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_arrive()
+{
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void cluster_wait()
+{
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void cluster_barrier()
+{
+  cluster_arrive();
+  cluster_wait();
+}
+
+// The ord-th tile (in tile order) of a 256-bit tile set held one word per lane in lanes 0-7 (`mine`; `before` / `cnt` =
+// exclusive prefix / popcount of the lane's word).
+__device__ __forceinline__ uint32_t nth_tile(uint32_t mine, uint32_t before, uint32_t cnt, uint32_t ord, uint32_t lane)
+{
+  const bool here = lane < 8 && ord >= before && ord < before + cnt;
+  const uint32_t src = static_cast<uint32_t>(__ffs(static_cast<int>(__ballot_sync(0xFFFFFFFFu, here)))) - 1u;
+  return __shfl_sync(0xFFFFFFFFu, lane * 32u + __fns(mine, 0, static_cast<int>(ord - before) + 1), src);
+}
+__device__ __forceinline__ uint32_t tile_set_prefix(uint32_t mine, uint32_t lane, uint32_t& before)
+{
+  const uint32_t cnt = __popc(mine);
+  before = cnt;
+#pragma unroll
+  for (uint32_t o = 1; o < 8; o <<= 1)
+  {
+    const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, before, o);
+    if (lane >= o)
+      before += t;
+  }
+  const uint32_t total = __shfl_sync(0xFFFFFFFFu, before, 7);
+  before -= cnt;
+  return total;
+}
+
+// CopyVRAM whose source and destination alias, by the whole cluster at once.  The reference copies row after row, each
+// row read completely before it is written (CopyVRAMImpl, inl:1833-1939): with d = (dy - sy) mod 512, row r reads what
+// row r - d wrote wherever the source pixel lies inside the destination rectangle (rows r + 512 - d come later: they
+// only overwrite what was already read).  A destination pixel is written at most once, so "was it written" is a
+// question about the ORIGINAL mask bit, and what a pixel ends up with is the original value found by following
+// (r, c) -> (r - d, c + sx - dx) while the step stays inside the rectangle and lands on a written pixel: a closed form
+// without the mask test, a short chain of mask-bit probes with it.  Every thread resolves up to four pixels from the
+// original VRAM, the cluster barrier separates the reads from the writes.  Returns false (before any barrier, the same
+// answer in every thread of the cluster) when the copy wraps around the columns or is too large for one pass.
+template<int NT>
+__device__ __forceinline__ bool cluster_copy_fast(const PrimSetup& s, uint16_t* vram, uint32_t rank, uint32_t n_ctas)
+{
+  const uint32_t mand = (s.flags0 & F_CHECK_MASK) ? 0x8000u : 0u, mor = (s.flags0 & F_SET_MASK) ? 0x8000u : 0u;
+  const uint32_t sx = s.copy.sx, sy = s.copy.sy, dx = s.copy.dx, dy = s.copy.dy, w = s.copy.w, h = s.copy.h;
+  constexpr uint32_t PER_THREAD = 4;
+  const uint32_t total = w * h, n_threads = NT * n_ctas;
+  if (sx + w > VRAM_W || dx + w > VRAM_W || h > VRAM_H || total > PER_THREAD * n_threads)
+    return false;
+  const uint32_t d = (dy - sy) & (VRAM_H - 1);
+  const int32_t delta = static_cast<int32_t>(sx) - static_cast<int32_t>(dx);
+  uint32_t val[PER_THREAD], at[PER_THREAD];
+#pragma unroll
+  for (uint32_t k = 0; k < PER_THREAD; k++)
+  {
+    const uint32_t i = k * n_threads + rank * NT + threadIdx.x;
+    val[k] = 0;
+    at[k] = 0;
+    if (i < total)
+    {
+      const uint32_t r = i / w, c = i - r * w;
+      at[k] = ((dy + r) & (VRAM_H - 1)) * VRAM_W + dx + c;
+      if ((__ldcg(vram + at[k]) & mand) == 0)
+      {
+        uint32_t rc = r;
+        int32_t cc = static_cast<int32_t>(c);
+        if (d != 0 && !mand)
+        {
+          uint32_t n = rc / d;
+          if (delta > 0)
+            n = min(n, (w - 1u - c) / static_cast<uint32_t>(delta));
+          else if (delta < 0)
+            n = min(n, c / static_cast<uint32_t>(-delta));
+          rc -= n * d;
+          cc += static_cast<int32_t>(n) * delta;
+        }
+        else if (d != 0)
+        {
+          while (rc >= d)
+          {
+            const int32_t cn = cc + delta;
+            if (cn < 0 || cn >= static_cast<int32_t>(w))
+              break;
+            if (__ldcg(vram + ((dy + rc - d) & (VRAM_H - 1)) * VRAM_W + dx + static_cast<uint32_t>(cn)) & 0x8000u)
+              break; // masked: row rc - d left it alone, the source pixel still holds its original value
+            rc -= d;
+            cc = cn;
+          }
+        }
+        val[k] = __ldcg(vram + ((sy + rc) & (VRAM_H - 1)) * VRAM_W + sx + static_cast<uint32_t>(cc)) | mor | 0x10000u;
+      }
+    }
+  }
+  cluster_barrier();
+#pragma unroll
+  for (uint32_t k = 0; k < PER_THREAD; k++)
+    if (val[k] & 0x10000u)
+      vram[at[k]] = static_cast<uint16_t>(val[k]);
+  return true;
+}
+
+// RH = rows per strip (8 or 4: 4 or 8 strips per tile; a multiple of 4 keeps the dither phase of the word loop)
+template<uint32_t RH, uint32_t CLUSTER_WARPS>
+__global__ void __launch_bounds__(32 * CLUSTER_WARPS, 1) raster_cluster_kernel(
+  const InstWork* __restrict__ work, const Epoch* __restrict__ epochs, const uint32_t* __restrict__ tile_sets,
+  const PrimSetup* __restrict__ setups, const uint32_t* __restrict__ tile_cmds, const ClutOp* __restrict__ clut_ops, uint16_t* vram_pool,
+  uint16_t* clut_pool, const uint16_t* __restrict__ payload, uint32_t clut_slots, uint32_t debug_skip)
+{
+  extern __shared__ __align__(16) unsigned char dyn_smem[];
+  RasterShared<RH>* sh_all = reinterpret_cast<RasterShared<RH>*>(dyn_smem);
+  InstanceShared& cs = *reinterpret_cast<InstanceShared*>(dyn_smem + sizeof(RasterShared<RH>) * CLUSTER_WARPS);
+  constexpr uint32_t NT = 32 * CLUSTER_WARPS;
+  constexpr uint32_t CLUSTER_STRIPS = TILE_H / RH;
+  const uint32_t n_ctas = cluster_nctarank(), rank = cluster_ctarank();
+  const InstWork w = work[blockIdx.x / n_ctas];
+  uint16_t* vram = vram_pool + static_cast<size_t>(w.instance) * VRAM_PIXELS;
+  uint16_t* cluts = clut_pool + static_cast<size_t>(w.instance) * clut_slots * CLUT_ENTRIES;
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+  const uint32_t gw = warp * n_ctas + rank, n_gw = CLUSTER_WARPS * n_ctas; // consecutive strips -> different SMs
+  uint32_t clut_key = 0; // the palette this warp has staged; survives epochs that load no CLUT snapshot
+  PreBin pb;
+  bool have_pre = false;
+
+  auto epoch_item = [&](const Epoch& ep) {
+    WaveItem it;
+    it.instance = w.instance;
+    it.cmd_begin = w.cmd_base + ep.cmd_begin;
+    it.cmd_end = w.cmd_base + ep.cmd_end;
+    it.kind = ep.kind;
+    it.clut_begin = w.clut_base + ep.clut_begin;
+    it.clut_end = w.clut_base + ep.clut_end;
+    return it;
+  };
+
+  for (uint32_t k = 0; k < w.n_epochs; k++)
+  {
+    const uint32_t slot = k % INST_EPOCH_WINDOW;
+    if (slot == 0)
+    {
+      // every CTA keeps its own copy of the next window of epoch descriptors and tile sets (immutable inputs)
+      const uint32_t n = min(INST_EPOCH_WINDOW, w.n_epochs - k);
+      const uint32_t* src = reinterpret_cast<const uint32_t*>(epochs + w.epoch_first + k);
+      for (uint32_t i = threadIdx.x; i < n * (sizeof(Epoch) / 4); i += NT)
+        reinterpret_cast<uint32_t*>(cs.epochs)[i] = __ldg(src + i);
+      for (uint32_t i = threadIdx.x; i < n * 8; i += NT)
+        (&cs.tile_sets[0][0])[i] = __ldg(tile_sets + static_cast<size_t>(w.epoch_first + k) * 8 + i);
+      __syncthreads();
+      for (uint32_t i = threadIdx.x; i < n; i += NT)
+      {
+        uint32_t c = 0;
+#pragma unroll
+        for (uint32_t q = 0; q < 8; q++)
+          c += __popc(cs.tile_sets[i][q]);
+        cs.tile_total[i] = c;
+      }
+      __syncthreads();
+    }
+    const WaveItem it = epoch_item(cs.epochs[slot]);
+    if (it.clut_end > it.clut_begin && !(debug_skip & 4u)) // uniform over the cluster
+    {
+      clut_key = 0;
+      for (uint32_t o = it.clut_begin + rank; o < it.clut_end; o += n_ctas)
+      {
+        const ClutOp op = clut_ops[o];
+        for (uint32_t t = threadIdx.x; t < (op.is8bit ? 256u : 16u); t += NT)
+          cluts[op.dst_slot * CLUT_ENTRIES + t] = __ldcg(vram + op.y * VRAM_W + ((op.x + t) & (VRAM_W - 1)));
+      }
+      cluster_barrier();
+    }
+    if (it.cmd_end > it.cmd_begin && !(debug_skip & (it.kind == EPOCH_TILED ? 2u : 1u))) // (debug_skip: timing experiments only)
+    {
+      if (it.kind == EPOCH_TILED)
+      {
+        // (most epochs of such a stream touch a few tiles: a warp without a strip goes straight to the barrier)
+        const uint32_t total = cs.tile_total[slot] * CLUSTER_STRIPS;
+        uint32_t mine = 0, before = 0;
+        if (gw < total)
+        {
+          mine = (lane < 8) ? cs.tile_sets[slot][lane] : 0u; // lane L: tiles 32 L .. 32 L + 31
+          tile_set_prefix(mine, lane, before);
+        }
+        for (uint32_t j = gw; j < total; j += n_gw)
+        {
+          const uint32_t tile = nth_tile(mine, before, __popc(mine), j / CLUSTER_STRIPS, lane), strip = j % CLUSTER_STRIPS;
+          const uint32_t tx = tile % TILES_X, ty = tile / TILES_X;
+          process_epoch_region<RH, true>(it, sh_all[warp], tx, ty, ty * TILE_H + strip * RH, setups, tile_cmds, vram, cluts, payload, lane,
+                                         (have_pre && j == gw) ? &pb : nullptr, &clut_key);
+          __syncwarp();
+        }
+      }
+      else if (rank == 0 || it.kind == EPOCH_COPY_OVERLAP)
+      {
+        if (threadIdx.x < SETUP_WORDS)
+          cs.stage[threadIdx.x] = reinterpret_cast<const uint32_t*>(setups + it.cmd_begin)[threadIdx.x];
+        __syncthreads();
+        const PrimSetup& s = *reinterpret_cast<const PrimSetup*>(cs.stage);
+        if (s.op != OP_NOP)
+        {
+          if (it.kind == EPOCH_SELF_SAMPLING)
+          {
+            if (!(debug_skip & 32u))
+              serial_self_sampling<NT>(s, vram, cluts);
+          }
+          else if (it.kind == EPOCH_COPY_OVERLAP)
+          {
+            // every CTA of the cluster is here with the same record
+            if (!(debug_skip & 8u) && ((debug_skip & 128u) || !cluster_copy_fast<NT>(s, vram, rank, n_ctas)) && rank == 0)
+              serial_copy<NT>(s, vram);
+          }
+          else if (!(debug_skip & 16u))
+            serial_upload_masked<NT>(s, vram, payload, cs.row_count);
+        }
+      }
+    }
+    // The barrier that ends the epoch, split: between arriving and waiting the warp bins its first strip of the next
+    // epoch and requests that strip's first setup record — two dependent trips to L2 that need nothing this epoch
+    // writes (bins and setup records are inputs of the kernel).
+    cluster_arrive();
+    have_pre = false;
+    if (slot + 1 < INST_EPOCH_WINDOW && k + 1 < w.n_epochs && !(debug_skip & 64u))
+    {
+      const Epoch& en = cs.epochs[slot + 1];
+      if (en.kind == EPOCH_TILED && en.cmd_end > en.cmd_begin && gw < cs.tile_total[slot + 1] * CLUSTER_STRIPS)
+      {
+        const uint32_t mine = (lane < 8) ? cs.tile_sets[slot + 1][lane] : 0u;
+        uint32_t before;
+        tile_set_prefix(mine, lane, before);
+        {
+          const uint32_t tile = nth_tile(mine, before, __popc(mine), gw / CLUSTER_STRIPS, lane);
+          pb = prebin_region<RH>(epoch_item(en), sh_all[warp], tile % TILES_X, tile / TILES_X, setups, tile_cmds, lane);
+          have_pre = true;
+        }
+      }
+    }
+    cluster_wait();
   }
 }
 
@@ -1686,6 +2035,16 @@ cudaError_t launch_persistent(const WaveItem* items, const void* waves, uint32_t
                                      dim3(PERSIST_THREADS), args, 0, st);
 }
 
+// Instances up to which a flush in instance mode runs as one cluster per instance (PSXGPU_CLUSTER_MAX; 0 = never).
+uint32_t cluster_max_instances()
+{
+  static const uint32_t v = []() {
+    const char* e = std::getenv("PSXGPU_CLUSTER_MAX");
+    return e ? static_cast<uint32_t>(std::atoi(e)) : 8u;
+  }();
+  return v;
+}
+
 cudaError_t launch_instances(const InstWork* work, uint32_t n_instances, const Epoch* epochs, uint32_t* tile_sets, const PrimSetup* setups,
                              const uint32_t* tile_cmds, const ClutOp* clut_ops, uint16_t* vram_pool, uint16_t* clut_pool,
                              const uint16_t* payload, uint32_t clut_slots, bool wide, cudaStream_t st)
@@ -1694,6 +2053,75 @@ cudaError_t launch_instances(const InstWork* work, uint32_t n_instances, const E
     return cudaSuccess;
   epoch_tiles_kernel<<<n_instances, 128, 0, st>>>(work, epochs, tile_cmds, tile_sets);
   cudaError_t e;
+  if (wide && n_instances <= cluster_max_instances())
+  {
+    // cluster mode: 16 CTAs per instance where the GPU can place such a cluster (non-portable size), else 8
+    static const int rh = []() {
+      const char* e = std::getenv("PSXGPU_CLUSTER_RH");
+      return (e && std::atoi(e) == 8) ? 8 : 4; // rows per strip (measured: 4 is 8 % faster than 8 on the hazard stress stream)
+    }();
+    static const int warps = []() {
+      const char* e = std::getenv("PSXGPU_CLUSTER_WARPS");
+      const int v = e ? std::atoi(e) : 16; // (measured on the hazard stress stream: 16 warps 16.8 ms, 32 warps 18.0, 8 warps 22.0)
+      return (v == 8 || v == 32) ? v : 16;
+    }();
+    using ClusterKernel = void (*)(const InstWork*, const Epoch*, const uint32_t*, const PrimSetup*, const uint32_t*, const ClutOp*, uint16_t*,
+                                   uint16_t*, const uint16_t*, uint32_t, uint32_t);
+    ClusterKernel const kernel = rh == 4 ? (warps == 8 ? raster_cluster_kernel<4, 8> : warps == 16 ? raster_cluster_kernel<4, 16> : raster_cluster_kernel<4, 32>)
+                                         : (warps == 8 ? raster_cluster_kernel<8, 8> : warps == 16 ? raster_cluster_kernel<8, 16> : raster_cluster_kernel<8, 32>);
+    const uint32_t CLUSTER_WARPS = static_cast<uint32_t>(warps);
+    const size_t smem = sizeof(RasterShared<8>) * CLUSTER_WARPS + sizeof(InstanceShared);
+    static const int cluster_size = [&]() {
+      if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess)
+        return 0;
+      const char* env = std::getenv("PSXGPU_CLUSTER_SIZE");
+      const int want = env ? std::atoi(env) : 16;
+      for (int cs = want; cs >= 2; cs >>= 1)
+      {
+        if (cs > 8 && cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess)
+        {
+          cudaGetLastError();
+          continue;
+        }
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(static_cast<unsigned>(cs));
+        cfg.blockDim = dim3(32 * CLUSTER_WARPS);
+        cfg.dynamicSmemBytes = smem;
+        cudaLaunchAttribute attr;
+        attr.id = cudaLaunchAttributeClusterDimension;
+        attr.val.clusterDim.x = static_cast<unsigned>(cs);
+        attr.val.clusterDim.y = attr.val.clusterDim.z = 1;
+        cfg.attrs = &attr;
+        cfg.numAttrs = 1;
+        int n = 0;
+        if (cudaOccupancyMaxActiveClusters(&n, kernel, &cfg) == cudaSuccess && n >= 1)
+          return cs;
+        cudaGetLastError();
+      }
+      return 0;
+    }();
+    if (cluster_size >= 2)
+    {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(n_instances * static_cast<unsigned>(cluster_size));
+      cfg.blockDim = dim3(32 * CLUSTER_WARPS);
+      cfg.dynamicSmemBytes = smem;
+      cfg.stream = st;
+      cudaLaunchAttribute attr;
+      attr.id = cudaLaunchAttributeClusterDimension;
+      attr.val.clusterDim.x = static_cast<unsigned>(cluster_size);
+      attr.val.clusterDim.y = attr.val.clusterDim.z = 1;
+      cfg.attrs = &attr;
+      cfg.numAttrs = 1;
+      const uint32_t* ts = tile_sets;
+      static const uint32_t debug_skip = []() {
+        const char* e = std::getenv("PSXGPU_DEBUG_SKIP"); // timing experiments: 1 = no serial epochs, 2 = no tiled epochs, 4 = no CLUT ops (results are wrong)
+        return e ? static_cast<uint32_t>(std::atoi(e)) : 0u;
+      }();
+      return cudaLaunchKernelEx(&cfg, kernel, work, epochs, ts, setups, tile_cmds, clut_ops, vram_pool, clut_pool, payload,
+                                clut_slots, debug_skip);
+    }
+  }
   if (wide)
   {
     constexpr uint32_t W = 32;
