@@ -31,6 +31,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cstdlib>
+#include <type_traits>
 
 namespace psx {
 
@@ -45,7 +46,7 @@ __global__ void __launch_bounds__(128) setup_kernel(const PackedCmd* __restrict_
 {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t lane = threadIdx.x & 31u;
-  uint32_t mask = 0;
+  uint32_t mask = 0, reject = 0, n_reject = 0;
   if (i < n)
   {
     // 64-byte record as four 128-bit loads
@@ -68,6 +69,54 @@ __global__ void __launch_bounds__(128) setup_kernel(const PackedCmd* __restrict_
       dst[k] = sw[k];
     bins[i].tilemask = b.tilemask;
     mask = b.tilemask;
+    // Exact binning for triangles: the mask above is the bounding box, and a triangle that spans 2 x 2 tiles or more
+    // usually misses a corner tile (13 % of the raster warps' visits found no pixel).  Per band of 32 rows the spans lie
+    // between the two edges evaluated at the band's first and last row of each part (the edges are linear inside a
+    // part, the same 32.32 values the raster warps evaluate), cut to the drawing area: tile columns outside that hull
+    // cannot hold a pixel.  Up to four such tiles per command are remembered and their bits cleared below.
+    if (s.op == OP_TRIANGLE && !(s.desc.path & LP_COMPLEX))
+    {
+      const uint32_t cols = mask & 0xFFFFu, rows = mask >> 16;
+      const auto& T = s.tri;
+      // (only where VRAM row == triangle row: a drawing area that reaches past row 511 makes the rows wrap)
+      const bool rows_plain = imin(T.lo[0], T.lo[1]) >= 0 && imax(T.hi[0], T.hi[1]) <= static_cast<int32_t>(VRAM_H);
+      if ((cols & (cols - 1u)) != 0 && (rows & (rows - 1u)) != 0 && rows_plain)
+      {
+        for (uint32_t ty = static_cast<uint32_t>(__ffs(static_cast<int>(rows))) - 1u; ty < TILES_Y && n_reject < 4u; ty++)
+        {
+          if (!((rows >> ty) & 1u))
+            continue;
+          int32_t h_lo = 0x7FFFFFFF, h_hi = static_cast<int32_t>(0x80000000u);
+#pragma unroll
+          for (int p = 0; p < 2; p++)
+          {
+            const int32_t ra = imax(T.lo[p], static_cast<int32_t>(ty * TILE_H)), rb = imin(T.hi[p], static_cast<int32_t>(ty * TILE_H + TILE_H)) - 1;
+            if (ra > rb)
+              continue;
+            const TriPart& P = T.part[p];
+#pragma unroll
+            for (int q = 0; q < 2; q++)
+            {
+              const uint64_t k = static_cast<uint64_t>(static_cast<uint32_t>((q ? rb : ra) - T.lo[p]));
+              h_lo = imin(h_lo, static_cast<int32_t>((P.l_start + k * P.l_step) >> 32));
+              h_hi = imax(h_hi, static_cast<int32_t>((P.r_start + k * P.r_step) >> 32));
+            }
+          }
+          h_lo = imax(h_lo, s.clip_l);
+          h_hi = imin(h_hi, s.clip_r + 1);
+          for (uint32_t tx = 0; tx < TILES_X && n_reject < 4u; tx++)
+          {
+            if (!((cols >> tx) & 1u))
+              continue;
+            if (h_hi <= h_lo || h_hi <= static_cast<int32_t>(tx * TILE_W) || h_lo >= static_cast<int32_t>(tx * TILE_W + TILE_W))
+            {
+              reject |= (ty * TILES_X + tx) << (8u * n_reject);
+              n_reject++;
+            }
+          }
+        }
+      }
+    }
   }
   if ((i & ~31u) >= n)
     return; // the whole warp is past the end
@@ -88,6 +137,11 @@ __global__ void __launch_bounds__(128) setup_kernel(const PackedCmd* __restrict_
     if ((y & 1u) == (lane >> 4))
       out[(y >> 1) * 32u] = v & colv;
   }
+  // the corner tiles found empty above: clear the command's bit (after the warp's stores, which __syncwarp orders)
+  __syncwarp();
+  uint32_t* const group_words = tile_cmds + static_cast<size_t>(i >> 5) * NUM_TILES;
+  for (uint32_t k = 0; k < n_reject; k++)
+    atomicAnd(group_words + ((reject >> (8u * k)) & 0xFFu), ~(1u << lane));
 }
 
 // ------------------------------------------------------------------------------------------------ CLUT snapshots
@@ -128,6 +182,7 @@ struct alignas(16) RasterShared
   uint32_t stage[2][SETUP_WORDS];         // the primitive being rasterised and the next one (cp.async double buffer)
   uint16_t clut[CLUT_ENTRIES];            // merged palette of the current primitive (entries 0-15 lo slot, 16-255 hi slot)
   uint16_t list[LIST_CAP];                // bin: primitive indices (relative to the epoch), submission order
+  unsigned long long mbar[4];             // transaction barriers of the bulk copies (throughput kernels): stage[0], stage[1], region
 };
 
 // 16-byte asynchronous copy global -> shared (LDGSTS): no register holds the data while it is in flight.
@@ -147,6 +202,70 @@ template<int kPending>
 __device__ __forceinline__ void cp_async_wait()
 {
   asm volatile("cp.async.wait_group %0;" ::"n"(kPending) : "memory");
+}
+
+// ---- bulk asynchronous copies (the TMA engine, non-tensor form: UBLKCP in SASS) + transaction barriers ----
+// One instruction moves a whole setup record (256 B) or a whole tile row (128 B) between global and shared memory; an
+// mbarrier counts the bytes in.  No register holds data in flight, no per-16-byte address arithmetic, no LDG/STS pair
+// per word.  Used by the throughput kernels (everything they read this way is constant while the kernel runs, and what
+// they write back is not read again before the kernel ends).
+__device__ __forceinline__ uint32_t smem_u32(const void* p)
+{
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(unsigned long long* b, uint32_t count)
+{
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* b, uint32_t bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* b, uint32_t parity)
+{
+  asm volatile("{\n"
+               ".reg .pred p;\n"
+               "MBAR_WAIT:\n"
+               "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+               "@p bra MBAR_DONE;\n"
+               "bra MBAR_WAIT;\n"
+               "MBAR_DONE:\n"
+               "}" ::"r"(smem_u32(b)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem, const void* gmem, uint32_t bytes, unsigned long long* b)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem)), "l"(gmem),
+               "r"(bytes), "r"(smem_u32(b))
+               : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* gmem, const void* smem, uint32_t bytes)
+{
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem), "r"(smem_u32(smem)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit()
+{
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_read() // the engine has read the shared memory of every committed bulk store
+{
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem()
+{
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+// once per warp, before the first bulk copy (lane 0 initialises, the warp synchronises)
+template<typename Shared>
+__device__ __forceinline__ void init_bulk_barriers(Shared& sh, uint32_t lane)
+{
+  if (lane == 0)
+  {
+    mbar_init(&sh.mbar[0], 1);
+    mbar_init(&sh.mbar[1], 1);
+    mbar_init(&sh.mbar[2], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
 }
 
 struct PixelCtx
@@ -329,147 +448,162 @@ __device__ __forceinline__ void raster_spans(const PrimSetup& s, const uint16_t*
                           (static_cast<uint32_t>(xs) << 16) | (static_cast<uint32_t>(xe) << 24);
   const uint32_t ub = (D.ubase + rx0) & 0xFFu; // rectangle: u of tile column 0 (mod 256: (ub + column) * 0x10001 cannot carry)
 
-  // The loop is software-pipelined by hand: the row lookup of the next batch (a REDUX, two POPC and two dependent
-  // shuffles) is issued right after this batch's texel loads, so that it runs while they are in flight.
-  // warp-uniform constants of the loop, read once (the compiler keeps them in uniform registers)
-  const uint32_t c_chk15 = D.chk15, c_set15 = D.set15, c_tex_shift = D.tex_shift, c_tex_bx2 = D.tex_bx2, c_trow = D.tex_rows;
-  const uint32_t c_sub_mask2 = D.sub_mask2, c_sub_shift = D.sub_shift, c_im = D.idx_mask, c_fr = D.fr, c_fg = D.fg, c_fb = D.fb;
-  const uint32_t c_du = T.ddx[3], c_dv = T.ddx[4];
-  uint32_t r = row_of_pixel(start, 0, rowmap, lane);
-  uint32_t pk = __shfl_sync(0xFFFFFFFFu, packed, r);
-#pragma unroll 1
-  for (uint32_t base = 0; base < total; base += 32)
-  {
-    const uint32_t w = pk_prmt<0x9910>(pk, 0) + base + lane; // sign-extended word offset + j = word of the tile row
-    // coverage of the two halves: column 2w >= xs, column 2w + 1 < xe (bit 15 of each half; the bias keeps the halves
-    // apart).  Lanes past the last word of the batch land behind their row's last word: not covered.
-    const uint32_t pos = w * 0x00020002u + 0x80018000u;
-    const uint32_t cov15 = (pos - pk_prmt<0x4242>(pk, 0)) & ~(pos - pk_prmt<0x4343>(pk, 0)) & 0x80008000u;
-    uint32_t* const wp = region + r * REGION_PITCH + w;
-    const uint32_t bg = *wp; // (lanes past the end read at most 31 words behind their row: still inside this warp's shared memory)
+  // The word loop exists in three instantiations — textured flat, textured Gouraud, untextured — chosen per visit: the
+  // flags fixed by the instantiation (kMask / kVal) fold at compile time, which removes their warp-uniform branches
+  // and the zero-initialisations behind them from every iteration; the other flags stay run-time (uniform) tests.
+  auto word_loop = [&](auto kmask_c, auto kval_c) {
+    constexpr uint32_t kMask = decltype(kmask_c)::value, kVal = decltype(kval_c)::value;
+    const uint32_t path = (D.path & ~kMask) | kVal;
+    // The loop is software-pipelined by hand: the row lookup of the next batch (a REDUX, two POPC and two dependent
+    // shuffles) is issued right after this batch's texel loads, so that it runs while they are in flight.
+    // warp-uniform constants of the loop, read once (the compiler keeps them in uniform registers)
+    const uint32_t c_chk15 = D.chk15, c_set15 = D.set15, c_tex_shift = D.tex_shift, c_tex_bx2 = D.tex_bx2, c_trow = D.tex_rows;
+    const uint32_t c_sub_mask2 = D.sub_mask2, c_sub_shift = D.sub_shift, c_im = D.idx_mask, c_fr = D.fr, c_fg = D.fg, c_fb = D.fb;
+    const uint32_t c_du = T.ddx[3], c_dv = T.ddx[4];
+    uint32_t r = row_of_pixel(start, 0, rowmap, lane);
+    uint32_t pk = __shfl_sync(0xFFFFFFFFu, packed, r);
+  #pragma unroll 1
+    for (uint32_t base = 0; base < total; base += 32)
+    {
+      const uint32_t w = pk_prmt<0x9910>(pk, 0) + base + lane; // sign-extended word offset + j = word of the tile row
+      // coverage of the two halves: column 2w >= xs, column 2w + 1 < xe (bit 15 of each half; the bias keeps the halves
+      // apart).  Lanes past the last word of the batch land behind their row's last word: not covered.
+      const uint32_t pos = w * 0x00020002u + 0x80018000u;
+      const uint32_t cov15 = (pos - pk_prmt<0x4242>(pk, 0)) & ~(pos - pk_prmt<0x4343>(pk, 0)) & 0x80008000u;
+      uint32_t* const wp = region + r * REGION_PITCH + w;
+      const uint32_t bg = *wp; // (lanes past the end read at most 31 words behind their row: still inside this warp's shared memory)
 
-    uint32_t d16 = 0;
-    if (path & LP_DITHER)
-    {
-      // pair_dither_entry in closed form: rows 2, 3 are rows 0, 1 with the column pairs swapped
-      d16 = 0x0000FFC0u + (r & 1u) * 0xFFDF0060u + ((w ^ (r >> 1)) & 1u) * 0x00100010u;
-    }
+      uint32_t d16 = 0;
+      if (path & LP_DITHER)
+      {
+        // pair_dither_entry in closed form: rows 2, 3 are rows 0, 1 with the column pairs swapped
+        d16 = 0x0000FFC0u + (r & 1u) * 0xFFDF0060u + ((w ^ (r >> 1)) & 1u) * 0x00100010u;
+      }
 
-    uint32_t t0 = 0, t1 = 0, U = 0;
-    if (path & LP_TEXTURED)
-    {
-      uint32_t V;
-      if (path & LP_TRI)
+      uint32_t t0 = 0, t1 = 0, U = 0;
+      if (path & LP_TEXTURED)
       {
-        const uint32_t du = c_du, dv = c_dv;
-        const uint32_t u0 = __shfl_sync(0xFFFFFFFFu, rb_u, r) + du * (2u * w);
-        const uint32_t v0 = __shfl_sync(0xFFFFFFFFu, rb_v, r) + dv * (2u * w);
-        U = __byte_perm(u0, u0 + du, 0x7733); // top bytes; the odd bytes are cleared by the masks below
-        V = __byte_perm(v0, v0 + dv, 0x7733);
-      }
-      else
-      {
-        U = (ub + 2u * w) * 0x00010001u + 0x00010000u;
-        V = __shfl_sync(0xFFFFFFFFu, rb_v, r);
-      }
-      if (path & LP_WINDOW)
-      {
-        U = (U & D.and_x2) | D.or_x2;
-        V = (V & D.and_y2) | D.or_y2;
-      }
-      else
-      {
-        U &= 0x00FF00FFu;
-        V &= 0x00FF00FFu;
-      }
-      // psx_pixel.h:texel_addr on both pixels at once; page base row (0 or 256) + v never wraps
-      const uint32_t tx = ((U >> c_tex_shift) + c_tex_bx2) & 0x03FF03FFu;
-      const uint32_t trow = c_trow;
-      t0 = ld_ro<kCoh>(vram + (trow + ((V & 0xFFFFu) << 10) + (tx & 0xFFFFu)));
-      t1 = ld_ro<kCoh>(vram + (trow + ((V >> 16) << 10) + (tx >> 16)));
-    }
-    // per-pixel colours (before the row lookup moves on)
-    uint32_t ar = 0, ag = 0, ab = 0;
-    if (path & LP_GOURAUD)
-    {
-      ar = __shfl_sync(0xFFFFFFFFu, rb_r, r) + T.ddx[0] * (2u * w);
-      ag = __shfl_sync(0xFFFFFFFFu, rb_g, r) + T.ddx[1] * (2u * w);
-      ab = __shfl_sync(0xFFFFFFFFu, rb_b, r) + T.ddx[2] * (2u * w);
-    }
-    // next batch's row lookup, while the texel loads are in flight
-    if (base + 32 < total)
-    {
-      r = row_of_pixel(start, base + 32, rowmap, lane);
-      pk = __shfl_sync(0xFFFFFFFFu, packed, r);
-    }
-
-    uint32_t tex = 0, we15;
-    if (path & LP_TEXTURED)
-    {
-      if (path & LP_PALETTED)
-      {
-        const uint32_t sub = (U & c_sub_mask2) << c_sub_shift; // bit offset of the index in its word
-        const uint32_t im = c_im;
-        t0 = clut_smem[(t0 >> (sub & 0xFFFFu)) & im];
-        t1 = clut_smem[(t1 >> (sub >> 16)) & im];
-      }
-      tex = __byte_perm(t0, t1, 0x5410);
-      we15 = cov15 & (((tex & 0x7FFF7FFFu) + 0x7FFF7FFFu) | tex) & ~(bg & c_chk15); // pair_we_textured
-    }
-    else
-      we15 = cov15 & ~(bg & c_chk15);
-
-    uint32_t col15;
-    if (!(path & LP_MODULATED))
-      col15 = tex & 0x7FFF7FFFu;
-    else
-    {
-      uint32_t pr, pg, pb;
-      if (path & LP_GOURAUD)
-      {
-        const uint32_t dr = T.ddx[0], dg = T.ddx[1], db = T.ddx[2];
-        if (path & LP_TEXTURED)
+        uint32_t V;
+        if (path & LP_TRI)
         {
-          const uint32_t cm = D.cmask;
-          const uint32_t tr = tex & 0x001F001Fu, tg = (tex >> 5) & 0x001F001Fu, tb = (tex >> 10) & 0x001F001Fu;
-          pr = (tr & 0xFFFFu) * ((ar >> 24) & cm) + (tr & 0xFFFF0000u) * (((ar + dr) >> 24) & cm);
-          pg = (tg & 0xFFFFu) * ((ag >> 24) & cm) + (tg & 0xFFFF0000u) * (((ag + dg) >> 24) & cm);
-          pb = (tb & 0xFFFFu) * ((ab >> 24) & cm) + (tb & 0xFFFF0000u) * (((ab + db) >> 24) & cm);
+          const uint32_t du = c_du, dv = c_dv;
+          const uint32_t u0 = __shfl_sync(0xFFFFFFFFu, rb_u, r) + du * (2u * w);
+          const uint32_t v0 = __shfl_sync(0xFFFFFFFFu, rb_v, r) + dv * (2u * w);
+          U = __byte_perm(u0, u0 + du, 0x7733); // top bytes; the odd bytes are cleared by the masks below
+          V = __byte_perm(v0, v0 + dv, 0x7733);
         }
         else
         {
-          pr = ((ar >> 24) << 4) + (((ar + dr) >> 24) << 20);
-          pg = ((ag >> 24) << 4) + (((ag + dg) >> 24) << 20);
-          pb = ((ab >> 24) << 4) + (((ab + db) >> 24) << 20);
+          U = (ub + 2u * w) * 0x00010001u + 0x00010000u;
+          V = __shfl_sync(0xFFFFFFFFu, rb_v, r);
         }
+        if (path & LP_WINDOW)
+        {
+          U = (U & D.and_x2) | D.or_x2;
+          V = (V & D.and_y2) | D.or_y2;
+        }
+        else
+        {
+          U &= 0x00FF00FFu;
+          V &= 0x00FF00FFu;
+        }
+        // psx_pixel.h:texel_addr on both pixels at once; page base row (0 or 256) + v never wraps
+        const uint32_t tx = ((U >> c_tex_shift) + c_tex_bx2) & 0x03FF03FFu;
+        const uint32_t trow = c_trow;
+        t0 = ld_ro<kCoh>(vram + (trow + ((V & 0xFFFFu) << 10) + (tx & 0xFFFFu)));
+        t1 = ld_ro<kCoh>(vram + (trow + ((V >> 16) << 10) + (tx >> 16)));
       }
-      else if (path & LP_TEXTURED)
+      // per-pixel colours (before the row lookup moves on)
+      uint32_t ar = 0, ag = 0, ab = 0;
+      if (path & LP_GOURAUD)
       {
-        pr = (tex & 0x001F001Fu) * c_fr;
-        pg = ((tex >> 5) & 0x001F001Fu) * c_fg;
-        pb = ((tex >> 10) & 0x001F001Fu) * c_fb;
+        ar = __shfl_sync(0xFFFFFFFFu, rb_r, r) + T.ddx[0] * (2u * w);
+        ag = __shfl_sync(0xFFFFFFFFu, rb_g, r) + T.ddx[1] * (2u * w);
+        ab = __shfl_sync(0xFFFFFFFFu, rb_b, r) + T.ddx[2] * (2u * w);
+      }
+      // next batch's row lookup, while the texel loads are in flight
+      if (base + 32 < total)
+      {
+        r = row_of_pixel(start, base + 32, rowmap, lane);
+        pk = __shfl_sync(0xFFFFFFFFu, packed, r);
+      }
+
+      uint32_t tex = 0, we15;
+      if (path & LP_TEXTURED)
+      {
+        if (path & LP_PALETTED)
+        {
+          const uint32_t sub = (U & c_sub_mask2) << c_sub_shift; // bit offset of the index in its word
+          const uint32_t im = c_im;
+          t0 = clut_smem[(t0 >> (sub & 0xFFFFu)) & im];
+          t1 = clut_smem[(t1 >> (sub >> 16)) & im];
+        }
+        tex = __byte_perm(t0, t1, 0x5410);
+        we15 = cov15 & (((tex & 0x7FFF7FFFu) + 0x7FFF7FFFu) | tex) & ~(bg & c_chk15); // pair_we_textured
       }
       else
+        we15 = cov15 & ~(bg & c_chk15);
+
+      uint32_t col15;
+      if (!(path & LP_MODULATED))
+        col15 = tex & 0x7FFF7FFFu;
+      else
       {
-        pr = c_fr;
-        pg = c_fg;
-        pb = c_fb;
+        uint32_t pr, pg, pb;
+        if (path & LP_GOURAUD)
+        {
+          const uint32_t dr = T.ddx[0], dg = T.ddx[1], db = T.ddx[2];
+          if (path & LP_TEXTURED)
+          {
+            const uint32_t cm = D.cmask;
+            const uint32_t tr = tex & 0x001F001Fu, tg = (tex >> 5) & 0x001F001Fu, tb = (tex >> 10) & 0x001F001Fu;
+            pr = (tr & 0xFFFFu) * ((ar >> 24) & cm) + (tr & 0xFFFF0000u) * (((ar + dr) >> 24) & cm);
+            pg = (tg & 0xFFFFu) * ((ag >> 24) & cm) + (tg & 0xFFFF0000u) * (((ag + dg) >> 24) & cm);
+            pb = (tb & 0xFFFFu) * ((ab >> 24) & cm) + (tb & 0xFFFF0000u) * (((ab + db) >> 24) & cm);
+          }
+          else
+          {
+            pr = ((ar >> 24) << 4) + (((ar + dr) >> 24) << 20);
+            pg = ((ag >> 24) << 4) + (((ag + dg) >> 24) << 20);
+            pb = ((ab >> 24) << 4) + (((ab + db) >> 24) << 20);
+          }
+        }
+        else if (path & LP_TEXTURED)
+        {
+          pr = (tex & 0x001F001Fu) * c_fr;
+          pg = ((tex >> 5) & 0x001F001Fu) * c_fg;
+          pb = ((tex >> 10) & 0x001F001Fu) * c_fb;
+        }
+        else
+        {
+          pr = c_fr;
+          pg = c_fg;
+          pb = c_fb;
+        }
+        col15 = pair_pack15(pr, pg, pb, d16);
       }
-      col15 = pair_pack15(pr, pg, pb, d16);
+      const uint32_t t15 = tex & 0x80008000u;
+      if (path & LP_TRANSP)
+      {
+        const uint32_t blended = pair_blend15((path >> LP_TMODE_SHIFT) & 3u, bg & 0x7FFF7FFFu, col15);
+        const uint32_t bm = (path & LP_TEXTURED) ? pk_expand15(t15) : 0xFFFFFFFFu;
+        col15 = (col15 & ~bm) | (blended & bm);
+      }
+      if (we15)
+      {
+        const uint32_t wm = pk_expand15(we15);
+        *wp = (bg & ~wm) | ((col15 | t15 | c_set15) & wm);
+      }
     }
-    const uint32_t t15 = tex & 0x80008000u;
-    if (path & LP_TRANSP)
-    {
-      const uint32_t blended = pair_blend15((path >> LP_TMODE_SHIFT) & 3u, bg & 0x7FFF7FFFu, col15);
-      const uint32_t bm = (path & LP_TEXTURED) ? pk_expand15(t15) : 0xFFFFFFFFu;
-      col15 = (col15 & ~bm) | (blended & bm);
-    }
-    if (we15)
-    {
-      const uint32_t wm = pk_expand15(we15);
-      *wp = (bg & ~wm) | ((col15 | t15 | c_set15) & wm);
-    }
-  }
+  };
+  using std::integral_constant;
+  if (!(D.path & LP_TEXTURED))
+    word_loop(integral_constant<uint32_t, LP_TEXTURED | LP_PALETTED | LP_WINDOW | LP_MODULATED>{}, integral_constant<uint32_t, LP_MODULATED>{});
+  else if (D.path & LP_GOURAUD)
+    word_loop(integral_constant<uint32_t, LP_TEXTURED | LP_GOURAUD | LP_MODULATED | LP_TRI>{},
+              integral_constant<uint32_t, LP_TEXTURED | LP_GOURAUD | LP_MODULATED | LP_TRI>{});
+  else
+    word_loop(integral_constant<uint32_t, LP_TEXTURED | LP_GOURAUD>{}, integral_constant<uint32_t, LP_TEXTURED>{});
 }
 
 // A warp applies one primitive to its region (rows ry0 .. ry0+RH-1, columns rx0 .. rx0+63), held in shared memory.
@@ -1085,8 +1219,13 @@ template<uint32_t RH, bool kCoh>
 __device__ __forceinline__ void process_epoch_region(const WaveItem& it, RasterShared<RH>& sh, uint32_t tx, uint32_t ty, uint32_t ry0,
                                                      const PrimSetup* __restrict__ setups, const uint32_t* __restrict__ tile_cmds,
                                                      uint16_t* vram, const uint16_t* cluts, const uint16_t* __restrict__ payload,
-                                                     uint32_t lane, const PreBin* pre = nullptr, uint32_t* clut_key_io = nullptr)
+                                                     uint32_t lane, const PreBin* pre = nullptr, uint32_t* clut_key_io = nullptr,
+                                                     uint32_t* mb_phase_io = nullptr)
 {
+  // kBulk (the throughput kernels): setup records and tile rows travel as bulk asynchronous copies counted in by
+  // transaction barriers; *mb_phase_io carries the barriers' phase bits from one region of the warp to the next.
+  // Otherwise (the kernels that stay resident across epochs and read what other CTAs wrote): 16-byte cp.async from L2.
+  constexpr bool kBulk = !kCoh;
   const uint32_t rx0 = tx * TILE_W;
   uint32_t* gword = reinterpret_cast<uint32_t*>(vram + ry0 * VRAM_W + rx0) + lane; // this lane's word of region row 0
 
@@ -1098,6 +1237,7 @@ __device__ __forceinline__ void process_epoch_region(const WaveItem& it, RasterS
   uint32_t list_n = pre ? pre->list_n : 0u;
   uint32_t next_cmd = pre ? pre->next_cmd : it.cmd_begin; // first command of the epoch that is not in a list yet
   bool first_requested = pre != nullptr; // pre-binned: the list's first setup record is already on its way to stage[0]
+  uint32_t mb_phase = (kBulk && mb_phase_io) ? *mb_phase_io : 0u;
   if (pre && list_n == 0)
     return; // pre-binned and nothing of the epoch touches the region
   if (kCoh)
@@ -1111,6 +1251,37 @@ __device__ __forceinline__ void process_epoch_region(const WaveItem& it, RasterS
       cp_async16_l2(sh.region + (c / (TILE_W / 8)) * REGION_PITCH + (c % (TILE_W / 8)) * 4, gtile + (c / (TILE_W / 8)) * VRAM_W + (c % (TILE_W / 8)) * 8);
     cp_async_commit();
   }
+  const PrimSetup* const epoch_setups = setups + it.cmd_begin;
+  // request the setup record of list entry `rel` into stage[buf]
+  auto request_record = [&](uint32_t buf, uint32_t rel) {
+    if (kBulk)
+    {
+      if (lane == 0)
+      {
+        mbar_expect_tx(&sh.mbar[buf], static_cast<uint32_t>(sizeof(PrimSetup)));
+        bulk_g2s(sh.stage[buf], epoch_setups + rel, static_cast<uint32_t>(sizeof(PrimSetup)), &sh.mbar[buf]);
+      }
+    }
+    else
+    {
+      if (lane < SETUP_VECS)
+        cp_async16(reinterpret_cast<uint4*>(sh.stage[buf]) + lane, reinterpret_cast<const uint4*>(epoch_setups + rel) + lane);
+      cp_async_commit();
+    }
+  };
+  // wait until stage[buf] holds its record (newer_in_flight: one younger request may stay outstanding)
+  auto await_record = [&](uint32_t buf, bool newer_in_flight) {
+    if (kBulk)
+    {
+      mbar_wait(&sh.mbar[buf], (mb_phase >> buf) & 1u);
+      mb_phase ^= 1u << buf;
+    }
+    else if (newer_in_flight)
+      cp_async_wait<1>();
+    else
+      cp_async_wait<0>();
+    __syncwarp();
+  };
 #pragma unroll 1
   for (;;)
   {
@@ -1120,22 +1291,23 @@ __device__ __forceinline__ void process_epoch_region(const WaveItem& it, RasterS
     __syncwarp();
 
     // ---- raster: walk the bin in order ----
-    // The 240-byte setup records travel global -> shared with 16-byte asynchronous copies (lanes 0-14), the next
-    // primitive's while the current one is rasterised: no register holds a record in flight.
-    const uint4* const setup_vecs = reinterpret_cast<const uint4*>(setups + it.cmd_begin);
+    // The 256-byte setup records travel global -> shared asynchronously, the next primitive's while the current one is
+    // rasterised: no register holds a record in flight.
     if (!first_requested)
-    {
-      if (lane < SETUP_VECS)
-        cp_async16(reinterpret_cast<uint4*>(sh.stage[0]) + lane, setup_vecs + static_cast<size_t>(sh.list[0]) * SETUP_VECS + lane);
-      cp_async_commit();
-    }
+      request_record(0, sh.list[0]);
     first_requested = false;
+    bool first_awaited = false;
     if (!loaded)
     {
+      if (kBulk)
+      {
+        bulk_wait_read(); // the previous region's write-back has left the buffer (it was reading it during the binning above)
+        __syncwarp();
+      }
       // A FillVRAM (not interlaced) or an unmasked upload that covers the whole region overwrites every pixel of it:
       // the region's old contents need not be read (a frame clear would otherwise read all of VRAM first).
-      cp_async_wait<0>();
-      __syncwarp();
+      await_record(0, false); // (kCoh: also covers the rows requested on entry)
+      first_awaited = true;
       const PrimSetup& first = *reinterpret_cast<const PrimSetup*>(sh.stage[0]);
       const uint32_t op = first.op;
       bool overwritten = false;
@@ -1146,11 +1318,16 @@ __device__ __forceinline__ void process_epoch_region(const WaveItem& it, RasterS
         overwritten = !interlaced && (((rx0 - first.fill.x) & (VRAM_W - 1)) + TILE_W <= first.fill.w) &&
                       (((ry0 - first.fill.y) & (VRAM_H - 1)) + RH <= first.fill.h);
       }
-      if (!kCoh && !overwritten) // (kCoh: the rows were requested on entry and the wait above covers them)
+      if (kBulk && !overwritten)
       {
-#pragma unroll 8
-        for (uint32_t r = 0; r < RH; r++)
-          sh.region[r * REGION_PITCH + lane] = __ldcs(gword + r * (VRAM_W / 2)); // read once: keep it out of L1
+        // lane r fetches row r of the region: one 128-byte bulk copy each, counted in by the region's barrier
+        if (lane == 0)
+          mbar_expect_tx(&sh.mbar[2], RH * TILE_W * 2u);
+        __syncwarp();
+        if (RH == 32 || lane < RH)
+          bulk_g2s(sh.region + lane * REGION_PITCH, vram + (ry0 + lane) * VRAM_W + rx0, TILE_W * 2u, &sh.mbar[2]);
+        mbar_wait(&sh.mbar[2], (mb_phase >> 2) & 1u);
+        mb_phase ^= 4u;
       }
       loaded = true;
     }
@@ -1158,15 +1335,9 @@ __device__ __forceinline__ void process_epoch_region(const WaveItem& it, RasterS
     for (uint32_t e = 0; e < list_n; e++)
     {
       if (e + 1 < list_n)
-      {
-        if (lane < SETUP_VECS)
-          cp_async16(reinterpret_cast<uint4*>(sh.stage[(e + 1) & 1u]) + lane, setup_vecs + static_cast<size_t>(sh.list[e + 1]) * SETUP_VECS + lane);
-        cp_async_commit();
-        cp_async_wait<1>(); // this primitive's record has landed, the next one's stays in flight
-      }
-      else
-        cp_async_wait<0>();
-      __syncwarp();
+        request_record((e + 1) & 1u, sh.list[e + 1]);
+      if (!(e == 0 && first_awaited))
+        await_record(e & 1u, e + 1 < list_n);
       raster_prim_on_region<RH, kCoh>(*reinterpret_cast<const PrimSetup*>(sh.stage[e & 1u]), sh.region, rx0, ry0, vram, cluts, payload, sh.clut,
                                       clut_key, lane);
       __syncwarp();
@@ -1180,12 +1351,26 @@ __device__ __forceinline__ void process_epoch_region(const WaveItem& it, RasterS
   }
   if (loaded)
   {
+    if (kBulk)
+    {
+      // the rows were written through the generic proxy: make them visible to the copy engine, then one bulk store per row
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (RH == 32 || lane < RH)
+        bulk_s2g(vram + (ry0 + lane) * VRAM_W + rx0, sh.region + lane * REGION_PITCH, TILE_W * 2u);
+      bulk_commit(); // (the region buffer may be reused once the engine has read it: bulk_wait_read() before the next region is staged, and before the CTA exits)
+    }
+    else
+    {
 #pragma unroll 8
-    for (uint32_t r = 0; r < RH; r++)
-      gword[r * (VRAM_W / 2)] = sh.region[r * REGION_PITCH + lane];
+      for (uint32_t r = 0; r < RH; r++)
+        gword[r * (VRAM_W / 2)] = sh.region[r * REGION_PITCH + lane];
+    }
   }
   if (clut_key_io)
     *clut_key_io = clut_key;
+  if (kBulk && mb_phase_io)
+    *mb_phase_io = mb_phase;
 }
 
 // The binning half of process_epoch_region, run ahead of time (see PreBin).
@@ -1232,8 +1417,11 @@ __global__ void __launch_bounds__(32 * PSX_RASTER_WARPS, PSX_RASTER_MIN_CTAS) ra
     return;
   uint16_t* vram = vram_pool + static_cast<size_t>(it.instance) * VRAM_PIXELS;
   const uint16_t* cluts = clut_pool + static_cast<size_t>(it.instance) * clut_slots * CLUT_ENTRIES;
+  uint32_t mb_phase = 0;
+  init_bulk_barriers(sh_all[threadIdx.x >> 5], threadIdx.x & 31u);
   process_epoch_region<TILE_H, false>(it, sh_all[threadIdx.x >> 5], tx, ty, ty * TILE_H, setups, tile_cmds, vram, cluts, payload,
-                                      threadIdx.x & 31u);
+                                      threadIdx.x & 31u, nullptr, nullptr, &mb_phase);
+  bulk_wait_read();
 }
 
 // Same work as raster_kernel, other scheduling: exactly as many one-warp CTAs as the GPU holds (SMs x 32), each pulling
@@ -1254,6 +1442,8 @@ __global__ void __launch_bounds__(32, PSX_RASTER_MIN_CTAS) raster_loop_kernel(
   __shared__ RasterShared<TILE_H> sh;
   const uint32_t lane = threadIdx.x;
   const uint32_t total = n_items * NUM_TILES;
+  uint32_t mb_phase = 0;
+  init_bulk_barriers(sh, lane);
   for (;;)
   {
     uint32_t first = 0, grab = 0;
@@ -1282,10 +1472,11 @@ __global__ void __launch_bounds__(32, PSX_RASTER_MIN_CTAS) raster_loop_kernel(
         continue;
       uint16_t* vram = vram_pool + static_cast<size_t>(it.instance) * VRAM_PIXELS;
       const uint16_t* cluts = clut_pool + static_cast<size_t>(it.instance) * clut_slots * CLUT_ENTRIES;
-      process_epoch_region<TILE_H, false>(it, sh, tx, ty, ty * TILE_H, setups, tile_cmds, vram, cluts, payload, lane);
+      process_epoch_region<TILE_H, false>(it, sh, tx, ty, ty * TILE_H, setups, tile_cmds, vram, cluts, payload, lane, nullptr, nullptr, &mb_phase);
       __syncwarp();
     }
   }
+  bulk_wait_read();
 }
 
 // Union of the tile masks of every epoch (one warp per wave item), stored in WaveItem::pad[0].
