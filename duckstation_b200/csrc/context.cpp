@@ -315,6 +315,19 @@ bool instance_mode_wanted(psxgpu_ctx* ctx, uint64_t total_epochs, uint32_t n_ins
 // setup + all waves of one chunk, on ctx->stream
 int run_chunk(psxgpu_ctx* ctx, psxgpu_ctx::Chunk& S)
 {
+#ifdef PSX_DEBUG_BOUNDS
+  {
+    // what the chunk's kernels may index (kernels.cu, PSX_CHECK): the allocations' extents, like a memory checker would
+    DebugLimits lim;
+    lim.n_cmds = S.n_cmds;
+    lim.n_payload = static_cast<uint32_t>(std::min<size_t>(S.d_payload.cap / 2, 0xFFFFFFFFu));
+    lim.n_clutops = static_cast<uint32_t>(S.d_clutops.cap / sizeof(ClutOp));
+    lim.n_items = S.wave_off.empty() ? 0u : S.wave_off.back();
+    lim.n_instances = ctx->n;
+    lim.clut_slots = ctx->clut_slots;
+    CK(launch_debug_limits(lim, ctx->stream), "debug limits");
+  }
+#endif
   CK(launch_setup(static_cast<const PackedCmd*>(S.d_cmds.p), static_cast<PrimSetup*>(S.d_setups.p),
                   static_cast<BinInfo*>(S.d_bins.p), static_cast<uint32_t*>(S.d_tilecmds.p), S.n_cmds, ctx->stream),
      "setup_kernel");

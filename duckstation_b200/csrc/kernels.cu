@@ -30,10 +30,41 @@
 
 #include <algorithm>
 #include <atomic>
+#include <cstdio>
 #include <cstdlib>
 #include <type_traits>
 
 namespace psx {
+
+// ------------------------------------------------------------------------------------------------ debug bounds build
+// compute-sanitizer is not available on the GPU pool, so a -DPSX_DEBUG_BOUNDS build carries its own checks: every index
+// into a bin list, the transposed tile bitmaps, the setup records, the upload payload, the CLUT slots, the wave items
+// and the shared tile, plus the grid barrier's generation, traps (`__trap()` -> the launch fails with an error the C
+// ABI reports) instead of reading or writing out of range.  The extents of the chunk's buffers reach the kernels
+// through g_dbg, written on the context's stream ahead of the chunk's launches (one context at a time in such a
+// build).  A normal build compiles all of it away.  profiles/r02_debug_bounds.log is the GPU suite run under it.
+#ifdef PSX_DEBUG_BOUNDS
+__device__ DebugLimits g_dbg;
+#define PSX_CHECK(cond)                                                                                                \
+  do                                                                                                                   \
+  {                                                                                                                    \
+    if (!(cond))                                                                                                       \
+    {                                                                                                                  \
+      printf("PSX_DEBUG_BOUNDS: %s failed at %s:%d (block %u thread %u)\n", #cond, __FILE__, __LINE__, blockIdx.x, threadIdx.x); \
+      __trap();                                                                                                        \
+    }                                                                                                                  \
+  } while (0)
+cudaError_t launch_debug_limits(const DebugLimits& lim, cudaStream_t st)
+{
+  return cudaMemcpyToSymbolAsync(g_dbg, &lim, sizeof(lim), 0, cudaMemcpyHostToDevice, st);
+}
+#else
+#define PSX_CHECK(cond) ((void)0)
+cudaError_t launch_debug_limits(const DebugLimits&, cudaStream_t)
+{
+  return cudaSuccess;
+}
+#endif
 
 // ------------------------------------------------------------------------------------------------ setup
 // Besides the PrimSetup records the kernel leaves two views of "which tiles can this command touch" (bounding box):
@@ -155,7 +186,9 @@ __global__ void __launch_bounds__(256) clut_kernel(const WaveItem* __restrict__ 
   const uint32_t t = threadIdx.x;
   for (uint32_t o = it.clut_begin; o < it.clut_end; o++)
   {
+    PSX_CHECK(o < g_dbg.n_clutops);
     const ClutOp op = ops[o];
+    PSX_CHECK(op.dst_slot < clut_slots && op.y < VRAM_H && it.instance < g_dbg.n_instances);
     if (op.is8bit || t < 16)
       cluts[op.dst_slot * CLUT_ENTRIES + t] = vram[op.y * VRAM_W + ((op.x + t) & (VRAM_W - 1))];
   }
@@ -510,6 +543,7 @@ __device__ __forceinline__ void raster_spans(const PrimSetup& s, const uint16_t*
         // psx_pixel.h:texel_addr on both pixels at once; page base row (0 or 256) + v never wraps
         const uint32_t tx = ((U >> c_tex_shift) + c_tex_bx2) & 0x03FF03FFu;
         const uint32_t trow = c_trow;
+        PSX_CHECK(trow + ((V & 0xFFFFu) << 10) + (tx & 0xFFFFu) < VRAM_PIXELS && trow + ((V >> 16) << 10) + (tx >> 16) < VRAM_PIXELS);
         t0 = ld_ro<kCoh>(vram + (trow + ((V & 0xFFFFu) << 10) + (tx & 0xFFFFu)));
         t1 = ld_ro<kCoh>(vram + (trow + ((V >> 16) << 10) + (tx >> 16)));
       }
@@ -535,6 +569,7 @@ __device__ __forceinline__ void raster_spans(const PrimSetup& s, const uint16_t*
         {
           const uint32_t sub = (U & c_sub_mask2) << c_sub_shift; // bit offset of the index in its word
           const uint32_t im = c_im;
+          PSX_CHECK(im < CLUT_ENTRIES);
           t0 = clut_smem[(t0 >> (sub & 0xFFFFu)) & im];
           t1 = clut_smem[(t1 >> (sub >> 16)) & im];
         }
@@ -591,7 +626,8 @@ __device__ __forceinline__ void raster_spans(const PrimSetup& s, const uint16_t*
       }
       if (we15)
       {
-        const uint32_t wm = pk_expand15(we15);
+PSX_CHECK(r < RH && w < TILE_W / 2);
+                const uint32_t wm = pk_expand15(we15);
         *wp = (bg & ~wm) | ((col15 | t15 | c_set15) & wm);
       }
     }
@@ -615,6 +651,7 @@ __device__ __forceinline__ void raster_prim_on_region(const PrimSetup& s, uint32
                                                       uint32_t lane)
 {
   const uint32_t op = s.op;
+  PSX_CHECK(op <= OP_NOP);
   if (op <= OP_RECT) // OP_TRIANGLE, OP_RECT
   {
     // paletted: make sure the merged palette is in shared memory (one coalesced 512-byte read when it changes)
@@ -623,6 +660,7 @@ __device__ __forceinline__ void raster_prim_on_region(const PrimSetup& s, uint32
     {
       clut_key = key;
       const uint32_t lo = key & 0xFFu, hi = (key >> 8) & 0xFFu, is8 = (key >> 16) & 1u;
+      PSX_CHECK(lo < g_dbg.clut_slots && hi < g_dbg.clut_slots);
       uint4* dst = reinterpret_cast<uint4*>(clut_smem);
       if (is8)
       {
@@ -775,6 +813,7 @@ __device__ __forceinline__ void raster_prim_on_region(const PrimSetup& s, uint32
 #pragma unroll 8
           for (uint32_t r = 0; r < RH; r++)
           {
+            PSX_CHECK(idx + 1 < g_dbg.n_payload);
             uint32_t word;
             if (idx & 1u) // (the same for every lane of the row)
               word = static_cast<uint32_t>(__ldg(payload + idx)) | (static_cast<uint32_t>(__ldg(payload + idx + 1)) << 16);
@@ -794,6 +833,7 @@ __device__ __forceinline__ void raster_prim_on_region(const PrimSetup& s, uint32
         const bool c0 = upload_covers(s, px0, Y, p0), c1 = upload_covers(s, px0 + 1, Y, p1);
         if (!(c0 || c1))
           continue;
+        PSX_CHECK((!c0 || p0 < g_dbg.n_payload) && (!c1 || p1 < g_dbg.n_payload));
         uint32_t word = region[r * REGION_PITCH + lane];
         if (c0)
           word = set_half(word, 0, transfer_write(s, static_cast<uint16_t>(word), __ldg(payload + p0)));
@@ -1122,6 +1162,7 @@ __device__ void serial_upload_masked(const PrimSetup& s, uint16_t* vram, const u
       const bool masked = in && (d & 0x8000u);
       const uint32_t bal = __ballot_sync(0xFFFFFFFFu, masked && c >= aw);
       const uint32_t before = __popc(bal & ((1u << lane) - 1u));
+      PSX_CHECK(!(in && !masked) || U.payload + r * w + c - (deficit + before) < g_dbg.n_payload);
       if (in && !masked)
         vram[a] = static_cast<uint16_t>(__ldg(payload + U.payload + r * w + c - (deficit + before)) | mor);
       deficit += __popc(bal);
@@ -1170,6 +1211,7 @@ __device__ __forceinline__ void bin_fill(const WaveItem& it, uint16_t* list, uin
     uint32_t bits = 0;
     if (c0 < it.cmd_end)
     {
+      PSX_CHECK(tx < TILES_X && ty < TILES_Y && mine <= (g_dbg.n_cmds + 31u) / 32u);
       bits = __ldg(tile_cmds + (static_cast<size_t>(mine) * NUM_TILES + (ty * TILES_X + tx)));
       if (c0 < next_cmd)
         bits &= 0xFFFFFFFFu << (next_cmd - c0);
@@ -1196,6 +1238,7 @@ __device__ __forceinline__ void bin_fill(const WaveItem& it, uint16_t* list, uin
       {
         const uint32_t c = static_cast<uint32_t>(__ffs(static_cast<int>(bits))) - 1u;
         bits &= bits - 1u;
+        PSX_CHECK(pos < LIST_CAP && rel + c < it.cmd_end - it.cmd_begin);
         list[pos++] = static_cast<uint16_t>(rel + c);
       }
     }
@@ -1226,6 +1269,8 @@ __device__ __forceinline__ void process_epoch_region(const WaveItem& it, RasterS
   // transaction barriers; *mb_phase_io carries the barriers' phase bits from one region of the warp to the next.
   // Otherwise (the kernels that stay resident across epochs and read what other CTAs wrote): 16-byte cp.async from L2.
   constexpr bool kBulk = !kCoh;
+  PSX_CHECK(it.cmd_begin <= it.cmd_end && it.cmd_end <= g_dbg.n_cmds && it.instance < g_dbg.n_instances);
+  PSX_CHECK(tx < TILES_X && ry0 + RH <= VRAM_H && (ry0 % RH) == 0);
   const uint32_t rx0 = tx * TILE_W;
   uint32_t* gword = reinterpret_cast<uint32_t*>(vram + ry0 * VRAM_W + rx0) + lane; // this lane's word of region row 0
 
@@ -1254,6 +1299,7 @@ __device__ __forceinline__ void process_epoch_region(const WaveItem& it, RasterS
   const PrimSetup* const epoch_setups = setups + it.cmd_begin;
   // request the setup record of list entry `rel` into stage[buf]
   auto request_record = [&](uint32_t buf, uint32_t rel) {
+    PSX_CHECK(buf < 2 && rel < it.cmd_end - it.cmd_begin);
     if (kBulk)
     {
       if (lane == 0)
@@ -1462,6 +1508,7 @@ __global__ void __launch_bounds__(32, PSX_RASTER_MIN_CTAS) raster_loop_kernel(
     const uint32_t last = min(first + grab, total);
     for (uint32_t id = first; id < last; id++)
     {
+      PSX_CHECK(id / NUM_TILES < n_items);
       const WaveItem it = items[id / NUM_TILES];
       if (it.kind != EPOCH_TILED || it.cmd_begin == it.cmd_end)
         continue;
@@ -1526,6 +1573,7 @@ __device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int
     while (*reinterpret_cast<volatile unsigned int*>(counter) < target)
     {
     }
+    PSX_CHECK(*reinterpret_cast<volatile unsigned int*>(counter) - target < n_ctas); // nobody is a whole generation ahead
     __threadfence();
   }
   __syncthreads();

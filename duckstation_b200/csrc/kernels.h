@@ -18,6 +18,13 @@ struct ScanoutParams
   uint32_t out_stride; // bytes
 };
 
+// -DPSX_DEBUG_BOUNDS builds: extents of the chunk whose kernels come next on the stream (kernels.cu, PSX_CHECK).
+struct DebugLimits
+{
+  uint32_t n_cmds, n_payload, n_clutops, n_items, n_instances, clut_slots;
+};
+cudaError_t launch_debug_limits(const DebugLimits& lim, cudaStream_t st);
+
 // tile_cmds: (n + 31) / 32 groups x NUM_TILES words, the transposed tile masks the raster kernels bin from.
 cudaError_t launch_setup(const PackedCmd* cmds, PrimSetup* setups, BinInfo* bins, uint32_t* tile_cmds, uint32_t n, cudaStream_t st);
 inline size_t tile_cmds_bytes(size_t n_cmds)

@@ -108,3 +108,23 @@ def test_boundary_subclass_compiles_against_the_reference_header():
     r = subprocess.run(["make", "-f", "Makefile.decoder", "boundary_check", "OUT=/tmp/_boundary_drift",
                         "CXX=g++ -DBOUNDARY_DRIFT"], cwd=d, capture_output=True, text=True)
     assert r.returncode != 0 and "override" in r.stderr
+
+
+def test_debug_bounds_build_compiles(tmp_path):
+    """The sanitizer substitute (-DPSX_DEBUG_BOUNDS: index checks that trap, kernels.cu PSX_CHECK) must keep compiling
+    and must put trap sites into the kernels; the normal build must have none."""
+    import shutil
+    import subprocess
+
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not found")
+    src = os.path.join(ROOT, "duckstation_b200", "csrc", "kernels.cu")
+    out = str(tmp_path / "kernels_dbg.cubin")
+    subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-DPSX_DEBUG_BOUNDS", "-cubin", "-o", out, src],
+                   check=True, capture_output=True)
+    sass = subprocess.run(["cuobjdump", "-sass", out], capture_output=True, text=True, check=True).stdout
+    assert sass.count("BPT.TRAP") > 50
+    normal = subprocess.run(["cuobjdump", "-sass", os.path.join(ROOT, "duckstation_b200", "libpsxgpu.so")], capture_output=True, text=True,
+                            check=True).stdout
+    assert normal.count("BPT.TRAP") == 0
