@@ -410,11 +410,25 @@ int run_chunk(psxgpu_ctx* ctx, psxgpu_ctx::Chunk& S)
       CK(cudaEventRecord(S.ev_raster[S.ev_raster_used++], ctx->stream), "event record");
     if (S.wave_has_tiled[k])
     {
-      CK(launch_raster(items + off, cnt, static_cast<const PrimSetup*>(S.d_setups.p), static_cast<const uint32_t*>(S.d_tilecmds.p),
-                       ctx->d_vram, ctx->d_clut, static_cast<const uint16_t*>(S.d_payload.p), ctx->clut_slots, ctx->stream,
-                       S.wave_tiled_cmds[k], ctx->d_barrier + 4),
-         "raster_kernel");
-      ctx->counters.kernel_launches += (cnt + 32767) / 32768;
+      // A wave of a pipelined (device-encoded) batch goes out in PSXGPU_WAVE_SPLIT pieces: the persistent raster CTAs of
+      // a piece all end together, and at that seam the next chunk's framing / encode kernels, which wait on a
+      // higher-priority stream, get onto the SMs instead of waiting for the whole wave.
+      static const uint32_t wave_split = []() {
+        const char* e = std::getenv("PSXGPU_WAVE_SPLIT");
+        const int v = e ? std::atoi(e) : 1;
+        return static_cast<uint32_t>(v < 1 ? 1 : (v > 8 ? 8 : v));
+      }();
+      const uint32_t pieces = (S.device_encoded && cnt >= 128u * wave_split) ? wave_split : 1u;
+      for (uint32_t pc = 0; pc < pieces; pc++)
+      {
+        const uint32_t lo = static_cast<uint32_t>(static_cast<uint64_t>(cnt) * pc / pieces);
+        const uint32_t hi = static_cast<uint32_t>(static_cast<uint64_t>(cnt) * (pc + 1) / pieces);
+        CK(launch_raster(items + off + lo, hi - lo, static_cast<const PrimSetup*>(S.d_setups.p), static_cast<const uint32_t*>(S.d_tilecmds.p),
+                         ctx->d_vram, ctx->d_clut, static_cast<const uint16_t*>(S.d_payload.p), ctx->clut_slots, ctx->stream,
+                         static_cast<uint32_t>(static_cast<uint64_t>(S.wave_tiled_cmds[k]) * (hi - lo) / cnt), ctx->d_barrier + 4),
+           "raster_kernel");
+        ctx->counters.kernel_launches += (hi - lo + 32767) / 32768;
+      }
     }
     if (S.wave_has_serial[k])
     {
@@ -1165,6 +1179,10 @@ int submit_batch_device(psxgpu_ctx* ctx, uint32_t first, uint32_t count, const v
     return status;
   };
   uint32_t chunk_index = 0;
+  static const bool taper = []() {
+    const char* e = std::getenv("PSXGPU_CHUNK_TAPER");
+    return !e || std::atoi(e) != 0;
+  }();
   const bool ramp = ctx->batch_chunk == 0 && count > 256; // automatic chunking: small first chunks fill the pipeline sooner
   for (uint32_t c0 = 0, cn = 0; c0 < count && status == PSXGPU_OK; c0 += cn, chunk_index++)
   {
@@ -1173,7 +1191,11 @@ int submit_batch_device(psxgpu_ctx* ctx, uint32_t first, uint32_t count, const v
       want = std::max<uint32_t>(64, per / 4);
     else if (ramp && chunk_index == 1)
       want = std::max<uint32_t>(64, per / 2);
+    else if (ramp && count - c0 <= per + per / 2 && taper)
+      want = std::max<uint32_t>(128, (count - c0) / 2); // ... and small last chunks shorten what is left to do after the last copy
     cn = std::min(want, count - c0);
+    if (ramp && count - c0 - cn < 64)
+      cn = count - c0; // (no crumbs)
     int rc = open_group(ctx);
     if (rc != PSXGPU_OK)
       return rc;

@@ -401,7 +401,7 @@ __device__ __forceinline__ uint32_t row_lane_map(uint32_t rows, uint32_t lane)
 // warp-uniform branch around a short block, and the constants those blocks use come ready-made from the staged record
 // (LoopDesc, written by setup_kernel): the loop keeps few registers live, so nothing is rematerialised per word.
 template<uint32_t RH, bool kCoh>
-__device__ __forceinline__ void raster_spans(const PrimSetup& s, const uint16_t* vram, const uint16_t* clut_smem, uint32_t* region,
+__device__ __forceinline__ void raster_spans(const PrimSetup& s, const uint16_t* vram, RasterShared<RH>& sh,
                                              uint32_t rx0, uint32_t ry0, uint32_t lane)
 {
   const LoopDesc& D = s.desc;
@@ -503,7 +503,7 @@ __device__ __forceinline__ void raster_spans(const PrimSetup& s, const uint16_t*
       // apart).  Lanes past the last word of the batch land behind their row's last word: not covered.
       const uint32_t pos = w * 0x00020002u + 0x80018000u;
       const uint32_t cov15 = (pos - pk_prmt<0x4242>(pk, 0)) & ~(pos - pk_prmt<0x4343>(pk, 0)) & 0x80008000u;
-      uint32_t* const wp = region + r * REGION_PITCH + w;
+      uint32_t* const wp = sh.region + r * REGION_PITCH + w;
       const uint32_t bg = *wp; // (lanes past the end read at most 31 words behind their row: still inside this warp's shared memory)
 
       uint32_t d16 = 0;
@@ -570,8 +570,8 @@ __device__ __forceinline__ void raster_spans(const PrimSetup& s, const uint16_t*
           const uint32_t sub = (U & c_sub_mask2) << c_sub_shift; // bit offset of the index in its word
           const uint32_t im = c_im;
           PSX_CHECK(im < CLUT_ENTRIES);
-          t0 = clut_smem[(t0 >> (sub & 0xFFFFu)) & im];
-          t1 = clut_smem[(t1 >> (sub >> 16)) & im];
+          t0 = sh.clut[(t0 >> (sub & 0xFFFFu)) & im];
+          t1 = sh.clut[(t1 >> (sub >> 16)) & im];
         }
         tex = __byte_perm(t0, t1, 0x5410);
         we15 = cov15 & (((tex & 0x7FFF7FFFu) + 0x7FFF7FFFu) | tex) & ~(bg & c_chk15); // pair_we_textured
@@ -645,9 +645,9 @@ PSX_CHECK(r < RH && w < TILE_W / 2);
 // A warp applies one primitive to its region (rows ry0 .. ry0+RH-1, columns rx0 .. rx0+63), held in shared memory.
 // clut_key: which palette (lo slot | hi slot << 8 | depth << 16) currently sits in clut_smem; reloaded on change.
 template<uint32_t RH, bool kCoh>
-__device__ __forceinline__ void raster_prim_on_region(const PrimSetup& s, uint32_t* __restrict__ region, uint32_t rx0, uint32_t ry0,
+__device__ __forceinline__ void raster_prim_on_region(const PrimSetup& s, RasterShared<RH>& sh, uint32_t rx0, uint32_t ry0,
                                                       const uint16_t* vram, const uint16_t* clut_pool_inst,
-                                                      const uint16_t* __restrict__ payload, uint16_t* clut_smem, uint32_t& clut_key,
+                                                      const uint16_t* __restrict__ payload, uint32_t& clut_key,
                                                       uint32_t lane)
 {
   const uint32_t op = s.op;
@@ -661,7 +661,7 @@ __device__ __forceinline__ void raster_prim_on_region(const PrimSetup& s, uint32
       clut_key = key;
       const uint32_t lo = key & 0xFFu, hi = (key >> 8) & 0xFFu, is8 = (key >> 16) & 1u;
       PSX_CHECK(lo < g_dbg.clut_slots && hi < g_dbg.clut_slots);
-      uint4* dst = reinterpret_cast<uint4*>(clut_smem);
+      uint4* dst = reinterpret_cast<uint4*>(sh.clut);
       if (is8)
       {
         dst[lane] = ld_ro<kCoh>(reinterpret_cast<const uint4*>(clut_pool_inst + hi * CLUT_ENTRIES) + lane);
@@ -671,13 +671,14 @@ __device__ __forceinline__ void raster_prim_on_region(const PrimSetup& s, uint32
         dst[lane] = ld_ro<kCoh>(reinterpret_cast<const uint4*>(clut_pool_inst + lo * CLUT_ENTRIES) + lane);
       __syncwarp();
     }
-    raster_spans<RH, kCoh>(s, vram, clut_smem, region, rx0, ry0, lane);
+    raster_spans<RH, kCoh>(s, vram, sh, rx0, ry0, lane);
     return;
   }
   const ShadeState st = shade_state_from_words(reinterpret_cast<const uint32_t*>(&s));
   PixelCtx ctx;
   ctx.vram = vram;
-  ctx.clut = clut_smem;
+  ctx.clut = sh.clut;
+  uint32_t* const region = sh.region;
   uint16_t* region16 = reinterpret_cast<uint16_t*>(region);
   const int32_t x_min = static_cast<int32_t>(rx0);
 
@@ -1384,8 +1385,7 @@ __device__ __forceinline__ void process_epoch_region(const WaveItem& it, RasterS
         request_record((e + 1) & 1u, sh.list[e + 1]);
       if (!(e == 0 && first_awaited))
         await_record(e & 1u, e + 1 < list_n);
-      raster_prim_on_region<RH, kCoh>(*reinterpret_cast<const PrimSetup*>(sh.stage[e & 1u]), sh.region, rx0, ry0, vram, cluts, payload, sh.clut,
-                                      clut_key, lane);
+      raster_prim_on_region<RH, kCoh>(*reinterpret_cast<const PrimSetup*>(sh.stage[e & 1u]), sh, rx0, ry0, vram, cluts, payload, clut_key, lane);
       __syncwarp();
     }
     list_n = 0;
@@ -1486,7 +1486,8 @@ __global__ void __launch_bounds__(32, PSX_RASTER_MIN_CTAS) raster_loop_kernel(
   unsigned int* __restrict__ work_counter, uint32_t want)
 {
   __shared__ RasterShared<TILE_H> sh;
-  const uint32_t lane = threadIdx.x;
+  uint32_t lane;
+  asm volatile("mov.u32 %0, %%tid.x;" : "=r"(lane)); // (opaque to the compiler: it would otherwise re-read the special register — 20 cycles each — all over the per-primitive code instead of keeping the lane in a register)
   const uint32_t total = n_items * NUM_TILES;
   uint32_t mb_phase = 0;
   init_bulk_barriers(sh, lane);

@@ -1,0 +1,8 @@
+for e in "PSXGPU_WAVE_SPLIT=1" "PSXGPU_WAVE_SPLIT=2 PSXGPU_ENC_PRIO=1" "PSXGPU_WAVE_SPLIT=3 PSXGPU_ENC_PRIO=1" "PSXGPU_WAVE_SPLIT=2" "PSXGPU_WAVE_SPLIT=1 PSXGPU_ENC_PRIO=1" "PSXGPU_WAVE_SPLIT=4 PSXGPU_ENC_PRIO=1"; do
+env $e timeout 300 python bench.py --steps 5 --warmup 3 --headline-only --no-cpu-baseline 2>/dev/null | python -c "
+import sys,json
+for l in sys.stdin:
+    if l.strip().startswith('{'):
+        d=json.loads(l); print('$e', 'value',round(d['value'],1),'e2e',round(d['e2e']['value'],1),'e2e ms',round(d['e2e']['ms_per_step'],2), 'dev', round(d['e2e']['breakdown_ms_per_step']['device_ms'],2))
+"
+done
