@@ -1707,8 +1707,8 @@ __global__ void __launch_bounds__(128) epoch_tiles_kernel(const InstWork* __rest
   }
 }
 
-template<uint32_t WARPS>
-__global__ void __launch_bounds__(32 * WARPS, WARPS == 32 ? 1 : (32 / WARPS)) raster_instance_kernel(
+template<uint32_t WARPS, uint32_t MIN_CTAS>
+__global__ void __launch_bounds__(32 * WARPS, MIN_CTAS) raster_instance_kernel(
   const InstWork* __restrict__ work, const Epoch* __restrict__ epochs, const uint32_t* __restrict__ tile_sets,
   const PrimSetup* __restrict__ setups, const uint32_t* __restrict__ tile_cmds, const ClutOp* __restrict__ clut_ops, uint16_t* vram_pool,
   uint16_t* clut_pool, const uint16_t* __restrict__ payload, uint32_t clut_slots)
@@ -2362,24 +2362,48 @@ cudaError_t launch_instances(const InstWork* work, uint32_t n_instances, const E
                                 clut_slots, debug_skip);
     }
   }
-  if (wide)
+  // warps per CTA x CTAs per SM: 32 x 1 — one instance has an SM to itself, all of its epoch's tiles in flight at once and
+  // its 1 MiB of VRAM the only one that SM pulls through L2.  Measured on 2048 instances of the hazard variant of the
+  // batched workload: 8 x 4 23.5 ms, 16 x 2 20.1 ms, 32 x 1 18.6 ms (4 x 8: worse still); PSXGPU_INST_VARIANT = 84 / 83 /
+  // 48 / 46 / 162 selects the other shapes for experiments.
+  using InstKernel = void (*)(const InstWork*, const Epoch*, const uint32_t*, const PrimSetup*, const uint32_t*, const ClutOp*, uint16_t*,
+                              uint16_t*, const uint16_t*, uint32_t);
+  static const int variant = []() {
+    const char* v = std::getenv("PSXGPU_INST_VARIANT");
+    return v ? std::atoi(v) : 0;
+  }();
+  (void)wide;
+  InstKernel kernel = raster_instance_kernel<32, 1>;
+  uint32_t W = 32;
+  if (variant == 84)
   {
-    constexpr uint32_t W = 32;
-    const size_t smem = sizeof(RasterShared<TILE_H>) * W + sizeof(InstanceShared);
-    if ((e = cudaFuncSetAttribute(raster_instance_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))) != cudaSuccess)
-      return e;
-    raster_instance_kernel<W><<<n_instances, 32 * W, smem, st>>>(work, epochs, tile_sets, setups, tile_cmds, clut_ops, vram_pool, clut_pool,
-                                                                 payload, clut_slots);
+    kernel = raster_instance_kernel<8, 4>;
+    W = 8;
   }
-  else
+  else if (variant == 83)
   {
-    constexpr uint32_t W = 8;
-    const size_t smem = sizeof(RasterShared<TILE_H>) * W + sizeof(InstanceShared);
-    if ((e = cudaFuncSetAttribute(raster_instance_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))) != cudaSuccess)
-      return e;
-    raster_instance_kernel<W><<<n_instances, 32 * W, smem, st>>>(work, epochs, tile_sets, setups, tile_cmds, clut_ops, vram_pool, clut_pool,
-                                                                 payload, clut_slots);
+    kernel = raster_instance_kernel<8, 3>;
+    W = 8;
   }
+  else if (variant == 48)
+  {
+    kernel = raster_instance_kernel<4, 8>;
+    W = 4;
+  }
+  else if (variant == 46)
+  {
+    kernel = raster_instance_kernel<4, 6>;
+    W = 4;
+  }
+  else if (variant == 162)
+  {
+    kernel = raster_instance_kernel<16, 2>;
+    W = 16;
+  }
+  const size_t smem = sizeof(RasterShared<TILE_H>) * W + sizeof(InstanceShared);
+  if ((e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))) != cudaSuccess)
+    return e;
+  kernel<<<n_instances, 32 * W, smem, st>>>(work, epochs, tile_sets, setups, tile_cmds, clut_ops, vram_pool, clut_pool, payload, clut_slots);
   return cudaGetLastError();
 }
 
