@@ -1773,6 +1773,12 @@ static int psxgpu_submit_batch_impl(psxgpu_ctx* ctx, uint32_t first, uint32_t co
     HostLayout layout;
     layout.host_cmd_base.assign(cn, 0);
     std::vector<uint64_t> inst_p(cn, 0), used_c(T, 0), used_p(T, 0);
+    // the encoders' persistent state (drawing area, current CLUT slots, snapshot table) as it is before this chunk: a
+    // chunk that is dropped because one of its streams is malformed must not leave slots marked valid whose snapshot
+    // ops were never run
+    std::vector<EncoderStateBlob> saved(cn);
+    for (uint32_t k = 0; k < cn; k++)
+      ctx->enc[first + c0 + k].export_state(saved[k]);
     parallel_ranges(cn, T, [&](uint32_t t, uint32_t lo, uint32_t hi) {
       uint64_t cc = arena_c[t], cp = arena_p[t];
       for (uint32_t k = lo; k < hi; k++)
@@ -1799,8 +1805,14 @@ static int psxgpu_submit_batch_impl(psxgpu_ctx* ctx, uint32_t first, uint32_t co
       {
         ctx->error = (status[c0 + k] == PSXGPU_E_MALFORMED) ? "submit_batch: malformed record stream"
                                                             : "submit_batch: read-back / state records are not allowed in a batch";
-        for (uint32_t j = 0; j < cn; j++) // drop the half-encoded chunk
+        // Drop the half-encoded chunk and put its encoders back where they were.  Earlier chunks of the same batch have
+        // already been launched: a failing batch is applied up to the chunk that holds the bad stream (documented in
+        // include/psxgpu.h).
+        for (uint32_t j = 0; j < cn; j++)
+        {
           ctx->enc[first + c0 + j].begin_flush();
+          ctx->enc[first + c0 + j].import_state(saved[j]);
+        }
         return status[c0 + k];
       }
       work.push_back(first + c0 + k);

@@ -101,7 +101,10 @@ int psxgpu_submit_wire(psxgpu_ctx* ctx, uint32_t instance, const void* wire, siz
 
 /* Batched form: streams[i] goes to instance first_instance + i.  Large batches are uploaded raw and encoded on the
  * device (one warp per instance); small ones are encoded on host threads (latency mode).
- * Barrier records (ReadVRAM, LoadState, ClearVRAM, UpdateDisplay) are not allowed here. */
+ * Barrier records (ReadVRAM, LoadState, ClearVRAM, UpdateDisplay) are not allowed here.
+ * On PSXGPU_E_MALFORMED / PSXGPU_E_UNSUPPORTED the batch has been applied up to (not including) the chunk that holds the
+ * offending stream: earlier chunks are already on the device, the failing chunk is dropped as a whole and its
+ * instances' encoder state (drawing area, CLUT snapshot table) is put back to what it was before the chunk. */
 int psxgpu_submit_batch(psxgpu_ctx* ctx, uint32_t first_instance, uint32_t count, const void* const* streams,
                         const size_t* bytes);
 

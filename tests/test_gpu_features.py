@@ -718,3 +718,47 @@ def test_full_tile_copies(oracle):
             ctx.submit_batch([stream] * 16)
             ctx.flush()
             assert [int(h) for h in ctx.hash()] == [oracle.hash64(want)] * 16, mode
+
+
+@pytest.mark.gpu
+def test_dropped_batch_chunk_restores_encoder_state(oracle):
+    """A host-encoded batch that fails because one stream is malformed is dropped as a whole chunk, and the encoders go
+    back to their state before it (the CLUT snapshot table must not keep slots whose snapshot ops were
+    never run).  What follows must render as if the dropped chunk had never been submitted."""
+    from duckstation_b200 import PsxGpuError
+
+    n = 4
+    parts = []
+    for seed in range(n):
+        s = _strip_barriers(streams.generate(2, 40 + seed, 1500, 0))
+        cuts = [off for _, off, _ in streams.iter_records(s)]
+        a, b = cuts[len(cuts) // 3], cuts[2 * len(cuts) // 3]
+        parts.append((s[:a], s[a:b], s[b:]))
+    want = [oracle.hash64(oracle.render(p[0] + p[2])) for p in parts]
+    with _ctx(n, encode_mode=1) as ctx:
+        ctx.submit_batch([p[0] for p in parts])
+        bad = [p[1] for p in parts]
+        bad[2] = bad[2] + b"\x07\x00\x00\x00\x16\x00\x00\x00"  # a record of size 7 at the end: malformed
+        with pytest.raises(PsxGpuError):
+            ctx.submit_batch(bad)
+        ctx.submit_batch([p[2] for p in parts])
+        ctx.flush()
+        assert [int(h) for h in ctx.hash()] == want
+
+
+@pytest.mark.gpu
+def test_cluster_mode_several_instances(oracle):
+    """Up to eight instances whose streams are cut into many short epochs run as one thread-block cluster per instance
+    (raster_cluster_kernel): five different hazard-heavy streams in one flush, every VRAM against the oracle — aliasing
+    copies (closed form over the cluster), mask-checked uploads and self-sampling primitives included."""
+    cases = [(3, 11, 3000, 0), (3, 12, 2500, 0), (0, 77, 2500, 3), (6, 5, 1500, 0), (3, 13, 600, 0)]
+    ss = [_strip_barriers(streams.generate(*c)) for c in cases]
+    want = [oracle.hash64(oracle.render(s)) for s in ss]
+    with _ctx(len(ss)) as ctx:
+        for i, s in enumerate(ss):
+            ctx.submit(s, i)
+        ctx.flush()
+        got = [int(h) for h in ctx.hash()]
+        assert got == want, [cases[i] for i in range(len(ss)) if got[i] != want[i]]
+        st = ctx.stats()
+        assert st["epochs"] > 8 * len(ss) and st["serial_copy"] > 0 and st["serial_upload"] > 0
