@@ -355,7 +355,7 @@ int run_chunk(psxgpu_ctx* ctx, psxgpu_ctx::Chunk& S)
     CK(launch_instances(static_cast<const InstWork*>(S.d_instwork.p), S.n_instances, static_cast<const Epoch*>(S.d_epochs.p),
                         static_cast<uint32_t*>(S.d_items.p), // (the wave items are not used in this mode: their buffer, 32 bytes per
                                                              // epoch, holds the epochs' tile sets)
-                        static_cast<const PrimSetup*>(S.d_setups.p),
+                        static_cast<const PrimSetup*>(S.d_setups.p), static_cast<const BinInfo*>(S.d_bins.p),
                         static_cast<const uint32_t*>(S.d_tilecmds.p), static_cast<const ClutOp*>(S.d_clutops.p), ctx->d_vram, ctx->d_clut,
                         static_cast<const uint16_t*>(S.d_payload.p), ctx->clut_slots, S.instance_wide, ctx->stream),
        "raster_instance_kernel");
@@ -557,7 +557,7 @@ int launch_chunk_impl(psxgpu_ctx* ctx, const std::vector<uint32_t>& work, const 
   CK(S.d_tilecmds.ensure(tile_cmds_bytes(n_cmds)), "device alloc (tile command bitmaps)");
   CK(S.d_payload.ensure(n_pay * 2 + 16), "device alloc (payload)");
   CK(S.d_clutops.ensure(n_clut * sizeof(ClutOp) + 16), "device alloc (clut ops)");
-  CK(S.d_items.ensure(total_epochs * sizeof(WaveItem) + 16), "device alloc (wave items)");
+  CK(S.d_items.ensure(total_epochs * 64 + 16), "device alloc (wave items / epoch tile sets)"); // (instance mode keeps 64 bytes of tile sets per epoch here)
 
   PackedCmd* hc = static_cast<PackedCmd*>(P.cmds.p);
   uint16_t* hp = static_cast<uint16_t*>(P.payload.p);
@@ -989,7 +989,7 @@ int stage_encode(psxgpu_ctx* ctx, PendingChunk& pc)
   CK(S.d_rects.ensure(cmd * 16 + 64), "device alloc (footprints)");
   CK(S.d_clutops.ensure(clut * sizeof(ClutOp) + 16), "device alloc (clut ops)");
   CK(S.d_epochs.ensure(epoch * sizeof(Epoch) + 16), "device alloc (epochs)");
-  CK(S.d_items.ensure(epoch * sizeof(WaveItem) + 16), "device alloc (wave items)");
+  CK(S.d_items.ensure(static_cast<size_t>(epoch) * 64 + 16), "device alloc (wave items / epoch tile sets)");
   CK(S.d_result.ensure(static_cast<size_t>(cn) * sizeof(EncResult)), "device alloc (encode result)");
   CK(S.d_waves.ensure(static_cast<size_t>(wave_cap) * sizeof(EncWave)), "device alloc (wave table)");
   CK(S.d_cursor.ensure(static_cast<size_t>(wave_cap) * 4), "device alloc (wave cursors)");

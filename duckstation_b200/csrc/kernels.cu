@@ -98,7 +98,8 @@ __global__ void __launch_bounds__(128) setup_kernel(const PackedCmd* __restrict_
 #pragma unroll
     for (int k = 0; k < static_cast<int>(sizeof(PrimSetup) / 16); k++)
       dst[k] = sw[k];
-    bins[i].tilemask = b.tilemask;
+    b.readmask = (s.op == OP_NOP) ? 0u : read_tilemask(c);
+    bins[i] = b;
     mask = b.tilemask;
     // Exact binning for triangles: the mask above is the bounding box, and a triangle that spans 2 x 2 tiles or more
     // usually misses a corner tile (13 % of the raster warps' visits found no pixel).  Per band of 32 rows the spans lie
@@ -1658,15 +1659,28 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 7) raster_persistent_kernel(
 // to L2, kCoh).  No cross-CTA synchronisation exists: instances are independent.  WARPS = 8 for batches (four CTAs
 // per SM), 32 for a handful of instances (one CTA per SM, 1024 threads on the serial epochs).
 constexpr uint32_t INST_EPOCH_WINDOW = 64; // epochs whose descriptors are staged in shared memory at a time
+constexpr uint32_t INST_RUN_MAX = 16;      // tiled epochs that may be in flight together (tile-granular dependencies)
+constexpr uint32_t EPOCH_SET_WORDS = 16;   // per epoch: 256 bits of written tiles + 256 bits of read tiles (epoch_tiles_kernel)
 
 struct InstanceShared
 {
   uint32_t row_count[VRAM_H + 1];
   alignas(16) uint32_t stage[SETUP_WORDS];
   Epoch epochs[INST_EPOCH_WINDOW];
-  uint32_t tile_sets[INST_EPOCH_WINDOW][8];
-  uint32_t tile_total[INST_EPOCH_WINDOW]; // tiles in each set (cluster mode)
+  uint32_t tile_sets[INST_EPOCH_WINDOW][EPOCH_SET_WORDS]; // [0..7] tiles written, [8..15] tiles read
+  uint32_t tile_total[INST_EPOCH_WINDOW]; // tiles written by each epoch
   uint32_t next_tile[2];
+};
+// raster_instance_dag_kernel only: tile-granular dependencies inside a run of tiled epochs — per (epoch of the run, tile)
+// how many writer items / reader signals must have completed before the epoch's item on that tile may start, and the
+// completion counters themselves
+struct InstanceDagShared : InstanceShared
+{
+  uint8_t need_w[INST_RUN_MAX][NUM_TILES];
+  uint16_t need_r[INST_RUN_MAX][NUM_TILES];
+  uint32_t done_w[NUM_TILES], done_r[NUM_TILES];
+  uint32_t run_item_base[INST_RUN_MAX + 1];
+  uint32_t run_next;
 };
 
 // Which tiles does each epoch of each instance touch?  One warp per epoch, lane L looks after tiles 8 L .. 8 L + 7: the
@@ -1674,7 +1688,8 @@ struct InstanceShared
 // binning's own granularity, where the union of the commands' column and row masks would name every tile of the
 // drawing area.  Eight words (256 bits) per epoch, for raster_instance_kernel.
 __global__ void __launch_bounds__(128) epoch_tiles_kernel(const InstWork* __restrict__ work, const Epoch* __restrict__ epochs,
-                                                          const uint32_t* __restrict__ tile_cmds, uint32_t* __restrict__ tile_sets)
+                                                          const uint32_t* __restrict__ tile_cmds, const BinInfo* __restrict__ bins,
+                                                          uint32_t* __restrict__ tile_sets, uint32_t want_reads)
 {
   const InstWork w = work[blockIdx.x];
   const uint32_t lane = threadIdx.x & 31u;
@@ -1698,20 +1713,61 @@ __global__ void __launch_bounds__(128) epoch_tiles_kernel(const InstWork* __rest
                 ((c.x & keep) ? 16u : 0u) | ((c.y & keep) ? 32u : 0u) | ((c.z & keep) ? 64u : 0u) | ((c.w & keep) ? 128u : 0u);
       }
     }
-    // four lanes make one word
-    uint32_t word = byte << (8u * (lane & 3u));
+    // ... and the tiles the epoch's commands may READ (texture footprints, copy sources: BinInfo::readmask, a rectangle
+    // of tiles per command): lane L holds tile row L / 2, columns 8 (L & 1) .. + 7
+    uint32_t rbyte = 0;
+    if (want_reads && ep.cmd_end > ep.cmd_begin) // (only the kernel with tile-granular dependencies uses the read sets)
+    {
+      for (uint32_t i = w.cmd_base + ep.cmd_begin; i < w.cmd_base + ep.cmd_end; i++)
+      {
+        const uint32_t rm = __ldg(&bins[i].readmask);
+        if ((rm >> (16u + (lane >> 1))) & 1u)
+          rbyte |= (rm >> (8u * (lane & 1u))) & 0xFFu;
+      }
+    }
+    // four lanes make one word: eight words of written tiles, then eight words of read tiles per epoch
+    uint32_t word = byte << (8u * (lane & 3u)), rword = rbyte << (8u * (lane & 3u));
     word |= __shfl_xor_sync(0xFFFFFFFFu, word, 1);
     word |= __shfl_xor_sync(0xFFFFFFFFu, word, 2);
+    rword |= __shfl_xor_sync(0xFFFFFFFFu, rword, 1);
+    rword |= __shfl_xor_sync(0xFFFFFFFFu, rword, 2);
     if ((lane & 3u) == 0)
-      tile_sets[static_cast<size_t>(w.epoch_first + k) * 8 + (lane >> 2)] = word;
+    {
+      tile_sets[static_cast<size_t>(w.epoch_first + k) * EPOCH_SET_WORDS + (lane >> 2)] = word;
+      tile_sets[static_cast<size_t>(w.epoch_first + k) * EPOCH_SET_WORDS + 8 + (lane >> 2)] = rword;
+    }
   }
+}
+
+// The ord-th tile (in tile order) of a 256-bit tile set held one word per lane in lanes 0-7 (`mine`; `before` / `cnt` =
+// exclusive prefix / popcount of the lane's word).
+__device__ __forceinline__ uint32_t nth_tile(uint32_t mine, uint32_t before, uint32_t cnt, uint32_t ord, uint32_t lane)
+{
+  const bool here = lane < 8 && ord >= before && ord < before + cnt;
+  const uint32_t src = static_cast<uint32_t>(__ffs(static_cast<int>(__ballot_sync(0xFFFFFFFFu, here)))) - 1u;
+  return __shfl_sync(0xFFFFFFFFu, lane * 32u + __fns(mine, 0, static_cast<int>(ord - before) + 1), src);
+}
+__device__ __forceinline__ uint32_t tile_set_prefix(uint32_t mine, uint32_t lane, uint32_t& before)
+{
+  const uint32_t cnt = __popc(mine);
+  before = cnt;
+#pragma unroll
+  for (uint32_t o = 1; o < 8; o <<= 1)
+  {
+    const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, before, o);
+    if (lane >= o)
+      before += t;
+  }
+  const uint32_t total = __shfl_sync(0xFFFFFFFFu, before, 7);
+  before -= cnt;
+  return total;
 }
 
 template<uint32_t WARPS, uint32_t MIN_CTAS>
 __global__ void __launch_bounds__(32 * WARPS, MIN_CTAS) raster_instance_kernel(
   const InstWork* __restrict__ work, const Epoch* __restrict__ epochs, const uint32_t* __restrict__ tile_sets,
   const PrimSetup* __restrict__ setups, const uint32_t* __restrict__ tile_cmds, const ClutOp* __restrict__ clut_ops, uint16_t* vram_pool,
-  uint16_t* clut_pool, const uint16_t* __restrict__ payload, uint32_t clut_slots)
+  uint16_t* clut_pool, const uint16_t* __restrict__ payload, uint32_t clut_slots, uint32_t /*run_max*/)
 {
   extern __shared__ __align__(16) unsigned char dyn_smem[];
   RasterShared<TILE_H>* sh_all = reinterpret_cast<RasterShared<TILE_H>*>(dyn_smem);
@@ -1734,8 +1790,8 @@ __global__ void __launch_bounds__(32 * WARPS, MIN_CTAS) raster_instance_kernel(
       const uint32_t* src = reinterpret_cast<const uint32_t*>(epochs + w.epoch_first + k);
       for (uint32_t i = threadIdx.x; i < n * (sizeof(Epoch) / 4); i += NT)
         reinterpret_cast<uint32_t*>(cs.epochs)[i] = __ldg(src + i);
-      for (uint32_t i = threadIdx.x; i < n * 8; i += NT)
-        (&cs.tile_sets[0][0])[i] = __ldg(tile_sets + static_cast<size_t>(w.epoch_first + k) * 8 + i);
+      for (uint32_t i = threadIdx.x; i < n * EPOCH_SET_WORDS; i += NT)
+        (&cs.tile_sets[0][0])[i] = __ldg(tile_sets + static_cast<size_t>(w.epoch_first + k) * EPOCH_SET_WORDS + i);
       __syncthreads();
     }
     const Epoch ep = cs.epochs[slot];
@@ -1818,6 +1874,206 @@ __global__ void __launch_bounds__(32 * WARPS, MIN_CTAS) raster_instance_kernel(
   }
 }
 
+// The same, with TILE-granular dependencies inside runs of tiled epochs instead of a barrier per epoch (PSXGPU_INST_RUN=n,
+// n > 1, selects it).  Measured on the hazard variant of the batched workload (512 instances): barrier stalls per issue
+// 6.0 -> 4.1, issue slots 44 % -> 46 % busy, but 13 % more instructions (per-item dependency tests, signals, tile
+// lookup) — 5.8 ms against 5.3 ms for the kernel above.  The runs are short there: every CLUT snapshot op and every
+// serial epoch ends one (a snapshot op may overwrite a palette slot that items of earlier epochs still use, so it has
+// to wait for all of them), which leaves two or three epochs per run.  Kept for streams with long runs of plain
+// render-to-texture hazards, and as the measured answer to "why not per-tile dependencies".
+template<uint32_t WARPS, uint32_t MIN_CTAS>
+__global__ void __launch_bounds__(32 * WARPS, MIN_CTAS) raster_instance_dag_kernel(
+  const InstWork* __restrict__ work, const Epoch* __restrict__ epochs, const uint32_t* __restrict__ tile_sets,
+  const PrimSetup* __restrict__ setups, const uint32_t* __restrict__ tile_cmds, const ClutOp* __restrict__ clut_ops, uint16_t* vram_pool,
+  uint16_t* clut_pool, const uint16_t* __restrict__ payload, uint32_t clut_slots, uint32_t run_max)
+{
+  extern __shared__ __align__(16) unsigned char dyn_smem[];
+  RasterShared<TILE_H>* sh_all = reinterpret_cast<RasterShared<TILE_H>*>(dyn_smem);
+  InstanceDagShared& cs = *reinterpret_cast<InstanceDagShared*>(dyn_smem + sizeof(RasterShared<TILE_H>) * WARPS);
+  constexpr uint32_t NT = 32 * WARPS;
+  const InstWork w = work[blockIdx.x];
+  uint16_t* vram = vram_pool + static_cast<size_t>(w.instance) * VRAM_PIXELS;
+  uint16_t* cluts = clut_pool + static_cast<size_t>(w.instance) * clut_slots * CLUT_ENTRIES;
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+  uint32_t clut_key = 0; // the palette this warp has staged; survives until the next CLUT snapshot op
+
+  auto epoch_item = [&](const Epoch& ep) {
+    WaveItem it;
+    it.instance = w.instance;
+    it.cmd_begin = w.cmd_base + ep.cmd_begin;
+    it.cmd_end = w.cmd_base + ep.cmd_end;
+    it.kind = ep.kind;
+    it.clut_begin = w.clut_base + ep.clut_begin;
+    it.clut_end = w.clut_base + ep.clut_end;
+    return it;
+  };
+
+  uint32_t k = 0;
+  while (k < w.n_epochs)
+  {
+    const uint32_t slot = k % INST_EPOCH_WINDOW;
+    if (slot == 0)
+    {
+      // the next window of epoch descriptors and tile sets: they do not depend on anything this kernel writes
+      const uint32_t n = min(INST_EPOCH_WINDOW, w.n_epochs - k);
+      const uint32_t* src = reinterpret_cast<const uint32_t*>(epochs + w.epoch_first + k);
+      for (uint32_t i = threadIdx.x; i < n * (sizeof(Epoch) / 4); i += NT)
+        reinterpret_cast<uint32_t*>(cs.epochs)[i] = __ldg(src + i);
+      for (uint32_t i = threadIdx.x; i < n * EPOCH_SET_WORDS; i += NT)
+        (&cs.tile_sets[0][0])[i] = __ldg(tile_sets + static_cast<size_t>(w.epoch_first + k) * EPOCH_SET_WORDS + i);
+      __syncthreads();
+      for (uint32_t i = threadIdx.x; i < n; i += NT)
+      {
+        uint32_t c = 0;
+#pragma unroll
+        for (uint32_t q = 0; q < 8; q++)
+          c += __popc(cs.tile_sets[i][q]);
+        cs.tile_total[i] = c;
+      }
+      __syncthreads();
+    }
+    const WaveItem it = epoch_item(cs.epochs[slot]);
+    if (it.clut_end > it.clut_begin) // uniform over the CTA
+    {
+      clut_key = 0;
+      for (uint32_t o = it.clut_begin; o < it.clut_end; o++)
+      {
+        const ClutOp op = clut_ops[o];
+        for (uint32_t t = threadIdx.x; t < (op.is8bit ? 256u : 16u); t += NT)
+          cluts[op.dst_slot * CLUT_ENTRIES + t] = __ldcg(vram + op.y * VRAM_W + ((op.x + t) & (VRAM_W - 1)));
+      }
+      __syncthreads();
+    }
+    if (it.cmd_end == it.cmd_begin)
+    {
+      k++;
+      continue;
+    }
+    if (it.kind != EPOCH_TILED)
+    {
+      if (threadIdx.x < SETUP_WORDS)
+        cs.stage[threadIdx.x] = reinterpret_cast<const uint32_t*>(setups + it.cmd_begin)[threadIdx.x];
+      __syncthreads();
+      const PrimSetup& s = *reinterpret_cast<const PrimSetup*>(cs.stage);
+      if (s.op != OP_NOP)
+      {
+        if (it.kind == EPOCH_SELF_SAMPLING)
+          serial_self_sampling<NT>(s, vram, cluts);
+        else if (it.kind == EPOCH_COPY_OVERLAP)
+          serial_copy<NT>(s, vram);
+        else
+          serial_upload_masked<NT>(s, vram, payload, cs.row_count);
+      }
+      __syncthreads();
+      k++;
+      continue;
+    }
+
+    // ---- a run of tiled epochs: this one and the tiled epochs behind it (same window, no CLUT snapshot op in front of
+    // them), executed with TILE-granular dependencies instead of a barrier per epoch.  The splitter cut these epochs
+    // apart because somewhere a later command reads or overwrites what an earlier one wrote or read; that concerns a
+    // few tiles, and the other tiles of the later epochs need not wait.  An item = (epoch j of the run, tile t written
+    // by it), pulled in (epoch, tile) order.  Item (j, t) may start when
+    //   * every earlier item on t and on every tile epoch j reads is complete (RAW, WAW): done_w[s] >= need_w[j][s];
+    //   * every item of an earlier epoch that reads t is complete (WAR): done_r[t] >= need_r[j][t]
+    // (epoch-level read sets from epoch_tiles_kernel: coarser than the splitter's cells, never finer — a superset of the
+    // true dependencies).  A finished item writes its tile back, fences, and bumps done_w[t] and done_r[s] for every s
+    // its epoch reads.  Items are pulled in an order in which every dependency comes first, so the lowest item in
+    // flight never waits: no deadlock.
+    uint32_t n_run = 1;
+    while (n_run < run_max && slot + n_run < INST_EPOCH_WINDOW && k + n_run < w.n_epochs)
+    {
+      const Epoch& e2 = cs.epochs[slot + n_run];
+      if (e2.kind != EPOCH_TILED || e2.clut_end > e2.clut_begin)
+        break;
+      n_run++;
+    }
+    if (threadIdx.x < NUM_TILES)
+    {
+      const uint32_t t = threadIdx.x, word = t >> 5, bit = t & 31u;
+      uint32_t cw = 0, cr = 0;
+      for (uint32_t j = 0; j < n_run; j++)
+      {
+        cs.need_w[j][t] = static_cast<uint8_t>(cw);
+        cs.need_r[j][t] = static_cast<uint16_t>(cr);
+        cw += (cs.tile_sets[slot + j][word] >> bit) & 1u;
+        if ((cs.tile_sets[slot + j][8 + word] >> bit) & 1u)
+          cr += cs.tile_total[slot + j];
+      }
+      cs.done_w[t] = 0;
+      cs.done_r[t] = 0;
+    }
+    if (threadIdx.x == 0)
+    {
+      uint32_t base = 0;
+      for (uint32_t j = 0; j < n_run; j++)
+      {
+        cs.run_item_base[j] = base;
+        base += cs.tile_total[slot + j];
+      }
+      cs.run_item_base[n_run] = base;
+      cs.run_next = 0;
+    }
+    __syncthreads();
+    const uint32_t n_items = cs.run_item_base[n_run];
+    for (;;)
+    {
+      uint32_t g = 0;
+      if (lane == 0)
+        g = atomicAdd(&cs.run_next, 1u);
+      g = __shfl_sync(0xFFFFFFFFu, g, 0);
+      if (g >= n_items)
+        break;
+      uint32_t j = 0;
+      while (cs.run_item_base[j + 1] <= g)
+        j++;
+      const uint32_t mine = (lane < 8) ? cs.tile_sets[slot + j][lane] : 0u; // lane L: tiles 32 L .. 32 L + 31
+      uint32_t before;
+      tile_set_prefix(mine, lane, before);
+      const uint32_t tile = nth_tile(mine, before, __popc(mine), g - cs.run_item_base[j], lane);
+      // dependencies: lane L looks after tiles 8 L .. 8 L + 7
+      const uint32_t reads8 = (cs.tile_sets[slot + j][8 + (lane >> 2)] >> (8u * (lane & 3u))) & 0xFFu;
+      const uint32_t own8 = ((tile >> 3) == lane) ? (1u << (tile & 7u)) : 0u;
+      if (j != 0) // (the first epoch of a run waits for nothing)
+      {
+        for (;;)
+        {
+          bool ok = true;
+          uint32_t m = reads8 | own8;
+          while (m)
+          {
+            const uint32_t b = static_cast<uint32_t>(__ffs(static_cast<int>(m))) - 1u;
+            m &= m - 1u;
+            const uint32_t sidx = lane * 8u + b;
+            ok = ok && *reinterpret_cast<volatile uint32_t*>(&cs.done_w[sidx]) >= cs.need_w[j][sidx];
+          }
+          if (own8)
+            ok = ok && *reinterpret_cast<volatile uint32_t*>(&cs.done_r[tile]) >= cs.need_r[j][tile];
+          if (__all_sync(0xFFFFFFFFu, ok))
+            break;
+          __nanosleep(40);
+        }
+      }
+      process_epoch_region<TILE_H, true>(epoch_item(cs.epochs[slot + j]), sh_all[warp], tile % TILES_X, tile / TILES_X, (tile / TILES_X) * TILE_H,
+                                         setups, tile_cmds, vram, cluts, payload, lane, nullptr, &clut_key);
+      // the tile is back in global memory: publish it to the CTA, then signal
+      __threadfence_block();
+      __syncwarp();
+      if (lane == 0)
+        atomicAdd(&cs.done_w[tile], 1u);
+      uint32_t m = reads8;
+      while (m)
+      {
+        const uint32_t b = static_cast<uint32_t>(__ffs(static_cast<int>(m))) - 1u;
+        m &= m - 1u;
+        atomicAdd(&cs.done_r[lane * 8u + b], 1u);
+      }
+    }
+    __syncthreads();
+    k += n_run;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ cluster mode
 // A single VRAM (or a handful) whose stream is cut into thousands of short epochs: one CTA cannot win (one SM's issue
 // rate), and a grid-wide barrier per epoch costs more than the epoch's work (≈7 µs through L2 atomics).  Here one
@@ -1850,30 +2106,6 @@ __device__ __forceinline__ void cluster_barrier()
 {
   cluster_arrive();
   cluster_wait();
-}
-
-// The ord-th tile (in tile order) of a 256-bit tile set held one word per lane in lanes 0-7 (`mine`; `before` / `cnt` =
-// exclusive prefix / popcount of the lane's word).
-__device__ __forceinline__ uint32_t nth_tile(uint32_t mine, uint32_t before, uint32_t cnt, uint32_t ord, uint32_t lane)
-{
-  const bool here = lane < 8 && ord >= before && ord < before + cnt;
-  const uint32_t src = static_cast<uint32_t>(__ffs(static_cast<int>(__ballot_sync(0xFFFFFFFFu, here)))) - 1u;
-  return __shfl_sync(0xFFFFFFFFu, lane * 32u + __fns(mine, 0, static_cast<int>(ord - before) + 1), src);
-}
-__device__ __forceinline__ uint32_t tile_set_prefix(uint32_t mine, uint32_t lane, uint32_t& before)
-{
-  const uint32_t cnt = __popc(mine);
-  before = cnt;
-#pragma unroll
-  for (uint32_t o = 1; o < 8; o <<= 1)
-  {
-    const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, before, o);
-    if (lane >= o)
-      before += t;
-  }
-  const uint32_t total = __shfl_sync(0xFFFFFFFFu, before, 7);
-  before -= cnt;
-  return total;
 }
 
 // CopyVRAM whose source and destination alias, by the whole cluster at once.  The reference copies row after row, each
@@ -1989,8 +2221,8 @@ __global__ void __launch_bounds__(32 * CLUSTER_WARPS, 1) raster_cluster_kernel(
       const uint32_t* src = reinterpret_cast<const uint32_t*>(epochs + w.epoch_first + k);
       for (uint32_t i = threadIdx.x; i < n * (sizeof(Epoch) / 4); i += NT)
         reinterpret_cast<uint32_t*>(cs.epochs)[i] = __ldg(src + i);
-      for (uint32_t i = threadIdx.x; i < n * 8; i += NT)
-        (&cs.tile_sets[0][0])[i] = __ldg(tile_sets + static_cast<size_t>(w.epoch_first + k) * 8 + i);
+      for (uint32_t i = threadIdx.x; i < n * EPOCH_SET_WORDS; i += NT)
+        (&cs.tile_sets[0][0])[i] = __ldg(tile_sets + static_cast<size_t>(w.epoch_first + k) * EPOCH_SET_WORDS + i);
       __syncthreads();
       for (uint32_t i = threadIdx.x; i < n; i += NT)
       {
@@ -2286,12 +2518,11 @@ uint32_t cluster_max_instances()
 }
 
 cudaError_t launch_instances(const InstWork* work, uint32_t n_instances, const Epoch* epochs, uint32_t* tile_sets, const PrimSetup* setups,
-                             const uint32_t* tile_cmds, const ClutOp* clut_ops, uint16_t* vram_pool, uint16_t* clut_pool,
+                             const BinInfo* bins, const uint32_t* tile_cmds, const ClutOp* clut_ops, uint16_t* vram_pool, uint16_t* clut_pool,
                              const uint16_t* payload, uint32_t clut_slots, bool wide, cudaStream_t st)
 {
   if (n_instances == 0)
     return cudaSuccess;
-  epoch_tiles_kernel<<<n_instances, 128, 0, st>>>(work, epochs, tile_cmds, tile_sets);
   cudaError_t e;
   if (wide && n_instances <= cluster_max_instances())
   {
@@ -2353,6 +2584,7 @@ cudaError_t launch_instances(const InstWork* work, uint32_t n_instances, const E
       attr.val.clusterDim.y = attr.val.clusterDim.z = 1;
       cfg.attrs = &attr;
       cfg.numAttrs = 1;
+      epoch_tiles_kernel<<<n_instances, 128, 0, st>>>(work, epochs, tile_cmds, bins, tile_sets, 0u);
       const uint32_t* ts = tile_sets;
       static const uint32_t debug_skip = []() {
         const char* e = std::getenv("PSXGPU_DEBUG_SKIP"); // timing experiments: 1 = no serial epochs, 2 = no tiled epochs, 4 = no CLUT ops (results are wrong)
@@ -2367,7 +2599,12 @@ cudaError_t launch_instances(const InstWork* work, uint32_t n_instances, const E
   // batched workload: 8 x 4 23.5 ms, 16 x 2 20.1 ms, 32 x 1 18.6 ms (4 x 8: worse still); PSXGPU_INST_VARIANT = 84 / 83 /
   // 48 / 46 / 162 selects the other shapes for experiments.
   using InstKernel = void (*)(const InstWork*, const Epoch*, const uint32_t*, const PrimSetup*, const uint32_t*, const ClutOp*, uint16_t*,
-                              uint16_t*, const uint16_t*, uint32_t);
+                              uint16_t*, const uint16_t*, uint32_t, uint32_t);
+  static const uint32_t run_max = []() {
+    const char* v = std::getenv("PSXGPU_INST_RUN"); // tiled epochs in flight together (tile-granular dependencies); 1 = a barrier per epoch
+    const int n = v ? std::atoi(v) : 1;
+    return static_cast<uint32_t>(n < 1 ? 1 : (n > static_cast<int>(INST_RUN_MAX) ? static_cast<int>(INST_RUN_MAX) : n));
+  }();
   static const int variant = []() {
     const char* v = std::getenv("PSXGPU_INST_VARIANT");
     return v ? std::atoi(v) : 0;
@@ -2400,10 +2637,15 @@ cudaError_t launch_instances(const InstWork* work, uint32_t n_instances, const E
     kernel = raster_instance_kernel<16, 2>;
     W = 16;
   }
-  const size_t smem = sizeof(RasterShared<TILE_H>) * W + sizeof(InstanceShared);
+  const bool dag = run_max > 1 && W == 32;
+  if (dag)
+    kernel = raster_instance_dag_kernel<32, 1>;
+  epoch_tiles_kernel<<<n_instances, 128, 0, st>>>(work, epochs, tile_cmds, bins, tile_sets, dag ? 1u : 0u);
+  const size_t smem = sizeof(RasterShared<TILE_H>) * W + (dag ? sizeof(InstanceDagShared) : sizeof(InstanceShared));
   if ((e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))) != cudaSuccess)
     return e;
-  kernel<<<n_instances, 32 * W, smem, st>>>(work, epochs, tile_sets, setups, tile_cmds, clut_ops, vram_pool, clut_pool, payload, clut_slots);
+  kernel<<<n_instances, 32 * W, smem, st>>>(work, epochs, tile_sets, setups, tile_cmds, clut_ops, vram_pool, clut_pool, payload, clut_slots,
+                                            run_max);
   return cudaGetLastError();
 }
 

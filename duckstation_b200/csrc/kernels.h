@@ -51,9 +51,9 @@ cudaError_t launch_persistent(const WaveItem* items, const void* waves, uint32_t
                               cudaStream_t st);
 // Instance mode (many short epochs per instance): one CTA per instance for a whole flush, __syncthreads() between
 // epochs.  `work` / `epochs`: device arrays (psx_types.h).  wide = 32 warps per CTA (a handful of instances), else 8.
-// `tile_sets`: scratch, eight words per epoch slot (filled here by epoch_tiles_kernel: the tiles each epoch touches).
+// `tile_sets`: scratch, sixteen words per epoch (filled here by epoch_tiles_kernel: the tiles each epoch writes / reads).
 cudaError_t launch_instances(const InstWork* work, uint32_t n_instances, const Epoch* epochs, uint32_t* tile_sets, const PrimSetup* setups,
-                             const uint32_t* tile_cmds, const ClutOp* clut_ops, uint16_t* vram_pool, uint16_t* clut_pool,
+                             const BinInfo* bins, const uint32_t* tile_cmds, const ClutOp* clut_ops, uint16_t* vram_pool, uint16_t* clut_pool,
                              const uint16_t* payload, uint32_t clut_slots, bool wide, cudaStream_t st);
 cudaError_t launch_hash(const uint16_t* vram_pool, uint32_t first, uint32_t count, unsigned long long* out, cudaStream_t st);
 cudaError_t launch_scanout(const uint16_t* vram, const ScanoutParams& p, uint8_t* out, cudaStream_t st);

@@ -39,6 +39,83 @@ PSX_HD uint32_t tile_rowmask(uint32_t y, uint32_t h)
   return (m | (m >> TILES_Y)) & 0xFFFFu;
 }
 
+// Tiles a command may READ from VRAM while it is rasterised — the texture footprint (the rule of
+// Encoder::texture_footprint, encoder.cpp, at tile granularity: texcoord range of the vertices widened by one step, or
+// the window's range, on the texture page) or a copy's source rectangle — as column bits | row bits << 16 of the
+// bounding rectangle, wrapping.  0 = reads nothing.  The kernels that order work per tile instead of per epoch
+// (raster_instance_kernel) build their dependencies from it; a superset is always safe.
+PSX_HD uint32_t read_tilemask(const PackedCmd& c)
+{
+  if (c.op == OP_COPY)
+    return tile_colmask(c.copy.sx, c.copy.w) | (tile_rowmask(c.copy.sy, c.copy.h) << 16);
+  if ((c.op != OP_TRIANGLE && c.op != OP_RECT) || !(c.flags0 & F_TEXTURE))
+    return 0;
+  uint32_t umin, umax, vmin, vmax;
+  if (c.op == OP_TRIANGLE)
+  {
+    umin = c.v[0].u < c.v[1].u ? c.v[0].u : c.v[1].u;
+    umin = c.v[2].u < umin ? c.v[2].u : umin;
+    umax = c.v[0].u > c.v[1].u ? c.v[0].u : c.v[1].u;
+    umax = c.v[2].u > umax ? c.v[2].u : umax;
+    vmin = c.v[0].v < c.v[1].v ? c.v[0].v : c.v[1].v;
+    vmin = c.v[2].v < vmin ? c.v[2].v : vmin;
+    vmax = c.v[0].v > c.v[1].v ? c.v[0].v : c.v[1].v;
+    vmax = c.v[2].v > vmax ? c.v[2].v : vmax;
+    // interpolated coordinates may overshoot by one step, and wrap at the ends of the range
+    if (umin == 0 || umax == 255)
+    {
+      umin = 0;
+      umax = 255;
+    }
+    else
+    {
+      umin--;
+      umax++;
+    }
+    if (vmin == 0 || vmax == 255)
+    {
+      vmin = 0;
+      vmax = 255;
+    }
+    else
+    {
+      vmin--;
+      vmax++;
+    }
+  }
+  else
+  {
+    umin = c.rect.u0;
+    umax = c.rect.u0 + (c.rect.w ? c.rect.w - 1u : 0u);
+    vmin = c.rect.v0;
+    vmax = c.rect.v0 + (c.rect.h ? c.rect.h - 1u : 0u);
+    if (umax > 255)
+    {
+      umin = 0;
+      umax = 255;
+    }
+    if (vmax > 255)
+    {
+      vmin = 0;
+      vmax = 255;
+    }
+  }
+  if (c.win_and_x != 0xFF || c.win_or_x != 0)
+  {
+    umin = c.win_or_x;
+    umax = c.win_or_x | c.win_and_x;
+  }
+  if (c.win_and_y != 0xFF || c.win_or_y != 0)
+  {
+    vmin = c.win_or_y;
+    vmax = c.win_or_y | c.win_and_y;
+  }
+  const uint32_t mode = (c.draw_mode >> 7) & 3u;
+  const uint32_t sh = (mode == 0) ? 2u : (mode == 1 ? 1u : 0u);
+  const uint32_t bx = (c.draw_mode & 0xFu) * 64u, by = ((c.draw_mode >> 4) & 1u) * 256u;
+  return tile_colmask(bx + (umin >> sh), (umax >> sh) - (umin >> sh) + 1u) | (tile_rowmask(by + vmin, vmax - vmin + 1u) << 16);
+}
+
 PSX_HD void set_bins(PrimSetup& s, BinInfo& b, int32_t x0, int32_t x1, uint32_t row0, uint32_t rowcount, bool cols_wrap,
                      uint32_t wrap_x, uint32_t wrap_w)
 {

@@ -270,6 +270,7 @@ static_assert(sizeof(PrimSetup) == 256, "PrimSetup must be 256 bytes");
 struct BinInfo
 {
   uint32_t tilemask; // bits 0-15: 64-px tile columns touched, bits 16-31: 32-row tile rows touched
+  uint32_t readmask; // the same form: tiles the command may read while it runs (texture footprint, copy source); 0 = none
 };
 
 PSX_HD int32_t sext11(int32_t v)
