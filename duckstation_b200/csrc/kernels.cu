@@ -201,6 +201,15 @@ constexpr int SERIAL_WARPS = SERIAL_THREADS / 32;
 constexpr uint32_t LIST_CAP = 160;                      // per-tile bin capacity between raster phases (5216 B per warp: 32 warps fit the 196 KB shared-memory configuration, L1 keeps 60 KB)
 constexpr uint32_t SETUP_WORDS = sizeof(PrimSetup) / 4; // 60
 constexpr uint32_t SETUP_VECS = sizeof(PrimSetup) / 16; // 16
+#ifndef PSX_REC_MODE
+#define PSX_REC_MODE 2 // (measured, draw wave of 512 instances: 0 = 1.640 ms, 1 = 1.653, 2 = 1.634; with the two options below 1.613)
+#endif
+#ifndef PSX_OPT_WIN
+#define PSX_OPT_WIN 1
+#endif
+#ifndef PSX_OPT_CLUTLD
+#define PSX_OPT_CLUTLD 1
+#endif
 #ifndef PSX_REGION_PITCH
 #define PSX_REGION_PITCH 36
 #endif
@@ -287,6 +296,12 @@ __device__ __forceinline__ void bulk_wait_read() // the engine has read the shar
 __device__ __forceinline__ void fence_proxy_async_smem()
 {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t lds_u16(uint32_t addr)
+{
+  uint16_t v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
+  return v;
 }
 // once per warp, before the first bulk copy (lane 0 initialises, the warp synchronises)
 template<typename Shared>
@@ -494,6 +509,9 @@ __device__ __forceinline__ void raster_spans(const PrimSetup& s, const uint16_t*
     const uint32_t c_chk15 = D.chk15, c_set15 = D.set15, c_tex_shift = D.tex_shift, c_tex_bx2 = D.tex_bx2, c_trow = D.tex_rows;
     const uint32_t c_sub_mask2 = D.sub_mask2, c_sub_shift = D.sub_shift, c_im = D.idx_mask, c_fr = D.fr, c_fg = D.fg, c_fb = D.fb;
     const uint32_t c_du = T.ddx[3], c_dv = T.ddx[4];
+#if PSX_OPT_CLUTLD
+    const uint32_t clut_s = smem_u32(sh.clut);
+#endif
     uint32_t r = row_of_pixel(start, 0, rowmap, lane);
     uint32_t pk = __shfl_sync(0xFFFFFFFFu, packed, r);
   #pragma unroll 1
@@ -531,6 +549,12 @@ __device__ __forceinline__ void raster_spans(const PrimSetup& s, const uint16_t*
           U = (ub + 2u * w) * 0x00010001u + 0x00010000u;
           V = __shfl_sync(0xFFFFFFFFu, rb_v, r);
         }
+#if PSX_OPT_WIN
+        // the window constants of a primitive without a texture window are and = 0xFF, or = 0 (make_loop_desc): one
+        // form for both cases, no test
+        U = (U & D.and_x2) | D.or_x2;
+        V = (V & D.and_y2) | D.or_y2;
+#else
         if (path & LP_WINDOW)
         {
           U = (U & D.and_x2) | D.or_x2;
@@ -541,6 +565,7 @@ __device__ __forceinline__ void raster_spans(const PrimSetup& s, const uint16_t*
           U &= 0x00FF00FFu;
           V &= 0x00FF00FFu;
         }
+#endif
         // psx_pixel.h:texel_addr on both pixels at once; page base row (0 or 256) + v never wraps
         const uint32_t tx = ((U >> c_tex_shift) + c_tex_bx2) & 0x03FF03FFu;
         const uint32_t trow = c_trow;
@@ -571,8 +596,15 @@ __device__ __forceinline__ void raster_spans(const PrimSetup& s, const uint16_t*
           const uint32_t sub = (U & c_sub_mask2) << c_sub_shift; // bit offset of the index in its word
           const uint32_t im = c_im;
           PSX_CHECK(im < CLUT_ENTRIES);
+#if PSX_OPT_CLUTLD
+          // (explicit 32-bit shared addresses from a base computed once per visit: the generic form re-derives the
+          // shared window's base inside the loop)
+          t0 = lds_u16(clut_s + 2u * ((t0 >> (sub & 0xFFFFu)) & im));
+          t1 = lds_u16(clut_s + 2u * ((t1 >> (sub >> 16)) & im));
+#else
           t0 = sh.clut[(t0 >> (sub & 0xFFFFu)) & im];
           t1 = sh.clut[(t1 >> (sub >> 16)) & im];
+#endif
         }
         tex = __byte_perm(t0, t1, 0x5410);
         we15 = cov15 & (((tex & 0x7FFF7FFFu) + 0x7FFF7FFFu) | tex) & ~(bg & c_chk15); // pair_we_textured
@@ -1271,6 +1303,12 @@ __device__ __forceinline__ void process_epoch_region(const WaveItem& it, RasterS
   // transaction barriers; *mb_phase_io carries the barriers' phase bits from one region of the warp to the next.
   // Otherwise (the kernels that stay resident across epochs and read what other CTAs wrote): 16-byte cp.async from L2.
   constexpr bool kBulk = !kCoh;
+  // How the 256-byte setup records reach shared memory in the throughput kernels (PSX_REC_MODE): 0 = one bulk copy per
+  // record + transaction barrier, 1 = 16-byte cp.async (as the resident kernels), 2 = each lane loads 8 bytes of the NEXT
+  // record into two registers while the current one is rasterised and stores them when its turn comes.
+  constexpr bool kBulkRec = kBulk && PSX_REC_MODE == 0;
+  constexpr bool kRegRec = kBulk && PSX_REC_MODE == 2;
+  uint2 rec_next = make_uint2(0u, 0u);
   PSX_CHECK(it.cmd_begin <= it.cmd_end && it.cmd_end <= g_dbg.n_cmds && it.instance < g_dbg.n_instances);
   PSX_CHECK(tx < TILES_X && ry0 + RH <= VRAM_H && (ry0 % RH) == 0);
   const uint32_t rx0 = tx * TILE_W;
@@ -1302,7 +1340,9 @@ __device__ __forceinline__ void process_epoch_region(const WaveItem& it, RasterS
   // request the setup record of list entry `rel` into stage[buf]
   auto request_record = [&](uint32_t buf, uint32_t rel) {
     PSX_CHECK(buf < 2 && rel < it.cmd_end - it.cmd_begin);
-    if (kBulk)
+    if (kRegRec)
+      rec_next = __ldg(reinterpret_cast<const uint2*>(epoch_setups + rel) + lane); // 32 lanes x 8 bytes = one record
+    else if (kBulkRec)
     {
       if (lane == 0)
       {
@@ -1319,7 +1359,9 @@ __device__ __forceinline__ void process_epoch_region(const WaveItem& it, RasterS
   };
   // wait until stage[buf] holds its record (newer_in_flight: one younger request may stay outstanding)
   auto await_record = [&](uint32_t buf, bool newer_in_flight) {
-    if (kBulk)
+    if (kRegRec)
+      reinterpret_cast<uint2*>(sh.stage[buf])[lane] = rec_next;
+    else if (kBulkRec)
     {
       mbar_wait(&sh.mbar[buf], (mb_phase >> buf) & 1u);
       mb_phase ^= 1u << buf;
@@ -1382,10 +1424,21 @@ __device__ __forceinline__ void process_epoch_region(const WaveItem& it, RasterS
 #pragma unroll 1
     for (uint32_t e = 0; e < list_n; e++)
     {
-      if (e + 1 < list_n)
-        request_record((e + 1) & 1u, sh.list[e + 1]);
-      if (!(e == 0 && first_awaited))
-        await_record(e & 1u, e + 1 < list_n);
+      if (kRegRec)
+      {
+        // the registers hold record e: store it, then start loading record e + 1
+        if (!(e == 0 && first_awaited))
+          await_record(e & 1u, false);
+        if (e + 1 < list_n)
+          request_record((e + 1) & 1u, sh.list[e + 1]);
+      }
+      else
+      {
+        if (e + 1 < list_n)
+          request_record((e + 1) & 1u, sh.list[e + 1]);
+        if (!(e == 0 && first_awaited))
+          await_record(e & 1u, e + 1 < list_n);
+      }
       raster_prim_on_region<RH, kCoh>(*reinterpret_cast<const PrimSetup*>(sh.stage[e & 1u]), sh, rx0, ry0, vram, cluts, payload, clut_key, lane);
       __syncwarp();
     }

@@ -39,11 +39,41 @@ void shade_and_store(const PrimSetup& s, const uint16_t*, uint32_t px, uint32_t 
   dst = static_cast<uint16_t>(blend_mask(st, dst, colour));
 }
 
+// Work model of the raster kernel's word loop (profiling aid): per (primitive, tile) visit the 32-bit words its spans
+// touch, the batches of 32 words the warp walks, and the pixels covered.
+uint64_t g_work[8]; // visits, words, batches, pixels, visits by words bucket: <=32, <=64, <=128, >128
+void account_span(std::vector<uint32_t>& words, std::vector<uint32_t>& touched, int32_t lo, int32_t hi, uint32_t Y)
+{
+  for (int32_t tx = lo >> 6; tx <= (hi - 1) >> 6; tx++)
+  {
+    const int32_t a = lo > tx * 64 ? lo : tx * 64, b = hi < tx * 64 + 64 ? hi : tx * 64 + 64;
+    const uint32_t t = (Y >> 5) * 16u + (static_cast<uint32_t>(tx) & 15u);
+    if (words[t] == 0)
+      touched.push_back(t);
+    words[t] += static_cast<uint32_t>(((b - 1) >> 1) - (a >> 1) + 1);
+    g_work[3] += static_cast<uint32_t>(b - a);
+  }
+}
+void account_flush(std::vector<uint32_t>& words, std::vector<uint32_t>& touched)
+{
+  for (uint32_t t : touched)
+  {
+    const uint32_t w = words[t];
+    g_work[0]++;
+    g_work[1] += w;
+    g_work[2] += (w + 31) / 32;
+    g_work[w <= 32 ? 4 : w <= 64 ? 5 : w <= 128 ? 6 : 7]++;
+    words[t] = 0;
+  }
+  touched.clear();
+}
+
 void run_tiled_prim(const PrimSetup& s, const uint16_t* payload)
 {
   const uint16_t* clut = nullptr;
   if (s.op == OP_NOP)
     return;
+  static std::vector<uint32_t> acc_words(NUM_TILES, 0), acc_touched;
   for (uint32_t i = 0; i < s.bycount; i++)
   {
     const uint32_t Y = (s.by0 + i) & (VRAM_H - 1);
@@ -54,6 +84,8 @@ void run_tiled_prim(const PrimSetup& s, const uint16_t* payload)
         TriRow row;
         if (!tri_row(s, Y, row))
           break;
+        if (row.x_hi > row.x_lo)
+          account_span(acc_words, acc_touched, row.x_lo, row.x_hi, Y);
         for (int32_t px = row.x_lo; px < row.x_hi; px++)
         {
           uint32_t r, g, b, u, v;
@@ -67,6 +99,8 @@ void run_tiled_prim(const PrimSetup& s, const uint16_t* payload)
         RectRow row;
         if (!rect_row(s, Y, row))
           break;
+        if (row.x_hi > row.x_lo)
+          account_span(acc_words, acc_touched, row.x_lo, row.x_hi, Y);
         for (int32_t px = row.x_lo; px < row.x_hi; px++)
           shade_and_store(s, clut, static_cast<uint32_t>(px), Y, s.rect.r, s.rect.g, s.rect.b,
                           (s.rect.u0 + static_cast<uint32_t>(px - s.rect.x)) & 0xFFu, row.v);
@@ -115,6 +149,7 @@ void run_tiled_prim(const PrimSetup& s, const uint16_t* payload)
       default: break;
     }
   }
+  account_flush(acc_words, acc_touched);
 }
 
 // ---- serial kinds: reference-order emulation (what the single-CTA kernels do) ----
@@ -361,6 +396,16 @@ void hostsim_handover(int modulation_crop)
   delete g_enc;
   g_enc = new Encoder(SLOTS, modulation_crop != 0);
   g_enc->import_state(blob);
+}
+
+void hostsim_work(uint64_t* out, int reset)
+{
+  for (int i = 0; i < 8; i++)
+  {
+    out[i] = g_work[i];
+    if (reset)
+      g_work[i] = 0;
+  }
 }
 
 void hostsim_stats(uint64_t* out, int n)
