@@ -357,7 +357,7 @@ int run_chunk(psxgpu_ctx* ctx, psxgpu_ctx::Chunk& S)
                                                              // epoch, holds the epochs' tile sets)
                         static_cast<const PrimSetup*>(S.d_setups.p), static_cast<const BinInfo*>(S.d_bins.p),
                         static_cast<const uint32_t*>(S.d_tilecmds.p), static_cast<const ClutOp*>(S.d_clutops.p), ctx->d_vram, ctx->d_clut,
-                        static_cast<const uint16_t*>(S.d_payload.p), ctx->clut_slots, S.instance_wide, ctx->stream),
+                        static_cast<const uint16_t*>(S.d_payload.p), ctx->clut_slots, S.instance_wide, ctx->stream, ctx->d_barrier + 8),
        "raster_instance_kernel");
     if (prof_i)
       CK(cudaEventRecord(S.ev_raster[S.ev_raster_used++], ctx->stream), "event record");

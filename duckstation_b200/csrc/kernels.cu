@@ -1927,6 +1927,288 @@ __global__ void __launch_bounds__(32 * WARPS, MIN_CTAS) raster_instance_kernel(
   }
 }
 
+// ------------------------------------------------------------------------------------------------ slot mode
+// raster_instance_kernel leaves most of an SM idle on streams cut into many short epochs: an epoch of a few dozen
+// primitives touches a few dozen tiles, the warp that owns the busiest tile walks its bin alone while the other warps
+// wait at the barrier, and one warp issues an instruction every 5-10 cycles.  More resident warps are not to be had (64
+// registers, 6 KB of shared memory each), so here the CTA's 32 warps serve SEVERAL instances at a time: the CTA holds
+// n_slots instance slots, every slot walks its own instance's epochs in order, and a warp that finds nothing left to
+// claim in one slot's epoch claims a tile of another slot's.  What separates two epochs of a slot is that slot's own
+// counter (tiles done == tiles of the epoch), not a barrier of the CTA: the warp that finishes the epoch's last tile
+// runs the transition (CLUT snapshot ops, next epoch's tile set) by itself while the others keep rasterising the other
+// slots.  Finished instances are replaced from a global counter.  Only the serial epoch kinds (self-sampling, aliasing
+// copies, mask-checked uploads: whole-CTA code) make the CTA meet: they are flagged, every warp leaves the work loop
+// after its current tile, the CTA runs the flagged slots' serial epochs with all of its threads and resumes.
+// Ordering inside a slot: tile write-back (st.global) -> __threadfence_block -> atomic on `done` (shared) -> ... ->
+// publishing store to `next` -> the claimant's atomic on `next` -> __threadfence_block -> its loads (ld.global.cg /
+// cp.async.cg: L2, never a stale L1 line).  All parties are warps of one CTA, so CTA scope is enough.
+constexpr uint32_t MULTI_SLOTS_MAX = 6;
+constexpr uint32_t SLOT_IDLE = 0, SLOT_TILED = 1, SLOT_SERIAL = 2, SLOT_BUSY = 3;
+constexpr uint32_t SLOT_CLOSED = 0x80000000u; // `next` while the slot has no tiles to hand out (a claim lands above every total)
+struct MultiSlot
+{
+  WaveItem it;        // the current epoch (global command / CLUT-op indices)
+  uint32_t tiles[8];  // its tile set
+  uint32_t before[8]; // exclusive prefix of the words' popcounts
+  uint32_t total;     // tiles in the set
+  uint32_t next;      // next ordinal to hand out
+  uint32_t done;      // tiles finished
+  uint32_t state;
+  uint32_t epoch, n_epochs, epoch_first, cmd_base, clut_base, instance;
+  uint32_t pad[2];
+};
+struct MultiShared
+{
+  uint32_t row_count[VRAM_H + 1];
+  alignas(16) uint32_t stage[SETUP_WORDS];
+  MultiSlot slot[MULTI_SLOTS_MAX];
+  uint32_t serial_pending; // slots waiting for the CTA to run their serial epoch
+  uint32_t active;         // slots that still hold an instance
+};
+
+// One warp moves slot `s` to its next epoch with work (or to its next instance, or to rest).  On entry nobody can claim
+// from the slot (next >= SLOT_CLOSED) and every tile of its previous epoch has been written back.
+__device__ __noinline__ void multi_advance_slot(MultiShared& cs, uint32_t s, bool fresh, const InstWork* __restrict__ work, uint32_t n_instances,
+                                                const Epoch* __restrict__ epochs, const uint32_t* __restrict__ tile_sets,
+                                                const ClutOp* __restrict__ clut_ops, uint16_t* vram_pool, uint16_t* clut_pool, uint32_t clut_slots,
+                                                unsigned int* inst_counter, uint32_t lane)
+{
+  MultiSlot& S = cs.slot[s];
+  uint32_t k = fresh ? 0u : S.epoch + 1u;
+  uint32_t n_epochs = fresh ? 0u : S.n_epochs;
+  for (;;)
+  {
+    if (k >= n_epochs)
+    {
+      uint32_t idx = 0;
+      if (lane == 0)
+        idx = atomicAdd(inst_counter, 1u);
+      idx = __shfl_sync(0xFFFFFFFFu, idx, 0);
+      if (idx >= n_instances)
+      {
+        if (lane == 0)
+        {
+          S.state = SLOT_IDLE;
+          __threadfence_block();
+          atomicSub(&cs.active, 1u);
+        }
+        __syncwarp();
+        return;
+      }
+      const InstWork w = work[idx];
+      if (lane == 0)
+      {
+        S.instance = w.instance;
+        S.cmd_base = w.cmd_base;
+        S.clut_base = w.clut_base;
+        S.epoch_first = w.epoch_first;
+        S.n_epochs = w.n_epochs;
+      }
+      __syncwarp();
+      n_epochs = w.n_epochs;
+      k = 0;
+      if (n_epochs == 0)
+        continue;
+    }
+    const uint32_t epoch_first = S.epoch_first, instance = S.instance;
+    const Epoch ep = epochs[epoch_first + k];
+    uint16_t* vram = vram_pool + static_cast<size_t>(instance) * VRAM_PIXELS;
+    uint16_t* cluts = clut_pool + static_cast<size_t>(instance) * clut_slots * CLUT_ENTRIES;
+    WaveItem it;
+    it.instance = instance;
+    it.cmd_begin = S.cmd_base + ep.cmd_begin;
+    it.cmd_end = S.cmd_base + ep.cmd_end;
+    it.kind = ep.kind;
+    it.clut_begin = S.clut_base + ep.clut_begin;
+    it.clut_end = S.clut_base + ep.clut_end;
+    it.pad[0] = it.pad[1] = 0;
+    for (uint32_t o = it.clut_begin; o < it.clut_end; o++)
+    {
+      const ClutOp op = clut_ops[o];
+      for (uint32_t t = lane; t < (op.is8bit ? 256u : 16u); t += 32)
+        cluts[op.dst_slot * CLUT_ENTRIES + t] = __ldcg(vram + op.y * VRAM_W + ((op.x + t) & (VRAM_W - 1)));
+    }
+    if (it.cmd_end > it.cmd_begin)
+    {
+      if (ep.kind != EPOCH_TILED)
+      {
+        if (lane == 0)
+        {
+          S.it = it;
+          S.epoch = k;
+          S.state = SLOT_SERIAL;
+          __threadfence_block();
+          atomicAdd(&cs.serial_pending, 1u);
+        }
+        __syncwarp();
+        return;
+      }
+      const uint32_t mine = (lane < 8) ? __ldg(tile_sets + static_cast<size_t>(epoch_first + k) * EPOCH_SET_WORDS + lane) : 0u;
+      uint32_t before;
+      const uint32_t total = tile_set_prefix(mine, lane, before);
+      if (total != 0)
+      {
+        if (lane < 8)
+        {
+          S.tiles[lane] = mine;
+          S.before[lane] = before;
+        }
+        if (lane == 0)
+        {
+          S.it = it;
+          S.epoch = k;
+          S.total = total;
+          S.done = 0;
+        }
+        __syncwarp();
+        __threadfence_block(); // the descriptor and the CLUT slots written above, before the slot opens
+        if (lane == 0)
+        {
+          S.state = SLOT_TILED;
+          atomicExch(&S.next, 0u);
+        }
+        __syncwarp();
+        return;
+      }
+    }
+    k++;
+  }
+}
+
+template<uint32_t WARPS>
+__global__ void __launch_bounds__(32 * WARPS, 1) raster_multi_kernel(
+  const InstWork* __restrict__ work, uint32_t n_instances, const Epoch* __restrict__ epochs, const uint32_t* __restrict__ tile_sets,
+  const PrimSetup* __restrict__ setups, const uint32_t* __restrict__ tile_cmds, const ClutOp* __restrict__ clut_ops, uint16_t* vram_pool,
+  uint16_t* clut_pool, const uint16_t* __restrict__ payload, uint32_t clut_slots, uint32_t n_slots, unsigned int* inst_counter)
+{
+  extern __shared__ __align__(16) unsigned char dyn_smem[];
+  RasterShared<TILE_H>* sh_all = reinterpret_cast<RasterShared<TILE_H>*>(dyn_smem);
+  MultiShared& cs = *reinterpret_cast<MultiShared*>(dyn_smem + sizeof(RasterShared<TILE_H>) * WARPS);
+  constexpr uint32_t NT = 32 * WARPS;
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+  if (threadIdx.x < MULTI_SLOTS_MAX)
+  {
+    cs.slot[threadIdx.x].state = SLOT_BUSY;
+    cs.slot[threadIdx.x].next = SLOT_CLOSED;
+    cs.slot[threadIdx.x].total = 0;
+    cs.slot[threadIdx.x].done = 0;
+  }
+  if (threadIdx.x == 0)
+  {
+    cs.serial_pending = 0;
+    cs.active = n_slots;
+  }
+  __syncthreads();
+  if (warp < n_slots)
+    multi_advance_slot(cs, warp, true, work, n_instances, epochs, tile_sets, clut_ops, vram_pool, clut_pool, clut_slots, inst_counter, lane);
+  __syncthreads();
+
+  volatile uint32_t* const v_pending = &cs.serial_pending;
+  volatile uint32_t* const v_active = &cs.active;
+  for (;;)
+  {
+    // ---- work loop: claim a tile of any slot's current epoch ----
+    uint32_t idle_spins = 0;
+    for (;;)
+    {
+      uint32_t claim = 0xFFFFFFFFu; // slot | ordinal << 8
+      if (lane == 0)
+      {
+        if (*v_pending == 0 && *v_active != 0)
+        {
+          for (uint32_t i = 0; i < n_slots; i++)
+          {
+            const uint32_t s = (warp + i) % n_slots; // (warps start at different slots: fewer collisions on one counter)
+            volatile MultiSlot& S = cs.slot[s];
+            if (S.state != SLOT_TILED || S.next >= S.total)
+              continue;
+            const uint32_t j = atomicAdd(const_cast<uint32_t*>(&S.next), 1u);
+            __threadfence_block();
+            if (j < S.total) // (read after the claim: a claim that lands in the NEXT epoch of the slot is a valid claim of that epoch)
+            {
+              claim = s | (j << 8);
+              break;
+            }
+          }
+          if (claim == 0xFFFFFFFFu)
+            claim = 0xFFFFFFFEu; // nothing to claim right now
+        }
+      }
+      claim = __shfl_sync(0xFFFFFFFFu, claim, 0);
+      __syncwarp();
+      if (claim == 0xFFFFFFFFu)
+        break; // a serial epoch is waiting for the CTA, or every slot is at rest
+      if (claim == 0xFFFFFFFEu)
+      {
+        __nanosleep(idle_spins < 8 ? 64u : 256u);
+        idle_spins++;
+        continue;
+      }
+      idle_spins = 0;
+      const uint32_t s = claim & 0xFFu, j = claim >> 8;
+      MultiSlot& S = cs.slot[s];
+      const WaveItem it = S.it;
+      const uint32_t total = S.total;
+      const uint32_t mine = (lane < 8) ? S.tiles[lane] : 0u, before = (lane < 8) ? S.before[lane] : 0u;
+      const uint32_t tile = nth_tile(mine, before, __popc(mine), j, lane);
+      const uint32_t tx = tile % TILES_X, ty = tile / TILES_X;
+      uint16_t* vram = vram_pool + static_cast<size_t>(it.instance) * VRAM_PIXELS;
+      const uint16_t* cluts = clut_pool + static_cast<size_t>(it.instance) * clut_slots * CLUT_ENTRIES;
+      process_epoch_region<TILE_H, true>(it, sh_all[warp], tx, ty, ty * TILE_H, setups, tile_cmds, vram, cluts, payload, lane);
+      __syncwarp();
+      __threadfence_block(); // the tile's write-back, before it counts as done
+      uint32_t last = 0;
+      if (lane == 0)
+      {
+        last = (atomicAdd(&S.done, 1u) + 1u == total) ? 1u : 0u;
+        if (last)
+        {
+          S.state = SLOT_BUSY;
+          atomicExch(&S.next, SLOT_CLOSED);
+        }
+      }
+      last = __shfl_sync(0xFFFFFFFFu, last, 0);
+      if (last)
+      {
+        __threadfence_block();
+        multi_advance_slot(cs, s, false, work, n_instances, epochs, tile_sets, clut_ops, vram_pool, clut_pool, clut_slots, inst_counter, lane);
+      }
+    }
+    __syncthreads(); // every warp is out of the work loop: no claim, no transition in flight
+    if (cs.active == 0)
+      break;
+    // ---- serial epochs of the flagged slots, all threads ----
+    for (uint32_t s = 0; s < n_slots; s++)
+    {
+      if (cs.slot[s].state != SLOT_SERIAL) // (uniform: nobody writes slot states between the barriers)
+        continue;
+      const WaveItem it = cs.slot[s].it;
+      uint16_t* vram = vram_pool + static_cast<size_t>(it.instance) * VRAM_PIXELS;
+      uint16_t* cluts = clut_pool + static_cast<size_t>(it.instance) * clut_slots * CLUT_ENTRIES;
+      if (threadIdx.x < SETUP_WORDS)
+        cs.stage[threadIdx.x] = reinterpret_cast<const uint32_t*>(setups + it.cmd_begin)[threadIdx.x];
+      __syncthreads();
+      const PrimSetup& ps = *reinterpret_cast<const PrimSetup*>(cs.stage);
+      if (ps.op != OP_NOP)
+      {
+        if (it.kind == EPOCH_SELF_SAMPLING)
+          serial_self_sampling<NT>(ps, vram, cluts);
+        else if (it.kind == EPOCH_COPY_OVERLAP)
+          serial_copy<NT>(ps, vram);
+        else
+          serial_upload_masked<NT>(ps, vram, payload, cs.row_count);
+      }
+      __syncthreads();
+    }
+    if (threadIdx.x == 0)
+      cs.serial_pending = 0;
+    __syncthreads();
+    if (warp < n_slots && cs.slot[warp].state == SLOT_SERIAL)
+      multi_advance_slot(cs, warp, false, work, n_instances, epochs, tile_sets, clut_ops, vram_pool, clut_pool, clut_slots, inst_counter, lane);
+    __syncthreads();
+  }
+}
+
 // The same, with TILE-granular dependencies inside runs of tiled epochs instead of a barrier per epoch (PSXGPU_INST_RUN=n,
 // n > 1, selects it).  Measured on the hazard variant of the batched workload (512 instances): barrier stalls per issue
 // 6.0 -> 4.1, issue slots 44 % -> 46 % busy, but 13 % more instructions (per-item dependency tests, signals, tile
@@ -2572,7 +2854,7 @@ uint32_t cluster_max_instances()
 
 cudaError_t launch_instances(const InstWork* work, uint32_t n_instances, const Epoch* epochs, uint32_t* tile_sets, const PrimSetup* setups,
                              const BinInfo* bins, const uint32_t* tile_cmds, const ClutOp* clut_ops, uint16_t* vram_pool, uint16_t* clut_pool,
-                             const uint16_t* payload, uint32_t clut_slots, bool wide, cudaStream_t st)
+                             const uint16_t* payload, uint32_t clut_slots, bool wide, cudaStream_t st, unsigned int* inst_counter)
 {
   if (n_instances == 0)
     return cudaSuccess;
@@ -2693,6 +2975,35 @@ cudaError_t launch_instances(const InstWork* work, uint32_t n_instances, const E
   const bool dag = run_max > 1 && W == 32;
   if (dag)
     kernel = raster_instance_dag_kernel<32, 1>;
+  // slot mode (raster_multi_kernel): one 32-warp CTA per SM serves n_slots instances at a time
+  static const uint32_t n_slots = []() {
+    const char* v = std::getenv("PSXGPU_SLOTS"); // 0 = one instance per CTA and a barrier per epoch (raster_instance_kernel)
+    const int n = v ? std::atoi(v) : 3;
+    return static_cast<uint32_t>(n < 0 ? 0 : (n > static_cast<int>(MULTI_SLOTS_MAX) ? static_cast<int>(MULTI_SLOTS_MAX) : n));
+  }();
+  if (n_slots != 0 && variant == 0 && !dag && inst_counter != nullptr)
+  {
+    static const int n_sms = []() {
+      int dev = 0, n = 0;
+      if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+        n = 148;
+      return n;
+    }();
+    // few instances: fewer slots per CTA, so that every SM gets one
+    uint32_t slots = n_slots;
+    while (slots > 1 && static_cast<uint64_t>(n_sms) * (slots - 1) >= n_instances)
+      slots--;
+    const uint32_t ctas = std::min<uint32_t>(static_cast<uint32_t>(n_sms), (n_instances + slots - 1) / slots);
+    const size_t smem_multi = sizeof(RasterShared<TILE_H>) * 32 + sizeof(MultiShared);
+    if ((e = cudaFuncSetAttribute(raster_multi_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_multi))) != cudaSuccess)
+      return e;
+    if ((e = cudaMemsetAsync(inst_counter, 0, sizeof(unsigned int), st)) != cudaSuccess)
+      return e;
+    epoch_tiles_kernel<<<n_instances, 128, 0, st>>>(work, epochs, tile_cmds, bins, tile_sets, 0u);
+    raster_multi_kernel<32><<<ctas, 32 * 32, smem_multi, st>>>(work, n_instances, epochs, tile_sets, setups, tile_cmds, clut_ops, vram_pool, clut_pool,
+                                                              payload, clut_slots, slots, inst_counter);
+    return cudaGetLastError();
+  }
   epoch_tiles_kernel<<<n_instances, 128, 0, st>>>(work, epochs, tile_cmds, bins, tile_sets, dag ? 1u : 0u);
   const size_t smem = sizeof(RasterShared<TILE_H>) * W + (dag ? sizeof(InstanceDagShared) : sizeof(InstanceShared));
   if ((e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))) != cudaSuccess)

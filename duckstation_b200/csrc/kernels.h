@@ -54,7 +54,7 @@ cudaError_t launch_persistent(const WaveItem* items, const void* waves, uint32_t
 // `tile_sets`: scratch, sixteen words per epoch (filled here by epoch_tiles_kernel: the tiles each epoch writes / reads).
 cudaError_t launch_instances(const InstWork* work, uint32_t n_instances, const Epoch* epochs, uint32_t* tile_sets, const PrimSetup* setups,
                              const BinInfo* bins, const uint32_t* tile_cmds, const ClutOp* clut_ops, uint16_t* vram_pool, uint16_t* clut_pool,
-                             const uint16_t* payload, uint32_t clut_slots, bool wide, cudaStream_t st);
+                             const uint16_t* payload, uint32_t clut_slots, bool wide, cudaStream_t st, unsigned int* inst_counter);
 cudaError_t launch_hash(const uint16_t* vram_pool, uint32_t first, uint32_t count, unsigned long long* out, cudaStream_t st);
 cudaError_t launch_scanout(const uint16_t* vram, const ScanoutParams& p, uint8_t* out, cudaStream_t st);
 
