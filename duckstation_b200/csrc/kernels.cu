@@ -210,6 +210,12 @@ constexpr uint32_t SETUP_VECS = sizeof(PrimSetup) / 16; // 16
 #ifndef PSX_OPT_CLUTLD
 #define PSX_OPT_CLUTLD 1
 #endif
+#ifndef PSX_OPT_CLUTASYNC
+#define PSX_OPT_CLUTASYNC 1
+#endif
+#ifndef PSX_HASH_UNROLL
+#define PSX_HASH_UNROLL 0
+#endif
 #ifndef PSX_REGION_PITCH
 #define PSX_REGION_PITCH 36
 #endif
@@ -418,7 +424,7 @@ __device__ __forceinline__ uint32_t row_lane_map(uint32_t rows, uint32_t lane)
 // (LoopDesc, written by setup_kernel): the loop keeps few registers live, so nothing is rematerialised per word.
 template<uint32_t RH, bool kCoh>
 __device__ __forceinline__ void raster_spans(const PrimSetup& s, const uint16_t* vram, RasterShared<RH>& sh,
-                                             uint32_t rx0, uint32_t ry0, uint32_t lane)
+                                             uint32_t rx0, uint32_t ry0, uint32_t lane, bool clut_pending)
 {
   const LoopDesc& D = s.desc;
   const uint32_t path = D.path;
@@ -487,7 +493,14 @@ __device__ __forceinline__ void raster_spans(const PrimSetup& s, const uint16_t*
   const uint32_t cnt = (xe > xs) ? static_cast<uint32_t>(((xe - 1) >> 1) - (xs >> 1) + 1) : 0u; // words touched
   const uint32_t rows = __ballot_sync(0xFFFFFFFFu, cnt != 0);
   if (rows == 0)
+  {
+    if (clut_pending) // (the palette counts as staged from here on)
+    {
+      cp_async_wait<0>();
+      __syncwarp();
+    }
     return;
+  }
   const uint32_t incl = warp_inclusive_scan(cnt, lane);
   const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
   const uint32_t start = cnt ? (incl - cnt) : ROW_EMPTY;
@@ -665,6 +678,11 @@ PSX_CHECK(r < RH && w < TILE_W / 2);
       }
     }
   };
+  if (clut_pending) // the palette requested by raster_prim_on_region (asynchronous copy) has to be there now
+  {
+    cp_async_wait<0>();
+    __syncwarp();
+  }
   using std::integral_constant;
   if (!(D.path & LP_TEXTURED))
     word_loop(integral_constant<uint32_t, LP_TEXTURED | LP_PALETTED | LP_WINDOW | LP_MODULATED>{}, integral_constant<uint32_t, LP_MODULATED>{});
@@ -687,6 +705,7 @@ __device__ __forceinline__ void raster_prim_on_region(const PrimSetup& s, Raster
   PSX_CHECK(op <= OP_NOP);
   if (op <= OP_RECT) // OP_TRIANGLE, OP_RECT
   {
+    bool clut_pending = false;
     // paletted: make sure the merged palette is in shared memory (one coalesced 512-byte read when it changes)
     const uint32_t key = s.desc.clut_key; // lo slot | hi slot << 8 | 8-bit << 16 | 1 << 31, 0 = no palette
     if (key != 0 && key != clut_key)
@@ -695,6 +714,20 @@ __device__ __forceinline__ void raster_prim_on_region(const PrimSetup& s, Raster
       const uint32_t lo = key & 0xFFu, hi = (key >> 8) & 0xFFu, is8 = (key >> 16) & 1u;
       PSX_CHECK(lo < g_dbg.clut_slots && hi < g_dbg.clut_slots);
       uint4* dst = reinterpret_cast<uint4*>(sh.clut);
+#if PSX_OPT_CLUTASYNC
+      // asynchronous copy (no register, no wait here): the palette arrives while the spans are worked out, the word
+      // loop waits for it.  Entries 0-15 (lanes 0-1) come from the lo slot, the rest of an 8-bit palette from the hi slot.
+      if (is8 || lane < 2)
+      {
+        const uint4* src = reinterpret_cast<const uint4*>(clut_pool_inst + ((lane < 2) ? lo : hi) * CLUT_ENTRIES) + lane;
+        if (kCoh)
+          cp_async16_l2(dst + lane, src);
+        else
+          cp_async16(dst + lane, src);
+      }
+      cp_async_commit();
+      clut_pending = true;
+#else
       if (is8)
       {
         dst[lane] = ld_ro<kCoh>(reinterpret_cast<const uint4*>(clut_pool_inst + hi * CLUT_ENTRIES) + lane);
@@ -703,8 +736,9 @@ __device__ __forceinline__ void raster_prim_on_region(const PrimSetup& s, Raster
       if (lane < 2 && (!is8 || lo != hi))
         dst[lane] = ld_ro<kCoh>(reinterpret_cast<const uint4*>(clut_pool_inst + lo * CLUT_ENTRIES) + lane);
       __syncwarp();
+#endif
     }
-    raster_spans<RH, kCoh>(s, vram, sh, rx0, ry0, lane);
+    raster_spans<RH, kCoh>(s, vram, sh, rx0, ry0, lane, clut_pending);
     return;
   }
   const ShadeState st = shade_state_from_words(reinterpret_cast<const uint32_t*>(&s));
@@ -1939,10 +1973,16 @@ __global__ void __launch_bounds__(32 * WARPS, MIN_CTAS) raster_instance_kernel(
 // slots.  Finished instances are replaced from a global counter.  Only the serial epoch kinds (self-sampling, aliasing
 // copies, mask-checked uploads: whole-CTA code) make the CTA meet: they are flagged, every warp leaves the work loop
 // after its current tile, the CTA runs the flagged slots' serial epochs with all of its threads and resumes.
+// Measured on 2048 instances of the hazard variant of the batched workload (generator config 6): barrier per epoch
+// 18.5 ms, 1 slot 21.7 (the claim protocol alone costs more than __syncthreads), 2 slots 16.6, 3 slots 16.5, 4 slots 17.5
+// (444+ instances in flight no longer fit L2: 8 + 5 GB of DRAM traffic per 512 instances, long-scoreboard the top
+// stall).  Tried and dropped: L2 prefetch of the tiles one round ahead of their claim and at the epoch's start (18-20 ms:
+// the lookups and the prefetches cost more than the misses they save), the epoch's bin words staged in shared memory by
+// the transition (21.6 ms: 16 KB more shared memory put the CTA into the 228 KB configuration, no L1 left).
 // Ordering inside a slot: tile write-back (st.global) -> __threadfence_block -> atomic on `done` (shared) -> ... ->
 // publishing store to `next` -> the claimant's atomic on `next` -> __threadfence_block -> its loads (ld.global.cg /
 // cp.async.cg: L2, never a stale L1 line).  All parties are warps of one CTA, so CTA scope is enough.
-constexpr uint32_t MULTI_SLOTS_MAX = 6;
+constexpr uint32_t MULTI_SLOTS_MAX = 4;
 constexpr uint32_t SLOT_IDLE = 0, SLOT_TILED = 1, SLOT_SERIAL = 2, SLOT_BUSY = 3;
 constexpr uint32_t SLOT_CLOSED = 0x80000000u; // `next` while the slot has no tiles to hand out (a claim lands above every total)
 struct MultiSlot
@@ -1970,6 +2010,7 @@ struct MultiShared
 // from the slot (next >= SLOT_CLOSED) and every tile of its previous epoch has been written back.
 __device__ __noinline__ void multi_advance_slot(MultiShared& cs, uint32_t s, bool fresh, const InstWork* __restrict__ work, uint32_t n_instances,
                                                 const Epoch* __restrict__ epochs, const uint32_t* __restrict__ tile_sets,
+                                                const uint32_t* __restrict__ tile_cmds,
                                                 const ClutOp* __restrict__ clut_ops, uint16_t* vram_pool, uint16_t* clut_pool, uint32_t clut_slots,
                                                 unsigned int* inst_counter, uint32_t lane)
 {
@@ -2100,9 +2141,10 @@ __global__ void __launch_bounds__(32 * WARPS, 1) raster_multi_kernel(
   }
   __syncthreads();
   if (warp < n_slots)
-    multi_advance_slot(cs, warp, true, work, n_instances, epochs, tile_sets, clut_ops, vram_pool, clut_pool, clut_slots, inst_counter, lane);
+    multi_advance_slot(cs, warp, true, work, n_instances, epochs, tile_sets, tile_cmds, clut_ops, vram_pool, clut_pool, clut_slots, inst_counter, lane);
   __syncthreads();
 
+  const uint32_t first_slot = warp % n_slots;
   volatile uint32_t* const v_pending = &cs.serial_pending;
   volatile uint32_t* const v_active = &cs.active;
   for (;;)
@@ -2116,9 +2158,9 @@ __global__ void __launch_bounds__(32 * WARPS, 1) raster_multi_kernel(
       {
         if (*v_pending == 0 && *v_active != 0)
         {
-          for (uint32_t i = 0; i < n_slots; i++)
+          uint32_t s = first_slot; // (warps start at different slots: fewer collisions on one counter)
+          for (uint32_t i = 0; i < n_slots; i++, s = (s + 1u == n_slots) ? 0u : s + 1u)
           {
-            const uint32_t s = (warp + i) % n_slots; // (warps start at different slots: fewer collisions on one counter)
             volatile MultiSlot& S = cs.slot[s];
             if (S.state != SLOT_TILED || S.next >= S.total)
               continue;
@@ -2171,7 +2213,7 @@ __global__ void __launch_bounds__(32 * WARPS, 1) raster_multi_kernel(
       if (last)
       {
         __threadfence_block();
-        multi_advance_slot(cs, s, false, work, n_instances, epochs, tile_sets, clut_ops, vram_pool, clut_pool, clut_slots, inst_counter, lane);
+        multi_advance_slot(cs, s, false, work, n_instances, epochs, tile_sets, tile_cmds, clut_ops, vram_pool, clut_pool, clut_slots, inst_counter, lane);
       }
     }
     __syncthreads(); // every warp is out of the work loop: no claim, no transition in flight
@@ -2204,7 +2246,7 @@ __global__ void __launch_bounds__(32 * WARPS, 1) raster_multi_kernel(
       cs.serial_pending = 0;
     __syncthreads();
     if (warp < n_slots && cs.slot[warp].state == SLOT_SERIAL)
-      multi_advance_slot(cs, warp, false, work, n_instances, epochs, tile_sets, clut_ops, vram_pool, clut_pool, clut_slots, inst_counter, lane);
+      multi_advance_slot(cs, warp, false, work, n_instances, epochs, tile_sets, tile_cmds, clut_ops, vram_pool, clut_pool, clut_slots, inst_counter, lane);
     __syncthreads();
   }
 }
@@ -2661,6 +2703,24 @@ __global__ void __launch_bounds__(256) hash_kernel(const uint16_t* __restrict__ 
   constexpr uint32_t VEC_PER_INSTANCE = VRAM_PIXELS * 2 / 16; // 65536
   constexpr uint32_t VEC_PER_BLOCK = VEC_PER_INSTANCE / HASH_BLOCKS_PER_INSTANCE;
   uint64_t h = 0;
+#if PSX_HASH_UNROLL
+  // all of the thread's loads first (eight 16-byte loads in flight), then the mixing: the kernel is bound as much by the
+  // 21 instructions per 32-bit word as by HBM, and a load per iteration left the memory pipe waiting on the arithmetic
+  static_assert(VEC_PER_BLOCK == 8 * 256, "hash_kernel: eight vectors per thread");
+  uint4 q[8];
+#pragma unroll
+  for (uint32_t k = 0; k < 8; k++)
+    q[k] = __ldcs(v + blockIdx.x * VEC_PER_BLOCK + threadIdx.x + k * 256);
+#pragma unroll
+  for (uint32_t k = 0; k < 8; k++)
+  {
+    const uint64_t wi = static_cast<uint64_t>(blockIdx.x * VEC_PER_BLOCK + threadIdx.x + k * 256) * 4;
+    h += mix64(((wi + 0) << 32) | q[k].x);
+    h += mix64(((wi + 1) << 32) | q[k].y);
+    h += mix64(((wi + 2) << 32) | q[k].z);
+    h += mix64(((wi + 3) << 32) | q[k].w);
+  }
+#else
   for (uint32_t k = threadIdx.x; k < VEC_PER_BLOCK; k += 256)
   {
     const uint32_t vi = blockIdx.x * VEC_PER_BLOCK + k;
@@ -2671,6 +2731,7 @@ __global__ void __launch_bounds__(256) hash_kernel(const uint16_t* __restrict__ 
     h += mix64(((wi + 2) << 32) | q.z);
     h += mix64(((wi + 3) << 32) | q.w);
   }
+#endif
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1)
     h += __shfl_xor_sync(0xFFFFFFFFu, h, o);
@@ -2981,18 +3042,20 @@ cudaError_t launch_instances(const InstWork* work, uint32_t n_instances, const E
     const int n = v ? std::atoi(v) : 3;
     return static_cast<uint32_t>(n < 0 ? 0 : (n > static_cast<int>(MULTI_SLOTS_MAX) ? static_cast<int>(MULTI_SLOTS_MAX) : n));
   }();
-  if (n_slots != 0 && variant == 0 && !dag && inst_counter != nullptr)
+  static const int n_sms = []() {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;
+    return n;
+  }();
+  // few instances: fewer slots per CTA, so that every SM gets one; with one instance per SM the barrier per epoch of
+  // raster_instance_kernel is cheaper than the claim protocol (18.5 against 21.7 ms at one slot)
+  uint32_t slots = n_slots;
+  while (slots > 1 && static_cast<uint64_t>(n_sms) * (slots - 1) >= n_instances)
+    slots--;
+  static const bool force_slots = std::getenv("PSXGPU_SLOTS") != nullptr;
+  if (n_slots != 0 && (slots > 1 || force_slots) && variant == 0 && !dag && inst_counter != nullptr)
   {
-    static const int n_sms = []() {
-      int dev = 0, n = 0;
-      if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
-        n = 148;
-      return n;
-    }();
-    // few instances: fewer slots per CTA, so that every SM gets one
-    uint32_t slots = n_slots;
-    while (slots > 1 && static_cast<uint64_t>(n_sms) * (slots - 1) >= n_instances)
-      slots--;
     const uint32_t ctas = std::min<uint32_t>(static_cast<uint32_t>(n_sms), (n_instances + slots - 1) / slots);
     const size_t smem_multi = sizeof(RasterShared<TILE_H>) * 32 + sizeof(MultiShared);
     if ((e = cudaFuncSetAttribute(raster_multi_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_multi))) != cudaSuccess)
