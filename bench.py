@@ -530,9 +530,10 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             roofline = {"bound": "hbm", "kernel": "raster_loop_kernel (draw wave)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                         "frac": achieved / peak, "traffic": rec.get("raster_kernel_dram_bytes_per_launch"), "peak_source": peak_src,
                         "limiter": rec.get("limiter"), "issue_slot_frac": rec.get("issue_slot_frac"),
-                        "alu_pipe_frac": rec.get("alu_pipe_frac"), "warp_instructions_per_pixel": rec.get("warp_instructions_per_pixel"),
-                        "applies": "instruction issue (integer ALU pipe), not HBM: the HBM fraction is reported because the contract "
-                                   "asks for it, the issue-slot fraction says how close the kernel is to its own bound",
+                        "alu_pipe_frac": rec.get("alu_pipe_frac"), "lsu_pipe_frac": rec.get("lsu_pipe_frac"), "warp_instructions_per_pixel": rec.get("warp_instructions_per_pixel"),
+                        "applies": "instruction issue and the load/store data pipe (texel gathers, shared-memory traffic), not HBM: the "
+                                   "HBM fraction is reported because the contract asks for it, the issue-slot and pipe fractions "
+                                   "say how close the kernel is to its own bounds",
                         "algorithmic_bytes_per_launch": algo, "launch_ms": avg[dom], "raster_launch_ms": avg,
                         "whole_step_algorithmic_frac": (bm["total"] / (ms_step * 1e-3) / 1e9) / peak,
                         "compulsory_hbm_frac": ((2 * (1 << 20) * n_inst + main["staged_stats"]["h2d_bytes"]) / (ms_step * 1e-3) / 1e9) / peak}

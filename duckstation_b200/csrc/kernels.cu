@@ -213,8 +213,8 @@ constexpr uint32_t SETUP_VECS = sizeof(PrimSetup) / 16; // 16
 #ifndef PSX_OPT_CLUTASYNC
 #define PSX_OPT_CLUTASYNC 1
 #endif
-#ifndef PSX_HASH_UNROLL
-#define PSX_HASH_UNROLL 0
+#ifndef PSX_SLOT_COH
+#define PSX_SLOT_COH 2 // (measured, 2048 instances of the hazard variant: 16.37 -> 16.08 ms) slot mode: 1 = VRAM / CLUT reads from L2 (ld.global.cg), 2 = through L1 (the instance belongs to one SM)
 #endif
 #ifndef PSX_REGION_PITCH
 #define PSX_REGION_PITCH 36
@@ -342,20 +342,22 @@ __device__ __forceinline__ ShadeState shade_state_from_words(const uint32_t* w)
 }
 
 // kCoh: the kernel outlives an epoch (persistent kernel), so VRAM / CLUT-slot reads must not come from a stale L1 line.
-template<bool kCoh, typename T>
+// kCoh == 2: every access to this VRAM / these CLUT slots while the kernel runs comes from ONE SM (slot mode): an
+// ordinary cached load is coherent with that SM's own stores (write-through L1), and repeated texels hit L1.
+template<int kCoh, typename T>
 __device__ __forceinline__ T ld_ro(const T* p)
 {
-  return kCoh ? __ldcg(p) : __ldg(p);
+  return kCoh == 2 ? *p : (kCoh ? __ldcg(p) : __ldg(p));
 }
 
 // One pixel through the pipeline.  bg = current value; returns the new value.
-template<bool kCoh>
+template<int kCoh>
 __device__ __forceinline__ uint32_t shade_pixel(const ShadeState& st, const PixelCtx& ctx, uint32_t px, uint32_t Y, uint32_t r,
                                                 uint32_t g, uint32_t b, uint32_t u, uint32_t v, uint32_t bg)
 {
   uint32_t texel = 0;
   if (st.flags & F_TEXTURE)
-    texel = fetch_texel<kCoh, true>(st, ctx.vram, ctx.clut, ctx.clut, u, v);
+    texel = fetch_texel<kCoh != 0, true>(st, ctx.vram, ctx.clut, ctx.clut, u, v);
   uint32_t colour;
   if (!shade_colour(st, px, Y, r, g, b, texel, colour))
     return bg;
@@ -422,7 +424,7 @@ __device__ __forceinline__ uint32_t row_lane_map(uint32_t rows, uint32_t lane)
 // Everything that depends only on the primitive (texture mode, raw / modulated, flat / Gouraud, transparency) is a
 // warp-uniform branch around a short block, and the constants those blocks use come ready-made from the staged record
 // (LoopDesc, written by setup_kernel): the loop keeps few registers live, so nothing is rematerialised per word.
-template<uint32_t RH, bool kCoh>
+template<uint32_t RH, int kCoh>
 __device__ __forceinline__ void raster_spans(const PrimSetup& s, const uint16_t* vram, RasterShared<RH>& sh,
                                              uint32_t rx0, uint32_t ry0, uint32_t lane, bool clut_pending)
 {
@@ -695,7 +697,7 @@ PSX_CHECK(r < RH && w < TILE_W / 2);
 
 // A warp applies one primitive to its region (rows ry0 .. ry0+RH-1, columns rx0 .. rx0+63), held in shared memory.
 // clut_key: which palette (lo slot | hi slot << 8 | depth << 16) currently sits in clut_smem; reloaded on change.
-template<uint32_t RH, bool kCoh>
+template<uint32_t RH, int kCoh>
 __device__ __forceinline__ void raster_prim_on_region(const PrimSetup& s, RasterShared<RH>& sh, uint32_t rx0, uint32_t ry0,
                                                       const uint16_t* vram, const uint16_t* clut_pool_inst,
                                                       const uint16_t* __restrict__ payload, uint32_t& clut_key,
@@ -1326,7 +1328,7 @@ struct PreBin
 
 // One warp runs one epoch of one instance on its region: bins the epoch's primitives (submission order), stages the
 // region in shared memory on the first hit, rasterises, writes it back.
-template<uint32_t RH, bool kCoh>
+template<uint32_t RH, int kCoh>
 __device__ __forceinline__ void process_epoch_region(const WaveItem& it, RasterShared<RH>& sh, uint32_t tx, uint32_t ty, uint32_t ry0,
                                                      const PrimSetup* __restrict__ setups, const uint32_t* __restrict__ tile_cmds,
                                                      uint16_t* vram, const uint16_t* cluts, const uint16_t* __restrict__ payload,
@@ -2196,7 +2198,7 @@ __global__ void __launch_bounds__(32 * WARPS, 1) raster_multi_kernel(
       const uint32_t tx = tile % TILES_X, ty = tile / TILES_X;
       uint16_t* vram = vram_pool + static_cast<size_t>(it.instance) * VRAM_PIXELS;
       const uint16_t* cluts = clut_pool + static_cast<size_t>(it.instance) * clut_slots * CLUT_ENTRIES;
-      process_epoch_region<TILE_H, true>(it, sh_all[warp], tx, ty, ty * TILE_H, setups, tile_cmds, vram, cluts, payload, lane);
+      process_epoch_region<TILE_H, PSX_SLOT_COH>(it, sh_all[warp], tx, ty, ty * TILE_H, setups, tile_cmds, vram, cluts, payload, lane);
       __syncwarp();
       __threadfence_block(); // the tile's write-back, before it counts as done
       uint32_t last = 0;
@@ -2703,24 +2705,6 @@ __global__ void __launch_bounds__(256) hash_kernel(const uint16_t* __restrict__ 
   constexpr uint32_t VEC_PER_INSTANCE = VRAM_PIXELS * 2 / 16; // 65536
   constexpr uint32_t VEC_PER_BLOCK = VEC_PER_INSTANCE / HASH_BLOCKS_PER_INSTANCE;
   uint64_t h = 0;
-#if PSX_HASH_UNROLL
-  // all of the thread's loads first (eight 16-byte loads in flight), then the mixing: the kernel is bound as much by the
-  // 21 instructions per 32-bit word as by HBM, and a load per iteration left the memory pipe waiting on the arithmetic
-  static_assert(VEC_PER_BLOCK == 8 * 256, "hash_kernel: eight vectors per thread");
-  uint4 q[8];
-#pragma unroll
-  for (uint32_t k = 0; k < 8; k++)
-    q[k] = __ldcs(v + blockIdx.x * VEC_PER_BLOCK + threadIdx.x + k * 256);
-#pragma unroll
-  for (uint32_t k = 0; k < 8; k++)
-  {
-    const uint64_t wi = static_cast<uint64_t>(blockIdx.x * VEC_PER_BLOCK + threadIdx.x + k * 256) * 4;
-    h += mix64(((wi + 0) << 32) | q[k].x);
-    h += mix64(((wi + 1) << 32) | q[k].y);
-    h += mix64(((wi + 2) << 32) | q[k].z);
-    h += mix64(((wi + 3) << 32) | q[k].w);
-  }
-#else
   for (uint32_t k = threadIdx.x; k < VEC_PER_BLOCK; k += 256)
   {
     const uint32_t vi = blockIdx.x * VEC_PER_BLOCK + k;
@@ -2731,7 +2715,6 @@ __global__ void __launch_bounds__(256) hash_kernel(const uint16_t* __restrict__ 
     h += mix64(((wi + 2) << 32) | q.z);
     h += mix64(((wi + 3) << 32) | q.w);
   }
-#endif
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1)
     h += __shfl_xor_sync(0xFFFFFFFFu, h, o);
