@@ -693,7 +693,11 @@ __device__ __forceinline__ bool vertex_ok(int32_t x, int32_t y)
   return x >= -32768 && x <= 32767 && y >= -32768 && y <= 32767;
 }
 
+#ifdef PSX_ENC_MAXREG
+__global__ void __maxnreg__(PSX_ENC_MAXREG) encode_kernel(EncodeArgs A)
+#else
 __global__ void __launch_bounds__(32 * ENC_WARPS) encode_kernel(EncodeArgs A)
+#endif
 {
   __shared__ uint32_t sh_key[ENC_WARPS][256];
   __shared__ uint32_t sh_last[ENC_WARPS][256];

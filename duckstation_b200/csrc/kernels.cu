@@ -114,10 +114,10 @@ __global__ void __launch_bounds__(128) setup_kernel(const PackedCmd* __restrict_
       const bool rows_plain = imin(T.lo[0], T.lo[1]) >= 0 && imax(T.hi[0], T.hi[1]) <= static_cast<int32_t>(VRAM_H);
       if ((cols & (cols - 1u)) != 0 && (rows & (rows - 1u)) != 0 && rows_plain)
       {
-        for (uint32_t ty = static_cast<uint32_t>(__ffs(static_cast<int>(rows))) - 1u; ty < TILES_Y && n_reject < 4u; ty++)
+        // (the set bits only: a bounding box spans two or three tile rows and columns, not sixteen)
+        for (uint32_t rbits = rows; rbits != 0 && n_reject < 4u; rbits &= rbits - 1u)
         {
-          if (!((rows >> ty) & 1u))
-            continue;
+          const uint32_t ty = static_cast<uint32_t>(__ffs(static_cast<int>(rbits))) - 1u;
           int32_t h_lo = 0x7FFFFFFF, h_hi = static_cast<int32_t>(0x80000000u);
 #pragma unroll
           for (int p = 0; p < 2; p++)
@@ -136,10 +136,9 @@ __global__ void __launch_bounds__(128) setup_kernel(const PackedCmd* __restrict_
           }
           h_lo = imax(h_lo, s.clip_l);
           h_hi = imin(h_hi, s.clip_r + 1);
-          for (uint32_t tx = 0; tx < TILES_X && n_reject < 4u; tx++)
+          for (uint32_t cbits = cols; cbits != 0 && n_reject < 4u; cbits &= cbits - 1u)
           {
-            if (!((cols >> tx) & 1u))
-              continue;
+            const uint32_t tx = static_cast<uint32_t>(__ffs(static_cast<int>(cbits))) - 1u;
             if (h_hi <= h_lo || h_hi <= static_cast<int32_t>(tx * TILE_W) || h_lo >= static_cast<int32_t>(tx * TILE_W + TILE_W))
             {
               reject |= (ty * TILES_X + tx) << (8u * n_reject);
@@ -172,8 +171,13 @@ __global__ void __launch_bounds__(128) setup_kernel(const PackedCmd* __restrict_
   // the corner tiles found empty above: clear the command's bit (after the warp's stores, which __syncwarp orders)
   __syncwarp();
   uint32_t* const group_words = tile_cmds + static_cast<size_t>(i >> 5) * NUM_TILES;
-  for (uint32_t k = 0; k < n_reject; k++)
-    atomicAnd(group_words + ((reject >> (8u * k)) & 0xFFu), ~(1u << lane));
+  if (__any_sync(0xFFFFFFFFu, n_reject != 0))
+  {
+#pragma unroll
+    for (uint32_t k = 0; k < 4; k++) // (predicated, not a divergent loop)
+      if (k < n_reject)
+        atomicAnd(group_words + ((reject >> (8u * k)) & 0xFFu), ~(1u << lane));
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ CLUT snapshots

@@ -153,17 +153,45 @@ PSX_HD int64_t makefp_xy(int32_t x) // inl:1463
 {
   return static_cast<int64_t>((static_cast<uint64_t>(static_cast<int64_t>(x)) << 32) + ((1ull << 32) - (1u << 11)));
 }
+// The integer divisions of the set-up, through double precision (a 64-bit integer division is a ~140-instruction
+// routine on the GPU, a 32-bit one ~25, and a shaded textured triangle has ten of the latter by the same determinant).
+// Both are exact:
+//  * makestep_xy: |n| < 2^53 is exact as a double and 0 < dy < 2^31; the rounded quotient is off by less than 1, so
+//    one look at the remainder settles it.
+//  * trunc_div_rcp: trunc(n / d) from rd = 1.0 / d.  n * rd is off by at most |q| * 2^-51 and a true quotient that is
+//    not an integer lies at least 1 / |d| from the nearest one; |q| * |d| <= 2^31 makes the first smaller than the second, so
+//    truncation can only go wrong when the true quotient IS an integer and the product lands just inside it — the
+//    remainder is then +-d, which is what the fix tests.
 PSX_HD int64_t makestep_xy(int32_t dx, int32_t dy) // inl:1464-1466, truncating s64 division
 {
   const int64_t adj = (dx < 0) ? -static_cast<int64_t>(dy - 1) : ((dx > 0) ? static_cast<int64_t>(dy - 1) : 0);
-  return static_cast<int64_t>((static_cast<uint64_t>(static_cast<int64_t>(dx)) << 32) + static_cast<uint64_t>(adj)) / dy;
+  const int64_t n = static_cast<int64_t>((static_cast<uint64_t>(static_cast<int64_t>(dx)) << 32) + static_cast<uint64_t>(adj));
+  const uint64_t a = static_cast<uint64_t>(n < 0 ? -n : n);
+  if (a >= (1ull << 52) || dy <= 0)
+    return n / dy; // (never for coordinates the decoder lets through; keeps the function total)
+  uint64_t q = static_cast<uint64_t>(static_cast<double>(a) / static_cast<double>(dy));
+  const int64_t r = static_cast<int64_t>(a - q * static_cast<uint64_t>(dy));
+  if (r < 0)
+    q--;
+  else if (r >= dy)
+    q++;
+  return n < 0 ? -static_cast<int64_t>(q) : static_cast<int64_t>(q);
 }
-PSX_HD uint32_t attrib_step(int32_t a0, int32_t a1, int32_t a2, int32_t b0, int32_t b1, int32_t b2, int32_t det) // inl:1495-1496
+PSX_HD int32_t trunc_div_rcp(int32_t n, int32_t d, double rd) // trunc(n / d), rd = 1.0 / d, d != 0, (n, d) != (INT32_MIN, -1)
+{
+  int32_t q = static_cast<int32_t>(static_cast<double>(n) * rd);
+  const int32_t r = static_cast<int32_t>(static_cast<uint32_t>(n) - static_cast<uint32_t>(q) * static_cast<uint32_t>(d));
+  const int32_t ad = d < 0 ? -d : d;
+  if (r >= ad || r <= -ad)
+    q += ((r ^ d) < 0) ? -1 : 1;
+  return q;
+}
+PSX_HD uint32_t attrib_step(int32_t a0, int32_t a1, int32_t a2, int32_t b0, int32_t b1, int32_t b2, int32_t det, double rdet) // inl:1495-1496
 {
   const uint32_t num = (static_cast<uint32_t>(a1 - a0) * static_cast<uint32_t>(b2 - b1)) -
                        (static_cast<uint32_t>(a2 - a1) * static_cast<uint32_t>(b1 - b0));
   const int32_t scaled = static_cast<int32_t>(num * 4096u);
-  const int32_t q = (det == -1 && scaled == INT32_MIN) ? INT32_MIN : scaled / det;
+  const int32_t q = ((det == -1 && scaled == INT32_MIN) || det == INT32_MIN) ? ((det == -1) ? INT32_MIN : scaled / det) : trunc_div_rcp(scaled, det, rdet);
   return static_cast<uint32_t>(q) << 12;
 }
 
@@ -355,6 +383,7 @@ PSX_HD void setup_triangle(const PackedCmd& c, PrimSetup& s, BinInfo& bin)
 
   const PackedVertex tv = (tl == 0) ? v0 : ((tl == 1) ? v1 : v2);
   const bool shaded = (c.flags0 & F_SHADED) != 0, textured = (c.flags0 & F_TEXTURE) != 0;
+  const double rdet = 1.0 / static_cast<double>(det);
   const int32_t at[5][3] = {{v0.r, v1.r, v2.r}, {v0.g, v1.g, v2.g}, {v0.b, v1.b, v2.b}, {v0.u, v1.u, v2.u}, {v0.v, v1.v, v2.v}};
   const uint32_t start[5] = {tv.r, tv.g, tv.b, tv.u, tv.v};
   for (int i = 0; i < 5; i++)
@@ -363,8 +392,8 @@ PSX_HD void setup_triangle(const PackedCmd& c, PrimSetup& s, BinInfo& bin)
     uint32_t base = ((start[i] << 12) + (1u << 11)) << 12, ddx = 0, ddy = 0;
     if (on)
     {
-      ddx = attrib_step(at[i][0], at[i][1], at[i][2], v0.y, v1.y, v2.y, det);
-      ddy = attrib_step(v0.x, v1.x, v2.x, at[i][0], at[i][1], at[i][2], det);
+      ddx = attrib_step(at[i][0], at[i][1], at[i][2], v0.y, v1.y, v2.y, det, rdet);
+      ddy = attrib_step(v0.x, v1.x, v2.x, at[i][0], at[i][1], at[i][2], det, rdet);
       base += ddx * static_cast<uint32_t>(-static_cast<int32_t>(tv.x)) + ddy * static_cast<uint32_t>(-static_cast<int32_t>(tv.y));
     }
     T.base[i] = base;

@@ -12,7 +12,7 @@ os.makedirs(OUT, exist_ok=True)
 OBJ = os.path.join(OUT, "obj")
 os.makedirs(OBJ, exist_ok=True)
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC,-Wall"]
-REST = ["encode_kernel.cu", "presenter.cu", "context.cpp", "encoder.cpp", "backend.cpp", "gp0_frontend.cpp"]
+REST = ["presenter.cu", "context.cpp", "encoder.cpp", "backend.cpp", "gp0_frontend.cpp"]
 
 
 def obj(src, extra, tag):
@@ -29,15 +29,20 @@ def main():
     with ThreadPoolExecutor(max_workers=8) as ex:
         rest = [ex.submit(obj, s, [], "base") for s in REST]
         kern = {n: ex.submit(obj, "kernels.cu", f.split(), n) for n, f in variants.items()}
+        enc = {n: ex.submit(obj, "encode_kernel.cu", f.split(), n) for n, f in variants.items()}
         rest = [f.result()[0] for f in rest]
         for n, f in kern.items():
             o, log = f.result()
+            eo, elog = enc[n].result()
+            for i, ln in enumerate(elog.splitlines()):
+                if "13encode_kernelE" in ln and "Compiling" in ln:
+                    print(n, "encode_kernel:", " ".join(x.strip() for x in elog.splitlines()[i + 1:i + 4] if "registers" in x or "spill" in x))
             lines = log.splitlines()
             for i, ln in enumerate(lines):
                 if "raster_loop_kernel" in ln and "Compiling" in ln:
                     print(n, "raster_loop_kernel:", " ".join(x.strip() for x in lines[i + 1:i + 4] if "registers" in x or "spill" in x))
             so = os.path.join(OUT, f"libpsxgpu_{n}.so")
-            subprocess.check_call(["nvcc", "-shared", "-o", so, o, *rest])
+            subprocess.check_call(["nvcc", "-shared", "-o", so, o, eo, *rest])
             print("built", so)
 
 

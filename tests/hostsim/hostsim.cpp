@@ -13,6 +13,7 @@
 #include "../../duckstation_b200/csrc/psx_setup.h"
 #include "../../include/psxgpu_wire.h"
 
+#include <climits>
 #include <cstring>
 #include <vector>
 
@@ -416,6 +417,46 @@ void hostsim_stats(uint64_t* out, int n)
   for (int i = 0; i < n && i < 12; i++)
     out[i] = v[i];
 }
+}
+
+// ---- the set-up's divisions through double precision (psx_setup.h: trunc_div_rcp, makestep_xy) against integer division ----
+extern "C" long hostsim_division_check(long n)
+{
+  uint64_t s = 88172645463325252ull;
+  auto rnd = [&]() {
+    s ^= s << 13;
+    s ^= s >> 7;
+    s ^= s << 17;
+    return s;
+  };
+  long bad = 0;
+  for (long it = 0; it < n; it++)
+  {
+    int32_t a = static_cast<int32_t>(rnd()), d = static_cast<int32_t>(rnd());
+    const int mode = static_cast<int>(it & 7);
+    if (mode < 4) // determinants of 11-bit coordinate differences
+      d = static_cast<int32_t>(rnd() % (1u << (1 + rnd() % 22))) - static_cast<int32_t>(1u << (rnd() % 21));
+    if (mode == 1) // exact multiples: the case the remainder test exists for
+      a = static_cast<int32_t>(static_cast<uint32_t>(static_cast<int32_t>(rnd() % 4096) - 2048) * static_cast<uint32_t>(d));
+    if (mode == 2) // ... and the values right below the next multiple
+      a = static_cast<int32_t>(static_cast<uint32_t>(static_cast<int32_t>(rnd() % 4096) - 2048) * static_cast<uint32_t>(d) +
+                               static_cast<uint32_t>((d > 0) ? (d - 1) : (d + 1)));
+    if (d == 0 || d == INT32_MIN || (a == INT32_MIN && d == -1))
+      continue;
+    if (trunc_div_rcp(a, d, 1.0 / static_cast<double>(d)) != a / d)
+      bad++;
+    int32_t dx = static_cast<int32_t>(rnd() % 4096) - 2048, dy = 1 + static_cast<int32_t>(rnd() % 2047);
+    if (it & 1)
+    {
+      dx = static_cast<int32_t>(rnd() % 2097152) - 1048576;
+      dy = 1 + static_cast<int32_t>(rnd() % 1048575);
+    }
+    const int64_t adj = (dx < 0) ? -static_cast<int64_t>(dy - 1) : ((dx > 0) ? static_cast<int64_t>(dy - 1) : 0);
+    const int64_t num = static_cast<int64_t>((static_cast<uint64_t>(static_cast<int64_t>(dx)) << 32) + static_cast<uint64_t>(adj));
+    if (makestep_xy(dx, dy) != num / dy)
+      bad++;
+  }
+  return bad;
 }
 
 // ---- psx_pair.h (two pixels per register) against the scalar pipeline of psx_pixel.h ----

@@ -173,3 +173,12 @@ def test_encoder_state_survives_flushes_and_hand_over(case):
     for handover in (False, True):
         got = sim.render_parts(parts, handover)
         assert np.array_equal(got, want), (handover, describe_diff(got, want))
+
+
+def test_setup_divisions_through_double_precision_are_exact(sim):
+    """psx_setup.h divides through double precision on the GPU (trunc_div_rcp: ten divisions by the determinant from one
+    reciprocal; makestep_xy: the 64-bit edge steps): both must equal C integer division on every input class."""
+    import ctypes as C
+    sim.lib.hostsim_division_check.restype = C.c_long
+    sim.lib.hostsim_division_check.argtypes = [C.c_long]
+    assert sim.lib.hostsim_division_check(20_000_000) == 0
