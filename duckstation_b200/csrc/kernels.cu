@@ -3037,10 +3037,10 @@ cudaError_t launch_instances(const InstWork* work, uint32_t n_instances, const E
   }();
   // few instances: fewer slots per CTA, so that every SM gets one; with one instance per SM the barrier per epoch of
   // raster_instance_kernel is cheaper than the claim protocol (18.5 against 21.7 ms at one slot)
+  static const bool force_slots = std::getenv("PSXGPU_SLOTS") != nullptr; // (set: that many slots whatever the instance count — tests)
   uint32_t slots = n_slots;
-  while (slots > 1 && static_cast<uint64_t>(n_sms) * (slots - 1) >= n_instances)
+  while (!force_slots && slots > 1 && static_cast<uint64_t>(n_sms) * (slots - 1) >= n_instances)
     slots--;
-  static const bool force_slots = std::getenv("PSXGPU_SLOTS") != nullptr;
   if (n_slots != 0 && (slots > 1 || force_slots) && variant == 0 && !dag && inst_counter != nullptr)
   {
     const uint32_t ctas = std::min<uint32_t>(static_cast<uint32_t>(n_sms), (n_instances + slots - 1) / slots);

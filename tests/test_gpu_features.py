@@ -762,3 +762,45 @@ def test_cluster_mode_several_instances(oracle):
         assert got == want, [cases[i] for i in range(len(ss)) if got[i] != want[i]]
         st = ctx.stats()
         assert st["epochs"] > 8 * len(ss) and st["serial_copy"] > 0 and st["serial_upload"] > 0
+
+
+def test_slot_mode_mixed_batch(oracle):
+    """More instances than SMs, cut into many short epochs: the batch runs in slot mode (raster_multi_kernel — several
+    instances per CTA, each slot behind its own epoch counter).  The mix makes every path of the kernel happen: hazard
+    streams (config 6), streams full of serial epoch kinds (config 3 and the fuzz generator: aliasing copies, mask-checked
+    uploads, self-sampling primitives — the CTA-wide rendezvous), streams that start with a serial epoch, empty streams and
+    single-command streams (slots that finish at once and pull the next instance), ragged lengths (slots that run out at
+    different times).  Every instance against the oracle."""
+    from tests.test_hostsim import _area, _copy, _rect
+    cases = ([(6, 200 + i, 300 + 37 * (i % 9), 0) for i in range(120)] + [(3, 300 + i, 200 + 53 * (i % 7), 0) for i in range(120)] +
+             [(0, 400 + i, 300, 3) for i in range(40)])
+    ss = [_strip_barriers(streams.generate(*c)) for c in cases]
+    noise = _strip_barriers(streams.generate(0, 5, 0, 0))
+    ss += [b""] * 12                                                              # nothing to do
+    ss += [_area(0, 0, 1023, 511) + _rect(3 * i, 5 * i, 40, 30, 0x40A0F0) for i in range(12)]  # one epoch, one primitive
+    ss += [noise + _copy(100, 100, 104, 110, 200, 150) + _rect(7, 9, 50, 50, 0x3050F0)] * 6    # a serial epoch first
+    want = [oracle.hash64(oracle.render(s)) for s in ss]
+    assert len(ss) > 300
+    with _ctx(len(ss)) as ctx:
+        ctx.set_batch_chunk(len(ss))  # one chunk: more than two instances per SM, so the launcher picks three slots per CTA
+        ctx.submit_batch(ss)
+        ctx.flush()
+        got = [int(h) for h in ctx.hash()]
+        bad = [i for i in range(len(ss)) if got[i] != want[i]]
+        assert not bad, bad[:10]
+        st = ctx.stats()
+        assert st["epochs"] > 8 * len(ss) and st["serial_copy"] > 0 and st["serial_upload"] > 0
+        assert st["kernel_launches"] < 40  # one launch for all epochs, not one per epoch
+
+
+@pytest.mark.parametrize("slots", [1, 2, 4])
+def test_slot_mode_forced_slot_counts(slots):
+    """raster_multi_kernel with 1, 2 and 4 instance slots per CTA (PSXGPU_SLOTS, read once per process: a worker process per
+    value) on a batch of hazard-heavy streams with serial epochs; with the variable set the slot kernel runs whatever the
+    instance count, so 40 instances put 1-4 of them on each of a few CTAs.  Worker: tests/slot_worker.py."""
+    import subprocess
+    import sys
+    env = dict(os.environ, PSXGPU_SLOTS=str(slots), PSXGPU_CLUSTER_MAX="0")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "slot_worker.py"), "40"], env=env, capture_output=True, text=True,
+                       timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
