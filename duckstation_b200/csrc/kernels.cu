@@ -2058,7 +2058,10 @@ __device__ __noinline__ void multi_advance_slot(MultiShared& cs, uint32_t s, boo
         continue;
     }
     const uint32_t epoch_first = S.epoch_first, instance = S.instance;
+    PSX_CHECK(k < n_epochs && instance < g_dbg.n_instances);
     const Epoch ep = epochs[epoch_first + k];
+    PSX_CHECK(ep.cmd_begin <= ep.cmd_end && S.cmd_base + ep.cmd_end <= g_dbg.n_cmds && ep.clut_begin <= ep.clut_end &&
+              S.clut_base + ep.clut_end <= g_dbg.n_clutops);
     uint16_t* vram = vram_pool + static_cast<size_t>(instance) * VRAM_PIXELS;
     uint16_t* cluts = clut_pool + static_cast<size_t>(instance) * clut_slots * CLUT_ENTRIES;
     WaveItem it;
@@ -2197,9 +2200,12 @@ __global__ void __launch_bounds__(32 * WARPS, 1) raster_multi_kernel(
       MultiSlot& S = cs.slot[s];
       const WaveItem it = S.it;
       const uint32_t total = S.total;
+      PSX_CHECK(s < n_slots && j < total && total <= NUM_TILES && S.state == SLOT_TILED && it.kind == EPOCH_TILED);
+      PSX_CHECK(it.instance < g_dbg.n_instances && it.cmd_begin < it.cmd_end && it.cmd_end <= g_dbg.n_cmds);
       const uint32_t mine = (lane < 8) ? S.tiles[lane] : 0u, before = (lane < 8) ? S.before[lane] : 0u;
       const uint32_t tile = nth_tile(mine, before, __popc(mine), j, lane);
       const uint32_t tx = tile % TILES_X, ty = tile / TILES_X;
+      PSX_CHECK(tile < NUM_TILES && ((mine >> (tile & 31u)) & 1u || (lane != (tile >> 5))));
       uint16_t* vram = vram_pool + static_cast<size_t>(it.instance) * VRAM_PIXELS;
       const uint16_t* cluts = clut_pool + static_cast<size_t>(it.instance) * clut_slots * CLUT_ENTRIES;
       process_epoch_region<TILE_H, PSX_SLOT_COH>(it, sh_all[warp], tx, ty, ty * TILE_H, setups, tile_cmds, vram, cluts, payload, lane);
@@ -2208,7 +2214,9 @@ __global__ void __launch_bounds__(32 * WARPS, 1) raster_multi_kernel(
       uint32_t last = 0;
       if (lane == 0)
       {
-        last = (atomicAdd(&S.done, 1u) + 1u == total) ? 1u : 0u;
+        const uint32_t done_now = atomicAdd(&S.done, 1u) + 1u;
+        PSX_CHECK(done_now <= total);
+        last = (done_now == total) ? 1u : 0u;
         if (last)
         {
           S.state = SLOT_BUSY;
