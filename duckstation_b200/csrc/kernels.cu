@@ -2838,7 +2838,12 @@ cudaError_t launch_raster(const WaveItem* items, uint32_t n_items, const PrimSet
     if (e != cudaSuccess)
       return e;
     const uint32_t total = n_items * NUM_TILES;
-    const uint32_t ctas = std::min<uint32_t>(static_cast<uint32_t>(sms) * PSX_RASTER_MIN_CTAS, total / 2u + 1u);
+    static const uint32_t ctas_per_sm = []() {
+      const char* e = std::getenv("PSXGPU_LOOP_CTAS"); // experiments: persistent one-warp CTAs per SM (fewer leave room for the encoder's kernels beside a wave)
+      const int v = e ? std::atoi(e) : 0;
+      return (v >= 1 && v <= PSX_RASTER_MIN_CTAS) ? static_cast<uint32_t>(v) : static_cast<uint32_t>(PSX_RASTER_MIN_CTAS);
+    }();
+    const uint32_t ctas = std::min<uint32_t>(static_cast<uint32_t>(sms) * ctas_per_sm, total / 2u + 1u);
     const uint32_t grab = (tiled_cmds <= static_cast<uint64_t>(n_items) * LOOP_LIGHT_CMDS_PER_ITEM) ? LOOP_GRAB_LIGHT : LOOP_GRAB_HEAVY;
     raster_loop_kernel<<<ctas, 32, 0, st>>>(items, n_items, setups, tile_cmds, vram_pool, clut_pool, payload, clut_slots, loop_counter, grab);
     return cudaGetLastError();
