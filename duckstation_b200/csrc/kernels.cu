@@ -220,6 +220,9 @@ constexpr uint32_t SETUP_VECS = sizeof(PrimSetup) / 16; // 16
 #ifndef PSX_SLOT_COH
 #define PSX_SLOT_COH 2 // (measured, 2048 instances of the hazard variant: 16.37 -> 16.08 ms) slot mode: 1 = VRAM / CLUT reads from L2 (ld.global.cg), 2 = through L1 (the instance belongs to one SM)
 #endif
+#ifndef PSX_MULTI_WARPS_DEFAULT
+#define PSX_MULTI_WARPS_DEFAULT 32u // (2048 instances of the hazard variant, 3 slots: 32 warps 16.03 ms, 28 warps at 72 registers 16.39, 24 at 80 registers 17.16)
+#endif
 #ifndef PSX_REGION_PITCH
 #define PSX_REGION_PITCH 36
 #endif
@@ -1538,7 +1541,7 @@ __device__ __forceinline__ PreBin prebin_region(const WaveItem& it, RasterShared
 #define PSX_RASTER_WARPS 1 // independent tiles (warps) per CTA; no barrier between them
 #endif
 #ifndef PSX_RASTER_MIN_CTAS
-#define PSX_RASTER_MIN_CTAS 32
+#define PSX_RASTER_MIN_CTAS 28 // (28 CTAs per SM at 72 registers and the 196 KB shared-memory configuration (60 KB of L1): draw wave 1.606 -> 1.523 ms against 32 CTAs at 64 registers; 27: 1.544, 24 at 80 registers: 1.613, 30: 1.62)
 #endif
 __global__ void __launch_bounds__(32 * PSX_RASTER_WARPS, PSX_RASTER_MIN_CTAS) raster_kernel(
   const WaveItem* __restrict__ items, const PrimSetup* __restrict__ setups, const uint32_t* __restrict__ tile_cmds,
@@ -2843,6 +2846,13 @@ cudaError_t launch_raster(const WaveItem* items, uint32_t n_items, const PrimSet
       const int v = e ? std::atoi(e) : 0;
       return (v >= 1 && v <= PSX_RASTER_MIN_CTAS) ? static_cast<uint32_t>(v) : static_cast<uint32_t>(PSX_RASTER_MIN_CTAS);
     }();
+    static const bool carveout_set = []() {
+      const char* e = std::getenv("PSXGPU_LOOP_CARVEOUT"); // experiments: preferred shared-memory carve-out in percent (the rest is L1)
+      if (e && std::atoi(e) > 0)
+        cudaFuncSetAttribute(raster_loop_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, std::atoi(e));
+      return true;
+    }();
+    (void)carveout_set;
     const uint32_t ctas = std::min<uint32_t>(static_cast<uint32_t>(sms) * ctas_per_sm, total / 2u + 1u);
     const uint32_t grab = (tiled_cmds <= static_cast<uint64_t>(n_items) * LOOP_LIGHT_CMDS_PER_ITEM) ? LOOP_GRAB_LIGHT : LOOP_GRAB_HEAVY;
     raster_loop_kernel<<<ctas, 32, 0, st>>>(items, n_items, setups, tile_cmds, vram_pool, clut_pool, payload, clut_slots, loop_counter, grab);
@@ -3057,14 +3067,23 @@ cudaError_t launch_instances(const InstWork* work, uint32_t n_instances, const E
   if (n_slots != 0 && (slots > 1 || force_slots) && variant == 0 && !dag && inst_counter != nullptr)
   {
     const uint32_t ctas = std::min<uint32_t>(static_cast<uint32_t>(n_sms), (n_instances + slots - 1) / slots);
-    const size_t smem_multi = sizeof(RasterShared<TILE_H>) * 32 + sizeof(MultiShared);
-    if ((e = cudaFuncSetAttribute(raster_multi_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_multi))) != cudaSuccess)
+    // warps per CTA (PSXGPU_MULTI_WARPS): 32 at 64 registers, or 28 / 24 at 72 / 80 registers and more L1 (measured slower)
+    static const uint32_t multi_warps = []() {
+      const char* v = std::getenv("PSXGPU_MULTI_WARPS");
+      const int w = v ? std::atoi(v) : 0;
+      return (w == 24 || w == 28 || w == 32) ? static_cast<uint32_t>(w) : PSX_MULTI_WARPS_DEFAULT;
+    }();
+    using MultiKernel = void (*)(const InstWork*, uint32_t, const Epoch*, const uint32_t*, const PrimSetup*, const uint32_t*, const ClutOp*, uint16_t*,
+                                 uint16_t*, const uint16_t*, uint32_t, uint32_t, unsigned int*);
+    MultiKernel const mk = multi_warps == 32 ? raster_multi_kernel<32> : multi_warps == 24 ? raster_multi_kernel<24> : raster_multi_kernel<28>;
+    const size_t smem_multi = sizeof(RasterShared<TILE_H>) * multi_warps + sizeof(MultiShared);
+    if ((e = cudaFuncSetAttribute(mk, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_multi))) != cudaSuccess)
       return e;
     if ((e = cudaMemsetAsync(inst_counter, 0, sizeof(unsigned int), st)) != cudaSuccess)
       return e;
     epoch_tiles_kernel<<<n_instances, 128, 0, st>>>(work, epochs, tile_cmds, bins, tile_sets, 0u);
-    raster_multi_kernel<32><<<ctas, 32 * 32, smem_multi, st>>>(work, n_instances, epochs, tile_sets, setups, tile_cmds, clut_ops, vram_pool, clut_pool,
-                                                              payload, clut_slots, slots, inst_counter);
+    mk<<<ctas, 32 * multi_warps, smem_multi, st>>>(work, n_instances, epochs, tile_sets, setups, tile_cmds, clut_ops, vram_pool, clut_pool, payload,
+                                                   clut_slots, slots, inst_counter);
     return cudaGetLastError();
   }
   epoch_tiles_kernel<<<n_instances, 128, 0, st>>>(work, epochs, tile_cmds, bins, tile_sets, dag ? 1u : 0u);
