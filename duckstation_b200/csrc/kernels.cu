@@ -223,6 +223,9 @@ constexpr uint32_t SETUP_VECS = sizeof(PrimSetup) / 16; // 16
 #ifndef PSX_MULTI_WARPS_DEFAULT
 #define PSX_MULTI_WARPS_DEFAULT 32u // (2048 instances of the hazard variant, 3 slots: 32 warps 16.03 ms, 28 warps at 72 registers 16.39, 24 at 80 registers 17.16)
 #endif
+#ifndef PSX_REC_STREAM
+#define PSX_REC_STREAM 0
+#endif
 #ifndef PSX_REGION_PITCH
 #define PSX_REGION_PITCH 36
 #endif
@@ -1384,7 +1387,11 @@ __device__ __forceinline__ void process_epoch_region(const WaveItem& it, RasterS
   auto request_record = [&](uint32_t buf, uint32_t rel) {
     PSX_CHECK(buf < 2 && rel < it.cmd_end - it.cmd_begin);
     if (kRegRec)
+#if PSX_REC_STREAM
+      rec_next = __ldcs(reinterpret_cast<const uint2*>(epoch_setups + rel) + lane); // (streaming: read once per visit, leave L1 to the texels)
+#else
       rec_next = __ldg(reinterpret_cast<const uint2*>(epoch_setups + rel) + lane); // 32 lanes x 8 bytes = one record
+#endif
     else if (kBulkRec)
     {
       if (lane == 0)
