@@ -75,6 +75,10 @@ cudaError_t launch_debug_limits(const DebugLimits&, cudaStream_t)
 __global__ void __launch_bounds__(128) setup_kernel(const PackedCmd* __restrict__ cmds, PrimSetup* __restrict__ setups,
                                                     BinInfo* __restrict__ bins, uint32_t* __restrict__ tile_cmds, uint32_t n)
 {
+  constexpr uint32_t SV = sizeof(PrimSetup) / 16; // 16-byte chunks per record
+#if PSX_SETUP_COALESCE
+  __shared__ uint4 setup_stage[4][32 * SV]; // per warp: 32 records of 256 bytes
+#endif
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t lane = threadIdx.x & 31u;
   uint32_t mask = 0, reject = 0, n_reject = 0;
@@ -94,10 +98,22 @@ __global__ void __launch_bounds__(128) setup_kernel(const PackedCmd* __restrict_
       sw[k] = make_uint4(0, 0, 0, 0);
     BinInfo b;
     setup_prim(c, s, b);
+#if PSX_SETUP_COALESCE
+    // the record goes to the warp's staging area first (16-byte chunk k of lane L at L * 16 + (k ^ (L & 15)): four lanes per
+    // group of four banks, the minimum for a 128-bit store) and leaves it below as 512 contiguous bytes per instruction;
+    // written straight from here, every store instruction touched 32 different cache lines
+    {
+      uint4* const st = setup_stage[threadIdx.x >> 5];
+#pragma unroll
+      for (uint32_t k = 0; k < SV; k++)
+        st[lane * SV + (k ^ (lane & 15u))] = sw[k];
+    }
+#else
     uint4* dst = reinterpret_cast<uint4*>(setups + i);
 #pragma unroll
     for (int k = 0; k < static_cast<int>(sizeof(PrimSetup) / 16); k++)
       dst[k] = sw[k];
+#endif
     b.readmask = (s.op == OP_NOP) ? 0u : read_tilemask(c);
     bins[i] = b;
     mask = b.tilemask;
@@ -151,6 +167,21 @@ __global__ void __launch_bounds__(128) setup_kernel(const PackedCmd* __restrict_
   }
   if ((i & ~31u) >= n)
     return; // the whole warp is past the end
+#if PSX_SETUP_COALESCE
+  {
+    __syncwarp();
+    const uint4* const st = setup_stage[threadIdx.x >> 5];
+    const uint32_t wbase = i & ~31u;
+    uint4* const gdst = reinterpret_cast<uint4*>(setups + wbase);
+#pragma unroll
+    for (uint32_t t = 0; t < SV; t++)
+    {
+      const uint32_t g = t * 32u + lane, r = g / SV, c = g % SV; // record of the warp, chunk of the record
+      if (wbase + r < n)
+        gdst[g] = st[r * SV + (c ^ (r & 15u))];
+    }
+  }
+#endif
   // lane L writes tiles L, L + 32, ...: column L & 15, rows (L >> 4) + 2k
   uint32_t colv = 0;
 #pragma unroll
@@ -228,6 +259,9 @@ constexpr uint32_t SETUP_VECS = sizeof(PrimSetup) / 16; // 16
 #endif
 #ifndef PSX_GRAB_NOPEEK
 #define PSX_GRAB_NOPEEK 1
+#endif
+#ifndef PSX_SETUP_COALESCE
+#define PSX_SETUP_COALESCE 1 // (setup_kernel per 4096 instances: 1.108 -> 0.980 ms)
 #endif
 #ifndef PSX_REGION_PITCH
 #define PSX_REGION_PITCH 36
