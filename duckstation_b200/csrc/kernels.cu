@@ -7,14 +7,20 @@
 //                   one warp (= one CTA of 32 threads) per (instance, 64x32 VRAM tile): lists the epoch's
 //                   primitives for its tile in submission order from tile_cmds (one word per 32 commands), stages
 //                   the tile in shared memory and walks the list in order; no block-level barrier exists.  Per
-//                   primitive the 32 lanes compute the 32 row spans in one pass, a warp prefix sum compacts the
-//                   covered pixels and they are shaded 32 at a time (one pixel per lane), so small primitives keep
-//                   the lanes busy.  Tiles are read/written as coalesced 128-byte rows.  Texels come from global
-//                   memory through the read-only path (L2), palettes are staged in shared memory.  The loop
-//                   variant (waves of 16+ instances) is SMs x 32 persistent CTAs pulling tiles from a counter.
+//                   primitive the 32 lanes compute the 32 row spans in one pass, a warp prefix sum compacts the 32-bit
+//                   tile words the spans touch and they are shaded 32 words at a time — two pixels per lane, packed
+//                   16x2 arithmetic (psx_pair.h) — so small primitives keep the lanes busy.  Tile rows move as bulk
+//                   asynchronous copies counted in by a transaction barrier, the next primitive's record is
+//                   prefetched into registers, palettes are staged in shared memory by cp.async.  Texels come from
+//                   global memory through the read-only path.  The loop variant (waves of 16+ instances) is
+//                   SMs x 28 persistent CTAs (72 registers, 60 KB of L1 left) pulling tiles from a counter.
 //   raster_persistent_kernel
 //                   latency mode (up to 4 instances): one cooperative launch for a whole flush, grid barrier
 //                   between epochs, four warps per tile
+//   raster_instance_kernel / raster_multi_kernel / raster_cluster_kernel
+//                   streams cut into many short epochs, one launch for all of them: one CTA per instance with
+//                   __syncthreads between epochs; several instances per CTA, each behind its own epoch counter
+//                   (slot mode: the batched case); one thread-block cluster per instance (a handful of instances)
 //   serial_kernel   epochs of a serial kind (self-sampling primitive, aliasing copy, mask-checked upload tail):
 //                   one CTA each, in the reference's own order.
 //   hash_kernel     vramhash64 per instance
@@ -256,9 +262,6 @@ constexpr uint32_t SETUP_VECS = sizeof(PrimSetup) / 16; // 16
 #endif
 #ifndef PSX_MULTI_WARPS_DEFAULT
 #define PSX_MULTI_WARPS_DEFAULT 32u // (2048 instances of the hazard variant, 3 slots: 32 warps 16.03 ms, 28 warps at 72 registers 16.39, 24 at 80 registers 17.16)
-#endif
-#ifndef PSX_REC_STREAM
-#define PSX_REC_STREAM 0
 #endif
 #ifndef PSX_GRAB_NOPEEK
 #define PSX_GRAB_NOPEEK 1
@@ -1426,11 +1429,7 @@ __device__ __forceinline__ void process_epoch_region(const WaveItem& it, RasterS
   auto request_record = [&](uint32_t buf, uint32_t rel) {
     PSX_CHECK(buf < 2 && rel < it.cmd_end - it.cmd_begin);
     if (kRegRec)
-#if PSX_REC_STREAM
-      rec_next = __ldcs(reinterpret_cast<const uint2*>(epoch_setups + rel) + lane); // (streaming: read once per visit, leave L1 to the texels)
-#else
-      rec_next = __ldg(reinterpret_cast<const uint2*>(epoch_setups + rel) + lane); // 32 lanes x 8 bytes = one record
-#endif
+      rec_next = __ldg(reinterpret_cast<const uint2*>(epoch_setups + rel) + lane); // 32 lanes x 8 bytes = one record (a streaming load, ld.global.cs, measured the same)
     else if (kBulkRec)
     {
       if (lane == 0)
@@ -2072,7 +2071,6 @@ struct MultiShared
 // from the slot (next >= SLOT_CLOSED) and every tile of its previous epoch has been written back.
 __device__ __noinline__ void multi_advance_slot(MultiShared& cs, uint32_t s, bool fresh, const InstWork* __restrict__ work, uint32_t n_instances,
                                                 const Epoch* __restrict__ epochs, const uint32_t* __restrict__ tile_sets,
-                                                const uint32_t* __restrict__ tile_cmds,
                                                 const ClutOp* __restrict__ clut_ops, uint16_t* vram_pool, uint16_t* clut_pool, uint32_t clut_slots,
                                                 unsigned int* inst_counter, uint32_t lane)
 {
@@ -2206,7 +2204,7 @@ __global__ void __launch_bounds__(32 * WARPS, 1) raster_multi_kernel(
   }
   __syncthreads();
   if (warp < n_slots)
-    multi_advance_slot(cs, warp, true, work, n_instances, epochs, tile_sets, tile_cmds, clut_ops, vram_pool, clut_pool, clut_slots, inst_counter, lane);
+    multi_advance_slot(cs, warp, true, work, n_instances, epochs, tile_sets, clut_ops, vram_pool, clut_pool, clut_slots, inst_counter, lane);
   __syncthreads();
 
   const uint32_t first_slot = warp % n_slots;
@@ -2283,7 +2281,7 @@ __global__ void __launch_bounds__(32 * WARPS, 1) raster_multi_kernel(
       if (last)
       {
         __threadfence_block();
-        multi_advance_slot(cs, s, false, work, n_instances, epochs, tile_sets, tile_cmds, clut_ops, vram_pool, clut_pool, clut_slots, inst_counter, lane);
+        multi_advance_slot(cs, s, false, work, n_instances, epochs, tile_sets, clut_ops, vram_pool, clut_pool, clut_slots, inst_counter, lane);
       }
     }
     __syncthreads(); // every warp is out of the work loop: no claim, no transition in flight
@@ -2316,7 +2314,7 @@ __global__ void __launch_bounds__(32 * WARPS, 1) raster_multi_kernel(
       cs.serial_pending = 0;
     __syncthreads();
     if (warp < n_slots && cs.slot[warp].state == SLOT_SERIAL)
-      multi_advance_slot(cs, warp, false, work, n_instances, epochs, tile_sets, tile_cmds, clut_ops, vram_pool, clut_pool, clut_slots, inst_counter, lane);
+      multi_advance_slot(cs, warp, false, work, n_instances, epochs, tile_sets, clut_ops, vram_pool, clut_pool, clut_slots, inst_counter, lane);
     __syncthreads();
   }
 }
