@@ -260,9 +260,6 @@ constexpr uint32_t SETUP_VECS = sizeof(PrimSetup) / 16; // 16
 #ifndef PSX_SLOT_COH
 #define PSX_SLOT_COH 2 // (measured, 2048 instances of the hazard variant: 16.37 -> 16.08 ms) slot mode: 1 = VRAM / CLUT reads from L2 (ld.global.cg), 2 = through L1 (the instance belongs to one SM)
 #endif
-#ifndef PSX_MULTI_WARPS_DEFAULT
-#define PSX_MULTI_WARPS_DEFAULT 32u // (2048 instances of the hazard variant, 3 slots: 32 warps 16.03 ms, 28 warps at 72 registers 16.39, 24 at 80 registers 17.16)
-#endif
 #ifndef PSX_GRAB_NOPEEK
 #define PSX_GRAB_NOPEEK 1
 #endif
@@ -3061,8 +3058,7 @@ cudaError_t launch_instances(const InstWork* work, uint32_t n_instances, const E
   }
   // warps per CTA x CTAs per SM: 32 x 1 — one instance has an SM to itself, all of its epoch's tiles in flight at once and
   // its 1 MiB of VRAM the only one that SM pulls through L2.  Measured on 2048 instances of the hazard variant of the
-  // batched workload: 8 x 4 23.5 ms, 16 x 2 20.1 ms, 32 x 1 18.6 ms (4 x 8: worse still); PSXGPU_INST_VARIANT = 84 / 83 /
-  // 48 / 46 / 162 selects the other shapes for experiments.
+  // batched workload: 8 x 4 23.5 ms, 16 x 2 20.1 ms, 32 x 1 18.6 ms (4 x 8: worse still).
   using InstKernel = void (*)(const InstWork*, const Epoch*, const uint32_t*, const PrimSetup*, const uint32_t*, const ClutOp*, uint16_t*,
                               uint16_t*, const uint16_t*, uint32_t, uint32_t);
   static const uint32_t run_max = []() {
@@ -3070,38 +3066,9 @@ cudaError_t launch_instances(const InstWork* work, uint32_t n_instances, const E
     const int n = v ? std::atoi(v) : 1;
     return static_cast<uint32_t>(n < 1 ? 1 : (n > static_cast<int>(INST_RUN_MAX) ? static_cast<int>(INST_RUN_MAX) : n));
   }();
-  static const int variant = []() {
-    const char* v = std::getenv("PSXGPU_INST_VARIANT");
-    return v ? std::atoi(v) : 0;
-  }();
-  (void)wide;
+  constexpr int variant = 0; // (the other shapes are no longer built)
   InstKernel kernel = raster_instance_kernel<32, 1>;
-  uint32_t W = 32;
-  if (variant == 84)
-  {
-    kernel = raster_instance_kernel<8, 4>;
-    W = 8;
-  }
-  else if (variant == 83)
-  {
-    kernel = raster_instance_kernel<8, 3>;
-    W = 8;
-  }
-  else if (variant == 48)
-  {
-    kernel = raster_instance_kernel<4, 8>;
-    W = 4;
-  }
-  else if (variant == 46)
-  {
-    kernel = raster_instance_kernel<4, 6>;
-    W = 4;
-  }
-  else if (variant == 162)
-  {
-    kernel = raster_instance_kernel<16, 2>;
-    W = 16;
-  }
+  const uint32_t W = 32;
   const bool dag = run_max > 1 && W == 32;
   if (dag)
     kernel = raster_instance_dag_kernel<32, 1>;
@@ -3126,15 +3093,9 @@ cudaError_t launch_instances(const InstWork* work, uint32_t n_instances, const E
   if (n_slots != 0 && (slots > 1 || force_slots) && variant == 0 && !dag && inst_counter != nullptr)
   {
     const uint32_t ctas = std::min<uint32_t>(static_cast<uint32_t>(n_sms), (n_instances + slots - 1) / slots);
-    // warps per CTA (PSXGPU_MULTI_WARPS): 32 at 64 registers, or 28 / 24 at 72 / 80 registers and more L1 (measured slower)
-    static const uint32_t multi_warps = []() {
-      const char* v = std::getenv("PSXGPU_MULTI_WARPS");
-      const int w = v ? std::atoi(v) : 0;
-      return (w == 24 || w == 28 || w == 32) ? static_cast<uint32_t>(w) : PSX_MULTI_WARPS_DEFAULT;
-    }();
-    using MultiKernel = void (*)(const InstWork*, uint32_t, const Epoch*, const uint32_t*, const PrimSetup*, const uint32_t*, const ClutOp*, uint16_t*,
-                                 uint16_t*, const uint16_t*, uint32_t, uint32_t, unsigned int*);
-    MultiKernel const mk = multi_warps == 32 ? raster_multi_kernel<32> : multi_warps == 24 ? raster_multi_kernel<24> : raster_multi_kernel<28>;
+    // (28 / 24 warps per CTA at 72 / 80 registers and more L1 were measured slower: 16.39 / 17.16 against 16.03 ms)
+    constexpr uint32_t multi_warps = 32;
+    auto const mk = raster_multi_kernel<32>;
     const size_t smem_multi = sizeof(RasterShared<TILE_H>) * multi_warps + sizeof(MultiShared);
     if ((e = cudaFuncSetAttribute(mk, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_multi))) != cudaSuccess)
       return e;
